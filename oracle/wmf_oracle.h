@@ -1,0 +1,149 @@
+/*
+ * wmf_oracle.h -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A literal, sequential C restatement of the reference's Fortran for the two
+ * hot paths (nicolas998/WMF: wmf/cuencas.f90 module `cu`, wmf/modelosv2.f90
+ * module `models`).  Same loop order, float / int32_t arithmetic, powf from
+ * libm, left-associated sums.  Build: -O2 -fno-fast-math -ffp-contract=off.
+ *
+ * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for
+ * either path and no Fortran compiler exists in the build image, so the real
+ * reference cannot be run.  This oracle is pinned only by the hand-derived
+ * KAT-1 (tests/golden/kat1.json), structural invariants and closed-form
+ * single-cell cases (tests/test_oracle_*.py).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library.
+ *
+ * Array layout follows f2py / Fortran column-major: X(k,N) is stored
+ * k-fastest, i.e. element (k,i) (1-based) lives at [(i-1)*K + (k-1)].
+ * Rasters M(nc,nr): element (col,row) (1-based) at [(row-1)*nc + (col-1)].
+ */
+#ifndef WMF_ORACLE_H
+#define WMF_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* module cu globals, cuencas.f90:49-54 */
+typedef struct {
+    int32_t ncols, nrows;
+    float xll, yll, dx, dy, dxp, nodata;
+} wo_geo;
+
+/* results written to module scalars by basin_basics/basin_acum, cuencas.f90:60-62 */
+typedef struct {
+    float area, pend_media, elevacion, centrox, centroy;
+} wo_basin_scalars;
+
+/* ---- Path A: cuencas.f90 ------------------------------------------------ */
+void wo_coord2fil_col(const wo_geo *g, float x, float y, int32_t *col, int32_t *fil);
+/* basin_temp must hold 3*ncols*nrows int32; returns nceldas */
+int32_t wo_basin_find(const wo_geo *g, float x, float y, const int32_t *dir,
+                      int32_t nc, int32_t nr, int32_t *basin_temp);
+void wo_basin_cut(const wo_geo *g, const int32_t *basin_temp, int32_t nceldas, int32_t *basin_f);
+void wo_basin_acum(const wo_geo *g, const int32_t *basin_f, int32_t n, int32_t *acum, float *area);
+void wo_basin_acum_var(const int32_t *drain, int32_t n, const float *var, float *acum);
+void wo_basin_basics(const wo_geo *g, const int32_t *basin_f, const float *dem, const int32_t *dir,
+                     int32_t n, int32_t *acum, float *lng, float *pend, float *elev,
+                     wo_basin_scalars *sc);
+void wo_basin_coordxy(const wo_geo *g, const int32_t *basin_f, int32_t n, float *x, float *y);
+void wo_basin_map2basin(const wo_geo *g, const int32_t *basin_f, int32_t n, const float *mapa,
+                        float xllm, float yllm, int32_t ncolsm, int32_t nrowsm, float dxm, float dym,
+                        float nodatam, float *vec);
+void wo_basin_2map_find(const int32_t *basin, int32_t n, int32_t *map_ncols, int32_t *map_nrows);
+void wo_basin_2map(const wo_geo *g, const int32_t *basin, const float *var, int32_t n,
+                   int32_t map_ncols, int32_t map_nrows, float *mapa, float *map_xll, float *map_yll);
+void wo_basin_float_var2map(const wo_geo *g, const int32_t *basin_f, const float *vect, int32_t n,
+                            int32_t nc, int32_t nf, float *mapa);
+void wo_basin_stream_nod(const int32_t *basin_f, const int32_t *acum, int32_t n, int32_t umbral,
+                         int32_t *cauce, int32_t *nodos, int32_t *trazado, int32_t *n_nodos,
+                         int32_t *n_cauce);
+void wo_basin_stream_type(const int32_t *acum, int32_t n, const int32_t *umbrales, int32_t numbrales,
+                          int32_t *stream_types);
+void wo_geo_acum_to_cauce(const int32_t *acum, int32_t ncells, int32_t umbral, int32_t *cauce);
+void wo_geo_hand(const int32_t *basin_f, const float *elev, const float *lng, const int32_t *cauce,
+                 int32_t n, float *hand, float *hdnd, int32_t *a_quien);
+void wo_geo_hand_global(const wo_geo *g, const float *dem, const int32_t *dir, const int32_t *red,
+                        int32_t nc, int32_t nr, float *hand);
+void wo_basin_time_to_out(const int32_t *basin_f, const float *lng, const float *speed, int32_t n,
+                          float *time);
+void wo_basin_propagate(const int32_t *basin_f, const float *var, int32_t n, float *var_prop);
+
+/* ---- Path B: modelosv2.f90 ---------------------------------------------- */
+typedef struct {
+    /* sizes */
+    int32_t n_cel, n_reg, n_cont, n_conth;
+    /* scalar config (module globals modelosv2.f90:71-97) */
+    float dt, dxp, retorno_gr, retorno_aq, storage_constant;
+    int32_t speed_type[3];
+    int32_t calc_niter;
+    int32_t sim_sediments, sim_slides;
+    int32_t show_storage, show_speed, show_mean_speed, show_mean_retorno, save_retorno;
+    int32_t save_vfluxes, save_rc;
+    float calib[11];
+    /* topology + statics, all (1,N) or (K,N) column-major */
+    const int32_t *drena;      /* (N) drain ids = structure row 1 */
+    const int32_t *unit_type;  /* (N) */
+    const float *hill_long, *hill_slope, *stream_long, *stream_slope, *elem_area; /* (N) */
+    const float *v_coef, *h_coef, *h_exp;  /* (4,N) */
+    const float *max_capilar, *max_gravita, *max_aquifer; /* (N) */
+    const float *evpserie;     /* (n_reg) */
+    const float *storage;      /* (5,N) module Storage */
+    const int32_t *control, *control_h; /* (N) */
+    const float *stoin;        /* (5,N) or NULL */
+    const float *hspeedin;     /* (4,N) or NULL */
+    /* rain held in memory: records are 1-based, record r at rain + (r-1)*N;
+       posEvento(t)==1 means "no rain" (modelosv2.f90:444-445) */
+    const int32_t *rain;       /* (n_records, N) int32 mm*1000 */
+    int32_t n_records;
+    const int32_t *pos_evento; /* (n_reg) */
+    /* sediments (modelosv2.f90:115-125) */
+    float sed_factor, wi[3], diametro[3];
+    const float *krus, *crus, *prus; /* (N) */
+    const float *parliac;      /* (3,N) */
+    float *vd_init;            /* (3,N) or NULL: Vd persists across runs (sed_allocate :1301-1304) */
+    /* slides (modelosv2.f90:135-150) */
+    int32_t sl_gullienogullie;
+    float sl_fs, sl_gammaw;
+    const float *sl_zs, *sl_gammas, *sl_cohesion, *sl_frictionangle, *sl_radslope; /* (N) */
+} wo_shia_in;
+
+typedef struct {
+    float *q;           /* (n_cont, n_reg) column-major: [ (t)*n_cont + c ] */
+    float *qsed;        /* (n_cont, 3, n_reg) */
+    float *hum, *st1, *st3; /* (n_conth, n_reg) */
+    float *balance;     /* (n_reg) literal fp32 sequential sums */
+    double *balance64;  /* (n_reg) same terms accumulated in double (diagnostic, may be NULL) */
+    float *speed, *areacontrol; /* (n_cont, n_reg) */
+    float *stoout;      /* (5,N) */
+    float *hspeed_out;  /* (4,N) final horizontal speeds (Speed_map analogue) */
+    float *mean_rain;   /* (n_reg) */
+    float *acum_rain;   /* (N) */
+    float *mean_storage;/* (5,n_reg) or NULL */
+    float *mean_speed;  /* (4,n_reg) or NULL */
+    float *mean_retorno;/* (n_reg) or NULL */
+    float *retorned;    /* (N) or NULL */
+    float *mean_vfluxes;/* (4,n_reg) or NULL */
+    float *rc_coef;     /* (2,N) or NULL */
+    /* sediments */
+    float *vs, *vd, *vsc, *vdc; /* (3,N) */
+    float *volero, *voldepo;    /* (N) */
+    float *erot, *dept;         /* (3) */
+    /* slides */
+    float *sl_zmin, *sl_zcrit, *sl_zmax, *sl_bo, *sl_riskvector, *sl_slideocurrence; /* (N) */
+    int32_t *sl_slideacumulate; /* (N) */
+    int32_t *sl_slidencelltime; /* (n_reg) */
+} wo_shia_out;
+
+int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out);
+/* modelosv2.f90:1278-1293; returns area, updates *speed */
+float wo_calc_speed(float sm, float coef, float expo, float elem_long, float *speed, float dt,
+                    int32_t calc_niter);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

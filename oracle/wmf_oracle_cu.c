@@ -1,0 +1,434 @@
+/*
+ * wmf_oracle_cu.c -- CPU ORACLE (test infrastructure, NOT product code).
+ * Literal restatement of the Path-A routines of wmf/cuencas.f90 (module cu).
+ * See wmf_oracle.h for the status of this file ("parity unpinned").
+ *
+ * Fenced quirks (reference behaviour is undefined / non-terminating there):
+ *  - basin_find: the reference's res(2,7) scratch holds 7 children although 8
+ *    are possible (cuencas.f90:537); the oracle accepts 8.
+ *  - basin_find: the centre probe (kf=2,kc=2, DIR==5) would make a cell its own
+ *    child and never terminate (cuencas.f90:562); the oracle skips the centre.
+ *  - basin_find: termination reads basin_temp(2,celTot-cont2), index 0 when the
+ *    basin fills the whole raster (cuencas.f90:584-586); the oracle stops.
+ *  - basin_basics: pend(i-1) for an outlet at i==1 (cuencas.f90:640) -> 0.
+ *  - basin_map2basin: column/row computed with ceiling() can land one past the
+ *    map edge through fp32 rounding (cuencas.f90:1171-1174); clamped.
+ *  - geo_hand: a non-channel outlet indexes N+1 (cuencas.f90:2156) -> 0,0,0.
+ */
+#include "wmf_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define BF(k, i) basin_f[3 * (size_t)(i) + (k)] /* k = 0 drain, 1 col, 2 row; i 0-based */
+
+/* cuencas.f90:77-90 */
+void wo_coord2fil_col(const wo_geo *g, float x, float y, int32_t *col, int32_t *fil)
+{
+    int32_t c = (int32_t)ceilf((x - g->xll) / g->dx);
+    if (c < 0) c = -c;
+    int32_t f = g->nrows - (int32_t)floorf((y - g->yll) / g->dx);
+    if (c > g->ncols || c <= 0) c = -999;
+    if (f > g->nrows || f <= 0) f = -999;
+    *col = c;
+    *fil = f;
+}
+
+/* cuencas.f90:525-591 */
+int32_t wo_basin_find(const wo_geo *g, float x, float y, const int32_t *dir, int32_t nc, int32_t nr,
+                      int32_t *bt)
+{
+    const int32_t ncols = g->ncols, nrows = g->nrows;
+    const int64_t celTot = (int64_t)ncols * nrows;
+    int32_t coli, fili;
+    wo_coord2fil_col(g, x, y, &coli, &fili);
+    for (int64_t i = 0; i < 3 * celTot; ++i) bt[i] = -1;
+#define BT(k, p) bt[3 * ((p)-1) + ((k)-1)] /* 1-based (k,p) */
+    BT(1, celTot) = 0;
+    BT(2, celTot) = coli;
+    BT(3, celTot) = fili;
+    int64_t tenia = 1, cont2 = 1;
+    int32_t col2 = coli, row2 = fili;
+    int32_t res[2][8];
+    while (col2 > 0) {
+        int cont3 = 0;
+        for (int kf = 1; kf <= 3; ++kf) {
+            for (int kc = 1; kc <= 3; ++kc) {
+                if (kf == 2 && kc == 2) continue; /* fenced: DIR==5 self loop */
+                int32_t c = col2 + kc - 2, f = row2 + kf - 2;
+                if (c <= ncols && c > 0 && f <= nrows && f > 0) {
+                    if (dir[(size_t)(f - 1) * nc + (c - 1)] == 3 * kf - kc + 1) {
+                        res[0][cont3] = c;
+                        res[1][cont3] = f;
+                        ++cont3;
+                    }
+                }
+            }
+        }
+        for (int i = 1; i <= cont3; ++i) {
+            int64_t p = celTot - tenia + 1 - i;
+            if (p < 1) return -1; /* cyclic DIR: queue overflow */
+            BT(1, p) = (int32_t)cont2;
+            BT(2, p) = res[0][i - 1];
+            BT(3, p) = res[1][i - 1];
+        }
+        tenia += cont3;
+        int64_t paso = celTot - cont2;
+        if (paso < 1) break; /* fenced: basin fills the raster */
+        col2 = BT(2, paso);
+        row2 = BT(3, paso);
+        ++cont2;
+    }
+#undef BT
+    (void)nr;
+    return (int32_t)tenia;
+}
+
+/* cuencas.f90:592-607 */
+void wo_basin_cut(const wo_geo *g, const int32_t *bt, int32_t n, int32_t *basin_f)
+{
+    const int64_t celTot = (int64_t)g->ncols * g->nrows;
+    memcpy(basin_f, bt + 3 * (celTot - n), sizeof(int32_t) * 3 * (size_t)n);
+}
+
+/* cuencas.f90:659-680 */
+void wo_basin_acum(const wo_geo *g, const int32_t *basin_f, int32_t n, int32_t *acum, float *area)
+{
+    for (int32_t i = 0; i < n; ++i) acum[i] = 1;
+    for (int32_t i = 0; i < n; ++i) {
+        int32_t d = BF(0, i);
+        if (d != 0) {
+            int32_t drenaid = n - d; /* 0-based */
+            acum[drenaid] = acum[drenaid] + acum[i];
+        }
+    }
+    if (area) *area = (float)n * (g->dxp * g->dxp) / 1e6f;
+}
+
+/* cuencas.f90:681-701 ; drain is the first row only */
+void wo_basin_acum_var(const int32_t *drain, int32_t n, const float *var, float *acum)
+{
+    for (int32_t i = 0; i < n; ++i) acum[i] = var[i];
+    for (int32_t i = 0; i < n; ++i) {
+        if (drain[i] != 0) {
+            int32_t drenaid = n - drain[i];
+            acum[drenaid] = acum[drenaid] + acum[i];
+        }
+    }
+}
+
+/* cuencas.f90:797-808 */
+void wo_basin_coordxy(const wo_geo *g, const int32_t *basin_f, int32_t n, float *x, float *y)
+{
+    for (int32_t i = 0; i < n; ++i) {
+        x[i] = g->xll + g->dx * ((float)BF(1, i) - 0.5f);
+        y[i] = g->yll + g->dx * ((float)(g->nrows - BF(2, i)) + 0.5f);
+    }
+}
+
+static int cmp_float(const void *a, const void *b)
+{
+    float fa = *(const float *)a, fb = *(const float *)b;
+    return (fa > fb) - (fa < fb);
+}
+
+/* cuencas.f90:608-658 */
+void wo_basin_basics(const wo_geo *g, const int32_t *basin_f, const float *dem, const int32_t *dir,
+                     int32_t n, int32_t *acum, float *lng, float *pend, float *elev,
+                     wo_basin_scalars *sc)
+{
+    const float dxp = g->dxp;
+    for (int32_t i = 0; i < n; ++i) {
+        elev[i] = dem[i];
+        acum[i] = 1;
+    }
+    for (int32_t i = 0; i < n; ++i) {
+        int32_t d = BF(0, i);
+        int32_t drenaid = n - d;
+        float prueba = (float)(dir[i] % 2);
+        if (prueba == 0.0f)
+            lng[i] = dxp;
+        else
+            lng[i] = dxp * sqrtf(2.0f);
+        if (d != 0) {
+            acum[drenaid] = acum[drenaid] + acum[i];
+            pend[i] = fabsf(dem[i] - dem[drenaid]) / lng[i];
+        } else {
+            pend[i] = (i > 0) ? pend[i - 1] : 0.0f; /* fenced for N==1 */
+        }
+        if (pend[i] == 0.0f) pend[i] = 0.001f;
+    }
+    if (!sc) return;
+    sc->area = (float)n * (dxp * dxp) / 1e6f;
+    float s = 0.0f;
+    for (int32_t i = 0; i < n; ++i) s += pend[i];
+    sc->pend_media = s / (float)n;
+    s = 0.0f;
+    for (int32_t i = 0; i < n; ++i) s += dem[i];
+    sc->elevacion = s / (float)n;
+    float *X = (float *)malloc(sizeof(float) * (size_t)n), *Y = (float *)malloc(sizeof(float) * (size_t)n);
+    wo_basin_coordxy(g, basin_f, n, X, Y);
+    qsort(X, (size_t)n, sizeof(float), cmp_float);
+    qsort(Y, (size_t)n, sizeof(float), cmp_float);
+    int32_t k = (n % 2 == 0) ? n / 2 : (n + 1) / 2; /* 1-based */
+    sc->centrox = X[k - 1];
+    sc->centroy = Y[k - 1];
+    free(X);
+    free(Y);
+}
+
+/* cuencas.f90:1144-1184 */
+void wo_basin_map2basin(const wo_geo *g, const int32_t *basin_f, int32_t n, const float *mapa,
+                        float xllm, float yllm, int32_t ncolsm, int32_t nrowsm, float dxm, float dym,
+                        float nodatam, float *vec)
+{
+    int64_t cantidad = 0;
+    float media = 0.0f;
+    const int64_t tot = (int64_t)ncolsm * nrowsm;
+    for (int64_t k = 0; k < tot; ++k)
+        if (mapa[k] != nodatam) {
+            ++cantidad;
+            media += mapa[k];
+        }
+    media = media / (float)(int32_t)cantidad;
+    for (int32_t i = 0; i < n; ++i) {
+        vec[i] = nodatam;
+        float xpos = g->xll + g->dx * ((float)BF(1, i) - 0.5f);
+        float ypos = g->yll + g->dy * ((float)(g->nrows - BF(2, i)) + 0.5f);
+        if (xpos > xllm && xpos < (xllm + dxm * (float)ncolsm) && ypos > yllm &&
+            ypos < (yllm + (float)nrowsm * dym)) {
+            int32_t columna = (int32_t)ceilf((xpos - xllm) / dxm);
+            int32_t fila = (int32_t)ceilf((ypos - yllm) / dym);
+            fila = nrowsm - fila + 1;
+            if (columna < 1) columna = 1; /* fenced */
+            if (columna > ncolsm) columna = ncolsm;
+            if (fila < 1) fila = 1;
+            if (fila > nrowsm) fila = nrowsm;
+            vec[i] = mapa[(size_t)(fila - 1) * ncolsm + (columna - 1)];
+            if (vec[i] == nodatam) vec[i] = media;
+        }
+    }
+}
+
+/* cuencas.f90:1185-1201 */
+void wo_basin_2map_find(const int32_t *basin_f, int32_t n, int32_t *map_ncols, int32_t *map_nrows)
+{
+    int32_t cmin = BF(1, 0), cmax = BF(1, 0), fmin = BF(2, 0), fmax = BF(2, 0);
+    for (int32_t i = 1; i < n; ++i) {
+        if (BF(1, i) < cmin) cmin = BF(1, i);
+        if (BF(1, i) > cmax) cmax = BF(1, i);
+        if (BF(2, i) < fmin) fmin = BF(2, i);
+        if (BF(2, i) > fmax) fmax = BF(2, i);
+    }
+    *map_ncols = cmax - cmin + 1;
+    *map_nrows = fmax - fmin + 1;
+}
+
+/* cuencas.f90:1202-1229 */
+void wo_basin_2map(const wo_geo *g, const int32_t *basin_f, const float *var, int32_t n,
+                   int32_t map_ncols, int32_t map_nrows, float *mapa, float *map_xll, float *map_yll)
+{
+    int32_t cmin = BF(1, 0), fmin = BF(2, 0), fmax = BF(2, 0);
+    for (int32_t i = 1; i < n; ++i) {
+        if (BF(1, i) < cmin) cmin = BF(1, i);
+        if (BF(2, i) < fmin) fmin = BF(2, i);
+        if (BF(2, i) > fmax) fmax = BF(2, i);
+    }
+    *map_xll = g->xll + g->dx * (float)(cmin - 1);
+    *map_yll = g->yll + g->dx * (float)(g->nrows - fmax);
+    for (int64_t k = 0; k < (int64_t)map_ncols * map_nrows; ++k) mapa[k] = g->nodata;
+    for (int32_t i = 0; i < n; ++i) {
+        int32_t col_rel = BF(1, i) - cmin + 1, fil_rel = BF(2, i) - fmin + 1;
+        mapa[(size_t)(fil_rel - 1) * map_ncols + (col_rel - 1)] = var[i];
+    }
+}
+
+/* cuencas.f90:1037-1051 */
+void wo_basin_float_var2map(const wo_geo *g, const int32_t *basin_f, const float *vect, int32_t n,
+                            int32_t nc, int32_t nf, float *mapa)
+{
+    for (int64_t k = 0; k < (int64_t)nc * nf; ++k) mapa[k] = g->nodata;
+    for (int32_t i = 0; i < n; ++i) mapa[(size_t)(BF(2, i) - 1) * nc + (BF(1, i) - 1)] = vect[i];
+}
+
+/* cuencas.f90:1340-1379 */
+void wo_basin_stream_nod(const int32_t *basin_f, const int32_t *acum, int32_t n, int32_t umbral,
+                         int32_t *cauce, int32_t *nodos, int32_t *trazado, int32_t *n_nodos,
+                         int32_t *n_cauce)
+{
+    int32_t nca = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        cauce[i] = (acum[i] >= umbral) ? 1 : 0;
+        nca += cauce[i];
+        nodos[i] = 0;
+    }
+    *n_cauce = nca;
+    for (int32_t i = 0; i < n; ++i) {
+        int32_t d = BF(0, i);
+        if (d != 0 && cauce[i] == 1) nodos[n - d] += 1;
+    }
+    for (int32_t i = 0; i < n; ++i)
+        if (nodos[i] == 0 && cauce[i] == 1) nodos[i] = 3;
+    nodos[n - 1] = 2;
+    int32_t nn = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        if (nodos[i] < 2) nodos[i] = 0;
+        if (nodos[i] > 0) ++nn;
+    }
+    *n_nodos = nn;
+    for (int32_t i = 0; i < n; ++i) trazado[i] = 0;
+    trazado[n - 1] = 1;
+    for (int32_t i = 0; i < n; ++i) {
+        int32_t d = BF(0, i);
+        if (d != 0 && nodos[n - d] != 0 && cauce[i] == 1) trazado[i] = 1;
+    }
+}
+
+/* cuencas.f90:1439-1463 */
+void wo_basin_stream_type(const int32_t *acum, int32_t n, const int32_t *umbrales, int32_t numbrales,
+                          int32_t *stream_types)
+{
+    for (int32_t j = 0; j < n; ++j) stream_types[j] = 1;
+    for (int32_t i = 0; i < numbrales; ++i)
+        for (int32_t j = 0; j < n; ++j)
+            if (acum[j] > umbrales[i]) stream_types[j] = i + 2;
+}
+
+/* cuencas.f90:2120-2129 */
+void wo_geo_acum_to_cauce(const int32_t *acum, int32_t ncells, int32_t umbral, int32_t *cauce)
+{
+    for (int32_t k = 0; k < ncells; ++k) cauce[k] = (acum[k] > umbral) ? 1 : 0;
+}
+
+/* cuencas.f90:2131-2174 ; a_quien is 1-based cell id (0 = none), channel cells get 0 */
+void wo_geo_hand(const int32_t *basin_f, const float *elev, const float *lng, const int32_t *cauce,
+                 int32_t n, float *hand, float *hdnd, int32_t *a_quien)
+{
+    for (int32_t i = 0; i < n; ++i) {
+        hand[i] = 0.0f;
+        hdnd[i] = (cauce[i] == 1) ? 0.0f : lng[i];
+        a_quien[i] = 0;
+    }
+    for (int32_t i = 0; i < n; ++i) {
+        if (cauce[i] == 1) continue;
+        int32_t it = i;
+        float lsum = lng[i];
+        for (;;) {
+            int32_t d = BF(0, it);
+            if (d == 0) { /* fenced: non-channel outlet */
+                hand[i] = 0.0f;
+                hdnd[i] = 0.0f;
+                a_quien[i] = 0;
+                break;
+            }
+            int32_t drenaid = n - d;
+            if (cauce[drenaid] == 1) {
+                hand[i] = elev[i] - elev[drenaid];
+                hdnd[i] = lsum;
+                a_quien[i] = drenaid + 1;
+                break;
+            } else if (BF(0, drenaid) == 0) {
+                hand[i] = 0.0f;
+                hdnd[i] = 0.0f;
+                a_quien[i] = 0;
+                break;
+            } else {
+                it = drenaid;
+                lsum = lsum + lng[drenaid];
+            }
+        }
+    }
+}
+
+/* cuencas.f90:2679-2703 */
+static int drain_colfil(int32_t d, int32_t *dc, int32_t *df)
+{
+    switch (d) {
+    case 7: *dc = -1; *df = -1; return 1;
+    case 8: *dc = 0; *df = -1; return 1;
+    case 9: *dc = 1; *df = -1; return 1;
+    case 4: *dc = -1; *df = 0; return 1;
+    case 6: *dc = 1; *df = 0; return 1;
+    case 1: *dc = -1; *df = 1; return 1;
+    case 2: *dc = 0; *df = 1; return 1;
+    case 3: *dc = 1; *df = 1; return 1;
+    default: return 0; /* reference adds noData to col/fil -> leaves the map */
+    }
+}
+
+/* cuencas.f90:2175-2219 */
+void wo_geo_hand_global(const wo_geo *g, const float *dem, const int32_t *dir, const int32_t *red,
+                        int32_t nc, int32_t nr, float *hand)
+{
+    const float nodata = g->nodata;
+#define M(a, c, f) a[(size_t)((f)-1) * nc + ((c)-1)]
+    for (int64_t k = 0; k < (int64_t)nc * nr; ++k) hand[k] = (red[k] == 1) ? 0.0f : nodata;
+    for (int32_t i = 1; i <= nc; ++i) {
+        for (int32_t j = 1; j <= nr; ++j) {
+            if ((float)M(dir, i, j) != nodata && M(red, i, j) == 0) {
+                int32_t col = i, fil = j;
+                int flag = 1;
+                int64_t guard = 0;
+                while (flag == 1 && (float)M(dir, col, fil) != nodata) {
+                    int32_t dc, df;
+                    if (!drain_colfil(M(dir, col, fil), &dc, &df)) {
+                        M(hand, i, j) = nodata;
+                        break;
+                    }
+                    col += dc;
+                    fil += df;
+                    if (col > 0 && col <= g->ncols && fil > 0 && fil <= g->nrows && col <= nc && fil <= nr) {
+                        if (M(red, col, fil) == 1) {
+                            M(hand, i, j) = M(dem, i, j) - M(dem, col, fil);
+                            flag = 0;
+                        } else if ((float)M(red, col, fil) == nodata) {
+                            M(hand, i, j) = nodata;
+                            flag = 0;
+                        }
+                    } else {
+                        M(hand, i, j) = nodata;
+                        flag = 0;
+                    }
+                    if (++guard > (int64_t)nc * nr) break; /* fenced: cyclic DIR */
+                }
+            }
+        }
+    }
+#undef M
+}
+
+/* cuencas.f90:724-756 */
+void wo_basin_time_to_out(const int32_t *basin_f, const float *lng, const float *speed, int32_t n,
+                          float *time)
+{
+    float *tc = (float *)malloc(sizeof(float) * (size_t)n);
+    for (int32_t i = 0; i < n; ++i) tc[i] = lng[i] / speed[i];
+    for (int32_t i = 1; i <= n; ++i) {
+        int32_t drenaid = n - BF(0, i - 1) + 1; /* 1-based */
+        if (drenaid < n) {
+            float acc = tc[i - 1];
+            int flag = 1;
+            while (flag) {
+                acc = acc + tc[drenaid - 1];
+                drenaid = n - BF(0, drenaid - 1) + 1;
+                if (drenaid >= n) flag = 0;
+            }
+            time[i - 1] = acc;
+        } else {
+            time[i - 1] = tc[i - 1];
+        }
+    }
+    free(tc);
+}
+
+/* cuencas.f90:1811-1833 */
+void wo_basin_propagate(const int32_t *basin_f, const float *var, int32_t n, float *var_prop)
+{
+    for (int32_t i = 0; i < n; ++i) var_prop[i] = var[i];
+    for (int32_t i = 0; i < n; ++i) {
+        if (var_prop[i] > 0.0f) {
+            int32_t drenaid = n - BF(0, i) + 1; /* 1-based */
+            if (drenaid <= n) var_prop[drenaid - 1] = var_prop[drenaid - 1] + var_prop[i];
+        }
+    }
+}

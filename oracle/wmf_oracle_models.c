@@ -1,0 +1,528 @@
+/*
+ * wmf_oracle_models.c -- CPU ORACLE (test infrastructure, NOT product code).
+ * Literal sequential restatement of shia_v1 and its sub-models from
+ * wmf/modelosv2.f90 (module models).  See wmf_oracle.h ("parity unpinned").
+ *
+ * Scope: vertical tanks, hillslope outflow (linear / kinematic), routing,
+ * channel kinematic wave, control-point records, per-step means and balance,
+ * SED sediment sub-model, landslide sub-model.  Not restated:
+ * separate_fluxes, separate_rain, floods, per-step file dumps.
+ *
+ * Fenced quirks (undefined in the reference; oracle AND kernels do this):
+ *  - vspeed is always computed (the reference leaves it uninitialised when
+ *    HspeedIn is supplied, modelosv2.f90:285-299).
+ *  - speed_type(4) is read out of bounds at :293; hspeed(4,:) starts at 0
+ *    (the channel always uses the kinematic solver).
+ *  - hflux(4)/section_area are stale for a type-1 control cell (:750,:764);
+ *    the oracle records 0 there.
+ *  - at the outlet drenaid = N+1 (:468): the unguarded writes
+ *    StoOut(4,drenaid) (:617), Vs(i,drena_id) (:1374,:1401,:1418) and
+ *    Vsc(i,drena_id) (:1601) are dropped.
+ *  - slide_hill2gullie walks past the outlet (:1695); the walk stops there.
+ *  - x**2.0 in slide_allocate is evaluated as x*x.
+ */
+#include "wmf_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define A4(a, k, i) a[4 * (size_t)(i) + (k)]
+#define A5(a, k, i) a[5 * (size_t)(i) + (k)]
+#define A3(a, k, i) a[3 * (size_t)(i) + (k)]
+
+/* modelosv2.f90:1278-1293 */
+float wo_calc_speed(float sm, float coef, float expo, float elem_long, float *speed, float dt,
+                    int32_t calc_niter)
+{
+    float area = 0.0f;
+    for (int i = 0; i < calc_niter; ++i) {
+        area = sm / (elem_long + *speed * dt);
+        float new_speed = coef * powf(area, expo);
+        *speed = (2.0f * new_speed + *speed) / 3.0f;
+    }
+    return area;
+}
+
+typedef struct {
+    const wo_shia_in *in;
+    wo_shia_out *out;
+    float qlin_sed;
+    float DEP[3];
+    float EROt[3], DEPt[3];
+} sed_state;
+
+/* modelosv2.f90:1321-1428 ; celda, drena_id 0-based (drena_id == n_cel means "outside") */
+static void sed_hillslope(sed_state *S, float alfa, float v2, float S2, float So, int32_t celda,
+                          int32_t drena_id, int32_t tipo)
+{
+    const wo_shia_in *in = S->in;
+    wo_shia_out *o = S->out;
+    const float dt = in->dt, dxp = in->dxp;
+    const int32_t N = in->n_cel;
+    float qsSUStot = 0, qsBMtot = 0, qsEROtot = 0, qsSUS[3] = {0, 0, 0}, qsBM[3] = {0, 0, 0},
+          qsERO[3] = {0, 0, 0};
+    float SUStot = 0, DEPtot = 0, Te[3];
+    float *Vs = o->vs, *Vd = o->vd, *Vsc = o->vsc;
+    S->DEP[0] = S->DEP[1] = S->DEP[2] = 0;
+    float Qskr = alfa * powf(So, 1.664f) * powf(S->qlin_sed, 2.035f) * in->krus[celda] *
+                 in->crus[celda] * in->prus[celda] * dxp * dt;
+    for (int i = 0; i < 3; ++i) {
+        if (S2 / 1000.0f > in->wi[i] * dt)
+            Te[i] = in->wi[i] * dt * 1000.0f / S2;
+        else
+            Te[i] = 1.0f;
+        A3(Vd, i, celda) = A3(Vd, i, celda) + Te[i] * A3(Vs, i, celda);
+        A3(Vs, i, celda) = A3(Vs, i, celda) - Te[i] * A3(Vs, i, celda);
+        S->DEP[i] = Te[i] * A3(Vs, i, celda);
+        SUStot = SUStot + A3(Vs, i, celda);
+        DEPtot = DEPtot + A3(Vd, i, celda);
+    }
+    for (int i = 0; i < 3; ++i) {
+        if (A3(Vs, i, celda) > 0.0f) {
+            if (Qskr < SUStot) {
+                float cap = Qskr * A3(Vs, i, celda) / SUStot;
+                float Adv = A3(Vs, i, celda) * v2 * dt / (dxp + v2 * dt);
+                qsSUS[i] = fmaxf(cap, Adv);
+            } else {
+                qsSUS[i] = A3(Vs, i, celda);
+            }
+        }
+        qsSUStot = qsSUStot + qsSUS[i];
+        A3(Vs, i, celda) = A3(Vs, i, celda) - qsSUS[i];
+        if (tipo == 1) {
+            if (drena_id < N) A3(Vs, i, drena_id) = A3(Vs, i, drena_id) + qsSUS[i];
+        } else {
+            A3(Vsc, i, celda) = A3(Vsc, i, celda) + qsSUS[i];
+        }
+    }
+    float totXSScap = fmaxf(0.0f, Qskr - qsSUStot);
+    if (totXSScap > 0.0f && DEPtot > 0.0f) {
+        for (int i = 0; i < 3; ++i) {
+            if (A3(Vd, i, celda) > 0.0f) {
+                if (totXSScap < DEPtot)
+                    qsBM[i] = totXSScap * A3(Vd, i, celda) / DEPtot;
+                else
+                    qsBM[i] = A3(Vd, i, celda);
+            }
+            qsBMtot = qsBMtot + qsBM[i];
+            S->DEP[i] = S->DEP[i] - qsBM[i];
+            if (S->DEP[i] < 0) S->DEP[i] = 0;
+            A3(Vd, i, celda) = A3(Vd, i, celda) - qsBM[i];
+            if (tipo == 1) {
+                if (drena_id < N) A3(Vs, i, drena_id) = A3(Vs, i, drena_id) + qsBM[i];
+            } else {
+                A3(Vsc, i, celda) = A3(Vsc, i, celda) + qsBM[i];
+            }
+        }
+    }
+    for (int i = 0; i < 3; ++i) S->DEPt[i] = S->DEPt[i] + S->DEP[i];
+    float REScap = fmaxf(0.0f, totXSScap - qsBMtot);
+    if (REScap > 0.0f) {
+        for (int i = 0; i < 3; ++i) {
+            qsERO[i] = A3(in->parliac, i, celda) * REScap / 100.0f;
+            qsEROtot = qsEROtot + qsERO[i];
+            if (tipo == 1) {
+                if (drena_id < N) A3(Vs, i, drena_id) = A3(Vs, i, drena_id) + qsERO[i];
+            } else {
+                A3(Vsc, i, celda) = A3(Vsc, i, celda) + qsERO[i];
+            }
+        }
+    }
+    for (int i = 0; i < 3; ++i) S->EROt[i] = S->EROt[i] + qsERO[i];
+    o->volero[celda] = o->volero[celda] + ((qsERO[0] + qsERO[1]) + qsERO[2]);
+    o->voldepo[celda] = o->voldepo[celda] + ((S->DEP[0] + S->DEP[1]) + S->DEP[2]);
+    (void)qsEROtot;
+}
+
+/* modelosv2.f90:1537-1608 */
+static void sed_channel(sed_state *S, float S5, float v5, float Q5, float So, float area_sec,
+                        int32_t celda, int32_t drena_id, float VolSal[3])
+{
+    const wo_shia_in *in = S->in;
+    wo_shia_out *o = S->out;
+    const float dt = in->dt, dxp = in->dxp;
+    const int32_t N = in->n_cel;
+    const float grav = 9.8f, Gsed = 2.65f;
+    float Cw[3], Te[3], qsSUS[3] = {0, 0, 0}, qsBM[3] = {0, 0, 0};
+    float L, Rh;
+    float *Vsc = o->vsc, *Vdc = o->vdc;
+    S->DEP[0] = S->DEP[1] = S->DEP[2] = 0;
+    if (S5 > 0.0f) {
+        L = area_sec * 1000.0f / S5;
+        Rh = L * S5 / (1000.0f * L + 2.0f * S5);
+    } else {
+        Rh = 0.0f;
+    }
+    for (int i = 0; i < 3; ++i) {
+        float d = in->diametro[i];
+        Cw[i] = 0.05f * (Gsed / (Gsed - 1.0f)) * (v5 * So) / (sqrtf((Gsed - 1.0f) * grav * d / 1000.0f)) *
+                sqrtf((Rh * So) / ((Gsed - 1.0f) * (d / 1000.0f)));
+        if (S5 / 1000.0f > in->wi[i] * dt)
+            Te[i] = in->wi[i] * dt * 1000.0f / S5;
+        else
+            Te[i] = 1.0f;
+        A3(Vdc, i, celda) = A3(Vdc, i, celda) + Te[i] * A3(Vsc, i, celda);
+        A3(Vsc, i, celda) = A3(Vsc, i, celda) - Te[i] * A3(Vsc, i, celda);
+        S->DEP[i] = S->DEP[i] + Te[i] * A3(Vsc, i, celda);
+    }
+    for (int i = 0; i < 3; ++i) {
+        float supply = A3(Vsc, i, celda) + A3(Vdc, i, celda);
+        qsSUS[i] = 0.0f;
+        if (supply > 0.0f) {
+            float VolEH = Q5 * Cw[i] * dt / 2.65f;
+            float AdvF = fminf(1.0f, v5 * dt / (dxp + v5 * dt));
+            qsSUS[i] = A3(Vsc, i, celda) * AdvF;
+            float XSScap = fmaxf(0.0f, VolEH - qsSUS[i]);
+            qsBM[i] = A3(Vdc, i, celda) * AdvF;
+            qsBM[i] = fminf(XSScap, qsBM[i]);
+            S->DEP[i] = S->DEP[i] - qsBM[i];
+            if (S->DEP[i] < 0.0f) S->DEP[i] = 0.0f;
+            A3(Vsc, i, celda) = A3(Vsc, i, celda) - qsSUS[i];
+            A3(Vdc, i, celda) = A3(Vdc, i, celda) - qsBM[i];
+            if (drena_id < N) A3(Vsc, i, drena_id) = A3(Vsc, i, drena_id) + qsSUS[i] + qsBM[i];
+            VolSal[i] = (qsSUS[i] + qsBM[i]) / dt;
+        }
+    }
+    o->voldepo[celda] = o->voldepo[celda] + ((S->DEP[0] + S->DEP[1]) + S->DEP[2]);
+}
+
+/* modelosv2.f90:1613-1648 */
+static void slide_allocate(const wo_shia_in *in, wo_shia_out *o)
+{
+    const int32_t N = in->n_cel;
+    const float gw = in->sl_gammaw;
+    for (int32_t i = 0; i < N; ++i) {
+        float gs = in->sl_gammas[i], co = in->sl_cohesion[i], fa = in->sl_frictionangle[i],
+              rs = in->sl_radslope[i], zs = in->sl_zs[i];
+        float c2 = cosf(rs) * cosf(rs);
+        o->sl_zmin[i] = co / ((gw * c2 * tanf(fa)) + (gs * c2 * (tanf(rs) - tanf(fa))));
+        o->sl_zcrit[i] = (gs / gw) * zs * (1.0f - (tanf(rs) / tanf(fa))) + (co / (gw * c2 * tanf(fa)));
+        o->sl_zmax[i] = co / ((gs * c2) * (tanf(rs) - tanf(fa)));
+        o->sl_bo[i] = atanf(-tanf(fa * (gw - gs) / gs));
+        float rv = 2.0f;
+        if (in->unit_type[i] == 3) rv = 0.0f;
+        if (rs < o->sl_bo[i]) rv = 0.0f;
+        if (zs < o->sl_zmin[i] && rs < o->sl_bo[i]) rv = 0.0f;
+        if (zs > o->sl_zmax[i] && rs > o->sl_bo[i]) rv = 1.0f;
+        o->sl_riskvector[i] = rv;
+        o->sl_slideocurrence[i] = 0.0f;
+        o->sl_slideacumulate[i] = 0;
+    }
+    for (int32_t t = 0; t < in->n_reg; ++t) o->sl_slidencelltime[t] = 0;
+}
+
+/* modelosv2.f90:1683-1707 ; cell 0-based, t 0-based */
+static void slide_hill2gullie(const wo_shia_in *in, wo_shia_out *o, int32_t cell, int32_t t)
+{
+    const int32_t N = in->n_cel;
+    if (in->unit_type[cell] <= 2) {
+        int32_t local = cell;
+        for (;;) {
+            if (in->drena[local] == 0) break; /* fenced: outlet */
+            int32_t direction = N - in->drena[local];
+            if (in->unit_type[direction] > in->unit_type[local]) break;
+            o->sl_slideocurrence[direction] = 3.0f;
+            o->sl_slideacumulate[direction] += 1;
+            o->sl_slidencelltime[t] += 1;
+            local = direction;
+        }
+    }
+}
+
+/* modelosv2.f90:1649-1682 */
+static void slide_ocurrence(const wo_shia_in *in, wo_shia_out *o, int32_t t, int32_t cell,
+                            float StorageT3, float MaxStoT3)
+{
+    if (o->sl_riskvector[cell] == 2.0f && o->sl_slideocurrence[cell] == 0.0f) {
+        float Zw = (StorageT3 * in->sl_zs[cell]) / MaxStoT3;
+        if (Zw >= o->sl_zcrit[cell]) {
+            o->sl_slideocurrence[cell] = 1.0f;
+            o->sl_slideacumulate[cell] = 1;
+            o->sl_slidencelltime[t] += 1;
+            if (in->sl_gullienogullie == 1) slide_hill2gullie(in, o, cell, t);
+        } else {
+            float rs = in->sl_radslope[cell];
+            float Num = in->sl_cohesion[cell] + (in->sl_gammas[cell] * in->sl_zs[cell] - Zw * in->sl_gammaw) *
+                                                    (cosf(rs) * cosf(rs)) * tanf(in->sl_frictionangle[cell]);
+            float Den = in->sl_gammas[cell] * in->sl_zs[cell] * sinf(rs) * cosf(rs);
+            if (Num / Den <= in->sl_fs) {
+                o->sl_slideocurrence[cell] = 1.0f;
+                o->sl_slideacumulate[cell] = 1;
+                o->sl_slidencelltime[t] += 1;
+                if (in->sl_gullienogullie == 1) slide_hill2gullie(in, o, cell, t);
+            }
+        }
+    }
+}
+
+static float sum_f(const float *a, size_t n)
+{
+    float s = 0.0f;
+    for (size_t i = 0; i < n; ++i) s += a[i];
+    return s;
+}
+static double sum_d(const float *a, size_t n)
+{
+    double s = 0.0;
+    for (size_t i = 0; i < n; ++i) s += (double)a[i];
+    return s;
+}
+
+/* modelosv2.f90:191-869 */
+int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
+{
+    const int32_t N = in->n_cel, T = in->n_reg, NC = in->n_cont, NH = in->n_conth;
+    const float dt = in->dt;
+    if (N <= 0 || T <= 0 || NC < 1 || in->calc_niter < 1) return 1;
+    float *Sto = out->stoout;
+    float *vspeed = (float *)malloc(sizeof(float) * 4 * (size_t)N);
+    float *hspeed = out->hspeed_out;
+    float *H = (float *)malloc(sizeof(float) * 3 * (size_t)N);
+    float *m3_mm = (float *)malloc(sizeof(float) * (size_t)N);
+    float *rain = (float *)malloc(sizeof(float) * (size_t)N);
+    float *vfl_map = in->save_vfluxes ? (float *)malloc(sizeof(float) * 4 * (size_t)N) : NULL;
+    sed_state SS;
+    memset(&SS, 0, sizeof SS);
+    SS.in = in;
+    SS.out = out;
+
+    /* setup :257-304 */
+    for (int32_t t = 0; t < T; ++t) out->mean_rain[t] = 0.0f;
+    for (int32_t i = 0; i < N; ++i) out->acum_rain[i] = 0.0f;
+    for (int32_t i = 0; i < N; ++i) m3_mm[i] = in->elem_area[i] / 1000.0f;
+    for (size_t k = 0; k < (size_t)NC * T; ++k) out->q[k] = 0.0f;
+    if (out->speed) memset(out->speed, 0, sizeof(float) * (size_t)NC * T);
+    if (out->areacontrol) memset(out->areacontrol, 0, sizeof(float) * (size_t)NC * T);
+    if (out->hum) memset(out->hum, 0, sizeof(float) * (size_t)NH * T);
+    if (out->st1) memset(out->st1, 0, sizeof(float) * (size_t)NH * T);
+    if (out->st3) memset(out->st3, 0, sizeof(float) * (size_t)NH * T);
+    if (in->stoin && in->stoin[0] > 0.0f)
+        memcpy(Sto, in->stoin, sizeof(float) * 5 * (size_t)N);
+    else
+        for (size_t k = 0; k < 5 * (size_t)N; ++k) Sto[k] = in->storage[k] + in->storage_constant;
+    float entradas = 0.0f, salidas = 0.0f;
+    double entradas64 = 0.0, salidas64 = 0.0;
+    for (int32_t t = 0; t < T; ++t) out->balance[t] = 0.0f;
+    for (int32_t i = 0; i < N; ++i)
+        for (int k = 0; k < 4; ++k) A4(vspeed, k, i) = A4(in->v_coef, k, i) * in->calib[k] * dt;
+    if (in->hspeedin && in->hspeedin[0] > 0.0f) {
+        memcpy(hspeed, in->hspeedin, sizeof(float) * 4 * (size_t)N);
+    } else {
+        for (int32_t i = 0; i < N; ++i) {
+            for (int k = 0; k < 3; ++k)
+                A4(hspeed, k, i) = (in->speed_type[k] == 1) ? A4(in->h_coef, k, i) * in->calib[k + 4] : 0.0f;
+            A4(hspeed, 3, i) = 0.0f;
+        }
+    }
+    for (int32_t i = 0; i < N; ++i) {
+        A3(H, 0, i) = in->max_capilar[i] * in->calib[8];
+        A3(H, 1, i) = in->max_gravita[i] * in->calib[9];
+        A3(H, 2, i) = in->max_aquifer[i] * in->calib[10];
+    }
+    /* optional setup :310-426 */
+    if (in->retorno_gr == 1.0f && out->retorned)
+        for (int32_t i = 0; i < N; ++i) out->retorned[i] = 0.0f;
+    if (in->retorno_gr == 1.0f && in->show_mean_retorno == 1 && out->mean_retorno)
+        for (int32_t t = 0; t < T; ++t) out->mean_retorno[t] = 0.0f;
+    if (in->sim_sediments == 1) {
+        /* sed_allocate :1298-1319 */
+        for (size_t k = 0; k < 3 * (size_t)N; ++k) {
+            out->vd[k] = in->vd_init ? in->vd_init[k] : 0.0f;
+            out->vs[k] = 0.0f;
+            out->vsc[k] = 0.0f;
+            out->vdc[k] = 0.0f;
+        }
+        for (int32_t i = 0; i < N; ++i) out->volero[i] = out->voldepo[i] = 0.0f;
+        for (size_t k = 0; k < (size_t)NC * 3 * T; ++k) out->qsed[k] = 0.0f;
+    }
+    if (in->sim_slides == 1) slide_allocate(in, out);
+    if (in->save_rc == 1 && out->rc_coef)
+        for (size_t k = 0; k < 2 * (size_t)N; ++k) out->rc_coef[k] = 0.0f;
+
+    /* time loop :433 */
+    for (int32_t t = 0; t < T; ++t) {
+        int32_t control_cont = 2, controlh_cont = 1;
+        float StoAtras = sum_f(Sto, 5 * (size_t)N);
+        double StoAtras64 = sum_d(Sto, 5 * (size_t)N);
+        if (in->pos_evento[t] == 1) {
+            for (int32_t i = 0; i < N; ++i) rain[i] = 0.0f;
+        } else {
+            const int32_t *rec = in->rain + (size_t)(in->pos_evento[t] - 1) * N;
+            for (int32_t i = 0; i < N; ++i) rain[i] = (float)rec[i] / 1000.0f;
+        }
+        float rain_sum = 0.0f;
+        for (int32_t i = 0; i < N; ++i) out->acum_rain[i] = out->acum_rain[i] + rain[i];
+        float hflux[4] = {0, 0, 0, 0}, vflux[4];
+        float section_area = 0.0f;
+        float Vsal_sed[3] = {0, 0, 0};
+
+        for (int32_t c = 0; c < N; ++c) {
+            const int32_t drenaid = N - in->drena[c]; /* 0-based; == N at the outlet */
+            const int32_t ut = in->unit_type[c];
+            entradas = entradas + rain[c];
+            entradas64 += (double)rain[c];
+            rain_sum = rain_sum + rain[c];
+            /* vertical :478-512 */
+            vflux[0] = fmaxf(0.0f, rain[c] - A3(H, 0, c) + A5(Sto, 0, c));
+            A5(Sto, 0, c) = A5(Sto, 0, c) + rain[c] - vflux[0];
+            float Evp_loss = fminf(in->evpserie[t] * A4(vspeed, 0, c) *
+                                       powf(A5(Sto, 0, c) / A3(H, 0, c), 0.6f),
+                                   A5(Sto, 0, c));
+            A5(Sto, 0, c) = A5(Sto, 0, c) - Evp_loss;
+            for (int i = 0; i < 3; ++i) {
+                vflux[i + 1] = fminf(vflux[i], A4(vspeed, i + 1, c));
+                A5(Sto, i + 1, c) = A5(Sto, i + 1, c) + vflux[i] - vflux[i + 1];
+            }
+            if (in->retorno_aq > 0.0f) {
+                float Ret_aq = fmaxf(0.0f, A5(Sto, 3, c) - A3(H, 2, c));
+                A5(Sto, 2, c) = A5(Sto, 2, c) + Ret_aq;
+                A5(Sto, 3, c) = A5(Sto, 3, c) - Ret_aq;
+            }
+            if (in->retorno_gr > 0.0f) {
+                float Ret = fmaxf(0.0f, A5(Sto, 2, c) - A3(H, 1, c));
+                A5(Sto, 1, c) = A5(Sto, 1, c) + Ret;
+                A5(Sto, 2, c) = A5(Sto, 2, c) - Ret;
+                if (out->retorned) out->retorned[c] = out->retorned[c] + Ret;
+                vflux[1] = vflux[1] + Ret;
+                vflux[2] = vflux[2] - Ret;
+            }
+            if (vfl_map)
+                for (int i = 0; i < 4; ++i) A4(vfl_map, i, c) = vflux[i];
+            if (in->save_rc == 1 && out->rc_coef) {
+                out->rc_coef[2 * (size_t)c] = out->rc_coef[2 * (size_t)c] + vflux[1] - vflux[2];
+                out->rc_coef[2 * (size_t)c + 1] = out->rc_coef[2 * (size_t)c + 1] + rain[c];
+            }
+            salidas = salidas + vflux[3] + Evp_loss;
+            salidas64 += (double)vflux[3] + (double)Evp_loss;
+            /* hillslope outflow :553-595 */
+            for (int i = 0; i < 3; ++i) {
+                if (in->speed_type[i] == 1) {
+                    hflux[i] = (1.0f - in->hill_long[c] / (A4(hspeed, i, c) * dt + in->hill_long[c])) *
+                               A5(Sto, i + 1, c);
+                } else if (in->speed_type[i] == 2) {
+                    section_area = wo_calc_speed(A5(Sto, i + 1, c) * m3_mm[c],
+                                                 A4(in->h_coef, i, c) * in->calib[i + 4], A4(in->h_exp, i, c),
+                                                 in->hill_long[c], &A4(hspeed, i, c), dt, in->calc_niter);
+                    hflux[i] = fminf(section_area * A4(hspeed, i, c) * dt / m3_mm[c], A5(Sto, i + 1, c));
+                    if (in->sim_sediments == 1 && i == 0) {
+                        SS.qlin_sed = hflux[i] * m3_mm[c] / (dt * in->dxp);
+                        sed_hillslope(&SS, in->sed_factor, A4(hspeed, 0, c), A5(Sto, 1, c), in->hill_slope[c],
+                                      c, drenaid, ut);
+                    }
+                }
+                A5(Sto, i + 1, c) = A5(Sto, i + 1, c) - hflux[i];
+            }
+            /* routing :599-719 */
+            if (ut == 1) {
+                if (in->drena[c] != 0) {
+                    for (int i = 0; i < 3; ++i) A5(Sto, i + 1, drenaid) = A5(Sto, i + 1, drenaid) + hflux[i];
+                } else {
+                    float s3 = (hflux[0] + hflux[1]) + hflux[2];
+                    out->q[(size_t)t * NC + 0] = out->q[(size_t)t * NC + 0] + s3 * m3_mm[c];
+                    salidas = salidas + s3;
+                    salidas64 += (double)s3;
+                }
+            } else if (ut > 1) {
+                if (drenaid < N) A5(Sto, 3, drenaid) = A5(Sto, 3, drenaid) + hflux[2] * (float)(3 - ut);
+                A5(Sto, 4, c) = A5(Sto, 4, c) + (hflux[0] + hflux[1]) + hflux[2] * (float)(ut - 2);
+                section_area = wo_calc_speed(A5(Sto, 4, c) * m3_mm[c], A4(in->h_coef, 3, c) * in->calib[7],
+                                             A4(in->h_exp, 3, c), in->stream_long[c], &A4(hspeed, 3, c), dt,
+                                             in->calc_niter);
+                hflux[3] = fminf(section_area * A4(hspeed, 3, c) * dt / m3_mm[c], A5(Sto, 4, c));
+                if (in->sim_sediments == 1) {
+                    Vsal_sed[0] = Vsal_sed[1] = Vsal_sed[2] = 0.0f;
+                    sed_channel(&SS, A5(Sto, 4, c), A4(hspeed, 3, c), hflux[3] * m3_mm[c] / dt,
+                                in->stream_slope[c], section_area, c, drenaid, Vsal_sed);
+                }
+                A5(Sto, 4, c) = A5(Sto, 4, c) - hflux[3];
+                if (in->drena[c] != 0) {
+                    A5(Sto, 4, drenaid) = A5(Sto, 4, drenaid) + hflux[3];
+                } else {
+                    out->q[(size_t)t * NC + 0] = hflux[3] * m3_mm[c] / dt;
+                    salidas = salidas + hflux[3];
+                    salidas64 += (double)hflux[3];
+                    if (in->sim_sediments == 1)
+                        for (int i = 0; i < 3; ++i) out->qsed[((size_t)t * 3 + i) * NC + 0] = Vsal_sed[i];
+                    if (in->show_speed == 1) {
+                        out->speed[(size_t)t * NC + 0] = A4(hspeed, 3, c);
+                        out->areacontrol[(size_t)t * NC + 0] = section_area;
+                    }
+                }
+            }
+            /* slides :723 */
+            if (in->sim_slides == 1) slide_ocurrence(in, out, t, c, A5(Sto, 2, c), A3(H, 1, c));
+            /* records :749-787 */
+            if (in->control[c] != 0) {
+                if (control_cont <= NC) {
+                    size_t k = (size_t)t * NC + (control_cont - 1);
+                    if (ut > 1) {
+                        out->q[k] = hflux[3] * m3_mm[c] / dt;
+                        if (in->show_speed == 1) {
+                            out->speed[k] = A4(hspeed, 3, c);
+                            out->areacontrol[k] = section_area;
+                        }
+                        if (in->sim_sediments == 1)
+                            for (int i = 0; i < 3; ++i)
+                                out->qsed[((size_t)t * 3 + i) * NC + (control_cont - 1)] = Vsal_sed[i];
+                    } else { /* fenced: stale hflux(4) for a hillslope control cell */
+                        out->q[k] = 0.0f;
+                    }
+                }
+                control_cont = control_cont + 1;
+            }
+            if (in->control_h[c] != 0) {
+                if (controlh_cont <= NH) {
+                    size_t k = (size_t)t * NH + (controlh_cont - 1);
+                    out->hum[k] = A5(Sto, 0, c) + A5(Sto, 2, c);
+                    out->st1[k] = A5(Sto, 0, c);
+                    out->st3[k] = A5(Sto, 2, c);
+                }
+                controlh_cont = controlh_cont + 1;
+            }
+        }
+        /* per-step epilogue :797-848 */
+        out->mean_rain[t] = rain_sum / (float)N;
+        if (vfl_map && out->mean_vfluxes)
+            for (int k = 0; k < 4; ++k) {
+                float s = 0.0f;
+                for (int32_t i = 0; i < N; ++i) s += A4(vfl_map, k, i);
+                out->mean_vfluxes[4 * (size_t)t + k] = s / (float)N;
+            }
+        if (in->show_storage == 1 && out->mean_storage)
+            for (int k = 0; k < 5; ++k) {
+                float s = 0.0f;
+                for (int32_t i = 0; i < N; ++i) s += A5(Sto, k, i);
+                out->mean_storage[5 * (size_t)t + k] = s / (float)N;
+            }
+        if (in->show_mean_speed == 1 && out->mean_speed)
+            for (int k = 0; k < 4; ++k) {
+                float s = 0.0f;
+                for (int32_t i = 0; i < N; ++i) s += A4(hspeed, k, i);
+                out->mean_speed[4 * (size_t)t + k] = s / (float)N;
+            }
+        if (in->retorno_gr == 1.0f && in->show_mean_retorno == 1 && out->mean_retorno && out->retorned)
+            out->mean_retorno[t] = sum_f(out->retorned, (size_t)N) / (float)N;
+        if ((in->show_mean_retorno == 1 || in->save_retorno == 1) && out->retorned && in->retorno_gr == 1.0f)
+            for (int32_t i = 0; i < N; ++i) out->retorned[i] = 0.0f;
+        out->balance[t] = sum_f(Sto, 5 * (size_t)N) - StoAtras - entradas + salidas;
+        if (out->balance64) out->balance64[t] = sum_d(Sto, 5 * (size_t)N) - StoAtras64 - entradas64 + salidas64;
+        entradas = 0.0f;
+        salidas = 0.0f;
+        entradas64 = 0.0;
+        salidas64 = 0.0;
+    }
+    if (in->save_rc == 1 && out->rc_coef)
+        for (int32_t i = 0; i < N; ++i)
+            if (out->rc_coef[2 * (size_t)i] > out->rc_coef[2 * (size_t)i + 1])
+                out->rc_coef[2 * (size_t)i] = out->rc_coef[2 * (size_t)i + 1];
+    if (in->sim_sediments == 1) {
+        if (out->erot) memcpy(out->erot, SS.EROt, sizeof SS.EROt);
+        if (out->dept) memcpy(out->dept, SS.DEPt, sizeof SS.DEPt);
+    }
+    free(vspeed);
+    free(H);
+    free(m3_mm);
+    free(rain);
+    free(vfl_map);
+    return 0;
+}
