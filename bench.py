@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SHIA/TETIS hot path (BASELINE.json configs[1], "C2").
+
+    python bench.py --gpus N --steps K --warmup W             # our CUDA path, one rank per GPU (torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm on the host cores
+
+A "step" is one complete SHIA run (modelosv2.f90:191-869): ~1M-cell synthetic basin x 1000 hourly steps of
+synthetic rainfall, i.e. ~1.04e9 cell-steps.  With N>1 every rank runs the same basin with its own calibration
+set (one ensemble member per GPU -- the path shards by member, no data-path collective) and the per-member
+objective scores are gathered over NCCL; value = N * cell-steps / max-over-ranks time  ("weak" scaling).
+
+Numbers on the JSON line
+  value      cell-steps/s, inputs resident in HBM, timed with CUDA events on the launch stream
+  e2e        the same run through the public drop-in call models.shia_v1(...) with HOST (pinned) buffers:
+             host->device copies of every input and device->host reads of every output are inside the timed region
+  roofline   dominant kernel k_shia_wave: algorithmic bytes (144 B/cell-step, SURVEY 8d / DESIGN.md) / CUDA-event
+             time of the wave launches, against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle (C restatement of the Fortran, -O3 -funroll-loops, 1 thread) on a bounded sample
+  extra      Path A (basin_find+basin_cut+basin_acum) Mcell/s on the same raster, and run statistics
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_CELL_STEP = 144.0      # algorithmic bytes of one cell-step of a single run
+WORKLOADS = {
+    # name: (ncols, nrows, steps, generator)
+    "c2": (1024, 1024, 1000, "G2"),      # BASELINE.json configs[1]
+    "c2-small": (258, 258, 200, "G2"),   # smoke-sized variant for quick checks
+}
+DX = 30.0
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        mhz = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(mhz)}
+
+
+def build_workload(name: str, cu, rank: int = 0, verbose: bool = False):
+    """Synthetic basin + SHIA inputs of workload ``name``; the topology is traced with OUR Path-A kernels."""
+    from wmf_b200 import synth
+    nc, nr, T, gen = WORKLOADS[name]
+    t0 = time.time()
+    DIR, DEM = synth.make_raster(gen, nc, nr, seed=0)
+    cu.ncols, cu.nrows, cu.xll, cu.yll, cu.dx, cu.dy, cu.dxp, cu.nodata = nc, nr, 0.0, 0.0, DX, DX, DX, synth.NODATA
+    x, y = synth.outlet_xy(nc, nr, 0.0, 0.0, DX)
+    n = cu.basin_find(x, y, DIR, nc, nr)
+    b = cu.basin_cut(n)
+    dv = cu.basin_map2basin(b, DIR.astype(np.float32), 0.0, 0.0, DX, DX, synth.NODATA).astype(np.int32)
+    de = cu.basin_map2basin(b, DEM, 0.0, 0.0, DX, DX, synth.NODATA)
+    acum, lng, pend, _ = cu.basin_basics(b, de, dv)
+    inp = synth.make_shia_inputs(b, acum, lng, pend, dxp=DX, dt=3600.0, n_reg=T, seed=0, thresholds=(30, 500),
+                                 speed_type=(1, 1, 1), n_control=16)
+    if verbose:
+        print(f"[bench] workload {name}: {n} cells, {T} steps, {inp['rain'].shape[0]} rain records, "
+              f"built in {time.time() - t0:.1f}s", file=sys.stderr)
+    return dict(DIR=DIR, DEM=DEM, x=x, y=y, n=n, basin=b, inp=inp, T=T, nc=nc, nr=nr)
+
+
+def bench_path_a(cu, wl, reps=3):
+    """Mcell/s of basin_find + basin_cut + basin_acum with DIR resident in HBM (extra, not the headline)."""
+    import torch
+    d_dir = torch.from_numpy(np.ascontiguousarray(wl["DIR"].T)).cuda()
+    best = None
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = cu.basin_find(wl["x"], wl["y"], d_dir)
+        b = cu.basin_cut(n, resident=True)
+        acum = cu.basin_acum(b)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    assert int(acum[-1].item()) == n
+    return {"path_a_mcell_per_s": n / best / 1e6, "path_a_ms": best * 1e3, "path_a_cells": n,
+            "path_a_levels": cu.basin_find_depth(), "path_a_workload": f"{wl['nc']}x{wl['nr']} G2 raster, find+cut+acum"}
+
+
+def cpu_sample(wl, sample_steps, fast=True):
+    """(cell-steps/s, seconds) of the CPU oracle on the first ``sample_steps`` steps of the workload, 1 thread."""
+    import oracle
+    inp = dict(wl["inp"])
+    inp["n_reg"] = sample_steps
+    inp["pos_evento"] = inp["pos_evento"][:sample_steps]
+    inp["evpserie"] = inp["evpserie"][:sample_steps]
+    t0 = time.perf_counter()
+    oracle.shia_v1(inp, fast=fast)
+    dt = time.perf_counter() - t0
+    return wl["n"] * sample_steps / dt, dt
+
+
+def _ref_worker(args):
+    name, sample_steps = args
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    import oracle  # noqa: F401
+    wl = _REF_WL[0]
+    return cpu_sample(wl, sample_steps)
+
+
+_REF_WL = [None]
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Fortran cannot be built here) on the host
+    cores.  The reference's only parallelism is one process per ensemble member (wmf.py:872-878), so all cores
+    run one member each, on a bounded sample of the workload's steps."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import oracle
+    oracle.build()
+    name = args.workload
+    nc, nr, T, gen = WORKLOADS[name]
+    # the topology must come from somewhere that is not our GPU code: the oracle traces it
+    from wmf_b200 import synth
+    DIR, DEM = synth.make_raster(gen, nc, nr, seed=0)
+    ocu = oracle.Cu(fast=True)
+    ocu.ncols, ocu.nrows, ocu.xll, ocu.yll, ocu.dx, ocu.dy, ocu.dxp, ocu.nodata = nc, nr, 0.0, 0.0, DX, DX, DX, synth.NODATA
+    x, y = synth.outlet_xy(nc, nr, 0.0, 0.0, DX)
+    n = ocu.basin_find(x, y, DIR)
+    b = ocu.basin_cut(n)
+    dv = ocu.basin_map2basin(b, DIR.astype(np.float32), 0.0, 0.0, DX, DX, synth.NODATA).astype(np.int32)
+    de = ocu.basin_map2basin(b, DEM, 0.0, 0.0, DX, DX, synth.NODATA)
+    acum, lng, pend, _ = ocu.basin_basics(b, de, dv)
+    sample_steps = max(2, min(T, args.ref_sample_steps))
+    inp = synth.make_shia_inputs(b, acum, lng, pend, dxp=DX, dt=3600.0, n_reg=T, seed=0, thresholds=(30, 500),
+                                 speed_type=(1, 1, 1), n_control=16)
+    # keep only the rain records the sample touches (memory: every worker holds a copy)
+    pos = inp["pos_evento"][:sample_steps]
+    keep = np.unique(np.concatenate([[1], pos]))
+    remap = np.zeros(inp["rain"].shape[0] + 1, np.int32)
+    remap[keep] = np.arange(1, keep.size + 1)
+    inp["rain"] = np.ascontiguousarray(inp["rain"][keep - 1])
+    inp["pos_evento"] = np.concatenate([remap[pos], np.ones(T - sample_steps, np.int32)])
+    _REF_WL[0] = dict(inp=inp, n=n)
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_ref_worker, [(name, sample_steps)] * cores)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = cores * n * sample_steps / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "shia_cell_steps_per_s", "value": value, "unit": "cell-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name}: SHIA/TETIS 5-tank run, {n}-cell synthetic basin ({nc}x{nr} G2 raster), "
+                               f"{T} hourly steps", "cells": n, "steps_per_run": T},
+        "cpu_baseline": {"value": value, "unit": "cell-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"first {sample_steps} of {T} steps of the same basin and rainfall, one ensemble member "
+                                   f"per core ({cores} processes, as wmf.py:872-878 does), oracle -O3 -funroll-loops"},
+        "e2e": {"value": value, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- wmf_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    from wmf_b200 import Context, CuModule, ModelsModule, synth
+    ctx = Context(local)
+    cu, m = CuModule(ctx), ModelsModule(ctx)
+    wl = build_workload(args.workload, cu, rank, verbose=(rank == 0))
+    inp, n, T = wl["inp"], wl["n"], wl["T"]
+    synth.apply_to_models(m, inp)
+    calibs = synth.make_ensemble_calibs(max(world, 1), seed=0)
+    calib = calibs[rank % calibs.shape[0]][None, :].copy()          # one ensemble member per GPU
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    # --- resident arm: everything in HBM before the clock starts ---
+    stream = torch.cuda.Stream()
+    ctx.use_stream(stream.cuda_stream)
+    m.make_resident()
+    d_rain = torch.from_numpy(inp["rain"]).to(f"cuda:{local}")
+    pos = inp["pos_evento"]
+    want = {"q", "stoout", "balance", "mean_rain"}
+    qobs = None
+
+    def step_resident():
+        nonlocal qobs
+        out = m._run(calib, n_cont, 1, T, d_rain, pos, device_out=True, want=want)
+        if qobs is None:
+            qobs = out["q"][:, 0].contiguous()                       # "observed" series = this member's first run
+        scores = torch.empty((1, 2), dtype=torch.float32, device=f"cuda:{local}")
+        ctx.check(ctx.L.wmf_eval_scores(ctx.h, out["q"].data_ptr(), 1, n_cont, T, 0, qobs.data_ptr(), scores.data_ptr()))
+        if world > 1:                                                # the only collective: gather the members' scores
+            allsc = [torch.empty_like(scores) for _ in range(world)]
+            with torch.cuda.stream(stream):
+                dist.all_gather(allsc, scores)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wave_ms = []
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+        wave_ms.append(ctx.last_kernel_ms())
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launches - l0
+    ms = ev0.elapsed_time(ev1) / args.steps
+    n_levels, n_waves = ctx.last_shia_stats()
+    # --- e2e arm: the drop-in call with host buffers (pinned), copies inside the timed region ---
+    m.make_resident(False)
+    pin_rain = torch.from_numpy(inp["rain"]).pin_memory()
+    m.set_rain(pin_rain.numpy(), pos)
+    a = object.__getattribute__(m, "__dict__")["_a"]
+    h2d = sum(v.nbytes for k, v in a.items() if k in ("drena", "unit_type", "hill_long", "stream_long", "elem_area",
+                                                        "max_capilar", "max_gravita", "max_aquifer", "hill_slope",
+                                                        "stream_slope", "v_coef", "h_coef", "h_exp", "storage", "control",
+                                                        "control_h")) + pin_rain.numel() * 4 + T * 8 + 44
+    d2h = 4 * (n_cont * T * 3 + 3 * T + T + 5 * n + 4 * n + T + n)
+
+    def step_e2e():
+        return m.shia_v1(None, None, calib[0], n_cont, 1, T, None, None, n)
+
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_e2e = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(k_e2e):
+        ret = step_e2e()
+    e1.record(stream)
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / k_e2e
+    assert np.isfinite(ret[0]).all()
+    # --- max over ranks ---
+    tt = torch.tensor([ms, e2e_ms, float(np.mean(wave_ms))], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, wave = (float(v) for v in tt.cpu())
+    if rank == 0:
+        cell_steps = float(n) * T
+        peak, peak_kind = peaks()
+        achieved = BYTES_PER_CELL_STEP * cell_steps / (wave / 1e3) / 1e9
+        extra = bench_path_a(cu, wl)
+        extra.update({"levels": n_levels, "waves_per_run": n_waves, "wave_kernel_ms_per_run": wave,
+                      "setup_and_epilogue_ms_per_run": ms - wave})
+        cpu_steps = max(2, min(T, args.cpu_sample_steps))
+        cpu_v, cpu_s = cpu_sample(wl, cpu_steps)
+        line = {
+            "metric": "shia_cell_steps_per_s", "value": world * cell_steps / (ms / 1e3), "unit": "cell-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: SHIA/TETIS 5-tank run, {n}-cell synthetic basin "
+                                   f"({wl['nc']}x{wl['nr']} G2 raster), {T} hourly steps, 1 ensemble member per GPU",
+                       "cells": n, "steps_per_run": T, "members_per_gpu": 1,
+                       "l2": "inputs larger than L2 (rain table %.2f GB + %.0f MB state/maps)" % (
+                           inp["rain"].nbytes / 1e9, 150.0 * n / 1e6)},
+            "e2e": {"value": world * cell_steps / (e2e_ms / 1e3), "unit": "cell-steps/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_kind": peak_kind, "kernel": "k_shia_wave<false,false>",
+                         "bytes_per_cell_step": BYTES_PER_CELL_STEP,
+                         "launches_per_run": n_waves},
+            "cpu_baseline": {"value": cpu_v, "unit": "cell-steps/s", "cores": 1, "kind": "port",
+                             "sample": f"first {cpu_steps} of {T} steps of the same basin ({cpu_s:.1f} s), oracle "
+                                       "-O3 -funroll-loops, single thread like the reference's Fortran"},
+            "clocks": clocks, "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample-steps", type=int, default=120, help="steps of the workload timed on one CPU core")
+    ap.add_argument("--ref-sample-steps", type=int, default=40, help="steps per reference-arm iteration")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

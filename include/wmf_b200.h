@@ -1,0 +1,214 @@
+/*
+ * wmf_b200.h -- C ABI of libwmf_b200.so: the B200 (sm_100a) drop-in for the two
+ * data-parallel hot paths of nicolas998/WMF.
+ *
+ * What this replaces.  The reference reaches its Fortran through two f2py
+ * extension modules (`cu` from wmf/cuencas.f90, `models` from
+ * wmf/modelosv2.f90; setup.py:5-8, generated wrappers
+ * build/src.win-amd64-3.7/{cumodule.c,modelsmodule.c}).  Every entry point
+ * below names the f2py-wrapped Fortran subroutine it stands in for.  The
+ * Python side (wmf_b200/_cu.py, wmf_b200/_models.py) loads this library with
+ * ctypes and re-creates the `cu` / `models` module objects with the reference's
+ * positional signatures.
+ *
+ * Conventions
+ *  - Plain C: opaque context handle, pointers and sizes only.
+ *  - Every array pointer may be a HOST pointer or a DEVICE pointer of the
+ *    context's GPU (detected with cudaPointerGetAttributes).  Host inputs are
+ *    staged host->device and host outputs device->host on the context stream
+ *    inside the call; device pointers are used in place (zero copies), which is
+ *    how resident pipelines and the benchmark's kernel-only number run.
+ *  - Layouts are the Fortran/f2py ones: X(k,N) is k-fastest
+ *    ([(i-1)*K + (k-1)]); a raster M(nc,nr) stores (col,row) at
+ *    [(row-1)*nc + (col-1)]; cell ids, columns and rows are 1-based.
+ *  - Every function returns a status (0 = WMF_OK) and never throws; the text of
+ *    the last error is available from wmf_last_error().  The Fortran printed
+ *    and carried on instead (cuencas.f90:605, modelosv2.f90:889).
+ *  - There is NO CPU fallback: without a CUDA device wmf_ctx_create fails.
+ *  - A context is not thread-safe; use one per thread / per GPU.  (The Fortran
+ *    modules are process-global and non-reentrant.)
+ */
+#ifndef WMF_B200_H
+#define WMF_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WMF_ABI_VERSION 1
+
+enum {
+    WMF_OK = 0,
+    WMF_ERR_ARG = 1,      /* bad size / null pointer / unsupported switch */
+    WMF_ERR_CUDA = 2,     /* CUDA runtime error, see wmf_last_error */
+    WMF_ERR_TOPOLOGY = 3, /* drain table is cyclic, not upstream-first or not level-ordered */
+    WMF_ERR_STATE = 4,    /* call order violated (e.g. basin_cut before basin_find) */
+    WMF_ERR_NOMEM = 5
+};
+
+typedef struct wmf_ctx wmf_ctx;
+
+/* ------------------------------------------------------------------ context */
+int wmf_abi_version(void);
+int wmf_ctx_create(int device, wmf_ctx **out);
+int wmf_ctx_destroy(wmf_ctx *ctx);
+const char *wmf_last_error(const wmf_ctx *ctx);
+/* Run on an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream. */
+int wmf_set_stream(wmf_ctx *ctx, void *cuda_stream);
+int wmf_synchronize(wmf_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int64_t wmf_launch_count(const wmf_ctx *ctx);
+
+/* module `cu` globals (cuencas.f90:49-54), set by wmf.read_map_raster (wmf.py:319-333) */
+int wmf_set_geo(wmf_ctx *ctx, int32_t ncols, int32_t nrows, float xll, float yll, float dx, float dy,
+                float dxp, float nodata);
+/* module `cu` result scalars (cuencas.f90:60-62): area, pend_media, elevacion, centrox, centroy */
+int wmf_get_basin_scalars(wmf_ctx *ctx, float out5[5]);
+
+/* ------------------------------------------------------------ Path A: `cu` */
+/* coord2fil_col, cuencas.f90:77-90 (host arithmetic in fp32, bit-exact) */
+int wmf_coord2fil_col(wmf_ctx *ctx, float x, float y, int32_t *col, int32_t *fil);
+/* basin_find, cuencas.f90:525-591.  dir: int32 (nc,nr).  Keeps the BFS queue in the context
+ * (the reference keeps it in the module global basin_temp). */
+int wmf_basin_find(wmf_ctx *ctx, float x, float y, const int32_t *dir, int32_t nc, int32_t nr,
+                   int32_t *nceldas);
+/* basin_cut, cuencas.f90:592-607.  basin_f: int32 (3,nceldas) */
+int wmf_basin_cut(wmf_ctx *ctx, int32_t nceldas, int32_t *basin_f);
+/* number of BFS levels (tree depth + 1) of the last basin_find; diagnostic */
+int wmf_basin_find_depth(wmf_ctx *ctx, int32_t *depth);
+/* basin_acum, cuencas.f90:659-680 (also sets the `area` scalar) */
+int wmf_basin_acum(wmf_ctx *ctx, const int32_t *basin_f, int32_t nceldas, int32_t *acum);
+/* basin_acum_var, cuencas.f90:681-701.  drain: int32 (nceldas) = basin_f row 1 */
+int wmf_basin_acum_var(wmf_ctx *ctx, const int32_t *drain, int32_t nceldas, const float *var, float *acum);
+/* basin_basics, cuencas.f90:608-658 (sets all five scalars) */
+int wmf_basin_basics(wmf_ctx *ctx, const int32_t *basin_f, const float *dem, const int32_t *dir,
+                     int32_t nceldas, int32_t *acum, float *lng, float *pend, float *elev);
+/* basin_coordXY, cuencas.f90:797-808 */
+int wmf_basin_coordxy(wmf_ctx *ctx, const int32_t *basin_f, int32_t nceldas, float *x, float *y);
+/* basin_map2basin, cuencas.f90:1144-1184.  mapa: fp32 (ncolsm,nrowsm) */
+int wmf_basin_map2basin(wmf_ctx *ctx, const int32_t *basin_f, int32_t nceldas, const float *mapa,
+                        float xllm, float yllm, int32_t ncolsm, int32_t nrowsm, float dxm, float dym,
+                        float nodatam, float *vec);
+/* basin_2map_find, cuencas.f90:1185-1201 */
+int wmf_basin_2map_find(wmf_ctx *ctx, const int32_t *basin, int32_t nceldas, int32_t *map_ncols,
+                        int32_t *map_nrows);
+/* basin_2map, cuencas.f90:1202-1229.  mapa: fp32 (map_ncols,map_nrows) */
+int wmf_basin_2map(wmf_ctx *ctx, const int32_t *basin, const float *var, int32_t nceldas,
+                   int32_t map_ncols, int32_t map_nrows, float *mapa, float *map_xll, float *map_yll);
+/* basin_float_var2map, cuencas.f90:1037-1051.  mapa: fp32 (nc,nf) */
+int wmf_basin_float_var2map(wmf_ctx *ctx, const int32_t *basin_f, const float *vect, int32_t nceldas,
+                            int32_t nc, int32_t nf, float *mapa);
+/* channel mask of basin_stream_nod, cuencas.f90:1351-1353: cauce = (acum >= umbral) */
+int wmf_basin_stream_mask(wmf_ctx *ctx, const int32_t *acum, int32_t nceldas, int32_t umbral,
+                          int32_t *cauce, int32_t *n_cauce);
+/* basin_stream_type, cuencas.f90:1439-1463 */
+int wmf_basin_stream_type(wmf_ctx *ctx, const int32_t *acum, int32_t nceldas, const int32_t *umbrales,
+                          int32_t numbrales, int32_t *stream_types);
+/* geo_acum_to_cauce, cuencas.f90:2120-2129 (strict >) over ncells raster cells */
+int wmf_geo_acum_to_cauce(wmf_ctx *ctx, const int32_t *acum, int64_t ncells, int32_t umbral, int32_t *cauce);
+/* geo_hand, cuencas.f90:2131-2174 */
+int wmf_geo_hand(wmf_ctx *ctx, const int32_t *basin_f, const float *elev, const float *lng,
+                 const int32_t *cauce, int32_t nceldas, float *hand, float *hdnd, int32_t *a_quien);
+/* geo_hand_global, cuencas.f90:2175-2219.  rasters (nc,nr) */
+int wmf_geo_hand_global(wmf_ctx *ctx, const float *dem, const int32_t *dir, const int32_t *red,
+                        int32_t nc, int32_t nr, float *hand);
+/* basin_time_to_out, cuencas.f90:724-756 */
+int wmf_basin_time_to_out(wmf_ctx *ctx, const int32_t *basin_f, const float *lng, const float *speed,
+                          int32_t nceldas, float *time);
+/* basin_propagate, cuencas.f90:1811-1833 */
+int wmf_basin_propagate(wmf_ctx *ctx, const int32_t *basin_f, const float *var, int32_t nceldas,
+                        float *var_prop);
+
+/* -------------------------------------------------------- Path B: `models` */
+/* Scalar switches = module `models` globals (modelosv2.f90:71-97) + shia_v1 sizes (:191-216). */
+typedef struct {
+    int32_t n_cel, n_reg, n_cont, n_conth;
+    float dt, dxp, retorno_gr, retorno_aq, storage_constant;
+    int32_t speed_type[3];
+    int32_t calc_niter;
+    int32_t sim_sediments, sim_slides;
+    int32_t show_storage, show_speed, show_mean_speed, show_mean_retorno, save_retorno;
+    /* sediments (modelosv2.f90:115-125, wmf.py:4046-4104) */
+    float sed_factor, wi[3], diametro[3];
+    /* slides (modelosv2.f90:135-150, wmf.py:4106-4163) */
+    int32_t sl_gullienogullie;
+    float sl_fs, sl_gammaw;
+    /* ensemble: number of members sharing topology, maps and rain (1 = the reference's single run) */
+    int32_t n_members;
+} wmf_shia_cfg;
+
+/* Arrays = module `models` allocatables (modelosv2.f90:53-113) in their f2py layouts. */
+typedef struct {
+    const int32_t *drena;     /* (N) drain ids = structure row 1 */
+    int32_t drena_stride;     /* 1, or 3 when `drena` points at a (3,N) structure table */
+    const int32_t *unit_type; /* (N) */
+    const float *hill_long, *hill_slope, *stream_long, *stream_slope, *elem_area; /* (N) */
+    const float *v_coef, *h_coef, *h_exp; /* (4,N) */
+    const float *max_capilar, *max_gravita, *max_aquifer; /* (N) */
+    const float *evpserie;    /* (n_reg) */
+    const float *storage;     /* (5,N) module Storage (used when stoin is NULL or stoin[0] <= 0) */
+    const int32_t *control, *control_h; /* (N), may be NULL */
+    const float *calib;       /* (11) ; ensembles: (n_members, 11) row-major */
+    const float *stoin;       /* (5,N) or NULL   -- shia_v1 optional StoIn   */
+    const float *hspeedin;    /* (4,N) or NULL   -- shia_v1 optional HspeedIn */
+    /* rainfall held in memory instead of the per-step direct-access read (modelosv2.f90:444-449):
+     * record r (1-based) at rain + (r-1)*N, int32 mm*1000; pos_evento(t)==1 means "dry step". */
+    const int32_t *rain;
+    int32_t n_records;
+    const int32_t *pos_evento; /* (n_reg) */
+    /* sediments */
+    const float *krus, *crus, *prus; /* (N) */
+    const float *parliac;            /* (3,N) */
+    const float *vd_init;            /* (3,N) or NULL: Vd carried over from a previous run (:1301-1304) */
+    /* slides */
+    const float *sl_zs, *sl_gammas, *sl_cohesion, *sl_frictionangle, *sl_radslope; /* (N) */
+} wmf_shia_inputs;
+
+/* Outputs.  Any pointer may be NULL (= not wanted).  Shapes as returned by f2py (modelsmodule.c:375-408).
+ * For ensembles (n_members = M > 1) q is (M, n_cont, n_reg) with the member slowest, stoout /
+ * hspeed_out are (M, 5|4, N); the remaining per-run outputs must be NULL. */
+typedef struct {
+    float *q;            /* (n_cont, n_reg) */
+    float *qsed;         /* (n_cont, 3, n_reg) */
+    float *hum, *st1, *st3; /* (n_conth, n_reg) */
+    float *balance;      /* (n_reg); accumulated in fp64 on the GPU, rounded once */
+    float *speed, *areacontrol; /* (n_cont, n_reg) */
+    float *stoout;       /* (5,N) */
+    float *hspeed_out;   /* (4,N) final horizontal speeds (feeds HspeedIn of the next run) */
+    float *mean_rain;    /* (n_reg)  module Mean_Rain */
+    float *acum_rain;    /* (N)      module Acum_rain */
+    float *mean_storage; /* (5,n_reg) when show_storage */
+    float *mean_speed;   /* (4,n_reg) when show_mean_speed */
+    float *mean_retorno; /* (n_reg)   when retorno_gr & show_mean_retorno */
+    float *retorned;     /* (N)       when retorno_gr */
+    float *vs, *vd, *vsc, *vdc; /* (3,N) sediments */
+    float *volero, *voldepo;    /* (N) */
+    float *erot, *dept;         /* (3) */
+    float *sl_zmin, *sl_zcrit, *sl_zmax, *sl_bo, *sl_riskvector, *sl_slideocurrence; /* (N) */
+    int32_t *sl_slideacumulate; /* (N) */
+    int32_t *sl_slidencelltime; /* (n_reg) */
+} wmf_shia_outputs;
+
+/* shia_v1, modelosv2.f90:191-869 (+ calc_speed :1278-1293, sed_* :1298-1608, slide_* :1613-1707). */
+int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *in, wmf_shia_outputs *out);
+
+/* Objective scores of an ensemble against one observed series: wmf.py:749-754 (__eval_nash__) and
+ * wmf.py:775-781 (__eval_q_pico__).  q: (M, n_cont, n_reg) as produced by wmf_shia_run, row = 0-based
+ * control row to score (wmf.py:875 uses Qsim[nodo]); scores: (M,2) = [nash, qpico]. */
+int wmf_eval_scores(wmf_ctx *ctx, const float *q, int32_t n_members, int32_t n_cont, int32_t n_reg,
+                    int32_t row, const float *qobs, float *scores);
+
+/* calc_speed, modelosv2.f90:1278-1293 (one evaluation on the device; mirrors the f2py export) */
+int wmf_calc_speed(wmf_ctx *ctx, float sm, float coef, float expo, float elem_long, float dt,
+                   int32_t calc_niter, float *speed_inout, float *area_out);
+
+/* time spent inside the last wmf_shia_run between its first and last kernel, CUDA events, ms */
+int wmf_last_kernel_ms(wmf_ctx *ctx, float *ms);
+/* topology statistics of the last wmf_shia_run: levels (tree depth+1) and waves launched */
+int wmf_last_shia_stats(wmf_ctx *ctx, int32_t *n_levels, int32_t *n_waves);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WMF_B200_H */

@@ -87,8 +87,9 @@ class ShiaOut(C.Structure):
         ("stoout", f32p), ("hspeed_out", f32p), ("mean_rain", f32p), ("acum_rain", f32p),
         ("mean_storage", f32p), ("mean_speed", f32p), ("mean_retorno", f32p), ("retorned", f32p),
         ("mean_vfluxes", f32p), ("rc_coef", f32p),
+        ("mean_storage64", f64p), ("mean_speed64", f64p), ("mean_retorno64", f64p),
         ("vs", f32p), ("vd", f32p), ("vsc", f32p), ("vdc", f32p), ("volero", f32p), ("voldepo", f32p),
-        ("erot", f32p), ("dept", f32p),
+        ("erot", f32p), ("dept", f32p), ("erot64", f64p), ("dept64", f64p),
         ("sl_zmin", f32p), ("sl_zcrit", f32p), ("sl_zmax", f32p), ("sl_bo", f32p),
         ("sl_riskvector", f32p), ("sl_slideocurrence", f32p),
         ("sl_slideacumulate", i32p), ("sl_slidencelltime", i32p),
@@ -417,6 +418,9 @@ def shia_v1(inp: dict, fast: bool = False) -> dict:
     out("retorned", (N,))
     out("mean_vfluxes", (4, T))
     out("rc_coef", (2, N))
+    out("mean_storage64", (5, T), np.float64, f64p)
+    out("mean_speed64", (4, T), np.float64, f64p)
+    out("mean_retorno64", (T,), np.float64, f64p)
     if sed:
         for k in ("vs", "vd", "vsc", "vdc"):
             out(k, (3, N))
@@ -424,6 +428,8 @@ def shia_v1(inp: dict, fast: bool = False) -> dict:
         out("voldepo", (N,))
         out("erot", (3,))
         out("dept", (3,))
+        out("erot64", (3,), np.float64, f64p)
+        out("dept64", (3,), np.float64, f64p)
     if sl:
         for k in ("sl_zmin", "sl_zcrit", "sl_zmax", "sl_bo", "sl_riskvector", "sl_slideocurrence"):
             out(k, (N,))

@@ -128,10 +128,14 @@ typedef struct {
     float *retorned;    /* (N) or NULL */
     float *mean_vfluxes;/* (4,n_reg) or NULL */
     float *rc_coef;     /* (2,N) or NULL */
+    /* fp64-accumulated twins of the three per-step means (diagnostic, may be NULL): the reference's
+       sequential fp32 sums carry an error of order N*eps, these do not */
+    double *mean_storage64, *mean_speed64, *mean_retorno64;
     /* sediments */
     float *vs, *vd, *vsc, *vdc; /* (3,N) */
     float *volero, *voldepo;    /* (N) */
     float *erot, *dept;         /* (3) */
+    double *erot64, *dept64;    /* (3) fp64-accumulated twins (diagnostic, may be NULL) */
     /* slides */
     float *sl_zmin, *sl_zcrit, *sl_zmax, *sl_bo, *sl_riskvector, *sl_slideocurrence; /* (N) */
     int32_t *sl_slideacumulate; /* (N) */

@@ -49,6 +49,7 @@ typedef struct {
     float qlin_sed;
     float DEP[3];
     float EROt[3], DEPt[3];
+    double EROt64[3], DEPt64[3];
 } sed_state;
 
 /* modelosv2.f90:1321-1428 ; celda, drena_id 0-based (drena_id == n_cel means "outside") */
@@ -115,7 +116,10 @@ static void sed_hillslope(sed_state *S, float alfa, float v2, float S2, float So
             }
         }
     }
-    for (int i = 0; i < 3; ++i) S->DEPt[i] = S->DEPt[i] + S->DEP[i];
+    for (int i = 0; i < 3; ++i) {
+        S->DEPt[i] = S->DEPt[i] + S->DEP[i];
+        S->DEPt64[i] += (double)S->DEP[i];
+    }
     float REScap = fmaxf(0.0f, totXSScap - qsBMtot);
     if (REScap > 0.0f) {
         for (int i = 0; i < 3; ++i) {
@@ -128,7 +132,10 @@ static void sed_hillslope(sed_state *S, float alfa, float v2, float S2, float So
             }
         }
     }
-    for (int i = 0; i < 3; ++i) S->EROt[i] = S->EROt[i] + qsERO[i];
+    for (int i = 0; i < 3; ++i) {
+        S->EROt[i] = S->EROt[i] + qsERO[i];
+        S->EROt64[i] += (double)qsERO[i];
+    }
     o->volero[celda] = o->volero[celda] + ((qsERO[0] + qsERO[1]) + qsERO[2]);
     o->voldepo[celda] = o->voldepo[celda] + ((S->DEP[0] + S->DEP[1]) + S->DEP[2]);
     (void)qsEROtot;
@@ -493,15 +500,28 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
                 float s = 0.0f;
                 for (int32_t i = 0; i < N; ++i) s += A5(Sto, k, i);
                 out->mean_storage[5 * (size_t)t + k] = s / (float)N;
+                if (out->mean_storage64) {
+                    double sd = 0.0;
+                    for (int32_t i = 0; i < N; ++i) sd += (double)A5(Sto, k, i);
+                    out->mean_storage64[5 * (size_t)t + k] = sd / (double)N;
+                }
             }
         if (in->show_mean_speed == 1 && out->mean_speed)
             for (int k = 0; k < 4; ++k) {
                 float s = 0.0f;
                 for (int32_t i = 0; i < N; ++i) s += A4(hspeed, k, i);
                 out->mean_speed[4 * (size_t)t + k] = s / (float)N;
+                if (out->mean_speed64) {
+                    double sd = 0.0;
+                    for (int32_t i = 0; i < N; ++i) sd += (double)A4(hspeed, k, i);
+                    out->mean_speed64[4 * (size_t)t + k] = sd / (double)N;
+                }
             }
         if (in->retorno_gr == 1.0f && in->show_mean_retorno == 1 && out->mean_retorno && out->retorned)
+        {
             out->mean_retorno[t] = sum_f(out->retorned, (size_t)N) / (float)N;
+            if (out->mean_retorno64) out->mean_retorno64[t] = sum_d(out->retorned, (size_t)N) / (double)N;
+        }
         if ((in->show_mean_retorno == 1 || in->save_retorno == 1) && out->retorned && in->retorno_gr == 1.0f)
             for (int32_t i = 0; i < N; ++i) out->retorned[i] = 0.0f;
         out->balance[t] = sum_f(Sto, 5 * (size_t)N) - StoAtras - entradas + salidas;
@@ -518,6 +538,8 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
     if (in->sim_sediments == 1) {
         if (out->erot) memcpy(out->erot, SS.EROt, sizeof SS.EROt);
         if (out->dept) memcpy(out->dept, SS.DEPt, sizeof SS.DEPt);
+        if (out->erot64) memcpy(out->erot64, SS.EROt64, sizeof SS.EROt64);
+        if (out->dept64) memcpy(out->dept64, SS.DEPt64, sizeof SS.DEPt64);
     }
     free(vspeed);
     free(H);

@@ -1,0 +1,110 @@
+"""CPU: the oracle's SHIA restatement against closed forms and physical invariants."""
+import numpy as np
+import pytest
+
+from conftest import basin_vectors, make_basin
+
+
+def one_cell(**kw):
+    """A single hillslope cell that is its own outlet."""
+    N, T = 1, 30
+    inp = dict(
+        drena=np.zeros((3, 1), np.int32), nceldas=1, n_reg=T, dt=3600.0, dxp=30.0, unit_type=np.ones((1, 1), np.int32),
+        hill_long=np.full((1, 1), 30.0, np.float32), hill_slope=np.full((1, 1), 0.1, np.float32),
+        stream_long=np.full((1, 1), 30.0, np.float32), stream_slope=np.full((1, 1), 0.1, np.float32),
+        elem_area=np.full((1, 1), 900.0, np.float32), speed_type=[1, 1, 1], calc_niter=5,
+        v_coef=np.zeros((4, 1), np.float32), h_coef=np.array([[0.01], [0.0], [0.0], [1.0]], np.float32),
+        h_exp=np.ones((4, 1), np.float32), max_capilar=np.full((1, 1), 50.0, np.float32),
+        max_gravita=np.full((1, 1), 100.0, np.float32), max_aquifer=np.full((1, 1), 1000.0, np.float32),
+        storage=np.array([[10.0], [8.0], [0.0], [0.0], [0.0]], np.float32), storage_constant=0.0,
+        evpserie=np.ones(T, np.float32), calib=np.ones(11, np.float32),
+        rain=np.zeros((1, 1), np.int32), pos_evento=np.ones(T, np.int32),
+    )
+    inp.update(kw)
+    return inp
+
+
+def test_linear_reservoir_closed_form():
+    """One hillslope cell, no rain, no vertical flow: S2(t) decays geometrically with ratio L/(v*dt+L)
+    (modelosv2.f90:558-559) and the outlet record is Q = hflux*m3_mm (:610, not divided by dt)."""
+    import oracle
+    inp = one_cell()
+    out = oracle.shia_v1(inp)
+    L, v, dt = np.float32(30.0), np.float32(0.01), np.float32(3600.0)
+    r = np.float32(1.0) - L / (v * dt + L)
+    s2, q = np.float32(8.0), []
+    for _ in range(30):
+        h = r * s2
+        s2 = s2 - h
+        q.append(h * np.float32(0.9))
+    np.testing.assert_array_equal(out["q"][0], np.array(q, np.float32))
+    assert out["stoout"][1, 0] == s2
+    assert out["stoout"][0, 0] == np.float32(10.0)          # v_coef = 0: no evaporation, no percolation
+    ratio = float(L / (v * dt + L))
+    np.testing.assert_allclose(out["q"][0][1:] / out["q"][0][:-1], ratio, rtol=1e-6)
+
+
+def test_vertical_cascade_by_hand():
+    """One step with rain: overflow of tank 1, evaporation with the 0.6 power, percolation caps (:478-494)."""
+    import math
+    import oracle
+    inp = one_cell(n_reg=1, evpserie=np.ones(1, np.float32), pos_evento=np.array([2], np.int32),
+                   rain=np.array([[0], [60000]], np.int32),
+                   v_coef=np.array([[1e-4], [2e-3], [1e-3], [0.0]], np.float32))
+    out = oracle.shia_v1(inp)
+    f = np.float32
+    R, H1, S1 = f(60.0), f(50.0), f(10.0)
+    vf1 = max(f(0), R - H1 + S1)                           # 20
+    S1 = S1 + R - vf1                                      # 50
+    E = min(f(1.0) * (f(1e-4) * f(1.0) * f(3600.0)) * f(math.pow(float(S1 / H1), 0.6)), S1)
+    S1 = S1 - E
+    vs2, vs3 = f(2e-3) * f(1) * f(3600), f(1e-3) * f(1) * f(3600)
+    vf2 = min(vf1, vs2)
+    vf3 = min(vf2, vs3)
+    assert out["stoout"][0, 0] == pytest.approx(float(S1), rel=1e-7)
+    S2 = f(8.0) + vf1 - vf2
+    S2 = S2 - (f(1.0) - f(30.0) / (f(0.01) * f(3600.0) + f(30.0))) * S2
+    assert out["stoout"][1, 0] == pytest.approx(float(S2), rel=1e-6)
+    assert out["stoout"][2, 0] == pytest.approx(float(vf2 - vf3), rel=1e-6)
+    assert out["stoout"][3, 0] == pytest.approx(float(vf3), rel=1e-6)      # vspeed4 = 0 -> everything stays in tank 4
+    assert out["mean_rain"][0] == 60.0 and out["acum_rain"][0] == 60.0
+
+
+def test_calc_speed_fixed_point():
+    import oracle
+    area, v = oracle.calc_speed(50.0, 1.2, 0.32, 30.0, 0.0, dt=3600.0, calc_niter=50)
+    assert v == pytest.approx(1.2 * area ** 0.32, rel=1e-4)            # converged: v = coef * A**expo
+    assert area == pytest.approx(50.0 / (30.0 + v * 3600.0), rel=1e-4)
+    a5, v5 = oracle.calc_speed(50.0, 1.2, 0.32, 30.0, 0.0, dt=3600.0, calc_niter=5)
+    assert v5 > 0 and a5 > 0
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(speed_type=(2, 2, 1), retorno_gr=1, retorno_aq=1),
+                                dict(speed_type=(2, 2, 1), sediments=True, slides=True)])
+def test_mass_balance_and_positivity(kw):
+    """|balance(t)| <= eps * sum(StoOut) every step when accumulated in fp64 (modelosv2.f90:846); storages >= 0."""
+    import oracle
+    from wmf_b200 import synth
+    bs = make_basin("G2", 70, 60, 1)
+    v = basin_vectors(bs)
+    inp = synth.make_shia_inputs(bs["basin"], v["acum"], v["lng"], v["pend"], dxp=30.0, n_reg=80, seed=1, **kw)
+    out = oracle.shia_v1(inp)
+    tot = float(out["stoout"].sum())
+    assert np.abs(out["balance64"]).max() <= 2e-6 * tot
+    assert out["stoout"].min() >= 0 and np.isfinite(out["q"]).all() and out["q"][0].max() > 0
+    # global water budget over the run: rain in = storage change + outflow + evaporation/losses (all inside balance)
+    assert abs(out["balance64"].sum()) <= 1e-5 * tot
+    if kw.get("sediments"):
+        assert out["qsed"].max() > 0 and out["vd"].min() >= 0
+    if kw.get("slides"):
+        assert set(np.unique(out["sl_riskvector"])) <= {0.0, 1.0, 2.0}
+        assert out["sl_slidencelltime"].sum() >= np.count_nonzero(out["sl_slideocurrence"] == 1)
+
+
+def test_zero_rain_record_shortcut():
+    """posEvento == 1 means Rain = 0 whatever record 1 holds (modelosv2.f90:444-445)."""
+    import oracle
+    inp = one_cell(n_reg=3, evpserie=np.ones(3, np.float32), pos_evento=np.array([1, 1, 1], np.int32),
+                   rain=np.array([[777000]], np.int32))
+    out = oracle.shia_v1(inp)
+    assert out["mean_rain"].max() == 0.0 and out["acum_rain"][0] == 0.0

@@ -1,0 +1,432 @@
+"""`models` -- host-side mirror of the reference's f2py module object ``models`` (wmf/modelosv2.f90).
+
+Semantics kept from f2py:
+  * attribute names are lower-case (``models.max_capilar``, ``models.evpserie``);
+  * assigning an array *copies and casts* it into a persistent Fortran-ordered buffer
+    (``models.control = np.zeros((1,N))`` becomes int32, wmf.py:3045);
+  * reading an attribute returns that same buffer, so ``models.h_coef[pos] = vec``
+    (wmf.py:3882) and ``models.storage[p] = vec`` (wmf.py:3952) mutate module state in place;
+  * ``shia_v1`` has the reference's positional signature and 11-tuple return
+    (modelsmodule.c:375-408), called positionally from ``SimuBasin.run_shia`` (wmf.py:4512-4531).
+
+The time loop itself runs in libwmf_b200.so (``wmf_shia_run``).  The rainfall ``.bin/.hdr`` pair
+is parsed here (formats: modelosv2.f90:911-926, 966-1002; writer wmf.py:3349-3362) and handed to
+the kernels in memory; ``set_rain`` supplies it without touching the file system.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import ShiaCfg, ShiaInputs, ShiaOutputs, is_torch_cuda, ptr
+
+# name -> (dtype, leading dimension K of the (K,N) array; 0 = 1-D)
+_ARRAYS = {
+    "drena": (np.int32, 3), "unit_type": (np.int32, 1),
+    "hill_long": (np.float32, 1), "hill_slope": (np.float32, 1), "stream_long": (np.float32, 1),
+    "stream_slope": (np.float32, 1), "stream_width": (np.float32, 1), "elem_area": (np.float32, 1),
+    "v_coef": (np.float32, 4), "v_exp": (np.float32, 4), "h_coef": (np.float32, 4), "h_exp": (np.float32, 4),
+    "max_capilar": (np.float32, 1), "max_gravita": (np.float32, 1), "max_aquifer": (np.float32, 1),
+    "storage": (np.float32, 5), "control": (np.int32, 1), "control_h": (np.int32, 1),
+    "evpserie": (np.float32, 0), "guarda_cond": (np.int32, 0), "guarda_vfluxes": (np.int32, 0),
+    "krus": (np.float32, 1), "crus": (np.float32, 1), "prus": (np.float32, 1), "parliac": (np.float32, 3),
+    "vd": (np.float32, 3), "vs": (np.float32, 3), "vsc": (np.float32, 3), "vdc": (np.float32, 3),
+    "sl_zs": (np.float32, 1), "sl_gammas": (np.float32, 1), "sl_cohesion": (np.float32, 1),
+    "sl_frictionangle": (np.float32, 1), "sl_radslope": (np.float32, 1),
+    "speed_type": (np.int32, 0), "wi": (np.float32, 0), "diametro": (np.float32, 0),
+}
+_SCALARS_F = {"dt": 60.0, "dxp": 1.0, "retorno_gr": 0.0, "retorno_aq": 0.0, "storage_constant": 0.0,
+              "sed_factor": 1.0, "sl_fs": 1.0, "sl_gammaw": 9.8, "xll": 0.0, "yll": 0.0, "nodata": -9999.0, "dx": 1.0}
+_SCALARS_I = {"nceldas": 0, "ncols": 0, "nrows": 0, "verbose": 0, "rain_first_point": 1, "calc_niter": 5,
+              "sim_sediments": 0, "sim_slides": 0, "sim_floods": 0, "save_storage": 0, "save_speed": 0,
+              "save_retorno": 0, "save_vfluxes": 0, "save_rc": 0, "show_storage": 0, "show_speed": 0,
+              "show_mean_speed": 0, "show_mean_retorno": 0, "show_area": 0, "separate_fluxes": 0,
+              "separate_rain": 0, "sl_gullienogullie": 0}
+# switches whose sub-models are outside the hot path built here
+_UNSUPPORTED = ("sim_floods", "save_storage", "save_speed", "save_retorno", "save_vfluxes", "save_rc",
+                "separate_fluxes", "separate_rain")
+
+
+def read_rain_hdr(ruta_hdr: str, n_reg: int, rain_first_point: int = 1):
+    """rain_read_ascii_table, modelosv2.f90:966-1002 -> (idEvento, posEvento)."""
+    with open(ruta_hdr) as f:
+        lines = f.read().splitlines()
+    ntotal = int(lines[2].replace(":", " ").split()[-1])
+    if n_reg + rain_first_point > ntotal + 1:
+        raise ValueError(f"rain header {ruta_hdr}: {n_reg} intervals from point {rain_first_point} exceed {ntotal} records")
+    body = lines[6:]
+    if rain_first_point > 1:          # the Fortran skips rain_first_point lines, not rain_first_point-1 (:989-993)
+        body = body[rain_first_point:]
+    ids, pos = [], []
+    for ln in body[:n_reg]:
+        parts = ln.replace("\t", " ").split(",")
+        ids.append(int(parts[0]))
+        pos.append(int(parts[1]))
+    if len(pos) < n_reg:
+        raise ValueError(f"rain header {ruta_hdr}: only {len(pos)} rows for {n_reg} intervals")
+    return np.array(ids, np.int32), np.array(pos, np.int32)
+
+
+def read_int_basin(ruta: str, record: int, n_cel: int):
+    """vect,res = read_int_basin(ruta,record,n_cel)   -- modelosv2.f90:911-926 (direct access, RECL=4*N)."""
+    try:
+        with open(ruta, "rb") as f:
+            f.seek(4 * n_cel * (int(record) - 1))
+            v = np.fromfile(f, dtype=np.int32, count=n_cel)
+        return (v, 0) if v.size == n_cel else (np.zeros(n_cel, np.int32), 1)
+    except OSError:
+        return np.zeros(n_cel, np.int32), 1
+
+
+def read_float_basin_ncol(ruta: str, record: int, n_cel: int, n_col: int):
+    """vect,res = read_float_basin_ncol(ruta,record,n_cel,n_col)   -- modelosv2.f90:893-909."""
+    try:
+        with open(ruta, "rb") as f:
+            f.seek(4 * n_cel * n_col * (int(record) - 1))
+            v = np.fromfile(f, dtype=np.float32, count=n_cel * n_col)
+        if v.size != n_cel * n_col:
+            return np.zeros((n_col, n_cel), np.float32, order="F"), 1
+        return np.asfortranarray(v.reshape((n_col, n_cel), order="F")), 0
+    except OSError:
+        return np.zeros((n_col, n_cel), np.float32, order="F"), 1
+
+
+def write_int_basin(ruta: str, vect, record: int, n_cel=None, n_col=None):
+    """write_int_basin(ruta,vect,record,[n_cel,n_col])   -- modelosv2.f90:945-959."""
+    a = np.asfortranarray(vect, dtype=np.int32)
+    mode = "wb" if int(record) == 1 or not os.path.exists(ruta) else "r+b"
+    with open(ruta, mode) as f:
+        f.seek(4 * a.size * (int(record) - 1))
+        f.write(a.tobytes(order="F"))
+
+
+def write_float_basin(ruta: str, vect, record: int, n_cel=None, n_col=None):
+    """write_float_basin(ruta,vect,record,[n_cel,n_col])   -- modelosv2.f90:928-944 (record <= 0 writes nothing)."""
+    if int(record) <= 0:
+        return
+    a = np.asfortranarray(vect, dtype=np.float32)
+    mode = "wb" if int(record) == 1 or not os.path.exists(ruta) else "r+b"
+    with open(ruta, mode) as f:
+        f.seek(4 * a.size * (int(record) - 1))
+        f.write(a.tobytes(order="F"))
+
+
+def write_rain_files(path_bin: str, path_hdr: str, rain, pos_evento, dates=None, n_hills=0):
+    """Write a rain ``.bin``/``.hdr`` pair in the reference's format (wmf.py:3349-3362): direct-access records
+    of N int32 (mm*1000), record 1 all zeros; six header lines then ``id, record, mean, date`` rows."""
+    rain = np.ascontiguousarray(rain, dtype=np.int32)
+    pos = np.asarray(pos_evento, dtype=np.int64)
+    with open(path_bin, "wb") as f:
+        f.write(rain.tobytes())
+    with open(path_hdr, "w") as f:
+        f.write("Numero de celdas: %d \n" % rain.shape[1])
+        f.write("Numero de laderas: %d \n" % n_hills)
+        f.write("Numero de registros: %d \n" % pos.size)
+        f.write("Numero de campos no cero: %d \n" % pos.max())
+        f.write("Tipo de interpolacion: TIN\n")
+        f.write("IDfecha, Record, Lluvia, Fecha \n")
+        for c, p in enumerate(pos):
+            mean = rain[p - 1].mean() / 1000.0
+            d = dates[c] if dates is not None else "2000-01-01-00:00"
+            f.write("%d, \t %d, \t %.2f, %s \n" % (c + 1, p, mean, d))
+
+
+class ModelsModule:
+    """Drop-in for the Fortran module object ``models``."""
+
+    def __init__(self, ctx: _lib.Context | None = None):
+        d = object.__getattribute__(self, "__dict__")
+        d["_ctx"] = ctx
+        d["_a"] = {}                       # persistent arrays
+        d["_s"] = dict(_SCALARS_F)
+        d["_s"].update(_SCALARS_I)
+        d["_rain_mem"] = None
+        d["_a"]["speed_type"] = np.ones(3, np.int32)
+        d["_a"]["wi"] = np.zeros(3, np.float32)
+        d["_a"]["diametro"] = np.zeros(3, np.float32)
+
+    # ---- f2py attribute semantics ------------------------------------------------------------
+    def __getattr__(self, name):
+        d = object.__getattribute__(self, "__dict__")
+        if name in d["_a"]:
+            return d["_a"][name]
+        if name in d["_s"]:
+            v = d["_s"][name]
+            return np.int32(v) if name in _SCALARS_I else np.float32(v)
+        if name in _ARRAYS:
+            return None                    # f2py: unallocated allocatable reads as None
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        d = object.__getattribute__(self, "__dict__")
+        if name in _ARRAYS:
+            dtype, K = _ARRAYS[name]
+            if value is None:
+                d["_a"].pop(name, None)
+                return
+            arr = np.array(value, dtype=dtype, order="F", copy=True)
+            if K == 0:
+                arr = arr.reshape(-1)
+                if name in ("speed_type", "wi", "diametro") and arr.size != 3:
+                    raise ValueError(f"models.{name} has 3 elements")
+            else:
+                if arr.ndim == 1:
+                    arr = np.asfortranarray(arr.reshape(1, -1))
+                if arr.ndim != 2:
+                    raise ValueError(f"models.{name} must be a rank-2 array")
+            d["_a"][name] = arr
+        elif name in _SCALARS_I:
+            d["_s"][name] = int(value)
+        elif name in _SCALARS_F:
+            d["_s"][name] = float(np.float32(value))
+        else:
+            d[name] = value
+
+    @property
+    def ctx(self) -> _lib.Context:
+        d = object.__getattribute__(self, "__dict__")
+        if d["_ctx"] is None:
+            d["_ctx"] = _lib.default_context()
+        return d["_ctx"]
+
+    # ---- helpers kept from the f2py export list ----------------------------------------------------
+    read_int_basin = staticmethod(read_int_basin)
+    read_float_basin_ncol = staticmethod(read_float_basin_ncol)
+    write_int_basin = staticmethod(write_int_basin)
+    write_float_basin = staticmethod(write_float_basin)
+
+    def calc_speed(self, sm, coef, expo, elem_long, speed):
+        """area = calc_speed(sm,coef,expo,elem_long,speed)   -- modelosv2.f90:1278-1293.
+        f2py returns only ``area`` (speed is intent(inout) on a scalar); both are returned here."""
+        c = self.ctx
+        s, a = C.c_float(float(speed)), C.c_float()
+        c.check(c.L.wmf_calc_speed(c.h, float(sm), float(coef), float(expo), float(elem_long), float(self.dt),
+                                   int(self.calc_niter), C.byref(s), C.byref(a)))
+        return a.value, s.value
+
+    def set_rain(self, rain, pos_evento):
+        """Extension: hold the rainfall in memory instead of the ``.bin/.hdr`` pair.  ``rain`` is
+        (n_records,N) int32 mm*1000 (numpy or torch CUDA), record 1 must be the all-zero record,
+        ``pos_evento`` (n_reg) 1-based.  ``shia_v1(None, None, ...)`` then uses it."""
+        object.__getattribute__(self, "__dict__")["_rain_mem"] = (rain, np.ascontiguousarray(pos_evento, np.int32))
+
+    def make_resident(self, enable: bool = True):
+        """Extension: upload every allocated module array to the GPU once (torch owns the buffers) so that repeated
+        runs -- calibration ensembles, benchmarks -- read their static maps in place.  Call again after changing an
+        array; ``make_resident(False)`` drops the device copies."""
+        d = object.__getattribute__(self, "__dict__")
+        if not enable:
+            d["_dev"] = {}
+            return
+        import torch
+        dev = {}
+        for name, arr in d["_a"].items():
+            if isinstance(arr, np.ndarray) and arr.size:
+                flat = np.ascontiguousarray(arr.ravel(order="F"))
+                dev[id(arr)] = torch.from_numpy(flat).to(f"cuda:{self.ctx.device}")
+        d["_dev"] = dev
+
+    def _load_rain(self, ruta_bin, ruta_hdr, n_reg, n_cel):
+        d = object.__getattribute__(self, "__dict__")
+        if ruta_bin is None and d["_rain_mem"] is not None:
+            rain, pos = d["_rain_mem"]
+            if pos.size < n_reg:
+                raise ValueError("set_rain: pos_evento shorter than n_reg")
+            return rain, pos[:n_reg].copy()
+        ruta_bin, ruta_hdr = str(ruta_bin).strip(), str(ruta_hdr).strip()
+        _, pos = read_rain_hdr(ruta_hdr, n_reg, int(self.rain_first_point))
+        uniq = np.unique(pos[pos != 1])
+        table = np.zeros((uniq.size + 1, n_cel), np.int32)       # row 0 = the dry record
+        with open(ruta_bin, "rb") as f:
+            for k, r in enumerate(uniq):
+                f.seek(4 * n_cel * (int(r) - 1))
+                rec = np.fromfile(f, dtype=np.int32, count=n_cel)
+                if rec.size != n_cel:
+                    raise ValueError(f"rain binary {ruta_bin}: record {r} is out of range")
+                table[k + 1] = rec
+        remap = np.ones(n_reg, np.int32)
+        wet = pos != 1
+        remap[wet] = (np.searchsorted(uniq, pos[wet]) + 2).astype(np.int32)
+        return table, remap
+
+    # ---- the model ------------------------------------------------------------------------------
+    def shia_v1(self, ruta_bin, ruta_hdr, calib, n_cont, n_conth, n_reg, stoin=None, hspeedin=None, n_cel=None,
+                ruta_storage=None, ruta_speed=None, ruta_vfluxes=None, ruta_binconv=None, ruta_binstra=None,
+                ruta_hdrconv=None, ruta_hdrstra=None, ruta_retorno=None, ruta_rc=None):
+        """q,qsed,qseparated,hum,st1,st3,balance,speed,areacontrol,stoout,qsep_byrain =
+        shia_v1(ruta_bin,ruta_hdr,calib,n_cont,n_conth,n_reg,[stoin,hspeedin,n_cel,...])
+        -- modelosv2.f90:191-869, f2py signature modelsmodule.c:375-408."""
+        for k in _UNSUPPORTED:
+            if int(getattr(self, k)) == 1:
+                raise NotImplementedError(f"models.{k} = 1 selects a sub-model that is outside the B200 hot path "
+                                          "(SURVEY.md 8f); set it to 0")
+        a = object.__getattribute__(self, "__dict__")["_a"]
+        if "drena" not in a:
+            raise ValueError("models.drena is not allocated")
+        N = int(n_cel) if n_cel is not None else a["drena"].shape[1]
+        if a["drena"].shape[1] != N:
+            raise ValueError(f"n_cel={N} but models.drena has {a['drena'].shape[1]} cells")
+        T = int(n_reg)
+        calib = np.ascontiguousarray(np.asarray(calib, dtype=np.float32).reshape(-1))
+        if calib.size != 11:
+            raise ValueError("calib must have 11 elements (modelosv2.f90:201)")
+        rain, pos = self._load_rain(ruta_bin, ruta_hdr, T, N)
+        out = self._run(calib[None, :], int(n_cont), int(n_conth), T, rain, pos, stoin, hspeedin)
+        nc, nh = int(n_cont), int(n_conth)
+        zeros = lambda *s: np.zeros(s, np.float32, order="F")
+        qsed = out.get("qsed", zeros(nc, 3, T))
+        return (out["q"], qsed, zeros(nc, 3, T), out["hum"], out["st1"], out["st3"], out["balance"], out["speed"],
+                out["areacontrol"], out["stoout"], zeros(nc, 2, T))
+
+    def _cell(self, name, K, N, dtype, required=True):
+        a = object.__getattribute__(self, "__dict__")["_a"]
+        if name not in a:
+            if required:
+                raise ValueError(f"models.{name} is not allocated")
+            return None
+        arr = a[name]
+        if arr.shape != (K, N):
+            raise ValueError(f"models.{name} has shape {arr.shape}, expected ({K},{N})")
+        return arr
+
+    def _run(self, calibs, n_cont, n_conth, T, rain, pos, stoin=None, hspeedin=None, device_out=False, want=None):
+        """Marshal module state into one wmf_shia_run call.  ``calibs`` is (M,11)."""
+        c = self.ctx
+        a = object.__getattribute__(self, "__dict__")["_a"]
+        N = a["drena"].shape[1]
+        M = calibs.shape[0]
+        cfg = ShiaCfg()
+        cfg.n_cel, cfg.n_reg, cfg.n_cont, cfg.n_conth = N, T, n_cont, n_conth
+        cfg.dt, cfg.dxp = float(self.dt), float(self.dxp)
+        cfg.retorno_gr, cfg.retorno_aq = float(self.retorno_gr), float(self.retorno_aq)
+        cfg.storage_constant = float(self.storage_constant)
+        cfg.speed_type = (C.c_int32 * 3)(*[int(v) for v in a["speed_type"]])
+        cfg.calc_niter = int(self.calc_niter)
+        for k in ("sim_sediments", "sim_slides", "show_storage", "show_speed", "show_mean_speed",
+                  "show_mean_retorno", "save_retorno", "sl_gullienogullie"):
+            setattr(cfg, k, int(getattr(self, k)))
+        cfg.sed_factor = float(self.sed_factor)
+        cfg.wi = (C.c_float * 3)(*[float(v) for v in a["wi"]])
+        cfg.diametro = (C.c_float * 3)(*[float(v) for v in a["diametro"]])
+        cfg.sl_fs, cfg.sl_gammaw = float(self.sl_fs), float(self.sl_gammaw)
+        cfg.n_members = M
+        keep = []
+        si = ShiaInputs()
+
+        dev = object.__getattribute__(self, "__dict__").get("_dev") or {}
+
+        def put(field, arr):
+            # a device-resident copy made by make_resident() is used in place (no host->device traffic)
+            if arr is not None and id(arr) in dev:
+                arr = dev[id(arr)]
+            keep.append(arr)
+            setattr(si, field, ptr(arr))
+
+        put("drena", self._cell("drena", 3, N, np.int32))
+        si.drena_stride = 3
+        put("unit_type", self._cell("unit_type", 1, N, np.int32))
+        for k in ("hill_long", "stream_long", "elem_area", "max_capilar", "max_gravita", "max_aquifer"):
+            put(k, self._cell(k, 1, N, np.float32))
+        for k in ("hill_slope", "stream_slope"):
+            put(k, self._cell(k, 1, N, np.float32, required=False))
+        for k in ("v_coef", "h_coef", "h_exp"):
+            put(k, self._cell(k, 4, N, np.float32))
+        put("storage", self._cell("storage", 5, N, np.float32))
+        put("control", self._cell("control", 1, N, np.int32, required=False))
+        put("control_h", self._cell("control_h", 1, N, np.int32, required=False))
+        evp = a.get("evpserie")
+        if evp is None or evp.size < T:
+            raise ValueError("models.evpserie must hold n_reg values (wmf.py:4487-4490)")
+        put("evpserie", np.ascontiguousarray(evp[:T], np.float32))
+        put("calib", np.ascontiguousarray(calibs, np.float32))
+        if stoin is not None:
+            s = np.asfortranarray(stoin, dtype=np.float32)
+            if s.shape != (5, N):
+                raise ValueError(f"stoin must be (5,{N})")
+            put("stoin", s)
+        if hspeedin is not None:
+            h = np.asfortranarray(hspeedin, dtype=np.float32)
+            if h.shape != (4, N):
+                raise ValueError(f"hspeedin must be (4,{N})")
+            put("hspeedin", h)
+        if is_torch_cuda(rain):
+            assert rain.dim() == 2 and rain.shape[1] == N and rain.is_contiguous()
+            n_records = rain.shape[0]
+        else:
+            rain = np.ascontiguousarray(rain, dtype=np.int32)
+            if rain.ndim != 2 or rain.shape[1] != N:
+                raise ValueError(f"rain table must be (n_records,{N})")
+            n_records = rain.shape[0]
+        put("rain", rain)
+        si.n_records = int(n_records)
+        put("pos_evento", np.ascontiguousarray(pos, np.int32))
+        sed, sl = cfg.sim_sediments == 1, cfg.sim_slides == 1
+        if sed:
+            for k in ("krus", "crus", "prus"):
+                put(k, self._cell(k, 1, N, np.float32))
+            put("parliac", self._cell("parliac", 3, N, np.float32))
+            if "vd" in a and not getattr(self, "_reset_vd", False):
+                put("vd_init", self._cell("vd", 3, N, np.float32))
+        if sl:
+            for k in ("sl_zs", "sl_gammas", "sl_cohesion", "sl_frictionangle", "sl_radslope"):
+                put(k, self._cell(k, 1, N, np.float32))
+
+        so = ShiaOutputs()
+        res = {}
+
+        def out(name, shape, dtype=np.float32):
+            if want is not None and name not in want:
+                return
+            if device_out:
+                import torch
+                tdt = torch.float32 if dtype == np.float32 else torch.int32
+                arr = torch.empty(tuple(reversed(shape)), dtype=tdt, device=f"cuda:{c.device}")
+            else:
+                arr = np.empty(shape, dtype=dtype, order="F")
+            res[name] = arr
+            setattr(so, name, ptr(arr))
+
+        if M == 1:
+            out("q", (n_cont, T)); out("hum", (n_conth, T)); out("st1", (n_conth, T)); out("st3", (n_conth, T))
+            out("balance", (T,)); out("speed", (n_cont, T)); out("areacontrol", (n_cont, T))
+            out("stoout", (5, N)); out("hspeed_out", (4, N)); out("mean_rain", (1, T)); out("acum_rain", (1, N))
+            if cfg.show_storage:
+                out("mean_storage", (5, T))
+            if cfg.show_mean_speed:
+                out("mean_speed", (4, T))
+            if cfg.retorno_gr == 1.0:
+                out("retorned", (1, N))
+                if cfg.show_mean_retorno:
+                    out("mean_retorno", (T,))
+            if sed:
+                out("qsed", (n_cont, 3, T))
+                for k in ("vs", "vd", "vsc", "vdc"):
+                    out(k, (3, N))
+                out("volero", (N,)); out("voldepo", (N,)); out("erot", (3,)); out("dept", (3,))
+            if sl:
+                for k in ("sl_zmin", "sl_zcrit", "sl_zmax", "sl_bo", "sl_riskvector", "sl_slideocurrence"):
+                    out(k, (1, N))
+                out("sl_slideacumulate", (1, N), np.int32)
+                out("sl_slidencelltime", (T,), np.int32)
+        else:
+            out("q", (n_cont, T, M))
+            out("stoout", (5, N, M))
+            out("hspeed_out", (4, N, M))
+        c.check(c.L.wmf_shia_run(c.h, C.byref(cfg), C.byref(si), C.byref(so)))
+        # module-global results the reference leaves behind (read back at wmf.py:4548-4601)
+        if M == 1 and not device_out:
+            d = object.__getattribute__(self, "__dict__")
+            for k in ("mean_rain", "acum_rain", "mean_storage", "mean_speed", "mean_retorno", "retorned", "vs", "vd",
+                      "vsc", "vdc", "volero", "voldepo", "sl_zmin", "sl_zcrit", "sl_zmax", "sl_bo", "sl_riskvector",
+                      "sl_slideocurrence", "sl_slideacumulate", "sl_slidencelltime"):
+                if k in res:
+                    if k in _ARRAYS:
+                        d["_a"][k] = res[k]
+                    else:
+                        d[k] = res[k]
+            if "erot" in res:
+                d["erot"], d["dept"] = res["erot"], res["dept"]
+        return res

@@ -1,0 +1,1259 @@
+// shia.cu -- Path B: the SHIA/TETIS time loop (module `models`, wmf/modelosv2.f90:191-869) on sm_100a.
+//
+// Execution model: (level x time) skewed topological wavefront.
+//   Cells are bucketed by hop distance to the outlet ("level"; basin_find's ordering makes each level a
+//   contiguous index range and the children of a cell a contiguous index range).  Cell (level L, step t)
+//   depends only on its children at the same step (level L+1) and on itself at step t-1, so all (L,t) with
+//   t + (Lmax - L) == w are independent: wave w is ONE kernel launch over a contiguous cell range, and the
+//   whole run takes T + Lmax launches instead of T * Lmax barriers.
+//   Each thread owns one (cell, member): it gathers its children's outflows of the same step in ascending
+//   cell order (== the Fortran's sequential fp32 addition order, no atomics on water), runs the vertical
+//   tank cascade and the three hillslope outflows with the state in registers, solves the channel kinematic
+//   wave, and publishes its own outflow into a buffer double-buffered on the step parity.
+// Memory: SoA, member-minor: state[tank][cell][member]; static maps are read in their f2py (K,N) layout,
+//   which is one aligned float4 per cell; rainfall records stay resident in HBM and are indexed per step.
+// Reductions (balance, means) are accumulated in fp64 per step slot.
+#include <limits.h>
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+constexpr int WAVE_THREADS = 256;
+constexpr int RED_SUB = 8;  // sub-slots per (step, quantity) to spread atomic traffic
+// reduction quantities per step
+enum { RQ_SAL = 0, RQ_STO1 = 1 /* ..5 */, RQ_SPD1 = 6 /* ..9 */, RQ_RET = 10, RQ_COUNT = 11 };
+
+constexpr uint32_t TW_CTRLQ = 1u << 6, TW_CTRLH = 1u << 7;
+
+struct ShiaP {
+    int N, T, M, Lmax, n_cont, n_conth;
+    float dt, dxp, retorno_gr, retorno_aq;
+    int st[3];
+    int niter;
+    int hs_state;  // HspeedIn supplied: linear tanks read their (constant) speed from the state array
+    int show_speed, show_storage, show_mean_speed, want_retorned, want_red;
+    // topology
+    const uint32_t *tw;   // level<<8 | ctrlH<<7 | ctrlQ<<6 | type<<4 | nchild
+    const int32_t *cs;    // first child
+    const int32_t *ctrl_cells, *ctrlh_cells;  // sorted cell ids of the control points
+    int n_ctrl, n_ctrlh;
+    // statics (f2py layouts)
+    const float *v_coef, *h_coef, *h_exp;  // (4,N): one float4 per cell
+    const float *max_capilar, *max_gravita, *max_aquifer, *hill_long, *hill_slope, *stream_long, *stream_slope,
+        *elem_area;
+    const float *evp;
+    const float *calib;  // (M,11)
+    const int32_t *rain;
+    const int32_t *pos;
+    // state (SoA member-minor)
+    float *sto;   // [5][N][M]
+    float *hsp;   // [4][N][M]
+    float *outb;  // [2][4][N][M]
+    float *retorned;  // [N] (M==1)
+    // outputs
+    float *q, *speed, *area, *hum, *st1o, *st3o, *qsed;
+    double *red;  // [T][RQ_COUNT][RED_SUB]
+    // sediments
+    float sed_factor, wi[3], diam[3];
+    const float *krus, *crus, *prus, *parliac;  // parliac (3,N)
+    float *sed;      // [12][N][M]: Vs(3) Vd(3) Vsc(3) Vdc(3)
+    float *sedout;   // [2][12][N][M]: hillslope->parent sus(3) bm(3) ero(3), channel->parent (3)
+    float *volero, *voldepo;  // [N][M]
+    double *sedtot;  // [6] EROt(3), DEPt(3)
+    // slides
+    int sl_gullie;
+    float sl_fs, sl_gammaw;
+    const float *sl_zs, *sl_gammas, *sl_cohesion, *sl_friction, *sl_radslope;
+    const float *sl_zcrit, *sl_risk;
+    const float *sl_cosr, *sl_sinr, *sl_tanfa;  // cos/sin of the slope angle, tan of the friction angle
+    int32_t *sl_slid;       // [N] own failure flag
+    int32_t *sl_marktime;   // [N] first step at which an upstream failure marked this cell (INT_MAX = never)
+    int32_t *sl_acum;       // [N]
+    int32_t *sl_ncelltime;  // [T]
+    const int32_t *drena;   // original drain ids (for the downstream marking walk)
+    int drena_stride;
+};
+
+__device__ __forceinline__ size_t sidx(const ShiaP &P, int k, int cell, int m) {
+    return ((size_t)k * P.N + cell) * P.M + m;
+}
+
+// modelosv2.f90:1278-1293
+__device__ __forceinline__ float calc_speed_dev(float sm, float coef, float expo, float elem_long, float &speed,
+                                                float dt, int niter) {
+    float area = 0.0f;
+    for (int i = 0; i < niter; ++i) {
+        area = sm / (elem_long + speed * dt);
+        const float new_speed = coef * powf(area, expo);
+        speed = (2.0f * new_speed + speed) / 3.0f;
+    }
+    return area;
+}
+
+struct SedLocal {
+    float Vs[3], Vd[3], Vsc[3], Vdc[3];
+    float up[12];  // what this cell sends to its parent this step
+    float DEP[3];
+    float ero_add[3], dep_add[3];  // contributions to EROt / DEPt
+    float volero_add, voldepo_add;
+};
+
+// modelosv2.f90:1321-1428
+__device__ __forceinline__ void sed_hillslope_dev(const ShiaP &P, SedLocal &S, float alfa, float v2, float S2, float So,
+                                                  float qlin, int cell, int tipo) {
+    const float dt = P.dt, dxp = P.dxp;
+    float qsSUStot = 0.f, qsBMtot = 0.f, qsSUS[3] = {0, 0, 0}, qsBM[3] = {0, 0, 0}, qsERO[3] = {0, 0, 0};
+    float SUStot = 0.f, DEPtot = 0.f, Te[3];
+    S.DEP[0] = S.DEP[1] = S.DEP[2] = 0.f;
+    const float Qskr = alfa * powf(So, 1.664f) * powf(qlin, 2.035f) * P.krus[cell] * P.crus[cell] * P.prus[cell] * dxp * dt;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (S2 / 1000.0f > P.wi[i] * dt)
+            Te[i] = P.wi[i] * dt * 1000.0f / S2;
+        else
+            Te[i] = 1.0f;
+        S.Vd[i] = S.Vd[i] + Te[i] * S.Vs[i];
+        S.Vs[i] = S.Vs[i] - Te[i] * S.Vs[i];
+        S.DEP[i] = Te[i] * S.Vs[i];
+        SUStot = SUStot + S.Vs[i];
+        DEPtot = DEPtot + S.Vd[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (S.Vs[i] > 0.0f) {
+            if (Qskr < SUStot) {
+                const float cap = Qskr * S.Vs[i] / SUStot;
+                const float Adv = S.Vs[i] * v2 * dt / (dxp + v2 * dt);
+                qsSUS[i] = fmaxf(cap, Adv);
+            } else {
+                qsSUS[i] = S.Vs[i];
+            }
+        }
+        qsSUStot = qsSUStot + qsSUS[i];
+        S.Vs[i] = S.Vs[i] - qsSUS[i];
+        if (tipo == 1) S.up[i] = qsSUS[i];
+        else S.Vsc[i] = S.Vsc[i] + qsSUS[i];
+    }
+    const float totXSScap = fmaxf(0.0f, Qskr - qsSUStot);
+    if (totXSScap > 0.0f && DEPtot > 0.0f) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (S.Vd[i] > 0.0f) {
+                if (totXSScap < DEPtot) qsBM[i] = totXSScap * S.Vd[i] / DEPtot;
+                else qsBM[i] = S.Vd[i];
+            }
+            qsBMtot = qsBMtot + qsBM[i];
+            S.DEP[i] = S.DEP[i] - qsBM[i];
+            if (S.DEP[i] < 0.f) S.DEP[i] = 0.f;
+            S.Vd[i] = S.Vd[i] - qsBM[i];
+            if (tipo == 1) S.up[3 + i] = qsBM[i];
+            else S.Vsc[i] = S.Vsc[i] + qsBM[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) S.dep_add[i] += S.DEP[i];
+    const float REScap = fmaxf(0.0f, totXSScap - qsBMtot);
+    if (REScap > 0.0f) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            qsERO[i] = P.parliac[3 * (size_t)cell + i] * REScap / 100.0f;
+            if (tipo == 1) S.up[6 + i] = qsERO[i];
+            else S.Vsc[i] = S.Vsc[i] + qsERO[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) S.ero_add[i] += qsERO[i];
+    S.volero_add = (qsERO[0] + qsERO[1]) + qsERO[2];
+    S.voldepo_add = (S.DEP[0] + S.DEP[1]) + S.DEP[2];
+}
+
+// modelosv2.f90:1537-1608 ; returns the second VolDEPo increment of the step through *voldepo2
+__device__ __forceinline__ void sed_channel_dev(const ShiaP &P, SedLocal &S, float S5, float v5, float Q5, float So,
+                                                float area_sec, float VolSal[3], float *voldepo2) {
+    const float dt = P.dt, dxp = P.dxp;
+    const float grav = 9.8f, Gsed = 2.65f;
+    float Cw[3], Te[3], qsSUS[3] = {0, 0, 0}, qsBM[3] = {0, 0, 0};
+    float L, Rh;
+    S.DEP[0] = S.DEP[1] = S.DEP[2] = 0.f;
+    if (S5 > 0.0f) {
+        L = area_sec * 1000.0f / S5;
+        Rh = L * S5 / (1000.0f * L + 2.0f * S5);
+    } else {
+        Rh = 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float d = P.diam[i];
+        Cw[i] = 0.05f * (Gsed / (Gsed - 1.0f)) * (v5 * So) / (sqrtf((Gsed - 1.0f) * grav * d / 1000.0f)) *
+                sqrtf((Rh * So) / ((Gsed - 1.0f) * (d / 1000.0f)));
+        if (S5 / 1000.0f > P.wi[i] * dt)
+            Te[i] = P.wi[i] * dt * 1000.0f / S5;
+        else
+            Te[i] = 1.0f;
+        S.Vdc[i] = S.Vdc[i] + Te[i] * S.Vsc[i];
+        S.Vsc[i] = S.Vsc[i] - Te[i] * S.Vsc[i];
+        S.DEP[i] = S.DEP[i] + Te[i] * S.Vsc[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float supply = S.Vsc[i] + S.Vdc[i];
+        qsSUS[i] = 0.0f;
+        if (supply > 0.0f) {
+            const float VolEH = Q5 * Cw[i] * dt / 2.65f;
+            const float AdvF = fminf(1.0f, v5 * dt / (dxp + v5 * dt));
+            qsSUS[i] = S.Vsc[i] * AdvF;
+            const float XSScap = fmaxf(0.0f, VolEH - qsSUS[i]);
+            qsBM[i] = S.Vdc[i] * AdvF;
+            qsBM[i] = fminf(XSScap, qsBM[i]);
+            S.DEP[i] = S.DEP[i] - qsBM[i];
+            if (S.DEP[i] < 0.0f) S.DEP[i] = 0.0f;
+            S.Vsc[i] = S.Vsc[i] - qsSUS[i];
+            S.Vdc[i] = S.Vdc[i] - qsBM[i];
+            S.up[9 + i] = qsSUS[i] + qsBM[i];
+            VolSal[i] = (qsSUS[i] + qsBM[i]) / dt;
+        }
+    }
+    *voldepo2 = (S.DEP[0] + S.DEP[1]) + S.DEP[2];
+}
+
+__device__ __forceinline__ int find_row(const int32_t *__restrict__ cells, int n, int cell) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cells[mid] < cell) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <bool SED, bool SLIDES>
+__global__ void __launch_bounds__(WAVE_THREADS)
+k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const int hi) {
+    const long long g = (long long)blockIdx.x * WAVE_THREADS + threadIdx.x;
+    int cell, m;
+    if (P.M == 1) { cell = lo + (int)g; m = 0; }
+    else { cell = lo + (int)(g / P.M); m = (int)(g % P.M); }
+    bool active = cell < hi;
+    int t = -1;
+    uint32_t tw = 0;
+    if (active) {
+        tw = __ldg(P.tw + cell);
+        t = w - (P.Lmax - (int)(tw >> 8));
+        active = (t >= 0) && (t < P.T);
+    }
+    double r_sal = 0.0, r_sto[5] = {0, 0, 0, 0, 0}, r_spd[4] = {0, 0, 0, 0}, r_ret = 0.0;
+    float sed_ero[3] = {0, 0, 0}, sed_dep[3] = {0, 0, 0};
+    if (active) {
+        const int N = P.N, M = P.M;
+        const int type = (tw >> 4) & 3, nch = tw & 15;
+        const float dt = P.dt;
+        const size_t NM = (size_t)N * M;
+        const size_t base = (size_t)cell * M + m;
+        float S[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) S[k] = P.sto[k * NM + base];
+        SedLocal SL;
+        if (SED) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                SL.Vs[k] = P.sed[(0 + k) * NM + base];
+                SL.Vd[k] = P.sed[(3 + k) * NM + base];
+                SL.Vsc[k] = P.sed[(6 + k) * NM + base];
+                SL.Vdc[k] = P.sed[(9 + k) * NM + base];
+            }
+#pragma unroll
+            for (int k = 0; k < 12; ++k) SL.up[k] = 0.f;
+            SL.ero_add[0] = SL.ero_add[1] = SL.ero_add[2] = 0.f;
+            SL.dep_add[0] = SL.dep_add[1] = SL.dep_add[2] = 0.f;
+            SL.volero_add = SL.voldepo_add = 0.f;
+        }
+        // ---- gather what the upstream neighbours sent this step, in ascending cell order (:601,:617,:672) ----
+        if (nch) {
+            const int c0 = __ldg(P.cs + cell);
+            const float *ob = P.outb + (size_t)(t & 1) * 4 * NM;
+            for (int c = c0; c < c0 + nch; ++c) {
+                const size_t cb = (size_t)c * M + m;
+                S[1] = S[1] + ob[0 * NM + cb];
+                S[2] = S[2] + ob[1 * NM + cb];
+                S[3] = S[3] + ob[2 * NM + cb];
+                S[4] = S[4] + ob[3 * NM + cb];
+                if (SED) {
+                    const float *so = P.sedout + (size_t)(t & 1) * 12 * NM;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        SL.Vs[i] = SL.Vs[i] + so[(0 + i) * NM + cb];
+                        SL.Vs[i] = SL.Vs[i] + so[(3 + i) * NM + cb];
+                        SL.Vs[i] = SL.Vs[i] + so[(6 + i) * NM + cb];
+                        SL.Vsc[i] = SL.Vsc[i] + so[(9 + i) * NM + cb];
+                    }
+                }
+            }
+        }
+        // ---- per-cell parameters (:285-304), recomputed from the shared maps and the member's calibration ----
+        float cal[11];
+        {
+            const float *cp = P.calib + (size_t)m * 11;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) cal[k] = __ldg(cp + k);
+        }
+        const float4 vc = __ldg(reinterpret_cast<const float4 *>(P.v_coef) + cell);
+        const float4 hc = __ldg(reinterpret_cast<const float4 *>(P.h_coef) + cell);
+        const float vs1 = vc.x * cal[0] * dt, vs2 = vc.y * cal[1] * dt, vs3 = vc.z * cal[2] * dt, vs4 = vc.w * cal[3] * dt;
+        const float H1 = __ldg(P.max_capilar + cell) * cal[8];
+        const float Lh = __ldg(P.hill_long + cell);
+        const float m3 = __ldg(P.elem_area + cell) / 1000.0f;
+        // ---- rain (:444-449) ----
+        const int p = __ldg(P.pos + t);
+        float R = 0.0f;
+        if (p != 1) R = (float)__ldg(P.rain + (size_t)(p - 1) * N + cell) / 1000.0f;
+        // ---- vertical cascade (:478-512) ----
+        float vf1 = fmaxf(0.0f, R - H1 + S[0]);
+        S[0] = S[0] + R - vf1;
+        const float E = fminf(__ldg(P.evp + t) * vs1 * powf(S[0] / H1, 0.6f), S[0]);
+        S[0] = S[0] - E;
+        float vf2 = fminf(vf1, vs2);
+        S[1] = S[1] + vf1 - vf2;
+        float vf3 = fminf(vf2, vs3);
+        S[2] = S[2] + vf2 - vf3;
+        const float vf4 = fminf(vf3, vs4);
+        S[3] = S[3] + vf3 - vf4;
+        float H2 = 0.f;
+        if (P.retorno_gr > 0.0f || SLIDES) H2 = __ldg(P.max_gravita + cell) * cal[9];
+        if (P.retorno_aq > 0.0f) {
+            const float H3 = __ldg(P.max_aquifer + cell) * cal[10];
+            const float Ret_aq = fmaxf(0.0f, S[3] - H3);
+            S[2] = S[2] + Ret_aq;
+            S[3] = S[3] - Ret_aq;
+        }
+        if (P.retorno_gr > 0.0f) {
+            const float Ret = fmaxf(0.0f, S[2] - H2);
+            S[1] = S[1] + Ret;
+            S[2] = S[2] - Ret;
+            if (P.want_retorned) {
+                if (P.retorned) P.retorned[cell] = P.retorned[cell] + Ret;
+                r_ret = (double)Ret;
+            }
+        }
+        r_sal = (double)vf4 + (double)E;
+        // ---- hillslope outflows of tanks 2..4 (:553-595) ----
+        float h[4] = {0.f, 0.f, 0.f, 0.f};
+        float hs[4] = {0.f, 0.f, 0.f, 0.f};
+        const float hcoef[3] = {hc.x, hc.y, hc.z};
+        float4 he = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool any_kin = (P.st[0] == 2) | (P.st[1] == 2) | (P.st[2] == 2);
+        if (any_kin || type > 1) he = __ldg(reinterpret_cast<const float4 *>(P.h_exp) + cell);
+        const float hexp[3] = {he.x, he.y, he.z};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (P.st[k] == 1) {
+                const float v = P.hs_state ? P.hsp[k * NM + base] : hcoef[k] * cal[4 + k];
+                hs[k] = v;
+                h[k] = (1.0f - Lh / (v * dt + Lh)) * S[k + 1];
+            } else {
+                float v = P.hsp[k * NM + base];
+                const float sec = calc_speed_dev(S[k + 1] * m3, hcoef[k] * cal[4 + k], hexp[k], Lh, v, dt, P.niter);
+                h[k] = fminf(sec * v * dt / m3, S[k + 1]);
+                hs[k] = v;
+                P.hsp[k * NM + base] = v;
+                if (SED && k == 0) {
+                    const float qlin = h[0] * m3 / (dt * P.dxp);
+                    sed_hillslope_dev(P, SL, P.sed_factor, v, S[1], __ldg(P.hill_slope + cell), qlin, cell, type);
+                }
+            }
+            S[k + 1] = S[k + 1] - h[k];
+        }
+        // ---- routing (:599-719) ----
+        const bool outlet = (cell == N - 1);
+        float o0, o1, o2, o3;
+        float sec_area = 0.f;
+        float Vsal[3] = {0.f, 0.f, 0.f};
+        const size_t qoff = ((size_t)m * P.T + t) * P.n_cont;
+        if (type == 1) {
+            o0 = h[0]; o1 = h[1]; o2 = h[2]; o3 = 0.0f;
+            if (outlet) {
+                const float s3 = (h[0] + h[1]) + h[2];
+                if (P.q) P.q[qoff] = s3 * m3;
+                r_sal += (double)s3;
+            }
+        } else {
+            o0 = 0.0f; o1 = 0.0f;
+            o2 = h[2] * (float)(3 - type);
+            S[4] = S[4] + (h[0] + h[1]) + h[2] * (float)(type - 2);
+            float v = P.hsp[3 * NM + base];
+            sec_area = calc_speed_dev(S[4] * m3, hc.w * cal[7], he.w, __ldg(P.stream_long + cell), v, dt, P.niter);
+            h[3] = fminf(sec_area * v * dt / m3, S[4]);
+            hs[3] = v;
+            P.hsp[3 * NM + base] = v;
+            if (SED) {
+                float vd2 = 0.f;
+                sed_channel_dev(P, SL, S[4], v, h[3] * m3 / dt, __ldg(P.stream_slope + cell), sec_area, Vsal, &vd2);
+                // VolDEPo(celda) is incremented twice in a step for a channel cell (:1427 then :1607)
+                const size_t vb = base;
+                float vdep = P.voldepo[vb];
+                vdep = vdep + SL.voldepo_add;
+                vdep = vdep + vd2;
+                P.voldepo[vb] = vdep;
+                P.volero[vb] = P.volero[vb] + SL.volero_add;
+                SL.voldepo_add = 0.f;
+                SL.volero_add = 0.f;
+            }
+            S[4] = S[4] - h[3];
+            o3 = h[3];
+            if (outlet) {
+                if (P.q) P.q[qoff] = h[3] * m3 / dt;
+                r_sal += (double)h[3];
+                if (SED && P.qsed)
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) P.qsed[(((size_t)m * P.T + t) * 3 + i) * P.n_cont] = Vsal[i];
+                if (P.show_speed) {
+                    if (P.speed) P.speed[qoff] = v;
+                    if (P.area) P.area[qoff] = sec_area;
+                }
+            }
+        }
+        if (SED && type == 1 && P.st[0] == 2) {  // hillslope cell: single VolDEPo / VolERO increment (:1426-1427)
+            P.voldepo[base] = P.voldepo[base] + SL.voldepo_add;
+            P.volero[base] = P.volero[base] + SL.volero_add;
+        }
+        // ---- landslides (:723, :1649-1707) ----
+        if (SLIDES) {
+            if (__ldg(P.sl_risk + cell) == 2.0f && P.sl_slid[cell] == 0 && P.sl_marktime[cell] > t) {
+                const float zs = __ldg(P.sl_zs + cell);
+                const float Zw = (S[2] * zs) / H2;
+                bool fail = false;
+                if (Zw >= __ldg(P.sl_zcrit + cell)) {
+                    fail = true;
+                } else {
+                    const float gs = __ldg(P.sl_gammas + cell);
+                    const float cr = __ldg(P.sl_cosr + cell), sr = __ldg(P.sl_sinr + cell);
+                    const float Num = __ldg(P.sl_cohesion + cell) + (gs * zs - Zw * P.sl_gammaw) * (cr * cr) * __ldg(P.sl_tanfa + cell);
+                    const float Den = gs * zs * sr * cr;
+                    if (Num / Den <= P.sl_fs) fail = true;
+                }
+                if (fail) {
+                    P.sl_slid[cell] = 1;
+                    atomicAdd(P.sl_acum + cell, 1);
+                    int marks = 1;
+                    if (P.sl_gullie == 1 && type <= 2) {  // slide_hill2gullie :1683-1707
+                        int local = cell, ltype = type;
+                        for (;;) {
+                            const int d = P.drena[(size_t)local * P.drena_stride];
+                            if (d == 0) break;
+                            const int dir = N - d;
+                            const int dtype = (__ldg(P.tw + dir) >> 4) & 3;
+                            if (dtype > ltype) break;
+                            atomicMin(P.sl_marktime + dir, t);
+                            atomicAdd(P.sl_acum + dir, 1);
+                            ++marks;
+                            local = dir;
+                            ltype = dtype;
+                        }
+                    }
+                    atomicAdd(P.sl_ncelltime + t, marks);
+                }
+            }
+        }
+        // ---- records (:749-787) ----
+        if (tw & TW_CTRLQ) {
+            const int row = 1 + find_row(P.ctrl_cells, P.n_ctrl, cell);
+            if (row < P.n_cont) {
+                if (P.q) P.q[qoff + row] = (type > 1) ? h[3] * m3 / dt : 0.0f;
+                if (type > 1) {
+                    if (P.show_speed) {
+                        if (P.speed) P.speed[qoff + row] = hs[3];
+                        if (P.area) P.area[qoff + row] = sec_area;
+                    }
+                    if (SED && P.qsed)
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) P.qsed[(((size_t)m * P.T + t) * 3 + i) * P.n_cont + row] = Vsal[i];
+                }
+            }
+        }
+        if (tw & TW_CTRLH) {
+            const int row = find_row(P.ctrlh_cells, P.n_ctrlh, cell);
+            if (row < P.n_conth) {
+                const size_t k = ((size_t)m * P.T + t) * P.n_conth + row;
+                if (P.hum) P.hum[k] = S[0] + S[2];
+                if (P.st1o) P.st1o[k] = S[0];
+                if (P.st3o) P.st3o[k] = S[2];
+            }
+        }
+        // ---- publish ----
+#pragma unroll
+        for (int k = 0; k < 5; ++k) P.sto[k * NM + base] = S[k];
+        {
+            float *ob = P.outb + (size_t)(t & 1) * 4 * NM;
+            ob[0 * NM + base] = o0;
+            ob[1 * NM + base] = o1;
+            ob[2 * NM + base] = o2;
+            ob[3 * NM + base] = o3;
+        }
+        if (SED) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                P.sed[(0 + k) * NM + base] = SL.Vs[k];
+                P.sed[(3 + k) * NM + base] = SL.Vd[k];
+                P.sed[(6 + k) * NM + base] = SL.Vsc[k];
+                P.sed[(9 + k) * NM + base] = SL.Vdc[k];
+            }
+            float *so = P.sedout + (size_t)(t & 1) * 12 * NM;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) so[k * NM + base] = SL.up[k];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { sed_ero[i] = SL.ero_add[i]; sed_dep[i] = SL.dep_add[i]; }
+        }
+        if (P.want_red) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) r_sto[k] = (double)S[k];
+            if (P.show_mean_speed)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // sum(hspeed,dim=2): linear tanks hold their constant speed, channel speed is 0 on hillslopes
+                    r_spd[k] = (double)((k < 3) ? hs[k] : ((type > 1) ? hs[3] : (P.hs_state ? P.hsp[3 * NM + base] : 0.0f)));
+                }
+        }
+    }
+    // ---- per-step reductions (balance :846, mean_storage :828, mean_speed :833, mean_retorno :838) ----
+    if (P.want_red && P.M == 1) {
+        // steps are monotone along the cell index, so a warp (usually a whole block) shares one step
+        const unsigned full = 0xffffffffu;
+        const int t0 = __shfl_sync(full, t, 0);
+        const bool uni = __all_sync(full, t == t0);
+        const int sub = blockIdx.x & (RED_SUB - 1);
+        auto flush = [&](double v, int q, int tt) {
+            if (v != 0.0) atomicAdd(P.red + ((size_t)tt * RQ_COUNT + q) * RED_SUB + sub, v);
+        };
+        if (uni) {
+            if (t0 >= 0) {
+                const double a = warp_sum_d(r_sal);
+                double b[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) b[k] = warp_sum_d(r_sto[k]);
+                if ((threadIdx.x & 31) == 0) {
+                    flush(a, RQ_SAL, t0);
+                    if (P.show_storage) {
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) flush(b[k], RQ_STO1 + k, t0);
+                    } else {
+                        flush(((b[0] + b[1]) + (b[2] + b[3])) + b[4], RQ_STO1, t0);
+                    }
+                }
+                if (P.show_mean_speed) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double c = warp_sum_d(r_spd[k]);
+                        if ((threadIdx.x & 31) == 0) flush(c, RQ_SPD1 + k, t0);
+                    }
+                }
+                if (P.want_retorned) {
+                    const double c = warp_sum_d(r_ret);
+                    if ((threadIdx.x & 31) == 0) flush(c, RQ_RET, t0);
+                }
+            }
+        } else if (t >= 0) {
+            flush(r_sal, RQ_SAL, t);
+            if (P.show_storage) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) flush(r_sto[k], RQ_STO1 + k, t);
+            } else {
+                flush(((r_sto[0] + r_sto[1]) + (r_sto[2] + r_sto[3])) + r_sto[4], RQ_STO1, t);
+            }
+            if (P.show_mean_speed)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) flush(r_spd[k], RQ_SPD1 + k, t);
+            if (P.want_retorned) flush(r_ret, RQ_RET, t);
+        }
+    }
+    if (SED) {  // EROt / DEPt (:1403, :1420): global totals, fp64
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double a = warp_sum_d((double)sed_ero[i]);
+            const double b = warp_sum_d((double)sed_dep[i]);
+            if ((threadIdx.x & 31) == 0) {
+                if (a != 0.0) atomicAdd(P.sedtot + i, a);
+                if (b != 0.0) atomicAdd(P.sedtot + 3 + i, b);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// plan: levels, child ranges, packed topology words
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_plan_init(const int32_t *__restrict__ drena, int stride, int n, int32_t *__restrict__ lev,
+                            int32_t *__restrict__ jmp, int32_t *__restrict__ nch, int32_t *__restrict__ cmin,
+                            int32_t *__restrict__ cmax, int *__restrict__ err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d = drena[(size_t)i * stride];
+    if (d == 0) {
+        if (i != n - 1) *err = 2;  // a second outlet
+        lev[i] = 0;
+        jmp[i] = -1;
+        return;
+    }
+    const int p = n - d;
+    if (d < 0 || p <= i || p >= n) { *err = 1; lev[i] = 0; jmp[i] = -1; return; }
+    lev[i] = 1;
+    jmp[i] = p;
+    atomicAdd(&nch[p], 1);
+    atomicMin(&cmin[p], i);
+    atomicMax(&cmax[p], i);
+}
+
+// pointer doubling: lev[i] = hops to the outlet
+__global__ void k_plan_jump(const int32_t *__restrict__ lev_in, const int32_t *__restrict__ jmp_in, int n,
+                            int32_t *__restrict__ lev_out, int32_t *__restrict__ jmp_out, int *__restrict__ more) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int j = jmp_in[i];
+    int l = lev_in[i], nj = -1;
+    if (j >= 0) {
+        l += lev_in[j];
+        nj = jmp_in[j];
+        if (nj >= 0) *more = 1;
+    }
+    lev_out[i] = l;
+    jmp_out[i] = nj;
+}
+
+__global__ void k_plan_pack(const int32_t *__restrict__ lev, const int32_t *__restrict__ nch,
+                            const int32_t *__restrict__ cmin, const int32_t *__restrict__ cmax,
+                            const int32_t *__restrict__ unit_type, const int32_t *__restrict__ control,
+                            const int32_t *__restrict__ control_h, int n, uint32_t *__restrict__ tw,
+                            int32_t *__restrict__ cs, int32_t *__restrict__ level_first, int32_t *__restrict__ fq,
+                            int32_t *__restrict__ fh, int *__restrict__ err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int l = lev[i];
+    if (i + 1 < n && lev[i + 1] > l) *err = 3;             // not level-ordered
+    if (l >= (1 << 24)) *err = 4;
+    const int c = nch[i];
+    if (c > 0 && cmax[i] - cmin[i] + 1 != c) *err = 5;     // children not contiguous
+    if (c > 15) *err = 6;
+    const int ut = unit_type[i];
+    if (ut < 1 || ut > 3) *err = 7;
+    if (i == 0 || lev[i - 1] != l) level_first[l] = i;
+    const int cq = (control && control[i] != 0) ? 1 : 0, ch = (control_h && control_h[i] != 0) ? 1 : 0;
+    fq[i] = cq;
+    fh[i] = ch;
+    tw[i] = ((uint32_t)l << 8) | (ch ? TW_CTRLH : 0u) | (cq ? TW_CTRLQ : 0u) | ((uint32_t)(ut & 3) << 4) | (uint32_t)(c & 15);
+    cs[i] = (c > 0) ? cmin[i] : 0;
+}
+
+__global__ void k_compact(const int32_t *__restrict__ flag, const int32_t *__restrict__ pos, int n,
+                          int32_t *__restrict__ list) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) list[pos[i]] = i;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// init / finalize
+// ---------------------------------------------------------------------------------------------------
+// StoOut = StoIn | Storage + storage_constant (:271-277), AoS (5,N) -> SoA [5][N][M]; also the initial total
+__global__ void k_state_init(const float *__restrict__ src, float add, int n, int M, float *__restrict__ sto,
+                             double *__restrict__ sto0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0.0;
+    if (i < n) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const float v = src[5 * (size_t)i + k] + add;
+            s += (double)v;
+            for (int m = 0; m < M; ++m) sto[((size_t)k * n + i) * M + m] = v;
+        }
+    }
+    s = warp_sum_d(s);
+    if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(sto0, s);
+}
+
+// hspeed initial state (:285-299): HspeedIn, or h_coef*Calib for linear tanks / 0 for kinematic ones; tank 4 -> 0
+__global__ void k_hspeed_init(const float *__restrict__ hspeedin, int n, int M, float *__restrict__ hsp) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)n * M) return;
+    const int i = (int)(g / M), m = (int)(g % M);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hsp[((size_t)k * n + i) * M + m] = hspeedin ? hspeedin[4 * (size_t)i + k] : 0.0f;
+}
+
+__global__ void k_state_final(const ShiaP P, float *__restrict__ stoout, float *__restrict__ hspeed_out) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)P.N * P.M) return;
+    const int i = (int)(g / P.M), m = (int)(g % P.M);
+    const size_t NM = (size_t)P.N * P.M, base = (size_t)i * P.M + m;
+    if (stoout)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) stoout[((size_t)m * P.N + i) * 5 + k] = P.sto[k * NM + base];
+    if (hspeed_out) {
+        const float4 hc = reinterpret_cast<const float4 *>(P.h_coef)[i];
+        const float hcoef[3] = {hc.x, hc.y, hc.z};
+        const float *cal = P.calib + (size_t)m * 11;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float v;
+            if (k < 3 && P.st[k] == 1 && !P.hs_state) v = hcoef[k] * cal[4 + k];
+            else v = P.hsp[k * NM + base];
+            hspeed_out[((size_t)m * P.N + i) * 4 + k] = v;
+        }
+    }
+}
+
+// per-record basin total of the rain field in mm (fp64), used for Mean_Rain (:797) and `entradas` (:469)
+__global__ void k_rain_record_sum(const int32_t *__restrict__ rain, int n, double *__restrict__ recsum) {
+    const int r = blockIdx.y;
+    const int32_t *rec = rain + (size_t)r * n;
+    double s = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        s += (double)((float)rec[i] / 1000.0f);
+    s = warp_sum_d(s);
+    if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(recsum + r, s);
+}
+
+// Acum_rain (:451): per-cell fp32 running sum over the steps, in time order
+__global__ void k_acum_rain(const int32_t *__restrict__ rain, const int32_t *__restrict__ pos, int n, int T,
+                            float *__restrict__ acum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a = 0.0f;
+    for (int t = 0; t < T; ++t) {
+        const int p = pos[t];
+        if (p != 1) a = a + (float)rain[(size_t)(p - 1) * n + i] / 1000.0f;
+    }
+    acum[i] = a;
+}
+
+__global__ void k_shia_epilogue(const double *__restrict__ red, const double *__restrict__ recsum,
+                                const int32_t *__restrict__ pos, const double *__restrict__ sto0, int n, int T,
+                                int show_storage, float *__restrict__ balance, float *__restrict__ mean_rain,
+                                float *__restrict__ mean_storage, float *__restrict__ mean_speed,
+                                float *__restrict__ mean_retorno) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    auto q = [&](int tt, int k) {
+        double s = 0.0;
+        for (int j = 0; j < RED_SUB; ++j) s += red[((size_t)tt * RQ_COUNT + k) * RED_SUB + j];
+        return s;
+    };
+    auto total = [&](int tt) {
+        if (tt < 0) return *sto0;
+        if (!show_storage) return q(tt, RQ_STO1);
+        double s = 0.0;
+        for (int k = 0; k < 5; ++k) s += q(tt, RQ_STO1 + k);
+        return s;
+    };
+    const double entradas = recsum[pos[t] - 1];
+    if (balance) balance[t] = (float)(total(t) - total(t - 1) - entradas + q(t, RQ_SAL));
+    if (mean_rain) mean_rain[t] = (float)(entradas / (double)n);
+    if (mean_storage)
+        for (int k = 0; k < 5; ++k) mean_storage[5 * (size_t)t + k] = (float)(q(t, RQ_STO1 + k) / (double)n);
+    if (mean_speed)
+        for (int k = 0; k < 4; ++k) mean_speed[4 * (size_t)t + k] = (float)(q(t, RQ_SPD1 + k) / (double)n);
+    if (mean_retorno) mean_retorno[t] = (float)(q(t, RQ_RET) / (double)n);
+}
+
+// slide_allocate, modelosv2.f90:1613-1648
+// The fp32 trig of the reference (libm, < 1 ulp) is reproduced by evaluating in fp64 and rounding once: the soil
+// thresholds subtract nearly equal tangents, so a 2-4 ulp tanf would be amplified into visible differences.
+__device__ __forceinline__ float tan_cr(float x) { return (float)tan((double)x); }
+__device__ __forceinline__ float cos_cr(float x) { return (float)cos((double)x); }
+__device__ __forceinline__ float sin_cr(float x) { return (float)sin((double)x); }
+__device__ __forceinline__ float atan_cr(float x) { return (float)atan((double)x); }
+
+__global__ void k_slide_allocate(const ShiaP P, float *__restrict__ zmin, float *__restrict__ zcrit,
+                                 float *__restrict__ zmax, float *__restrict__ bo, float *__restrict__ risk,
+                                 float *__restrict__ cosr, float *__restrict__ sinr, float *__restrict__ tanfa) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N) return;
+    const float gw = P.sl_gammaw;
+    const float gs = P.sl_gammas[i], co = P.sl_cohesion[i], fa = P.sl_friction[i], rs = P.sl_radslope[i], zs = P.sl_zs[i];
+    const float cr = cos_cr(rs), tfa = tan_cr(fa), trs = tan_cr(rs);
+    cosr[i] = cr; sinr[i] = sin_cr(rs); tanfa[i] = tfa;
+    const float c2 = cr * cr;
+    const float zmn = co / ((gw * c2 * tfa) + (gs * c2 * (trs - tfa)));
+    const float zcr = (gs / gw) * zs * (1.0f - (trs / tfa)) + (co / (gw * c2 * tfa));
+    const float zmx = co / ((gs * c2) * (trs - tfa));
+    const float b = atan_cr(-tan_cr(fa * (gw - gs) / gs));
+    float rv = 2.0f;
+    if (((P.tw[i] >> 4) & 3) == 3) rv = 0.0f;
+    if (rs < b) rv = 0.0f;
+    if (zs < zmn && rs < b) rv = 0.0f;
+    if (zs > zmx && rs > b) rv = 1.0f;
+    zmin[i] = zmn; zcrit[i] = zcr; zmax[i] = zmx; bo[i] = b; risk[i] = rv;
+    P.sl_slid[i] = 0;
+    P.sl_marktime[i] = INT_MAX;
+    P.sl_acum[i] = 0;
+}
+
+__global__ void k_slide_final(const ShiaP P, float *__restrict__ occ) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N) return;
+    occ[i] = (P.sl_marktime[i] != INT_MAX) ? 3.0f : (P.sl_slid[i] ? 1.0f : 0.0f);
+}
+
+__global__ void k_sed_init(const float *__restrict__ vd_init, int n, int M, float *__restrict__ sed) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)n * M) return;
+    const int i = (int)(g / M), m = (int)(g % M);
+    const size_t NM = (size_t)n * M, base = (size_t)i * M + m;
+    for (int k = 0; k < 12; ++k) sed[k * NM + base] = 0.0f;
+    if (vd_init)
+        for (int k = 0; k < 3; ++k) sed[(3 + k) * NM + base] = vd_init[3 * (size_t)i + k];
+}
+
+// SoA [12][N] -> the four (3,N) arrays
+__global__ void k_sed_final(const float *__restrict__ sed, int n, float *vs, float *vd, float *vsc, float *vdc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < 3; ++k) {
+        if (vs) vs[3 * (size_t)i + k] = sed[(size_t)(0 + k) * n + i];
+        if (vd) vd[3 * (size_t)i + k] = sed[(size_t)(3 + k) * n + i];
+        if (vsc) vsc[3 * (size_t)i + k] = sed[(size_t)(6 + k) * n + i];
+        if (vdc) vdc[3 * (size_t)i + k] = sed[(size_t)(9 + k) * n + i];
+    }
+}
+
+__global__ void k_d2f(const double *__restrict__ a, int n, float *__restrict__ b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = (float)a[i];
+}
+
+// wmf.py:749-754 (__eval_nash__) and :775-781 (__eval_q_pico__), one block per member, fp64
+__global__ void __launch_bounds__(256) k_eval_scores(const float *__restrict__ q, int n_cont, int T, int row,
+                                                     const float *__restrict__ qobs, float *__restrict__ scores) {
+    const int m = blockIdx.x;
+    const float *qs = q + (size_t)m * T * n_cont + row;
+    __shared__ double sh[3][8];
+    __shared__ double s_mean;
+    auto block_sum = [&](double v, int slot) {
+        v = warp_sum_d(v);
+        if ((threadIdx.x & 31) == 0) sh[slot][threadIdx.x >> 5] = v;
+        __syncthreads();
+        double r = 0.0;
+        for (int k = 0; k < 8; ++k) r += sh[slot][k];
+        __syncthreads();
+        return r;
+    };
+    double so = 0.0, cnt = 0.0;
+    for (int t = threadIdx.x; t < T; t += 256) {
+        const float o = qobs[t];
+        if (isfinite(o)) { so += (double)o; cnt += 1.0; }
+        else if (!isnan(o)) { so += (double)o; }  // nansum keeps infinities
+    }
+    const double tot = block_sum(so, 0), n_ok = block_sum(cnt, 1);
+    if (threadIdx.x == 0) s_mean = tot / n_ok;
+    __syncthreads();
+    const double med = s_mean;
+    double num = 0.0, den = 0.0;
+    // argmax over the non-NaN entries, first occurrence wins (np.argmax on a masked array)
+    double bo = -INFINITY, bs = -INFINITY;
+    int io = T, is = T;
+    for (int t = threadIdx.x; t < T; t += 256) {
+        const double o = (double)qobs[t], s = (double)qs[(size_t)t * n_cont];
+        const double d1 = (o - s) * (o - s), d2 = (o - med) * (o - med);
+        if (!isnan(d1)) num += d1;
+        if (!isnan(d2)) den += d2;
+        if (!isnan(o) && (o > bo)) { bo = o; io = t; }
+        if (!isnan(s) && (s > bs)) { bs = s; is = t; }
+    }
+    num = block_sum(num, 0);
+    den = block_sum(den, 1);
+    __shared__ double mo[256], ms[256];
+    __shared__ int ko[256], ks[256];
+    mo[threadIdx.x] = bo; ko[threadIdx.x] = io; ms[threadIdx.x] = bs; ks[threadIdx.x] = is;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 256; ++k) {
+            if (mo[k] > bo || (mo[k] == bo && ko[k] < io)) { bo = mo[k]; io = ko[k]; }
+            if (ms[k] > bs || (ms[k] == bs && ks[k] < is)) { bs = ms[k]; is = ks[k]; }
+        }
+        scores[2 * (size_t)m + 0] = (float)(1.0 - num / den);
+        scores[2 * (size_t)m + 1] = (float)(((bo - bs) / bo) * 100.0);
+    }
+}
+
+__global__ void k_calc_speed(float sm, float coef, float expo, float elem_long, float dt, int niter, float *io) {
+    float v = io[0];
+    io[1] = calc_speed_dev(sm, coef, expo, elem_long, v, dt, niter);
+    io[0] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------------
+static int read_flag(wmf_ctx *ctx, const int *d, int *h) {
+    CU_TRY(ctx, cudaMemcpyAsync(h, d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return WMF_OK;
+}
+
+template <bool SED, bool SLIDES>
+static void launch_wave(wmf_ctx *ctx, const ShiaP &P, int w, int lo, int hi) {
+    const long long work = (long long)(hi - lo) * P.M;
+    const int grid = (int)((work + WAVE_THREADS - 1) / WAVE_THREADS);
+    k_shia_wave<SED, SLIDES><<<grid, WAVE_THREADS, 0, ctx->stream>>>(P, w, lo, hi);
+    ctx->launches++;
+}
+
+extern "C" {
+
+int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *in, wmf_shia_outputs *out) {
+    if (!ctx || !cfg || !in || !out) return WMF_ERR_ARG;
+    const int N = cfg->n_cel, T = cfg->n_reg, M = cfg->n_members > 0 ? cfg->n_members : 1;
+    if (N <= 0 || T <= 0 || cfg->n_cont < 1 || cfg->n_conth < 1) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: bad sizes");
+    if (cfg->calc_niter < 1) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: calc_niter must be >= 1");
+    for (int k = 0; k < 3; ++k)
+        if (cfg->speed_type[k] != 1 && cfg->speed_type[k] != 2)
+            WMF_FAIL(ctx, WMF_ERR_ARG, "shia: speed_type(%d)=%d, only 1 (linear) and 2 (kinematic) exist", k + 1, cfg->speed_type[k]);
+    if (!in->drena || !in->unit_type || !in->hill_long || !in->elem_area || !in->v_coef || !in->h_coef || !in->h_exp ||
+        !in->max_capilar || !in->max_gravita || !in->max_aquifer || !in->evpserie || !in->calib || !in->rain || !in->pos_evento ||
+        !in->stream_long || (!in->storage && !in->stoin))
+        WMF_FAIL(ctx, WMF_ERR_ARG, "shia: a required input array is NULL");
+    const bool sed = cfg->sim_sediments == 1, slides = cfg->sim_slides == 1;
+    if (sed && (!in->krus || !in->crus || !in->prus || !in->parliac || !in->hill_slope || !in->stream_slope))
+        WMF_FAIL(ctx, WMF_ERR_ARG, "shia: sim_sediments=1 needs krus, crus, prus, parliac, hill_slope, stream_slope");
+    if (slides && (!in->sl_zs || !in->sl_gammas || !in->sl_cohesion || !in->sl_frictionangle || !in->sl_radslope))
+        WMF_FAIL(ctx, WMF_ERR_ARG, "shia: sim_slides=1 needs the sl_* soil maps");
+    if (M > 1 && (sed || slides)) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: ensembles with sediments / slides are not supported yet");
+    const int stride = in->drena_stride > 0 ? in->drena_stride : 1;
+    if ((long long)N * M >= (1LL << 40)) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: ensemble too large");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    ShiaP P;
+    memset(&P, 0, sizeof P);
+    P.N = N; P.T = T; P.M = M; P.n_cont = cfg->n_cont; P.n_conth = cfg->n_conth;
+    P.dt = cfg->dt; P.dxp = cfg->dxp; P.retorno_gr = cfg->retorno_gr; P.retorno_aq = cfg->retorno_aq;
+    for (int k = 0; k < 3; ++k) P.st[k] = cfg->speed_type[k];
+    P.niter = cfg->calc_niter;
+    P.show_speed = cfg->show_speed; P.show_storage = cfg->show_storage && out->mean_storage;
+    P.show_mean_speed = cfg->show_mean_speed && out->mean_speed;
+    P.sed_factor = cfg->sed_factor;
+    for (int k = 0; k < 3; ++k) { P.wi[k] = cfg->wi[k]; P.diam[k] = cfg->diametro[k]; }
+    P.sl_gullie = cfg->sl_gullienogullie; P.sl_fs = cfg->sl_fs; P.sl_gammaw = cfg->sl_gammaw;
+    P.drena_stride = stride;
+
+    // ---- stage inputs ----
+    const int32_t *d_unit, *d_control, *d_controlh;
+    WMF_TRY(sc.in(in->drena, (size_t)N * stride - (stride - 1), &P.drena));
+    WMF_TRY(sc.in(in->unit_type, (size_t)N, &d_unit));
+    WMF_TRY(sc.in(in->control, (size_t)N, &d_control));
+    WMF_TRY(sc.in(in->control_h, (size_t)N, &d_controlh));
+    WMF_TRY(sc.in(in->v_coef, (size_t)4 * N, &P.v_coef));
+    WMF_TRY(sc.in(in->h_coef, (size_t)4 * N, &P.h_coef));
+    WMF_TRY(sc.in(in->h_exp, (size_t)4 * N, &P.h_exp));
+    if (((uintptr_t)P.v_coef | (uintptr_t)P.h_coef | (uintptr_t)P.h_exp) & 15)
+        WMF_FAIL(ctx, WMF_ERR_ARG, "shia: v_coef/h_coef/h_exp device pointers must be 16-byte aligned");
+    WMF_TRY(sc.in(in->max_capilar, (size_t)N, &P.max_capilar));
+    WMF_TRY(sc.in(in->max_gravita, (size_t)N, &P.max_gravita));
+    WMF_TRY(sc.in(in->max_aquifer, (size_t)N, &P.max_aquifer));
+    WMF_TRY(sc.in(in->hill_long, (size_t)N, &P.hill_long));
+    WMF_TRY(sc.in(in->hill_slope, (size_t)N, &P.hill_slope));
+    WMF_TRY(sc.in(in->stream_long, (size_t)N, &P.stream_long));
+    WMF_TRY(sc.in(in->stream_slope, (size_t)N, &P.stream_slope));
+    WMF_TRY(sc.in(in->elem_area, (size_t)N, &P.elem_area));
+    WMF_TRY(sc.in(in->evpserie, (size_t)T, &P.evp));
+    WMF_TRY(sc.in(in->calib, (size_t)11 * M, &P.calib));
+    if (in->n_records < 1) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: n_records must be >= 1");
+    WMF_TRY(sc.in(in->rain, (size_t)in->n_records * N, &P.rain));
+    // pos_evento is needed on both sides: validate on the host
+    std::vector<int32_t> h_pos((size_t)T);
+    if (Scope::on_device(in->pos_evento)) {
+        CU_TRY(ctx, cudaMemcpyAsync(h_pos.data(), in->pos_evento, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        memcpy(h_pos.data(), in->pos_evento, sizeof(int32_t) * T);
+    }
+    for (int t = 0; t < T; ++t)
+        if (h_pos[t] < 1 || h_pos[t] > in->n_records)
+            WMF_FAIL(ctx, WMF_ERR_ARG, "shia: pos_evento(%d)=%d outside 1..n_records=%d", t + 1, h_pos[t], in->n_records);
+    WMF_TRY(sc.in(in->pos_evento, (size_t)T, &P.pos));
+    const float *d_storage = nullptr, *d_stoin = nullptr, *d_hspeedin = nullptr;
+    // StoIn / HspeedIn are honoured when their first element is > 0 (:271, :285)
+    auto first_positive = [&](const float *p, bool *res) -> int {
+        float v = 0.f;
+        if (!p) { *res = false; return WMF_OK; }
+        if (Scope::on_device(p)) {
+            CU_TRY(ctx, cudaMemcpyAsync(&v, p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        } else v = p[0];
+        *res = v > 0.0f;
+        return WMF_OK;
+    };
+    bool use_stoin = false, use_hsin = false;
+    WMF_TRY(first_positive(in->stoin, &use_stoin));
+    WMF_TRY(first_positive(in->hspeedin, &use_hsin));
+    if (!use_stoin && !in->storage) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: StoIn(1,1) <= 0 and no module Storage given");
+    if (use_stoin) WMF_TRY(sc.in(in->stoin, (size_t)5 * N, &d_stoin));
+    else WMF_TRY(sc.in(in->storage, (size_t)5 * N, &d_storage));
+    if (use_hsin) WMF_TRY(sc.in(in->hspeedin, (size_t)4 * N, &d_hspeedin));
+    P.hs_state = use_hsin ? 1 : 0;
+
+    // ---- plan ----
+    int32_t *lev_a, *lev_b, *jmp_a, *jmp_b, *nch, *cmin, *cmax, *cs, *level_first, *fq, *fh, *posq, *posh;
+    uint32_t *tw;
+    int *d_err;
+    WMF_TRY(sc.alloc(&lev_a, (size_t)N)); WMF_TRY(sc.alloc(&lev_b, (size_t)N));
+    WMF_TRY(sc.alloc(&jmp_a, (size_t)N)); WMF_TRY(sc.alloc(&jmp_b, (size_t)N));
+    WMF_TRY(sc.alloc(&nch, (size_t)N)); WMF_TRY(sc.alloc(&cmin, (size_t)N)); WMF_TRY(sc.alloc(&cmax, (size_t)N));
+    WMF_TRY(sc.alloc(&cs, (size_t)N)); WMF_TRY(sc.alloc(&tw, (size_t)N));
+    WMF_TRY(sc.alloc(&fq, (size_t)N)); WMF_TRY(sc.alloc(&fh, (size_t)N));
+    WMF_TRY(sc.alloc(&posq, (size_t)N)); WMF_TRY(sc.alloc(&posh, (size_t)N));
+    WMF_TRY(sc.alloc(&d_err, 2));
+    CU_TRY(ctx, cudaMemsetAsync(d_err, 0, 2 * sizeof(int), ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(nch, 0, sizeof(int32_t) * (size_t)N, ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(cmin, 0x7f, sizeof(int32_t) * (size_t)N, ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(cmax, 0, sizeof(int32_t) * (size_t)N, ctx->stream));
+    const int B = 256, G = grid_for(N, B);
+    LAUNCH(ctx, k_plan_init, G, B, 0, P.drena, stride, N, lev_a, jmp_a, nch, cmin, cmax, d_err);
+    int herr = 0;
+    WMF_TRY(read_flag(ctx, d_err, &herr));
+    if (herr == 1) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "shia: drena is not upstream-first (need 0 <= id < n and parent index > cell index)");
+    if (herr == 2) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "shia: drena has an outlet (id 0) that is not the last cell");
+    {
+        int32_t dlast = 1;
+        CU_TRY(ctx, cudaMemcpyAsync(&dlast, P.drena + (size_t)(N - 1) * stride, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (dlast != 0) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "shia: the last cell must be the outlet (drena == 0)");
+    }
+    for (int round = 0; round < 40; ++round) {
+        CU_TRY(ctx, cudaMemsetAsync(d_err + 1, 0, sizeof(int), ctx->stream));
+        LAUNCH(ctx, k_plan_jump, G, B, 0, lev_a, jmp_a, N, lev_b, jmp_b, d_err + 1);
+        std::swap(lev_a, lev_b);
+        std::swap(jmp_a, jmp_b);
+        int more = 0;
+        WMF_TRY(read_flag(ctx, d_err + 1, &more));
+        if (!more) break;
+    }
+    int32_t Lmax = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&Lmax, lev_a, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (Lmax < 0 || Lmax >= (1 << 24)) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "shia: tree depth %d unsupported", Lmax);
+    WMF_TRY(sc.alloc(&level_first, (size_t)Lmax + 2));
+    CU_TRY(ctx, cudaMemsetAsync(level_first, 0xff, sizeof(int32_t) * ((size_t)Lmax + 2), ctx->stream));
+    LAUNCH(ctx, k_plan_pack, G, B, 0, lev_a, nch, cmin, cmax, d_unit, d_control, d_controlh, N, tw, cs, level_first, fq, fh, d_err);
+    WMF_TRY(read_flag(ctx, d_err, &herr));
+    if (herr == 3 || herr == 5)
+        WMF_FAIL(ctx, WMF_ERR_TOPOLOGY,
+                 "shia: cells are not in basin_find order (levels must be non-increasing and the cells draining into one cell "
+                 "contiguous); pass the structure produced by basin_find/basin_cut");
+    if (herr == 4 || herr == 6) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "shia: more than 15 cells drain into one cell, or depth >= 2^24");
+    if (herr == 7) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: unit_type must be 1, 2 or 3");
+    std::vector<int32_t> h_first((size_t)Lmax + 2);
+    CU_TRY(ctx, cudaMemcpyAsync(h_first.data(), level_first, sizeof(int32_t) * ((size_t)Lmax + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    int64_t nq = 0, nh = 0;
+    WMF_TRY(wmf_device_exclusive_scan_i32(ctx, sc, fq, posq, N, &nq));
+    WMF_TRY(wmf_device_exclusive_scan_i32(ctx, sc, fh, posh, N, &nh));
+    if (nq + 1 > cfg->n_cont) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: %lld control cells need n_cont >= %lld, got %d", (long long)nq, (long long)nq + 1, cfg->n_cont);
+    if (nh > cfg->n_conth) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: %lld humidity control cells but n_conth = %d", (long long)nh, cfg->n_conth);
+    int32_t *ctrl_cells, *ctrlh_cells;
+    WMF_TRY(sc.alloc(&ctrl_cells, (size_t)nq + 1));
+    WMF_TRY(sc.alloc(&ctrlh_cells, (size_t)nh + 1));
+    LAUNCH(ctx, k_compact, G, B, 0, fq, posq, N, ctrl_cells);
+    LAUNCH(ctx, k_compact, G, B, 0, fh, posh, N, ctrlh_cells);
+    P.tw = tw; P.cs = cs; P.Lmax = Lmax;
+    P.ctrl_cells = ctrl_cells; P.ctrlh_cells = ctrlh_cells; P.n_ctrl = (int)nq; P.n_ctrlh = (int)nh;
+
+    // ---- state ----
+    const size_t NM = (size_t)N * M;
+    WMF_TRY(sc.alloc(&P.sto, 5 * NM));
+    WMF_TRY(sc.alloc(&P.hsp, 4 * NM));
+    WMF_TRY(sc.alloc(&P.outb, 8 * NM));
+    double *d_sto0, *d_recsum;
+    WMF_TRY(sc.alloc(&d_sto0, 1));
+    WMF_TRY(sc.alloc(&d_recsum, (size_t)in->n_records));
+    CU_TRY(ctx, cudaMemsetAsync(d_sto0, 0, sizeof(double), ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(d_recsum, 0, sizeof(double) * (size_t)in->n_records, ctx->stream));
+    LAUNCH(ctx, k_state_init, G, B, 0, use_stoin ? d_stoin : d_storage, use_stoin ? 0.0f : cfg->storage_constant, N, M, P.sto, d_sto0);
+    LAUNCH(ctx, k_hspeed_init, grid_for((long long)NM, B), B, 0, d_hspeedin, N, M, P.hsp);
+    const bool per_run = (M == 1);
+    // ---- outputs ----
+    const size_t QN = (size_t)M * cfg->n_cont * T, HN = (size_t)M * cfg->n_conth * T;
+    WMF_TRY(sc.out(out->q, QN, &P.q));
+    WMF_TRY(sc.out(out->speed, QN, &P.speed));
+    WMF_TRY(sc.out(out->areacontrol, QN, &P.area));
+    WMF_TRY(sc.out(out->hum, HN, &P.hum));
+    WMF_TRY(sc.out(out->st1, HN, &P.st1o));
+    WMF_TRY(sc.out(out->st3, HN, &P.st3o));
+    if (P.q) CU_TRY(ctx, cudaMemsetAsync(P.q, 0, sizeof(float) * QN, ctx->stream));
+    if (P.speed) CU_TRY(ctx, cudaMemsetAsync(P.speed, 0, sizeof(float) * QN, ctx->stream));
+    if (P.area) CU_TRY(ctx, cudaMemsetAsync(P.area, 0, sizeof(float) * QN, ctx->stream));
+    if (P.hum) CU_TRY(ctx, cudaMemsetAsync(P.hum, 0, sizeof(float) * HN, ctx->stream));
+    if (P.st1o) CU_TRY(ctx, cudaMemsetAsync(P.st1o, 0, sizeof(float) * HN, ctx->stream));
+    if (P.st3o) CU_TRY(ctx, cudaMemsetAsync(P.st3o, 0, sizeof(float) * HN, ctx->stream));
+    float *d_stoout, *d_hsout, *d_balance = nullptr, *d_mean_rain = nullptr, *d_acum_rain = nullptr, *d_mean_storage = nullptr,
+          *d_mean_speed = nullptr, *d_mean_retorno = nullptr;
+    WMF_TRY(sc.out(out->stoout, 5 * NM, &d_stoout));
+    WMF_TRY(sc.out(out->hspeed_out, 4 * NM, &d_hsout));
+    if (per_run) {
+        WMF_TRY(sc.out(out->balance, (size_t)T, &d_balance));
+        WMF_TRY(sc.out(out->mean_rain, (size_t)T, &d_mean_rain));
+        WMF_TRY(sc.out(out->acum_rain, (size_t)N, &d_acum_rain));
+        if (cfg->show_storage) WMF_TRY(sc.out(out->mean_storage, (size_t)5 * T, &d_mean_storage));
+        if (cfg->show_mean_speed) WMF_TRY(sc.out(out->mean_speed, (size_t)4 * T, &d_mean_speed));
+        if (cfg->retorno_gr == 1.0f && cfg->show_mean_retorno) WMF_TRY(sc.out(out->mean_retorno, (size_t)T, &d_mean_retorno));
+        if (cfg->retorno_gr == 1.0f && (out->retorned || d_mean_retorno)) {
+            P.want_retorned = 1;
+            if (out->retorned && !(cfg->show_mean_retorno == 1 || cfg->save_retorno == 1)) {
+                WMF_TRY(sc.out(out->retorned, (size_t)N, &P.retorned));
+                CU_TRY(ctx, cudaMemsetAsync(P.retorned, 0, sizeof(float) * (size_t)N, ctx->stream));
+            }
+        }
+        P.want_red = (d_balance || d_mean_storage || d_mean_speed || d_mean_retorno) ? 1 : 0;
+    }
+    if (P.want_red) {
+        WMF_TRY(sc.alloc(&P.red, (size_t)T * RQ_COUNT * RED_SUB));
+        CU_TRY(ctx, cudaMemsetAsync(P.red, 0, sizeof(double) * (size_t)T * RQ_COUNT * RED_SUB, ctx->stream));
+    }
+    // ---- sediments / slides ----
+    float *d_zmin = nullptr, *d_zcrit = nullptr, *d_zmax = nullptr, *d_bo = nullptr, *d_risk = nullptr;
+    if (sed) {
+        WMF_TRY(sc.in(in->krus, (size_t)N, &P.krus));
+        WMF_TRY(sc.in(in->crus, (size_t)N, &P.crus));
+        WMF_TRY(sc.in(in->prus, (size_t)N, &P.prus));
+        WMF_TRY(sc.in(in->parliac, (size_t)3 * N, &P.parliac));
+        const float *d_vd0;
+        WMF_TRY(sc.in(in->vd_init, (size_t)3 * N, &d_vd0));
+        WMF_TRY(sc.alloc(&P.sed, 12 * NM));
+        WMF_TRY(sc.alloc(&P.sedout, 24 * NM));
+        WMF_TRY(sc.alloc(&P.volero, NM));
+        WMF_TRY(sc.alloc(&P.voldepo, NM));
+        WMF_TRY(sc.alloc(&P.sedtot, 6));
+        CU_TRY(ctx, cudaMemsetAsync(P.volero, 0, sizeof(float) * NM, ctx->stream));
+        CU_TRY(ctx, cudaMemsetAsync(P.voldepo, 0, sizeof(float) * NM, ctx->stream));
+        CU_TRY(ctx, cudaMemsetAsync(P.sedtot, 0, sizeof(double) * 6, ctx->stream));
+        CU_TRY(ctx, cudaMemsetAsync(P.sedout, 0, sizeof(float) * 24 * NM, ctx->stream));
+        LAUNCH(ctx, k_sed_init, grid_for((long long)NM, B), B, 0, d_vd0, N, M, P.sed);
+        WMF_TRY(sc.out(out->qsed, QN * 3, &P.qsed));
+        if (P.qsed) CU_TRY(ctx, cudaMemsetAsync(P.qsed, 0, sizeof(float) * QN * 3, ctx->stream));
+    }
+    if (slides) {
+        WMF_TRY(sc.in(in->sl_zs, (size_t)N, &P.sl_zs));
+        WMF_TRY(sc.in(in->sl_gammas, (size_t)N, &P.sl_gammas));
+        WMF_TRY(sc.in(in->sl_cohesion, (size_t)N, &P.sl_cohesion));
+        WMF_TRY(sc.in(in->sl_frictionangle, (size_t)N, &P.sl_friction));
+        WMF_TRY(sc.in(in->sl_radslope, (size_t)N, &P.sl_radslope));
+        WMF_TRY(sc.alloc(&d_zmin, (size_t)N)); WMF_TRY(sc.alloc(&d_zcrit, (size_t)N)); WMF_TRY(sc.alloc(&d_zmax, (size_t)N));
+        WMF_TRY(sc.alloc(&d_bo, (size_t)N)); WMF_TRY(sc.alloc(&d_risk, (size_t)N));
+        WMF_TRY(sc.alloc(&P.sl_slid, (size_t)N)); WMF_TRY(sc.alloc(&P.sl_marktime, (size_t)N));
+        WMF_TRY(sc.out(out->sl_slideacumulate, (size_t)N, &P.sl_acum));
+        if (!P.sl_acum) WMF_TRY(sc.alloc(&P.sl_acum, (size_t)N));
+        WMF_TRY(sc.out(out->sl_slidencelltime, (size_t)T, &P.sl_ncelltime));
+        if (!P.sl_ncelltime) WMF_TRY(sc.alloc(&P.sl_ncelltime, (size_t)T));
+        CU_TRY(ctx, cudaMemsetAsync(P.sl_ncelltime, 0, sizeof(int32_t) * (size_t)T, ctx->stream));
+        float *d_cosr, *d_sinr, *d_tanfa;
+        WMF_TRY(sc.alloc(&d_cosr, (size_t)N)); WMF_TRY(sc.alloc(&d_sinr, (size_t)N)); WMF_TRY(sc.alloc(&d_tanfa, (size_t)N));
+        LAUNCH(ctx, k_slide_allocate, G, B, 0, P, d_zmin, d_zcrit, d_zmax, d_bo, d_risk, d_cosr, d_sinr, d_tanfa);
+        P.sl_zcrit = d_zcrit;
+        P.sl_risk = d_risk;
+        P.sl_cosr = d_cosr; P.sl_sinr = d_sinr; P.sl_tanfa = d_tanfa;
+    }
+    // rain statistics that do not depend on the model state
+    if (per_run) {
+        dim3 rg((unsigned)std::min(grid_for(N, 256), 64), (unsigned)in->n_records);
+        LAUNCH(ctx, k_rain_record_sum, rg, 256, 0, P.rain, N, d_recsum);
+        if (d_acum_rain) LAUNCH(ctx, k_acum_rain, G, B, 0, P.rain, P.pos, N, T, d_acum_rain);
+    }
+
+    // ---- the wavefront ----
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // h_first is complete
+    auto level_end = [&](int L) { return L == 0 ? N : h_first[L - 1]; };
+    const int n_waves = T + Lmax;
+    CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int w = 0; w < n_waves; ++w) {
+        const int Lhi = std::min(Lmax, Lmax - w + T - 1), Llo = std::max(0, Lmax - w);
+        const int lo = h_first[Lhi], hi = level_end(Llo);
+        if (hi <= lo) continue;
+        if (sed && slides) launch_wave<true, true>(ctx, P, w, lo, hi);
+        else if (sed) launch_wave<true, false>(ctx, P, w, lo, hi);
+        else if (slides) launch_wave<false, true>(ctx, P, w, lo, hi);
+        else launch_wave<false, false>(ctx, P, w, lo, hi);
+    }
+    CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->last_levels = Lmax + 1;
+    ctx->last_waves = n_waves;
+
+    // ---- epilogue ----
+    if (d_stoout || d_hsout) LAUNCH(ctx, k_state_final, grid_for((long long)NM, B), B, 0, P, d_stoout, d_hsout);
+    if (per_run && (d_balance || d_mean_rain || d_mean_storage || d_mean_speed || d_mean_retorno)) {
+        double *red = P.red;
+        if (!red) {  // only mean_rain wanted
+            WMF_TRY(sc.alloc(&red, (size_t)T * RQ_COUNT * RED_SUB));
+            CU_TRY(ctx, cudaMemsetAsync(red, 0, sizeof(double) * (size_t)T * RQ_COUNT * RED_SUB, ctx->stream));
+        }
+        LAUNCH(ctx, k_shia_epilogue, grid_for(T, 128), 128, 0, red, d_recsum, P.pos, d_sto0, N, T, P.show_storage, d_balance,
+               d_mean_rain, d_mean_storage, d_mean_speed, d_mean_retorno);
+    }
+    if (sed) {
+        float *vs, *vd, *vsc, *vdc, *ve, *vdp, *erot, *dept;
+        WMF_TRY(sc.out(out->vs, 3 * NM, &vs)); WMF_TRY(sc.out(out->vd, 3 * NM, &vd));
+        WMF_TRY(sc.out(out->vsc, 3 * NM, &vsc)); WMF_TRY(sc.out(out->vdc, 3 * NM, &vdc));
+        LAUNCH(ctx, k_sed_final, G, B, 0, P.sed, N, vs, vd, vsc, vdc);
+        WMF_TRY(sc.out(out->volero, NM, &ve)); WMF_TRY(sc.out(out->voldepo, NM, &vdp));
+        if (ve) CU_TRY(ctx, cudaMemcpyAsync(ve, P.volero, sizeof(float) * NM, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (vdp) CU_TRY(ctx, cudaMemcpyAsync(vdp, P.voldepo, sizeof(float) * NM, cudaMemcpyDeviceToDevice, ctx->stream));
+        WMF_TRY(sc.out(out->erot, 3, &erot)); WMF_TRY(sc.out(out->dept, 3, &dept));
+        if (erot) LAUNCH(ctx, k_d2f, 1, 32, 0, P.sedtot, 3, erot);
+        if (dept) LAUNCH(ctx, k_d2f, 1, 32, 0, P.sedtot + 3, 3, dept);
+    }
+    if (slides) {
+        float *o;
+        auto copy_out = [&](float *dst, const float *src) -> int {
+            if (!dst) return WMF_OK;
+            float *d;
+            WMF_TRY(sc.out(dst, (size_t)N, &d));
+            CU_TRY(ctx, cudaMemcpyAsync(d, src, sizeof(float) * (size_t)N, cudaMemcpyDeviceToDevice, ctx->stream));
+            return WMF_OK;
+        };
+        WMF_TRY(copy_out(out->sl_zmin, d_zmin)); WMF_TRY(copy_out(out->sl_zcrit, d_zcrit));
+        WMF_TRY(copy_out(out->sl_zmax, d_zmax)); WMF_TRY(copy_out(out->sl_bo, d_bo));
+        WMF_TRY(copy_out(out->sl_riskvector, d_risk));
+        WMF_TRY(sc.out(out->sl_slideocurrence, (size_t)N, &o));
+        if (o) LAUNCH(ctx, k_slide_final, G, B, 0, P, o);
+    }
+    if (per_run && out->retorned && cfg->retorno_gr == 1.0f && (cfg->show_mean_retorno == 1 || cfg->save_retorno == 1)) {
+        // the Fortran zeroes Retorned after every step in this mode (:841-843)
+        float *r;
+        WMF_TRY(sc.out(out->retorned, (size_t)N, &r));
+        CU_TRY(ctx, cudaMemsetAsync(r, 0, sizeof(float) * (size_t)N, ctx->stream));
+    }
+    WMF_TRY(sc.finish());
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    return WMF_OK;
+}
+
+int wmf_eval_scores(wmf_ctx *ctx, const float *q, int32_t n_members, int32_t n_cont, int32_t n_reg, int32_t row,
+                    const float *qobs, float *scores) {
+    if (!ctx || !q || !qobs || !scores || n_members <= 0 || n_cont <= 0 || n_reg <= 0 || row < 0 || row >= n_cont)
+        return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    const float *d_q, *d_o;
+    float *d_s;
+    WMF_TRY(sc.in(q, (size_t)n_members * n_cont * n_reg, &d_q));
+    WMF_TRY(sc.in(qobs, (size_t)n_reg, &d_o));
+    WMF_TRY(sc.out(scores, (size_t)2 * n_members, &d_s));
+    LAUNCH(ctx, k_eval_scores, n_members, 256, 0, d_q, n_cont, n_reg, row, d_o, d_s);
+    return sc.finish();
+}
+
+int wmf_calc_speed(wmf_ctx *ctx, float sm, float coef, float expo, float elem_long, float dt, int32_t calc_niter,
+                   float *speed_inout, float *area_out) {
+    if (!ctx || !speed_inout || !area_out || calc_niter < 1) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    float *d;
+    WMF_TRY(sc.alloc(&d, 2));
+    CU_TRY(ctx, cudaMemcpyAsync(d, speed_inout, 4, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_calc_speed, 1, 1, 0, sm, coef, expo, elem_long, dt, calc_niter, d);
+    float h[2];
+    CU_TRY(ctx, cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *speed_inout = h[0];
+    *area_out = h[1];
+    return WMF_OK;
+}
+
+}  // extern "C"

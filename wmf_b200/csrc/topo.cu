@@ -1,0 +1,1120 @@
+// topo.cu -- Path A: D8 flow-direction topology (module `cu`, wmf/cuencas.f90) on sm_100a.
+//
+//  basin_find   level-synchronous BFS in ONE persistent cooperative kernel.  Queue order == the Fortran's
+//               FIFO order (cuencas.f90:552-589): children of queue entry q are appended in the 3x3 scan
+//               order kf=1..3,kc=1..3, positions from an exclusive scan of child counts in queue order.
+//               Narrow frontiers run inside block 0 with __syncthreads only; wide ones use all SMs with two
+//               grid barriers per level.
+//  basin_acum   leaf-to-root "last arriver climbs" sweep: one 64-bit atomicAdd per tree edge carries both the
+//               partial cell count and the arrival counter, no global barriers, exact (integer sums commute).
+//  acum_var /   same sweep, but the last arriver *gathers* its children in ascending cell order, which
+//  propagate    reproduces the Fortran's fp32 addition order bit for bit.
+//  the rest     one thread per cell / raster cell.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+// ---------------------------------------------------------------------------------------------------
+// basin_find
+// ---------------------------------------------------------------------------------------------------
+struct FindState {
+    long long fs, fe;  // current frontier = queue positions [fs, fe)
+    int depth;         // levels completed
+    int err;           // 1 = queue overflow (cyclic DIR)
+    int done;
+    int pad;
+    int blocksum[1024];
+};
+
+constexpr int FIND_THREADS = 1024;
+constexpr int FIND_SB_MAX = 8192;     // frontiers up to this size stay inside block 0
+constexpr int FIND_MASK_CAP = 32768;  // per-block child-mask cache (bytes of shared memory)
+
+// 8-bit mask of the neighbours of raster cell `lin` that drain into it, bit order = Fortran scan order
+// (kf outer, kc inner, centre skipped): cuencas.f90:555-571.
+__device__ __forceinline__ unsigned probe_children(const int32_t *__restrict__ dir, int nc, int nr, int lin) {
+    const int c0 = lin % nc, f0 = lin / nc;  // 0-based
+    unsigned m = 0;
+    int bit = 0;
+#pragma unroll
+    for (int kf = 1; kf <= 3; ++kf) {
+#pragma unroll
+        for (int kc = 1; kc <= 3; ++kc) {
+            if (kf == 2 && kc == 2) continue;
+            const int c = c0 + kc - 2, f = f0 + kf - 2;
+            if (c >= 0 && c < nc && f >= 0 && f < nr) {
+                if (__ldg(dir + (size_t)f * nc + c) == 3 * kf - kc + 1) m |= 1u << bit;
+            }
+            ++bit;
+        }
+    }
+    return m;
+}
+
+__device__ __forceinline__ void write_children(unsigned m, int lin, int nc, long long pos, int parent_qpos1,
+                                               int32_t *__restrict__ q_lin, int32_t *__restrict__ q_par) {
+    int bit = 0;
+#pragma unroll
+    for (int kf = 1; kf <= 3; ++kf) {
+#pragma unroll
+        for (int kc = 1; kc <= 3; ++kc) {
+            if (kf == 2 && kc == 2) continue;
+            if (m & (1u << bit)) {
+                q_lin[pos] = lin + (kf - 2) * nc + (kc - 2);
+                q_par[pos] = parent_qpos1;
+                ++pos;
+            }
+            ++bit;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FIND_THREADS, 1)
+k_basin_find(const int32_t *__restrict__ dir, int nc, int nr, int32_t *__restrict__ q_lin,
+             int32_t *__restrict__ q_par, long long cap, FindState *st) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int s_scan[33];
+    __shared__ int s_red[32];
+    __shared__ unsigned char s_mask[FIND_MASK_CAP];
+    const int tid = threadIdx.x, b = blockIdx.x, nb = gridDim.x;
+    long long fs = 0, fe = 1;
+    int depth = 0;
+    for (;;) {
+        const long long F = fe - fs;
+        if (F <= FIND_SB_MAX) {
+            // ---- narrow frontier: block 0 advances alone, level after level -------------------------
+            if (b == 0) {
+                int err = 0, done = 0;
+                for (;;) {
+                    long long running = fe;
+                    const long long Fl = fe - fs;
+                    for (long long base = fs; base < fe; base += FIND_THREADS) {
+                        const long long p = base + tid;
+                        unsigned m = 0;
+                        int lin = 0;
+                        if (p < fe) {
+                            lin = q_lin[p];
+                            m = probe_children(dir, nc, nr, lin);
+                        }
+                        int tot;
+                        const int ex = block_scan_excl(__popc(m), s_scan, &tot);
+                        if (running + tot > cap) { err = 1; break; }
+                        if (m) write_children(m, lin, nc, running + ex, (int)(p + 1), q_lin, q_par);
+                        running += tot;
+                    }
+                    __syncthreads();
+                    if (err) break;
+                    ++depth;
+                    fs = fe;
+                    fe = running;
+                    if (fe == fs) { done = 1; break; }
+                    if (fe - fs > FIND_SB_MAX) break;
+                    (void)Fl;
+                }
+                if (tid == 0) {
+                    st->fs = fs; st->fe = fe; st->depth = depth; st->err = err; st->done = done || err;
+                }
+            }
+            grid.sync();
+            fs = st->fs; fe = st->fe; depth = st->depth;
+            const int done = st->done;
+            grid.sync();  // nobody may overwrite st before everyone has read it
+            if (done) break;
+            continue;
+        }
+        // ---- wide frontier: all blocks, chunked in queue order ----------------------------------------
+        long long chunk = (F + nb - 1) / nb;
+        chunk = (chunk + FIND_THREADS - 1) / FIND_THREADS * FIND_THREADS;
+        const long long lo = fs + (long long)b * chunk;
+        long long hi = lo + chunk;
+        if (hi > fe) hi = fe;
+        // phase 1: count children of my chunk
+        int cnt = 0;
+        for (long long p = lo + tid; p < hi; p += FIND_THREADS) {
+            const unsigned m = probe_children(dir, nc, nr, q_lin[p]);
+            if (p - lo < FIND_MASK_CAP) s_mask[p - lo] = (unsigned char)m;
+            cnt += __popc(m);
+        }
+        cnt = warp_sum_i(cnt);
+        if ((tid & 31) == 0) s_red[tid >> 5] = cnt;
+        __syncthreads();
+        if (tid < 32) {
+            int v = s_red[tid];
+            v = warp_sum_i(v);
+            if (tid == 0) st->blocksum[b] = v;
+        }
+        grid.sync();
+        // phase 2: my offset = sum of the counts of the blocks before me; total = sum of all
+        int mine = 0, all = 0;
+        for (int j = tid; j < nb; j += FIND_THREADS) {
+            const int v = st->blocksum[j];
+            all += v;
+            if (j < b) mine += v;
+        }
+        mine = warp_sum_i(mine);
+        all = warp_sum_i(all);
+        __syncthreads();
+        if ((tid & 31) == 0) { s_red[tid >> 5] = mine; }
+        __syncthreads();
+        int off = 0;
+        if (tid < 32) off = warp_sum_i(s_red[tid]);
+        __syncthreads();
+        if ((tid & 31) == 0) { s_red[tid >> 5] = all; }
+        __syncthreads();
+        int total = 0;
+        if (tid < 32) total = warp_sum_i(s_red[tid]);
+        if (tid == 0) { s_scan[0] = off; s_scan[1] = total; }
+        __syncthreads();
+        off = s_scan[0];
+        total = s_scan[1];
+        __syncthreads();
+        if (fe + total > cap) {
+            if (b == 0 && tid == 0) { st->err = 1; st->depth = depth; st->fs = fs; st->fe = fe; }
+            break;  // uniform across the grid
+        }
+        long long running = fe + off;
+        for (long long base = lo; base < hi; base += FIND_THREADS) {
+            const long long p = base + tid;
+            unsigned m = 0;
+            int lin = 0;
+            if (p < hi) {
+                lin = q_lin[p];
+                m = (p - lo < FIND_MASK_CAP) ? (unsigned)s_mask[p - lo] : probe_children(dir, nc, nr, lin);
+            }
+            int tot;
+            const int ex = block_scan_excl(__popc(m), s_scan, &tot);
+            if (m) write_children(m, lin, nc, running + ex, (int)(p + 1), q_lin, q_par);
+            running += tot;
+        }
+        ++depth;
+        fs = fe;
+        fe = fe + total;
+        grid.sync();
+        if (total == 0) {
+            if (b == 0 && tid == 0) { st->fs = fs; st->fe = fe; st->depth = depth; st->err = 0; }
+            break;
+        }
+    }
+}
+
+__global__ void k_find_seed(int32_t *q_lin, int32_t *q_par, int lin, FindState *st) {
+    q_lin[0] = lin;
+    q_par[0] = 0;
+    st->fs = 0; st->fe = 1; st->depth = 0; st->err = 0; st->done = 0;
+}
+
+// cuencas.f90:592-607 : basin_f(:,i) = (drain id, col, row) of queue position n-i+1
+__global__ void k_basin_cut(const int32_t *__restrict__ q_lin, const int32_t *__restrict__ q_par, int n, int nc,
+                            int32_t *__restrict__ basin_f) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = n - 1 - i;
+    const int lin = q_lin[p];
+    basin_f[3 * (size_t)i + 0] = q_par[p];
+    basin_f[3 * (size_t)i + 1] = lin % nc + 1;
+    basin_f[3 * (size_t)i + 2] = lin / nc + 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// accumulation sweeps
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_fill_u64(unsigned long long *w, long long n, unsigned long long v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) w[i] = v;
+}
+
+// high half of w[parent] counts down one per child; flags a drain table that is not upstream-first
+__global__ void k_count_children_u64(const int32_t *__restrict__ drain, int stride, int n,
+                                     unsigned long long *__restrict__ w, int *__restrict__ err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d = drain[(size_t)i * stride];
+    if (d == 0) return;
+    const int p = n - d;
+    if (d < 0 || p <= i || p >= n) { *err = 1; return; }
+    atomicAdd(&w[p], 0xFFFFFFFF00000000ull);
+}
+
+// cuencas.f90:659-680.  w[i] = (arrivals - nchildren) << 32 | partial count.  A leaf climbs while it is the last
+// child to arrive at each ancestor; the atomic's return value carries the finished subtotal.
+// (the leaf test must not read w: a finished inner cell also shows a zero counter, so leaves are flagged up front)
+__global__ void k_mark_leaves(const unsigned long long *__restrict__ w, int n, int32_t *__restrict__ leaf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) leaf[i] = ((unsigned)(w[i] >> 32) == 0u) ? 1 : 0;
+}
+
+__global__ void k_acum_climb(const int32_t *__restrict__ drain, int stride, int n,
+                             unsigned long long *__restrict__ w, const int32_t *__restrict__ leaf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!leaf[i]) return;  // has children: the last of them to arrive finishes this cell
+    unsigned v = 1u;
+    int cur = i;
+    for (;;) {
+        const int d = drain[(size_t)cur * stride];
+        if (d == 0) break;
+        const int p = n - d;
+        const unsigned long long old = atomicAdd(&w[p], (1ull << 32) + (unsigned long long)v);
+        if ((unsigned)(old >> 32) != 0xFFFFFFFFu) break;  // not the last arriver
+        v = (unsigned)old + v;
+        cur = p;
+    }
+}
+
+__global__ void k_acum_extract(const unsigned long long *__restrict__ w, int n, int32_t *__restrict__ acum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acum[i] = (int32_t)(unsigned)w[i];
+}
+
+// --- ordered (floating point) variant: CSR of children, ascending ---
+__global__ void k_count_children_i32(const int32_t *__restrict__ drain, int stride, int n,
+                                     int32_t *__restrict__ cnt, int *__restrict__ err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d = drain[(size_t)i * stride];
+    if (d == 0) return;
+    const int p = n - d;
+    if (d < 0 || p <= i || p >= n) { *err = 1; return; }
+    atomicAdd(&cnt[p], 1);
+}
+
+__global__ void k_fill_children(const int32_t *__restrict__ drain, int stride, int n,
+                                const int32_t *__restrict__ start, int32_t *__restrict__ cursor,
+                                int32_t *__restrict__ child) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d = drain[(size_t)i * stride];
+    if (d == 0) return;
+    const int p = n - d;
+    const int slot = atomicAdd(&cursor[p], 1);
+    child[start[p] + slot] = i;
+}
+
+__global__ void k_sort_children(const int32_t *__restrict__ start, const int32_t *__restrict__ cnt, int n,
+                                int32_t *__restrict__ child) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int s = start[j], c = cnt[j];
+    for (int a = 1; a < c; ++a) {  // insertion sort; D8 lists have at most 8 entries
+        const int key = child[s + a];
+        int k = a - 1;
+        while (k >= 0 && child[s + k] > key) {
+            child[s + k + 1] = child[s + k];
+            --k;
+        }
+        child[s + k + 1] = key;
+    }
+}
+
+// cuencas.f90:681-701 (positive_only = 0) and :1811-1833 (positive_only = 1)
+__global__ void k_acum_var_climb(const int32_t *__restrict__ drain, int stride, int n,
+                                 const int32_t *__restrict__ start, const int32_t *__restrict__ cnt,
+                                 const int32_t *__restrict__ child, int32_t *__restrict__ pending,
+                                 const float *__restrict__ var, float *val, int positive_only) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (cnt[i] != 0) return;
+    val[i] = var[i];
+    int cur = i;
+    for (;;) {
+        const int d = drain[(size_t)cur * stride];
+        if (d == 0) break;
+        const int p = n - d;
+        __threadfence();  // publish val[cur] before announcing the arrival
+        const int old = atomicSub(&pending[p], 1);
+        if (old != 1) break;
+        __threadfence();
+        float acc = var[p];
+        const int s = start[p], c = cnt[p];
+        for (int k = 0; k < c; ++k) {
+            const float v = __ldcg(val + child[s + k]);
+            if (!positive_only || v > 0.0f) acc = acc + v;
+        }
+        val[p] = acc;
+        cur = p;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device-wide exclusive scan (int32), three small kernels
+// ---------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const int32_t *__restrict__ in, int32_t *__restrict__ out,
+                                                             long long n, long long *__restrict__ tile_sum) {
+    __shared__ int sm[33];
+    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    int tot;
+    int ex = block_scan_excl(s, sm, &tot);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+    }
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tile_sums(long long *tile_sum, int ntiles, long long *total) {
+    __shared__ long long sm[1024];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += 1024) {
+        const int j = base + threadIdx.x;
+        long long v = (j < ntiles) ? tile_sum[j] : 0;
+        sm[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            long long t = (threadIdx.x >= o) ? sm[threadIdx.x - o] : 0;
+            __syncthreads();
+            sm[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (j < ntiles) tile_sum[j] = carry + sm[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += sm[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(int32_t *__restrict__ out, long long n,
+                                                           const long long *__restrict__ tile_sum) {
+    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    const int add = (int)tile_sum[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) out[base + k] += add;
+}
+
+int wmf_device_exclusive_scan_i32(wmf_ctx *ctx, Scope &sc, const int32_t *in, int32_t *out, int64_t n,
+                                  int64_t *total_host) {
+    if (n <= 0) {
+        if (total_host) *total_host = 0;
+        return WMF_OK;
+    }
+    const int ntiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+    long long *tile_sum;
+    WMF_TRY(sc.alloc(&tile_sum, (size_t)ntiles + 1));
+    LAUNCH(ctx, k_scan_tiles, ntiles, SCAN_THREADS, 0, in, out, (long long)n, tile_sum);
+    LAUNCH(ctx, k_scan_tile_sums, 1, 1024, 0, tile_sum, ntiles, tile_sum + ntiles);
+    LAUNCH(ctx, k_scan_add, ntiles, SCAN_THREADS, 0, out, (long long)n, tile_sum);
+    if (total_host) {
+        long long t;
+        CU_TRY(ctx, cudaMemcpyAsync(&t, tile_sum + ntiles, sizeof t, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        *total_host = t;
+    }
+    return WMF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-cell kernels
+// ---------------------------------------------------------------------------------------------------
+// cuencas.f90:623-644 (long, pend, elev) ; acum comes from the climb sweep
+__global__ void k_basics_cell(const int32_t *__restrict__ basin_f, const float *__restrict__ dem,
+                              const int32_t *__restrict__ dir, int n, float dxp, float *__restrict__ lng,
+                              float *__restrict__ pend, float *__restrict__ elev) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto cell_long = [&](int k) { return (dir[k] % 2 == 0) ? dxp : dxp * 1.41421354f; };  // dxp*sqrt(2.) in fp32
+    auto cell_pend = [&](int k, float lk) {  // pend of a non-outlet cell k
+        const int p = n - basin_f[3 * (size_t)k];
+        float s = fabsf(dem[k] - dem[p]) / lk;
+        return (s == 0.0f) ? 0.001f : s;
+    };
+    const float li = cell_long(i);
+    lng[i] = li;
+    elev[i] = dem[i];
+    float s;
+    if (basin_f[3 * (size_t)i] != 0) {
+        s = cell_pend(i, li);
+    } else {  // outlet copies the previous cell's slope (cuencas.f90:640)
+        s = 0.0f;
+        if (i > 0 && basin_f[3 * (size_t)(i - 1)] != 0) s = cell_pend(i - 1, cell_long(i - 1));
+        if (s == 0.0f) s = 0.001f;
+    }
+    pend[i] = s;
+}
+
+// fp64 sums of two fp32 arrays (pend_media, elevacion) + column / row histograms for the median centroid
+__global__ void k_basics_reduce(const int32_t *__restrict__ basin_f, const float *__restrict__ pend,
+                                const float *__restrict__ dem, int n, double *__restrict__ sums,
+                                int32_t *__restrict__ hist_col, int32_t *__restrict__ hist_row) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double a = 0.0, b = 0.0;
+    if (i < n) {
+        a = (double)pend[i];
+        b = (double)dem[i];
+        atomicAdd(&hist_col[basin_f[3 * (size_t)i + 1] - 1], 1);
+        atomicAdd(&hist_row[basin_f[3 * (size_t)i + 2] - 1], 1);
+    }
+    a = warp_sum_d(a);
+    b = warp_sum_d(b);
+    __shared__ double sa[32], sb[32];
+    if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sb[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = blockDim.x >> 5;
+        a = (threadIdx.x < nw) ? sa[threadIdx.x] : 0.0;
+        b = (threadIdx.x < nw) ? sb[threadIdx.x] : 0.0;
+        a = warp_sum_d(a);
+        b = warp_sum_d(b);
+        if (threadIdx.x == 0) { atomicAdd(&sums[0], a); atomicAdd(&sums[1], b); }
+    }
+}
+
+// cuencas.f90:797-808
+__global__ void k_coordxy(const int32_t *__restrict__ basin_f, int n, float xll, float yll, float dx, int nrows,
+                          float *__restrict__ x, float *__restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    x[i] = xll + dx * ((float)basin_f[3 * (size_t)i + 1] - 0.5f);
+    y[i] = yll + dx * ((float)(nrows - basin_f[3 * (size_t)i + 2]) + 0.5f);
+}
+
+// sum / count of the non-nodata cells of a raster (cuencas.f90:1159-1161); fp64 accumulation
+__global__ void k_map_mean(const float *__restrict__ mapa, long long tot, float nodatam, double *__restrict__ sum,
+                           unsigned long long *__restrict__ cnt) {
+    double s = 0.0;
+    unsigned long long c = 0;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < tot; k += (long long)gridDim.x * blockDim.x) {
+        const float v = mapa[k];
+        if (v != nodatam) { s += (double)v; ++c; }
+    }
+    s = warp_sum_d(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(sum, s); atomicAdd(cnt, c); }
+}
+
+// cuencas.f90:1163-1183
+__global__ void k_map2basin(const int32_t *__restrict__ basin_f, int n, const float *__restrict__ mapa, float xll,
+                            float yll, float dx, float dy, int nrows, float xllm, float yllm, int ncolsm, int nrowsm,
+                            float dxm, float dym, float nodatam, const double *__restrict__ sum,
+                            const unsigned long long *__restrict__ cnt, float *__restrict__ vec) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float xpos = xll + dx * ((float)basin_f[3 * (size_t)i + 1] - 0.5f);
+    const float ypos = yll + dy * ((float)(nrows - basin_f[3 * (size_t)i + 2]) + 0.5f);
+    float v = nodatam;
+    if (xpos > xllm && xpos < (xllm + dxm * (float)ncolsm) && ypos > yllm && ypos < (yllm + (float)nrowsm * dym)) {
+        int columna = (int)ceilf((xpos - xllm) / dxm);
+        int fila = (int)ceilf((ypos - yllm) / dym);
+        fila = nrowsm - fila + 1;
+        columna = min(max(columna, 1), ncolsm);
+        fila = min(max(fila, 1), nrowsm);
+        v = mapa[(size_t)(fila - 1) * ncolsm + (columna - 1)];
+        if (v == nodatam) v = (float)(*sum / (double)(*cnt));
+    }
+    vec[i] = v;
+}
+
+__global__ void k_minmax_colrow(const int32_t *__restrict__ basin_f, int n, int32_t *__restrict__ mm) {
+    int cmin = INT_MAX, cmax = INT_MIN, fmin = INT_MAX, fmax = INT_MIN;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = basin_f[3 * (size_t)i + 1], f = basin_f[3 * (size_t)i + 2];
+        cmin = min(cmin, c); cmax = max(cmax, c); fmin = min(fmin, f); fmax = max(fmax, f);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+        fmin = min(fmin, __shfl_xor_sync(0xffffffffu, fmin, o));
+        fmax = max(fmax, __shfl_xor_sync(0xffffffffu, fmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&mm[0], cmin); atomicMax(&mm[1], cmax); atomicMin(&mm[2], fmin); atomicMax(&mm[3], fmax);
+    }
+}
+
+__global__ void k_fill_f32(float *a, long long n, float v) {
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) a[k] = v;
+}
+__global__ void k_fill_i32(int32_t *a, long long n, int32_t v) {
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) a[k] = v;
+}
+
+// cuencas.f90:1224-1228 / :1048-1050 : scatter a basin vector into a raster window
+__global__ void k_scatter_map(const int32_t *__restrict__ basin_f, const float *__restrict__ var, int n, int col0,
+                              int fil0, int ncm, float *__restrict__ mapa) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = basin_f[3 * (size_t)i + 1] - col0, f = basin_f[3 * (size_t)i + 2] - fil0;
+    mapa[(size_t)f * ncm + c] = var[i];
+}
+
+// cuencas.f90:1351-1353 (ge = 1) and :2127-2128 (ge = 0)
+__global__ void k_threshold_mask(const int32_t *__restrict__ acum, long long n, int umbral, int ge,
+                                 int32_t *__restrict__ cauce, unsigned long long *__restrict__ count) {
+    unsigned long long c = 0;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const int a = acum[k];
+        const int m = ge ? (a >= umbral) : (a > umbral);
+        cauce[k] = m;
+        c += m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (count && (threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
+// cuencas.f90:1455-1462
+__global__ void k_stream_type(const int32_t *__restrict__ acum, int n, const int32_t *__restrict__ umbrales, int nu,
+                              int32_t *__restrict__ types) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int a = acum[j];
+    int t = 1;
+    for (int i = 0; i < nu; ++i)
+        if (a > umbrales[i]) t = i + 2;
+    types[j] = t;
+}
+
+// cuencas.f90:2131-2174 : every hillslope cell walks down to its first channel cell
+__global__ void k_geo_hand(const int32_t *__restrict__ basin_f, const float *__restrict__ elev,
+                           const float *__restrict__ lng, const int32_t *__restrict__ cauce, int n,
+                           float *__restrict__ hand, float *__restrict__ hdnd, int32_t *__restrict__ a_quien) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float h = 0.0f, hd = 0.0f;
+    int aq = 0;
+    if (cauce[i] != 1) {
+        int it = i;
+        float lsum = lng[i];
+        for (;;) {
+            const int d = basin_f[3 * (size_t)it];
+            if (d == 0) break;  // non-channel outlet: 0,0,0
+            const int p = n - d;
+            if (cauce[p] == 1) {
+                h = elev[i] - elev[p];
+                hd = lsum;
+                aq = p + 1;
+                break;
+            } else if (basin_f[3 * (size_t)p] == 0) {
+                break;
+            } else {
+                it = p;
+                lsum = lsum + lng[p];
+            }
+        }
+    }
+    hand[i] = h;
+    hdnd[i] = hd;
+    a_quien[i] = aq;
+}
+
+// cuencas.f90:2175-2219 : raster-wide HAND, one thread per raster cell
+__global__ void k_geo_hand_global(const float *__restrict__ dem, const int32_t *__restrict__ dir,
+                                  const int32_t *__restrict__ red, int nc, int nr, int gncols, int gnrows,
+                                  float nodata, float *__restrict__ hand) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long tot = (long long)nc * nr;
+    if (k >= tot) return;
+    const int r0 = red[k];
+    float h = (r0 == 1) ? 0.0f : nodata;
+    if ((float)dir[k] != nodata && r0 == 0) {
+        int col = (int)(k % nc), fil = (int)(k / nc);  // 0-based
+        long long guard = 0;
+        for (;;) {
+            const int d = dir[(size_t)fil * nc + col];
+            if ((float)d == nodata) break;
+            if (d < 1 || d > 9 || d == 5) { h = nodata; break; }
+            col += (d - 1) % 3 - 1;  // keypad: 7 8 9 / 4 5 6 / 1 2 3
+            fil += 1 - (d - 1) / 3;
+            if (col >= 0 && col < gncols && fil >= 0 && fil < gnrows && col < nc && fil < nr) {
+                const int r = red[(size_t)fil * nc + col];
+                if (r == 1) { h = dem[k] - dem[(size_t)fil * nc + col]; break; }
+                if ((float)r == nodata) { h = nodata; break; }
+            } else { h = nodata; break; }
+            if (++guard > tot) break;
+        }
+    }
+    hand[k] = h;
+}
+
+// cuencas.f90:724-756
+__global__ void k_time_to_out(const int32_t *__restrict__ basin_f, const float *__restrict__ lng,
+                              const float *__restrict__ speed, int n, float *__restrict__ time) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = lng[i] / speed[i];
+    int drenaid = n - basin_f[3 * (size_t)i] + 1;  // 1-based
+    if (drenaid < n) {
+        for (;;) {
+            acc = acc + lng[drenaid - 1] / speed[drenaid - 1];
+            drenaid = n - basin_f[3 * (size_t)(drenaid - 1)] + 1;
+            if (drenaid >= n) break;
+        }
+    }
+    time[i] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host entry points
+// ---------------------------------------------------------------------------------------------------
+static int check_flag(wmf_ctx *ctx, int *d_err, const char *what) {
+    int e = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&e, d_err, sizeof e, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (e) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "%s", what);
+    return WMF_OK;
+}
+
+// integer subtree sums into d_acum (device pointer)
+static int acum_device(wmf_ctx *ctx, Scope &sc, const int32_t *d_drain, int stride, int n, int32_t *d_acum) {
+    unsigned long long *w;
+    int *d_err;
+    WMF_TRY(sc.alloc(&w, (size_t)n));
+    WMF_TRY(sc.alloc(&d_err, 1));
+    CU_TRY(ctx, cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
+    const int B = 256, G = grid_for(n, B);
+    LAUNCH(ctx, k_fill_u64, G, B, 0, w, (long long)n, 1ull);
+    LAUNCH(ctx, k_count_children_u64, G, B, 0, d_drain, stride, n, w, d_err);
+    WMF_TRY(check_flag(ctx, d_err, "drain table is not upstream-first (need 0 <= id < n and parent index > cell index)"));
+    LAUNCH(ctx, k_mark_leaves, G, B, 0, w, n, d_acum);  // the output buffer doubles as the leaf flag until extract
+    LAUNCH(ctx, k_acum_climb, G, B, 0, d_drain, stride, n, w, d_acum);
+    LAUNCH(ctx, k_acum_extract, G, B, 0, w, n, d_acum);
+    return WMF_OK;
+}
+
+static int acum_var_device(wmf_ctx *ctx, Scope &sc, const int32_t *d_drain, int stride, int n, const float *d_var,
+                           float *d_out, int positive_only) {
+    int32_t *cnt, *start, *cursor, *child, *pending;
+    int *d_err;
+    WMF_TRY(sc.alloc(&cnt, (size_t)n));
+    WMF_TRY(sc.alloc(&start, (size_t)n));
+    WMF_TRY(sc.alloc(&cursor, (size_t)n));
+    WMF_TRY(sc.alloc(&child, (size_t)n));
+    WMF_TRY(sc.alloc(&pending, (size_t)n));
+    WMF_TRY(sc.alloc(&d_err, 1));
+    CU_TRY(ctx, cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)n, ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)n, ctx->stream));
+    const int B = 256, G = grid_for(n, B);
+    LAUNCH(ctx, k_count_children_i32, G, B, 0, d_drain, stride, n, cnt, d_err);
+    WMF_TRY(check_flag(ctx, d_err, "drain table is not upstream-first (need 0 <= id < n and parent index > cell index)"));
+    WMF_TRY(wmf_device_exclusive_scan_i32(ctx, sc, cnt, start, n, nullptr));
+    LAUNCH(ctx, k_fill_children, G, B, 0, d_drain, stride, n, start, cursor, child);
+    LAUNCH(ctx, k_sort_children, G, B, 0, start, cnt, n, child);
+    CU_TRY(ctx, cudaMemcpyAsync(pending, cnt, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    LAUNCH(ctx, k_acum_var_climb, G, B, 0, d_drain, stride, n, start, cnt, child, pending, d_var, d_out, positive_only);
+    return WMF_OK;
+}
+
+extern "C" {
+
+int wmf_basin_find(wmf_ctx *ctx, float x, float y, const int32_t *dir, int32_t nc, int32_t nr, int32_t *nceldas) {
+    if (!ctx || !dir || !nceldas) return WMF_ERR_ARG;
+    const wmf_geo &g = ctx->geo;
+    if (nc != g.ncols || nr != g.nrows || nc <= 0 || nr <= 0)
+        WMF_FAIL(ctx, WMF_ERR_ARG, "basin_find: DIR is (%d,%d) but cu.ncols,nrows = (%d,%d)", nc, nr, g.ncols, g.nrows);
+    const long long celTot = (long long)nc * nr;
+    if (celTot >= 2147483647LL) WMF_FAIL(ctx, WMF_ERR_ARG, "basin_find: raster has more than 2^31-1 cells");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    int32_t coli, fili;
+    wmf_coord2fil_col(ctx, x, y, &coli, &fili);
+    ctx->find_nc = nc;
+    ctx->find_nr = nr;
+    if (ctx->q_cap < celTot) {
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->q_lin) cudaFree(ctx->q_lin);
+        if (ctx->q_par) cudaFree(ctx->q_par);
+        ctx->q_lin = ctx->q_par = nullptr;
+        ctx->q_cap = 0;
+        CU_TRY(ctx, cudaMalloc(&ctx->q_lin, sizeof(int32_t) * (size_t)celTot));
+        CU_TRY(ctx, cudaMalloc(&ctx->q_par, sizeof(int32_t) * (size_t)celTot));
+        ctx->q_cap = celTot;
+    }
+    if (coli <= 0 || fili <= 0) {
+        // outlet outside the map: the Fortran returns a one-cell "basin" holding (-999 | col, -999 | fil)
+        ctx->find_n = 1;
+        ctx->find_depth = 1;
+        // encode through the queue: lin = (fil-1)*nc + (col-1) cannot hold -999, keep it on the host side
+        const int32_t lin = -1, par = 0;
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->q_lin, &lin, 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->q_par, &par, 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->scalars[3] = (float)coli;  // stash (unused scalars until basin_basics runs)
+        ctx->scalars[4] = (float)fili;
+        *nceldas = 1;
+        return WMF_OK;
+    }
+    Scope sc(ctx);
+    const int32_t *d_dir;
+    WMF_TRY(sc.in(dir, (size_t)celTot, &d_dir));
+    FindState *st;
+    WMF_TRY(sc.alloc((void **)&st, sizeof(FindState)));
+    const int lin0 = (fili - 1) * nc + (coli - 1);
+    LAUNCH(ctx, k_find_seed, 1, 1, 0, ctx->q_lin, ctx->q_par, lin0, st);
+    int occ = 0;
+    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_basin_find, FIND_THREADS, 0));
+    if (occ < 1) WMF_FAIL(ctx, WMF_ERR_CUDA, "basin_find kernel does not fit on an SM");
+    int nb = ctx->num_sms;  // one CTA per SM: fewer barrier participants, full memory parallelism
+    if (nb > 1024) nb = 1024;
+    long long cap = celTot;
+    void *args[] = {(void *)&d_dir, (void *)&nc, (void *)&nr, (void *)&ctx->q_lin, (void *)&ctx->q_par, (void *)&cap,
+                    (void *)&st};
+    CU_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_basin_find, dim3(nb), dim3(FIND_THREADS), args, 0, ctx->stream));
+    ctx->launches++;
+    FindState h;
+    CU_TRY(ctx, cudaMemcpyAsync(&h, st, sizeof(long long) * 2 + sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h.err) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "basin_find: BFS queue overflow -- the DIR map is cyclic");
+    ctx->find_n = (int32_t)h.fe;
+    ctx->find_depth = h.depth;
+    *nceldas = ctx->find_n;
+    return WMF_OK;
+}
+
+int wmf_basin_find_depth(wmf_ctx *ctx, int32_t *depth) {
+    if (!ctx || !depth) return WMF_ERR_ARG;
+    *depth = ctx->find_depth;
+    return WMF_OK;
+}
+
+int wmf_basin_cut(wmf_ctx *ctx, int32_t nceldas, int32_t *basin_f) {
+    if (!ctx || !basin_f) return WMF_ERR_ARG;
+    if (!ctx->q_lin || ctx->find_n <= 0) WMF_FAIL(ctx, WMF_ERR_STATE, "basin_cut: call basin_find first");
+    if (nceldas <= 0 || nceldas > ctx->find_n)
+        WMF_FAIL(ctx, WMF_ERR_ARG, "basin_cut: nceldas=%d but the last basin_find traced %d cells", nceldas, ctx->find_n);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    int32_t *d_out;
+    WMF_TRY(sc.out(basin_f, (size_t)3 * nceldas, &d_out));
+    int32_t lin0 = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&lin0, ctx->q_lin, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (lin0 < 0) {  // degenerate outlet outside the map
+        const int32_t v[3] = {0, (int32_t)ctx->scalars[3], (int32_t)ctx->scalars[4]};
+        CU_TRY(ctx, cudaMemcpyAsync(d_out, v, sizeof v, cudaMemcpyHostToDevice, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return sc.finish();
+    }
+    LAUNCH(ctx, k_basin_cut, grid_for(nceldas, 256), 256, 0, ctx->q_lin, ctx->q_par, nceldas, ctx->find_nc, d_out);
+    return sc.finish();
+}
+
+int wmf_basin_acum(wmf_ctx *ctx, const int32_t *basin_f, int32_t n, int32_t *acum) {
+    if (!ctx || !basin_f || !acum || n <= 0) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    const int32_t *d_b;
+    int32_t *d_a;
+    WMF_TRY(sc.in(basin_f, (size_t)3 * n, &d_b));
+    WMF_TRY(sc.out(acum, (size_t)n, &d_a));
+    WMF_TRY(acum_device(ctx, sc, d_b, 3, n, d_a));
+    ctx->scalars[0] = (float)n * (ctx->geo.dxp * ctx->geo.dxp) / 1e6f;  // cuencas.f90:679
+    return sc.finish();
+}
+
+int wmf_basin_acum_var(wmf_ctx *ctx, const int32_t *drain, int32_t n, const float *var, float *acum) {
+    if (!ctx || !drain || !var || !acum || n <= 0) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    const int32_t *d_d;
+    const float *d_v;
+    float *d_o;
+    WMF_TRY(sc.in(drain, (size_t)n, &d_d));
+    WMF_TRY(sc.in(var, (size_t)n, &d_v));
+    WMF_TRY(sc.out(acum, (size_t)n, &d_o));
+    WMF_TRY(acum_var_device(ctx, sc, d_d, 1, n, d_v, d_o, 0));
+    return sc.finish();
+}
+
+int wmf_basin_propagate(wmf_ctx *ctx, const int32_t *basin_f, const float *var, int32_t n, float *var_prop) {
+    if (!ctx || !basin_f || !var || !var_prop || n <= 0) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    const int32_t *d_b;
+    const float *d_v;
+    float *d_o;
+    WMF_TRY(sc.in(basin_f, (size_t)3 * n, &d_b));
+    WMF_TRY(sc.in(var, (size_t)n, &d_v));
+    WMF_TRY(sc.out(var_prop, (size_t)n, &d_o));
+    WMF_TRY(acum_var_device(ctx, sc, d_b, 3, n, d_v, d_o, 1));
+    return sc.finish();
+}
+
+int wmf_basin_basics(wmf_ctx *ctx, const int32_t *basin_f, const float *dem, const int32_t *dir, int32_t n,
+                     int32_t *acum, float *lng, float *pend, float *elev) {
+    if (!ctx || !basin_f || !dem || !dir || !acum || !lng || !pend || !elev || n <= 0) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const wmf_geo &g = ctx->geo;
+    Scope sc(ctx);
+    const int32_t *d_b, *d_dir;
+    const float *d_dem;
+    int32_t *d_a;
+    float *d_l, *d_p, *d_e;
+    WMF_TRY(sc.in(basin_f, (size_t)3 * n, &d_b));
+    WMF_TRY(sc.in(dem, (size_t)n, &d_dem));
+    WMF_TRY(sc.in(dir, (size_t)n, &d_dir));
+    WMF_TRY(sc.out(acum, (size_t)n, &d_a));
+    WMF_TRY(sc.out(lng, (size_t)n, &d_l));
+    WMF_TRY(sc.out(pend, (size_t)n, &d_p));
+    WMF_TRY(sc.out(elev, (size_t)n, &d_e));
+    WMF_TRY(acum_device(ctx, sc, d_b, 3, n, d_a));
+    LAUNCH(ctx, k_basics_cell, grid_for(n, 256), 256, 0, d_b, d_dem, d_dir, n, g.dxp, d_l, d_p, d_e);
+    // scalars: means in fp64, centroid = median column / row (the Fortran sorts X and Y, cuencas.f90:650-657)
+    double *d_sums;
+    int32_t *d_hist;
+    WMF_TRY(sc.alloc(&d_sums, 2));
+    WMF_TRY(sc.alloc(&d_hist, (size_t)g.ncols + g.nrows));
+    CU_TRY(ctx, cudaMemsetAsync(d_sums, 0, 2 * sizeof(double), ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(d_hist, 0, sizeof(int32_t) * ((size_t)g.ncols + g.nrows), ctx->stream));
+    LAUNCH(ctx, k_basics_reduce, grid_for(n, 256), 256, 0, d_b, d_p, d_dem, n, d_sums, d_hist, d_hist + g.ncols);
+    double h_sums[2];
+    std::vector<int32_t> h_hist((size_t)g.ncols + g.nrows);
+    CU_TRY(ctx, cudaMemcpyAsync(h_sums, d_sums, sizeof h_sums, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(h_hist.data(), d_hist, sizeof(int32_t) * h_hist.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->scalars[0] = (float)n * (g.dxp * g.dxp) / 1e6f;
+    ctx->scalars[1] = (float)(h_sums[0] / (double)n);
+    ctx->scalars[2] = (float)(h_sums[1] / (double)n);
+    const long long k = (n % 2 == 0) ? n / 2 : (n + 1) / 2;  // 1-based rank in the sorted X / Y
+    {
+        // X grows with col: k-th smallest X = k-th smallest col
+        long long run = 0;
+        int col = 1;
+        for (int c = 0; c < g.ncols; ++c) { run += h_hist[c]; if (run >= k) { col = c + 1; break; } }
+        volatile float t = (float)col - 0.5f;
+        ctx->scalars[3] = g.xll + g.dx * t;
+        // Y shrinks with row: k-th smallest Y = k-th largest row
+        run = 0;
+        int row = g.nrows;
+        for (int f = g.nrows - 1; f >= 0; --f) { run += h_hist[g.ncols + f]; if (run >= k) { row = f + 1; break; } }
+        volatile float u = (float)(g.nrows - row) + 0.5f;
+        ctx->scalars[4] = g.yll + g.dx * u;
+    }
+    return sc.finish();
+}
+
+int wmf_basin_coordxy(wmf_ctx *ctx, const int32_t *basin_f, int32_t n, float *x, float *y) {
+    if (!ctx || !basin_f || !x || !y || n <= 0) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const wmf_geo &g = ctx->geo;
+    Scope sc(ctx);
+    const int32_t *d_b;
+    float *d_x, *d_y;
+    WMF_TRY(sc.in(basin_f, (size_t)3 * n, &d_b));
+    WMF_TRY(sc.out(x, (size_t)n, &d_x));
+    WMF_TRY(sc.out(y, (size_t)n, &d_y));
+    LAUNCH(ctx, k_coordxy, grid_for(n, 256), 256, 0, d_b, n, g.xll, g.yll, g.dx, g.nrows, d_x, d_y);
+    return sc.finish();
+}
+
+int wmf_basin_map2basin(wmf_ctx *ctx, const int32_t *basin_f, int32_t n, const float *mapa, float xllm, float yllm,
+                        int32_t ncolsm, int32_t nrowsm, float dxm, float dym, float nodatam, float *vec) {
+    if (!ctx || !basin_f || !mapa || !vec || n <= 0 || ncolsm <= 0 || nrowsm <= 0) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const wmf_geo &g = ctx->geo;
+    Scope sc(ctx);
+    const int32_t *d_b;
+    const float *d_m;
+    float *d_v;
+    const long long tot = (long long)ncolsm * nrowsm;
+    WMF_TRY(sc.in(basin_f, (size_t)3 * n, &d_b));
+    WMF_TRY(sc.in(mapa, (size_t)tot, &d_m));
+    WMF_TRY(sc.out(vec, (size_t)n, &d_v));
+    double *d_sum;
+    WMF_TRY(sc.alloc(&d_sum, 2));  // [0] sum, [1] reinterpreted as u64 count
+    CU_TRY(ctx, cudaMemsetAsync(d_sum, 0, 2 * sizeof(double), ctx->stream));
+    int G = grid_for(tot, 256);
+    if (G > ctx->num_sms * 16) G = ctx->num_sms * 16;
+    LAUNCH(ctx, k_map_mean, G, 256, 0, d_m, tot, nodatam, d_sum, (unsigned long long *)(d_sum + 1));
+    LAUNCH(ctx, k_map2basin, grid_for(n, 256), 256, 0, d_b, n, d_m, g.xll, g.yll, g.dx, g.dy, g.nrows, xllm, yllm, ncolsm,
+           nrowsm, dxm, dym, nodatam, d_sum, (const unsigned long long *)(d_sum + 1), d_v);
+    return sc.finish();
+}
+
+static int minmax_colrow(wmf_ctx *ctx, Scope &sc, const int32_t *d_b, int n, int32_t mm[4]) {
+    int32_t *d_mm;
+    WMF_TRY(sc.alloc(&d_mm, 4));
+    const int32_t init[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};
+    CU_TRY(ctx, cudaMemcpyAsync(d_mm, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    int G = grid_for(n, 256);
+    if (G > ctx->num_sms * 8) G = ctx->num_sms * 8;
+    LAUNCH(ctx, k_minmax_colrow, G, 256, 0, d_b, n, d_mm);
+    CU_TRY(ctx, cudaMemcpyAsync(mm, d_mm, sizeof init, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return WMF_OK;
+}
+
+int wmf_basin_2map_find(wmf_ctx *ctx, const int32_t *basin, int32_t n, int32_t *map_ncols, int32_t *map_nrows) {
+    if (!ctx || !basin || !map_ncols || !map_nrows || n <= 0) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    const int32_t *d_b;
+    WMF_TRY(sc.in(basin, (size_t)3 * n, &d_b));
+    int32_t mm[4];
+    WMF_TRY(minmax_colrow(ctx, sc, d_b, n, mm));
+    *map_ncols = mm[1] - mm[0] + 1;
+    *map_nrows = mm[3] - mm[2] + 1;
+    return sc.finish();
+}
+
+int wmf_basin_2map(wmf_ctx *ctx, const int32_t *basin, const float *var, int32_t n, int32_t map_ncols,
+                   int32_t map_nrows, float *mapa, float *map_xll, float *map_yll) {
+    if (!ctx || !basin || !var || !mapa || n <= 0 || map_ncols <= 0 || map_nrows <= 0) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const wmf_geo &g = ctx->geo;
+    Scope sc(ctx);
+    const int32_t *d_b;
+    const float *d_v;
+    float *d_m;
+    WMF_TRY(sc.in(basin, (size_t)3 * n, &d_b));
+    WMF_TRY(sc.in(var, (size_t)n, &d_v));
+    WMF_TRY(sc.out(mapa, (size_t)map_ncols * map_nrows, &d_m));
+    int32_t mm[4];
+    WMF_TRY(minmax_colrow(ctx, sc, d_b, n, mm));
+    if (mm[1] - mm[0] + 1 > map_ncols || mm[3] - mm[2] + 1 > map_nrows)
+        WMF_FAIL(ctx, WMF_ERR_ARG, "basin_2map: window (%d,%d) smaller than the basin extent (%d,%d)", map_ncols, map_nrows,
+                 mm[1] - mm[0] + 1, mm[3] - mm[2] + 1);
+    if (map_xll) { volatile float t = (float)(mm[0] - 1); *map_xll = g.xll + g.dx * t; }
+    if (map_yll) { volatile float t = (float)(g.nrows - mm[3]); *map_yll = g.yll + g.dx * t; }
+    const long long tot = (long long)map_ncols * map_nrows;
+    int G = grid_for(tot, 256);
+    if (G > ctx->num_sms * 16) G = ctx->num_sms * 16;
+    LAUNCH(ctx, k_fill_f32, G, 256, 0, d_m, tot, g.nodata);
+    LAUNCH(ctx, k_scatter_map, grid_for(n, 256), 256, 0, d_b, d_v, n, mm[0], mm[2], map_ncols, d_m);
+    return sc.finish();
+}
+
+int wmf_basin_float_var2map(wmf_ctx *ctx, const int32_t *basin_f, const float *vect, int32_t n, int32_t nc, int32_t nf,
+                            float *mapa) {
+    if (!ctx || !basin_f || !vect || !mapa || n <= 0 || nc <= 0 || nf <= 0) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    const int32_t *d_b;
+    const float *d_v;
+    float *d_m;
+    WMF_TRY(sc.in(basin_f, (size_t)3 * n, &d_b));
+    WMF_TRY(sc.in(vect, (size_t)n, &d_v));
+    WMF_TRY(sc.out(mapa, (size_t)nc * nf, &d_m));
+    int32_t mm[4];
+    WMF_TRY(minmax_colrow(ctx, sc, d_b, n, mm));
+    if (mm[0] < 1 || mm[1] > nc || mm[2] < 1 || mm[3] > nf)
+        WMF_FAIL(ctx, WMF_ERR_ARG, "basin_float_var2map: basin cells fall outside the (%d,%d) map", nc, nf);
+    const long long tot = (long long)nc * nf;
+    int G = grid_for(tot, 256);
+    if (G > ctx->num_sms * 16) G = ctx->num_sms * 16;
+    LAUNCH(ctx, k_fill_f32, G, 256, 0, d_m, tot, ctx->geo.nodata);
+    LAUNCH(ctx, k_scatter_map, grid_for(n, 256), 256, 0, d_b, d_v, n, 1, 1, nc, d_m);
+    return sc.finish();
+}
+
+static int threshold_mask(wmf_ctx *ctx, const int32_t *acum, int64_t n, int32_t umbral, int ge, int32_t *cauce,
+                          int32_t *count) {
+    if (!ctx || !acum || !cauce || n <= 0) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    const int32_t *d_a;
+    int32_t *d_c;
+    WMF_TRY(sc.in(acum, (size_t)n, &d_a));
+    WMF_TRY(sc.out(cauce, (size_t)n, &d_c));
+    unsigned long long *d_cnt = nullptr;
+    if (count) {
+        WMF_TRY(sc.alloc(&d_cnt, 1));
+        CU_TRY(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), ctx->stream));
+    }
+    int G = grid_for(n, 256);
+    if (G > ctx->num_sms * 16) G = ctx->num_sms * 16;
+    LAUNCH(ctx, k_threshold_mask, G, 256, 0, d_a, (long long)n, umbral, ge, d_c, d_cnt);
+    if (count) {
+        unsigned long long h;
+        CU_TRY(ctx, cudaMemcpyAsync(&h, d_cnt, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        *count = (int32_t)h;
+    }
+    return sc.finish();
+}
+
+int wmf_basin_stream_mask(wmf_ctx *ctx, const int32_t *acum, int32_t n, int32_t umbral, int32_t *cauce, int32_t *n_cauce) {
+    return threshold_mask(ctx, acum, n, umbral, 1, cauce, n_cauce);
+}
+
+int wmf_geo_acum_to_cauce(wmf_ctx *ctx, const int32_t *acum, int64_t ncells, int32_t umbral, int32_t *cauce) {
+    return threshold_mask(ctx, acum, ncells, umbral, 0, cauce, nullptr);
+}
+
+int wmf_basin_stream_type(wmf_ctx *ctx, const int32_t *acum, int32_t n, const int32_t *umbrales, int32_t nu,
+                          int32_t *stream_types) {
+    if (!ctx || !acum || !stream_types || n <= 0 || nu < 0 || (nu > 0 && !umbrales)) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    const int32_t *d_a, *d_u;
+    int32_t *d_t;
+    WMF_TRY(sc.in(acum, (size_t)n, &d_a));
+    WMF_TRY(sc.in(umbrales, (size_t)nu, &d_u));
+    WMF_TRY(sc.out(stream_types, (size_t)n, &d_t));
+    LAUNCH(ctx, k_stream_type, grid_for(n, 256), 256, 0, d_a, n, d_u, nu, d_t);
+    return sc.finish();
+}
+
+int wmf_geo_hand(wmf_ctx *ctx, const int32_t *basin_f, const float *elev, const float *lng, const int32_t *cauce,
+                 int32_t n, float *hand, float *hdnd, int32_t *a_quien) {
+    if (!ctx || !basin_f || !elev || !lng || !cauce || !hand || !hdnd || !a_quien || n <= 0) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    const int32_t *d_b, *d_c;
+    const float *d_e, *d_l;
+    float *d_h, *d_hd;
+    int32_t *d_aq;
+    WMF_TRY(sc.in(basin_f, (size_t)3 * n, &d_b));
+    WMF_TRY(sc.in(elev, (size_t)n, &d_e));
+    WMF_TRY(sc.in(lng, (size_t)n, &d_l));
+    WMF_TRY(sc.in(cauce, (size_t)n, &d_c));
+    WMF_TRY(sc.out(hand, (size_t)n, &d_h));
+    WMF_TRY(sc.out(hdnd, (size_t)n, &d_hd));
+    WMF_TRY(sc.out(a_quien, (size_t)n, &d_aq));
+    LAUNCH(ctx, k_geo_hand, grid_for(n, 256), 256, 0, d_b, d_e, d_l, d_c, n, d_h, d_hd, d_aq);
+    return sc.finish();
+}
+
+int wmf_geo_hand_global(wmf_ctx *ctx, const float *dem, const int32_t *dir, const int32_t *red, int32_t nc, int32_t nr,
+                        float *hand) {
+    if (!ctx || !dem || !dir || !red || !hand || nc <= 0 || nr <= 0) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const wmf_geo &g = ctx->geo;
+    Scope sc(ctx);
+    const long long tot = (long long)nc * nr;
+    const float *d_dem;
+    const int32_t *d_dir, *d_red;
+    float *d_h;
+    WMF_TRY(sc.in(dem, (size_t)tot, &d_dem));
+    WMF_TRY(sc.in(dir, (size_t)tot, &d_dir));
+    WMF_TRY(sc.in(red, (size_t)tot, &d_red));
+    WMF_TRY(sc.out(hand, (size_t)tot, &d_h));
+    LAUNCH(ctx, k_geo_hand_global, grid_for(tot, 256), 256, 0, d_dem, d_dir, d_red, nc, nr, g.ncols, g.nrows, g.nodata, d_h);
+    return sc.finish();
+}
+
+int wmf_basin_time_to_out(wmf_ctx *ctx, const int32_t *basin_f, const float *lng, const float *speed, int32_t n,
+                          float *time) {
+    if (!ctx || !basin_f || !lng || !speed || !time || n <= 0) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    const int32_t *d_b;
+    const float *d_l, *d_s;
+    float *d_t;
+    WMF_TRY(sc.in(basin_f, (size_t)3 * n, &d_b));
+    WMF_TRY(sc.in(lng, (size_t)n, &d_l));
+    WMF_TRY(sc.in(speed, (size_t)n, &d_s));
+    WMF_TRY(sc.out(time, (size_t)n, &d_t));
+    LAUNCH(ctx, k_time_to_out, grid_for(n, 256), 256, 0, d_b, d_l, d_s, n, d_t);
+    return sc.finish();
+}
+
+}  // extern "C"

@@ -225,3 +225,14 @@ def make_ensemble_calibs(n_members: int, seed: int = 0) -> np.ndarray:
     c = rng.uniform(lo, hi, size=(n_members, 11)).astype(np.float32)
     c[0] = DEFAULT_CALIB
     return c
+
+
+def apply_to_models(models, inp: dict) -> None:
+    """Load a ``make_shia_inputs`` dict into a ``models`` module object the way wmf.py's set_* methods do
+    (attribute assignment, wmf.py:3024-3045, 3687-3695, 3882, 3952, 4046-4163)."""
+    skip = {"calib", "rain", "pos_evento", "n_reg", "nceldas", "stoin", "hspeedin"}
+    for k, v in inp.items():
+        if k in skip:
+            continue
+        setattr(models, k, v)
+    models.nceldas = inp["nceldas"]
