@@ -21,6 +21,9 @@
 #include "common.cuh"
 
 constexpr int WAVE_THREADS = 256;
+#ifndef WAVE_MIN_BLOCKS
+#define WAVE_MIN_BLOCKS 4
+#endif
 constexpr int RED_SUB = 8;  // sub-slots per (step, quantity) to spread atomic traffic
 // reduction quantities per step
 enum { RQ_SAL = 0, RQ_STO1 = 1 /* ..5 */, RQ_SPD1 = 6 /* ..9 */, RQ_RET = 10, RQ_COUNT = 11 };
@@ -228,9 +231,16 @@ __device__ __forceinline__ int find_row(const int32_t *__restrict__ cells, int n
     return lo;
 }
 
+// The channel kinematic-wave solve (calc_niter x {div, powf, div}) is ~10x the cost of everything else a cell does,
+// and channel cells are a few percent of a basin scattered among hillslope cells: solved in place, most warps would
+// run the whole solver for one or two lanes.  Instead the block compacts its channel cells into shared memory and
+// the first ceil(n/32) warps solve them with full lanes; results travel back through shared memory.
 template <bool SED, bool SLIDES>
-__global__ void __launch_bounds__(WAVE_THREADS)
+__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS)
 k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const int hi) {
+    __shared__ float4 s_in[WAVE_THREADS];  // sm, coef, expo, stream_long
+    __shared__ float2 s_io[WAVE_THREADS];  // in: x = speed ; out: x = section area, y = speed
+    __shared__ int s_wcnt[WAVE_THREADS / 32];
     const long long g = (long long)blockIdx.x * WAVE_THREADS + threadIdx.x;
     int cell, m;
     if (P.M == 1) { cell = lo + (int)g; m = 0; }
@@ -243,18 +253,22 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
         t = w - (P.Lmax - (int)(tw >> 8));
         active = (t >= 0) && (t < P.T);
     }
-    double r_sal = 0.0, r_sto[5] = {0, 0, 0, 0, 0}, r_spd[4] = {0, 0, 0, 0}, r_ret = 0.0;
+    const int N = P.N, M = P.M;
+    const int type = (tw >> 4) & 3, nch = tw & 15;
+    const float dt = P.dt;
+    const size_t NM = (size_t)N * M;
+    const size_t base = (size_t)cell * M + m;
+    double r_sal = 0.0, r_ret = 0.0;
     float sed_ero[3] = {0, 0, 0}, sed_dep[3] = {0, 0, 0};
+    float S[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    float h[4] = {0.f, 0.f, 0.f, 0.f};
+    float hs[4] = {0.f, 0.f, 0.f, 0.f};
+    float m3 = 1.0f, H2 = 0.f;
+    SedLocal SL;
+    // =========================== phase A: everything up to the channel solve ===========================
     if (active) {
-        const int N = P.N, M = P.M;
-        const int type = (tw >> 4) & 3, nch = tw & 15;
-        const float dt = P.dt;
-        const size_t NM = (size_t)N * M;
-        const size_t base = (size_t)cell * M + m;
-        float S[5];
 #pragma unroll
         for (int k = 0; k < 5; ++k) S[k] = P.sto[k * NM + base];
-        SedLocal SL;
         if (SED) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -291,6 +305,9 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
                 }
             }
         }
+    }
+    float chan_coef = 0.f, chan_expo = 0.f;
+    if (active) {
         // ---- per-cell parameters (:285-304), recomputed from the shared maps and the member's calibration ----
         float cal[11];
         {
@@ -303,7 +320,7 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
         const float vs1 = vc.x * cal[0] * dt, vs2 = vc.y * cal[1] * dt, vs3 = vc.z * cal[2] * dt, vs4 = vc.w * cal[3] * dt;
         const float H1 = __ldg(P.max_capilar + cell) * cal[8];
         const float Lh = __ldg(P.hill_long + cell);
-        const float m3 = __ldg(P.elem_area + cell) / 1000.0f;
+        m3 = __ldg(P.elem_area + cell) / 1000.0f;
         // ---- rain (:444-449) ----
         const int p = __ldg(P.pos + t);
         float R = 0.0f;
@@ -319,7 +336,6 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
         S[2] = S[2] + vf2 - vf3;
         const float vf4 = fminf(vf3, vs4);
         S[3] = S[3] + vf3 - vf4;
-        float H2 = 0.f;
         if (P.retorno_gr > 0.0f || SLIDES) H2 = __ldg(P.max_gravita + cell) * cal[9];
         if (P.retorno_aq > 0.0f) {
             const float H3 = __ldg(P.max_aquifer + cell) * cal[10];
@@ -338,8 +354,6 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
         }
         r_sal = (double)vf4 + (double)E;
         // ---- hillslope outflows of tanks 2..4 (:553-595) ----
-        float h[4] = {0.f, 0.f, 0.f, 0.f};
-        float hs[4] = {0.f, 0.f, 0.f, 0.f};
         const float hcoef[3] = {hc.x, hc.y, hc.z};
         float4 he = make_float4(0.f, 0.f, 0.f, 0.f);
         const bool any_kin = (P.st[0] == 2) | (P.st[1] == 2) | (P.st[2] == 2);
@@ -364,10 +378,54 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
             }
             S[k + 1] = S[k + 1] - h[k];
         }
+        if (type > 1) {  // channel cell: what stays in the channel tank before the kinematic solve (:617-621)
+            S[4] = S[4] + (h[0] + h[1]) + h[2] * (float)(type - 2);
+            chan_coef = hc.w * cal[7];
+            chan_expo = he.w;
+        }
+    }
+    // =========================== channel solve, compacted over the block (:631-635) ===========================
+    const bool is_ch = active && type > 1;
+    float sec_area = 0.f;
+    {
+        const unsigned full = 0xffffffffu;
+        const unsigned bal = __ballot_sync(full, is_ch);
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) s_wcnt[wid] = __popc(bal);
+        __syncthreads();
+        int woff = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < WAVE_THREADS / 32; ++k) {
+            const int c = s_wcnt[k];
+            if (k < wid) woff += c;
+            total += c;
+        }
+        if (total > 0) {  // block-uniform
+            const int slot = woff + __popc(bal & ((1u << lane) - 1u));
+            if (is_ch) {
+                s_in[slot] = make_float4(S[4] * m3, chan_coef, chan_expo, __ldg(P.stream_long + cell));
+                s_io[slot] = make_float2(P.hsp[3 * NM + base], 0.f);
+            }
+            __syncthreads();
+            for (int j = threadIdx.x; j < total; j += WAVE_THREADS) {
+                const float4 a = s_in[j];
+                float v = s_io[j].x;
+                const float ar = calc_speed_dev(a.x, a.y, a.z, a.w, v, dt, P.niter);
+                s_io[j] = make_float2(ar, v);
+            }
+            __syncthreads();
+            if (is_ch) {
+                const float2 r = s_io[slot];
+                sec_area = r.x;
+                hs[3] = r.y;
+            }
+        }
+    }
+    // =========================== phase B: routing, records, publish ===========================
+    if (active) {
         // ---- routing (:599-719) ----
         const bool outlet = (cell == N - 1);
         float o0, o1, o2, o3;
-        float sec_area = 0.f;
         float Vsal[3] = {0.f, 0.f, 0.f};
         const size_t qoff = ((size_t)m * P.T + t) * P.n_cont;
         if (type == 1) {
@@ -380,22 +438,18 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
         } else {
             o0 = 0.0f; o1 = 0.0f;
             o2 = h[2] * (float)(3 - type);
-            S[4] = S[4] + (h[0] + h[1]) + h[2] * (float)(type - 2);
-            float v = P.hsp[3 * NM + base];
-            sec_area = calc_speed_dev(S[4] * m3, hc.w * cal[7], he.w, __ldg(P.stream_long + cell), v, dt, P.niter);
+            const float v = hs[3];
             h[3] = fminf(sec_area * v * dt / m3, S[4]);
-            hs[3] = v;
             P.hsp[3 * NM + base] = v;
             if (SED) {
                 float vd2 = 0.f;
                 sed_channel_dev(P, SL, S[4], v, h[3] * m3 / dt, __ldg(P.stream_slope + cell), sec_area, Vsal, &vd2);
                 // VolDEPo(celda) is incremented twice in a step for a channel cell (:1427 then :1607)
-                const size_t vb = base;
-                float vdep = P.voldepo[vb];
+                float vdep = P.voldepo[base];
                 vdep = vdep + SL.voldepo_add;
                 vdep = vdep + vd2;
-                P.voldepo[vb] = vdep;
-                P.volero[vb] = P.volero[vb] + SL.volero_add;
+                P.voldepo[base] = vdep;
+                P.volero[base] = P.volero[base] + SL.volero_add;
                 SL.voldepo_add = 0.f;
                 SL.volero_add = 0.f;
             }
@@ -504,16 +558,6 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
 #pragma unroll
             for (int i = 0; i < 3; ++i) { sed_ero[i] = SL.ero_add[i]; sed_dep[i] = SL.dep_add[i]; }
         }
-        if (P.want_red) {
-#pragma unroll
-            for (int k = 0; k < 5; ++k) r_sto[k] = (double)S[k];
-            if (P.show_mean_speed)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // sum(hspeed,dim=2): linear tanks hold their constant speed, channel speed is 0 on hillslopes
-                    r_spd[k] = (double)((k < 3) ? hs[k] : ((type > 1) ? hs[3] : (P.hs_state ? P.hsp[3 * NM + base] : 0.0f)));
-                }
-        }
     }
     // ---- per-step reductions (balance :846, mean_storage :828, mean_speed :833, mean_retorno :838) ----
     if (P.want_red && P.M == 1) {
@@ -522,47 +566,54 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
         const int t0 = __shfl_sync(full, t, 0);
         const bool uni = __all_sync(full, t == t0);
         const int sub = blockIdx.x & (RED_SUB - 1);
+        const bool lead = (threadIdx.x & 31) == 0;
         auto flush = [&](double v, int q, int tt) {
             if (v != 0.0) atomicAdd(P.red + ((size_t)tt * RQ_COUNT + q) * RED_SUB + sub, v);
+        };
+        // sum(hspeed,dim=2): linear tanks hold their constant speed, the channel speed of a hillslope cell keeps its
+        // initial value
+        auto spd = [&](int k) -> double {
+            if (!active) return 0.0;
+            if (k < 3) return (double)hs[k];
+            return (double)((type > 1) ? hs[3] : (P.hs_state ? P.hsp[3 * NM + base] : 0.0f));
         };
         if (uni) {
             if (t0 >= 0) {
                 const double a = warp_sum_d(r_sal);
-                double b[5];
+                if (lead) flush(a, RQ_SAL, t0);
+                if (P.show_storage) {
 #pragma unroll
-                for (int k = 0; k < 5; ++k) b[k] = warp_sum_d(r_sto[k]);
-                if ((threadIdx.x & 31) == 0) {
-                    flush(a, RQ_SAL, t0);
-                    if (P.show_storage) {
-#pragma unroll
-                        for (int k = 0; k < 5; ++k) flush(b[k], RQ_STO1 + k, t0);
-                    } else {
-                        flush(((b[0] + b[1]) + (b[2] + b[3])) + b[4], RQ_STO1, t0);
+                    for (int k = 0; k < 5; ++k) {
+                        const double b = warp_sum_d((double)S[k]);
+                        if (lead) flush(b, RQ_STO1 + k, t0);
                     }
+                } else {
+                    const double b = warp_sum_d(((double)S[0] + (double)S[1]) + ((double)S[2] + (double)S[3]) + (double)S[4]);
+                    if (lead) flush(b, RQ_STO1, t0);
                 }
                 if (P.show_mean_speed) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const double c = warp_sum_d(r_spd[k]);
-                        if ((threadIdx.x & 31) == 0) flush(c, RQ_SPD1 + k, t0);
+                        const double c = warp_sum_d(spd(k));
+                        if (lead) flush(c, RQ_SPD1 + k, t0);
                     }
                 }
                 if (P.want_retorned) {
                     const double c = warp_sum_d(r_ret);
-                    if ((threadIdx.x & 31) == 0) flush(c, RQ_RET, t0);
+                    if (lead) flush(c, RQ_RET, t0);
                 }
             }
-        } else if (t >= 0) {
+        } else if (t >= 0 && active) {
             flush(r_sal, RQ_SAL, t);
             if (P.show_storage) {
 #pragma unroll
-                for (int k = 0; k < 5; ++k) flush(r_sto[k], RQ_STO1 + k, t);
+                for (int k = 0; k < 5; ++k) flush((double)S[k], RQ_STO1 + k, t);
             } else {
-                flush(((r_sto[0] + r_sto[1]) + (r_sto[2] + r_sto[3])) + r_sto[4], RQ_STO1, t);
+                flush(((double)S[0] + (double)S[1]) + ((double)S[2] + (double)S[3]) + (double)S[4], RQ_STO1, t);
             }
             if (P.show_mean_speed)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) flush(r_spd[k], RQ_SPD1 + k, t);
+                for (int k = 0; k < 4; ++k) flush(spd(k), RQ_SPD1 + k, t);
             if (P.want_retorned) flush(r_ret, RQ_RET, t);
         }
     }
