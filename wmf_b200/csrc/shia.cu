@@ -15,6 +15,7 @@
 // Reductions (balance, means) are accumulated in fp64 per step slot.
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -77,6 +78,13 @@ struct ShiaP {
     int32_t *sl_ncelltime;  // [T]
     const int32_t *drena;   // original drain ids (for the downstream marking walk)
     int drena_stride;
+    // time-blocked wavefront (k_shia_tb): cell lists by role, AoS state, per-step outflow ring
+    int nb;                 // number of time blocks = ceil(T / K)
+    const int32_t *hidx, *cidx;  // hillslope (type 1) / channel (type 2,3) cells, ascending cell id
+    float4 *st4;            // [N][M] tanks 1..4
+    float *s5;              // [N][M] tank 5
+    float4 *outb4;          // [2][K][N][M] what a cell sends downstream at each step of its time block
+    int bal_direct;         // red[t][RQ_SAL] holds sum(dS + outputs), balance = that - inputs
 };
 
 __device__ __forceinline__ size_t sidx(const ShiaP &P, int k, int cell, int m) {
@@ -631,6 +639,325 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Time-blocked wavefront.  One thread owns a (cell, member) for K consecutive steps: its state stays in registers,
+// the per-cell parameters are derived once per block of steps, and only the per-step traffic (children's outflow,
+// rain, own outflow) touches memory -- produced one wave earlier, so it is served from L2.  Cell (level L, time
+// block b) runs in wave w = b + (Lmax - L): its children finished block b one wave earlier, and so did its own
+// block b-1.  Hillslope and channel cells run in different CTAs of the same launch (lists of cell ids per role),
+// so no warp mixes the cheap hillslope update with the channel's kinematic-wave iterations.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TB_THREADS = 256;
+#ifndef TB_MIN_BLOCKS
+#define TB_MIN_BLOCKS 4
+#endif
+
+template <int K, bool CHAN, bool KIN>
+__device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int jlo, const int jhi, const int tile,
+                                        float *__restrict__ s_acc) {
+    const int N = P.N, M = P.M;
+    const long long g = (long long)tile * 32 + (threadIdx.x & 31);
+    int j, m;
+    if (M == 1) { j = jlo + (int)g; m = 0; }
+    else { j = jlo + (int)(g / M); m = (int)(g % M); }
+    bool active = j < jhi;
+    int cell = 0, b = -1;
+    uint32_t tw = 0;
+    if (active) {
+        cell = __ldg((CHAN ? P.cidx : P.hidx) + j);
+        tw = __ldg(P.tw + cell);
+        b = w - (P.Lmax - (int)(tw >> 8));
+        active = (b >= 0) && (b < P.nb);
+    }
+    const int t0 = b * K;
+    const int nt = active ? min(K, P.T - t0) : 0;
+    const float dt = P.dt;
+    const size_t NM = (size_t)N * M;
+    const size_t base = (size_t)cell * M + m;
+    const int type = (tw >> 4) & 3, nch = tw & 15;
+    // ---- per-thread constants of the time block (:285-304) ----
+    float S0 = 0.f, S1 = 0.f, S2 = 0.f, S3 = 0.f, S4 = 0.f;
+    float vs1 = 0.f, vs2 = 0.f, vs3 = 0.f, vs4 = 0.f, H1 = 1.f, H2 = 0.f, H3 = 0.f, Lh = 1.f, m3 = 1.f;
+    float fl[3] = {0.f, 0.f, 0.f};      // linear reservoirs: 1 - L/(v dt + L), constant over the run
+    float kv[3] = {0.f, 0.f, 0.f};      // speeds (state for kinematic tanks)
+    float kc[3] = {0.f, 0.f, 0.f}, ke[3] = {0.f, 0.f, 0.f};
+    float vch = 0.f, ccoef = 0.f, cexpo = 0.f, Ls = 1.f, ret_acc = 0.f;
+    int c0 = 0, rowq = -1, rowh = -1;
+    if (active) {
+        float cal[11];
+        {
+            const float *cp = P.calib + (size_t)m * 11;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) cal[k] = __ldg(cp + k);
+        }
+        const float4 vc = __ldg(reinterpret_cast<const float4 *>(P.v_coef) + cell);
+        const float4 hc = __ldg(reinterpret_cast<const float4 *>(P.h_coef) + cell);
+        vs1 = vc.x * cal[0] * dt; vs2 = vc.y * cal[1] * dt; vs3 = vc.z * cal[2] * dt; vs4 = vc.w * cal[3] * dt;
+        H1 = __ldg(P.max_capilar + cell) * cal[8];
+        if (P.retorno_gr > 0.0f) H2 = __ldg(P.max_gravita + cell) * cal[9];
+        if (P.retorno_aq > 0.0f) H3 = __ldg(P.max_aquifer + cell) * cal[10];
+        Lh = __ldg(P.hill_long + cell);
+        m3 = __ldg(P.elem_area + cell) / 1000.0f;
+        const float4 s = P.st4[base];
+        S0 = s.x; S1 = s.y; S2 = s.z; S3 = s.w;
+        S4 = P.s5[base];
+        float4 he = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (KIN || CHAN) he = __ldg(reinterpret_cast<const float4 *>(P.h_exp) + cell);
+        const float hcoef[3] = {hc.x, hc.y, hc.z}, hexp[3] = {he.x, he.y, he.z};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (!KIN || P.st[k] == 1) {
+                const float v = P.hs_state ? P.hsp[k * NM + base] : hcoef[k] * cal[4 + k];
+                kv[k] = v;
+                fl[k] = 1.0f - Lh / (v * dt + Lh);
+            } else {
+                kv[k] = P.hsp[k * NM + base];
+                kc[k] = hcoef[k] * cal[4 + k];
+                ke[k] = hexp[k];
+            }
+        }
+        if (CHAN) {
+            vch = P.hsp[3 * NM + base];
+            ccoef = hc.w * cal[7];
+            cexpo = he.w;
+            Ls = __ldg(P.stream_long + cell);
+        }
+        if (nch) c0 = __ldg(P.cs + cell);
+        if (tw & TW_CTRLQ) {
+            rowq = 1 + find_row(P.ctrl_cells, P.n_ctrl, cell);
+            if (rowq >= P.n_cont) rowq = -1;
+        }
+        if (tw & TW_CTRLH) {
+            rowh = find_row(P.ctrlh_cells, P.n_ctrlh, cell);
+            if (rowh >= P.n_conth) rowh = -1;
+        }
+        if (P.retorned) ret_acc = P.retorned[cell];
+    }
+    const bool outlet = active && (cell == N - 1);
+    const float4 *ob_in = P.outb4 + (size_t)(b & 1) * K * NM + m;
+    float4 *ob_out = P.outb4 + (size_t)(b & 1) * K * NM + base;
+    // ---- the K steps of the block ----
+#pragma unroll 1
+    for (int tt = 0; tt < K; ++tt) {
+        float dq = 0.0f;
+        if (tt < nt) {
+            const int t = t0 + tt;
+            const float So0 = S0, So1 = S1, So2 = S2, So3 = S3, So4 = S4;
+            // what the upstream neighbours sent this step, in ascending cell order (:601,:617,:672)
+            {
+                const float4 *ob = ob_in + (size_t)tt * NM;
+#pragma unroll 1
+                for (int c = c0; c < c0 + nch; ++c) {
+                    const float4 o = ob[(size_t)c * M];
+                    S1 = S1 + o.x;
+                    S2 = S2 + o.y;
+                    S3 = S3 + o.z;
+                    S4 = S4 + o.w;
+                }
+            }
+            // rain (:444-449)
+            const int p = __ldg(P.pos + t);
+            float R = 0.0f;
+            if (p != 1) R = (float)__ldg(P.rain + (size_t)(p - 1) * N + cell) / 1000.0f;
+            // vertical cascade (:478-512)
+            const float vf1 = fmaxf(0.0f, R - H1 + S0);
+            S0 = S0 + R - vf1;
+            const float E = fminf(__ldg(P.evp + t) * vs1 * powf(S0 / H1, 0.6f), S0);
+            S0 = S0 - E;
+            const float vf2 = fminf(vf1, vs2);
+            S1 = S1 + vf1 - vf2;
+            const float vf3 = fminf(vf2, vs3);
+            S2 = S2 + vf2 - vf3;
+            const float vf4 = fminf(vf3, vs4);
+            S3 = S3 + vf3 - vf4;
+            if (P.retorno_aq > 0.0f) {
+                const float Ret_aq = fmaxf(0.0f, S3 - H3);
+                S2 = S2 + Ret_aq;
+                S3 = S3 - Ret_aq;
+            }
+            if (P.retorno_gr > 0.0f) {
+                const float Ret = fmaxf(0.0f, S2 - H2);
+                S1 = S1 + Ret;
+                S2 = S2 - Ret;
+                ret_acc = ret_acc + Ret;
+            }
+            float sal = vf4 + E;
+            // hillslope outflows of tanks 2..4 (:553-595)
+            float h0, h1, h2;
+            {
+                float Sk[3] = {S1, S2, S3}, hk[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (!KIN || P.st[k] == 1) {
+                        hk[k] = fl[k] * Sk[k];
+                    } else {
+                        const float sec = calc_speed_dev(Sk[k] * m3, kc[k], ke[k], Lh, kv[k], dt, P.niter);
+                        hk[k] = fminf(sec * kv[k] * dt / m3, Sk[k]);
+                    }
+                    Sk[k] = Sk[k] - hk[k];
+                }
+                S1 = Sk[0]; S2 = Sk[1]; S3 = Sk[2];
+                h0 = hk[0]; h1 = hk[1]; h2 = hk[2];
+            }
+            // routing (:599-719)
+            float4 o;
+            const size_t qoff = ((size_t)m * P.T + t) * P.n_cont;
+            if (!CHAN) {
+                o = make_float4(h0, h1, h2, 0.0f);
+                if (outlet) {
+                    const float s3 = (h0 + h1) + h2;
+                    if (P.q) P.q[qoff] = s3 * m3;
+                    sal = sal + s3;
+                }
+                if (rowq >= 0 && P.q) P.q[qoff + rowq] = 0.0f;
+            } else {
+                S4 = S4 + (h0 + h1) + h2 * (float)(type - 2);
+                const float sec_area = calc_speed_dev(S4 * m3, ccoef, cexpo, Ls, vch, dt, P.niter);
+                const float h3 = fminf(sec_area * vch * dt / m3, S4);
+                S4 = S4 - h3;
+                o = make_float4(0.0f, 0.0f, h2 * (float)(3 - type), h3);
+                if (outlet) {
+                    if (P.q) P.q[qoff] = h3 * m3 / dt;
+                    sal = sal + h3;
+                    if (P.show_speed) {
+                        if (P.speed) P.speed[qoff] = vch;
+                        if (P.area) P.area[qoff] = sec_area;
+                    }
+                }
+                if (rowq >= 0) {  // records (:749-787)
+                    if (P.q) P.q[qoff + rowq] = h3 * m3 / dt;
+                    if (P.show_speed) {
+                        if (P.speed) P.speed[qoff + rowq] = vch;
+                        if (P.area) P.area[qoff + rowq] = sec_area;
+                    }
+                }
+            }
+            if (rowh >= 0) {
+                const size_t k = ((size_t)m * P.T + t) * P.n_conth + rowh;
+                if (P.hum) P.hum[k] = S0 + S2;
+                if (P.st1o) P.st1o[k] = S0;
+                if (P.st3o) P.st3o[k] = S2;
+            }
+            ob_out[(size_t)tt * NM] = o;
+            // storage change of the cell over the step + what left the basin through it: summed over the cells this
+            // is sum(StoOut) - StoAtras + salidas of :846 (the transfers between cells cancel)
+            dq = (((S0 - So0) + (S1 - So1)) + ((S2 - So2) + (S3 - So3))) + (S4 - So4) + sal;
+        }
+        if (P.want_red) s_acc[tt * TB_THREADS + threadIdx.x] = dq;
+    }
+    if (active) {
+        P.st4[base] = make_float4(S0, S1, S2, S3);
+        P.s5[base] = S4;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (KIN && P.st[k] == 2) P.hsp[k * NM + base] = kv[k];
+        if (CHAN) P.hsp[3 * NM + base] = vch;
+        if (P.retorned) P.retorned[cell] = ret_acc;
+    }
+    // ---- per-step balance terms: one fp64 atomic per (warp, step) ----
+    if (P.want_red) {
+        const unsigned full = 0xffffffffu;
+        const unsigned act = __ballot_sync(full, active);
+        if (act) {
+            const int lane = threadIdx.x & 31;
+            const int b0 = __shfl_sync(full, b, __ffs(act) - 1);
+            const bool uni = __all_sync(full, !active || b == b0);
+            const int sub = blockIdx.x & (RED_SUB - 1);
+            if (uni) {
+                constexpr int G = 32 / K;  // lanes per step
+                const int s = lane / G, part = lane % G;
+                const float *src = s_acc + s * TB_THREADS + (threadIdx.x & ~31) + part * K;
+                double a = 0.0;
+#pragma unroll
+                for (int i = 0; i < K; ++i) a += (double)src[i];
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) a += __shfl_xor_sync(full, a, o);
+                const int t = b0 * K + s;
+                if (part == 0 && t < P.T && a != 0.0) atomicAdd(P.red + ((size_t)t * RQ_COUNT + RQ_SAL) * RED_SUB + sub, a);
+            } else if (active) {
+                for (int tt = 0; tt < nt; ++tt) {
+                    const double a = (double)s_acc[tt * TB_THREADS + threadIdx.x];
+                    if (a != 0.0) atomicAdd(P.red + ((size_t)(t0 + tt) * RQ_COUNT + RQ_SAL) * RED_SUB + sub, a);
+                }
+            }
+        }
+    }
+}
+
+// Every CTA carries the same mix of roles: its first `cpb` warps take 32-thread tiles of the channel list, the
+// others tiles of the hillslope list, so the SMs stay balanced although a channel thread costs ~4x a hillslope one.
+template <int K, bool KIN>
+__global__ void __launch_bounds__(TB_THREADS, TB_MIN_BLOCKS)
+k_shia_tb(const __grid_constant__ ShiaP P, const int w, const int clo, const int chi, const int hlo, const int hhi,
+          const int cpb, const int n_ctiles, const int n_htiles) {
+    __shared__ float s_acc[K * TB_THREADS];
+    const int wi = threadIdx.x >> 5;
+    if (wi < cpb) {
+        const int tile = (int)blockIdx.x * cpb + wi;
+        if (tile < n_ctiles) tb_role<K, true, KIN>(P, w, clo, chi, tile, s_acc);
+    } else {
+        const int tile = (int)blockIdx.x * (TB_THREADS / 32 - cpb) + (wi - cpb);
+        if (tile < n_htiles) tb_role<K, false, KIN>(P, w, hlo, hhi, tile, s_acc);
+    }
+}
+
+// role lists: is_h[i] = 1 for hillslope cells; hpos = exclusive scan of is_h
+__global__ void k_role_flags(const uint32_t *__restrict__ tw, int n, int32_t *__restrict__ is_h) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) is_h[i] = (((tw[i] >> 4) & 3) == 1) ? 1 : 0;
+}
+__global__ void k_role_lists(const int32_t *__restrict__ is_h, const int32_t *__restrict__ hpos, int n,
+                             int32_t *__restrict__ hidx, int32_t *__restrict__ cidx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (is_h[i]) hidx[hpos[i]] = i;
+    else cidx[i - hpos[i]] = i;
+}
+// hfirst[L] = number of hillslope cells below the first cell of level L (list position of the level's first cell)
+__global__ void k_role_level_first(const int32_t *__restrict__ level_first, const int32_t *__restrict__ hpos, int nlev,
+                                   int32_t *__restrict__ hfirst) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < nlev) hfirst[l] = hpos[level_first[l]];
+}
+
+// StoOut = StoIn | Storage + storage_constant (:271-277), (5,N) -> tanks 1-4 as one float4 per (cell, member) + tank 5
+__global__ void k_state_init_tb(const float *__restrict__ src, float add, int n, int M, float4 *__restrict__ st4,
+                                float *__restrict__ s5) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) v[k] = src[5 * (size_t)i + k] + add;
+    for (int m = 0; m < M; ++m) {
+        st4[(size_t)i * M + m] = make_float4(v[0], v[1], v[2], v[3]);
+        s5[(size_t)i * M + m] = v[4];
+    }
+}
+
+__global__ void k_state_final_tb(const ShiaP P, float *__restrict__ stoout, float *__restrict__ hspeed_out) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)P.N * P.M) return;
+    const int i = (int)(g / P.M), m = (int)(g % P.M);
+    const size_t NM = (size_t)P.N * P.M, base = (size_t)i * P.M + m;
+    if (stoout) {
+        const float4 s = P.st4[base];
+        float *o = stoout + ((size_t)m * P.N + i) * 5;
+        o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w; o[4] = P.s5[base];
+    }
+    if (hspeed_out) {
+        const float4 hc = reinterpret_cast<const float4 *>(P.h_coef)[i];
+        const float hcoef[3] = {hc.x, hc.y, hc.z};
+        const float *cal = P.calib + (size_t)m * 11;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float v;
+            if (k < 3 && P.st[k] == 1 && !P.hs_state) v = hcoef[k] * cal[4 + k];
+            else v = P.hsp[k * NM + base];
+            hspeed_out[((size_t)m * P.N + i) * 4 + k] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // plan: levels, child ranges, packed topology words
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_plan_init(const int32_t *__restrict__ drena, int stride, int n, int32_t *__restrict__ lev,
@@ -777,7 +1104,8 @@ __global__ void k_acum_rain(const int32_t *__restrict__ rain, const int32_t *__r
 
 __global__ void k_shia_epilogue(const double *__restrict__ red, const double *__restrict__ recsum,
                                 const int32_t *__restrict__ pos, const double *__restrict__ sto0, int n, int T,
-                                int show_storage, float *__restrict__ balance, float *__restrict__ mean_rain,
+                                int show_storage, int bal_direct, float *__restrict__ balance,
+                                float *__restrict__ mean_rain,
                                 float *__restrict__ mean_storage, float *__restrict__ mean_speed,
                                 float *__restrict__ mean_retorno) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -795,7 +1123,10 @@ __global__ void k_shia_epilogue(const double *__restrict__ red, const double *__
         return s;
     };
     const double entradas = recsum[pos[t] - 1];
-    if (balance) balance[t] = (float)(total(t) - total(t - 1) - entradas + q(t, RQ_SAL));
+    if (balance) {
+        if (bal_direct) balance[t] = (float)(q(t, RQ_SAL) - entradas);  // k_shia_tb sums dS + outputs per cell
+        else balance[t] = (float)(total(t) - total(t - 1) - entradas + q(t, RQ_SAL));
+    }
     if (mean_rain) mean_rain[t] = (float)(entradas / (double)n);
     if (mean_storage)
         for (int k = 0; k < 5; ++k) mean_storage[5 * (size_t)t + k] = (float)(q(t, RQ_STO1 + k) / (double)n);
@@ -945,6 +1276,39 @@ static void launch_wave(wmf_ctx *ctx, const ShiaP &P, int w, int lo, int hi) {
     const int grid = (int)((work + WAVE_THREADS - 1) / WAVE_THREADS);
     k_shia_wave<SED, SLIDES><<<grid, WAVE_THREADS, 0, ctx->stream>>>(P, w, lo, hi);
     ctx->launches++;
+}
+
+template <int K>
+static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int hlo, int hhi) {
+    constexpr int WPB = TB_THREADS / 32;
+    const int wc = (int)(((long long)(chi - clo) * P.M + 31) / 32), wh = (int)(((long long)(hhi - hlo) * P.M + 31) / 32);
+    if (wc + wh == 0) return;
+    int cpb = 0, nblk = 0;
+    if (wc == 0) { cpb = 0; nblk = (wh + WPB - 1) / WPB; }
+    else if (wh == 0) { cpb = WPB; nblk = (wc + WPB - 1) / WPB; }
+    else {
+        for (int c = 1; c < WPB; ++c) {
+            const int nb = std::max((wc + c - 1) / c, (wh + (WPB - c) - 1) / (WPB - c));
+            if (nblk == 0 || nb < nblk) { nblk = nb; cpb = c; }
+        }
+    }
+    if (P.st[0] == 2 || P.st[1] == 2 || P.st[2] == 2)
+        k_shia_tb<K, true><<<nblk, TB_THREADS, 0, ctx->stream>>>(P, w, clo, chi, hlo, hhi, cpb, wc, wh);
+    else
+        k_shia_tb<K, false><<<nblk, TB_THREADS, 0, ctx->stream>>>(P, w, clo, chi, hlo, hhi, cpb, wc, wh);
+    ctx->launches++;
+}
+
+// steps per time block of k_shia_tb (power of two <= 32); 0 = use the one-step-per-launch kernel k_shia_wave
+static int tb_steps(int T, bool eligible) {
+    if (!eligible) return 0;
+    int k = 8;
+    if (const char *e = getenv("WMF_SHIA_K")) k = atoi(e);
+    if (k <= 0) return 0;
+    int p = 1;
+    while (p * 2 <= k && p * 2 <= 32) p *= 2;
+    while (p > 1 && p > T) p /= 2;
+    return p;
 }
 
 extern "C" {
@@ -1105,19 +1469,47 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     P.tw = tw; P.cs = cs; P.Lmax = Lmax;
     P.ctrl_cells = ctrl_cells; P.ctrlh_cells = ctrlh_cells; P.n_ctrl = (int)nq; P.n_ctrlh = (int)nh;
 
+    // ---- which kernel: the time-blocked wavefront unless an output only the one-step kernel produces is wanted ----
+    const bool per_run = (M == 1);
+    const bool tb_ok = !sed && !slides && !(cfg->show_storage && out->mean_storage) && !(cfg->show_mean_speed && out->mean_speed) &&
+                       !(cfg->retorno_gr == 1.0f && cfg->show_mean_retorno && out->mean_retorno);
+    const int KT = tb_steps(T, tb_ok);
+    std::vector<int32_t> h_hfirst;
+    int64_t n_hill = 0;
+    if (KT) {
+        int32_t *is_h, *hpos, *hidx, *cidx, *d_hfirst;
+        WMF_TRY(sc.alloc(&is_h, (size_t)N)); WMF_TRY(sc.alloc(&hpos, (size_t)N));
+        WMF_TRY(sc.alloc(&hidx, (size_t)N)); WMF_TRY(sc.alloc(&cidx, (size_t)N));
+        WMF_TRY(sc.alloc(&d_hfirst, (size_t)Lmax + 2));
+        LAUNCH(ctx, k_role_flags, G, B, 0, tw, N, is_h);
+        WMF_TRY(wmf_device_exclusive_scan_i32(ctx, sc, is_h, hpos, N, &n_hill));
+        LAUNCH(ctx, k_role_lists, G, B, 0, is_h, hpos, N, hidx, cidx);
+        LAUNCH(ctx, k_role_level_first, grid_for(Lmax + 1, B), B, 0, level_first, hpos, Lmax + 1, d_hfirst);
+        h_hfirst.resize((size_t)Lmax + 2);
+        CU_TRY(ctx, cudaMemcpyAsync(h_hfirst.data(), d_hfirst, sizeof(int32_t) * ((size_t)Lmax + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        P.hidx = hidx; P.cidx = cidx;
+        P.nb = (T + KT - 1) / KT;
+        P.bal_direct = 1;
+    }
     // ---- state ----
     const size_t NM = (size_t)N * M;
     WMF_TRY(sc.alloc(&P.sto, 5 * NM));
     WMF_TRY(sc.alloc(&P.hsp, 4 * NM));
-    WMF_TRY(sc.alloc(&P.outb, 8 * NM));
     double *d_sto0, *d_recsum;
     WMF_TRY(sc.alloc(&d_sto0, 1));
     WMF_TRY(sc.alloc(&d_recsum, (size_t)in->n_records));
     CU_TRY(ctx, cudaMemsetAsync(d_sto0, 0, sizeof(double), ctx->stream));
     CU_TRY(ctx, cudaMemsetAsync(d_recsum, 0, sizeof(double) * (size_t)in->n_records, ctx->stream));
-    LAUNCH(ctx, k_state_init, G, B, 0, use_stoin ? d_stoin : d_storage, use_stoin ? 0.0f : cfg->storage_constant, N, M, P.sto, d_sto0);
+    if (KT) {
+        P.st4 = reinterpret_cast<float4 *>(P.sto);
+        P.s5 = P.sto + 4 * NM;
+        WMF_TRY(sc.alloc(&P.outb4, (size_t)2 * KT * NM));
+        LAUNCH(ctx, k_state_init_tb, G, B, 0, use_stoin ? d_stoin : d_storage, use_stoin ? 0.0f : cfg->storage_constant, N, M, P.st4, P.s5);
+    } else {
+        WMF_TRY(sc.alloc(&P.outb, 8 * NM));
+        LAUNCH(ctx, k_state_init, G, B, 0, use_stoin ? d_stoin : d_storage, use_stoin ? 0.0f : cfg->storage_constant, N, M, P.sto, d_sto0);
+    }
     LAUNCH(ctx, k_hspeed_init, grid_for((long long)NM, B), B, 0, d_hspeedin, N, M, P.hsp);
-    const bool per_run = (M == 1);
     // ---- outputs ----
     const size_t QN = (size_t)M * cfg->n_cont * T, HN = (size_t)M * cfg->n_conth * T;
     WMF_TRY(sc.out(out->q, QN, &P.q));
@@ -1209,16 +1601,35 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     // ---- the wavefront ----
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // h_first is complete
     auto level_end = [&](int L) { return L == 0 ? N : h_first[L - 1]; };
-    const int n_waves = T + Lmax;
+    const int n_waves = (KT ? P.nb : T) + Lmax;
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    for (int w = 0; w < n_waves; ++w) {
-        const int Lhi = std::min(Lmax, Lmax - w + T - 1), Llo = std::max(0, Lmax - w);
-        const int lo = h_first[Lhi], hi = level_end(Llo);
-        if (hi <= lo) continue;
-        if (sed && slides) launch_wave<true, true>(ctx, P, w, lo, hi);
-        else if (sed) launch_wave<true, false>(ctx, P, w, lo, hi);
-        else if (slides) launch_wave<false, true>(ctx, P, w, lo, hi);
-        else launch_wave<false, false>(ctx, P, w, lo, hi);
+    if (KT) {
+        const int nb = P.nb;
+        for (int w = 0; w < n_waves; ++w) {
+            const int Lhi = std::min(Lmax, Lmax - w + nb - 1), Llo = std::max(0, Lmax - w);
+            const int lo = h_first[Lhi], hi = level_end(Llo);
+            if (hi <= lo) continue;
+            const int hlo = h_hfirst[Lhi], hhi = (Llo == 0) ? (int)n_hill : h_hfirst[Llo - 1];
+            const int clo = lo - hlo, chi = hi - hhi;
+            switch (KT) {
+                case 1: launch_tb<1>(ctx, P, w, clo, chi, hlo, hhi); break;
+                case 2: launch_tb<2>(ctx, P, w, clo, chi, hlo, hhi); break;
+                case 4: launch_tb<4>(ctx, P, w, clo, chi, hlo, hhi); break;
+                case 8: launch_tb<8>(ctx, P, w, clo, chi, hlo, hhi); break;
+                case 16: launch_tb<16>(ctx, P, w, clo, chi, hlo, hhi); break;
+                default: launch_tb<32>(ctx, P, w, clo, chi, hlo, hhi); break;
+            }
+        }
+    } else {
+        for (int w = 0; w < n_waves; ++w) {
+            const int Lhi = std::min(Lmax, Lmax - w + T - 1), Llo = std::max(0, Lmax - w);
+            const int lo = h_first[Lhi], hi = level_end(Llo);
+            if (hi <= lo) continue;
+            if (sed && slides) launch_wave<true, true>(ctx, P, w, lo, hi);
+            else if (sed) launch_wave<true, false>(ctx, P, w, lo, hi);
+            else if (slides) launch_wave<false, true>(ctx, P, w, lo, hi);
+            else launch_wave<false, false>(ctx, P, w, lo, hi);
+        }
     }
     CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     CU_TRY(ctx, cudaGetLastError());
@@ -1226,15 +1637,18 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     ctx->last_waves = n_waves;
 
     // ---- epilogue ----
-    if (d_stoout || d_hsout) LAUNCH(ctx, k_state_final, grid_for((long long)NM, B), B, 0, P, d_stoout, d_hsout);
+    if (d_stoout || d_hsout) {
+        if (KT) LAUNCH(ctx, k_state_final_tb, grid_for((long long)NM, B), B, 0, P, d_stoout, d_hsout);
+        else LAUNCH(ctx, k_state_final, grid_for((long long)NM, B), B, 0, P, d_stoout, d_hsout);
+    }
     if (per_run && (d_balance || d_mean_rain || d_mean_storage || d_mean_speed || d_mean_retorno)) {
         double *red = P.red;
         if (!red) {  // only mean_rain wanted
             WMF_TRY(sc.alloc(&red, (size_t)T * RQ_COUNT * RED_SUB));
             CU_TRY(ctx, cudaMemsetAsync(red, 0, sizeof(double) * (size_t)T * RQ_COUNT * RED_SUB, ctx->stream));
         }
-        LAUNCH(ctx, k_shia_epilogue, grid_for(T, 128), 128, 0, red, d_recsum, P.pos, d_sto0, N, T, P.show_storage, d_balance,
-               d_mean_rain, d_mean_storage, d_mean_speed, d_mean_retorno);
+        LAUNCH(ctx, k_shia_epilogue, grid_for(T, 128), 128, 0, red, d_recsum, P.pos, d_sto0, N, T, P.show_storage, P.bal_direct,
+               d_balance, d_mean_rain, d_mean_storage, d_mean_speed, d_mean_retorno);
     }
     if (sed) {
         float *vs, *vd, *vsc, *vdc, *ve, *vdp, *erot, *dept;
