@@ -20,6 +20,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "wmf_pow.cuh"
 
 constexpr int WAVE_THREADS = 256;
 #ifndef WAVE_MIN_BLOCKS
@@ -91,14 +92,27 @@ __device__ __forceinline__ size_t sidx(const ShiaP &P, int k, int cell, int m) {
     return ((size_t)k * P.N + cell) * P.M + m;
 }
 
+// x / 3 and x / 1000, correctly rounded without the generic division sequence: q0 = x * (1/c), one fma for the exact
+// remainder, one to correct (tools/check_pow.cpp verifies both against x / c over every finite float with |q| >= 1e-30).
+__device__ __forceinline__ float div_by_3(float x) {
+    if (!(fabsf(x) >= 1e-29f && fabsf(x) < 1e37f)) return x / 3.0f;
+    const float rc = 1.0f / 3.0f, q0 = x * rc;
+    return fmaf(fmaf(-3.0f, q0, x), rc, q0);
+}
+__device__ __forceinline__ float div_by_1000(float x) {
+    if (!(fabsf(x) >= 1e-26f && fabsf(x) < 1e37f)) return x / 1000.0f;
+    const float rc = 1.0f / 1000.0f, q0 = x * rc;
+    return fmaf(fmaf(-1000.0f, q0, x), rc, q0);
+}
+
 // modelosv2.f90:1278-1293
 __device__ __forceinline__ float calc_speed_dev(float sm, float coef, float expo, float elem_long, float &speed,
                                                 float dt, int niter) {
     float area = 0.0f;
     for (int i = 0; i < niter; ++i) {
         area = sm / (elem_long + speed * dt);
-        const float new_speed = coef * powf(area, expo);
-        speed = (2.0f * new_speed + speed) / 3.0f;
+        const float new_speed = coef * wmf_powf(area, expo);
+        speed = div_by_3(2.0f * new_speed + speed);
     }
     return area;
 }
@@ -336,7 +350,7 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
         // ---- vertical cascade (:478-512) ----
         float vf1 = fmaxf(0.0f, R - H1 + S[0]);
         S[0] = S[0] + R - vf1;
-        const float E = fminf(__ldg(P.evp + t) * vs1 * powf(S[0] / H1, 0.6f), S[0]);
+        const float E = fminf(__ldg(P.evp + t) * vs1 * wmf_powf(S[0] / H1, 0.6f), S[0]);
         S[0] = S[0] - E;
         float vf2 = fminf(vf1, vs2);
         S[1] = S[1] + vf1 - vf2;
@@ -683,18 +697,14 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
     float vch = 0.f, ccoef = 0.f, cexpo = 0.f, Ls = 1.f, ret_acc = 0.f;
     int c0 = 0, rowq = -1, rowh = -1;
     if (active) {
-        float cal[11];
-        {
-            const float *cp = P.calib + (size_t)m * 11;
-#pragma unroll
-            for (int k = 0; k < 11; ++k) cal[k] = __ldg(cp + k);
-        }
+        const float *cal = P.calib + (size_t)m * 11;
         const float4 vc = __ldg(reinterpret_cast<const float4 *>(P.v_coef) + cell);
         const float4 hc = __ldg(reinterpret_cast<const float4 *>(P.h_coef) + cell);
-        vs1 = vc.x * cal[0] * dt; vs2 = vc.y * cal[1] * dt; vs3 = vc.z * cal[2] * dt; vs4 = vc.w * cal[3] * dt;
-        H1 = __ldg(P.max_capilar + cell) * cal[8];
-        if (P.retorno_gr > 0.0f) H2 = __ldg(P.max_gravita + cell) * cal[9];
-        if (P.retorno_aq > 0.0f) H3 = __ldg(P.max_aquifer + cell) * cal[10];
+        vs1 = vc.x * __ldg(cal + 0) * dt; vs2 = vc.y * __ldg(cal + 1) * dt;
+        vs3 = vc.z * __ldg(cal + 2) * dt; vs4 = vc.w * __ldg(cal + 3) * dt;
+        H1 = __ldg(P.max_capilar + cell) * __ldg(cal + 8);
+        if (P.retorno_gr > 0.0f) H2 = __ldg(P.max_gravita + cell) * __ldg(cal + 9);
+        if (P.retorno_aq > 0.0f) H3 = __ldg(P.max_aquifer + cell) * __ldg(cal + 10);
         Lh = __ldg(P.hill_long + cell);
         m3 = __ldg(P.elem_area + cell) / 1000.0f;
         const float4 s = P.st4[base];
@@ -706,18 +716,18 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             if (!KIN || P.st[k] == 1) {
-                const float v = P.hs_state ? P.hsp[k * NM + base] : hcoef[k] * cal[4 + k];
+                const float v = P.hs_state ? P.hsp[k * NM + base] : hcoef[k] * __ldg(cal + 4 + k);
                 kv[k] = v;
                 fl[k] = 1.0f - Lh / (v * dt + Lh);
             } else {
                 kv[k] = P.hsp[k * NM + base];
-                kc[k] = hcoef[k] * cal[4 + k];
+                kc[k] = hcoef[k] * __ldg(cal + 4 + k);
                 ke[k] = hexp[k];
             }
         }
         if (CHAN) {
             vch = P.hsp[3 * NM + base];
-            ccoef = hc.w * cal[7];
+            ccoef = hc.w * __ldg(cal + 7);
             cexpo = he.w;
             Ls = __ldg(P.stream_long + cell);
         }
@@ -733,7 +743,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
         if (P.retorned) ret_acc = P.retorned[cell];
     }
     const bool outlet = active && (cell == N - 1);
-    const float4 *ob_in = P.outb4 + (size_t)(b & 1) * K * NM + m;
+    const float4 *ob_in = P.outb4 + (size_t)(b & 1) * K * NM + (size_t)c0 * M + m;
     float4 *ob_out = P.outb4 + (size_t)(b & 1) * K * NM + base;
     // ---- the K steps of the block ----
 #pragma unroll 1
@@ -746,8 +756,8 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             {
                 const float4 *ob = ob_in + (size_t)tt * NM;
 #pragma unroll 1
-                for (int c = c0; c < c0 + nch; ++c) {
-                    const float4 o = ob[(size_t)c * M];
+                for (int c = 0; c < nch; ++c, ob += M) {
+                    const float4 o = *ob;
                     S1 = S1 + o.x;
                     S2 = S2 + o.y;
                     S3 = S3 + o.z;
@@ -757,11 +767,11 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             // rain (:444-449)
             const int p = __ldg(P.pos + t);
             float R = 0.0f;
-            if (p != 1) R = (float)__ldg(P.rain + (size_t)(p - 1) * N + cell) / 1000.0f;
+            if (p != 1) R = div_by_1000((float)__ldg(P.rain + (size_t)(p - 1) * N + cell));
             // vertical cascade (:478-512)
             const float vf1 = fmaxf(0.0f, R - H1 + S0);
             S0 = S0 + R - vf1;
-            const float E = fminf(__ldg(P.evp + t) * vs1 * powf(S0 / H1, 0.6f), S0);
+            const float E = fminf(__ldg(P.evp + t) * vs1 * wmf_powf(S0 / H1, 0.6f), S0);
             S0 = S0 - E;
             const float vf2 = fminf(vf1, vs2);
             S1 = S1 + vf1 - vf2;
@@ -1302,7 +1312,7 @@ static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int
 // steps per time block of k_shia_tb (power of two <= 32); 0 = use the one-step-per-launch kernel k_shia_wave
 static int tb_steps(int T, bool eligible) {
     if (!eligible) return 0;
-    int k = 8;
+    int k = 4;
     if (const char *e = getenv("WMF_SHIA_K")) k = atoi(e);
     if (k <= 0) return 0;
     int p = 1;
