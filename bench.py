@@ -13,8 +13,10 @@ Numbers on the JSON line
   value      cell-steps/s, inputs resident in HBM, timed with CUDA events on the launch stream
   e2e        the same run through the public drop-in call models.shia_v1(...) with HOST (pinned) buffers:
              host->device copies of every input and device->host reads of every output are inside the timed region
-  roofline   dominant kernel k_shia_wave: algorithmic bytes (144 B/cell-step, SURVEY 8d / DESIGN.md) / CUDA-event
-             time of the wave launches, against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  roofline   dominant kernel k_shia_tb (time-blocked wavefront): algorithmic bytes (144 B/cell-step, SURVEY 8d /
+             DESIGN.md) / CUDA-event time of the wave launches, against the measured HBM copy bandwidth
+             (MEASURED_PEAKS.json).  The kernel keeps a cell's state in registers for K steps and its per-step
+             traffic is served from L2, so its DRAM traffic (`traffic`, from ncu) is well below the algorithmic bytes.
   cpu_baseline  the CPU oracle (C restatement of the Fortran, -O3 -funroll-loops, 1 thread) on a bounded sample
   extra      Path A (basin_find+basin_cut+basin_acum) Mcell/s on the same raster, and run statistics
 """
@@ -34,6 +36,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BYTES_PER_CELL_STEP = 144.0      # algorithmic bytes of one cell-step of a single run
+# dram__bytes_read.sum + dram__bytes_write.sum per k_shia_tb launch from the ncu --set full capture under profiles/
+# (cold-cache replay of a mid-run wave, 1.33e6 cell-steps in that launch); None until a capture exists
+TRAFFIC_PER_LAUNCH = None
+TRAFFIC_NOTE = "see profiles/README.md"
 WORKLOADS = {
     # name: (ncols, nrows, steps, generator)
     "c2": (1024, 1024, 1000, "G2"),      # BASELINE.json configs[1]
@@ -335,9 +341,10 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": "k_shia_wave<false,false>",
-                         "bytes_per_cell_step": BYTES_PER_CELL_STEP,
-                         "launches_per_run": n_waves},
+                         "traffic": TRAFFIC_PER_LAUNCH, "peak_kind": peak_kind, "kernel": "k_shia_tb<4,false>",
+                         "bytes_per_cell_step": BYTES_PER_CELL_STEP, "launches_per_run": n_waves,
+                         "achieved_per_launch_bytes": BYTES_PER_CELL_STEP * cell_steps / max(n_waves, 1),
+                         "traffic_note": TRAFFIC_NOTE},
             "cpu_baseline": {"value": cpu_v, "unit": "cell-steps/s", "cores": 1, "kind": "port",
                              "sample": f"first {cpu_steps} of {T} steps of the same basin ({cpu_s:.1f} s), oracle "
                                        "-O3 -funroll-loops, single thread like the reference's Fortran"},

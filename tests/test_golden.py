@@ -1,0 +1,77 @@
+"""Committed golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py from the CPU oracle).
+
+CPU leg: today's oracle reproduces the frozen vectors (topology bit-exact, floats to 1e-6 to survive a libm update).
+GPU leg: the CUDA path through the C ABI matches the same vectors at the north-star tolerance without touching oracle/.
+"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+mg = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(mg)
+
+NAMES = sorted(mg.CASES)
+
+
+def load(name):
+    return dict(np.load(os.path.join(HERE, "golden", name + ".npz")))
+
+
+def close(got, ref, rtol, name):
+    got, ref = np.asarray(got, np.float64).reshape(-1), np.asarray(ref, np.float64).reshape(-1)
+    assert got.shape == ref.shape, (name, got.shape, ref.shape)
+    scale = max(float(np.abs(ref).max()), 1e-30)
+    bad = np.abs(got - ref) > rtol * np.abs(ref) + 1e-7 * scale
+    assert not bad.any(), f"{name}: {bad.sum()} of {bad.size} values off"
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_reproduces_golden(name):
+    g = load(name)
+    bs, v, inp, flags = mg.build_case(name)
+    np.testing.assert_array_equal(bs["basin"], g["basin_f"])
+    np.testing.assert_array_equal(v["acum"], g["acum"])
+    np.testing.assert_array_equal(v["lng"], g["long"])
+    np.testing.assert_array_equal(v["pend"], g["pend"])
+    assert int(inp["rain"].astype(np.int64).sum()) == int(g["rain_checksum"][0])
+    ref = mg.run_oracle(inp, flags)
+    for k in mg.KEEP:
+        if "o_" + k in g:
+            close(ref[k], g["o_" + k], 1e-6, f"{name}:{k}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_matches_golden(name):
+    from conftest import geo_to
+    from wmf_b200 import CuModule, ModelsModule, synth
+    g = load(name)
+    bs, v, inp, flags = mg.build_case(name)          # inputs only (generators); no oracle model run below
+    cu = CuModule()
+    geo_to(cu, bs)
+    n = cu.basin_find(bs["x"], bs["y"], bs["DIR"], bs["nc"], bs["nr"])
+    b = cu.basin_cut(n)
+    np.testing.assert_array_equal(b, g["basin_f"])
+    np.testing.assert_array_equal(cu.basin_acum(b), g["acum"])
+    m = ModelsModule()
+    synth.apply_to_models(m, inp)
+    for k, val in flags.items():
+        setattr(m, k, val)
+    m.set_rain(inp["rain"], inp["pos_evento"])
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    n_conth = max(1, int(np.count_nonzero(inp["control_h"])))
+    ret = m.shia_v1(None, None, inp["calib"], n_cont, n_conth, inp["n_reg"], None, None, n)
+    close(ret[0], g["o_q"], 1e-5, "Q")
+    close(ret[9], g["o_stoout"], 1e-5, "StoOut")
+    close(ret[3], g["o_hum"], 1e-5, "Hum")
+    tot = float(np.abs(g["o_stoout"]).sum())
+    assert np.abs(ret[6] - g["o_balance64"]).max() <= 2e-7 * tot
+    np.testing.assert_array_equal(m.acum_rain.reshape(-1), g["o_acum_rain"])
+    if "o_vs" in g:
+        close(ret[1], g["o_qsed"], 5e-5, "Qsed")
+        close(m.vd, g["o_vd"], 5e-5, "Vd")
+        np.testing.assert_array_equal(m.sl_riskvector.reshape(-1), g["o_sl_riskvector"])

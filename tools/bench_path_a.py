@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Path A at scale: basin_find + basin_cut + basin_acum (+ basics / HAND) on synthetic G2 rasters, DIR resident in HBM.
+Prints one JSON line per size: Mcell/s, levels, per-level time, achieved GB/s against the 28 B/cell algorithmic figure."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sizes", default="1024,4096,8192")
+    ap.add_argument("--kind", default="G2")
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--check", action="store_true", help="verify structural invariants on the host (slow for large N)")
+    a = ap.parse_args()
+    import torch
+    from wmf_b200 import Context, CuModule, synth
+    ctx = Context(0)
+    cu = CuModule(ctx)
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        peak = 6650.0
+    for s in a.sizes.split(","):
+        nc = nr = int(s)
+        t0 = time.time()
+        DIR, _ = synth.make_raster(a.kind, nc, nr, seed=0)
+        gen_s = time.time() - t0
+        cu.ncols, cu.nrows, cu.xll, cu.yll, cu.dx, cu.dy, cu.dxp, cu.nodata = nc, nr, 0.0, 0.0, 30.0, 30.0, 30.0, synth.NODATA
+        x, y = synth.outlet_xy(nc, nr, 0.0, 0.0, 30.0)
+        d_dir = torch.from_numpy(np.ascontiguousarray(DIR.T)).cuda()
+        del DIR
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        best = None
+        for _ in range(a.reps):
+            torch.cuda.synchronize()
+            ev[0].record()
+            n = cu.basin_find(x, y, d_dir)
+            ev[1].record()
+            b = cu.basin_cut(n, resident=True)
+            ev[2].record()
+            acum = cu.basin_acum(b)
+            ev[3].record()
+            torch.cuda.synchronize()
+            ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+            if best is None or sum(ts) < sum(best):
+                best = ts
+        levels = cu.basin_find_depth()
+        total = sum(best)
+        assert int(acum[-1].item()) == n, (int(acum[-1].item()), n)
+        line = {"raster": f"{nc}x{nr} {a.kind}", "cells": int(n), "levels": int(levels), "find_ms": best[0], "cut_ms": best[1],
+                "acum_ms": best[2], "total_ms": total, "mcell_per_s": n / total / 1e3,
+                "us_per_level_find": 1e3 * best[0] / max(levels, 1),
+                "achieved_gbs_28B": 28.0 * n / (total / 1e3) / 1e9, "frac_of_measured_hbm": 28.0 * n / (total / 1e3) / 1e9 / peak,
+                "gen_s": gen_s}
+        if a.check:
+            bb = b.cpu().numpy().reshape(-1, 3)
+            d = bb[:, 0]
+            assert d[-1] == 0 and (d[:-1] > 0).all()
+            par = n - d[:-1]
+            assert (par > np.arange(n - 1)).all()
+            line["checked"] = True
+        print(json.dumps(line), flush=True)
+        del d_dir, b, acum
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()

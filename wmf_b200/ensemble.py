@@ -1,0 +1,101 @@
+"""Calibration ensembles across GPUs -- the replacement of the reference's ``multiprocessing.Pool`` evaluation.
+
+Reference: ``SimuBasin.Calib_NSGAII`` (wmf.py:4662-4733) evaluates every NSGA-II generation with
+``__ejec_parallel__`` (wmf.py:872-878): ``Pool(nproc).map`` of ``run_shia`` over the population, keeping
+``Qsim[nodo]`` of each member, then scores it with ``__eval_nash__`` / ``__eval_q_pico__`` (wmf.py:749-754, 775-781).
+
+Here: one process per GPU (``torch.distributed``); member ``i`` of the population runs on rank ``i mod world``; every
+rank holds a full replica of topology, maps and rain (members are independent, so there is no data-path collective);
+the members of a rank run ``members_per_launch`` at a time in ONE wavefront launch sequence (member-minor state layout,
+``wmf_shia_run`` with ``n_members > 1``); the per-member objective scores are computed on the device
+(``wmf_eval_scores``) and exchanged with a single all-gather of ``[members, 2]`` fp32 -- the only collective.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_members(n_members: int, rank: int, world: int) -> np.ndarray:
+    """Indices of the population members evaluated by ``rank``: round-robin, as balanced as possible."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    return np.arange(rank, n_members, world, dtype=np.int64)
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def gather_scores(local_scores, n_members: int, device=None):
+    """All-gather the per-member scores of every rank into population order.
+
+    ``local_scores``: (len(shard_members(n_members, rank, world)), n_obj) torch tensor or numpy array on this rank.
+    Returns a (n_members, n_obj) torch tensor (same on every rank).  Ranks may hold different member counts; the
+    exchange is padded to the largest shard so that a single fixed-size ``all_gather`` (NCCL or gloo) does it."""
+    import torch
+    dist, rank, world = _dist()
+    t = torch.as_tensor(local_scores, dtype=torch.float32)
+    if device is not None:
+        t = t.to(device)
+    if t.dim() == 1:
+        t = t[:, None]
+    n_obj = t.shape[1]
+    mine = shard_members(n_members, rank, world)
+    if t.shape[0] != mine.size:
+        raise ValueError(f"rank {rank} holds {t.shape[0]} score rows, its shard has {mine.size} members")
+    if world == 1:
+        return t.clone()
+    per = (n_members + world - 1) // world
+    pad = torch.full((per, n_obj), float("nan"), dtype=torch.float32, device=t.device)
+    pad[: t.shape[0]] = t
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    out = torch.empty((n_members, n_obj), dtype=torch.float32, device=t.device)
+    for r in range(world):
+        idx = shard_members(n_members, r, world)
+        out[torch.as_tensor(idx, device=t.device)] = parts[r][: idx.size]
+    return out
+
+
+def evaluate_population(models, calibs, qobs, n_cont, n_reg, rain, pos_evento, row: int = 0,
+                        members_per_launch: int = 64, run_batch=None):
+    """Scores ``[nash, qpico]`` of every calibration set in ``calibs`` (P,11) against ``qobs`` (n_reg), sharded over the
+    ranks of the initialised process group (or run locally when there is none).  Returns a (P,2) torch tensor.
+
+    ``run_batch(calib_batch) -> (m,2) scores`` may be injected (CPU tests of the sharding / gather logic); by default
+    a batch is one ``wmf_shia_run`` with ``n_members = m`` followed by ``wmf_eval_scores``, all resident on the GPU."""
+    import torch
+    calibs = np.ascontiguousarray(np.asarray(calibs, dtype=np.float32))
+    if calibs.ndim != 2 or calibs.shape[1] != 11:
+        raise ValueError("calibs must be (P,11) (modelosv2.f90:201)")
+    P = calibs.shape[0]
+    _, rank, world = _dist()
+    mine = shard_members(P, rank, world)
+    dev = None
+    if run_batch is None:
+        c = models.ctx
+        dev = torch.device(f"cuda:{c.device}")
+        d_qobs = torch.as_tensor(np.ascontiguousarray(qobs, np.float32), device=dev)
+        if d_qobs.numel() != n_reg:
+            raise ValueError("qobs must hold n_reg values")
+
+        def run_batch(cb):
+            m = cb.shape[0]
+            # wmf_shia_run treats n_members == 1 as the single-run layout, which is the same memory for q
+            out = models._run(cb, n_cont, 1, n_reg, rain, pos_evento, device_out=True, want={"q"})
+            sc = torch.empty((m, 2), dtype=torch.float32, device=dev)
+            c.check(c.L.wmf_eval_scores(c.h, out["q"].data_ptr(), m, n_cont, n_reg, row, d_qobs.data_ptr(), sc.data_ptr()))
+            return sc
+
+    chunks = []
+    for s in range(0, mine.size, max(1, members_per_launch)):
+        idx = mine[s: s + members_per_launch]
+        chunks.append(torch.as_tensor(run_batch(calibs[idx]), dtype=torch.float32))
+    if chunks:
+        local = torch.cat(chunks, 0)
+    else:
+        local = torch.empty((0, 2), dtype=torch.float32, device=dev)
+    return gather_scores(local, P, device=local.device)
