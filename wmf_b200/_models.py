@@ -134,6 +134,21 @@ def write_rain_files(path_bin: str, path_hdr: str, rain, pos_evento, dates=None,
             f.write("%d, \t %d, \t %.2f, %s \n" % (c + 1, p, mean, d))
 
 
+def _pinned_empty(shape, dtype, order="F"):
+    """ndarray backed by page-locked host memory when a CUDA device is present (torch's caching pinned allocator), so
+    that the library's host<->device staging copies are true DMA transfers; plain numpy otherwise."""
+    n = int(np.prod(shape))
+    if n * np.dtype(dtype).itemsize >= (64 << 10):
+        try:
+            import torch
+            if torch.cuda.is_available():
+                tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
+                return torch.empty(n, dtype=tdt, pin_memory=True).numpy().reshape(shape, order=order)
+        except Exception:
+            pass
+    return np.empty(shape, dtype=dtype, order=order)
+
+
 class ModelsModule:
     """Drop-in for the Fortran module object ``models``."""
 
@@ -167,7 +182,9 @@ class ModelsModule:
             if value is None:
                 d["_a"].pop(name, None)
                 return
-            arr = np.array(value, dtype=dtype, order="F", copy=True)
+            src = np.asarray(value)
+            arr = _pinned_empty(src.shape, dtype)          # f2py copies and casts on assignment
+            arr[...] = src
             if K == 0:
                 arr = arr.reshape(-1)
                 if name in ("speed_type", "wi", "diametro") and arr.size != 3:
@@ -385,7 +402,7 @@ class ModelsModule:
                 tdt = torch.float32 if dtype == np.float32 else torch.int32
                 arr = torch.empty(tuple(reversed(shape)), dtype=tdt, device=f"cuda:{c.device}")
             else:
-                arr = np.empty(shape, dtype=dtype, order="F")
+                arr = _pinned_empty(shape, dtype)
             res[name] = arr
             setattr(so, name, ptr(arr))
 

@@ -19,6 +19,8 @@ struct wmf_ctx {
     int num_sms = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    cudaStream_t copy_stream = nullptr;          // host->device streaming of big inputs next to the compute stream
+    std::vector<cudaEvent_t> copy_events;
     cudaMemPool_t pool = nullptr;
     char err[512] = {0};
     int64_t launches = 0;

@@ -40,6 +40,8 @@ int wmf_ctx_destroy(wmf_ctx *ctx) {
     if (ctx->q_par) cudaFree(ctx->q_par);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return WMF_OK;

@@ -1280,6 +1280,55 @@ static int read_flag(wmf_ctx *ctx, const int *d, int *h) {
     return WMF_OK;
 }
 
+// Host -> device streaming of the rain table.  Pinned (or registered) host memory: chunks of whole records are copied on
+// the context's copy stream, each followed by an event; the compute stream waits only for the chunks a wave needs.
+// Pageable host memory cannot be copied asynchronously, and device memory needs no copy: both take the plain path.
+struct RainStream {
+    wmf_ctx *owner = nullptr;
+    int recs_per_chunk = 0, n_chunks = 0, waited = 0;
+    bool active = false;
+    ~RainStream() {  // an early error return must not free the buffer under a copy still in flight
+        if (active && waited < n_chunks && owner && owner->copy_stream) cudaStreamSynchronize(owner->copy_stream);
+    }
+    int begin(wmf_ctx *ctx, Scope &sc, const int32_t *rain, int n_records, int N, const int32_t **dev) {
+        cudaPointerAttributes a;
+        bool pinned = false;
+        if (cudaPointerGetAttributes(&a, rain) == cudaSuccess) pinned = (a.type == cudaMemoryTypeHost);
+        else cudaGetLastError();
+        const size_t total = (size_t)n_records * N;
+        if (!pinned || total * 4 < (32u << 20)) return sc.in(rain, total, dev);
+        int32_t *d;
+        WMF_TRY(sc.alloc(&d, total));
+        if (!ctx->copy_stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        // the allocation is ordered on the compute stream: the copy stream must not start before it
+        CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev0, 0));
+        recs_per_chunk = std::max(1, (int)((48u << 20) / ((size_t)N * 4)));
+        n_chunks = (n_records + recs_per_chunk - 1) / recs_per_chunk;
+        while ((int)ctx->copy_events.size() < n_chunks) {
+            cudaEvent_t e;
+            CU_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->copy_events.push_back(e);
+        }
+        for (int c = 0; c < n_chunks; ++c) {
+            const size_t r0 = (size_t)c * recs_per_chunk, r1 = std::min((size_t)n_records, r0 + recs_per_chunk);
+            CU_TRY(ctx, cudaMemcpyAsync(d + r0 * N, rain + r0 * N, (r1 - r0) * N * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CU_TRY(ctx, cudaEventRecord(ctx->copy_events[c], ctx->copy_stream));
+        }
+        active = true;
+        owner = ctx;
+        *dev = d;
+        return WMF_OK;
+    }
+    // make the compute stream wait until records 1..rec (1-based) are on the device
+    int wait_records(wmf_ctx *ctx, int rec) {
+        if (!active) return WMF_OK;
+        const int need = std::min(n_chunks, (rec + recs_per_chunk - 1) / recs_per_chunk);
+        while (waited < need) CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_events[waited++], 0));
+        return WMF_OK;
+    }
+};
+
 template <bool SED, bool SLIDES>
 static void launch_wave(wmf_ctx *ctx, const ShiaP &P, int w, int lo, int hi) {
     const long long work = (long long)(hi - lo) * P.M;
@@ -1380,7 +1429,10 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     WMF_TRY(sc.in(in->evpserie, (size_t)T, &P.evp));
     WMF_TRY(sc.in(in->calib, (size_t)11 * M, &P.calib));
     if (in->n_records < 1) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: n_records must be >= 1");
-    WMF_TRY(sc.in(in->rain, (size_t)in->n_records * N, &P.rain));
+    // Rainfall is the one big input (C2: 1.7 GB).  From pinned host memory it is streamed in chunks of whole records on a
+    // second stream while the wavefront already runs: wave w only needs the records of the steps it has reached.
+    RainStream rs;
+    WMF_TRY(rs.begin(ctx, sc, in->rain, in->n_records, N, &P.rain));
     // pos_evento is needed on both sides: validate on the host
     std::vector<int32_t> h_pos((size_t)T);
     if (Scope::on_device(in->pos_evento)) {
@@ -1601,24 +1653,22 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
         P.sl_risk = d_risk;
         P.sl_cosr = d_cosr; P.sl_sinr = d_sinr; P.sl_tanfa = d_tanfa;
     }
-    // rain statistics that do not depend on the model state
-    if (per_run) {
-        dim3 rg((unsigned)std::min(grid_for(N, 256), 64), (unsigned)in->n_records);
-        LAUNCH(ctx, k_rain_record_sum, rg, 256, 0, P.rain, N, d_recsum);
-        if (d_acum_rain) LAUNCH(ctx, k_acum_rain, G, B, 0, P.rain, P.pos, N, T, d_acum_rain);
-    }
 
     // ---- the wavefront ----
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // h_first is complete
     auto level_end = [&](int L) { return L == 0 ? N : h_first[L - 1]; };
     const int n_waves = (KT ? P.nb : T) + Lmax;
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    // need_rec[t] = highest rain record any step <= t reads
+    std::vector<int32_t> need_rec((size_t)T);
+    for (int t = 0, mx = 1; t < T; ++t) { mx = std::max(mx, h_pos[t]); need_rec[t] = mx; }
     if (KT) {
         const int nb = P.nb;
         for (int w = 0; w < n_waves; ++w) {
             const int Lhi = std::min(Lmax, Lmax - w + nb - 1), Llo = std::max(0, Lmax - w);
             const int lo = h_first[Lhi], hi = level_end(Llo);
             if (hi <= lo) continue;
+            WMF_TRY(rs.wait_records(ctx, need_rec[std::min((long long)T - 1, ((long long)std::min(w, nb - 1) + 1) * KT - 1)]));
             const int hlo = h_hfirst[Lhi], hhi = (Llo == 0) ? (int)n_hill : h_hfirst[Llo - 1];
             const int clo = lo - hlo, chi = hi - hhi;
             switch (KT) {
@@ -1635,6 +1685,7 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
             const int Lhi = std::min(Lmax, Lmax - w + T - 1), Llo = std::max(0, Lmax - w);
             const int lo = h_first[Lhi], hi = level_end(Llo);
             if (hi <= lo) continue;
+            WMF_TRY(rs.wait_records(ctx, need_rec[std::min(w, T - 1)]));
             if (sed && slides) launch_wave<true, true>(ctx, P, w, lo, hi);
             else if (sed) launch_wave<true, false>(ctx, P, w, lo, hi);
             else if (slides) launch_wave<false, true>(ctx, P, w, lo, hi);
@@ -1643,6 +1694,13 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     }
     CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     CU_TRY(ctx, cudaGetLastError());
+    WMF_TRY(rs.wait_records(ctx, in->n_records));
+    // rain statistics that do not depend on the model state
+    if (per_run) {
+        dim3 rg((unsigned)std::min(grid_for(N, 256), 64), (unsigned)in->n_records);
+        LAUNCH(ctx, k_rain_record_sum, rg, 256, 0, P.rain, N, d_recsum);
+        if (d_acum_rain) LAUNCH(ctx, k_acum_rain, G, B, 0, P.rain, P.pos, N, T, d_acum_rain);
+    }
     ctx->last_levels = Lmax + 1;
     ctx->last_waves = n_waves;
 

@@ -3,8 +3,8 @@
 //  basin_find   level-synchronous BFS in ONE persistent cooperative kernel.  Queue order == the Fortran's
 //               FIFO order (cuencas.f90:552-589): children of queue entry q are appended in the 3x3 scan
 //               order kf=1..3,kc=1..3, positions from an exclusive scan of child counts in queue order.
-//               Narrow frontiers run inside block 0 with __syncthreads only; wide ones use all SMs with two
-//               grid barriers per level.
+//               Each CTA owns a contiguous share of the level and of its children, so a level costs ONE
+//               all-to-all exchange of child counts (release/acquire slots) instead of grid barriers.
 //  basin_acum   leaf-to-root "last arriver climbs" sweep: one 64-bit atomicAdd per tree edge carries both the
 //               partial cell count and the arrival counter, no global barriers, exact (integer sums commute).
 //  acum_var /   same sweep, but the last arriver *gathers* its children in ascending cell order, which
@@ -12,6 +12,9 @@
 //  the rest     one thread per cell / raster cell.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -21,22 +24,27 @@ namespace cg = cooperative_groups;
 // basin_find
 // ---------------------------------------------------------------------------------------------------
 struct FindState {
-    long long fs, fe;  // current frontier = queue positions [fs, fe)
-    int depth;         // levels completed
-    int err;           // 1 = queue overflow (cyclic DIR)
-    int done;
-    int pad;
-    int blocksum[1024];
+    long long n;   // cells found
+    int depth;     // BFS levels (tree depth + 1)
+    int err;       // 1 = queue overflow (cyclic DIR)
 };
 
-constexpr int FIND_THREADS = 1024;
-constexpr int FIND_SB_MAX = 8192;     // frontiers up to this size stay inside block 0
-constexpr int FIND_MASK_CAP = 32768;  // per-block child-mask cache (bytes of shared memory)
+#ifndef FIND_THREADS_N
+#define FIND_THREADS_N 256
+#endif
+constexpr int FIND_THREADS = FIND_THREADS_N;
+constexpr int FIND_CAP = 16384;       // cells of a CTA's share of a level kept in shared memory (lin, next lin, mask)
+constexpr size_t FIND_SMEM = (size_t)FIND_CAP * 9;
+constexpr int FIND_MAX_CTAS = 256;
 
 // 8-bit mask of the neighbours of raster cell `lin` that drain into it, bit order = Fortran scan order
 // (kf outer, kc inner, centre skipped): cuencas.f90:555-571.
-__device__ __forceinline__ unsigned probe_children(const int32_t *__restrict__ dir, int nc, int nr, int lin) {
-    const int c0 = lin % nc, f0 = lin / nc;  // 0-based
+__device__ __forceinline__ unsigned probe_children(const int32_t *__restrict__ dir, int nc, int nr, float rnc, int lin) {
+    // row = lin / nc without the integer-division sequence: float estimate, one correction step (|error| <= 1)
+    int f0 = (int)((float)lin * rnc);
+    int c0 = lin - f0 * nc;
+    if (c0 < 0) { c0 += nc; --f0; }
+    else if (c0 >= nc) { c0 -= nc; ++f0; }
     unsigned m = 0;
     int bit = 0;
 #pragma unroll
@@ -54,8 +62,13 @@ __device__ __forceinline__ unsigned probe_children(const int32_t *__restrict__ d
     return m;
 }
 
-__device__ __forceinline__ void write_children(unsigned m, int lin, int nc, long long pos, int parent_qpos1,
-                                               int32_t *__restrict__ q_lin, int32_t *__restrict__ q_par) {
+__device__ __forceinline__ void prefetch_l2(const void *p);
+// Appends the children of `lin` at queue position `pos`; the first `cap - (pos - own_lo)` of them are also kept in
+// shared memory (`s_nxt`, the CTA's share of the next level) and the DIR rows they will probe are prefetched.
+__device__ __forceinline__ void write_children(unsigned m, int lin, int nc, long long ncell, long long pos, int parent_qpos1,
+                                               int32_t *__restrict__ q_lin, int32_t *__restrict__ q_par,
+                                               const int32_t *__restrict__ dir, int32_t *__restrict__ s_nxt,
+                                               long long own_lo, int cap) {
     int bit = 0;
 #pragma unroll
     for (int kf = 1; kf <= 3; ++kf) {
@@ -63,8 +76,10 @@ __device__ __forceinline__ void write_children(unsigned m, int lin, int nc, long
         for (int kc = 1; kc <= 3; ++kc) {
             if (kf == 2 && kc == 2) continue;
             if (m & (1u << bit)) {
-                q_lin[pos] = lin + (kf - 2) * nc + (kc - 2);
+                const int cl = lin + (kf - 2) * nc + (kc - 2);
+                q_lin[pos] = cl;
                 q_par[pos] = parent_qpos1;
+                if (pos - own_lo < cap) s_nxt[pos - own_lo] = cl;
                 ++pos;
             }
             ++bit;
@@ -72,138 +87,154 @@ __device__ __forceinline__ void write_children(unsigned m, int lin, int nc, long
     }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All-to-all exchange of one 32-bit value per CTA = the only grid-wide synchronisation of a BFS level.
+// CTA b publishes (stamp << 32 | value) in its slot; thread j of every CTA spins on slot j until it carries the
+// stamp.  Returns the exclusive prefix of the values over the CTAs before this one and the total.
+// Two slot sets alternate (a CTA can run at most one exchange ahead of the slowest one).  All CTAs are co-resident
+// (cooperative launch), so the spin cannot deadlock.  The slot traffic is relaxed; `fence` adds the release / acquire
+// fences that make the CTAs' earlier global writes visible to each other (needed only when they will read them).
+template <bool FENCE>
+__device__ __forceinline__ void cta_exchange(unsigned long long *slots, unsigned stamp, int value, int *s_scan,
+                                             int *my_off, int *total, int *lopsided) {
+    const int tid = threadIdx.x, b = blockIdx.x, nb = gridDim.x;
+    unsigned long long *set = slots + (size_t)(stamp & 1u) * FIND_MAX_CTAS;
+    __syncthreads();  // every thread's global writes of this phase precede the publication
+    if (tid == 0) {
+        if (FENCE) __threadfence();
+        st_relaxed_u64(set + b, ((unsigned long long)stamp << 32) | (unsigned)value);
+    }
+    int v = 0;
+    if (tid < nb) {
+        unsigned long long x;
+        do { x = ld_relaxed_u64(set + tid); } while ((unsigned)(x >> 32) != stamp);
+        v = (int)(unsigned)x;
+        if (FENCE) __threadfence();
+    }
+    int tot;
+    const int ex = block_scan_excl(v, s_scan, &tot);  // (contains __syncthreads)
+    if (tid == b) s_scan[33] = ex;
+    // some CTA holds much more than an even share of the total?  (same answer in every CTA)
+    *lopsided = __syncthreads_or(tid < nb && v > 2 * ((tot + nb - 1) / nb) + FIND_THREADS);
+    *my_off = s_scan[33];
+    *total = tot;
+    __syncthreads();
+}
+
+// Level-synchronous BFS with ONE grid-wide exchange per level.  Every CTA owns a contiguous range of queue positions
+// of the current level; it probes them, the CTAs exchange their child counts, and each CTA appends its children at
+// (level end + prefix of the counts before it) -- queue order == the Fortran's FIFO order (cuencas.f90:552-589) because
+// ranges are ordered by CTA.  A CTA's children are its range of the next level, so it never reads what another CTA
+// wrote, and no second barrier is needed.  When the ranges get lopsided the level is re-split evenly, which costs one
+// extra exchange (then CTAs do read each other's entries, with L1-bypassing loads).
 __global__ void __launch_bounds__(FIND_THREADS, 1)
 k_basin_find(const int32_t *__restrict__ dir, int nc, int nr, int32_t *__restrict__ q_lin,
-             int32_t *__restrict__ q_par, long long cap, FindState *st) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ int s_scan[33];
-    __shared__ int s_red[32];
-    __shared__ unsigned char s_mask[FIND_MASK_CAP];
-    const int tid = threadIdx.x, b = blockIdx.x, nb = gridDim.x;
-    long long fs = 0, fe = 1;
-    int depth = 0;
+             int32_t *__restrict__ q_par, long long cap, unsigned long long *slots, FindState *st) {
+    __shared__ int s_scan[34];
+    __shared__ int s_wsum[32];
+    extern __shared__ int32_t s_dyn[];      // [FIND_CAP] current share, [FIND_CAP] next share, [FIND_CAP] bytes of masks
+    int32_t *s_cur = s_dyn, *s_nxt = s_dyn + FIND_CAP;
+    unsigned char *s_mask = reinterpret_cast<unsigned char *>(s_dyn + 2 * FIND_CAP);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, b = blockIdx.x, nb = gridDim.x;
+    const float rnc = 1.0f / (float)nc;
+    const long long ncell = (long long)nc * nr;
+    long long fe = 1;                     // end of the current level in the queue
+    long long lo = 0, hi = (b == 0) ? 1 : 0;  // my share of it
+    bool cur_in_smem = false;             // s_cur[i] holds q_lin[lo + i] for i < FIND_CAP (I wrote them last level)
+    int depth = 0, err = 0;
+    unsigned stamp = 1;
     for (;;) {
-        const long long F = fe - fs;
-        if (F <= FIND_SB_MAX) {
-            // ---- narrow frontier: block 0 advances alone, level after level -------------------------
-            if (b == 0) {
-                int err = 0, done = 0;
-                for (;;) {
-                    long long running = fe;
-                    const long long Fl = fe - fs;
-                    for (long long base = fs; base < fe; base += FIND_THREADS) {
-                        const long long p = base + tid;
-                        unsigned m = 0;
-                        int lin = 0;
-                        if (p < fe) {
-                            lin = q_lin[p];
-                            m = probe_children(dir, nc, nr, lin);
-                        }
-                        int tot;
-                        const int ex = block_scan_excl(__popc(m), s_scan, &tot);
-                        if (running + tot > cap) { err = 1; break; }
-                        if (m) write_children(m, lin, nc, running + ex, (int)(p + 1), q_lin, q_par);
-                        running += tot;
-                    }
-                    __syncthreads();
-                    if (err) break;
-                    ++depth;
-                    fs = fe;
-                    fe = running;
-                    if (fe == fs) { done = 1; break; }
-                    if (fe - fs > FIND_SB_MAX) break;
-                    (void)Fl;
-                }
-                if (tid == 0) {
-                    st->fs = fs; st->fe = fe; st->depth = depth; st->err = err; st->done = done || err;
-                }
-            }
-            grid.sync();
-            fs = st->fs; fe = st->fe; depth = st->depth;
-            const int done = st->done;
-            grid.sync();  // nobody may overwrite st before everyone has read it
-            if (done) break;
-            continue;
-        }
-        // ---- wide frontier: all blocks, chunked in queue order ----------------------------------------
-        long long chunk = (F + nb - 1) / nb;
-        chunk = (chunk + FIND_THREADS - 1) / FIND_THREADS * FIND_THREADS;
-        const long long lo = fs + (long long)b * chunk;
-        long long hi = lo + chunk;
-        if (hi > fe) hi = fe;
-        // phase 1: count children of my chunk
+        const int mine = (int)(hi - lo);
+        // each warp takes a contiguous segment of 32*c positions; lane l handles seg + j*32 + l
+        const int c = (mine + FIND_THREADS - 1) / FIND_THREADS;
+        const long long seg = lo + (long long)wid * 32 * c;
+        // ---- phase 1: child masks and my count ----
         int cnt = 0;
-        for (long long p = lo + tid; p < hi; p += FIND_THREADS) {
-            const unsigned m = probe_children(dir, nc, nr, q_lin[p]);
-            if (p - lo < FIND_MASK_CAP) s_mask[p - lo] = (unsigned char)m;
-            cnt += __popc(m);
+        for (int j = 0; j < c; ++j) {
+            const long long p = seg + (long long)j * 32 + lane;
+            if (p < hi) {
+                const bool cached = p - lo < FIND_CAP;
+                int lin;
+                if (cached && cur_in_smem) lin = s_cur[p - lo];
+                else {
+                    lin = __ldcg(q_lin + p);
+                    if (cached) s_cur[p - lo] = lin;
+                }
+                const unsigned m = probe_children(dir, nc, nr, rnc, lin);
+                if (cached) s_mask[p - lo] = (unsigned char)m;
+                cnt += __popc(m);
+            }
         }
         cnt = warp_sum_i(cnt);
-        if ((tid & 31) == 0) s_red[tid >> 5] = cnt;
+        if (lane == 0) s_wsum[wid] = cnt;
         __syncthreads();
-        if (tid < 32) {
-            int v = s_red[tid];
-            v = warp_sum_i(v);
-            if (tid == 0) st->blocksum[b] = v;
+        int wpre = 0, mycnt = 0;  // children of the warps before mine / of the CTA
+#pragma unroll
+        for (int k = 0; k < FIND_THREADS / 32; ++k) {
+            const int v = s_wsum[k];
+            if (k < wid) wpre += v;
+            mycnt += v;
         }
-        grid.sync();
-        // phase 2: my offset = sum of the counts of the blocks before me; total = sum of all
-        int mine = 0, all = 0;
-        for (int j = tid; j < nb; j += FIND_THREADS) {
-            const int v = st->blocksum[j];
-            all += v;
-            if (j < b) mine += v;
-        }
-        mine = warp_sum_i(mine);
-        all = warp_sum_i(all);
-        __syncthreads();
-        if ((tid & 31) == 0) { s_red[tid >> 5] = mine; }
-        __syncthreads();
-        int off = 0;
-        if (tid < 32) off = warp_sum_i(s_red[tid]);
-        __syncthreads();
-        if ((tid & 31) == 0) { s_red[tid >> 5] = all; }
-        __syncthreads();
-        int total = 0;
-        if (tid < 32) total = warp_sum_i(s_red[tid]);
-        if (tid == 0) { s_scan[0] = off; s_scan[1] = total; }
-        __syncthreads();
-        off = s_scan[0];
-        total = s_scan[1];
-        __syncthreads();
-        if (fe + total > cap) {
-            if (b == 0 && tid == 0) { st->err = 1; st->depth = depth; st->fs = fs; st->fe = fe; }
-            break;  // uniform across the grid
-        }
-        long long running = fe + off;
-        for (long long base = lo; base < hi; base += FIND_THREADS) {
-            const long long p = base + tid;
+        // ---- the exchange ----
+        int off, total, lopsided;
+        cta_exchange<false>(slots, stamp++, mycnt, s_scan, &off, &total, &lopsided);
+        if (fe + total > cap) { err = 1; break; }  // uniform across the grid
+        // ---- phase 2: append my children in queue order ----
+        const long long nlo = fe + off;
+        long long base = nlo + wpre;
+        for (int j = 0; j < c; ++j) {
+            const long long p = seg + (long long)j * 32 + lane;
             unsigned m = 0;
             int lin = 0;
             if (p < hi) {
-                lin = q_lin[p];
-                m = (p - lo < FIND_MASK_CAP) ? (unsigned)s_mask[p - lo] : probe_children(dir, nc, nr, lin);
+                if (p - lo < FIND_CAP) { lin = s_cur[p - lo]; m = s_mask[p - lo]; }
+                else { lin = __ldcg(q_lin + p); m = probe_children(dir, nc, nr, rnc, lin); }
             }
-            int tot;
-            const int ex = block_scan_excl(__popc(m), s_scan, &tot);
-            if (m) write_children(m, lin, nc, running + ex, (int)(p + 1), q_lin, q_par);
-            running += tot;
+            const int k = __popc(m);
+            const int incl = warp_scan_incl(k);
+            if (m) write_children(m, lin, nc, ncell, base + incl - k, (int)(p + 1), q_lin, q_par, dir, s_nxt, nlo, FIND_CAP);
+            base += __shfl_sync(0xffffffffu, incl, 31);
         }
         ++depth;
-        fs = fe;
-        fe = fe + total;
-        grid.sync();
-        if (total == 0) {
-            if (b == 0 && tid == 0) { st->fs = fs; st->fe = fe; st->depth = depth; st->err = 0; }
-            break;
+        if (total == 0) break;
+        const long long nfs = fe, nfe = fe + total;
+        lo = nlo;
+        hi = lo + mycnt;
+        // ---- re-split the next level evenly when one CTA would carry much more than its share: the CTAs then read
+        // each other's entries, so this level needs a second exchange as a barrier (decision is grid-uniform) ----
+        if (lopsided) {
+            int d0, d1, d2;
+            cta_exchange<true>(slots, stamp++, 0, s_scan, &d0, &d1, &d2);
+            const long long chunk = ((long long)((total + nb - 1) / nb) + 31) / 32 * 32;
+            lo = nfs + (long long)b * chunk;
+            hi = lo + chunk;
+            if (lo > nfe) lo = nfe;
+            if (hi > nfe) hi = nfe;
+            cur_in_smem = false;
+        } else {
+            __syncthreads();  // s_nxt is complete
+            int32_t *t = s_cur; s_cur = s_nxt; s_nxt = t;
+            cur_in_smem = true;
         }
+        fe = nfe;
     }
+    if (b == 0 && tid == 0) { st->n = fe; st->depth = depth; st->err = err; }
 }
 
-__global__ void k_find_seed(int32_t *q_lin, int32_t *q_par, int lin, FindState *st) {
+__global__ void k_find_seed(int32_t *q_lin, int32_t *q_par, int lin, unsigned long long *slots, FindState *st) {
     q_lin[0] = lin;
     q_par[0] = 0;
-    st->fs = 0; st->fe = 1; st->depth = 0; st->err = 0; st->done = 0;
+    for (int i = 0; i < 2 * FIND_MAX_CTAS; ++i) slots[i] = 0;
+    st->n = 0; st->depth = 0; st->err = 0;
 }
 
 // cuencas.f90:592-607 : basin_f(:,i) = (drain id, col, row) of queue position n-i+1
@@ -756,24 +787,28 @@ int wmf_basin_find(wmf_ctx *ctx, float x, float y, const int32_t *dir, int32_t n
     const int32_t *d_dir;
     WMF_TRY(sc.in(dir, (size_t)celTot, &d_dir));
     FindState *st;
+    unsigned long long *slots;
     WMF_TRY(sc.alloc((void **)&st, sizeof(FindState)));
+    WMF_TRY(sc.alloc(&slots, (size_t)2 * FIND_MAX_CTAS));
     const int lin0 = (fili - 1) * nc + (coli - 1);
-    LAUNCH(ctx, k_find_seed, 1, 1, 0, ctx->q_lin, ctx->q_par, lin0, st);
+    LAUNCH(ctx, k_find_seed, 1, 1, 0, ctx->q_lin, ctx->q_par, lin0, slots, st);
     int occ = 0;
-    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_basin_find, FIND_THREADS, 0));
+    CU_TRY(ctx, cudaFuncSetAttribute(k_basin_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIND_SMEM));
+    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_basin_find, FIND_THREADS, FIND_SMEM));
     if (occ < 1) WMF_FAIL(ctx, WMF_ERR_CUDA, "basin_find kernel does not fit on an SM");
-    int nb = ctx->num_sms;  // one CTA per SM: fewer barrier participants, full memory parallelism
-    if (nb > 1024) nb = 1024;
+    int nb = std::min(ctx->num_sms, 32);  // co-resident CTAs (the exchange spins); 32 measured best: fewer pollers
+    if (nb > FIND_MAX_CTAS) nb = FIND_MAX_CTAS;
+    if (const char *e = getenv("WMF_FIND_CTAS")) nb = std::max(1, std::min(std::min(ctx->num_sms, FIND_MAX_CTAS), atoi(e)));
     long long cap = celTot;
     void *args[] = {(void *)&d_dir, (void *)&nc, (void *)&nr, (void *)&ctx->q_lin, (void *)&ctx->q_par, (void *)&cap,
-                    (void *)&st};
-    CU_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_basin_find, dim3(nb), dim3(FIND_THREADS), args, 0, ctx->stream));
+                    (void *)&slots, (void *)&st};
+    CU_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_basin_find, dim3(nb), dim3(FIND_THREADS), args, FIND_SMEM, ctx->stream));
     ctx->launches++;
     FindState h;
-    CU_TRY(ctx, cudaMemcpyAsync(&h, st, sizeof(long long) * 2 + sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(&h, st, sizeof(FindState), cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (h.err) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "basin_find: BFS queue overflow -- the DIR map is cyclic");
-    ctx->find_n = (int32_t)h.fe;
+    ctx->find_n = (int32_t)h.n;
     ctx->find_depth = h.depth;
     *nceldas = ctx->find_n;
     return WMF_OK;
