@@ -1280,53 +1280,98 @@ static int read_flag(wmf_ctx *ctx, const int *d, int *h) {
     return WMF_OK;
 }
 
-// Host -> device streaming of the rain table.  Pinned (or registered) host memory: chunks of whole records are copied on
-// the context's copy stream, each followed by an event; the compute stream waits only for the chunks a wave needs.
+// Host -> device streaming of the rain table next to the running wavefront.
+// The skewed sweep reads the table along anti-diagonals: cell (level L) needs the record of step t at wave
+// t/K + (Lmax - L), so the far-upstream cells want the last records long before the outlet wants the first ones.
+// The table [record][cell] is therefore cut into tiles (record group x level-contiguous cell group), the tiles are
+// copied in order of first use on the context's copy stream (2-D copies from pinned memory), and the compute stream
+// waits, wave by wave, only for the tiles that wave can touch.  Records no step refers to are never copied.
 // Pageable host memory cannot be copied asynchronously, and device memory needs no copy: both take the plain path.
 struct RainStream {
+    struct Tile { int w_first, r0, r1, c0, c1; };
     wmf_ctx *owner = nullptr;
-    int recs_per_chunk = 0, n_chunks = 0, waited = 0;
+    std::vector<Tile> tiles;
+    const int32_t *host = nullptr;
+    int32_t *dev = nullptr;
+    int n_records = 0, N = 0, waited = 0;
     bool active = false;
     ~RainStream() {  // an early error return must not free the buffer under a copy still in flight
-        if (active && waited < n_chunks && owner && owner->copy_stream) cudaStreamSynchronize(owner->copy_stream);
+        if (active && waited < (int)tiles.size() && owner && owner->copy_stream) cudaStreamSynchronize(owner->copy_stream);
     }
-    int begin(wmf_ctx *ctx, Scope &sc, const int32_t *rain, int n_records, int N, const int32_t **dev) {
+    int begin(wmf_ctx *ctx, Scope &sc, const int32_t *rain, int n_rec, int n, const int32_t **out) {
         cudaPointerAttributes a;
         bool pinned = false;
         if (cudaPointerGetAttributes(&a, rain) == cudaSuccess) pinned = (a.type == cudaMemoryTypeHost);
         else cudaGetLastError();
-        const size_t total = (size_t)n_records * N;
-        if (!pinned || total * 4 < (32u << 20)) return sc.in(rain, total, dev);
-        int32_t *d;
-        WMF_TRY(sc.alloc(&d, total));
+        const size_t total = (size_t)n_rec * n;
+        if (!pinned || total * 4 < (32u << 20)) return sc.in(rain, total, out);
+        WMF_TRY(sc.alloc(&dev, total));
         if (!ctx->copy_stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        // the allocation is ordered on the compute stream: the copy stream must not start before it
-        CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-        CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev0, 0));
-        recs_per_chunk = std::max(1, (int)((48u << 20) / ((size_t)N * 4)));
-        n_chunks = (n_records + recs_per_chunk - 1) / recs_per_chunk;
-        while ((int)ctx->copy_events.size() < n_chunks) {
+        host = rain; n_records = n_rec; N = n; owner = ctx; active = true;
+        *out = dev;
+        return WMF_OK;
+    }
+    // h_first[L] = first cell of level L (cells are ordered by decreasing level), pos[t] = 1-based record of step t
+    int schedule(wmf_ctx *ctx, const std::vector<int32_t> &h_first, int Lmax, const std::vector<int32_t> &pos, int K) {
+        if (!active) return WMF_OK;
+        const int T = (int)pos.size();
+        std::vector<int> tmin((size_t)n_records, INT_MAX);
+        for (int t = T - 1; t >= 0; --t) tmin[pos[t] - 1] = t;
+        // record groups x cell groups (on level boundaries)
+        int n_rg = 12, n_cg = 12;  // measured best on C2 (tools/e2e_probe.py): 12x12 47.4 ms, 24x24 48.7, by record only 68.9
+        if (const char *e = getenv("WMF_RAIN_TILES")) sscanf(e, "%d,%d", &n_rg, &n_cg);
+        n_rg = std::max(1, n_rg); n_cg = std::max(1, n_cg);
+        const int rg = std::max(1, (n_records + n_rg - 1) / n_rg);
+        std::vector<int> cb{0};
+        {
+            const int target = std::max(1, N / n_cg);
+            for (int L = Lmax - 1; L >= 0; --L)
+                if (h_first[L] - cb.back() >= target) cb.push_back(h_first[L]);
+            if (cb.back() != N) cb.push_back(N);
+        }
+        // level of the first (deepest) cell of a group: levels decrease with the cell index
+        auto level_of_cell = [&](int cell) {
+            int lo = 0, hi = Lmax;  // largest L with h_first[L] <= cell  (h_first is decreasing in L)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (h_first[mid] <= cell) hi = mid; else lo = mid + 1;
+            }
+            return lo;
+        };
+        for (int r0 = 0; r0 < n_records; r0 += rg) {
+            const int r1 = std::min(n_records, r0 + rg);
+            int tm = INT_MAX;
+            for (int r = r0; r < r1; ++r) tm = std::min(tm, tmin[r]);
+            if (tm == INT_MAX) continue;  // nobody reads these records
+            for (size_t g = 0; g + 1 < cb.size(); ++g)
+                tiles.push_back({tm / K + (Lmax - level_of_cell(cb[g])), r0, r1, cb[g], cb[g + 1]});
+        }
+        std::stable_sort(tiles.begin(), tiles.end(), [](const Tile &x, const Tile &y) { return x.w_first < y.w_first; });
+        while (ctx->copy_events.size() < tiles.size()) {
             cudaEvent_t e;
             CU_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             ctx->copy_events.push_back(e);
         }
-        for (int c = 0; c < n_chunks; ++c) {
-            const size_t r0 = (size_t)c * recs_per_chunk, r1 = std::min((size_t)n_records, r0 + recs_per_chunk);
-            CU_TRY(ctx, cudaMemcpyAsync(d + r0 * N, rain + r0 * N, (r1 - r0) * N * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-            CU_TRY(ctx, cudaEventRecord(ctx->copy_events[c], ctx->copy_stream));
+        // the allocation is ordered on the compute stream: the copy stream must not start before it
+        CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev1, 0));
+        for (size_t i = 0; i < tiles.size(); ++i) {
+            const Tile &t = tiles[i];
+            const size_t o = (size_t)t.r0 * N + t.c0;
+            CU_TRY(ctx, cudaMemcpy2DAsync(dev + o, (size_t)N * 4, host + o, (size_t)N * 4, (size_t)(t.c1 - t.c0) * 4,
+                                          (size_t)(t.r1 - t.r0), cudaMemcpyHostToDevice, ctx->copy_stream));
+            CU_TRY(ctx, cudaEventRecord(ctx->copy_events[i], ctx->copy_stream));
         }
-        active = true;
-        owner = ctx;
-        *dev = d;
         return WMF_OK;
     }
-    // make the compute stream wait until records 1..rec (1-based) are on the device
-    int wait_records(wmf_ctx *ctx, int rec) {
+    // make the compute stream wait for every tile wave `w` (or an earlier one) can read
+    int wait_wave(wmf_ctx *ctx, int w) {
         if (!active) return WMF_OK;
-        const int need = std::min(n_chunks, (rec + recs_per_chunk - 1) / recs_per_chunk);
-        while (waited < need) CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_events[waited++], 0));
+        while (waited < (int)tiles.size() && tiles[waited].w_first <= w)
+            CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_events[waited++], 0));
         return WMF_OK;
     }
+    int wait_all(wmf_ctx *ctx) { return wait_wave(ctx, INT_MAX); }
 };
 
 template <bool SED, bool SLIDES>
@@ -1659,16 +1704,14 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     auto level_end = [&](int L) { return L == 0 ? N : h_first[L - 1]; };
     const int n_waves = (KT ? P.nb : T) + Lmax;
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    // need_rec[t] = highest rain record any step <= t reads
-    std::vector<int32_t> need_rec((size_t)T);
-    for (int t = 0, mx = 1; t < T; ++t) { mx = std::max(mx, h_pos[t]); need_rec[t] = mx; }
+    WMF_TRY(rs.schedule(ctx, h_first, Lmax, h_pos, KT ? KT : 1));
     if (KT) {
         const int nb = P.nb;
         for (int w = 0; w < n_waves; ++w) {
             const int Lhi = std::min(Lmax, Lmax - w + nb - 1), Llo = std::max(0, Lmax - w);
             const int lo = h_first[Lhi], hi = level_end(Llo);
             if (hi <= lo) continue;
-            WMF_TRY(rs.wait_records(ctx, need_rec[std::min((long long)T - 1, ((long long)std::min(w, nb - 1) + 1) * KT - 1)]));
+            WMF_TRY(rs.wait_wave(ctx, w));
             const int hlo = h_hfirst[Lhi], hhi = (Llo == 0) ? (int)n_hill : h_hfirst[Llo - 1];
             const int clo = lo - hlo, chi = hi - hhi;
             switch (KT) {
@@ -1685,7 +1728,7 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
             const int Lhi = std::min(Lmax, Lmax - w + T - 1), Llo = std::max(0, Lmax - w);
             const int lo = h_first[Lhi], hi = level_end(Llo);
             if (hi <= lo) continue;
-            WMF_TRY(rs.wait_records(ctx, need_rec[std::min(w, T - 1)]));
+            WMF_TRY(rs.wait_wave(ctx, w));
             if (sed && slides) launch_wave<true, true>(ctx, P, w, lo, hi);
             else if (sed) launch_wave<true, false>(ctx, P, w, lo, hi);
             else if (slides) launch_wave<false, true>(ctx, P, w, lo, hi);
@@ -1694,7 +1737,7 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     }
     CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     CU_TRY(ctx, cudaGetLastError());
-    WMF_TRY(rs.wait_records(ctx, in->n_records));
+    WMF_TRY(rs.wait_all(ctx));
     // rain statistics that do not depend on the model state
     if (per_run) {
         dim3 rg((unsigned)std::min(grid_for(N, 256), 64), (unsigned)in->n_records);
