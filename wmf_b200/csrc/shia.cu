@@ -682,6 +682,8 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
         b = w - (P.Lmax - (int)(tw >> 8));
         active = (b >= 0) && (b < P.nb);
     }
+    // programmatic dependent launch: let the next wave's CTAs be scheduled now (they stop at their own wait below)
+    asm volatile("griddepcontrol.launch_dependents;");
     const int t0 = b * K;
     const int nt = active ? min(K, P.T - t0) : 0;
     const float dt = P.dt;
@@ -707,26 +709,22 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
         if (P.retorno_aq > 0.0f) H3 = __ldg(P.max_aquifer + cell) * __ldg(cal + 10);
         Lh = __ldg(P.hill_long + cell);
         m3 = __ldg(P.elem_area + cell) / 1000.0f;
-        const float4 s = P.st4[base];
-        S0 = s.x; S1 = s.y; S2 = s.z; S3 = s.w;
-        S4 = P.s5[base];
         float4 he = make_float4(0.f, 0.f, 0.f, 0.f);
         if (KIN || CHAN) he = __ldg(reinterpret_cast<const float4 *>(P.h_exp) + cell);
         const float hcoef[3] = {hc.x, hc.y, hc.z}, hexp[3] = {he.x, he.y, he.z};
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             if (!KIN || P.st[k] == 1) {
-                const float v = P.hs_state ? P.hsp[k * NM + base] : hcoef[k] * __ldg(cal + 4 + k);
-                kv[k] = v;
-                fl[k] = 1.0f - Lh / (v * dt + Lh);
+                if (!P.hs_state) {
+                    kv[k] = hcoef[k] * __ldg(cal + 4 + k);
+                    fl[k] = 1.0f - Lh / (kv[k] * dt + Lh);
+                }
             } else {
-                kv[k] = P.hsp[k * NM + base];
                 kc[k] = hcoef[k] * __ldg(cal + 4 + k);
                 ke[k] = hexp[k];
             }
         }
         if (CHAN) {
-            vch = P.hsp[3 * NM + base];
             ccoef = hc.w * __ldg(cal + 7);
             cexpo = he.w;
             Ls = __ldg(P.stream_long + cell);
@@ -740,6 +738,25 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             rowh = find_row(P.ctrlh_cells, P.n_ctrlh, cell);
             if (rowh >= P.n_conth) rowh = -1;
         }
+    }
+    // everything above reads run constants only; what follows was written by the previous wave
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (active) {
+        const float4 s = P.st4[base];
+        S0 = s.x; S1 = s.y; S2 = s.z; S3 = s.w;
+        S4 = P.s5[base];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (!KIN || P.st[k] == 1) {
+                if (P.hs_state) {
+                    kv[k] = P.hsp[k * NM + base];
+                    fl[k] = 1.0f - Lh / (kv[k] * dt + Lh);
+                }
+            } else {
+                kv[k] = P.hsp[k * NM + base];
+            }
+        }
+        if (CHAN) vch = P.hsp[3 * NM + base];
         if (P.retorned) ret_acc = P.retorned[cell];
     }
     const bool outlet = active && (cell == N - 1);
@@ -1383,7 +1400,7 @@ static void launch_wave(wmf_ctx *ctx, const ShiaP &P, int w, int lo, int hi) {
 }
 
 template <int K>
-static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int hlo, int hhi) {
+static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int hlo, int hhi, bool pdl) {
     constexpr int WPB = TB_THREADS / 32;
     const int wc = (int)(((long long)(chi - clo) * P.M + 31) / 32), wh = (int)(((long long)(hhi - hlo) * P.M + 31) / 32);
     if (wc + wh == 0) return;
@@ -1396,10 +1413,21 @@ static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int
             if (nblk == 0 || nb < nblk) { nblk = nb; cpb = c; }
         }
     }
+    // programmatic dependent launch: the CTAs of this wave may start while the previous wave drains; they run their
+    // constant-only prologue and block in griddepcontrol.wait until the previous wave has completed
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)nblk);
+    cfg.blockDim = dim3(TB_THREADS);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
     if (P.st[0] == 2 || P.st[1] == 2 || P.st[2] == 2)
-        k_shia_tb<K, true><<<nblk, TB_THREADS, 0, ctx->stream>>>(P, w, clo, chi, hlo, hhi, cpb, wc, wh);
+        cudaLaunchKernelEx(&cfg, k_shia_tb<K, true>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
     else
-        k_shia_tb<K, false><<<nblk, TB_THREADS, 0, ctx->stream>>>(P, w, clo, chi, hlo, hhi, cpb, wc, wh);
+        cudaLaunchKernelEx(&cfg, k_shia_tb<K, false>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
     ctx->launches++;
 }
 
@@ -1707,6 +1735,8 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     WMF_TRY(rs.schedule(ctx, h_first, Lmax, h_pos, KT ? KT : 1));
     if (KT) {
         const int nb = P.nb;
+        bool launched_any = false, use_pdl = true;
+        if (const char *e = getenv("WMF_SHIA_PDL")) use_pdl = atoi(e) != 0;
         for (int w = 0; w < n_waves; ++w) {
             const int Lhi = std::min(Lmax, Lmax - w + nb - 1), Llo = std::max(0, Lmax - w);
             const int lo = h_first[Lhi], hi = level_end(Llo);
@@ -1714,13 +1744,15 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
             WMF_TRY(rs.wait_wave(ctx, w));
             const int hlo = h_hfirst[Lhi], hhi = (Llo == 0) ? (int)n_hill : h_hfirst[Llo - 1];
             const int clo = lo - hlo, chi = hi - hhi;
+            const bool pdl = use_pdl && launched_any;  // the first wave follows memsets and plan kernels: plain launch
+            launched_any = true;
             switch (KT) {
-                case 1: launch_tb<1>(ctx, P, w, clo, chi, hlo, hhi); break;
-                case 2: launch_tb<2>(ctx, P, w, clo, chi, hlo, hhi); break;
-                case 4: launch_tb<4>(ctx, P, w, clo, chi, hlo, hhi); break;
-                case 8: launch_tb<8>(ctx, P, w, clo, chi, hlo, hhi); break;
-                case 16: launch_tb<16>(ctx, P, w, clo, chi, hlo, hhi); break;
-                default: launch_tb<32>(ctx, P, w, clo, chi, hlo, hhi); break;
+                case 1: launch_tb<1>(ctx, P, w, clo, chi, hlo, hhi, pdl); break;
+                case 2: launch_tb<2>(ctx, P, w, clo, chi, hlo, hhi, pdl); break;
+                case 4: launch_tb<4>(ctx, P, w, clo, chi, hlo, hhi, pdl); break;
+                case 8: launch_tb<8>(ctx, P, w, clo, chi, hlo, hhi, pdl); break;
+                case 16: launch_tb<16>(ctx, P, w, clo, chi, hlo, hhi, pdl); break;
+                default: launch_tb<32>(ctx, P, w, clo, chi, hlo, hhi, pdl); break;
             }
         }
     } else {
