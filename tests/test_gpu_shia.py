@@ -241,3 +241,53 @@ def test_ensemble_matches_single_runs():
         qp = (s_o[mo] - s_s[ms]) / s_o[mo] * 100
         assert scores[k, 0] == pytest.approx(nash, rel=1e-5, abs=1e-6)
         assert scores[k, 1] == pytest.approx(qp, rel=1e-5, abs=1e-4)
+
+
+def test_streamed_rain_and_pdl_are_bit_identical(monkeypatch):
+    """The pinned-memory rain streaming (tiles copied next to the running wavefront) and programmatic dependent launch
+    change scheduling only: results must equal the plain path bit for bit."""
+    import torch
+    from wmf_b200 import ModelsModule, synth
+    bs, inp = build("G2", 100, 80, 21, n_reg=90)
+    _, plain = run_gpu(inp)
+    pin = torch.from_numpy(np.ascontiguousarray(inp["rain"])).pin_memory()
+    monkeypatch.setenv("WMF_RAIN_STREAM_MIN_MB", "0")
+    monkeypatch.setenv("WMF_RAIN_TILES", "5,4")
+    m = ModelsModule()
+    synth.apply_to_models(m, inp)
+    m.set_rain(pin.numpy(), inp["pos_evento"])
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    ret = m.shia_v1(None, None, inp["calib"], n_cont, 1, inp["n_reg"], None, None, inp["nceldas"])
+    for k in (0, 6, 9):
+        np.testing.assert_array_equal(ret[k], plain[k])
+    monkeypatch.setenv("WMF_SHIA_PDL", "0")
+    ret2 = m.shia_v1(None, None, inp["calib"], n_cont, 1, inp["n_reg"], None, None, inp["nceldas"])
+    for k in (0, 6, 9):
+        np.testing.assert_array_equal(ret2[k], plain[k])
+    monkeypatch.setenv("WMF_SHIA_K", "0")          # the one-step-per-launch kernel streams too
+    ret3 = m.shia_v1(None, None, inp["calib"], n_cont, 1, inp["n_reg"], None, None, inp["nceldas"])
+    close(ret3[0], plain[0], name="Q one-step kernel")
+
+
+def test_evaluate_population_single_gpu():
+    """wmf_b200.ensemble on one GPU (no process group): batched members + device scores == per-member numpy scores."""
+    from wmf_b200 import ModelsModule, synth
+    from wmf_b200.ensemble import evaluate_population
+    bs, inp = build("G2", 72, 60, 22, n_reg=50)
+    calibs = synth.make_ensemble_calibs(10, seed=3)
+    m = ModelsModule()
+    synth.apply_to_models(m, inp)
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    one = dict(inp); one["calib"] = calibs[4]
+    _, ret = run_gpu(one)
+    qobs = ret[0][0].copy()
+    sc = evaluate_population(m, calibs, qobs, n_cont, inp["n_reg"], inp["rain"], inp["pos_evento"], row=0,
+                             members_per_launch=4).cpu().numpy()
+    assert sc.shape == (10, 2)
+    assert sc[4, 0] == pytest.approx(1.0, abs=1e-6) and abs(sc[4, 1]) < 1e-4      # the member that made qobs
+    for k in (0, 9):
+        o = dict(inp); o["calib"] = calibs[k]
+        _, r = run_gpu(o)
+        s_o, s_s = qobs.astype(np.float64), r[0][0].astype(np.float64)
+        nash = 1 - ((s_o - s_s) ** 2).sum() / ((s_o - s_o.mean()) ** 2).sum()
+        assert sc[k, 0] == pytest.approx(nash, rel=1e-5, abs=1e-6)

@@ -769,27 +769,38 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
         if (tt < nt) {
             const int t = t0 + tt;
             const float So0 = S0, So1 = S1, So2 = S2, So3 = S3, So4 = S4;
-            // what the upstream neighbours sent this step, in ascending cell order (:601,:617,:672)
-            {
-                const float4 *ob = ob_in + (size_t)tt * NM;
-#pragma unroll 1
-                for (int c = 0; c < nch; ++c, ob += M) {
-                    const float4 o = *ob;
-                    S1 = S1 + o.x;
-                    S2 = S2 + o.y;
-                    S3 = S3 + o.z;
-                    S4 = S4 + o.w;
-                }
-            }
+            // Loads first: the outflow of the first two upstream neighbours and this step's rain are requested before
+            // the surface-tank update (which needs only the rain) so that their latency hides behind its pow chain.
+            const float4 *ob = ob_in + (size_t)tt * NM;
+            float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), obb = oa;
+            if (nch > 0) oa = ob[0];
+            if (nch > 1) obb = ob[M];
             // rain (:444-449)
             const int p = __ldg(P.pos + t);
             float R = 0.0f;
             if (p != 1) R = div_by_1000((float)__ldg(P.rain + (size_t)(p - 1) * N + cell));
-            // vertical cascade (:478-512)
+            // vertical cascade, surface tank (:478-486)
             const float vf1 = fmaxf(0.0f, R - H1 + S0);
             S0 = S0 + R - vf1;
             const float E = fminf(__ldg(P.evp + t) * vs1 * wmf_powf(S0 / H1, 0.6f), S0);
             S0 = S0 - E;
+            // what the upstream neighbours sent this step, added in ascending cell order (:601,:617,:672) -- the
+            // reference's children deposit into StoOut(2:5) before the cell itself is processed
+            if (nch > 0) {
+                S1 = S1 + oa.x; S2 = S2 + oa.y; S3 = S3 + oa.z; S4 = S4 + oa.w;
+                if (nch > 1) {
+                    S1 = S1 + obb.x; S2 = S2 + obb.y; S3 = S3 + obb.z; S4 = S4 + obb.w;
+                    ob += 2 * (size_t)M;
+#pragma unroll 1
+                    for (int c = 2; c < nch; ++c, ob += M) {
+                        const float4 o = *ob;
+                        S1 = S1 + o.x;
+                        S2 = S2 + o.y;
+                        S3 = S3 + o.z;
+                        S4 = S4 + o.w;
+                    }
+                }
+            }
             const float vf2 = fminf(vf1, vs2);
             S1 = S1 + vf1 - vf2;
             const float vf3 = fminf(vf2, vs3);
@@ -1106,11 +1117,22 @@ __global__ void k_state_final(const ShiaP P, float *__restrict__ stoout, float *
 }
 
 // per-record basin total of the rain field in mm (fp64), used for Mean_Rain (:797) and `entradas` (:469)
-__global__ void k_rain_record_sum(const int32_t *__restrict__ rain, int n, double *__restrict__ recsum) {
+__global__ void __launch_bounds__(256) k_rain_record_sum(const int32_t *__restrict__ rain, int n, double *__restrict__ recsum) {
     const int r = blockIdx.y;
     const int32_t *rec = rain + (size_t)r * n;
     double s = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    // 128-bit loads where the record is 16-byte aligned (n % 4 == 0 or r == 0), scalar tail / fallback otherwise
+    const bool vec = ((((size_t)r * n) & 3) == 0) && ((reinterpret_cast<uintptr_t>(rain) & 15) == 0);
+    const int n4 = vec ? (n >> 2) : 0;
+    const int4 *rec4 = reinterpret_cast<const int4 *>(rec);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const int4 v = __ldg(rec4 + i);
+        s += (double)((float)v.x / 1000.0f);
+        s += (double)((float)v.y / 1000.0f);
+        s += (double)((float)v.z / 1000.0f);
+        s += (double)((float)v.w / 1000.0f);
+    }
+    for (int i = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         s += (double)((float)rec[i] / 1000.0f);
     s = warp_sum_d(s);
     if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(recsum + r, s);
@@ -1321,7 +1343,9 @@ struct RainStream {
         if (cudaPointerGetAttributes(&a, rain) == cudaSuccess) pinned = (a.type == cudaMemoryTypeHost);
         else cudaGetLastError();
         const size_t total = (size_t)n_rec * n;
-        if (!pinned || total * 4 < (32u << 20)) return sc.in(rain, total, out);
+        size_t min_bytes = 32u << 20;  // below this a single copy costs less than the tile bookkeeping
+        if (const char *e = getenv("WMF_RAIN_STREAM_MIN_MB")) min_bytes = (size_t)atol(e) << 20;
+        if (!pinned || total * 4 < min_bytes) return sc.in(rain, total, out);
         WMF_TRY(sc.alloc(&dev, total));
         if (!ctx->copy_stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         host = rain; n_records = n_rec; N = n; owner = ctx; active = true;
@@ -1772,7 +1796,7 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     WMF_TRY(rs.wait_all(ctx));
     // rain statistics that do not depend on the model state
     if (per_run) {
-        dim3 rg((unsigned)std::min(grid_for(N, 256), 64), (unsigned)in->n_records);
+        dim3 rg((unsigned)std::min(grid_for(N, 1024), 128), (unsigned)in->n_records);
         LAUNCH(ctx, k_rain_record_sum, rg, 256, 0, P.rain, N, d_recsum);
         if (d_acum_rain) LAUNCH(ctx, k_acum_rain, G, B, 0, P.rain, P.pos, N, T, d_acum_rain);
     }

@@ -70,7 +70,8 @@ WMF_HD float wmf_exp2_hl(float hi, float lo) {
 
 // x**y.  Fast path for 2^-126 <= x < inf and |y * log2(x)| < 125; everything else is powf's business.
 WMF_HD float wmf_powf(float x, float y) {
-    if (!(x >= 1.17549435e-38f && x < 3.0e38f)) return powf(x, y);
+    // positive, normal and finite: one unsigned compare on the bit pattern (0x00800000 <= bits < 0x7f800000)
+    if ((unsigned)(WMF_F2I(x) - 0x00800000) >= 0x7f000000u) return powf(x, y);
     float a, l;
     wmf_log2_hl(x, &a, &l);
     const float ph = y * a;
