@@ -15,6 +15,15 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5
 
 
+@pytest.fixture(autouse=True, params=["auto", "4"])
+def time_block(request, monkeypatch):
+    """Every test runs twice: with the library's own choice of steps per time block (1 for basins this small) and with
+    the K = 4 blocks the C2-sized runs use."""
+    if request.param != "auto":
+        monkeypatch.setenv("WMF_SHIA_K", request.param)
+    return request.param
+
+
 def close(got, ref, rtol=RTOL, afloor=1e-7, name=""):
     """|got-ref| <= rtol*|ref| + afloor*max|ref|.  The absolute floor is one fp32 epsilon of the largest value of
     the field: residues of the cancellations the model itself performs (e.g. Qskr - qsSUStot) sit below it."""
@@ -291,3 +300,23 @@ def test_evaluate_population_single_gpu():
         s_o, s_s = qobs.astype(np.float64), r[0][0].astype(np.float64)
         nash = 1 - ((s_o - s_s) ** 2).sum() / ((s_o - s_o.mean()) ** 2).sum()
         assert sc[k, 0] == pytest.approx(nash, rel=1e-5, abs=1e-6)
+
+
+def test_sediment_slide_kernels_agree(monkeypatch):
+    """SED + slides through the time-blocked kernel (K=4) and through the one-step-per-launch kernel: same per-cell fp32
+    operations in the same order, so every per-cell result is identical; only the global fp64 totals (atomics) may differ
+    in the last bits."""
+    bs, inp = build("G2", 130, 100, 23, n_reg=75, speed_type=(2, 2, 1), sediments=True, slides=True, retorno_gr=1,
+                    rain_peak_mm=60.0)
+    inp["sl_gullienogullie"] = 1
+    m1, r1 = run_gpu(inp)
+    monkeypatch.setenv("WMF_SHIA_K", "0")
+    m0, r0 = run_gpu(inp)
+    for k in (0, 1, 3, 9):
+        np.testing.assert_array_equal(r1[k], r0[k])
+    for k in ("vs", "vd", "vsc", "vdc", "volero", "voldepo", "sl_slideocurrence", "sl_slideacumulate", "sl_slidencelltime",
+              "retorned"):
+        np.testing.assert_array_equal(getattr(m1, k), getattr(m0, k))
+    close(m1.erot, m0.erot, rtol=1e-6, name="EROt")
+    close(m1.dept, m0.dept, rtol=1e-6, name="DEPt")
+    assert r1[1].max() > 0 and m1.sl_slidencelltime.sum() > 0

@@ -86,6 +86,7 @@ struct ShiaP {
     float *s5;              // [N][M] tank 5
     float4 *outb4;          // [2][K][N][M] what a cell sends downstream at each step of its time block
     int bal_direct;         // red[t][RQ_SAL] holds sum(dS + outputs), balance = that - inputs
+    float4 *sedout4;        // [2][K][3][N][M] sediment a cell sends downstream: sus(3) bm(3) ero(3) chan(3)
 };
 
 __device__ __forceinline__ size_t sidx(const ShiaP &P, int k, int cell, int m) {
@@ -665,7 +666,7 @@ constexpr int TB_THREADS = 256;
 #define TB_MIN_BLOCKS 4
 #endif
 
-template <int K, bool CHAN, bool KIN>
+template <int K, bool CHAN, bool KIN, bool SED, bool SLIDES>
 __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int jlo, const int jhi, const int tile,
                                         float *__restrict__ s_acc) {
     const int N = P.N, M = P.M;
@@ -705,7 +706,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
         vs1 = vc.x * __ldg(cal + 0) * dt; vs2 = vc.y * __ldg(cal + 1) * dt;
         vs3 = vc.z * __ldg(cal + 2) * dt; vs4 = vc.w * __ldg(cal + 3) * dt;
         H1 = __ldg(P.max_capilar + cell) * __ldg(cal + 8);
-        if (P.retorno_gr > 0.0f) H2 = __ldg(P.max_gravita + cell) * __ldg(cal + 9);
+        if (P.retorno_gr > 0.0f || SLIDES) H2 = __ldg(P.max_gravita + cell) * __ldg(cal + 9);
         if (P.retorno_aq > 0.0f) H3 = __ldg(P.max_aquifer + cell) * __ldg(cal + 10);
         Lh = __ldg(P.hill_long + cell);
         m3 = __ldg(P.elem_area + cell) / 1000.0f;
@@ -759,6 +760,30 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
         if (CHAN) vch = P.hsp[3 * NM + base];
         if (P.retorned) ret_acc = P.retorned[cell];
     }
+    // sediments (:1298-1608): the four 3-fraction stores and the two volume maps ride in registers for the block
+    SedLocal SL;
+    float vdep = 0.f, vero = 0.f;
+    double ero_acc[3] = {0.0, 0.0, 0.0}, dep_acc[3] = {0.0, 0.0, 0.0};
+    if (SED && active) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            SL.Vs[k] = P.sed[(0 + k) * NM + base];
+            SL.Vd[k] = P.sed[(3 + k) * NM + base];
+            SL.Vsc[k] = P.sed[(6 + k) * NM + base];
+            SL.Vdc[k] = P.sed[(9 + k) * NM + base];
+        }
+        vdep = P.voldepo[base];
+        vero = P.volero[base];
+    }
+    // slides (:1649-1707): own failure flag and the step at which an upstream failure reached this cell.  Every mark
+    // with a step of this block or earlier was made by a wave before this one, so one read per block is enough.
+    int sl_slid = 0, sl_mark = INT_MAX;
+    bool sl_risky = false;
+    if (SLIDES && active) {
+        sl_risky = __ldg(P.sl_risk + cell) == 2.0f;
+        sl_slid = P.sl_slid[cell];
+        sl_mark = P.sl_marktime[cell];
+    }
     const bool outlet = active && (cell == N - 1);
     const float4 *ob_in = P.outb4 + (size_t)(b & 1) * K * NM + (size_t)c0 * M + m;
     float4 *ob_out = P.outb4 + (size_t)(b & 1) * K * NM + base;
@@ -801,6 +826,26 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                     }
                 }
             }
+            if (SED) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k) SL.up[k] = 0.f;
+                SL.ero_add[0] = SL.ero_add[1] = SL.ero_add[2] = 0.f;
+                SL.dep_add[0] = SL.dep_add[1] = SL.dep_add[2] = 0.f;
+                SL.volero_add = SL.voldepo_add = 0.f;
+                const float4 *so = P.sedout4 + ((size_t)(b & 1) * K + tt) * 3 * NM + (size_t)c0 * M + m;
+#pragma unroll 1
+                for (int c = 0; c < nch; ++c, so += M) {
+                    const float4 f0 = so[0], f1 = so[NM], f2 = so[2 * NM];
+                    const float u[12] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w};
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        SL.Vs[i] = SL.Vs[i] + u[0 + i];
+                        SL.Vs[i] = SL.Vs[i] + u[3 + i];
+                        SL.Vs[i] = SL.Vs[i] + u[6 + i];
+                        SL.Vsc[i] = SL.Vsc[i] + u[9 + i];
+                    }
+                }
+            }
             const float vf2 = fminf(vf1, vs2);
             S1 = S1 + vf1 - vf2;
             const float vf3 = fminf(vf2, vs3);
@@ -830,6 +875,10 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                     } else {
                         const float sec = calc_speed_dev(Sk[k] * m3, kc[k], ke[k], Lh, kv[k], dt, P.niter);
                         hk[k] = fminf(sec * kv[k] * dt / m3, Sk[k]);
+                        if (SED && k == 0) {  // the reference calls sed_hillslope from inside the kinematic case only (:569-575)
+                            const float qlin = hk[0] * m3 / (dt * P.dxp);
+                            sed_hillslope_dev(P, SL, P.sed_factor, kv[0], Sk[0], __ldg(P.hill_slope + cell), qlin, cell, type);
+                        }
                     }
                     Sk[k] = Sk[k] - hk[k];
                 }
@@ -847,10 +896,31 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                     sal = sal + s3;
                 }
                 if (rowq >= 0 && P.q) P.q[qoff + rowq] = 0.0f;
+                if (SED && P.st[0] == 2) {  // hillslope cell: single VolDEPo / VolERO increment (:1426-1427)
+                    vdep = vdep + SL.voldepo_add;
+                    vero = vero + SL.volero_add;
+                }
             } else {
                 S4 = S4 + (h0 + h1) + h2 * (float)(type - 2);
                 const float sec_area = calc_speed_dev(S4 * m3, ccoef, cexpo, Ls, vch, dt, P.niter);
                 const float h3 = fminf(sec_area * vch * dt / m3, S4);
+                float Vsal[3] = {0.f, 0.f, 0.f};
+                if (SED) {
+                    float vd2 = 0.f;
+                    sed_channel_dev(P, SL, S4, vch, h3 * m3 / dt, __ldg(P.stream_slope + cell), sec_area, Vsal, &vd2);
+                    // VolDEPo(celda) is incremented twice in a step for a channel cell (:1427 then :1607)
+                    vdep = vdep + SL.voldepo_add;
+                    vdep = vdep + vd2;
+                    vero = vero + SL.volero_add;
+                    if (P.qsed) {
+                        if (outlet)
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) P.qsed[(((size_t)m * P.T + t) * 3 + i) * P.n_cont] = Vsal[i];
+                        if (rowq >= 0)
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) P.qsed[(((size_t)m * P.T + t) * 3 + i) * P.n_cont + rowq] = Vsal[i];
+                    }
+                }
                 S4 = S4 - h3;
                 o = make_float4(0.0f, 0.0f, h2 * (float)(3 - type), h3);
                 if (outlet) {
@@ -875,6 +945,49 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                 if (P.st1o) P.st1o[k] = S0;
                 if (P.st3o) P.st3o[k] = S2;
             }
+            if (SLIDES && sl_risky && sl_slid == 0 && sl_mark > t) {  // slide_ocurrence (:1649-1682)
+                const float zs = __ldg(P.sl_zs + cell);
+                const float Zw = (S2 * zs) / H2;
+                bool fail = false;
+                if (Zw >= __ldg(P.sl_zcrit + cell)) {
+                    fail = true;
+                } else {
+                    const float gs = __ldg(P.sl_gammas + cell);
+                    const float cr = __ldg(P.sl_cosr + cell), sr = __ldg(P.sl_sinr + cell);
+                    const float Num = __ldg(P.sl_cohesion + cell) + (gs * zs - Zw * P.sl_gammaw) * (cr * cr) * __ldg(P.sl_tanfa + cell);
+                    const float Den = gs * zs * sr * cr;
+                    if (Num / Den <= P.sl_fs) fail = true;
+                }
+                if (fail) {
+                    sl_slid = 1;
+                    atomicAdd(P.sl_acum + cell, 1);
+                    int marks = 1;
+                    if (P.sl_gullie == 1 && type <= 2) {  // slide_hill2gullie (:1683-1707)
+                        int local = cell, ltype = type;
+                        for (;;) {
+                            const int dd = P.drena[(size_t)local * P.drena_stride];
+                            if (dd == 0) break;
+                            const int dir = N - dd;
+                            const int dtype = (__ldg(P.tw + dir) >> 4) & 3;
+                            if (dtype > ltype) break;
+                            atomicMin(P.sl_marktime + dir, t);
+                            atomicAdd(P.sl_acum + dir, 1);
+                            ++marks;
+                            local = dir;
+                            ltype = dtype;
+                        }
+                    }
+                    atomicAdd(P.sl_ncelltime + t, marks);
+                }
+            }
+            if (SED) {
+                float4 *so = P.sedout4 + ((size_t)(b & 1) * K + tt) * 3 * NM + base;
+                so[0] = make_float4(SL.up[0], SL.up[1], SL.up[2], SL.up[3]);
+                so[NM] = make_float4(SL.up[4], SL.up[5], SL.up[6], SL.up[7]);
+                so[2 * NM] = make_float4(SL.up[8], SL.up[9], SL.up[10], SL.up[11]);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { ero_acc[i] += (double)SL.ero_add[i]; dep_acc[i] += (double)SL.dep_add[i]; }
+            }
             ob_out[(size_t)tt * NM] = o;
             // storage change of the cell over the step + what left the basin through it: summed over the cells this
             // is sum(StoOut) - StoAtras + salidas of :846 (the transfers between cells cancel)
@@ -890,6 +1003,29 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             if (KIN && P.st[k] == 2) P.hsp[k * NM + base] = kv[k];
         if (CHAN) P.hsp[3 * NM + base] = vch;
         if (P.retorned) P.retorned[cell] = ret_acc;
+        if (SED) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                P.sed[(0 + k) * NM + base] = SL.Vs[k];
+                P.sed[(3 + k) * NM + base] = SL.Vd[k];
+                P.sed[(6 + k) * NM + base] = SL.Vsc[k];
+                P.sed[(9 + k) * NM + base] = SL.Vdc[k];
+            }
+            P.voldepo[base] = vdep;
+            P.volero[base] = vero;
+        }
+        if (SLIDES) P.sl_slid[cell] = sl_slid;
+    }
+    if (SED) {  // EROt / DEPt (:1403, :1420): global totals, fp64
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double a = warp_sum_d(ero_acc[i]);
+            const double c = warp_sum_d(dep_acc[i]);
+            if ((threadIdx.x & 31) == 0) {
+                if (a != 0.0) atomicAdd(P.sedtot + i, a);
+                if (c != 0.0) atomicAdd(P.sedtot + 3 + i, c);
+            }
+        }
     }
     // ---- per-step balance terms: one fp64 atomic per (warp, step) ----
     if (P.want_red) {
@@ -923,18 +1059,18 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
 
 // Every CTA carries the same mix of roles: its first `cpb` warps take 32-thread tiles of the channel list, the
 // others tiles of the hillslope list, so the SMs stay balanced although a channel thread costs ~4x a hillslope one.
-template <int K, bool KIN>
-__global__ void __launch_bounds__(TB_THREADS, TB_MIN_BLOCKS)
+template <int K, bool KIN, bool SED, bool SLIDES>
+__global__ void __launch_bounds__(TB_THREADS, SED ? 2 : TB_MIN_BLOCKS)
 k_shia_tb(const __grid_constant__ ShiaP P, const int w, const int clo, const int chi, const int hlo, const int hhi,
           const int cpb, const int n_ctiles, const int n_htiles) {
     __shared__ float s_acc[K * TB_THREADS];
     const int wi = threadIdx.x >> 5;
     if (wi < cpb) {
         const int tile = (int)blockIdx.x * cpb + wi;
-        if (tile < n_ctiles) tb_role<K, true, KIN>(P, w, clo, chi, tile, s_acc);
+        if (tile < n_ctiles) tb_role<K, true, KIN, SED, SLIDES>(P, w, clo, chi, tile, s_acc);
     } else {
         const int tile = (int)blockIdx.x * (TB_THREADS / 32 - cpb) + (wi - cpb);
-        if (tile < n_htiles) tb_role<K, false, KIN>(P, w, hlo, hhi, tile, s_acc);
+        if (tile < n_htiles) tb_role<K, false, KIN, SED, SLIDES>(P, w, hlo, hhi, tile, s_acc);
     }
 }
 
@@ -1423,7 +1559,7 @@ static void launch_wave(wmf_ctx *ctx, const ShiaP &P, int w, int lo, int hi) {
     ctx->launches++;
 }
 
-template <int K>
+template <int K, bool SED = false, bool SLIDES = false>
 static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int hlo, int hhi, bool pdl) {
     constexpr int WPB = TB_THREADS / 32;
     const int wc = (int)(((long long)(chi - clo) * P.M + 31) / 32), wh = (int)(((long long)(hhi - hlo) * P.M + 31) / 32);
@@ -1448,23 +1584,33 @@ static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    if (P.st[0] == 2 || P.st[1] == 2 || P.st[2] == 2)
-        cudaLaunchKernelEx(&cfg, k_shia_tb<K, true>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
-    else
-        cudaLaunchKernelEx(&cfg, k_shia_tb<K, false>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
+    const bool kin = P.st[0] == 2 || P.st[1] == 2 || P.st[2] == 2;
+    if (kin) cudaLaunchKernelEx(&cfg, k_shia_tb<K, true, SED, SLIDES>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
+    else cudaLaunchKernelEx(&cfg, k_shia_tb<K, false, SED, SLIDES>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
     ctx->launches++;
 }
 
-// steps per time block of k_shia_tb (power of two <= 32); 0 = use the one-step-per-launch kernel k_shia_wave
-static int tb_steps(int T, bool eligible) {
+// Steps per time block of k_shia_tb; 0 = use the one-step-per-launch kernel k_shia_wave.
+// A wave holds N * M * min(1, (T/K) / Lmax) threads and the sweep's critical path grows with K * Lmax, so K is the
+// largest of {8, 4, 2, 1} that still fills about two thirds of the GPU's resident thread slots per wave (measured on the
+// C2 basin, Lmax = 1022: T = 1000 -> K = 4 (29 ms; K = 2: 35, K = 8: 34), T = 400 -> K = 2, T = 200 -> K = 1..2).
+static int tb_steps(int T, bool eligible, long long cells_x_members, int Lmax, int num_sms, bool single) {
     if (!eligible) return 0;
-    int k = 4;
-    if (const char *e = getenv("WMF_SHIA_K")) k = atoi(e);
-    if (k <= 0) return 0;
-    int p = 1;
-    while (p * 2 <= k && p * 2 <= 32) p *= 2;
-    while (p > 1 && p > T) p /= 2;
-    return p;
+    if (const char *e = getenv("WMF_SHIA_K")) {
+        const int k = atoi(e);
+        if (k <= 0) return 0;
+        int p = 1;
+        while (p * 2 <= k && p * 2 <= 32) p *= 2;
+        while (p > 1 && p > T) p /= 2;
+        return p;
+    }
+    const double want = 0.66 * 2048.0 * num_sms;
+    for (int k = single ? 8 : 4; k > 1; k /= 2) {
+        if (k > T) continue;
+        const double in_flight = std::min(1.0, ((double)T / k) / std::max(1, Lmax));
+        if ((double)cells_x_members * in_flight >= want) return k;
+    }
+    return 1;
 }
 
 extern "C" {
@@ -1630,9 +1776,10 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
 
     // ---- which kernel: the time-blocked wavefront unless an output only the one-step kernel produces is wanted ----
     const bool per_run = (M == 1);
-    const bool tb_ok = !sed && !slides && !(cfg->show_storage && out->mean_storage) && !(cfg->show_mean_speed && out->mean_speed) &&
+    const bool tb_ok = !(cfg->show_storage && out->mean_storage) && !(cfg->show_mean_speed && out->mean_speed) &&
                        !(cfg->retorno_gr == 1.0f && cfg->show_mean_retorno && out->mean_retorno);
-    const int KT = tb_steps(T, tb_ok);
+    int KT = tb_steps(T, tb_ok, (long long)N * M, Lmax, ctx->num_sms, M == 1);
+    if (KT && (sed || slides)) KT = (T >= 4) ? 4 : 0;  // the sediment / slide variants are built for K = 4 only
     std::vector<int32_t> h_hfirst;
     int64_t n_hill = 0;
     if (KT) {
@@ -1717,14 +1864,15 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
         const float *d_vd0;
         WMF_TRY(sc.in(in->vd_init, (size_t)3 * N, &d_vd0));
         WMF_TRY(sc.alloc(&P.sed, 12 * NM));
-        WMF_TRY(sc.alloc(&P.sedout, 24 * NM));
+        if (KT) WMF_TRY(sc.alloc(&P.sedout4, (size_t)2 * KT * 3 * NM));
+        else WMF_TRY(sc.alloc(&P.sedout, 24 * NM));
         WMF_TRY(sc.alloc(&P.volero, NM));
         WMF_TRY(sc.alloc(&P.voldepo, NM));
         WMF_TRY(sc.alloc(&P.sedtot, 6));
         CU_TRY(ctx, cudaMemsetAsync(P.volero, 0, sizeof(float) * NM, ctx->stream));
         CU_TRY(ctx, cudaMemsetAsync(P.voldepo, 0, sizeof(float) * NM, ctx->stream));
         CU_TRY(ctx, cudaMemsetAsync(P.sedtot, 0, sizeof(double) * 6, ctx->stream));
-        CU_TRY(ctx, cudaMemsetAsync(P.sedout, 0, sizeof(float) * 24 * NM, ctx->stream));
+        if (!KT) CU_TRY(ctx, cudaMemsetAsync(P.sedout, 0, sizeof(float) * 24 * NM, ctx->stream));
         LAUNCH(ctx, k_sed_init, grid_for((long long)NM, B), B, 0, d_vd0, N, M, P.sed);
         WMF_TRY(sc.out(out->qsed, QN * 3, &P.qsed));
         if (P.qsed) CU_TRY(ctx, cudaMemsetAsync(P.qsed, 0, sizeof(float) * QN * 3, ctx->stream));
@@ -1770,6 +1918,12 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
             const int clo = lo - hlo, chi = hi - hhi;
             const bool pdl = use_pdl && launched_any;  // the first wave follows memsets and plan kernels: plain launch
             launched_any = true;
+            if (sed || slides) {
+                if (sed && slides) launch_tb<4, true, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
+                else if (sed) launch_tb<4, true, false>(ctx, P, w, clo, chi, hlo, hhi, pdl);
+                else launch_tb<4, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
+                continue;
+            }
             switch (KT) {
                 case 1: launch_tb<1>(ctx, P, w, clo, chi, hlo, hhi, pdl); break;
                 case 2: launch_tb<2>(ctx, P, w, clo, chi, hlo, hhi, pdl); break;
