@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define WMF_ABI_VERSION 1
+#define WMF_ABI_VERSION 2
 
 enum {
     WMF_OK = 0,
@@ -136,6 +136,8 @@ typedef struct {
     float sl_fs, sl_gammaw;
     /* ensemble: number of members sharing topology, maps and rain (1 = the reference's single run) */
     int32_t n_members;
+    /* state dumps (modelosv2.f90:799-803, :815-818): the library returns the snapshots, the caller writes the files */
+    int32_t save_storage, save_speed;
 } wmf_shia_cfg;
 
 /* Arrays = module `models` allocatables (modelosv2.f90:53-113) in their f2py layouts. */
@@ -163,6 +165,9 @@ typedef struct {
     const float *vd_init;            /* (3,N) or NULL: Vd carried over from a previous run (:1301-1304) */
     /* slides */
     const float *sl_zs, *sl_gammas, *sl_cohesion, *sl_frictionangle, *sl_radslope; /* (N) */
+    /* module guarda_cond (n_reg): > 0 = dump StoOut after that step (the value is the record number the caller writes
+     * it to, wmf.py:4497-4505); needed when save_storage = 1 */
+    const int32_t *guarda_cond;
 } wmf_shia_inputs;
 
 /* Outputs.  Any pointer may be NULL (= not wanted).  Shapes as returned by f2py (modelsmodule.c:375-408).
@@ -188,6 +193,11 @@ typedef struct {
     float *sl_zmin, *sl_zcrit, *sl_zmax, *sl_bo, *sl_riskvector, *sl_slideocurrence; /* (N) */
     int32_t *sl_slideacumulate; /* (N) */
     int32_t *sl_slidencelltime; /* (n_reg) */
+    /* save_storage = 1: StoOut after every step with guarda_cond > 0, in step order: (n_snap, 5, N) -- what
+     * write_float_basin(ruta_storage, StoOut, guarda_cond(t), N_cel, 5) puts on disk (modelosv2.f90:799-803) */
+    float *sto_snap;
+    /* save_speed = 1: hspeed after every step: (n_reg, 4, N) (modelosv2.f90:815-818) */
+    float *speed_snap;
 } wmf_shia_outputs;
 
 /* shia_v1, modelosv2.f90:191-869 (+ calc_speed :1278-1293, sed_* :1298-1608, slide_* :1613-1707). */

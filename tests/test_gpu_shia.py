@@ -5,6 +5,8 @@ with an absolute floor scaled by the series maximum for near-zero flows.  `balan
 catastrophic-cancellation quantity (modelosv2.f90:846): the GPU accumulates it in fp64 and is compared with
 the oracle's fp64 restatement of the same sum, scaled by the total storage.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -320,3 +322,36 @@ def test_sediment_slide_kernels_agree(monkeypatch):
     close(m1.erot, m0.erot, rtol=1e-6, name="EROt")
     close(m1.dept, m0.dept, rtol=1e-6, name="DEPt")
     assert r1[1].max() > 0 and m1.sl_slidencelltime.sum() > 0
+
+
+def test_storage_and_speed_dumps(tmp_path):
+    """save_storage / save_speed (modelosv2.f90:799-803, 815-818): record guarda_cond(t) of the .StObin file holds StoOut
+    after step t and record t of the speed file holds hspeed -- i.e. exactly what a run truncated after step t returns."""
+    from wmf_b200 import ModelsModule, synth
+    from wmf_b200._models import read_float_basin_ncol
+    bs, inp = build("G2", 90, 70, 24, n_reg=40, speed_type=(2, 1, 1))
+    N, T = bs["n"], 40
+    guarda = np.zeros(T, np.int32)
+    guarda[[4, 17, 39]] = [1, 2, 3]                  # record numbers (record 1 replaces the file, modelosv2.f90:937-941)
+    m = ModelsModule()
+    synth.apply_to_models(m, inp)
+    m.set_rain(inp["rain"], inp["pos_evento"])
+    m.save_storage, m.save_speed = 1, 1
+    m.guarda_cond = guarda
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    sto_path, spd_path = str(tmp_path / "s.StObin"), str(tmp_path / "v.bin")
+    full = m.shia_v1(None, None, inp["calib"], n_cont, 1, T, None, None, N, sto_path, spd_path)
+    hs_full = m._run(np.asarray(inp["calib"], np.float32)[None, :], n_cont, 1, T, inp["rain"], inp["pos_evento"])
+    for t, rec in ((4, 1), (17, 2), (39, 3)):
+        a = dict(inp); a["n_reg"] = t + 1; a["pos_evento"] = inp["pos_evento"][:t + 1]; a["evpserie"] = inp["evpserie"][:t + 1]
+        mt = ModelsModule()
+        synth.apply_to_models(mt, a)
+        part = mt._run(np.asarray(a["calib"], np.float32)[None, :], n_cont, 1, t + 1, a["rain"], a["pos_evento"])
+        got, res = read_float_basin_ncol(sto_path, rec, N, 5)
+        assert res == 0
+        np.testing.assert_array_equal(got, part["stoout"])
+        spd, res = read_float_basin_ncol(spd_path, t + 1, N, 4)
+        assert res == 0
+        np.testing.assert_array_equal(spd, part["hspeed_out"])
+    np.testing.assert_array_equal(read_float_basin_ncol(sto_path, 3, N, 5)[0], full[9])
+    assert os.path.getsize(spd_path) == 4 * 4 * N * T and os.path.getsize(sto_path) == 4 * 5 * N * 3

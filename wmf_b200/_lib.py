@@ -40,6 +40,7 @@ class ShiaCfg(C.Structure):
         ("sed_factor", C.c_float), ("wi", C.c_float * 3), ("diametro", C.c_float * 3),
         ("sl_gullienogullie", C.c_int32), ("sl_fs", C.c_float), ("sl_gammaw", C.c_float),
         ("n_members", C.c_int32),
+        ("save_storage", C.c_int32), ("save_speed", C.c_int32),
     ]
 
 
@@ -58,6 +59,7 @@ class ShiaInputs(C.Structure):
         ("vd_init", C.c_void_p),
         ("sl_zs", C.c_void_p), ("sl_gammas", C.c_void_p), ("sl_cohesion", C.c_void_p),
         ("sl_frictionangle", C.c_void_p), ("sl_radslope", C.c_void_p),
+        ("guarda_cond", C.c_void_p),
     ]
 
 
@@ -66,7 +68,7 @@ _OUT_NAMES = [
     "mean_rain", "acum_rain", "mean_storage", "mean_speed", "mean_retorno", "retorned",
     "vs", "vd", "vsc", "vdc", "volero", "voldepo", "erot", "dept",
     "sl_zmin", "sl_zcrit", "sl_zmax", "sl_bo", "sl_riskvector", "sl_slideocurrence",
-    "sl_slideacumulate", "sl_slidencelltime",
+    "sl_slideacumulate", "sl_slidencelltime", "sto_snap", "speed_snap",
 ]
 
 

@@ -46,8 +46,7 @@ _SCALARS_I = {"nceldas": 0, "ncols": 0, "nrows": 0, "verbose": 0, "rain_first_po
               "show_mean_speed": 0, "show_mean_retorno": 0, "show_area": 0, "separate_fluxes": 0,
               "separate_rain": 0, "sl_gullienogullie": 0}
 # switches whose sub-models are outside the hot path built here
-_UNSUPPORTED = ("sim_floods", "save_storage", "save_speed", "save_retorno", "save_vfluxes", "save_rc",
-                "separate_fluxes", "separate_rain")
+_UNSUPPORTED = ("sim_floods", "save_retorno", "save_vfluxes", "save_rc", "separate_fluxes", "separate_rain")
 
 
 def read_rain_hdr(ruta_hdr: str, n_reg: int, rain_first_point: int = 1):
@@ -291,7 +290,21 @@ class ModelsModule:
         if calib.size != 11:
             raise ValueError("calib must have 11 elements (modelosv2.f90:201)")
         rain, pos = self._load_rain(ruta_bin, ruta_hdr, T, N)
+        save_sto, save_spd = int(self.save_storage) == 1, int(self.save_speed) == 1
+        if save_sto and not ruta_storage:
+            raise ValueError("models.save_storage = 1 needs ruta_storage (modelosv2.f90:799-803)")
+        if save_spd and not ruta_speed:
+            raise ValueError("models.save_speed = 1 needs ruta_speed (modelosv2.f90:815-818)")
         out = self._run(calib[None, :], int(n_cont), int(n_conth), T, rain, pos, stoin, hspeedin)
+        # state dumps in the reference's direct-access format: record guarda_cond(t) of ruta_storage holds StoOut(5,N)
+        # after step t; record t of ruta_speed holds hspeed(4,N)
+        if save_sto:
+            g = np.asarray(a["guarda_cond"]).reshape(-1)[:T]
+            for k, t in enumerate(np.nonzero(g > 0)[0]):
+                write_float_basin(str(ruta_storage).strip(), out["sto_snap"][:, :, k], int(g[t]), N, 5)
+        if save_spd:
+            for t in range(T):
+                write_float_basin(str(ruta_speed).strip(), out["speed_snap"][:, :, t], t + 1, N, 4)
         nc, nh = int(n_cont), int(n_conth)
         zeros = lambda *s: np.zeros(s, np.float32, order="F")
         qsed = out.get("qsed", zeros(nc, 3, T))
@@ -330,6 +343,8 @@ class ModelsModule:
         cfg.diametro = (C.c_float * 3)(*[float(v) for v in a["diametro"]])
         cfg.sl_fs, cfg.sl_gammaw = float(self.sl_fs), float(self.sl_gammaw)
         cfg.n_members = M
+        cfg.save_storage = int(self.save_storage) if M == 1 else 0
+        cfg.save_speed = int(self.save_speed) if M == 1 else 0
         keep = []
         si = ShiaInputs()
 
@@ -380,6 +395,14 @@ class ModelsModule:
         put("rain", rain)
         si.n_records = int(n_records)
         put("pos_evento", np.ascontiguousarray(pos, np.int32))
+        n_snap = 0
+        if cfg.save_storage == 1:
+            g = a.get("guarda_cond")
+            if g is None or g.size < T:
+                raise ValueError("models.guarda_cond must hold n_reg values when save_storage = 1 (wmf.py:4497-4505)")
+            g = np.ascontiguousarray(g.reshape(-1)[:T], np.int32)
+            n_snap = int(np.count_nonzero(g > 0))
+            put("guarda_cond", g)
         sed, sl = cfg.sim_sediments == 1, cfg.sim_slides == 1
         if sed:
             for k in ("krus", "crus", "prus"):
@@ -410,6 +433,10 @@ class ModelsModule:
             out("q", (n_cont, T)); out("hum", (n_conth, T)); out("st1", (n_conth, T)); out("st3", (n_conth, T))
             out("balance", (T,)); out("speed", (n_cont, T)); out("areacontrol", (n_cont, T))
             out("stoout", (5, N)); out("hspeed_out", (4, N)); out("mean_rain", (1, T)); out("acum_rain", (1, N))
+            if cfg.save_storage == 1:
+                out("sto_snap", (5, N, max(n_snap, 1)))
+            if cfg.save_speed == 1:
+                out("speed_snap", (4, N, T))
             if cfg.show_storage:
                 out("mean_storage", (5, T))
             if cfg.show_mean_speed:

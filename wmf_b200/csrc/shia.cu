@@ -87,6 +87,10 @@ struct ShiaP {
     float4 *outb4;          // [2][K][N][M] what a cell sends downstream at each step of its time block
     int bal_direct;         // red[t][RQ_SAL] holds sum(dS + outputs), balance = that - inputs
     float4 *sedout4;        // [2][K][3][N][M] sediment a cell sends downstream: sus(3) bm(3) ero(3) chan(3)
+    // state dumps (single runs): snap_slot[t] = row of sto_snap that receives StoOut after step t, or -1
+    const int32_t *snap_slot;
+    float *sto_snap;        // [n_snap][N][5]
+    float *spd_snap;        // [T][N][4]
 };
 
 __device__ __forceinline__ size_t sidx(const ShiaP &P, int k, int cell, int m) {
@@ -560,6 +564,16 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
         // ---- publish ----
 #pragma unroll
         for (int k = 0; k < 5; ++k) P.sto[k * NM + base] = S[k];
+        if (P.sto_snap) {  // save_storage (:799-803)
+            const int sl = __ldg(P.snap_slot + t);
+            if (sl >= 0) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) P.sto_snap[((size_t)sl * N + cell) * 5 + k] = S[k];
+            }
+        }
+        if (P.spd_snap)    // save_speed (:815-818)
+            reinterpret_cast<float4 *>(P.spd_snap)[(size_t)t * N + cell] =
+                make_float4(hs[0], hs[1], hs[2], (type > 1) ? hs[3] : P.hsp[3 * NM + base]);
         {
             float *ob = P.outb + (size_t)(t & 1) * 4 * NM;
             ob[0 * NM + base] = o0;
@@ -661,7 +675,10 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
 // block b-1.  Hillslope and channel cells run in different CTAs of the same launch (lists of cell ids per role),
 // so no warp mixes the cheap hillslope update with the channel's kinematic-wave iterations.
 // ---------------------------------------------------------------------------------------------------
-constexpr int TB_THREADS = 256;
+#ifndef TB_THREADS_N
+#define TB_THREADS_N 256
+#endif
+constexpr int TB_THREADS = TB_THREADS_N;
 #ifndef TB_MIN_BLOCKS
 #define TB_MIN_BLOCKS 4
 #endif
@@ -989,6 +1006,16 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                 for (int i = 0; i < 3; ++i) { ero_acc[i] += (double)SL.ero_add[i]; dep_acc[i] += (double)SL.dep_add[i]; }
             }
             ob_out[(size_t)tt * NM] = o;
+            if (P.sto_snap) {  // save_storage (:799-803)
+                const int sl = __ldg(P.snap_slot + t);
+                if (sl >= 0) {
+                    float *d = P.sto_snap + ((size_t)sl * N + cell) * 5;
+                    d[0] = S0; d[1] = S1; d[2] = S2; d[3] = S3; d[4] = S4;
+                }
+            }
+            if (P.spd_snap)    // save_speed (:815-818); a hillslope cell's channel speed keeps its initial value
+                reinterpret_cast<float4 *>(P.spd_snap)[(size_t)t * N + cell] =
+                    make_float4(kv[0], kv[1], kv[2], CHAN ? vch : P.hsp[3 * NM + base]);
             // storage change of the cell over the step + what left the basin through it: summed over the cells this
             // is sum(StoOut) - StoAtras + salidas of :846 (the transfers between cells cancel)
             dq = (((S0 - So0) + (S1 - So1)) + ((S2 - So2) + (S3 - So3))) + (S4 - So4) + sal;
@@ -1853,6 +1880,32 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     if (P.want_red) {
         WMF_TRY(sc.alloc(&P.red, (size_t)T * RQ_COUNT * RED_SUB));
         CU_TRY(ctx, cudaMemsetAsync(P.red, 0, sizeof(double) * (size_t)T * RQ_COUNT * RED_SUB, ctx->stream));
+    }
+    // ---- state dumps ----
+    if (cfg->save_storage == 1 || cfg->save_speed == 1) {
+        if (M != 1) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: save_storage / save_speed need a single run (n_members = 1)");
+        if (cfg->save_storage == 1 && out->sto_snap) {
+            if (!in->guarda_cond) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: save_storage = 1 needs guarda_cond");
+            std::vector<int32_t> g((size_t)T), slot((size_t)T);
+            if (Scope::on_device(in->guarda_cond)) {
+                CU_TRY(ctx, cudaMemcpyAsync(g.data(), in->guarda_cond, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, ctx->stream));
+                CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            } else {
+                memcpy(g.data(), in->guarda_cond, sizeof(int32_t) * T);
+            }
+            int n_snap = 0;
+            for (int t = 0; t < T; ++t) slot[t] = (g[t] > 0) ? n_snap++ : -1;
+            int32_t *d_slot;
+            WMF_TRY(sc.alloc(&d_slot, (size_t)T));
+            CU_TRY(ctx, cudaMemcpyAsync(d_slot, slot.data(), sizeof(int32_t) * T, cudaMemcpyHostToDevice, ctx->stream));
+            CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // `slot` goes out of scope
+            P.snap_slot = d_slot;
+            WMF_TRY(sc.out(out->sto_snap, (size_t)std::max(n_snap, 1) * 5 * N, &P.sto_snap));
+        }
+        if (cfg->save_speed == 1 && out->speed_snap) {
+            WMF_TRY(sc.out(out->speed_snap, (size_t)T * 4 * N, &P.spd_snap));
+            if (reinterpret_cast<uintptr_t>(P.spd_snap) & 15) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: speed_snap must be 16-byte aligned");
+        }
     }
     // ---- sediments / slides ----
     float *d_zmin = nullptr, *d_zcrit = nullptr, *d_zmax = nullptr, *d_bo = nullptr, *d_risk = nullptr;
