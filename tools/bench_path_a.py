@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--kind", default="G2")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", action="store_true", help="verify structural invariants on the host (slow for large N)")
+    ap.add_argument("--extras", action="store_true", help="also time basin_map2basin, basin_basics, stream mask and geo_hand (resident)")
     a = ap.parse_args()
     import torch
     from wmf_b200 import Context, CuModule, synth
@@ -30,8 +31,10 @@ def main():
     for s in a.sizes.split(","):
         nc = nr = int(s)
         t0 = time.time()
-        DIR, _ = synth.make_raster(a.kind, nc, nr, seed=0)
+        DIR, DEM = synth.make_raster(a.kind, nc, nr, seed=0)
         gen_s = time.time() - t0
+        d_dem = torch.from_numpy(np.ascontiguousarray(DEM.T)).cuda() if a.extras else None
+        del DEM
         cu.ncols, cu.nrows, cu.xll, cu.yll, cu.dx, cu.dy, cu.dxp, cu.nodata = nc, nr, 0.0, 0.0, 30.0, 30.0, 30.0, synth.NODATA
         x, y = synth.outlet_xy(nc, nr, 0.0, 0.0, 30.0)
         d_dir = torch.from_numpy(np.ascontiguousarray(DIR.T)).cuda()
@@ -59,6 +62,31 @@ def main():
                 "us_per_level_find": 1e3 * best[0] / max(levels, 1),
                 "achieved_gbs_28B": 28.0 * n / (total / 1e3) / 1e9, "frac_of_measured_hbm": 28.0 * n / (total / 1e3) / 1e9 / peak,
                 "gen_s": gen_s}
+        if a.extras:
+            def timed(fn):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                best_t, res = None, None
+                for _ in range(2):
+                    e0.record()
+                    res = fn()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    best_t = e0.elapsed_time(e1) if best_t is None else min(best_t, e0.elapsed_time(e1))
+                return best_t, res
+            d_dirf = d_dir.float()
+            t_m2b, demv = timed(lambda: cu.basin_map2basin(b, d_dem, 0.0, 0.0, 30.0, 30.0, synth.NODATA))
+            _, dirv = timed(lambda: cu.basin_map2basin(b, d_dirf, 0.0, 0.0, 30.0, 30.0, synth.NODATA))
+            dirv = dirv.int()
+            t_bas, (ac2, lng, pend, elev) = timed(lambda: cu.basin_basics(b, demv, dirv))
+            assert bool((ac2 == acum).all())
+            t_typ, _ = timed(lambda: cu.basin_stream_type(b, acum, [30, 500]))
+            cauce = (acum >= 500).int()
+            t_hand, (hand, hdnd, aq) = timed(lambda: cu.geo_hand(b, elev, lng, cauce))
+            assert float(hand.min()) >= 0.0
+            line.update({"map2basin_ms": t_m2b, "basics_ms": t_bas, "stream_type_ms": t_typ, "geo_hand_ms": t_hand,
+                         "basics_gbs_40B": 40.0 * n / (t_bas / 1e3) / 1e9, "geo_hand_gbs_40B": 40.0 * n / (t_hand / 1e3) / 1e9})
+            del d_dem, d_dirf, demv, dirv, ac2, lng, pend, elev, cauce, hand, hdnd, aq
         if a.check:
             bb = b.cpu().numpy().reshape(-1, 3)
             d = bb[:, 0]

@@ -486,11 +486,19 @@ __global__ void k_basics_reduce(const int32_t *__restrict__ basin_f, const float
                                 int32_t *__restrict__ hist_col, int32_t *__restrict__ hist_row) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double a = 0.0, b = 0.0;
+    int kc = -1, kr = -1;
     if (i < n) {
         a = (double)pend[i];
         b = (double)dem[i];
-        atomicAdd(&hist_col[basin_f[3 * (size_t)i + 1] - 1], 1);
-        atomicAdd(&hist_row[basin_f[3 * (size_t)i + 2] - 1], 1);
+        kc = basin_f[3 * (size_t)i + 1] - 1;
+        kr = basin_f[3 * (size_t)i + 2] - 1;
+    }
+    {   // consecutive cells of the table lie on one BFS ring and mostly share a row or a column: one atomic per
+        // distinct key of the warp instead of one per cell
+        const int lane = threadIdx.x & 31;
+        const unsigned pc = __match_any_sync(0xffffffffu, kc), pr = __match_any_sync(0xffffffffu, kr);
+        if (kc >= 0 && lane == __ffs(pc) - 1) atomicAdd(&hist_col[kc], __popc(pc));
+        if (kr >= 0 && lane == __ffs(pr) - 1) atomicAdd(&hist_row[kr], __popc(pr));
     }
     a = warp_sum_d(a);
     b = warp_sum_d(b);
