@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "common.cuh"
 #include "wmf_pow.cuh"
@@ -1495,7 +1496,9 @@ struct RainStream {
     std::vector<Tile> tiles;
     const int32_t *host = nullptr;
     int32_t *dev = nullptr;
-    int n_records = 0, N = 0, waited = 0;
+    int n_records = 0, N = 0, waited = 0, rg = 1, n_early = 0;
+    std::vector<int> tmin;       // first step that reads each record
+    std::vector<char> rg_done;   // record groups already on their way (early())
     bool active = false;
     ~RainStream() {  // an early error return must not free the buffer under a copy still in flight
         if (active && waited < (int)tiles.size() && owner && owner->copy_stream) cudaStreamSynchronize(owner->copy_stream);
@@ -1515,17 +1518,56 @@ struct RainStream {
         *out = dev;
         return WMF_OK;
     }
-    // h_first[L] = first cell of level L (cells are ordered by decreasing level), pos[t] = 1-based record of step t
-    int schedule(wmf_ctx *ctx, const std::vector<int32_t> &h_first, int Lmax, const std::vector<int32_t> &pos, int K) {
+    static void tile_grid(int *n_rg, int *n_cg) {
+        *n_rg = 12; *n_cg = 12;  // measured best on C2 (tools/e2e_probe.py): 12x12 47.4 ms, 24x24 48.7, by record only 68.9
+        if (const char *e = getenv("WMF_RAIN_TILES")) sscanf(e, "%d,%d", n_rg, n_cg);
+        *n_rg = std::max(1, *n_rg); *n_cg = std::max(1, *n_cg);
+    }
+    // Before anything else of the run is queued: the record groups the sweep reads first go out whole (all cells), so the
+    // link is busy while the other inputs are staged and the plan is built.  pos[t] = 1-based record of step t.
+    int early(wmf_ctx *ctx, const std::vector<int32_t> &pos) {
         if (!active) return WMF_OK;
         const int T = (int)pos.size();
-        std::vector<int> tmin((size_t)n_records, INT_MAX);
+        tmin.assign((size_t)n_records, INT_MAX);
         for (int t = T - 1; t >= 0; --t) tmin[pos[t] - 1] = t;
-        // record groups x cell groups (on level boundaries)
-        int n_rg = 12, n_cg = 12;  // measured best on C2 (tools/e2e_probe.py): 12x12 47.4 ms, 24x24 48.7, by record only 68.9
-        if (const char *e = getenv("WMF_RAIN_TILES")) sscanf(e, "%d,%d", &n_rg, &n_cg);
-        n_rg = std::max(1, n_rg); n_cg = std::max(1, n_cg);
-        const int rg = std::max(1, (n_records + n_rg - 1) / n_rg);
+        int n_rg, n_cg;
+        tile_grid(&n_rg, &n_cg);
+        rg = std::max(1, (n_records + n_rg - 1) / n_rg);
+        const int groups = (n_records + rg - 1) / rg;
+        rg_done.assign((size_t)groups, 0);
+        // the allocation is ordered on the compute stream: the copy stream must not start before it
+        CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev1, 0));
+        for (int k = 0; k < 2 && k < groups; ++k) {  // the two groups with the earliest first use
+            int best = -1, best_t = INT_MAX;
+            for (int g = 0; g < groups; ++g) {
+                if (rg_done[g]) continue;
+                int tm = INT_MAX;
+                for (int r = g * rg; r < std::min(n_records, (g + 1) * rg); ++r) tm = std::min(tm, tmin[r]);
+                if (tm < best_t) { best_t = tm; best = g; }
+            }
+            if (best < 0) break;
+            rg_done[best] = 1;
+            const int r0 = best * rg, r1 = std::min(n_records, r0 + rg);
+            tiles.push_back({-1, r0, r1, 0, N});
+            if (ctx->copy_events.size() < tiles.size()) {
+                cudaEvent_t e;
+                CU_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->copy_events.push_back(e);
+            }
+            CU_TRY(ctx, cudaMemcpyAsync(dev + (size_t)r0 * N, host + (size_t)r0 * N, (size_t)(r1 - r0) * N * 4, cudaMemcpyHostToDevice,
+                                        ctx->copy_stream));
+            CU_TRY(ctx, cudaEventRecord(ctx->copy_events[tiles.size() - 1], ctx->copy_stream));
+        }
+        n_early = (int)tiles.size();
+        return WMF_OK;
+    }
+    // h_first[L] = first cell of level L (cells are ordered by decreasing level)
+    int schedule(wmf_ctx *ctx, const std::vector<int32_t> &h_first, int Lmax, const std::vector<int32_t> &pos, int K) {
+        if (!active) return WMF_OK;
+        (void)pos;
+        int n_rg, n_cg;
+        tile_grid(&n_rg, &n_cg);
         std::vector<int> cb{0};
         {
             const int target = std::max(1, N / n_cg);
@@ -1543,6 +1585,7 @@ struct RainStream {
             return lo;
         };
         for (int r0 = 0; r0 < n_records; r0 += rg) {
+            if (rg_done[r0 / rg]) continue;  // went out whole in early()
             const int r1 = std::min(n_records, r0 + rg);
             int tm = INT_MAX;
             for (int r = r0; r < r1; ++r) tm = std::min(tm, tmin[r]);
@@ -1550,16 +1593,13 @@ struct RainStream {
             for (size_t g = 0; g + 1 < cb.size(); ++g)
                 tiles.push_back({tm / K + (Lmax - level_of_cell(cb[g])), r0, r1, cb[g], cb[g + 1]});
         }
-        std::stable_sort(tiles.begin(), tiles.end(), [](const Tile &x, const Tile &y) { return x.w_first < y.w_first; });
+        std::stable_sort(tiles.begin() + n_early, tiles.end(), [](const Tile &x, const Tile &y) { return x.w_first < y.w_first; });
         while (ctx->copy_events.size() < tiles.size()) {
             cudaEvent_t e;
             CU_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             ctx->copy_events.push_back(e);
         }
-        // the allocation is ordered on the compute stream: the copy stream must not start before it
-        CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-        CU_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev1, 0));
-        for (size_t i = 0; i < tiles.size(); ++i) {
+        for (size_t i = (size_t)n_early; i < tiles.size(); ++i) {
             const Tile &t = tiles[i];
             const size_t o = (size_t)t.r0 * N + t.c0;
             CU_TRY(ctx, cudaMemcpy2DAsync(dev + o, (size_t)N * 4, host + o, (size_t)N * 4, (size_t)(t.c1 - t.c0) * 4,
@@ -1666,6 +1706,16 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     Scope sc(ctx);
     ShiaP P;
     memset(&P, 0, sizeof P);
+    // WMF_TIMING=1: host wall clock per phase on stderr (each mark synchronises the stream, so it perturbs overlap)
+    const bool timing = getenv("WMF_TIMING") && atoi(getenv("WMF_TIMING")) != 0;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (!timing) return;
+        cudaStreamSynchronize(ctx->stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[wmf_shia_run] %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     P.N = N; P.T = T; P.M = M; P.n_cont = cfg->n_cont; P.n_conth = cfg->n_conth;
     P.dt = cfg->dt; P.dxp = cfg->dxp; P.retorno_gr = cfg->retorno_gr; P.retorno_aq = cfg->retorno_aq;
     for (int k = 0; k < 3; ++k) P.st[k] = cfg->speed_type[k];
@@ -1677,6 +1727,23 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     P.sl_gullie = cfg->sl_gullienogullie; P.sl_fs = cfg->sl_fs; P.sl_gammaw = cfg->sl_gammaw;
     P.drena_stride = stride;
 
+    // ---- rainfall: the long pole of a run fed from host memory ----
+    if (in->n_records < 1) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: n_records must be >= 1");
+    // Rainfall is the one big input (C2: 1.7 GB).  From pinned host memory it is streamed in chunks of whole records on a
+    // second stream while the wavefront already runs: wave w only needs the records of the steps it has reached.
+    RainStream rs;
+    WMF_TRY(rs.begin(ctx, sc, in->rain, in->n_records, N, &P.rain));
+    // pos_evento is needed on both sides: validate on the host
+    std::vector<int32_t> h_pos((size_t)T);
+    if (Scope::on_device(in->pos_evento)) {
+        CU_TRY(ctx, cudaMemcpyAsync(h_pos.data(), in->pos_evento, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        memcpy(h_pos.data(), in->pos_evento, sizeof(int32_t) * T);
+    }
+    for (int t = 0; t < T; ++t)
+        if (h_pos[t] < 1 || h_pos[t] > in->n_records)
+            WMF_FAIL(ctx, WMF_ERR_ARG, "shia: pos_evento(%d)=%d outside 1..n_records=%d", t + 1, h_pos[t], in->n_records);
     // ---- stage inputs ----
     const int32_t *d_unit, *d_control, *d_controlh;
     WMF_TRY(sc.in(in->drena, (size_t)N * stride - (stride - 1), &P.drena));
@@ -1698,22 +1765,6 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     WMF_TRY(sc.in(in->elem_area, (size_t)N, &P.elem_area));
     WMF_TRY(sc.in(in->evpserie, (size_t)T, &P.evp));
     WMF_TRY(sc.in(in->calib, (size_t)11 * M, &P.calib));
-    if (in->n_records < 1) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: n_records must be >= 1");
-    // Rainfall is the one big input (C2: 1.7 GB).  From pinned host memory it is streamed in chunks of whole records on a
-    // second stream while the wavefront already runs: wave w only needs the records of the steps it has reached.
-    RainStream rs;
-    WMF_TRY(rs.begin(ctx, sc, in->rain, in->n_records, N, &P.rain));
-    // pos_evento is needed on both sides: validate on the host
-    std::vector<int32_t> h_pos((size_t)T);
-    if (Scope::on_device(in->pos_evento)) {
-        CU_TRY(ctx, cudaMemcpyAsync(h_pos.data(), in->pos_evento, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    } else {
-        memcpy(h_pos.data(), in->pos_evento, sizeof(int32_t) * T);
-    }
-    for (int t = 0; t < T; ++t)
-        if (h_pos[t] < 1 || h_pos[t] > in->n_records)
-            WMF_FAIL(ctx, WMF_ERR_ARG, "shia: pos_evento(%d)=%d outside 1..n_records=%d", t + 1, h_pos[t], in->n_records);
     WMF_TRY(sc.in(in->pos_evento, (size_t)T, &P.pos));
     const float *d_storage = nullptr, *d_stoin = nullptr, *d_hspeedin = nullptr;
     // StoIn / HspeedIn are honoured when their first element is > 0 (:271, :285)
@@ -1736,6 +1787,9 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     if (use_hsin) WMF_TRY(sc.in(in->hspeedin, (size_t)4 * N, &d_hspeedin));
     P.hs_state = use_hsin ? 1 : 0;
 
+    // the small inputs are queued; now the first rain records start to travel while the sweep is planned
+    WMF_TRY(rs.early(ctx, h_pos));
+    mark("stage");
     // ---- plan ----
     int32_t *lev_a, *lev_b, *jmp_a, *jmp_b, *nch, *cmin, *cmax, *cs, *level_first, *fq, *fh, *posq, *posh;
     uint32_t *tw;
@@ -1824,6 +1878,7 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
         P.nb = (T + KT - 1) / KT;
         P.bal_direct = 1;
     }
+    mark("plan");
     // ---- state ----
     const size_t NM = (size_t)N * M;
     WMF_TRY(sc.alloc(&P.sto, 5 * NM));
@@ -1952,6 +2007,7 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
         P.sl_cosr = d_cosr; P.sl_sinr = d_sinr; P.sl_tanfa = d_tanfa;
     }
 
+    mark("setup");
     // ---- the wavefront ----
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // h_first is complete
     auto level_end = [&](int L) { return L == 0 ? N : h_first[L - 1]; };
@@ -2010,6 +2066,7 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     ctx->last_levels = Lmax + 1;
     ctx->last_waves = n_waves;
 
+    mark("waves");
     // ---- epilogue ----
     if (d_stoout || d_hsout) {
         if (KT) LAUNCH(ctx, k_state_final_tb, grid_for((long long)NM, B), B, 0, P, d_stoout, d_hsout);
@@ -2057,8 +2114,10 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
         WMF_TRY(sc.out(out->retorned, (size_t)N, &r));
         CU_TRY(ctx, cudaMemsetAsync(r, 0, sizeof(float) * (size_t)N, ctx->stream));
     }
+    mark("epilogue");
     WMF_TRY(sc.finish());
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    mark("d2h");
     cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
     return WMF_OK;
 }

@@ -27,6 +27,9 @@ struct FindState {
     long long n;   // cells found
     int depth;     // BFS levels (tree depth + 1)
     int err;       // 1 = queue overflow (cyclic DIR)
+#ifdef FIND_PROFILE
+    long long cyc[8];  // CTA 0: cycles in phase 1 / exchange / phase 2 / tail, number of re-splits
+#endif
 };
 
 #ifndef FIND_THREADS_N
@@ -152,11 +155,17 @@ k_basin_find(const int32_t *__restrict__ dir, int nc, int nr, int32_t *__restric
     bool cur_in_smem = false;             // s_cur[i] holds q_lin[lo + i] for i < FIND_CAP (I wrote them last level)
     int depth = 0, err = 0;
     unsigned stamp = 1;
+#ifdef FIND_PROFILE
+    long long pcyc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     for (;;) {
         const int mine = (int)(hi - lo);
         // each warp takes a contiguous segment of 32*c positions; lane l handles seg + j*32 + l
         const int c = (mine + FIND_THREADS - 1) / FIND_THREADS;
         const long long seg = lo + (long long)wid * 32 * c;
+#ifdef FIND_PROFILE
+        long long tp0 = clock64();
+#endif
         // ---- phase 1: child masks and my count ----
         int cnt = 0;
         for (int j = 0; j < c; ++j) {
@@ -184,10 +193,16 @@ k_basin_find(const int32_t *__restrict__ dir, int nc, int nr, int32_t *__restric
             if (k < wid) wpre += v;
             mycnt += v;
         }
+#ifdef FIND_PROFILE
+        long long tp1 = clock64();
+#endif
         // ---- the exchange ----
         int off, total, lopsided;
         cta_exchange<false>(slots, stamp++, mycnt, s_scan, &off, &total, &lopsided);
         if (fe + total > cap) { err = 1; break; }  // uniform across the grid
+#ifdef FIND_PROFILE
+        long long tp2 = clock64();
+#endif
         // ---- phase 2: append my children in queue order ----
         const long long nlo = fe + off;
         long long base = nlo + wpre;
@@ -205,6 +220,10 @@ k_basin_find(const int32_t *__restrict__ dir, int nc, int nr, int32_t *__restric
             base += __shfl_sync(0xffffffffu, incl, 31);
         }
         ++depth;
+#ifdef FIND_PROFILE
+        long long tp3 = clock64();
+        if (tid == 0) { pcyc[0] += tp1 - tp0; pcyc[1] += tp2 - tp1; pcyc[2] += tp3 - tp2; pcyc[5] += c; if (mine > 0) pcyc[6] += 1; }
+#endif
         if (total == 0) break;
         const long long nfs = fe, nfe = fe + total;
         lo = nlo;
@@ -226,7 +245,13 @@ k_basin_find(const int32_t *__restrict__ dir, int nc, int nr, int32_t *__restric
             cur_in_smem = true;
         }
         fe = nfe;
+#ifdef FIND_PROFILE
+        if (tid == 0) { pcyc[3] += clock64() - tp3; pcyc[4] += lopsided ? 1 : 0; }
+#endif
     }
+#ifdef FIND_PROFILE
+    if (b == 0 && tid == 0) for (int k = 0; k < 8; ++k) st->cyc[k] = pcyc[k];
+#endif
     if (b == 0 && tid == 0) { st->n = fe; st->depth = depth; st->err = err; }
 }
 
@@ -815,6 +840,10 @@ int wmf_basin_find(wmf_ctx *ctx, float x, float y, const int32_t *dir, int32_t n
     FindState h;
     CU_TRY(ctx, cudaMemcpyAsync(&h, st, sizeof(FindState), cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+#ifdef FIND_PROFILE
+    fprintf(stderr, "[find profile] CTA0 cycles: phase1 %lld exchange %lld phase2 %lld tail %lld | resplits %lld, sum(c) %lld, levels with work %lld of %d\n",
+            h.cyc[0], h.cyc[1], h.cyc[2], h.cyc[3], h.cyc[4], h.cyc[5], h.cyc[6], h.depth);
+#endif
     if (h.err) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "basin_find: BFS queue overflow -- the DIR map is cyclic");
     ctx->find_n = (int32_t)h.n;
     ctx->find_depth = h.depth;
