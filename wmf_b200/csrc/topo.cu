@@ -1,10 +1,10 @@
 // topo.cu -- Path A: D8 flow-direction topology (module `cu`, wmf/cuencas.f90) on sm_100a.
 //
-//  basin_find   level-synchronous BFS in ONE persistent cooperative kernel.  Queue order == the Fortran's
-//               FIFO order (cuencas.f90:552-589): children of queue entry q are appended in the 3x3 scan
-//               order kf=1..3,kc=1..3, positions from an exclusive scan of child counts in queue order.
-//               Each CTA owns a contiguous share of the level and of its children, so a level costs ONE
-//               all-to-all exchange of child counts (release/acquire slots) instead of grid barriers.
+//  basin_find   BFS in ONE persistent cooperative kernel.  Queue order == the Fortran's FIFO order
+//               (cuencas.f90:552-589): children of queue entry q are appended in the 3x3 scan order kf=1..3,
+//               kc=1..3.  Each CTA owns a contiguous share of the frontier and expands it for 32 levels on its
+//               own (no communication); a [level][CTA] table of child counts then gives every segment its queue
+//               position.  Two grid-wide exchanges per 32 levels instead of barriers every level.
 //  basin_acum   leaf-to-root "last arriver climbs" sweep: one 64-bit atomicAdd per tree edge carries both the
 //               partial cell count and the arrival counter, no global barriers, exact (integer sums commute).
 //  acum_var /   same sweep, but the last arriver *gathers* its children in ascending cell order, which
@@ -27,9 +27,6 @@ struct FindState {
     long long n;   // cells found
     int depth;     // BFS levels (tree depth + 1)
     int err;       // 1 = queue overflow (cyclic DIR)
-#ifdef FIND_PROFILE
-    long long cyc[8];  // CTA 0: cycles in phase 1 / exchange / phase 2 / tail, number of re-splits
-#endif
 };
 
 #ifndef FIND_THREADS_N
@@ -65,13 +62,11 @@ __device__ __forceinline__ unsigned probe_children(const int32_t *__restrict__ d
     return m;
 }
 
-__device__ __forceinline__ void prefetch_l2(const void *p);
 // Appends the children of `lin` at queue position `pos`; the first `cap - (pos - own_lo)` of them are also kept in
 // shared memory (`s_nxt`, the CTA's share of the next level) and the DIR rows they will probe are prefetched.
-__device__ __forceinline__ void write_children(unsigned m, int lin, int nc, long long ncell, long long pos, int parent_qpos1,
+__device__ __forceinline__ void write_children(unsigned m, int lin, int nc, long long pos, int parent,
                                                int32_t *__restrict__ q_lin, int32_t *__restrict__ q_par,
-                                               const int32_t *__restrict__ dir, int32_t *__restrict__ s_nxt,
-                                               long long own_lo, int cap) {
+                                               int32_t *__restrict__ s_nxt, long long own_lo, int cap) {
     int bit = 0;
 #pragma unroll
     for (int kf = 1; kf <= 3; ++kf) {
@@ -81,7 +76,7 @@ __device__ __forceinline__ void write_children(unsigned m, int lin, int nc, long
             if (m & (1u << bit)) {
                 const int cl = lin + (kf - 2) * nc + (kc - 2);
                 q_lin[pos] = cl;
-                q_par[pos] = parent_qpos1;
+                q_par[pos] = parent;
                 if (pos - own_lo < cap) s_nxt[pos - own_lo] = cl;
                 ++pos;
             }
@@ -90,7 +85,6 @@ __device__ __forceinline__ void write_children(unsigned m, int lin, int nc, long
     }
 }
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -133,125 +127,170 @@ __device__ __forceinline__ void cta_exchange(unsigned long long *slots, unsigned
     __syncthreads();
 }
 
-// Level-synchronous BFS with ONE grid-wide exchange per level.  Every CTA owns a contiguous range of queue positions
-// of the current level; it probes them, the CTAs exchange their child counts, and each CTA appends its children at
-// (level end + prefix of the counts before it) -- queue order == the Fortran's FIFO order (cuencas.f90:552-589) because
-// ranges are ordered by CTA.  A CTA's children are its range of the next level, so it never reads what another CTA
-// wrote, and no second barrier is needed.  When the ranges get lopsided the level is re-split evenly, which costs one
-// extra exchange (then CTAs do read each other's entries, with L1-bypassing loads).
+// Breadth-first search in epochs of FIND_EPOCH levels with NO communication inside an epoch.
+// At an epoch's start the numbered frontier (a contiguous range of queue positions) is split evenly among the CTAs,
+// in queue order.  Every CTA then expands its own share level after level on its own: it probes its cells, scans the
+// child counts locally and appends the children (raster index + index of the parent inside the previous level's
+// segment) to a private region, which is also its next frontier.  Because the shares are ordered by CTA and every
+// CTA keeps the Fortran's scan order inside its share, the queue order of level L (cuencas.f90:552-589) is "CTA 0's
+// segment of L, CTA 1's segment of L, ...": after the epoch one table of child counts [level][CTA] gives every
+// segment its final queue position, the CTAs copy their segments out (coalesced) and translate parent indices, and
+// the last level becomes the next epoch's frontier.  Two fenced grid-wide exchanges per epoch instead of one or more
+// per level; a level costs one dependent DIR load plus a CTA-local scan.
+// A CTA whose region would overflow stops early; the epoch then ends at the smallest number of completed levels
+// (later segments are simply ignored and re-expanded in the next epoch).
+constexpr int FIND_EPOCH = 32;
+
 __global__ void __launch_bounds__(FIND_THREADS, 1)
 k_basin_find(const int32_t *__restrict__ dir, int nc, int nr, int32_t *__restrict__ q_lin,
-             int32_t *__restrict__ q_par, long long cap, unsigned long long *slots, FindState *st) {
+             int32_t *__restrict__ q_par, long long cap, unsigned long long *slots, FindState *st,
+             int32_t *__restrict__ priv_lin, int32_t *__restrict__ priv_par, long long region,
+             int32_t *__restrict__ cnt_tab /* [FIND_EPOCH][nb] */, int32_t *__restrict__ done_tab /* [nb] */) {
     __shared__ int s_scan[34];
-    __shared__ int s_wsum[32];
+    __shared__ int s_wsum[FIND_THREADS / 32];
+    __shared__ long long s_seg[FIND_EPOCH + 1];      // start of every level's segment inside my region
+    __shared__ int s_mycnt[FIND_EPOCH];
+    __shared__ long long s_off[FIND_EPOCH];          // final queue position of my segment of every level
+    __shared__ int s_total[FIND_EPOCH];
     extern __shared__ int32_t s_dyn[];      // [FIND_CAP] current share, [FIND_CAP] next share, [FIND_CAP] bytes of masks
     int32_t *s_cur = s_dyn, *s_nxt = s_dyn + FIND_CAP;
     unsigned char *s_mask = reinterpret_cast<unsigned char *>(s_dyn + 2 * FIND_CAP);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, b = blockIdx.x, nb = gridDim.x;
     const float rnc = 1.0f / (float)nc;
-    const long long ncell = (long long)nc * nr;
-    long long fe = 1;                     // end of the current level in the queue
-    long long lo = 0, hi = (b == 0) ? 1 : 0;  // my share of it
-    bool cur_in_smem = false;             // s_cur[i] holds q_lin[lo + i] for i < FIND_CAP (I wrote them last level)
-    int depth = 0, err = 0;
+    int32_t *my_lin = priv_lin + (size_t)b * region, *my_par = priv_par + (size_t)b * region;
+    long long fs = 0, fe = 1;             // numbered frontier = queue positions [fs, fe)
+    int depth = 1, err = 0;               // the outlet's level is already in the queue
     unsigned stamp = 1;
-#ifdef FIND_PROFILE
-    long long pcyc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#endif
     for (;;) {
-        const int mine = (int)(hi - lo);
-        // each warp takes a contiguous segment of 32*c positions; lane l handles seg + j*32 + l
-        const int c = (mine + FIND_THREADS - 1) / FIND_THREADS;
-        const long long seg = lo + (long long)wid * 32 * c;
-#ifdef FIND_PROFILE
-        long long tp0 = clock64();
-#endif
-        // ---- phase 1: child masks and my count ----
-        int cnt = 0;
-        for (int j = 0; j < c; ++j) {
-            const long long p = seg + (long long)j * 32 + lane;
-            if (p < hi) {
-                const bool cached = p - lo < FIND_CAP;
-                int lin;
-                if (cached && cur_in_smem) lin = s_cur[p - lo];
-                else {
-                    lin = __ldcg(q_lin + p);
-                    if (cached) s_cur[p - lo] = lin;
+        // ---- my share of the frontier, in queue order ----
+        const long long F = fe - fs;
+        const long long chunk = ((F + nb - 1) / nb + 31) / 32 * 32;
+        long long lo = fs + (long long)b * chunk, hi = lo + chunk;
+        if (lo > fe) lo = fe;
+        if (hi > fe) hi = fe;
+        // ---- expand up to FIND_EPOCH levels on my own ----
+        long long used = 0;               // entries of my region in use
+        long long prev_start = 0;         // where the current level's segment starts in my region (levels >= 1)
+        int mine = (int)(hi - lo);
+        bool cur_in_smem = false;
+        int done = 0;
+        for (int e = 0; e < FIND_EPOCH; ++e) {
+            if (mine == 0) {              // nothing below me any more: the remaining levels are empty
+                for (int k = e + tid; k < FIND_EPOCH; k += FIND_THREADS) { cnt_tab[k * nb + b] = 0; s_mycnt[k] = 0; s_seg[k] = used; }
+                done = FIND_EPOCH;
+                break;
+            }
+            const int c = (mine + FIND_THREADS - 1) / FIND_THREADS;
+            const long long seg = (long long)wid * 32 * c;   // lane l handles local cells seg + j*32 + l
+            // phase 1: child masks and my count
+            int cnt = 0;
+            for (int j = 0; j < c; ++j) {
+                const long long i = seg + (long long)j * 32 + lane;
+                if (i < mine) {
+                    const bool cached = i < FIND_CAP;
+                    int lin;
+                    if (cached && cur_in_smem) lin = s_cur[i];
+                    else {
+                        lin = (e == 0) ? __ldcg(q_lin + lo + i) : __ldcg(my_lin + prev_start + i);
+                        if (cached) s_cur[i] = lin;
+                    }
+                    const unsigned m = probe_children(dir, nc, nr, rnc, lin);
+                    if (cached) s_mask[i] = (unsigned char)m;
+                    cnt += __popc(m);
                 }
-                const unsigned m = probe_children(dir, nc, nr, rnc, lin);
-                if (cached) s_mask[p - lo] = (unsigned char)m;
-                cnt += __popc(m);
             }
-        }
-        cnt = warp_sum_i(cnt);
-        if (lane == 0) s_wsum[wid] = cnt;
-        __syncthreads();
-        int wpre = 0, mycnt = 0;  // children of the warps before mine / of the CTA
+            cnt = warp_sum_i(cnt);
+            if (lane == 0) s_wsum[wid] = cnt;
+            __syncthreads();
+            int wpre = 0, mycnt = 0;
 #pragma unroll
-        for (int k = 0; k < FIND_THREADS / 32; ++k) {
-            const int v = s_wsum[k];
-            if (k < wid) wpre += v;
-            mycnt += v;
-        }
-#ifdef FIND_PROFILE
-        long long tp1 = clock64();
-#endif
-        // ---- the exchange ----
-        int off, total, lopsided;
-        cta_exchange<false>(slots, stamp++, mycnt, s_scan, &off, &total, &lopsided);
-        if (fe + total > cap) { err = 1; break; }  // uniform across the grid
-#ifdef FIND_PROFILE
-        long long tp2 = clock64();
-#endif
-        // ---- phase 2: append my children in queue order ----
-        const long long nlo = fe + off;
-        long long base = nlo + wpre;
-        for (int j = 0; j < c; ++j) {
-            const long long p = seg + (long long)j * 32 + lane;
-            unsigned m = 0;
-            int lin = 0;
-            if (p < hi) {
-                if (p - lo < FIND_CAP) { lin = s_cur[p - lo]; m = s_mask[p - lo]; }
-                else { lin = __ldcg(q_lin + p); m = probe_children(dir, nc, nr, rnc, lin); }
+            for (int k = 0; k < FIND_THREADS / 32; ++k) {
+                const int v = s_wsum[k];
+                if (k < wid) wpre += v;
+                mycnt += v;
             }
-            const int k = __popc(m);
-            const int incl = warp_scan_incl(k);
-            if (m) write_children(m, lin, nc, ncell, base + incl - k, (int)(p + 1), q_lin, q_par, dir, s_nxt, nlo, FIND_CAP);
-            base += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        ++depth;
-#ifdef FIND_PROFILE
-        long long tp3 = clock64();
-        if (tid == 0) { pcyc[0] += tp1 - tp0; pcyc[1] += tp2 - tp1; pcyc[2] += tp3 - tp2; pcyc[5] += c; if (mine > 0) pcyc[6] += 1; }
-#endif
-        if (total == 0) break;
-        const long long nfs = fe, nfe = fe + total;
-        lo = nlo;
-        hi = lo + mycnt;
-        // ---- re-split the next level evenly when one CTA would carry much more than its share: the CTAs then read
-        // each other's entries, so this level needs a second exchange as a barrier (decision is grid-uniform) ----
-        if (lopsided) {
-            int d0, d1, d2;
-            cta_exchange<true>(slots, stamp++, 0, s_scan, &d0, &d1, &d2);
-            const long long chunk = ((long long)((total + nb - 1) / nb) + 31) / 32 * 32;
-            lo = nfs + (long long)b * chunk;
-            hi = lo + chunk;
-            if (lo > nfe) lo = nfe;
-            if (hi > nfe) hi = nfe;
-            cur_in_smem = false;
-        } else {
-            __syncthreads();  // s_nxt is complete
+            if (used + mycnt > region) break;  // would not fit: this level is redone in the next epoch (CTA-uniform)
+            // phase 2: append my children to my region (and keep them in shared memory as the next frontier)
+            long long base = used + wpre;
+            for (int j = 0; j < c; ++j) {
+                const long long i = seg + (long long)j * 32 + lane;
+                unsigned m = 0;
+                int lin = 0;
+                if (i < mine) {
+                    if (i < FIND_CAP) { lin = s_cur[i]; m = s_mask[i]; }
+                    else {
+                        lin = (e == 0) ? __ldcg(q_lin + lo + i) : __ldcg(my_lin + prev_start + i);
+                        m = probe_children(dir, nc, nr, rnc, lin);
+                    }
+                }
+                const int k = __popc(m);
+                const int incl = warp_scan_incl(k);
+                if (m) write_children(m, lin, nc, base + incl - k, (int)i, my_lin, my_par, s_nxt, used, FIND_CAP);
+                base += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (tid == 0) { cnt_tab[e * nb + b] = mycnt; s_mycnt[e] = mycnt; s_seg[e] = used; }
+            __syncthreads();              // s_nxt complete, my region's new entries visible to my other warps
             int32_t *t = s_cur; s_cur = s_nxt; s_nxt = t;
             cur_in_smem = true;
+            prev_start = used;
+            used += mycnt;
+            mine = mycnt;
+            done = e + 1;
         }
-        fe = nfe;
-#ifdef FIND_PROFILE
-        if (tid == 0) { pcyc[3] += clock64() - tp3; pcyc[4] += lopsided ? 1 : 0; }
-#endif
+        if (tid == 0) done_tab[b] = done;
+        // ---- exchange A: everybody's counts are published ----
+        int d0, d1, d2;
+        cta_exchange<true>(slots, stamp++, 0, s_scan, &d0, &d1, &d2);
+        // levels every CTA completed; totals and my final positions (thread e works on level e)
+        int l_end = FIND_EPOCH;
+        for (int k = 0; k < nb; ++k) l_end = min(l_end, __ldcg(done_tab + k));
+        if (l_end == 0) { err = 2; break; }          // a single level does not fit a region (grid-uniform)
+        if (tid < FIND_EPOCH) {
+            int tot = 0, before = 0;
+            if (tid < l_end)
+                for (int k = 0; k < nb; ++k) {
+                    const int v = __ldcg(cnt_tab + tid * nb + k);
+                    if (k < b) before += v;
+                    tot += v;
+                }
+            s_total[tid] = tot;
+            s_off[tid] = before;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            long long run = fe;
+            for (int e = 0; e < l_end; ++e) { s_off[e] += run; run += s_total[e]; }
+        }
+        __syncthreads();
+        // the BFS ends at the first empty level; levels after it do not exist
+        int n_lev = l_end;
+        for (int e = 0; e < l_end; ++e)
+            if (s_total[e] == 0) { n_lev = e; break; }
+        long long new_fs = fe, new_fe = fe;
+        for (int e = 0; e < n_lev; ++e) { new_fs = new_fe; new_fe += s_total[e]; }
+        if (new_fe > cap) { err = 1; break; }
+        // ---- copy my segments to their queue positions; a parent's queue position = start of my segment of the
+        // previous level (my share of the frontier for the first level) + its index in that segment ----
+        for (int e = 0; e < n_lev; ++e) {
+            const long long src = s_seg[e], dst = s_off[e];
+            const long long pbase = (e == 0) ? lo : s_off[e - 1];
+            const int n_e = s_mycnt[e];
+            for (int i = tid; i < n_e; i += FIND_THREADS) {
+                q_lin[dst + i] = my_lin[src + i];
+                q_par[dst + i] = (int32_t)(pbase + my_par[src + i] + 1);
+            }
+        }
+        depth += n_lev;
+        const bool finished = (n_lev < l_end) || (new_fe == new_fs);
+        fs = new_fs;
+        fe = new_fe;
+        if (finished) {
+            // depth counts levels including the last, empty expansion (the Fortran's loop runs once more)
+            break;
+        }
+        // ---- exchange B: the new frontier is in the queue for everybody ----
+        cta_exchange<true>(slots, stamp++, 0, s_scan, &d0, &d1, &d2);
     }
-#ifdef FIND_PROFILE
-    if (b == 0 && tid == 0) for (int k = 0; k < 8; ++k) st->cyc[k] = pcyc[k];
-#endif
     if (b == 0 && tid == 0) { st->n = fe; st->depth = depth; st->err = err; }
 }
 
@@ -829,21 +868,27 @@ int wmf_basin_find(wmf_ctx *ctx, float x, float y, const int32_t *dir, int32_t n
     CU_TRY(ctx, cudaFuncSetAttribute(k_basin_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIND_SMEM));
     CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_basin_find, FIND_THREADS, FIND_SMEM));
     if (occ < 1) WMF_FAIL(ctx, WMF_ERR_CUDA, "basin_find kernel does not fit on an SM");
-    int nb = std::min(ctx->num_sms, 32);  // co-resident CTAs (the exchange spins); 32 measured best: fewer pollers
-    if (nb > FIND_MAX_CTAS) nb = FIND_MAX_CTAS;
+    // co-resident CTAs (the exchanges spin).  Measured: 32 CTAs are best up to the 1024^2 raster (2.4 ms; 64: 2.7),
+    // 64 from 8192^2 on (25.2 ms; 32: 30.8, 128: 29.9)
+    int nb = std::min(ctx->num_sms, celTot >= (32LL << 20) ? 64 : 32);
     if (const char *e = getenv("WMF_FIND_CTAS")) nb = std::max(1, std::min(std::min(ctx->num_sms, FIND_MAX_CTAS), atoi(e)));
+    // private regions: what a CTA discovers during one epoch (raster index + parent index per cell)
+    long long region = 2 * celTot / nb + 65536;
+    int32_t *priv_lin, *priv_par, *cnt_tab, *done_tab;
+    WMF_TRY(sc.alloc(&priv_lin, (size_t)region * nb));
+    WMF_TRY(sc.alloc(&priv_par, (size_t)region * nb));
+    WMF_TRY(sc.alloc(&cnt_tab, (size_t)FIND_EPOCH * nb));
+    WMF_TRY(sc.alloc(&done_tab, (size_t)nb));
     long long cap = celTot;
     void *args[] = {(void *)&d_dir, (void *)&nc, (void *)&nr, (void *)&ctx->q_lin, (void *)&ctx->q_par, (void *)&cap,
-                    (void *)&slots, (void *)&st};
+                    (void *)&slots, (void *)&st, (void *)&priv_lin, (void *)&priv_par, (void *)&region, (void *)&cnt_tab,
+                    (void *)&done_tab};
     CU_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_basin_find, dim3(nb), dim3(FIND_THREADS), args, FIND_SMEM, ctx->stream));
     ctx->launches++;
     FindState h;
     CU_TRY(ctx, cudaMemcpyAsync(&h, st, sizeof(FindState), cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-#ifdef FIND_PROFILE
-    fprintf(stderr, "[find profile] CTA0 cycles: phase1 %lld exchange %lld phase2 %lld tail %lld | resplits %lld, sum(c) %lld, levels with work %lld of %d\n",
-            h.cyc[0], h.cyc[1], h.cyc[2], h.cyc[3], h.cyc[4], h.cyc[5], h.cyc[6], h.depth);
-#endif
+    if (h.err == 2) WMF_FAIL(ctx, WMF_ERR_NOMEM, "basin_find: one BFS level does not fit the per-CTA scratch regions");
     if (h.err) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "basin_find: BFS queue overflow -- the DIR map is cyclic");
     ctx->find_n = (int32_t)h.n;
     ctx->find_depth = h.depth;
