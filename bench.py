@@ -342,7 +342,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC_PER_LAUNCH, "peak_kind": peak_kind, "kernel": "k_shia_tb<4,false>",
+                         "traffic": TRAFFIC_PER_LAUNCH, "peak_kind": peak_kind, "kernel": "k_shia_tb<4,false,false,false>",
                          "bytes_per_cell_step": BYTES_PER_CELL_STEP, "launches_per_run": n_waves,
                          "achieved_per_launch_bytes": BYTES_PER_CELL_STEP * cell_steps / max(n_waves, 1),
                          "traffic_note": TRAFFIC_NOTE},

@@ -684,7 +684,7 @@ constexpr int TB_THREADS = TB_THREADS_N;
 #define TB_MIN_BLOCKS 4
 #endif
 
-template <int K, bool CHAN, bool KIN, bool SED, bool SLIDES>
+template <int K, bool CHAN, bool KIN, bool SED, bool SLIDES, bool SNAP>
 __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int jlo, const int jhi, const int tile,
                                         float *__restrict__ s_acc) {
     const int N = P.N, M = P.M;
@@ -1007,14 +1007,14 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                 for (int i = 0; i < 3; ++i) { ero_acc[i] += (double)SL.ero_add[i]; dep_acc[i] += (double)SL.dep_add[i]; }
             }
             ob_out[(size_t)tt * NM] = o;
-            if (P.sto_snap) {  // save_storage (:799-803)
+            if (SNAP && P.sto_snap) {  // save_storage (:799-803)
                 const int sl = __ldg(P.snap_slot + t);
                 if (sl >= 0) {
                     float *d = P.sto_snap + ((size_t)sl * N + cell) * 5;
                     d[0] = S0; d[1] = S1; d[2] = S2; d[3] = S3; d[4] = S4;
                 }
             }
-            if (P.spd_snap)    // save_speed (:815-818); a hillslope cell's channel speed keeps its initial value
+            if (SNAP && P.spd_snap)  // save_speed (:815-818); a hillslope cell's channel speed keeps its initial value
                 reinterpret_cast<float4 *>(P.spd_snap)[(size_t)t * N + cell] =
                     make_float4(kv[0], kv[1], kv[2], CHAN ? vch : P.hsp[3 * NM + base]);
             // storage change of the cell over the step + what left the basin through it: summed over the cells this
@@ -1087,7 +1087,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
 
 // Every CTA carries the same mix of roles: its first `cpb` warps take 32-thread tiles of the channel list, the
 // others tiles of the hillslope list, so the SMs stay balanced although a channel thread costs ~4x a hillslope one.
-template <int K, bool KIN, bool SED, bool SLIDES>
+template <int K, bool KIN, bool SED, bool SLIDES, bool SNAP>
 __global__ void __launch_bounds__(TB_THREADS, SED ? 2 : TB_MIN_BLOCKS)
 k_shia_tb(const __grid_constant__ ShiaP P, const int w, const int clo, const int chi, const int hlo, const int hhi,
           const int cpb, const int n_ctiles, const int n_htiles) {
@@ -1095,10 +1095,10 @@ k_shia_tb(const __grid_constant__ ShiaP P, const int w, const int clo, const int
     const int wi = threadIdx.x >> 5;
     if (wi < cpb) {
         const int tile = (int)blockIdx.x * cpb + wi;
-        if (tile < n_ctiles) tb_role<K, true, KIN, SED, SLIDES>(P, w, clo, chi, tile, s_acc);
+        if (tile < n_ctiles) tb_role<K, true, KIN, SED, SLIDES, SNAP>(P, w, clo, chi, tile, s_acc);
     } else {
         const int tile = (int)blockIdx.x * (TB_THREADS / 32 - cpb) + (wi - cpb);
-        if (tile < n_htiles) tb_role<K, false, KIN, SED, SLIDES>(P, w, hlo, hhi, tile, s_acc);
+        if (tile < n_htiles) tb_role<K, false, KIN, SED, SLIDES, SNAP>(P, w, hlo, hhi, tile, s_acc);
     }
 }
 
@@ -1626,7 +1626,7 @@ static void launch_wave(wmf_ctx *ctx, const ShiaP &P, int w, int lo, int hi) {
     ctx->launches++;
 }
 
-template <int K, bool SED = false, bool SLIDES = false>
+template <int K, bool SED = false, bool SLIDES = false, bool SNAP = false>
 static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int hlo, int hhi, bool pdl) {
     constexpr int WPB = TB_THREADS / 32;
     const int wc = (int)(((long long)(chi - clo) * P.M + 31) / 32), wh = (int)(((long long)(hhi - hlo) * P.M + 31) / 32);
@@ -1652,8 +1652,8 @@ static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     const bool kin = P.st[0] == 2 || P.st[1] == 2 || P.st[2] == 2;
-    if (kin) cudaLaunchKernelEx(&cfg, k_shia_tb<K, true, SED, SLIDES>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
-    else cudaLaunchKernelEx(&cfg, k_shia_tb<K, false, SED, SLIDES>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
+    if (kin) cudaLaunchKernelEx(&cfg, k_shia_tb<K, true, SED, SLIDES, SNAP>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
+    else cudaLaunchKernelEx(&cfg, k_shia_tb<K, false, SED, SLIDES, SNAP>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
     ctx->launches++;
 }
 
@@ -1860,7 +1860,8 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     const bool tb_ok = !(cfg->show_storage && out->mean_storage) && !(cfg->show_mean_speed && out->mean_speed) &&
                        !(cfg->retorno_gr == 1.0f && cfg->show_mean_retorno && out->mean_retorno);
     int KT = tb_steps(T, tb_ok, (long long)N * M, Lmax, ctx->num_sms, M == 1);
-    if (KT && (sed || slides)) KT = (T >= 4) ? 4 : 0;  // the sediment / slide variants are built for K = 4 only
+    const bool snap = (cfg->save_storage == 1 && out->sto_snap) || (cfg->save_speed == 1 && out->speed_snap);
+    if (KT && (sed || slides || snap)) KT = (T >= 4) ? 4 : 0;  // sediment / slide / dump variants are built for K = 4 only
     std::vector<int32_t> h_hfirst;
     int64_t n_hill = 0;
     if (KT) {
@@ -2027,6 +2028,13 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
             const int clo = lo - hlo, chi = hi - hhi;
             const bool pdl = use_pdl && launched_any;  // the first wave follows memsets and plan kernels: plain launch
             launched_any = true;
+            if (snap) {  // state dumps: K = 4 variants with the snapshot stores compiled in
+                if (sed && slides) launch_tb<4, true, true, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
+                else if (sed) launch_tb<4, true, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
+                else if (slides) launch_tb<4, false, true, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
+                else launch_tb<4, false, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
+                continue;
+            }
             if (sed || slides) {
                 if (sed && slides) launch_tb<4, true, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
                 else if (sed) launch_tb<4, true, false>(ctx, P, w, clo, chi, hlo, hhi, pdl);
