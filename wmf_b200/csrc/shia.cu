@@ -1672,7 +1672,9 @@ static int tb_steps(int T, bool eligible, long long cells_x_members, int Lmax, i
         return p;
     }
     const double want = 0.66 * 2048.0 * num_sms;
-    for (int k = single ? 8 : 4; k > 1; k /= 2) {
+    // ensembles have threads to spare: they take the longest block (measured, 260 100 cells x 512 members x 200 steps:
+    // K = 4 58 G, 8 68 G, 16 72 G member-cell-steps/s); wmf_shia_run halves it again if the outflow ring would not fit
+    for (int k = single ? 8 : 16; k > 1; k /= 2) {
         if (k > T) continue;
         const double in_flight = std::min(1.0, ((double)T / k) / std::max(1, Lmax));
         if ((double)cells_x_members * in_flight >= want) return k;
@@ -1860,6 +1862,15 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     const bool tb_ok = !(cfg->show_storage && out->mean_storage) && !(cfg->show_mean_speed && out->mean_speed) &&
                        !(cfg->retorno_gr == 1.0f && cfg->show_mean_retorno && out->mean_retorno);
     int KT = tb_steps(T, tb_ok, (long long)N * M, Lmax, ctx->num_sms, M == 1);
+    if (KT > 4 && !getenv("WMF_SHIA_K")) {  // the outflow ring holds 2 * K float4 per (cell, member): keep it under a third of the free memory
+        size_t free_b = 0, total_b = 0;
+        CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+        uint64_t reserved = 0, used = 0;  // blocks the stream-ordered pool keeps cached count as available
+        cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        if (reserved > used) free_b += (size_t)(reserved - used);
+        while (KT > 4 && (double)2 * KT * N * M * sizeof(float4) > 0.33 * (double)free_b) KT /= 2;
+    }
     const bool snap = (cfg->save_storage == 1 && out->sto_snap) || (cfg->save_speed == 1 && out->speed_snap);
     if (KT && (sed || slides || snap)) KT = (T >= 4) ? 4 : 0;  // sediment / slide / dump variants are built for K = 4 only
     std::vector<int32_t> h_hfirst;
