@@ -183,3 +183,36 @@ def test_resident_pipeline(cu):
     np.testing.assert_array_equal(b.cpu().numpy().T, bs["basin"])
     acum = cu.basin_acum(b)
     np.testing.assert_array_equal(acum.cpu().numpy(), bs["cu"].basin_acum(bs["basin"]))
+
+
+@pytest.mark.parametrize("nc,nr,seed,noise", [(64, 48, 0, 1.8), (200, 150, 1, 1.6), (333, 257, 2, 1.8), (512, 512, 3, 1.5),
+                                               (90, 1200, 4, 1.4)])
+def test_partial_basins_with_pits_and_holes(cu, nc, nr, seed, noise):
+    """Random rasters where the outlet catches only part of the map (other pits, nodata holes, no nodata frame, up to 8
+    cells draining into one): basin table, accumulation, basics and HAND equal the oracle's, bit for bit."""
+    import oracle
+    from wmf_b200 import synth
+    DIR, (oc, orow) = synth.make_partial_raster(nc, nr, seed, noise=noise)
+    dx = 30.0
+    x, y = dx * (oc - 0.5), dx * (nr - orow + 0.5)
+    ocu = oracle.Cu()
+    for c in (cu, ocu):
+        c.ncols, c.nrows, c.xll, c.yll, c.dx, c.dy, c.dxp, c.nodata = nc, nr, 0.0, 0.0, dx, dx, dx, synth.NODATA
+    n = cu.basin_find(x, y, DIR, nc, nr)
+    assert n == ocu.basin_find(x, y, DIR) and 10 < n < nc * nr
+    b = cu.basin_cut(n)
+    np.testing.assert_array_equal(b, ocu.basin_cut(n))
+    acum = cu.basin_acum(b)
+    np.testing.assert_array_equal(acum, ocu.basin_acum(b))
+    rng = np.random.default_rng(seed)
+    dem = (rng.random((nc, nr)) * 50 + 100).astype(np.float32)
+    dv = cu.basin_map2basin(b, DIR.astype(np.float32), 0, 0, dx, dx, synth.NODATA).astype(np.int32)
+    de = cu.basin_map2basin(b, dem, 0, 0, dx, dx, synth.NODATA)
+    got = cu.basin_basics(b, de, dv)
+    want = ocu.basin_basics(b, de, dv)
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g, w)
+    cauce = (acum >= 12).astype(np.int32)
+    if cauce[-1]:
+        for g, w in zip(cu.geo_hand(b, got[3], got[1], cauce), ocu.geo_hand(b, got[3], got[1], cauce)):
+            np.testing.assert_array_equal(g, w)

@@ -101,3 +101,24 @@ def test_map2basin_identity_and_nodata_mean():
     m[hole] = o.nodata
     got = o.basin_map2basin(b, m, 0, 0, 30, 30, o.nodata)
     assert got[7] == pytest.approx(m[m != o.nodata].mean(), rel=1e-4)
+
+
+@pytest.mark.parametrize("nc,nr,seed", [(24, 20, 0), (31, 17, 1), (40, 40, 2), (18, 33, 3)])
+def test_two_independent_restatements_agree_on_partial_basins(nc, nr, seed):
+    """oracle/topo_py.py (pure Python, written from cuencas.f90) vs the C oracle on random rasters with pits, nodata holes
+    and a basin that covers only part of the map: identical basin tables and accumulations."""
+    import oracle
+    from oracle import topo_py
+    from wmf_b200 import synth
+    DIR, (oc, orow) = synth.make_partial_raster(nc, nr, seed)
+    dx = 30.0
+    x, y = dx * (oc - 0.5), dx * (nr - orow + 0.5)
+    ocu = oracle.Cu()
+    ocu.ncols, ocu.nrows, ocu.xll, ocu.yll, ocu.dx, ocu.dy, ocu.dxp, ocu.nodata = nc, nr, 0.0, 0.0, dx, dx, dx, synth.NODATA
+    n = ocu.basin_find(x, y, DIR)
+    b = ocu.basin_cut(n)
+    bp = topo_py.basin_find_cut(x, y, DIR, 0.0, 0.0, dx)
+    assert 10 < n < (nc * nr) and bp.shape == (3, n)          # a partial basin
+    np.testing.assert_array_equal(bp, b)
+    np.testing.assert_array_equal(topo_py.basin_acum(bp), ocu.basin_acum(b))
+    assert (b[1, -1], b[2, -1]) == (oc, orow)

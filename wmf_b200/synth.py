@@ -106,6 +106,40 @@ def make_raster(kind: str, nc: int, nr: int, seed: int = 0, chunk_rows: int = 20
     return dir_rc.T, dem_rc.T   # (ncols, nrows), F-contiguous views
 
 
+def make_partial_raster(nc: int, nr: int, seed: int = 0, noise: float = 1.8, p_hole: float = 0.03):
+    """Random D8 raster whose outlet catches only PART of the map: (DIR int32 (nc,nr), outlet (col,row) 1-based).
+
+    Every cell gets a pseudo-elevation = distance to the outlet + ``noise`` * uniform; it drains to a hash-chosen
+    neighbour that is strictly lower (so the map is acyclic), local minima and ``p_hole`` of the cells are nodata.  Cells
+    whose path ends in another pit or a hole are outside the basin; nothing is guaranteed about the number of cells
+    draining into one cell (up to 8).  No nodata frame is needed because the basin never fills the raster."""
+    rng = np.random.default_rng(seed)
+    oc, orow = (nc + 1) // 2, (2 * nr) // 3
+    cols, rows = np.meshgrid(np.arange(1, nc + 1), np.arange(1, nr + 1), indexing="ij")
+    h = np.hypot(cols - oc, rows - orow) + noise * rng.random((nc, nr))
+    h[oc - 1, orow - 1] = -1.0
+    hole = rng.random((nc, nr)) < p_hole
+    hole[oc - 1, orow - 1] = False
+    h = np.where(hole, np.inf, h)
+    pad = np.full((nc + 2, nr + 2), np.inf)
+    pad[1:-1, 1:-1] = h
+    lower, codes = [], []
+    for mx, my in _MOVES:
+        nb = pad[1 + mx: 1 + mx + nc, 1 + my: 1 + my + nr]
+        lower.append(nb < h)
+        codes.append(5 - 3 * my + mx)
+    lower = np.stack(lower)                                  # (8, nc, nr)
+    cnt = lower.sum(0)
+    pick = (rng.integers(0, 1 << 30, (nc, nr)) % np.maximum(cnt, 1)).astype(np.int64)
+    order = np.cumsum(lower, 0) - 1                          # rank of each admissible move
+    sel = lower & (order == pick[None])
+    DIR = np.full((nc, nr), int(NODATA), np.int32)
+    for k, code in enumerate(codes):
+        DIR = np.where(sel[k], code, DIR).astype(np.int32)
+    DIR = np.where(hole | (cnt == 0), int(NODATA), DIR).astype(np.int32)
+    return np.asfortranarray(DIR), (oc, orow)
+
+
 def loguniform(rng, lo, hi, n):
     return np.exp(rng.uniform(np.log(lo), np.log(hi), n))
 
