@@ -355,3 +355,32 @@ def test_storage_and_speed_dumps(tmp_path):
         np.testing.assert_array_equal(spd, part["hspeed_out"])
     np.testing.assert_array_equal(read_float_basin_ncol(sto_path, 3, N, 5)[0], full[9])
     assert os.path.getsize(spd_path) == 4 * 4 * N * T and os.path.getsize(sto_path) == 4 * 5 * N * 3
+
+
+def test_shia_on_random_partial_basin():
+    """SHIA on the irregular tree of a random partial basin (pits, holes, up to 6-8 cells draining into one, several
+    channel heads): same tolerance as the regular generators."""
+    import oracle
+    from wmf_b200 import synth
+    nc, nr, dx = 150, 110, 30.0
+    DIR, (oc, orow) = synth.make_partial_raster(nc, nr, 7, noise=1.5)
+    x, y = dx * (oc - 0.5), dx * (nr - orow + 0.5)
+    ocu = oracle.Cu()
+    ocu.ncols, ocu.nrows, ocu.xll, ocu.yll, ocu.dx, ocu.dy, ocu.dxp, ocu.nodata = nc, nr, 0.0, 0.0, dx, dx, dx, synth.NODATA
+    n = ocu.basin_find(x, y, DIR)
+    b = ocu.basin_cut(n)
+    rng = np.random.default_rng(7)
+    hop = np.zeros(n + 1)
+    par = n - b[0]
+    for i in range(n - 2, -1, -1):
+        hop[i] = hop[par[i]] + 1
+    demv = (10 + 0.5 * hop[:n] + 0.2 * rng.random(n)).astype(np.float32)
+    dv = ocu.basin_map2basin(b, DIR.astype(np.float32), 0, 0, dx, dx, synth.NODATA).astype(np.int32)
+    acum, lng, pend, _ = ocu.basin_basics(b, demv, dv)
+    inp = synth.make_shia_inputs(b, acum, lng, pend, dxp=dx, n_reg=90, seed=7, thresholds=(20, 300), speed_type=(2, 1, 1),
+                                 retorno_gr=1, n_control_h=3)
+    nch = np.bincount(par[par < n], minlength=n)
+    assert nch.max() >= 5 and (np.asarray(inp["unit_type"]) > 1).sum() > 50
+    m, ret = run_gpu(inp)
+    ref = run_oracle(inp)
+    compare_core(ret, m, ref, n)
