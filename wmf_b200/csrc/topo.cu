@@ -868,9 +868,9 @@ int wmf_basin_find(wmf_ctx *ctx, float x, float y, const int32_t *dir, int32_t n
     CU_TRY(ctx, cudaFuncSetAttribute(k_basin_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIND_SMEM));
     CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_basin_find, FIND_THREADS, FIND_SMEM));
     if (occ < 1) WMF_FAIL(ctx, WMF_ERR_CUDA, "basin_find kernel does not fit on an SM");
-    // co-resident CTAs (the exchanges spin).  Measured: 32 CTAs are best up to the 1024^2 raster (2.4 ms; 64: 2.7),
-    // 64 from 8192^2 on (25.2 ms; 32: 30.8, 128: 29.9)
-    int nb = std::min(ctx->num_sms, celTot >= (32LL << 20) ? 64 : 32);
+    // co-resident CTAs (the exchanges spin).  Measured find time: 1024^2 raster 32 CTAs 2.4 ms (64: 2.7); 8192^2 64 CTAs
+    // 25.2 ms (32: 30.8, 128: 29.9); 20000^2 96 CTAs 73.3 ms (64: 90.6, 128: 79.6, 148: 83.6)
+    int nb = std::min(ctx->num_sms, celTot >= (200LL << 20) ? 96 : (celTot >= (32LL << 20) ? 64 : 32));
     if (const char *e = getenv("WMF_FIND_CTAS")) nb = std::max(1, std::min(std::min(ctx->num_sms, FIND_MAX_CTAS), atoi(e)));
     // private regions: what a CTA discovers during one epoch (raster index + parent index per cell)
     long long region = 2 * celTot / nb + 65536;
