@@ -814,7 +814,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             const float So0 = S0, So1 = S1, So2 = S2, So3 = S3, So4 = S4;
             // Loads first: the outflow of the first two upstream neighbours and this step's rain are requested before
             // the surface-tank update (which needs only the rain) so that their latency hides behind its pow chain.
-            const float4 *ob = ob_in + (size_t)tt * NM;
+            const float4 *ob = ob_in;
             float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), obb = oa;
             if (nch > 0) oa = ob[0];
             if (nch > 1) obb = ob[M];
@@ -1006,7 +1006,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
 #pragma unroll
                 for (int i = 0; i < 3; ++i) { ero_acc[i] += (double)SL.ero_add[i]; dep_acc[i] += (double)SL.dep_add[i]; }
             }
-            ob_out[(size_t)tt * NM] = o;
+            *ob_out = o;
             if (SNAP && P.sto_snap) {  // save_storage (:799-803)
                 const int sl = __ldg(P.snap_slot + t);
                 if (sl >= 0) {
@@ -1022,6 +1022,8 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             dq = (((S0 - So0) + (S1 - So1)) + ((S2 - So2) + (S3 - So3))) + (S4 - So4) + sal;
         }
         if (P.want_red) s_acc[tt * TB_THREADS + threadIdx.x] = dq;
+        ob_in += NM;   // next step's slice of the ring
+        ob_out += NM;
     }
     if (active) {
         P.st4[base] = make_float4(S0, S1, S2, S3);
