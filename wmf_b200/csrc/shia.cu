@@ -905,15 +905,16 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             }
             // routing (:599-719)
             float4 o;
-            const size_t qoff = ((size_t)m * P.T + t) * P.n_cont;
+            // row offset of step t in the (n_cont, n_reg) record tables: only the outlet and control cells need it
+            auto qoff_of = [&]() { return ((size_t)m * P.T + t) * P.n_cont; };
             if (!CHAN) {
                 o = make_float4(h0, h1, h2, 0.0f);
                 if (outlet) {
                     const float s3 = (h0 + h1) + h2;
-                    if (P.q) P.q[qoff] = s3 * m3;
+                    if (P.q) P.q[qoff_of()] = s3 * m3;
                     sal = sal + s3;
                 }
-                if (rowq >= 0 && P.q) P.q[qoff + rowq] = 0.0f;
+                if (rowq >= 0 && P.q) P.q[qoff_of() + rowq] = 0.0f;
                 if (SED && P.st[0] == 2) {  // hillslope cell: single VolDEPo / VolERO increment (:1426-1427)
                     vdep = vdep + SL.voldepo_add;
                     vero = vero + SL.volero_add;
@@ -942,6 +943,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                 S4 = S4 - h3;
                 o = make_float4(0.0f, 0.0f, h2 * (float)(3 - type), h3);
                 if (outlet) {
+                    const size_t qoff = qoff_of();
                     if (P.q) P.q[qoff] = h3 * m3 / dt;
                     sal = sal + h3;
                     if (P.show_speed) {
@@ -950,6 +952,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                     }
                 }
                 if (rowq >= 0) {  // records (:749-787)
+                    const size_t qoff = qoff_of();
                     if (P.q) P.q[qoff + rowq] = h3 * m3 / dt;
                     if (P.show_speed) {
                         if (P.speed) P.speed[qoff + rowq] = vch;
