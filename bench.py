@@ -45,7 +45,10 @@ WORKLOADS = {
     # name: (ncols, nrows, steps, generator)
     "c2": (1024, 1024, 1000, "G2"),      # BASELINE.json configs[1]
     "c2-small": (258, 258, 200, "G2"),   # smoke-sized variant for quick checks
+    "c5": (1448, 1448, 288, "G2"),       # BASELINE.json configs[4] basin: ~2.1 M cells, 12 m, 5-minute steps (tools/profile_shia.py)
 }
+# per-workload overrides of (cell size [m], time step [s], unit-type thresholds on acum)
+WORKLOAD_GEO = {"c5": (12.0, 300.0, (200, 2000))}
 DX = 30.0
 
 
@@ -101,6 +104,7 @@ def build_workload(name: str, cu, rank: int = 0, verbose: bool = False):
     """Synthetic basin + SHIA inputs of workload ``name``; the topology is traced with OUR Path-A kernels."""
     from wmf_b200 import synth
     nc, nr, T, gen = WORKLOADS[name]
+    DX, dt, thresholds = WORKLOAD_GEO.get(name, (30.0, 3600.0, (30, 500)))
     t0 = time.time()
     DIR, DEM = synth.make_raster(gen, nc, nr, seed=0)
     cu.ncols, cu.nrows, cu.xll, cu.yll, cu.dx, cu.dy, cu.dxp, cu.nodata = nc, nr, 0.0, 0.0, DX, DX, DX, synth.NODATA
@@ -110,7 +114,7 @@ def build_workload(name: str, cu, rank: int = 0, verbose: bool = False):
     dv = cu.basin_map2basin(b, DIR.astype(np.float32), 0.0, 0.0, DX, DX, synth.NODATA).astype(np.int32)
     de = cu.basin_map2basin(b, DEM, 0.0, 0.0, DX, DX, synth.NODATA)
     acum, lng, pend, _ = cu.basin_basics(b, de, dv)
-    inp = synth.make_shia_inputs(b, acum, lng, pend, dxp=DX, dt=3600.0, n_reg=T, seed=0, thresholds=(30, 500),
+    inp = synth.make_shia_inputs(b, acum, lng, pend, dxp=DX, dt=dt, n_reg=T, seed=0, thresholds=thresholds,
                                  speed_type=(1, 1, 1), n_control=16)
     if verbose:
         print(f"[bench] workload {name}: {n} cells, {T} steps, {inp['rain'].shape[0]} rain records, "
@@ -382,7 +386,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=["c2", "c2-small"])
     ap.add_argument("--cpu-sample-steps", type=int, default=120, help="steps of the workload timed on one CPU core")
     ap.add_argument("--ref-sample-steps", type=int, default=40, help="steps per reference-arm iteration")
     args = ap.parse_args()
