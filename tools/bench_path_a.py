@@ -84,6 +84,14 @@ def main():
             cauce = (acum >= 500).int()
             t_hand, (hand, hdnd, aq) = timed(lambda: cu.geo_hand(b, elev, lng, cauce))
             assert float(hand.min()) >= 0.0
+            # raster-wide HAND (geo_hand_global, cuencas.f90:2175-2219): accumulation back on the raster, network mask
+            # acum > 1000 cells, every other cell walks down DIR to the network
+            t_v2m, acum_map = timed(lambda: cu.basin_float_var2map(b, acum.float(), nc, nr))
+            t_net, red = timed(lambda: cu.geo_acum_to_cauce(acum_map.int(), 1000))
+            t_hg, hand_g = timed(lambda: cu.geo_hand_global(d_dem, d_dir, red))
+            line.update({"var2map_ms": t_v2m, "acum_to_cauce_ms": t_net, "geo_hand_global_ms": t_hg,
+                         "geo_hand_global_gbs_16B": 16.0 * nc * nr / (t_hg / 1e3) / 1e9})
+            del acum_map, red, hand_g
             line.update({"map2basin_ms": t_m2b, "basics_ms": t_bas, "stream_type_ms": t_typ, "geo_hand_ms": t_hand,
                          "basics_gbs_40B": 40.0 * n / (t_bas / 1e3) / 1e9, "geo_hand_gbs_40B": 40.0 * n / (t_hand / 1e3) / 1e9})
             del d_dem, d_dirf, demv, dirv, ac2, lng, pend, elev, cauce, hand, hdnd, aq
