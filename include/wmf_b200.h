@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define WMF_ABI_VERSION 2
+#define WMF_ABI_VERSION 3
 
 enum {
     WMF_OK = 0,
@@ -138,6 +138,8 @@ typedef struct {
     int32_t n_members;
     /* state dumps (modelosv2.f90:799-803, :815-818): the library returns the snapshots, the caller writes the files */
     int32_t save_storage, save_speed;
+    /* module separate_fluxes (modelosv2.f90:90): track the runoff / subsurface / base-flow shares of the channel water */
+    int32_t separate_fluxes;
 } wmf_shia_cfg;
 
 /* Arrays = module `models` allocatables (modelosv2.f90:53-113) in their f2py layouts. */
@@ -198,6 +200,8 @@ typedef struct {
     float *sto_snap;
     /* save_speed = 1: hspeed after every step: (n_reg, 4, N) (modelosv2.f90:815-818) */
     float *speed_snap;
+    /* separate_fluxes = 1: Qseparated (n_cont, 3, n_reg), modelosv2.f90:697-704, 752-759 */
+    float *qseparated;
 } wmf_shia_outputs;
 
 /* shia_v1, modelosv2.f90:191-869 (+ calc_speed :1278-1293, sed_* :1298-1608, slide_* :1613-1707). */

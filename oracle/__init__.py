@@ -62,6 +62,7 @@ class ShiaIn(C.Structure):
         ("show_storage", C.c_int32), ("show_speed", C.c_int32), ("show_mean_speed", C.c_int32),
         ("show_mean_retorno", C.c_int32), ("save_retorno", C.c_int32),
         ("save_vfluxes", C.c_int32), ("save_rc", C.c_int32),
+        ("separate_fluxes", C.c_int32),
         ("calib", C.c_float * 11),
         ("drena", i32p), ("unit_type", i32p),
         ("hill_long", f32p), ("hill_slope", f32p), ("stream_long", f32p), ("stream_slope", f32p),
@@ -82,7 +83,7 @@ class ShiaIn(C.Structure):
 
 class ShiaOut(C.Structure):
     _fields_ = [
-        ("q", f32p), ("qsed", f32p), ("hum", f32p), ("st1", f32p), ("st3", f32p),
+        ("q", f32p), ("qsed", f32p), ("qseparated", f32p), ("hum", f32p), ("st1", f32p), ("st3", f32p),
         ("balance", f32p), ("balance64", f64p), ("speed", f32p), ("areacontrol", f32p),
         ("stoout", f32p), ("hspeed_out", f32p), ("mean_rain", f32p), ("acum_rain", f32p),
         ("mean_storage", f32p), ("mean_speed", f32p), ("mean_retorno", f32p), ("retorned", f32p),
@@ -348,7 +349,7 @@ def shia_v1(inp: dict, fast: bool = False) -> dict:
     si.speed_type = (C.c_int32 * 3)(*[int(v) for v in inp.get("speed_type", [1, 1, 1])])
     si.calc_niter = int(inp.get("calc_niter", 5))
     for k in ("sim_sediments", "sim_slides", "show_storage", "show_speed", "show_mean_speed",
-              "show_mean_retorno", "save_retorno", "save_vfluxes", "save_rc"):
+              "show_mean_retorno", "save_retorno", "save_vfluxes", "save_rc", "separate_fluxes"):
         setattr(si, k, int(inp.get(k, 0)))
     si.calib = (C.c_float * 11)(*[float(v) for v in inp["calib"]])
 
@@ -401,6 +402,7 @@ def shia_v1(inp: dict, fast: bool = False) -> dict:
 
     out("q", (n_cont, T))
     out("qsed", (n_cont, 3, T))
+    out("qseparated", (n_cont, 3, T))
     out("hum", (n_conth, T))
     out("st1", (n_conth, T))
     out("st3", (n_conth, T))

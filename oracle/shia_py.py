@@ -53,6 +53,9 @@ def shia_v1(inp):
     H = np.stack([A("max_capilar", 1)[0] * calib[8], A("max_gravita", 1)[0] * calib[9], A("max_aquifer", 1)[0] * calib[10]]).astype(np.float32)
     Q = np.zeros((n_cont, T), np.float32)
     Hum = np.zeros((n_conth, T), np.float32)
+    sep = int(inp.get("separate_fluxes", 0)) == 1
+    Fluxes = np.zeros((3, N + 1), np.float32)        # :340-344 (+1: the outlet's receiver)
+    Qsep = np.zeros((n_cont, 3, T), np.float32)
     mean_rain = np.zeros(T, np.float32)
     hflux = [f32(0)] * 4
     for t in range(T):
@@ -108,19 +111,41 @@ def shia_v1(inp):
                 hspeed[3, c], area = calc_speed(f32(Sto[4, c] * m3[c]), f32(h_coef[3, c] * calib[7]), h_exp[3, c],
                                                 stream_long[c], hspeed[3, c], dt, niter)
                 hflux[3] = min(f32(f32(f32(area * hspeed[3, c]) * dt) / m3[c]), Sto[4, c])
+                if sep:                              # :658-665
+                    for i in range(3):
+                        Fluxes[i, c] = f32(Fluxes[i, c] + hflux[i])
+                    if Sto[4, c] > 0:
+                        r = f32(hflux[3] / Sto[4, c])
+                        for i in range(3):
+                            Fluxes[i, c] = f32(Fluxes[i, c] - f32(Fluxes[i, c] * r))
+                    else:
+                        Fluxes[:, c] = 0
                 Sto[4, c] = f32(Sto[4, c] - hflux[3])
                 if drena[c] != 0:
                     Sto[4, drenaid] = f32(Sto[4, drenaid] + hflux[3])
+                    if sep:                          # :674-680
+                        if Sto[4, c] > 0:
+                            r = f32(hflux[3] / Sto[4, c])
+                            for i in range(3):
+                                Fluxes[i, drenaid] = f32(Fluxes[i, drenaid] + f32(Fluxes[i, c] * r))
+                        else:
+                            Fluxes[:, drenaid] = 0
                 else:
                     Q[0, t] = f32(f32(hflux[3] * m3[c]) / dt)
+                    if sep:                          # :697-704
+                        for i in range(3):
+                            Qsep[0, i, t] = f32(f32(f32(Fluxes[i, c] * f32(hflux[3] / Sto[4, c])) * m3[c]) / dt) if Sto[4, c] > 0 else f32(0)
             # records :749-787 (hflux(4) is whatever the last channel cell left there -- the reference's quirk)
             if control[c] != 0:
                 if control_cont < n_cont:
                     Q[control_cont, t] = f32(f32(hflux[3] * m3[c]) / dt)
+                    if sep and ut > 1:               # :752-759
+                        for i in range(3):
+                            Qsep[control_cont, i, t] = f32(f32(f32(Fluxes[i, c] * f32(hflux[3] / Sto[4, c])) * m3[c]) / dt) if Sto[4, c] > 0 else f32(0)
                 control_cont += 1
             if control_h[c] != 0:
                 if controlh_cont < n_conth:
                     Hum[controlh_cont, t] = f32(Sto[0, c] + Sto[2, c])
                 controlh_cont += 1
         mean_rain[t] = f32(rain_sum / f32(N))
-    return dict(q=Q, stoout=Sto, hum=Hum, mean_rain=mean_rain, hspeed=hspeed)
+    return dict(q=Q, stoout=Sto, hum=Hum, mean_rain=mean_rain, hspeed=hspeed, qseparated=Qsep)

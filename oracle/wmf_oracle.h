@@ -83,6 +83,7 @@ typedef struct {
     int32_t sim_sediments, sim_slides;
     int32_t show_storage, show_speed, show_mean_speed, show_mean_retorno, save_retorno;
     int32_t save_vfluxes, save_rc;
+    int32_t separate_fluxes;   /* modelosv2.f90:90, shadow shares of runoff / subsurface / base flow in the channel */
     float calib[11];
     /* topology + statics, all (1,N) or (K,N) column-major */
     const int32_t *drena;      /* (N) drain ids = structure row 1 */
@@ -114,6 +115,7 @@ typedef struct {
 typedef struct {
     float *q;           /* (n_cont, n_reg) column-major: [ (t)*n_cont + c ] */
     float *qsed;        /* (n_cont, 3, n_reg) */
+    float *qseparated;  /* (n_cont, 3, n_reg), separate_fluxes = 1 (may be NULL) */
     float *hum, *st1, *st3; /* (n_conth, n_reg) */
     float *balance;     /* (n_reg) literal fp32 sequential sums */
     double *balance64;  /* (n_reg) same terms accumulated in double (diagnostic, may be NULL) */

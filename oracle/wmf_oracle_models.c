@@ -288,6 +288,9 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
     float *m3_mm = (float *)malloc(sizeof(float) * (size_t)N);
     float *rain = (float *)malloc(sizeof(float) * (size_t)N);
     float *vfl_map = in->save_vfluxes ? (float *)malloc(sizeof(float) * 4 * (size_t)N) : NULL;
+    /* Fluxes(3,N_cel+1) :340-344 (one spare column: the outlet's out-of-range receiver is never written here) */
+    float *Fluxes = (in->separate_fluxes == 1) ? (float *)calloc(3 * ((size_t)N + 1), sizeof(float)) : NULL;
+    if (Fluxes && out->qseparated) memset(out->qseparated, 0, sizeof(float) * 3 * (size_t)NC * T);
     sed_state SS;
     memset(&SS, 0, sizeof SS);
     SS.in = in;
@@ -441,10 +444,36 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
                     sed_channel(&SS, A5(Sto, 4, c), A4(hspeed, 3, c), hflux[3] * m3_mm[c] / dt,
                                 in->stream_slope[c], section_area, c, drenaid, Vsal_sed);
                 }
+                /* separate_fluxes :658-665 -- note the ratio uses StoOut(5) BEFORE the outflow is taken out */
+                if (Fluxes) {
+                    for (int i = 0; i < 3; ++i) Fluxes[3 * (size_t)c + i] = Fluxes[3 * (size_t)c + i] + hflux[i];
+                    if (A5(Sto, 4, c) > 0.0f) {
+                        const float ratio = hflux[3] / A5(Sto, 4, c);
+                        for (int i = 0; i < 3; ++i)
+                            Fluxes[3 * (size_t)c + i] = Fluxes[3 * (size_t)c + i] - Fluxes[3 * (size_t)c + i] * ratio;
+                    } else {
+                        for (int i = 0; i < 3; ++i) Fluxes[3 * (size_t)c + i] = 0.0f;
+                    }
+                }
                 A5(Sto, 4, c) = A5(Sto, 4, c) - hflux[3];
                 if (in->drena[c] != 0) {
                     A5(Sto, 4, drenaid) = A5(Sto, 4, drenaid) + hflux[3];
+                    /* :674-680 -- and here AFTER; an empty channel zeroes the receiver's shares */
+                    if (Fluxes) {
+                        if (A5(Sto, 4, c) > 0.0f) {
+                            const float ratio = hflux[3] / A5(Sto, 4, c);
+                            for (int i = 0; i < 3; ++i)
+                                Fluxes[3 * (size_t)drenaid + i] = Fluxes[3 * (size_t)drenaid + i] + Fluxes[3 * (size_t)c + i] * ratio;
+                        } else {
+                            for (int i = 0; i < 3; ++i) Fluxes[3 * (size_t)drenaid + i] = 0.0f;
+                        }
+                    }
                 } else {
+                    if (Fluxes && out->qseparated) { /* :697-704 */
+                        for (int i = 0; i < 3; ++i)
+                            out->qseparated[((size_t)t * 3 + i) * NC + 0] =
+                                (A5(Sto, 4, c) > 0.0f) ? Fluxes[3 * (size_t)c + i] * (hflux[3] / A5(Sto, 4, c)) * m3_mm[c] / dt : 0.0f;
+                    }
                     out->q[(size_t)t * NC + 0] = hflux[3] * m3_mm[c] / dt;
                     salidas = salidas + hflux[3];
                     salidas64 += (double)hflux[3];
@@ -464,6 +493,10 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
                     size_t k = (size_t)t * NC + (control_cont - 1);
                     if (ut > 1) {
                         out->q[k] = hflux[3] * m3_mm[c] / dt;
+                        if (Fluxes && out->qseparated) /* :752-759 */
+                            for (int i = 0; i < 3; ++i)
+                                out->qseparated[((size_t)t * 3 + i) * NC + (control_cont - 1)] =
+                                    (A5(Sto, 4, c) > 0.0f) ? Fluxes[3 * (size_t)c + i] * (hflux[3] / A5(Sto, 4, c)) * m3_mm[c] / dt : 0.0f;
                         if (in->show_speed == 1) {
                             out->speed[k] = A4(hspeed, 3, c);
                             out->areacontrol[k] = section_area;
@@ -544,6 +577,7 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
     free(vspeed);
     free(H);
     free(m3_mm);
+    free(Fluxes);
     free(rain);
     free(vfl_map);
     return 0;

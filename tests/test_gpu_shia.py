@@ -384,3 +384,20 @@ def test_shia_on_random_partial_basin():
     m, ret = run_gpu(inp)
     ref = run_oracle(inp)
     compare_core(ret, m, ref, n)
+
+
+def test_separate_fluxes():
+    """separate_fluxes = 1 (modelosv2.f90:658-680, 697-704, 752-759): the runoff / subsurface / base-flow shares of the
+    discharge at the outlet and the control points, including the reference's "an emptied channel zeroes the receiver's
+    shares" rule, which makes the gather order-dependent."""
+    bs, inp = build("G2", 110, 84, 25, n_reg=100, rain_peak_mm=50.0)
+    inp["separate_fluxes"] = 1
+    m, ret = run_gpu(inp, dict(separate_fluxes=1))
+    ref = run_oracle(inp, dict(separate_fluxes=1))
+    compare_core(ret, m, ref, bs["n"])
+    assert ref["qseparated"].max() > 0 and ret[2].shape == ref["qseparated"].shape
+    close(ret[2], ref["qseparated"], name="Qseparated")
+    # without the switch the third return value is the zero array f2py would hand back
+    m0, ret0 = run_gpu(inp, dict(separate_fluxes=0))
+    assert not ret0[2].any()
+    np.testing.assert_array_equal(ret0[0], ret[0])

@@ -110,7 +110,8 @@ def test_zero_rain_record_shortcut():
     assert out["mean_rain"].max() == 0.0 and out["acum_rain"][0] == 0.0
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(speed_type=(2, 2, 1), retorno_gr=1, retorno_aq=1), dict(speed_type=(1, 2, 2))])
+@pytest.mark.parametrize("kw", [dict(), dict(speed_type=(2, 2, 1), retorno_gr=1, retorno_aq=1), dict(speed_type=(1, 2, 2)),
+                                dict(separate_fluxes=1)])
 def test_two_independent_restatements_agree(kw):
     """oracle/shia_py.py (pure Python, written from modelosv2.f90) and the C oracle agree bit for bit: the C restatement's
     tank cascade, kinematic solver, routing order and records carry no transcription slip that the second reading of
@@ -121,8 +122,10 @@ def test_two_independent_restatements_agree(kw):
     from wmf_b200 import synth
     bs = make_basin("G2", 26, 22, 5)
     v = basin_vectors(bs)
+    sep = kw.pop("separate_fluxes", 0) if isinstance(kw, dict) else 0
     inp = synth.make_shia_inputs(bs["basin"], v["acum"], v["lng"], v["pend"], dxp=30.0, n_reg=40, seed=5, thresholds=(8, 60),
                                  n_control=5, n_control_h=3, rain_peak_mm=40.0, **kw)
+    inp["separate_fluxes"] = sep
     a = oracle.shia_v1(dict(inp))
     b = shia_py.shia_v1(dict(inp))
     assert (np.asarray(inp["unit_type"]) > 1).sum() > 10 and a["q"].max() > 0
@@ -130,3 +133,11 @@ def test_two_independent_restatements_agree(kw):
     np.testing.assert_array_equal(b["q"], a["q"])
     np.testing.assert_array_equal(b["hum"], a["hum"])
     np.testing.assert_array_equal(b["mean_rain"], a["mean_rain"].reshape(-1))
+    if sep:
+        assert a["qseparated"].max() > 0
+        np.testing.assert_array_equal(b["qseparated"], a["qseparated"])
+        # the three shares add up to roughly the discharge (not exactly: a type-2 cell books its base flow in Fluxes
+        # although that water goes to the receiver's tank 4, modelosv2.f90:617-621 vs :659)
+        tot = a["qseparated"].sum(1)
+        ok = a["q"] > 1e-6
+        assert np.median(np.abs(tot[ok] - a["q"][ok]) / a["q"][ok]) < 0.1

@@ -40,7 +40,7 @@ class ShiaCfg(C.Structure):
         ("sed_factor", C.c_float), ("wi", C.c_float * 3), ("diametro", C.c_float * 3),
         ("sl_gullienogullie", C.c_int32), ("sl_fs", C.c_float), ("sl_gammaw", C.c_float),
         ("n_members", C.c_int32),
-        ("save_storage", C.c_int32), ("save_speed", C.c_int32),
+        ("save_storage", C.c_int32), ("save_speed", C.c_int32), ("separate_fluxes", C.c_int32),
     ]
 
 
@@ -68,7 +68,7 @@ _OUT_NAMES = [
     "mean_rain", "acum_rain", "mean_storage", "mean_speed", "mean_retorno", "retorned",
     "vs", "vd", "vsc", "vdc", "volero", "voldepo", "erot", "dept",
     "sl_zmin", "sl_zcrit", "sl_zmax", "sl_bo", "sl_riskvector", "sl_slideocurrence",
-    "sl_slideacumulate", "sl_slidencelltime", "sto_snap", "speed_snap",
+    "sl_slideacumulate", "sl_slidencelltime", "sto_snap", "speed_snap", "qseparated",
 ]
 
 

@@ -46,7 +46,7 @@ _SCALARS_I = {"nceldas": 0, "ncols": 0, "nrows": 0, "verbose": 0, "rain_first_po
               "show_mean_speed": 0, "show_mean_retorno": 0, "show_area": 0, "separate_fluxes": 0,
               "separate_rain": 0, "sl_gullienogullie": 0}
 # switches whose sub-models are outside the hot path built here
-_UNSUPPORTED = ("sim_floods", "save_retorno", "save_vfluxes", "save_rc", "separate_fluxes", "separate_rain")
+_UNSUPPORTED = ("sim_floods", "save_retorno", "save_vfluxes", "save_rc", "separate_rain")
 
 
 def read_rain_hdr(ruta_hdr: str, n_reg: int, rain_first_point: int = 1):
@@ -308,7 +308,7 @@ class ModelsModule:
         nc, nh = int(n_cont), int(n_conth)
         zeros = lambda *s: np.zeros(s, np.float32, order="F")
         qsed = out.get("qsed", zeros(nc, 3, T))
-        return (out["q"], qsed, zeros(nc, 3, T), out["hum"], out["st1"], out["st3"], out["balance"], out["speed"],
+        return (out["q"], qsed, out.get("qseparated", zeros(nc, 3, T)), out["hum"], out["st1"], out["st3"], out["balance"], out["speed"],
                 out["areacontrol"], out["stoout"], zeros(nc, 2, T))
 
     def _cell(self, name, K, N, dtype, required=True):
@@ -345,6 +345,7 @@ class ModelsModule:
         cfg.n_members = M
         cfg.save_storage = int(self.save_storage) if M == 1 else 0
         cfg.save_speed = int(self.save_speed) if M == 1 else 0
+        cfg.separate_fluxes = int(self.separate_fluxes) if M == 1 else 0
         keep = []
         si = ShiaInputs()
 
@@ -433,6 +434,8 @@ class ModelsModule:
             out("q", (n_cont, T)); out("hum", (n_conth, T)); out("st1", (n_conth, T)); out("st3", (n_conth, T))
             out("balance", (T,)); out("speed", (n_cont, T)); out("areacontrol", (n_cont, T))
             out("stoout", (5, N)); out("hspeed_out", (4, N)); out("mean_rain", (1, T)); out("acum_rain", (1, N))
+            if cfg.separate_fluxes == 1:
+                out("qseparated", (n_cont, 3, T))
             if cfg.save_storage == 1:
                 out("sto_snap", (5, N, max(n_snap, 1)))
             if cfg.save_speed == 1:

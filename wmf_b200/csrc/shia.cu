@@ -92,6 +92,10 @@ struct ShiaP {
     const int32_t *snap_slot;
     float *sto_snap;        // [n_snap][N][5]
     float *spd_snap;        // [T][N][4]
+    // separate_fluxes (:658-680, :697-704, :752-759): shares of runoff / subsurface / base flow in the channel tank
+    float *flx;             // [3][N][M]
+    float4 *flxout4;        // [2][K][N][M] (share sent downstream x3, flag: 1 add, 0 "receiver's shares := 0", 2 hillslope cell)
+    float *qsep;            // (n_cont, 3, n_reg)
 };
 
 __device__ __forceinline__ size_t sidx(const ShiaP &P, int k, int cell, int m) {
@@ -684,7 +688,7 @@ constexpr int TB_THREADS = TB_THREADS_N;
 #define TB_MIN_BLOCKS 4
 #endif
 
-template <int K, bool CHAN, bool KIN, bool SED, bool SLIDES, bool SNAP>
+template <int K, bool CHAN, bool KIN, bool SED, bool SLIDES, bool SNAP, bool SEPF>
 __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int jlo, const int jhi, const int tile,
                                         float *__restrict__ s_acc) {
     const int N = P.N, M = P.M;
@@ -802,6 +806,8 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
         sl_slid = P.sl_slid[cell];
         sl_mark = P.sl_marktime[cell];
     }
+    float F0 = 0.f, F1 = 0.f, F2 = 0.f;  // separate_fluxes: the channel tank's shares
+    if (SEPF && CHAN && active) { F0 = P.flx[base]; F1 = P.flx[NM + base]; F2 = P.flx[2 * NM + base]; }
     const bool outlet = active && (cell == N - 1);
     const float4 *ob_in = P.outb4 + (size_t)(b & 1) * K * NM + (size_t)c0 * M + m;
     float4 *ob_out = P.outb4 + (size_t)(b & 1) * K * NM + base;
@@ -842,6 +848,15 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                         S3 = S3 + o.z;
                         S4 = S4 + o.w;
                     }
+                }
+            }
+            if (SEPF && CHAN) {  // what the upstream channel cells did to my shares this step, in cell order (:674-680)
+                const float4 *fp = P.flxout4 + ((size_t)(b & 1) * K + tt) * NM + (size_t)c0 * M + m;
+#pragma unroll 1
+                for (int c = 0; c < nch; ++c, fp += M) {
+                    const float4 f = *fp;
+                    if (f.w == 1.0f) { F0 = F0 + f.x; F1 = F1 + f.y; F2 = F2 + f.z; }
+                    else if (f.w == 0.0f) { F0 = 0.0f; F1 = 0.0f; F2 = 0.0f; }
                 }
             }
             if (SED) {
@@ -915,6 +930,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                     sal = sal + s3;
                 }
                 if (rowq >= 0 && P.q) P.q[qoff_of() + rowq] = 0.0f;
+                if (SEPF) P.flxout4[((size_t)(b & 1) * K + tt) * NM + base] = make_float4(0.f, 0.f, 0.f, 2.0f);
                 if (SED && P.st[0] == 2) {  // hillslope cell: single VolDEPo / VolERO increment (:1426-1427)
                     vdep = vdep + SL.voldepo_add;
                     vero = vero + SL.volero_add;
@@ -940,7 +956,31 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                             for (int i = 0; i < 3; ++i) P.qsed[(((size_t)m * P.T + t) * 3 + i) * P.n_cont + rowq] = Vsal[i];
                     }
                 }
+                if (SEPF) {  // :658-665 (the ratio uses the channel tank BEFORE the outflow is taken out)
+                    F0 = F0 + h0; F1 = F1 + h1; F2 = F2 + h2;
+                    if (S4 > 0.0f) {
+                        const float r = h3 / S4;
+                        F0 = F0 - F0 * r; F1 = F1 - F1 * r; F2 = F2 - F2 * r;
+                    } else {
+                        F0 = 0.0f; F1 = 0.0f; F2 = 0.0f;
+                    }
+                }
                 S4 = S4 - h3;
+                if (SEPF) {  // :674-680, :697-704, :752-759 (and here AFTER)
+                    float4 f = make_float4(0.f, 0.f, 0.f, 0.0f);
+                    if (S4 > 0.0f) {
+                        const float r = h3 / S4;
+                        f = make_float4(F0 * r, F1 * r, F2 * r, 1.0f);
+                    }
+                    P.flxout4[((size_t)(b & 1) * K + tt) * NM + base] = f;
+                    if (P.qsep && (outlet || rowq >= 0)) {
+                        const size_t row = outlet ? 0 : (size_t)rowq;
+                        const size_t k3 = ((size_t)m * P.T + t) * 3 * P.n_cont + row;
+                        P.qsep[k3] = f.x * m3 / dt;
+                        P.qsep[k3 + P.n_cont] = f.y * m3 / dt;
+                        P.qsep[k3 + 2 * (size_t)P.n_cont] = f.z * m3 / dt;
+                    }
+                }
                 o = make_float4(0.0f, 0.0f, h2 * (float)(3 - type), h3);
                 if (outlet) {
                     const size_t qoff = qoff_of();
@@ -1048,6 +1088,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             P.volero[base] = vero;
         }
         if (SLIDES) P.sl_slid[cell] = sl_slid;
+        if (SEPF && CHAN) { P.flx[base] = F0; P.flx[NM + base] = F1; P.flx[2 * NM + base] = F2; }
     }
     if (SED) {  // EROt / DEPt (:1403, :1420): global totals, fp64
 #pragma unroll
@@ -1092,7 +1133,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
 
 // Every CTA carries the same mix of roles: its first `cpb` warps take 32-thread tiles of the channel list, the
 // others tiles of the hillslope list, so the SMs stay balanced although a channel thread costs ~4x a hillslope one.
-template <int K, bool KIN, bool SED, bool SLIDES, bool SNAP>
+template <int K, bool KIN, bool SED, bool SLIDES, bool SNAP, bool SEPF>
 __global__ void __launch_bounds__(TB_THREADS, SED ? 2 : TB_MIN_BLOCKS)
 k_shia_tb(const __grid_constant__ ShiaP P, const int w, const int clo, const int chi, const int hlo, const int hhi,
           const int cpb, const int n_ctiles, const int n_htiles) {
@@ -1100,10 +1141,10 @@ k_shia_tb(const __grid_constant__ ShiaP P, const int w, const int clo, const int
     const int wi = threadIdx.x >> 5;
     if (wi < cpb) {
         const int tile = (int)blockIdx.x * cpb + wi;
-        if (tile < n_ctiles) tb_role<K, true, KIN, SED, SLIDES, SNAP>(P, w, clo, chi, tile, s_acc);
+        if (tile < n_ctiles) tb_role<K, true, KIN, SED, SLIDES, SNAP, SEPF>(P, w, clo, chi, tile, s_acc);
     } else {
         const int tile = (int)blockIdx.x * (TB_THREADS / 32 - cpb) + (wi - cpb);
-        if (tile < n_htiles) tb_role<K, false, KIN, SED, SLIDES, SNAP>(P, w, hlo, hhi, tile, s_acc);
+        if (tile < n_htiles) tb_role<K, false, KIN, SED, SLIDES, SNAP, SEPF>(P, w, hlo, hhi, tile, s_acc);
     }
 }
 
@@ -1631,7 +1672,7 @@ static void launch_wave(wmf_ctx *ctx, const ShiaP &P, int w, int lo, int hi) {
     ctx->launches++;
 }
 
-template <int K, bool SED = false, bool SLIDES = false, bool SNAP = false>
+template <int K, bool SED = false, bool SLIDES = false, bool SNAP = false, bool SEPF = false>
 static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int hlo, int hhi, bool pdl) {
     constexpr int WPB = TB_THREADS / 32;
     const int wc = (int)(((long long)(chi - clo) * P.M + 31) / 32), wh = (int)(((long long)(hhi - hlo) * P.M + 31) / 32);
@@ -1657,8 +1698,8 @@ static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     const bool kin = P.st[0] == 2 || P.st[1] == 2 || P.st[2] == 2;
-    if (kin) cudaLaunchKernelEx(&cfg, k_shia_tb<K, true, SED, SLIDES, SNAP>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
-    else cudaLaunchKernelEx(&cfg, k_shia_tb<K, false, SED, SLIDES, SNAP>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
+    if (kin) cudaLaunchKernelEx(&cfg, k_shia_tb<K, true, SED, SLIDES, SNAP, SEPF>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
+    else cudaLaunchKernelEx(&cfg, k_shia_tb<K, false, SED, SLIDES, SNAP, SEPF>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
     ctx->launches++;
 }
 
@@ -1878,6 +1919,12 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     }
     const bool snap = (cfg->save_storage == 1 && out->sto_snap) || (cfg->save_speed == 1 && out->speed_snap);
     if (KT && (sed || slides || snap)) KT = (T >= 4) ? 4 : 0;  // sediment / slide / dump variants are built for K = 4 only
+    const bool sepf = cfg->separate_fluxes == 1;
+    if (sepf) {
+        if (sed || slides || snap || !tb_ok || M != 1)
+            WMF_FAIL(ctx, WMF_ERR_ARG, "shia: separate_fluxes cannot be combined with sediments, slides, state dumps, show_* means or ensembles");
+        KT = (T >= 4) ? 4 : 1;
+    }
     std::vector<int32_t> h_hfirst;
     int64_t n_hill = 0;
     if (KT) {
@@ -1909,6 +1956,11 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
         P.st4 = reinterpret_cast<float4 *>(P.sto);
         P.s5 = P.sto + 4 * NM;
         WMF_TRY(sc.alloc(&P.outb4, (size_t)2 * KT * NM));
+        if (sepf) {
+            WMF_TRY(sc.alloc(&P.flx, 3 * NM));
+            WMF_TRY(sc.alloc(&P.flxout4, (size_t)2 * KT * NM));
+            CU_TRY(ctx, cudaMemsetAsync(P.flx, 0, sizeof(float) * 3 * NM, ctx->stream));  // Fluxes = 0 (:343)
+        }
         LAUNCH(ctx, k_state_init_tb, G, B, 0, use_stoin ? d_stoin : d_storage, use_stoin ? 0.0f : cfg->storage_constant, N, M, P.st4, P.s5);
     } else {
         WMF_TRY(sc.alloc(&P.outb, 8 * NM));
@@ -1923,6 +1975,10 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     WMF_TRY(sc.out(out->hum, HN, &P.hum));
     WMF_TRY(sc.out(out->st1, HN, &P.st1o));
     WMF_TRY(sc.out(out->st3, HN, &P.st3o));
+    if (sepf) {
+        WMF_TRY(sc.out(out->qseparated, QN * 3, &P.qsep));
+        if (P.qsep) CU_TRY(ctx, cudaMemsetAsync(P.qsep, 0, sizeof(float) * QN * 3, ctx->stream));
+    }
     if (P.q) CU_TRY(ctx, cudaMemsetAsync(P.q, 0, sizeof(float) * QN, ctx->stream));
     if (P.speed) CU_TRY(ctx, cudaMemsetAsync(P.speed, 0, sizeof(float) * QN, ctx->stream));
     if (P.area) CU_TRY(ctx, cudaMemsetAsync(P.area, 0, sizeof(float) * QN, ctx->stream));
@@ -2044,6 +2100,11 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
             const int clo = lo - hlo, chi = hi - hhi;
             const bool pdl = use_pdl && launched_any;  // the first wave follows memsets and plan kernels: plain launch
             launched_any = true;
+            if (sepf) {  // separate_fluxes: K = 4 (or 1 for runs shorter than 4 steps)
+                if (KT == 4) launch_tb<4, false, false, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
+                else launch_tb<1, false, false, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
+                continue;
+            }
             if (snap) {  // state dumps: K = 4 variants with the snapshot stores compiled in
                 if (sed && slides) launch_tb<4, true, true, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
                 else if (sed) launch_tb<4, true, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
