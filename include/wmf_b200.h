@@ -102,6 +102,10 @@ int wmf_basin_float_var2map(wmf_ctx *ctx, const int32_t *basin_f, const float *v
 /* channel mask of basin_stream_nod, cuencas.f90:1351-1353: cauce = (acum >= umbral) */
 int wmf_basin_stream_mask(wmf_ctx *ctx, const int32_t *acum, int32_t nceldas, int32_t umbral,
                           int32_t *cauce, int32_t *n_cauce);
+/* basin_stream_nod, cuencas.f90:1340-1379: channel mask, hydrological nodes (3 = head, 2+ = confluence / outlet), tracing
+ * points */
+int wmf_basin_stream_nod(wmf_ctx *ctx, const int32_t *basin_f, const int32_t *acum, int32_t nceldas, int32_t umbral,
+                         int32_t *cauce, int32_t *nodos, int32_t *trazado, int32_t *n_nodos, int32_t *n_cauce);
 /* basin_stream_type, cuencas.f90:1439-1463 */
 int wmf_basin_stream_type(wmf_ctx *ctx, const int32_t *acum, int32_t nceldas, const int32_t *umbrales,
                           int32_t numbrales, int32_t *stream_types);

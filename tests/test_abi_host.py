@@ -134,3 +134,11 @@ def test_synthetic_generators_are_deterministic_and_acyclic():
         oc, orow = synth.outlet_colrow(48, 36)
         notout = ~((c + 1 == oc) & (r + 1 == orow))
         assert np.all(e1[c2, r2][notout] < e1[c, r][notout])
+
+
+def test_every_export_has_ctypes_argtypes():
+    """A C entry point called without argtypes gets its 64-bit pointers truncated to int: every export must declare them."""
+    from wmf_b200 import _lib
+    L = _lib.load()
+    missing = [s for s in _lib.EXPORTS if getattr(L, s).argtypes is None and s != "wmf_abi_version"]
+    assert not missing, missing

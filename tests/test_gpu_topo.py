@@ -216,3 +216,16 @@ def test_partial_basins_with_pits_and_holes(cu, nc, nr, seed, noise):
     if cauce[-1]:
         for g, w in zip(cu.geo_hand(b, got[3], got[1], cauce), ocu.geo_hand(b, got[3], got[1], cauce)):
             np.testing.assert_array_equal(g, w)
+
+
+@pytest.mark.parametrize("kind,nc,nr,umbral", [("G2", 200, 160, 30), ("G1", 150, 220, 12)])
+def test_stream_nod(cu, kind, nc, nr, umbral):
+    """basin_stream_nod (cuencas.f90:1340-1379): channel mask, hydrological nodes and tracing points, bit-exact."""
+    bs = make_basin(kind, nc, nr, 3)
+    geo_to(cu, bs)
+    v = basin_vectors(bs)
+    got = cu.basin_stream_nod(bs["basin"], v["acum"], umbral)
+    want = bs["cu"].basin_stream_nod(bs["basin"], v["acum"], umbral)
+    for g, w in zip(got[:3], want[:3]):
+        np.testing.assert_array_equal(g, w)
+    assert got[3:] == want[3:] and got[3] > 2 and got[4] > 10

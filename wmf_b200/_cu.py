@@ -257,6 +257,18 @@ class CuModule:
         c.check(c.L.wmf_basin_stream_mask(c.h, ptr(a), n, int(umbral), ptr(cauce), C.byref(cnt)))
         return cauce, cnt.value
 
+    def basin_stream_nod(self, basin_f, acum, umbral, nceldas=None):
+        """cauce,nodos,trazado,n_nodos,n_cauce = basin_stream_nod(basin_f,acum,umbral,[nceldas])   -- cuencas.f90:1340-1379"""
+        b, n, res = self._table(basin_f)
+        a = self._vec(acum, n, np.int32, "acum")
+        c = self.ctx
+        dev = getattr(b, "device", None)
+        cauce, nodos, traz = (self._new(res, (n,), np.int32, dev) for _ in range(3))
+        nn, ncau = C.c_int32(), C.c_int32()
+        c.check(c.L.wmf_basin_stream_nod(c.h, ptr(b), ptr(a), n, int(umbral), ptr(cauce), ptr(nodos), ptr(traz),
+                                         C.byref(nn), C.byref(ncau)))
+        return cauce, nodos, traz, nn.value, ncau.value
+
     def basin_stream_type(self, basin_f, acum, umbrales, numbrales=None, nceldas=None):
         """stream_types = basin_stream_type(basin_f,acum,umbrales,[numbrales,nceldas])   -- cuencas.f90:1439-1463"""
         res = is_torch_cuda(acum)

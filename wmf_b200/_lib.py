@@ -82,7 +82,7 @@ EXPORTS = [
     "wmf_synchronize", "wmf_launch_count", "wmf_set_geo", "wmf_get_basin_scalars",
     "wmf_coord2fil_col", "wmf_basin_find", "wmf_basin_cut", "wmf_basin_find_depth", "wmf_basin_acum",
     "wmf_basin_acum_var", "wmf_basin_basics", "wmf_basin_coordxy", "wmf_basin_map2basin",
-    "wmf_basin_2map_find", "wmf_basin_2map", "wmf_basin_float_var2map", "wmf_basin_stream_mask",
+    "wmf_basin_2map_find", "wmf_basin_2map", "wmf_basin_float_var2map", "wmf_basin_stream_mask", "wmf_basin_stream_nod",
     "wmf_basin_stream_type", "wmf_geo_acum_to_cauce", "wmf_geo_hand", "wmf_geo_hand_global",
     "wmf_basin_time_to_out", "wmf_basin_propagate", "wmf_shia_run", "wmf_eval_scores",
     "wmf_calc_speed", "wmf_last_kernel_ms", "wmf_last_shia_stats",
@@ -126,6 +126,7 @@ def load() -> C.CDLL:
     L.wmf_basin_2map.argtypes = [vp, vp, vp, i32, i32, i32, vp, f32p, f32p]
     L.wmf_basin_float_var2map.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     L.wmf_basin_stream_mask.argtypes = [vp, vp, i32, i32, vp, i32p]
+    L.wmf_basin_stream_nod.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, i32p, i32p]
     L.wmf_basin_stream_type.argtypes = [vp, vp, i32, vp, i32, vp]
     L.wmf_geo_acum_to_cauce.argtypes = [vp, vp, i64, i32, vp]
     L.wmf_geo_hand.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]

@@ -1158,6 +1158,72 @@ static int threshold_mask(wmf_ctx *ctx, const int32_t *acum, int64_t n, int32_t 
     return sc.finish();
 }
 
+// cuencas.f90:1340-1379 in three one-thread-per-cell passes (the counts commute: integer atomics)
+__global__ void k_nod_count(const int32_t *__restrict__ basin_f, const int32_t *__restrict__ acum, int n, int umbral,
+                            int32_t *__restrict__ cauce, int32_t *__restrict__ nodos, int *__restrict__ n_cauce) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = 0;
+    if (i < n) {
+        c = (acum[i] >= umbral) ? 1 : 0;
+        cauce[i] = c;
+        const int d = basin_f[3 * (size_t)i];
+        if (d != 0 && c) atomicAdd(&nodos[n - d], 1);   // channel cells draining into the cell (:1356-1363)
+    }
+    c = warp_sum_i(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(n_cauce, c);
+}
+__global__ void k_nod_class(const int32_t *__restrict__ cauce, int n, int32_t *__restrict__ nodos, int *__restrict__ n_nodos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = 0;
+    if (i < n) {
+        int v = nodos[i];
+        if (v == 0 && cauce[i] == 1) v = 3;             // channel heads (:1365)
+        if (i == n - 1) v = 2;                          // the outlet is a node too (:1366)
+        if (v < 2) v = 0;                               // cells with a single channel tributary are not nodes (:1367)
+        nodos[i] = v;
+        k = v > 0 ? 1 : 0;
+    }
+    k = warp_sum_i(k);
+    if ((threadIdx.x & 31) == 0 && k) atomicAdd(n_nodos, k);
+}
+__global__ void k_nod_trazado(const int32_t *__restrict__ basin_f, const int32_t *__restrict__ cauce,
+                              const int32_t *__restrict__ nodos, int n, int32_t *__restrict__ trazado) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d = basin_f[3 * (size_t)i];
+    int t = (d != 0 && nodos[n - d] != 0 && cauce[i] == 1) ? 1 : 0;   // :1371-1377
+    if (i == n - 1) t = 1;
+    trazado[i] = t;
+}
+
+extern "C" int wmf_basin_stream_nod(wmf_ctx *ctx, const int32_t *basin_f, const int32_t *acum, int32_t n, int32_t umbral,
+                                    int32_t *cauce, int32_t *nodos, int32_t *trazado, int32_t *n_nodos, int32_t *n_cauce) {
+    if (!ctx || !basin_f || !acum || !cauce || !nodos || !trazado || n <= 0) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    const int32_t *d_b, *d_a;
+    int32_t *d_c, *d_n, *d_t;
+    int *d_cnt;
+    WMF_TRY(sc.in(basin_f, (size_t)3 * n, &d_b));
+    WMF_TRY(sc.in(acum, (size_t)n, &d_a));
+    WMF_TRY(sc.out(cauce, (size_t)n, &d_c));
+    WMF_TRY(sc.out(nodos, (size_t)n, &d_n));
+    WMF_TRY(sc.out(trazado, (size_t)n, &d_t));
+    WMF_TRY(sc.alloc(&d_cnt, 2));
+    CU_TRY(ctx, cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(d_n, 0, sizeof(int32_t) * (size_t)n, ctx->stream));
+    const int G = grid_for(n, 256);
+    LAUNCH(ctx, k_nod_count, G, 256, 0, d_b, d_a, n, umbral, d_c, d_n, d_cnt);
+    LAUNCH(ctx, k_nod_class, G, 256, 0, d_c, n, d_n, d_cnt + 1);
+    LAUNCH(ctx, k_nod_trazado, G, 256, 0, d_b, d_c, d_n, n, d_t);
+    int h[2] = {0, 0};
+    CU_TRY(ctx, cudaMemcpyAsync(h, d_cnt, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    WMF_TRY(sc.finish());
+    if (n_cauce) *n_cauce = h[0];
+    if (n_nodos) *n_nodos = h[1];
+    return WMF_OK;
+}
+
 int wmf_basin_stream_mask(wmf_ctx *ctx, const int32_t *acum, int32_t n, int32_t umbral, int32_t *cauce, int32_t *n_cauce) {
     return threshold_mask(ctx, acum, n, umbral, 1, cauce, n_cauce);
 }
