@@ -401,3 +401,21 @@ def test_separate_fluxes():
     m0, ret0 = run_gpu(inp, dict(separate_fluxes=0))
     assert not ret0[2].any()
     np.testing.assert_array_equal(ret0[0], ret[0])
+
+
+def test_channel_cell_draining_into_hillslope_cell():
+    """Unit types are user input: a channel cell may drain into a hillslope cell, whose tank 5 then fills and never
+    drains (modelosv2.f90:617-621, 672): no kernel may assume that a hillslope cell's tank 5 is a constant of the run."""
+    bs, inp = build("G2", 80, 70, 26, n_reg=60)
+    ut = np.array(inp["unit_type"], copy=True).reshape(-1)
+    d = np.asarray(inp["drena"]).reshape(3, -1, order="F")[0] if np.asarray(inp["drena"]).ndim == 2 else np.asarray(inp["drena"])
+    n = ut.size
+    ch = np.nonzero((ut > 1) & (d > 0))[0]
+    pick = ch[len(ch) // 2]
+    par = n - d[pick]
+    ut[par] = 1                                   # a hillslope cell in the middle of the channel network
+    inp["unit_type"] = ut[None, :]
+    m, ret = run_gpu(inp)
+    ref = run_oracle(inp)
+    compare_core(ret, m, ref, bs["n"])
+    assert ret[9][4, par] > inp["storage"][4, par]          # its channel tank did receive water
