@@ -4,14 +4,20 @@
 //   Cells are bucketed by hop distance to the outlet ("level"; basin_find's ordering makes each level a
 //   contiguous index range and the children of a cell a contiguous index range).  Cell (level L, step t)
 //   depends only on its children at the same step (level L+1) and on itself at step t-1, so all (L,t) with
-//   t + (Lmax - L) == w are independent: wave w is ONE kernel launch over a contiguous cell range, and the
-//   whole run takes T + Lmax launches instead of T * Lmax barriers.
+//   t + (Lmax - L) == w are independent: wave w is ONE kernel launch over a contiguous cell range.
 //   Each thread owns one (cell, member): it gathers its children's outflows of the same step in ascending
 //   cell order (== the Fortran's sequential fp32 addition order, no atomics on water), runs the vertical
-//   tank cascade and the three hillslope outflows with the state in registers, solves the channel kinematic
-//   wave, and publishes its own outflow into a buffer double-buffered on the step parity.
-// Memory: SoA, member-minor: state[tank][cell][member]; static maps are read in their f2py (K,N) layout,
-//   which is one aligned float4 per cell; rainfall records stay resident in HBM and are indexed per step.
+//   tank cascade and the three hillslope outflows, solves the channel kinematic wave, and publishes its own
+//   outflow into a ring double-buffered on the parity of the time block.
+// Two kernels implement it:
+//   k_shia_tb    the product path: K steps per launch per thread (state in registers for the block, parameters
+//                derived once per block, programmatic dependent launch between waves, hillslope and channel cells
+//                in different warps); template flags add sediments, slides, state dumps and flux separation.
+//                AoS state: float4 st4[cell][member] (tanks 1-4) + s5; ring float4 outb4[2][K][cell][member].
+//   k_shia_wave  the first generation, one step per launch, SoA state[tank][cell][member]; serves the per-step
+//                mean outputs (show_storage, show_mean_speed, mean_retorno) and cross-checks k_shia_tb in the tests.
+// Static maps are read in their f2py (K,N) layout (one aligned float4 per cell); rainfall records stay resident in HBM
+// (or stream in from pinned host memory next to the sweep, see RainStream) and are indexed per step.
 // Reductions (balance, means) are accumulated in fp64 per step slot.
 #include <limits.h>
 #include <math.h>
