@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define WMF_ABI_VERSION 3
+#define WMF_ABI_VERSION 4
 
 enum {
     WMF_OK = 0,
@@ -144,6 +144,9 @@ typedef struct {
     int32_t save_storage, save_speed;
     /* module separate_fluxes (modelosv2.f90:90): track the runoff / subsurface / base-flow shares of the channel water */
     int32_t separate_fluxes;
+    /* module save_vfluxes / save_rc (modelosv2.f90:83, :392-426): vertical-flux dumps + mean_vfluxes, and the two
+     * runoff-coefficient accumulators; save_retorno (above) returns the per-step return-flow map */
+    int32_t save_vfluxes, save_rc;
 } wmf_shia_cfg;
 
 /* Arrays = module `models` allocatables (modelosv2.f90:53-113) in their f2py layouts. */
@@ -174,6 +177,8 @@ typedef struct {
     /* module guarda_cond (n_reg): > 0 = dump StoOut after that step (the value is the record number the caller writes
      * it to, wmf.py:4497-4505); needed when save_storage = 1 */
     const int32_t *guarda_cond;
+    /* module guarda_vfluxes (n_reg), same convention, for save_vfluxes = 1; NULL = no step is dumped (:399-401) */
+    const int32_t *guarda_vfluxes;
 } wmf_shia_inputs;
 
 /* Outputs.  Any pointer may be NULL (= not wanted).  Shapes as returned by f2py (modelsmodule.c:375-408).
@@ -206,6 +211,14 @@ typedef struct {
     float *speed_snap;
     /* separate_fluxes = 1: Qseparated (n_cont, 3, n_reg), modelosv2.f90:697-704, 752-759 */
     float *qseparated;
+    /* save_vfluxes = 1: mean_vfluxes (4, n_reg) = sum(vfluxes,dim=2)/N_cel of every step (:807-809; fp64 sums on the
+     * GPU, rounded once) and the vfluxes map (4,N) of every step with guarda_vfluxes > 0, in step order:
+     * (n_vsnap, 4, N) -- what write_float_basin(ruta_vfluxes, vfluxes, guarda_vfluxes(t), N_cel, 4) writes (:811-813) */
+    float *mean_vfluxes, *vfl_snap;
+    /* save_rc = 1: rc_coef (2,N) after the final clamp rc(1) = min(rc(1), rc(2)) (:521-524, :863-867) */
+    float *rc_coef;
+    /* save_retorno = 1: Retorned of every step, (n_reg, N) -- record t of ruta_retorno (:820-823) */
+    float *ret_snap;
 } wmf_shia_outputs;
 
 /* shia_v1, modelosv2.f90:191-869 (+ calc_speed :1278-1293, sed_* :1298-1608, slide_* :1613-1707). */

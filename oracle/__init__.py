@@ -89,6 +89,7 @@ class ShiaOut(C.Structure):
         ("mean_storage", f32p), ("mean_speed", f32p), ("mean_retorno", f32p), ("retorned", f32p),
         ("mean_vfluxes", f32p), ("rc_coef", f32p),
         ("mean_storage64", f64p), ("mean_speed64", f64p), ("mean_retorno64", f64p),
+        ("mean_vfluxes64", f64p), ("vfluxes_last", f32p), ("retorned_last", f32p),
         ("vs", f32p), ("vd", f32p), ("vsc", f32p), ("vdc", f32p), ("volero", f32p), ("voldepo", f32p),
         ("erot", f32p), ("dept", f32p), ("erot64", f64p), ("dept64", f64p),
         ("sl_zmin", f32p), ("sl_zcrit", f32p), ("sl_zmax", f32p), ("sl_bo", f32p),
@@ -423,6 +424,9 @@ def shia_v1(inp: dict, fast: bool = False) -> dict:
     out("mean_storage64", (5, T), np.float64, f64p)
     out("mean_speed64", (4, T), np.float64, f64p)
     out("mean_retorno64", (T,), np.float64, f64p)
+    out("mean_vfluxes64", (4, T), np.float64, f64p)
+    out("vfluxes_last", (4, N))
+    out("retorned_last", (N,))
     if sed:
         for k in ("vs", "vd", "vsc", "vdc"):
             out(k, (3, N))

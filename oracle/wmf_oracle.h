@@ -133,6 +133,9 @@ typedef struct {
     /* fp64-accumulated twins of the three per-step means (diagnostic, may be NULL): the reference's
        sequential fp32 sums carry an error of order N*eps, these do not */
     double *mean_storage64, *mean_speed64, *mean_retorno64;
+    double *mean_vfluxes64;  /* (4,n_reg) fp64 twin of mean_vfluxes (may be NULL) */
+    float *vfluxes_last;     /* (4,N) the vfluxes map after the last step (what a dump of that step holds), may be NULL */
+    float *retorned_last;    /* (N) Retorned after the last step, before the per-step reset (:841-843) = the record save_retorno writes for that step; may be NULL */
     /* sediments */
     float *vs, *vd, *vsc, *vdc; /* (3,N) */
     float *volero, *voldepo;    /* (N) */

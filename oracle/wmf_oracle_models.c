@@ -525,9 +525,12 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
         if (vfl_map && out->mean_vfluxes)
             for (int k = 0; k < 4; ++k) {
                 float s = 0.0f;
-                for (int32_t i = 0; i < N; ++i) s += A4(vfl_map, k, i);
+                double s64 = 0.0;
+                for (int32_t i = 0; i < N; ++i) { s += A4(vfl_map, k, i); s64 += (double)A4(vfl_map, k, i); }
                 out->mean_vfluxes[4 * (size_t)t + k] = s / (float)N;
+                if (out->mean_vfluxes64) out->mean_vfluxes64[4 * (size_t)t + k] = s64 / (double)N;
             }
+        if (vfl_map && out->vfluxes_last && t == T - 1) memcpy(out->vfluxes_last, vfl_map, sizeof(float) * 4 * (size_t)N);
         if (in->show_storage == 1 && out->mean_storage)
             for (int k = 0; k < 5; ++k) {
                 float s = 0.0f;
@@ -555,6 +558,7 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
             out->mean_retorno[t] = sum_f(out->retorned, (size_t)N) / (float)N;
             if (out->mean_retorno64) out->mean_retorno64[t] = sum_d(out->retorned, (size_t)N) / (double)N;
         }
+        if (out->retorned_last && out->retorned && t == T - 1) memcpy(out->retorned_last, out->retorned, sizeof(float) * (size_t)N);
         if ((in->show_mean_retorno == 1 || in->save_retorno == 1) && out->retorned && in->retorno_gr == 1.0f)
             for (int32_t i = 0; i < N; ++i) out->retorned[i] = 0.0f;
         out->balance[t] = sum_f(Sto, 5 * (size_t)N) - StoAtras - entradas + salidas;

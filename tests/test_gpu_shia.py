@@ -357,6 +357,59 @@ def test_storage_and_speed_dumps(tmp_path):
     assert os.path.getsize(spd_path) == 4 * 4 * N * T and os.path.getsize(sto_path) == 4 * 5 * N * 3
 
 
+@pytest.mark.parametrize("show_means", [0, 1])
+def test_vfluxes_rc_retorno_dumps(tmp_path, show_means):
+    """save_vfluxes / save_rc / save_retorno (modelosv2.f90:515-524, 806-823, 863-867): record guarda_vfluxes(t) of the
+    vfluxes file holds the four vertical fluxes of step t (vflux 2 and 3 carrying the return flow, :510-511), record t of
+    the retorno file the return flow of that step, the rc file the two runoff-coefficient accumulators after the final
+    clamp; mean_vfluxes is the per-step mean.  ``show_means`` = 1 sends the run through the one-step kernel."""
+    from wmf_b200 import ModelsModule, synth
+    from wmf_b200._models import read_float_basin_ncol
+    bs, inp = build("G2", 90, 70, 27, n_reg=40, retorno_gr=1, rain_peak_mm=40.0)
+    inp["calib"][9] = 0.02                           # small gravitational capacity: tank 3 does spill back into tank 2
+    N, T = bs["n"], 40
+    steps = (3, 20, 39)
+    guarda = np.zeros(T, np.int32)
+    guarda[list(steps)] = [1, 2, 3]
+    flags = dict(save_vfluxes=1, save_rc=1, save_retorno=1, show_storage=show_means)
+    m = ModelsModule()
+    synth.apply_to_models(m, inp)
+    m.set_rain(inp["rain"], inp["pos_evento"])
+    for k, v in flags.items():
+        setattr(m, k, v)
+    m.guarda_vfluxes = guarda
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    pv, pr, pc = str(tmp_path / "vf.bin"), str(tmp_path / "ret.bin"), str(tmp_path / "rc.bin")
+    ret = m.shia_v1(None, None, inp["calib"], n_cont, 1, T, None, None, N, None, None, pv, None, None, None, None, pr, pc)
+    ref = run_oracle(inp, flags)
+    compare_core(ret, m, ref, N)
+    close(m.mean_vfluxes, ref["mean_vfluxes64"], name="mean_vfluxes")
+    close(ref["mean_vfluxes"], ref["mean_vfluxes64"], rtol=N * 6e-8, name="oracle fp32 vs fp64 mean_vfluxes")
+    close(m.rc_coef, ref["rc_coef"], name="rc_coef")
+    rc_file, res = read_float_basin_ncol(pc, 1, N, 2)
+    assert res == 0
+    np.testing.assert_array_equal(rc_file, m.rc_coef)
+    assert (ref["rc_coef"][0] <= ref["rc_coef"][1]).all() and ref["rc_coef"][0].max() > 0
+    assert not m.retorned.any()                      # Retorned is reset after every step in this mode (:841-843)
+    seen_return = False
+    for t, rec in zip(steps, (1, 2, 3)):
+        a = dict(inp); a["n_reg"] = t + 1; a["pos_evento"] = inp["pos_evento"][:t + 1]; a["evpserie"] = inp["evpserie"][:t + 1]
+        part = run_oracle(a, flags)
+        got, res = read_float_basin_ncol(pv, rec, N, 4)
+        assert res == 0
+        close(got, part["vfluxes_last"], name=f"vfluxes record {rec}")
+        r, res = read_float_basin_ncol(pr, t + 1, N, 1)
+        assert res == 0
+        close(r.reshape(-1), part["retorned_last"], name=f"retorno record {t + 1}")
+        seen_return |= bool(part["retorned_last"].max() > 0)
+    assert seen_return
+    assert os.path.getsize(pv) == 4 * 4 * N * 3 and os.path.getsize(pr) == 4 * N * T and os.path.getsize(pc) == 4 * 2 * N
+    # the dumps do not perturb the run
+    m0, ret0 = run_gpu(inp, dict(show_storage=show_means))
+    np.testing.assert_array_equal(ret0[0], ret[0])
+    np.testing.assert_array_equal(ret0[9], ret[9])
+
+
 def test_shia_on_random_partial_basin():
     """SHIA on the irregular tree of a random partial basin (pits, holes, up to 6-8 cells draining into one, several
     channel heads): same tolerance as the regular generators."""

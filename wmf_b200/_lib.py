@@ -41,6 +41,7 @@ class ShiaCfg(C.Structure):
         ("sl_gullienogullie", C.c_int32), ("sl_fs", C.c_float), ("sl_gammaw", C.c_float),
         ("n_members", C.c_int32),
         ("save_storage", C.c_int32), ("save_speed", C.c_int32), ("separate_fluxes", C.c_int32),
+        ("save_vfluxes", C.c_int32), ("save_rc", C.c_int32),
     ]
 
 
@@ -59,7 +60,7 @@ class ShiaInputs(C.Structure):
         ("vd_init", C.c_void_p),
         ("sl_zs", C.c_void_p), ("sl_gammas", C.c_void_p), ("sl_cohesion", C.c_void_p),
         ("sl_frictionangle", C.c_void_p), ("sl_radslope", C.c_void_p),
-        ("guarda_cond", C.c_void_p),
+        ("guarda_cond", C.c_void_p), ("guarda_vfluxes", C.c_void_p),
     ]
 
 
@@ -69,6 +70,7 @@ _OUT_NAMES = [
     "vs", "vd", "vsc", "vdc", "volero", "voldepo", "erot", "dept",
     "sl_zmin", "sl_zcrit", "sl_zmax", "sl_bo", "sl_riskvector", "sl_slideocurrence",
     "sl_slideacumulate", "sl_slidencelltime", "sto_snap", "speed_snap", "qseparated",
+    "mean_vfluxes", "vfl_snap", "rc_coef", "ret_snap",
 ]
 
 

@@ -46,7 +46,7 @@ _SCALARS_I = {"nceldas": 0, "ncols": 0, "nrows": 0, "verbose": 0, "rain_first_po
               "show_mean_speed": 0, "show_mean_retorno": 0, "show_area": 0, "separate_fluxes": 0,
               "separate_rain": 0, "sl_gullienogullie": 0}
 # switches whose sub-models are outside the hot path built here
-_UNSUPPORTED = ("sim_floods", "save_retorno", "save_vfluxes", "save_rc", "separate_rain")
+_UNSUPPORTED = ("sim_floods", "separate_rain")
 
 
 def read_rain_hdr(ruta_hdr: str, n_reg: int, rain_first_point: int = 1):
@@ -295,6 +295,13 @@ class ModelsModule:
             raise ValueError("models.save_storage = 1 needs ruta_storage (modelosv2.f90:799-803)")
         if save_spd and not ruta_speed:
             raise ValueError("models.save_speed = 1 needs ruta_speed (modelosv2.f90:815-818)")
+        save_vfl, save_rc, save_ret = int(self.save_vfluxes) == 1, int(self.save_rc) == 1, int(self.save_retorno) == 1
+        if save_vfl and not ruta_vfluxes:
+            raise ValueError("models.save_vfluxes = 1 needs ruta_vfluxes (modelosv2.f90:806-813)")
+        if save_rc and not ruta_rc:
+            raise ValueError("models.save_rc = 1 needs ruta_rc (modelosv2.f90:863-867)")
+        if save_ret and not ruta_retorno:
+            raise ValueError("models.save_retorno = 1 needs ruta_retorno (modelosv2.f90:820-823)")
         out = self._run(calib[None, :], int(n_cont), int(n_conth), T, rain, pos, stoin, hspeedin)
         # state dumps in the reference's direct-access format: record guarda_cond(t) of ruta_storage holds StoOut(5,N)
         # after step t; record t of ruta_speed holds hspeed(4,N)
@@ -305,11 +312,29 @@ class ModelsModule:
         if save_spd:
             for t in range(T):
                 write_float_basin(str(ruta_speed).strip(), out["speed_snap"][:, :, t], t + 1, N, 4)
+        # record guarda_vfluxes(t) of ruta_vfluxes holds vfluxes(4,N) of step t (:811-813); record t of ruta_retorno the
+        # return flow of step t (:820-823); record 1 of ruta_rc the two runoff-coefficient accumulators (:863-867)
+        if save_vfl and "vfl_snap" in out:
+            g = self._guarda("guarda_vfluxes", T)
+            for k, t in enumerate(np.nonzero(g > 0)[0]):
+                write_float_basin(str(ruta_vfluxes).strip(), out["vfl_snap"][:, :, k], int(g[t]), N, 4)
+        if save_ret:
+            for t in range(T):
+                write_float_basin(str(ruta_retorno).strip(), out["ret_snap"][:, t][None, :], t + 1, N, 1)
+        if save_rc:
+            write_float_basin(str(ruta_rc).strip(), out["rc_coef"], 1, N, 2)
         nc, nh = int(n_cont), int(n_conth)
         zeros = lambda *s: np.zeros(s, np.float32, order="F")
         qsed = out.get("qsed", zeros(nc, 3, T))
         return (out["q"], qsed, out.get("qseparated", zeros(nc, 3, T)), out["hum"], out["st1"], out["st3"], out["balance"], out["speed"],
                 out["areacontrol"], out["stoout"], zeros(nc, 2, T))
+
+    def _guarda(self, name, T):
+        """guarda_vfluxes as shia_v1 sees it: allocated with >= n_reg entries, else "all zeros" (modelosv2.f90:399-409)."""
+        g = object.__getattribute__(self, "__dict__")["_a"].get(name)
+        if g is None or g.size < T:
+            return np.zeros(T, np.int32)
+        return np.ascontiguousarray(g.reshape(-1)[:T], np.int32)
 
     def _cell(self, name, K, N, dtype, required=True):
         a = object.__getattribute__(self, "__dict__")["_a"]
@@ -346,6 +371,10 @@ class ModelsModule:
         cfg.save_storage = int(self.save_storage) if M == 1 else 0
         cfg.save_speed = int(self.save_speed) if M == 1 else 0
         cfg.separate_fluxes = int(self.separate_fluxes) if M == 1 else 0
+        cfg.save_vfluxes = int(self.save_vfluxes) if M == 1 else 0
+        cfg.save_rc = int(self.save_rc) if M == 1 else 0
+        if M != 1:
+            cfg.save_retorno = 0
         keep = []
         si = ShiaInputs()
 
@@ -404,6 +433,11 @@ class ModelsModule:
             g = np.ascontiguousarray(g.reshape(-1)[:T], np.int32)
             n_snap = int(np.count_nonzero(g > 0))
             put("guarda_cond", g)
+        n_vsnap = 0
+        if cfg.save_vfluxes == 1:
+            g = self._guarda("guarda_vfluxes", T)
+            n_vsnap = int(np.count_nonzero(g > 0))
+            put("guarda_vfluxes", g)
         sed, sl = cfg.sim_sediments == 1, cfg.sim_slides == 1
         if sed:
             for k in ("krus", "crus", "prus"):
@@ -440,6 +474,14 @@ class ModelsModule:
                 out("sto_snap", (5, N, max(n_snap, 1)))
             if cfg.save_speed == 1:
                 out("speed_snap", (4, N, T))
+            if cfg.save_vfluxes == 1:
+                out("mean_vfluxes", (4, T))
+                if n_vsnap:
+                    out("vfl_snap", (4, N, n_vsnap))
+            if cfg.save_rc == 1:
+                out("rc_coef", (2, N))
+            if cfg.save_retorno == 1:
+                out("ret_snap", (N, T))
             if cfg.show_storage:
                 out("mean_storage", (5, T))
             if cfg.show_mean_speed:
@@ -466,7 +508,8 @@ class ModelsModule:
         # module-global results the reference leaves behind (read back at wmf.py:4548-4601)
         if M == 1 and not device_out:
             d = object.__getattribute__(self, "__dict__")
-            for k in ("mean_rain", "acum_rain", "mean_storage", "mean_speed", "mean_retorno", "retorned", "vs", "vd",
+            for k in ("mean_rain", "acum_rain", "mean_storage", "mean_speed", "mean_retorno", "mean_vfluxes", "rc_coef",
+                      "retorned", "vs", "vd",
                       "vsc", "vdc", "volero", "voldepo", "sl_zmin", "sl_zcrit", "sl_zmax", "sl_bo", "sl_riskvector",
                       "sl_slideocurrence", "sl_slideacumulate", "sl_slidencelltime"):
                 if k in res:

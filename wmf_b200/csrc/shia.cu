@@ -35,7 +35,7 @@ constexpr int WAVE_THREADS = 256;
 #endif
 constexpr int RED_SUB = 8;  // sub-slots per (step, quantity) to spread atomic traffic
 // reduction quantities per step
-enum { RQ_SAL = 0, RQ_STO1 = 1 /* ..5 */, RQ_SPD1 = 6 /* ..9 */, RQ_RET = 10, RQ_COUNT = 11 };
+enum { RQ_SAL = 0, RQ_STO1 = 1 /* ..5 */, RQ_SPD1 = 6 /* ..9 */, RQ_RET = 10, RQ_VFL1 = 11 /* ..14 */, RQ_COUNT = 15 };
 
 constexpr uint32_t TW_CTRLQ = 1u << 6, TW_CTRLH = 1u << 7;
 
@@ -98,6 +98,11 @@ struct ShiaP {
     const int32_t *snap_slot;
     float *sto_snap;        // [n_snap][N][5]
     float *spd_snap;        // [T][N][4]
+    const int32_t *vsnap_slot;  // like snap_slot, from guarda_vfluxes
+    float *vfl_snap;        // [n_vsnap][N][4] vertical fluxes of the flagged steps (save_vfluxes, :806-813)
+    int want_vmean;         // accumulate red[t][RQ_VFL1..4] = sum over the cells of the four vertical fluxes
+    float *rc;              // [2][N] save_rc accumulators (:521-524)
+    float *ret_snap;        // [T][N] return flow of every step (save_retorno, :820-823)
     // separate_fluxes (:658-680, :697-704, :752-759): shares of runoff / subsurface / base flow in the channel tank
     float *flx;             // [3][N][M]
     float4 *flxout4;        // [2][K][N][M] (share sent downstream x3, flag: 1 add, 0 "receiver's shares := 0", 2 hillslope cell)
@@ -297,6 +302,7 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
     const size_t NM = (size_t)N * M;
     const size_t base = (size_t)cell * M + m;
     double r_sal = 0.0, r_ret = 0.0;
+    double r_vf[4] = {0.0, 0.0, 0.0, 0.0};  // this step's vertical fluxes (mean_vfluxes)
     float sed_ero[3] = {0, 0, 0}, sed_dep[3] = {0, 0, 0};
     float S[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     float h[4] = {0.f, 0.f, 0.f, 0.f};
@@ -381,13 +387,30 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
             S[2] = S[2] + Ret_aq;
             S[3] = S[3] - Ret_aq;
         }
+        float ret_step = 0.0f;
         if (P.retorno_gr > 0.0f) {
             const float Ret = fmaxf(0.0f, S[2] - H2);
             S[1] = S[1] + Ret;
             S[2] = S[2] - Ret;
+            ret_step = Ret;
             if (P.want_retorned) {
                 if (P.retorned) P.retorned[cell] = P.retorned[cell] + Ret;
                 r_ret = (double)Ret;
+            }
+        }
+        if (P.want_vmean | (P.vfl_snap != nullptr) | (P.rc != nullptr) | (P.ret_snap != nullptr)) {
+            // the dumps that follow the vertical fluxes; vflux(2:3) carry the return flow (:509-524)
+            const float vx2 = (P.retorno_gr > 0.0f) ? vf2 + ret_step : vf2;
+            const float vx3 = (P.retorno_gr > 0.0f) ? vf3 - ret_step : vf3;
+            r_vf[0] = (double)vf1; r_vf[1] = (double)vx2; r_vf[2] = (double)vx3; r_vf[3] = (double)vf4;
+            if (P.rc) {
+                P.rc[cell] = P.rc[cell] + vx2 - vx3;
+                P.rc[(size_t)N + cell] = P.rc[(size_t)N + cell] + R;
+            }
+            if (P.ret_snap) P.ret_snap[(size_t)t * N + cell] = ret_step;
+            if (P.vfl_snap) {
+                const int sl = __ldg(P.vsnap_slot + t);
+                if (sl >= 0) reinterpret_cast<float4 *>(P.vfl_snap)[(size_t)sl * N + cell] = make_float4(vf1, vx2, vx3, vf4);
             }
         }
         r_sal = (double)vf4 + (double)E;
@@ -608,7 +631,7 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
         }
     }
     // ---- per-step reductions (balance :846, mean_storage :828, mean_speed :833, mean_retorno :838) ----
-    if (P.want_red && P.M == 1) {
+    if ((P.want_red | P.want_vmean) && P.M == 1) {
         // steps are monotone along the cell index, so a warp (usually a whole block) shares one step
         const unsigned full = 0xffffffffu;
         const int t0 = __shfl_sync(full, t, 0);
@@ -650,6 +673,13 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
                     const double c = warp_sum_d(r_ret);
                     if (lead) flush(c, RQ_RET, t0);
                 }
+                if (P.want_vmean) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double c = warp_sum_d(r_vf[k]);
+                        if (lead) flush(c, RQ_VFL1 + k, t0);
+                    }
+                }
             }
         } else if (t >= 0 && active) {
             flush(r_sal, RQ_SAL, t);
@@ -663,6 +693,9 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
 #pragma unroll
                 for (int k = 0; k < 4; ++k) flush(spd(k), RQ_SPD1 + k, t);
             if (P.want_retorned) flush(r_ret, RQ_RET, t);
+            if (P.want_vmean)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) flush(r_vf[k], RQ_VFL1 + k, t);
         }
     }
     if (SED) {  // EROt / DEPt (:1403, :1420): global totals, fp64
@@ -812,6 +845,8 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
         sl_slid = P.sl_slid[cell];
         sl_mark = P.sl_marktime[cell];
     }
+    float rc1 = 0.f, rc2 = 0.f;           // save_rc accumulators
+    if (SNAP && active && P.rc) { rc1 = P.rc[cell]; rc2 = P.rc[(size_t)N + cell]; }
     float F0 = 0.f, F1 = 0.f, F2 = 0.f;  // separate_fluxes: the channel tank's shares
     if (SEPF && CHAN && active) { F0 = P.flx[base]; F1 = P.flx[NM + base]; F2 = P.flx[2 * NM + base]; }
     const bool outlet = active && (cell == N - 1);
@@ -821,6 +856,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
 #pragma unroll 1
     for (int tt = 0; tt < K; ++tt) {
         float dq = 0.0f;
+        float vx1 = 0.f, vx2 = 0.f, vx3 = 0.f, vx4 = 0.f;  // this step's vertical fluxes (dump variants only)
         if (tt < nt) {
             const int t = t0 + tt;
             const float So0 = S0, So1 = S1, So2 = S2, So3 = S3, So4 = S4;
@@ -896,11 +932,24 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                 S2 = S2 + Ret_aq;
                 S3 = S3 - Ret_aq;
             }
+            float ret_step = 0.0f;
             if (P.retorno_gr > 0.0f) {
                 const float Ret = fmaxf(0.0f, S2 - H2);
                 S1 = S1 + Ret;
                 S2 = S2 - Ret;
                 ret_acc = ret_acc + Ret;
+                ret_step = Ret;
+            }
+            if (SNAP) {  // the dumps that follow the vertical fluxes; vflux(2:3) carry the return flow (:509-510)
+                vx1 = vf1; vx4 = vf4;
+                vx2 = (P.retorno_gr > 0.0f) ? vf2 + ret_step : vf2;
+                vx3 = (P.retorno_gr > 0.0f) ? vf3 - ret_step : vf3;
+                if (P.rc) { rc1 = rc1 + vx2 - vx3; rc2 = rc2 + R; }               // :521-524
+                if (P.ret_snap) P.ret_snap[(size_t)t * N + cell] = ret_step;     // :820-823 (Retorned is zeroed every step)
+                if (P.vfl_snap) {
+                    const int sl = __ldg(P.vsnap_slot + t);
+                    if (sl >= 0) reinterpret_cast<float4 *>(P.vfl_snap)[(size_t)sl * N + cell] = make_float4(vx1, vx2, vx3, vx4);
+                }
             }
             float sal = vf4 + E;
             // hillslope outflows of tanks 2..4 (:553-595)
@@ -1071,6 +1120,23 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             dq = (((S0 - So0) + (S1 - So1)) + ((S2 - So2) + (S3 - So3))) + (S4 - So4) + sal;
         }
         if (P.want_red) s_acc[tt * TB_THREADS + threadIdx.x] = dq;
+        if (SNAP && P.want_vmean) {  // mean_vfluxes (:807-809): fp64 sums per step; one atomic per warp when it shares the step
+            const unsigned full = 0xffffffffu;
+            const int ts = (tt < nt) ? t0 + tt : -1;
+            const int tl = __shfl_sync(full, ts, 0);
+            const bool same = __all_sync(full, ts == tl);
+            const float vx[4] = {vx1, vx2, vx3, vx4};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (same) {
+                    const double a = warp_sum_d((double)vx[k]);
+                    if ((threadIdx.x & 31) == 0 && tl >= 0 && a != 0.0)
+                        atomicAdd(P.red + ((size_t)tl * RQ_COUNT + RQ_VFL1 + k) * RED_SUB + (blockIdx.x & (RED_SUB - 1)), a);
+                } else if (ts >= 0 && vx[k] != 0.0f) {
+                    atomicAdd(P.red + ((size_t)ts * RQ_COUNT + RQ_VFL1 + k) * RED_SUB + (blockIdx.x & (RED_SUB - 1)), (double)vx[k]);
+                }
+            }
+        }
         ob_in += NM;   // next step's slice of the ring
         ob_out += NM;
     }
@@ -1095,6 +1161,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
         }
         if (SLIDES) P.sl_slid[cell] = sl_slid;
         if (SEPF && CHAN) { P.flx[base] = F0; P.flx[NM + base] = F1; P.flx[2 * NM + base] = F2; }
+        if (SNAP && P.rc) { P.rc[cell] = rc1; P.rc[(size_t)N + cell] = rc2; }
     }
     if (SED) {  // EROt / DEPt (:1403, :1420): global totals, fp64
 #pragma unroll
@@ -1372,7 +1439,7 @@ __global__ void k_shia_epilogue(const double *__restrict__ red, const double *__
                                 int show_storage, int bal_direct, float *__restrict__ balance,
                                 float *__restrict__ mean_rain,
                                 float *__restrict__ mean_storage, float *__restrict__ mean_speed,
-                                float *__restrict__ mean_retorno) {
+                                float *__restrict__ mean_retorno, float *__restrict__ mean_vfluxes) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     auto q = [&](int tt, int k) {
@@ -1398,6 +1465,16 @@ __global__ void k_shia_epilogue(const double *__restrict__ red, const double *__
     if (mean_speed)
         for (int k = 0; k < 4; ++k) mean_speed[4 * (size_t)t + k] = (float)(q(t, RQ_SPD1 + k) / (double)n);
     if (mean_retorno) mean_retorno[t] = (float)(q(t, RQ_RET) / (double)n);
+    if (mean_vfluxes)
+        for (int k = 0; k < 4; ++k) mean_vfluxes[4 * (size_t)t + k] = (float)(q(t, RQ_VFL1 + k) / (double)n);
+}
+
+// save_rc epilogue (:863-867): rc(1) = min(rc(1), rc(2)), SoA accumulators -> the (2,N) f2py layout
+__global__ void k_rc_final(const float *__restrict__ rc, int N, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float a = rc[i], b = rc[(size_t)N + i];
+    reinterpret_cast<float2 *>(out)[i] = make_float2(a > b ? b : a, b);
 }
 
 // slide_allocate, modelosv2.f90:1613-1648
@@ -1923,7 +2000,10 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
         if (reserved > used) free_b += (size_t)(reserved - used);
         while (KT > 4 && (double)2 * KT * N * M * sizeof(float4) > 0.33 * (double)free_b) KT /= 2;
     }
-    const bool snap = (cfg->save_storage == 1 && out->sto_snap) || (cfg->save_speed == 1 && out->speed_snap);
+    const bool vdump = cfg->save_vfluxes == 1 && (out->vfl_snap || out->mean_vfluxes);
+    const bool rcdump = cfg->save_rc == 1 && out->rc_coef;
+    const bool retdump = cfg->save_retorno == 1 && out->ret_snap;
+    const bool snap = (cfg->save_storage == 1 && out->sto_snap) || (cfg->save_speed == 1 && out->speed_snap) || vdump || rcdump || retdump;
     if (KT && (sed || slides || snap)) KT = (T >= 4) ? 4 : 0;  // sediment / slide / dump variants are built for K = 4 only
     const bool sepf = cfg->separate_fluxes == 1;
     if (sepf) {
@@ -2011,29 +2091,59 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
         }
         P.want_red = (d_balance || d_mean_storage || d_mean_speed || d_mean_retorno) ? 1 : 0;
     }
-    if (P.want_red) {
+    float *d_mean_vfluxes = nullptr;
+    if (per_run && vdump && out->mean_vfluxes) {
+        WMF_TRY(sc.out(out->mean_vfluxes, (size_t)4 * T, &d_mean_vfluxes));
+        P.want_vmean = 1;
+    }
+    if (P.want_red || P.want_vmean) {
         WMF_TRY(sc.alloc(&P.red, (size_t)T * RQ_COUNT * RED_SUB));
         CU_TRY(ctx, cudaMemsetAsync(P.red, 0, sizeof(double) * (size_t)T * RQ_COUNT * RED_SUB, ctx->stream));
     }
     // ---- state dumps ----
+    float *d_rc_out = nullptr;
+    // guarda_* (n_reg): row of the snapshot table that receives each flagged step, -1 elsewhere
+    auto make_slots = [&](const int32_t *guarda, const int32_t **d_slot_out, int *n_out) -> int {
+        std::vector<int32_t> g((size_t)T, 0), slot((size_t)T);
+        if (guarda) {
+            if (Scope::on_device(guarda)) {
+                CU_TRY(ctx, cudaMemcpyAsync(g.data(), guarda, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, ctx->stream));
+                CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            } else {
+                memcpy(g.data(), guarda, sizeof(int32_t) * T);
+            }
+        }
+        int n = 0;
+        for (int t = 0; t < T; ++t) slot[t] = (g[t] > 0) ? n++ : -1;
+        int32_t *d_slot;
+        WMF_TRY(sc.alloc(&d_slot, (size_t)T));
+        CU_TRY(ctx, cudaMemcpyAsync(d_slot, slot.data(), sizeof(int32_t) * T, cudaMemcpyHostToDevice, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // `slot` goes out of scope
+        *d_slot_out = d_slot;
+        *n_out = n;
+        return WMF_OK;
+    };
+    if (vdump || rcdump || retdump) {
+        if (M != 1) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: save_vfluxes / save_rc / save_retorno need a single run (n_members = 1)");
+        if (vdump && out->vfl_snap) {
+            int n_vsnap = 0;
+            WMF_TRY(make_slots(in->guarda_vfluxes, &P.vsnap_slot, &n_vsnap));
+            WMF_TRY(sc.out(out->vfl_snap, (size_t)std::max(n_vsnap, 1) * 4 * N, &P.vfl_snap));
+            if (reinterpret_cast<uintptr_t>(P.vfl_snap) & 15) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: vfl_snap must be 16-byte aligned");
+        }
+        if (rcdump) {
+            WMF_TRY(sc.alloc(&P.rc, (size_t)2 * N));
+            CU_TRY(ctx, cudaMemsetAsync(P.rc, 0, sizeof(float) * 2 * (size_t)N, ctx->stream));  // rc_coef = 0 (:425)
+            WMF_TRY(sc.out(out->rc_coef, (size_t)2 * N, &d_rc_out));
+        }
+        if (retdump) WMF_TRY(sc.out(out->ret_snap, (size_t)T * N, &P.ret_snap));
+    }
     if (cfg->save_storage == 1 || cfg->save_speed == 1) {
         if (M != 1) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: save_storage / save_speed need a single run (n_members = 1)");
         if (cfg->save_storage == 1 && out->sto_snap) {
             if (!in->guarda_cond) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: save_storage = 1 needs guarda_cond");
-            std::vector<int32_t> g((size_t)T), slot((size_t)T);
-            if (Scope::on_device(in->guarda_cond)) {
-                CU_TRY(ctx, cudaMemcpyAsync(g.data(), in->guarda_cond, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, ctx->stream));
-                CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-            } else {
-                memcpy(g.data(), in->guarda_cond, sizeof(int32_t) * T);
-            }
             int n_snap = 0;
-            for (int t = 0; t < T; ++t) slot[t] = (g[t] > 0) ? n_snap++ : -1;
-            int32_t *d_slot;
-            WMF_TRY(sc.alloc(&d_slot, (size_t)T));
-            CU_TRY(ctx, cudaMemcpyAsync(d_slot, slot.data(), sizeof(int32_t) * T, cudaMemcpyHostToDevice, ctx->stream));
-            CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // `slot` goes out of scope
-            P.snap_slot = d_slot;
+            WMF_TRY(make_slots(in->guarda_cond, &P.snap_slot, &n_snap));
             WMF_TRY(sc.out(out->sto_snap, (size_t)std::max(n_snap, 1) * 5 * N, &P.sto_snap));
         }
         if (cfg->save_speed == 1 && out->speed_snap) {
@@ -2163,15 +2273,16 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
         if (KT) LAUNCH(ctx, k_state_final_tb, grid_for((long long)NM, B), B, 0, P, d_stoout, d_hsout);
         else LAUNCH(ctx, k_state_final, grid_for((long long)NM, B), B, 0, P, d_stoout, d_hsout);
     }
-    if (per_run && (d_balance || d_mean_rain || d_mean_storage || d_mean_speed || d_mean_retorno)) {
+    if (per_run && (d_balance || d_mean_rain || d_mean_storage || d_mean_speed || d_mean_retorno || d_mean_vfluxes)) {
         double *red = P.red;
         if (!red) {  // only mean_rain wanted
             WMF_TRY(sc.alloc(&red, (size_t)T * RQ_COUNT * RED_SUB));
             CU_TRY(ctx, cudaMemsetAsync(red, 0, sizeof(double) * (size_t)T * RQ_COUNT * RED_SUB, ctx->stream));
         }
         LAUNCH(ctx, k_shia_epilogue, grid_for(T, 128), 128, 0, red, d_recsum, P.pos, d_sto0, N, T, P.show_storage, P.bal_direct,
-               d_balance, d_mean_rain, d_mean_storage, d_mean_speed, d_mean_retorno);
+               d_balance, d_mean_rain, d_mean_storage, d_mean_speed, d_mean_retorno, d_mean_vfluxes);
     }
+    if (d_rc_out) LAUNCH(ctx, k_rc_final, G, B, 0, P.rc, N, d_rc_out);
     if (sed) {
         float *vs, *vd, *vsc, *vdc, *ve, *vdp, *erot, *dept;
         WMF_TRY(sc.out(out->vs, 3 * NM, &vs)); WMF_TRY(sc.out(out->vd, 3 * NM, &vd));
