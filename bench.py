@@ -17,7 +17,9 @@ Numbers on the JSON line
              DESIGN.md) / CUDA-event time of the wave launches, against the measured HBM copy bandwidth
              (MEASURED_PEAKS.json).  The kernel keeps a cell's state in registers for K steps and its per-step
              traffic is served from L2, so its DRAM traffic (`traffic`, from ncu) is well below the algorithmic bytes.
-  cpu_baseline  the CPU oracle (C restatement of the Fortran, -O3 -funroll-loops, 1 thread) on a bounded sample
+  cpu_baseline  the reference's own compiled Fortran (oracle/_ref: the gfortran -O3 -funroll-loops objects shipped in
+             the reference tree, kind "reference"; the oracle's C port when that library is absent), 1 thread as the
+             reference runs, on a bounded sample
   extra      Path A (basin_find+basin_cut+basin_acum) Mcell/s on the same raster, and run statistics
 """
 from __future__ import annotations
@@ -141,33 +143,63 @@ def bench_path_a(cu, wl, reps=3):
             "path_a_levels": cu.basin_find_depth(), "path_a_workload": f"{wl['nc']}x{wl['nr']} G2 raster, find+cut+acum"}
 
 
-def cpu_sample(wl, sample_steps, fast=True):
-    """(cell-steps/s, seconds) of the CPU oracle on the first ``sample_steps`` steps of the workload, 1 thread."""
-    import oracle
+def cpu_kind():
+    """"reference" when the reference's own compiled Fortran is loadable (oracle/_ref/libwmf_ref.so, built from the
+    objects in the reference tree and shipped to the GPU box), else "port" (the C restatement in oracle/)."""
+    from oracle import ref
+    return "reference" if ref.available() else "port"
+
+
+def cpu_prepare(wl, sample_steps, workdir):
+    """Inputs of a CPU sample: the first ``sample_steps`` steps of the workload; for the reference arm the rain table is
+    written to the .bin / .hdr pair the Fortran reads record by record (modelosv2.f90:444-449), outside the timed call."""
     inp = dict(wl["inp"])
     inp["n_reg"] = sample_steps
-    inp["pos_evento"] = inp["pos_evento"][:sample_steps]
+    inp["pos_evento"] = np.ascontiguousarray(inp["pos_evento"][:sample_steps])
     inp["evpserie"] = inp["evpserie"][:sample_steps]
+    files = None
+    if cpu_kind() == "reference":
+        from oracle import ref
+        files = (os.path.join(workdir, "rain.bin"), os.path.join(workdir, "rain.hdr"))
+        if not os.path.exists(files[0]):
+            ref.write_rain(files[0], files[1], inp["rain"], inp["pos_evento"])
+    return inp, files
+
+
+def cpu_sample(wl, sample_steps, workdir):
+    """(cell-steps/s, seconds) of the reference's CPU path on the first ``sample_steps`` steps of the workload, 1 thread."""
+    inp, files = cpu_prepare(wl, sample_steps, workdir)
     t0 = time.perf_counter()
-    oracle.shia_v1(inp, fast=fast)
+    if files is not None:
+        from oracle import ref
+        ref.shia_v1(inp, rain_files=files)
+    else:
+        import oracle
+        oracle.shia_v1(inp, fast=True)
     dt = time.perf_counter() - t0
     return wl["n"] * sample_steps / dt, dt
 
 
+def cpu_label():
+    return ("the reference's own compiled Fortran (gfortran 5.3.0 -O3 -funroll-loops objects from the reference tree, "
+            "oracle/_ref), rain read from its .bin file every step" if cpu_kind() == "reference"
+            else "oracle port -O3 -funroll-loops, rain in memory")
+
+
 def _ref_worker(args):
-    name, sample_steps = args
+    name, sample_steps, workdir = args
     os.environ["CUDA_VISIBLE_DEVICES"] = ""
     import oracle  # noqa: F401
     wl = _REF_WL[0]
-    return cpu_sample(wl, sample_steps)
+    return cpu_sample(wl, sample_steps, workdir)
 
 
 _REF_WL = [None]
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Fortran cannot be built here) on the host
-    cores.  The reference's only parallelism is one process per ensemble member (wmf.py:872-878), so all cores
+    """--impl reference: the reference's CPU implementation (its own compiled Fortran through oracle/_ref when that
+    library is present, else the oracle port) on the host cores.  The reference's only parallelism is one process per ensemble member (wmf.py:872-878), so all cores
     run one member each, on a bounded sample of the workload's steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -180,7 +212,8 @@ def run_reference(args):
     # the topology must come from somewhere that is not our GPU code: the oracle traces it
     from wmf_b200 import synth
     DIR, DEM = synth.make_raster(gen, nc, nr, seed=0)
-    ocu = oracle.Cu(fast=True)
+    from oracle import ref as _ref
+    ocu = _ref.RefCu() if _ref.available() else oracle.Cu(fast=True)
     ocu.ncols, ocu.nrows, ocu.xll, ocu.yll, ocu.dx, ocu.dy, ocu.dxp, ocu.nodata = nc, nr, 0.0, 0.0, DX, DX, DX, synth.NODATA
     x, y = synth.outlet_xy(nc, nr, 0.0, 0.0, DX)
     n = ocu.basin_find(x, y, DIR)
@@ -202,10 +235,13 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     ctx = mp.get_context("fork")
     times = []
+    import tempfile
+    tmp = tempfile.TemporaryDirectory(prefix="wmf_ref_")
+    cpu_prepare(_REF_WL[0], sample_steps, tmp.name)          # writes the rain files once, before the pool forks
     with ctx.Pool(cores) as pool:
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            pool.map(_ref_worker, [(name, sample_steps)] * cores)
+            pool.map(_ref_worker, [(name, sample_steps, tmp.name)] * cores)
             dt = time.perf_counter() - t0
             if it >= args.warmup:
                 times.append(dt)
@@ -217,9 +253,9 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{name}: SHIA/TETIS 5-tank run, {n}-cell synthetic basin ({nc}x{nr} G2 raster), "
                                f"{T} hourly steps", "cells": n, "steps_per_run": T},
-        "cpu_baseline": {"value": value, "unit": "cell-steps/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "cell-steps/s", "cores": cores, "kind": cpu_kind(),
                          "sample": f"first {sample_steps} of {T} steps of the same basin and rainfall, one ensemble member "
-                                   f"per core ({cores} processes, as wmf.py:872-878 does), oracle -O3 -funroll-loops"},
+                                   f"per core ({cores} processes, as wmf.py:872-878 does); {cpu_label()}"},
         "e2e": {"value": value, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -332,7 +368,9 @@ def run_ours(args):
         extra.update({"levels": n_levels, "waves_per_run": n_waves, "wave_kernel_ms_per_run": wave,
                       "setup_and_epilogue_ms_per_run": ms - wave})
         cpu_steps = max(2, min(T, args.cpu_sample_steps))
-        cpu_v, cpu_s = cpu_sample(wl, cpu_steps)
+        import tempfile
+        with tempfile.TemporaryDirectory(prefix="wmf_cpu_") as tmpd:
+            cpu_v, cpu_s = cpu_sample(wl, cpu_steps, tmpd)
         line = {
             "metric": "shia_cell_steps_per_s", "value": world * cell_steps / (ms / 1e3), "unit": "cell-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -350,9 +388,9 @@ def run_ours(args):
                          "bytes_per_cell_step": BYTES_PER_CELL_STEP, "launches_per_run": n_waves,
                          "achieved_per_launch_bytes": BYTES_PER_CELL_STEP * cell_steps / max(n_waves, 1),
                          "traffic_note": TRAFFIC_NOTE},
-            "cpu_baseline": {"value": cpu_v, "unit": "cell-steps/s", "cores": 1, "kind": "port",
-                             "sample": f"first {cpu_steps} of {T} steps of the same basin ({cpu_s:.1f} s), oracle "
-                                       "-O3 -funroll-loops, single thread like the reference's Fortran"},
+            "cpu_baseline": {"value": cpu_v, "unit": "cell-steps/s", "cores": 1, "kind": cpu_kind(),
+                             "sample": f"first {cpu_steps} of {T} steps of the same basin ({cpu_s:.1f} s), single thread "
+                                       f"as the reference runs; {cpu_label()}"},
             "clocks": clocks, "extra": extra,
         }
         emit(line)

@@ -163,6 +163,9 @@ class RefCu:
         d = _i(dir_map)
         nc, nr = d.shape
         n = i32()
+        # basin_temp is allocated only when it is not yet (cuencas.f90:539): a second call on a LARGER raster overruns
+        # it, and basin_cut slices to the end of whatever size it has.  Start from the state of a freshly imported module.
+        _free_alloc(CU, "basin_temp")
         _call(CU, "basin_find", f32(x), f32(y), d, i32(nc), i32(nr), n)
         return n.value
 
@@ -336,9 +339,10 @@ def write_rain(path_bin, path_hdr, rain, pos):
             f.write("%d, \t %d, \t %.2f, %s \n" % (c + 1, int(p), 0.0, "2020-01-01-00:00"))
 
 
-def shia_v1(inp: dict, workdir: str | None = None, dumps: dict | None = None) -> dict:
+def shia_v1(inp: dict, workdir: str | None = None, dumps: dict | None = None, rain_files: tuple | None = None) -> dict:
     """Run the reference's ``shia_v1`` (modelosv2.f90:191-869) on the input dict ``oracle.shia_v1`` takes.  The rain
-    table is written to a ``.bin`` / ``.hdr`` pair the Fortran reads record by record, as in production.  ``dumps`` may
+    table is written to a ``.bin`` / ``.hdr`` pair the Fortran reads record by record, as in production
+    (``rain_files`` = an already written pair, so that a timed call does not include the writing).  ``dumps`` may
     give ``ruta_storage / ruta_speed / ruta_vfluxes / ruta_retorno / ruta_rc`` paths for the save_* switches."""
     drena = np.asarray(inp["drena"])
     drena = np.ascontiguousarray(drena[0] if drena.ndim == 2 else drena, np.int32)
@@ -389,11 +393,14 @@ def shia_v1(inp: dict, workdir: str | None = None, dumps: dict | None = None) ->
             _set_alloc(MODELS, k, _cell2(inp[k], K, N, np.float32), np.float32)
 
     tmp = None
-    if workdir is None:
-        tmp = tempfile.TemporaryDirectory(prefix="wref_")
-        workdir = tmp.name
-    pb, ph = os.path.join(workdir, "rain.bin"), os.path.join(workdir, "rain.hdr")
-    write_rain(pb, ph, inp["rain"], np.asarray(inp["pos_evento"])[:T])
+    if rain_files is not None:
+        pb, ph = rain_files
+    else:
+        if workdir is None:
+            tmp = tempfile.TemporaryDirectory(prefix="wref_")
+            workdir = tmp.name
+        pb, ph = os.path.join(workdir, "rain.bin"), os.path.join(workdir, "rain.hdr")
+        write_rain(pb, ph, inp["rain"], np.asarray(inp["pos_evento"])[:T])
     dumps = dumps or {}
     rutas = {k: _ruta(dumps.get(k)) for k in ("ruta_storage", "ruta_speed", "ruta_vfluxes", "ruta_retorno", "ruta_rc")}
     blank = _ruta("")
@@ -401,7 +408,10 @@ def shia_v1(inp: dict, workdir: str | None = None, dumps: dict | None = None) ->
     assert calib.size == 11
     stoin = _cell2(inp["stoin"], 5, N, np.float32) if inp.get("stoin") is not None else np.zeros((5, N), np.float32, order="F")
     hsin = _cell2(inp["hspeedin"], 4, N, np.float32) if inp.get("hspeedin") is not None else np.zeros((4, N), np.float32, order="F")
-    z = lambda *s: np.zeros(s, np.float32, order="F")
+    def z(*s):
+        # one spare column: StoOut(4, N_cel+1) is written at a channel outlet (modelosv2.f90:468, :617-618)
+        return np.zeros(s[:-1] + (s[-1] + 1,), np.float32, order="F")[..., :s[-1]]
+
     res = dict(q=z(n_cont, T), qsed=z(n_cont, 3, T), qseparated=z(n_cont, 3, T), hum=z(n_conth, T), st1=z(n_conth, T),
                st3=z(n_conth, T), balance=z(T), speed=z(n_cont, T), areacontrol=z(n_cont, T), stoout=z(5, N),
                qsep_byrain=z(n_cont, 2, T))

@@ -60,9 +60,14 @@ static char g_err[512];
 const char *wref_error(void) { return g_err; }
 
 /* ------------------------------------------------------------------ imports: ms_abi -> SysV thunks */
-static MS void *t_malloc(size_t n) { return malloc(n ? n : 1); }
+/* The reference writes one element past the end of several (k,N_cel) arrays: at the outlet drenaid = N_cel+1 and
+ * StoOut(4,drenaid), Fluxes(:,drenaid), Vs/Vsc(:,drena_id) are updated without a guard (modelosv2.f90:468, :617-618,
+ * :658-680, :1374, :1601).  On Windows that silently lands in allocator slack; here every block the
+ * Fortran allocates gets WREF_PAD spare bytes so glibc's heap checks stay quiet and the stray values go nowhere. */
+#define WREF_PAD 256
+static MS void *t_malloc(size_t n) { return calloc(1, n + WREF_PAD); }
 static MS void t_free(void *p) { free(p); }
-static MS void *t_realloc(void *p, size_t n) { return realloc(p, n ? n : 1); }
+static MS void *t_realloc(void *p, size_t n) { return realloc(p, n + WREF_PAD); }
 static MS void *t_memcpy(void *d, const void *s, size_t n) { return memcpy(d, s, n); }
 static MS void *t_memset(void *d, int c, size_t n) { return memset(d, c, n); }
 static MS float t_powf(float a, float b) { return powf(a, b); }
@@ -258,7 +263,7 @@ int wref_set_allocatable(void *desc_addr, int rank, int type, int64_t n0, int64_
     if (!d || rank < 1 || rank > 2) return 1;
     if (d->base) free(d->base);
     const size_t count = (size_t)n0 * (size_t)(rank == 2 ? n1 : 1);
-    d->base = malloc(count ? count * 4 : 1);
+    d->base = malloc(count * 4 + WREF_PAD);
     if (src) memcpy(d->base, src, count * 4); else memset(d->base, 0, count * 4);
     d->dtype = rank | (type << 3) | (4 << 6);
     d->dim[0].stride = 1; d->dim[0].lbound = 1; d->dim[0].ubound = n0;

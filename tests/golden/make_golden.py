@@ -1,8 +1,11 @@
 #!/usr/bin/env python
-"""Regenerate tests/golden/*.npz: outputs of the CPU oracle (oracle/, the C restatement of the reference's Fortran) on
-small seeded synthetic cases.  The real reference cannot run in this image (no Fortran compiler), so these vectors do
-NOT pin the oracle to the reference -- they freeze the oracle's output of the day they were made, so that later edits
-of oracle/ or of the generators cannot drift silently, and give the GPU tests a fixture that does not need the oracle.
+"""Regenerate tests/golden/*.npz: outputs of THE REFERENCE ITSELF on small seeded synthetic cases.
+
+Every ``o_*`` array is produced by the reference's own compiled Fortran (``oracle/_ref/libwmf_ref.so`` = the COFF objects
+of the reference's last f2py build, loaded by ``oracle/ref_loader.c``, driven by ``oracle/ref.py``) and, at generation
+time, checked to be bit-identical to the C restatement in ``oracle/``.  The one exception is ``o_balance64``, the fp64
+twin of the mass balance that only the restatement can produce (the reference sums in fp32).  The script needs
+``/root/reference`` (or a prebuilt ``oracle/_ref``); the committed vectors let the tests run without either.
 
     python tests/golden/make_golden.py
 """
@@ -21,6 +24,7 @@ CASES = {
     "shia_kinematic_returns": ("G1", 36, 40, 12, 40, dict(speed_type=(2, 2, 1), retorno_gr=1, retorno_aq=1), {}),
     "shia_sed_slides": ("G2", 44, 36, 13, 36, dict(speed_type=(2, 2, 1), sediments=True, slides=True, retorno_gr=1,
                                                     rain_peak_mm=60.0), {}),
+    "shia_separate_fluxes": ("G2", 44, 40, 14, 40, dict(rain_peak_mm=50.0), dict(separate_fluxes=1)),
 }
 
 
@@ -42,20 +46,42 @@ def run_oracle(inp, flags):
     return oracle.shia_v1(d)
 
 
-KEEP = ("q", "stoout", "hum", "st1", "st3", "balance64", "speed", "areacontrol", "mean_rain", "acum_rain", "qsed", "vs", "vd",
+def run_reference(inp, flags):
+    from oracle import ref
+    d = dict(inp)
+    d.update(flags)
+    return ref.shia_v1(d)
+
+
+KEEP = ("q", "stoout", "hum", "st1", "st3", "balance", "balance64", "speed", "areacontrol", "mean_rain", "acum_rain", "qsed", "qseparated", "vs", "vd",
         "vsc", "vdc", "volero", "voldepo", "retorned", "sl_riskvector", "sl_slideocurrence", "sl_slidencelltime")
 
 
 def main():
     for name in CASES:
         bs, v, inp, flags = build_case(name)
-        ref = run_oracle(inp, flags)
+        orc = run_oracle(inp, flags)
+        ref = run_reference(inp, flags)
+        from oracle import ref as refmod
+        rcu = refmod.RefCu()
+        o = bs["cu"]
+        rcu.ncols, rcu.nrows, rcu.xll, rcu.yll, rcu.dx, rcu.dy, rcu.dxp, rcu.nodata = o.ncols, o.nrows, o.xll, o.yll, o.dx, o.dy, o.dxp, o.nodata
+        n = rcu.basin_find(bs["x"], bs["y"], bs["DIR"])
+        rb = rcu.basin_cut(n)
+        racum, rlng, rpend, relev = rcu.basin_basics(rb, v["demv"], v["dirv"])
+        for a, b in ((rb, bs["basin"]), (racum, v["acum"]), (rlng, v["lng"]), (rpend, v["pend"]), (relev, v["elev"])):
+            assert np.array_equal(a, b), "Path A: reference and restatement differ"
+        for k in KEEP:
+            if k in ref and ref[k] is not None and k in orc:
+                assert np.array_equal(np.asarray(ref[k]).reshape(-1), np.asarray(orc[k]).reshape(-1)), (name, k)
+        ref["balance64"] = orc["balance64"]
         out = {"basin_f": bs["basin"], "acum": v["acum"], "long": v["lng"], "pend": v["pend"], "elev": v["elev"],
                "rain_checksum": np.array([int(inp["rain"].astype(np.int64).sum())]),
-               "calib": np.asarray(inp["calib"], np.float32)}
+               "calib": np.asarray(inp["calib"], np.float32),
+               "source": np.array(["reference Fortran objects (gfortran 5.3.0 -O3 -funroll-loops) via oracle/_ref; balance64 from oracle/"])}
         for k in KEEP:
             if k in ref and ref[k] is not None:
-                out["o_" + k] = np.asarray(ref[k])
+                out["o_" + k] = np.asarray(ref[k]).reshape(np.asarray(orc[k]).shape) if k in orc else np.asarray(ref[k])
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, {k: v.shape for k, v in out.items() if k.startswith("o_")})
 

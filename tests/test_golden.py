@@ -1,6 +1,8 @@
-"""Committed golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py from the CPU oracle).
+"""Committed golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py FROM THE REFERENCE'S OWN COMPILED
+FORTRAN, oracle/_ref; see that script).
 
-CPU leg: today's oracle reproduces the frozen vectors (topology bit-exact, floats to 1e-6 to survive a libm update).
+CPU leg: the C restatement in oracle/ reproduces the reference's vectors (topology bit-exact; floats are bit-identical
+on the day of generation and held to 1e-6 here to survive a libm update).
 GPU leg: the CUDA path through the C ABI matches the same vectors at the north-star tolerance without touching oracle/.
 """
 import importlib.util
@@ -71,6 +73,9 @@ def test_cuda_matches_golden(name):
     tot = float(np.abs(g["o_stoout"]).sum())
     assert np.abs(ret[6] - g["o_balance64"]).max() <= 2e-7 * tot
     np.testing.assert_array_equal(m.acum_rain.reshape(-1), g["o_acum_rain"])
+    if flags.get("separate_fluxes"):
+        assert g["o_qseparated"].max() > 0
+        close(ret[2], g["o_qseparated"], 1e-5, "Qseparated")
     if "o_vs" in g:
         close(ret[1], g["o_qsed"], 5e-5, "Qsed")
         close(m.vd, g["o_vd"], 5e-5, "Vd")
