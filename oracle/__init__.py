@@ -1,4 +1,4 @@
-"""CPU ORACLE -- test infrastructure, NOT product code ("parity unpinned", see wmf_oracle.h).
+"""CPU ORACLE -- test infrastructure, NOT product code (parity pinned against the reference's own compiled Fortran, see wmf_oracle.h).
 
 ctypes front-end of the C restatement of the reference's Fortran
 (wmf/cuencas.f90 module ``cu``; wmf/modelosv2.f90 module ``models``).  Only

@@ -1,4 +1,4 @@
-"""CPU ORACLE, second opinion -- test infrastructure, NOT product code ("parity unpinned", see wmf_oracle.h).
+"""CPU ORACLE, second opinion -- test infrastructure, NOT product code (parity pinned against the reference's own compiled Fortran, see wmf_oracle.h).
 
 A pure-Python (numpy float32 scalars) transliteration of the core of shia_v1, written from the Fortran source itself
 (wmf/modelosv2.f90:257-304 setup, :433-512 vertical tanks, :548-595 hillslope outflow, :599-719 routing, :745-787

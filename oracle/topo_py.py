@@ -1,4 +1,4 @@
-"""CPU ORACLE, second opinion for Path A -- test infrastructure, NOT product code ("parity unpinned", see wmf_oracle.h).
+"""CPU ORACLE, second opinion for Path A -- test infrastructure, NOT product code (parity pinned against the reference's own compiled Fortran, see wmf_oracle.h).
 
 Pure-Python transliteration of basin_find / basin_cut / basin_acum written from wmf/cuencas.f90:77-90, 525-607, 659-680
 (not from oracle/wmf_oracle_cu.c); tests require both restatements to agree exactly on small random rasters.

@@ -6,11 +6,11 @@
  * module `models`).  Same loop order, float / int32_t arithmetic, powf from
  * libm, left-associated sums.  Build: -O2 -fno-fast-math -ffp-contract=off.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for
- * either path and no Fortran compiler exists in the build image, so the real
- * reference cannot be run.  This oracle is pinned only by the hand-derived
- * KAT-1 (tests/golden/kat1.json), structural invariants and closed-form
- * single-cell cases (tests/test_oracle_*.py).
+ * PARITY PINNED against the reference's own compiled Fortran: oracle/_ref
+ * (ref_loader.c + ref.py) runs the COFF objects the reference tree ships, and
+ * tests/test_reference_pin.py requires this restatement to be BIT-IDENTICAL to
+ * them on every routine below and every sub-model switch.  Also held by KAT-1
+ * (tests/golden/kat1.json), invariants and closed forms (tests/test_oracle_*.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.

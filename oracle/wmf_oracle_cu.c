@@ -1,7 +1,7 @@
 /*
  * wmf_oracle_cu.c -- CPU ORACLE (test infrastructure, NOT product code).
  * Literal restatement of the Path-A routines of wmf/cuencas.f90 (module cu).
- * See wmf_oracle.h for the status of this file ("parity unpinned").
+ * See wmf_oracle.h for the status of this file (pinned against oracle/_ref).
  *
  * Fenced quirks (reference behaviour is undefined / non-terminating there):
  *  - basin_find: the reference's res(2,7) scratch holds 7 children although 8

@@ -1,7 +1,7 @@
 /*
  * wmf_oracle_models.c -- CPU ORACLE (test infrastructure, NOT product code).
  * Literal sequential restatement of shia_v1 and its sub-models from
- * wmf/modelosv2.f90 (module models).  See wmf_oracle.h ("parity unpinned").
+ * wmf/modelosv2.f90 (module models).  See wmf_oracle.h (pinned against oracle/_ref).
  *
  * Scope: vertical tanks, hillslope outflow (linear / kinematic), routing,
  * channel kinematic wave, control-point records, per-step means and balance,
