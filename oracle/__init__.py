@@ -62,7 +62,7 @@ class ShiaIn(C.Structure):
         ("show_storage", C.c_int32), ("show_speed", C.c_int32), ("show_mean_speed", C.c_int32),
         ("show_mean_retorno", C.c_int32), ("save_retorno", C.c_int32),
         ("save_vfluxes", C.c_int32), ("save_rc", C.c_int32),
-        ("separate_fluxes", C.c_int32),
+        ("separate_rain", C.c_int32), ("separate_fluxes", C.c_int32),
         ("calib", C.c_float * 11),
         ("drena", i32p), ("unit_type", i32p),
         ("hill_long", f32p), ("hill_slope", f32p), ("stream_long", f32p), ("stream_slope", f32p),
@@ -78,6 +78,8 @@ class ShiaIn(C.Structure):
         ("sl_gullienogullie", C.c_int32), ("sl_fs", C.c_float), ("sl_gammaw", C.c_float),
         ("sl_zs", f32p), ("sl_gammas", f32p), ("sl_cohesion", f32p), ("sl_frictionangle", f32p),
         ("sl_radslope", f32p),
+        ("conv", i32p), ("stra", i32p), ("n_conv_records", C.c_int32), ("n_stra_records", C.c_int32),
+        ("pos_conv", i32p), ("pos_stra", i32p),
     ]
 
 
@@ -95,6 +97,7 @@ class ShiaOut(C.Structure):
         ("sl_zmin", f32p), ("sl_zcrit", f32p), ("sl_zmax", f32p), ("sl_bo", f32p),
         ("sl_riskvector", f32p), ("sl_slideocurrence", f32p),
         ("sl_slideacumulate", i32p), ("sl_slidencelltime", i32p),
+        ("qsep_byrain", f32p), ("storage_conv", f32p), ("storage_stra", f32p),
     ]
 
 
@@ -350,7 +353,7 @@ def shia_v1(inp: dict, fast: bool = False) -> dict:
     si.speed_type = (C.c_int32 * 3)(*[int(v) for v in inp.get("speed_type", [1, 1, 1])])
     si.calc_niter = int(inp.get("calc_niter", 5))
     for k in ("sim_sediments", "sim_slides", "show_storage", "show_speed", "show_mean_speed",
-              "show_mean_retorno", "save_retorno", "save_vfluxes", "save_rc", "separate_fluxes"):
+              "show_mean_retorno", "save_retorno", "save_vfluxes", "save_rc", "separate_fluxes", "separate_rain"):
         setattr(si, k, int(inp.get(k, 0)))
     si.calib = (C.c_float * 11)(*[float(v) for v in inp["calib"]])
 
@@ -376,6 +379,15 @@ def shia_v1(inp: dict, fast: bool = False) -> dict:
     pos = np.ascontiguousarray(inp["pos_evento"], dtype=np.int32)
     assert pos.size >= T and pos.min() >= 1 and pos.max() <= rain.shape[0]
     put("pos_evento", pos, i32p)
+    if si.separate_rain == 1:            # rain-type tables (n_records, N) int32 and their record of every step (1-based)
+        for k in ("conv", "stra"):
+            tab = np.ascontiguousarray(inp[k], dtype=np.int32)
+            assert tab.ndim == 2 and tab.shape[1] == N
+            put(k, tab, i32p)
+            setattr(si, f"n_{k}_records", tab.shape[0])
+            pk = np.ascontiguousarray(inp["pos_" + k], dtype=np.int32)
+            assert pk.size >= T
+            put("pos_" + k, pk, i32p)
     sed = si.sim_sediments == 1
     sl = si.sim_slides == 1
     if sed:
@@ -426,6 +438,10 @@ def shia_v1(inp: dict, fast: bool = False) -> dict:
     out("mean_retorno64", (T,), np.float64, f64p)
     out("mean_vfluxes64", (4, T), np.float64, f64p)
     out("vfluxes_last", (4, N))
+    if si.separate_rain == 1:
+        out("qsep_byrain", (n_cont, 2, T))
+        out("storage_conv", (5, N))
+        out("storage_stra", (5, N))
     out("retorned_last", (N,))
     if sed:
         for k in ("vs", "vd", "vsc", "vdc"):

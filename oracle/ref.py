@@ -393,6 +393,7 @@ def shia_v1(inp: dict, workdir: str | None = None, dumps: dict | None = None, ra
             _set_alloc(MODELS, k, _cell2(inp[k], K, N, np.float32), np.float32)
 
     tmp = None
+    blank_path = ""
     if rain_files is not None:
         pb, ph = rain_files
     else:
@@ -401,6 +402,21 @@ def shia_v1(inp: dict, workdir: str | None = None, dumps: dict | None = None, ra
             workdir = tmp.name
         pb, ph = os.path.join(workdir, "rain.bin"), os.path.join(workdir, "rain.hdr")
         write_rain(pb, ph, inp["rain"], np.asarray(inp["pos_evento"])[:T])
+    conv_files = [blank_path] * 4
+    if int(inp.get("separate_rain", 0)) == 1:            # ruta_binConv, ruta_binStra, ruta_hdrConv, ruta_hdrStra
+        if tmp is None and workdir is None:
+            tmp = tempfile.TemporaryDirectory(prefix="wref_")
+            workdir = tmp.name
+        wd = workdir or tmp.name
+        names = {}
+        for k in ("conv", "stra"):
+            names[k] = (os.path.join(wd, k + ".bin"), os.path.join(wd, k + ".hdr"))
+            # one spare header row: the separate reader wants Nintervals + rain_first_point <= Ntotal (:1026)
+            pk = np.concatenate([np.asarray(inp["pos_" + k])[:T], [1]])
+            write_rain(names[k][0], names[k][1], inp[k], pk)
+        conv_files = [names["conv"][0], names["stra"][0], names["conv"][1], names["stra"][1]]
+        for k in ("storage_conv", "storage_stra"):
+            _free_alloc(MODELS, k)
     dumps = dumps or {}
     rutas = {k: _ruta(dumps.get(k)) for k in ("ruta_storage", "ruta_speed", "ruta_vfluxes", "ruta_retorno", "ruta_rc")}
     blank = _ruta("")
@@ -418,8 +434,9 @@ def shia_v1(inp: dict, workdir: str | None = None, dumps: dict | None = None, ra
     L500 = 500
     _call(MODELS, "shia_v1", _ruta(pb), _ruta(ph), calib, stoin, hsin, i32(N), i32(n_cont), i32(n_conth), i32(T),
           res["q"], res["qsed"], res["qseparated"], res["hum"], res["st1"], res["st3"], res["balance"], res["speed"],
-          res["areacontrol"], res["stoout"], rutas["ruta_storage"], rutas["ruta_speed"], rutas["ruta_vfluxes"], blank, blank,
-          blank, blank, res["qsep_byrain"], rutas["ruta_retorno"], rutas["ruta_rc"],
+          res["areacontrol"], res["stoout"], rutas["ruta_storage"], rutas["ruta_speed"], rutas["ruta_vfluxes"],
+          _ruta(conv_files[0]), _ruta(conv_files[1]), _ruta(conv_files[2]), _ruta(conv_files[3]),
+          res["qsep_byrain"], rutas["ruta_retorno"], rutas["ruta_rc"],
           *([L500] * 11))
     # module-level results (read back by wmf.py:4548-4601)
     for k, rank in (("mean_rain", 2), ("acum_rain", 2), ("mean_storage", 2), ("mean_speed", 2), ("mean_retorno", 1),
@@ -427,6 +444,9 @@ def shia_v1(inp: dict, workdir: str | None = None, dumps: dict | None = None, ra
         v = _get_alloc(MODELS, k, rank, np.float32)
         if v is not None:
             res[k] = v.reshape(-1) if (rank == 2 and v.shape[0] == 1) else v
+    if int(inp.get("separate_rain", 0)) == 1:
+        res["storage_conv"] = _get_alloc(MODELS, "storage_conv", 2, np.float32)
+        res["storage_stra"] = _get_alloc(MODELS, "storage_stra", 2, np.float32)
     if sed:
         for k in ("vs", "vd", "vsc", "vdc"):
             res[k] = _get_alloc(MODELS, k, 2, np.float32)

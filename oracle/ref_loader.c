@@ -13,7 +13,7 @@
  *   2. resolves the few imports (malloc/free/memset/memcpy/realloc, libm's powf/expf/logf/sinf/cosf/tanf/atanf/...,
  *      libgfortran entry points) to ms_abi thunks defined here -- the objects use the Windows x64 calling convention,
  *   3. replaces the routines that do file I/O through libgfortran 5.3's runtime (read_int_basin,
- *      rain_read_ascii_table, write_float_basin, write_int_basin) by C restatements of those few lines, patched in at
+ *      rain_read_ascii_table[_separate], write_float_basin, write_int_basin) by C restatements of those few lines, patched in at
  *      the routines' entry points; `print` statements become no-ops,
  *   4. calls any routine through a generic ms_abi trampoline (Fortran passes everything by reference, so every
  *      argument is a pointer or a hidden character length: integer class).
@@ -367,6 +367,46 @@ static MS void r_rain_read_ascii_table(const char *ruta, const int32_t *ninterva
     free(pos);
 }
 
+/* rain_read_ascii_table_separate, modelosv2.f90:1004-1065: posConv / posStra(Nintervals) from the two headers; note the
+ * stricter test Nintervals + rain_first_point <= Ntotal (the plain table reader allows Ntotal + 1) */
+static void read_pos_column(const char *ruta, int ruta_len, int n, int32_t *pos) {
+    char path[512], line[1024];
+    trim(path, sizeof path, ruta, ruta_len > 0 && ruta_len <= 500 ? ruta_len : 255);
+    FILE *f = fopen(path, "r");
+    if (!f) { fprintf(stderr, "wref: rain_read_ascii_table_separate cannot open '%s'\n", path); abort(); }
+    long ntotal = 0;
+    for (int i = 0; i < 3; ++i) {
+        next_line(f, line, sizeof line);
+        char *tok[4] = {0};
+        int k = 0;
+        for (char *t = strtok(line, " ,\t\r\n"); t && k < 4; t = strtok(NULL, " ,\t\r\n")) tok[k++] = t;
+        if (k == 4) ntotal = strtol(tok[3], NULL, 10);
+    }
+    for (int i = 0; i < 3; ++i) next_line(f, line, sizeof line);
+    const int32_t rfp = *(int32_t *)wref_sym(1, "__models_MOD_rain_first_point");
+    if (n + rfp <= ntotal) {
+        if (rfp > 1) for (int i = 0; i < rfp; ++i) next_line(f, line, sizeof line);
+        for (int i = 0; i < n; ++i) {
+            next_line(f, line, sizeof line);
+            char *t = strtok(line, " ,\t\r\n");
+            t = strtok(NULL, " ,\t\r\n");
+            if (t) pos[i] = (int32_t)strtol(t, NULL, 10);
+        }
+    }
+    fclose(f);
+}
+static MS void r_rain_read_ascii_table_separate(const char *ruta_conv, const char *ruta_stra, const int32_t *nintervals,
+                                                int len_conv, int len_stra) {
+    const int n = *nintervals;
+    int32_t *pc = calloc((size_t)(n > 0 ? n : 1), 4), *ps = calloc((size_t)(n > 0 ? n : 1), 4);
+    read_pos_column(ruta_conv, len_conv, n, pc);
+    read_pos_column(ruta_stra, len_stra, n, ps);
+    wref_set_allocatable(wref_sym(1, "__models_MOD_posconv"), 1, 1, n, 1, pc);
+    wref_set_allocatable(wref_sym(1, "__models_MOD_posstra"), 1, 1, n, 1, ps);
+    free(pc);
+    free(ps);
+}
+
 /* ------------------------------------------------------------------ entry points (SysV, called through ctypes) */
 int wref_init(void) {
     if (g_obj[0].region) return 0;
@@ -376,6 +416,7 @@ int wref_init(void) {
     if (patch(1, "__models_MOD_write_float_basin", (void *)r_write_float_basin)) return 1;
     if (patch(1, "__models_MOD_write_int_basin", (void *)r_write_int_basin)) return 1;
     if (patch(1, "__models_MOD_rain_read_ascii_table", (void *)r_rain_read_ascii_table)) return 1;
+    if (patch(1, "__models_MOD_rain_read_ascii_table_separate", (void *)r_rain_read_ascii_table_separate)) return 1;
     return 0;
 }
 

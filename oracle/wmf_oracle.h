@@ -83,6 +83,7 @@ typedef struct {
     int32_t sim_sediments, sim_slides;
     int32_t show_storage, show_speed, show_mean_speed, show_mean_retorno, save_retorno;
     int32_t save_vfluxes, save_rc;
+    int32_t separate_rain;  /* module separate_rain (:91): shadow storages by rain type, Qsep_byrain */
     int32_t separate_fluxes;   /* modelosv2.f90:90, shadow shares of runoff / subsurface / base flow in the channel */
     float calib[11];
     /* topology + statics, all (1,N) or (K,N) column-major */
@@ -110,6 +111,11 @@ typedef struct {
     int32_t sl_gullienogullie;
     float sl_fs, sl_gammaw;
     const float *sl_zs, *sl_gammas, *sl_cohesion, *sl_frictionangle, *sl_radslope; /* (N) */
+    /* separate_rain (:346-359, :452-456): rain-type tables like `rain` (int32, record r at conv + (r-1)*N, a cell is
+       convective / stratiform when its value / 1000 is non-zero) and the record of every step (n_reg, 1-based) */
+    const int32_t *conv, *stra;
+    int32_t n_conv_records, n_stra_records;
+    const int32_t *pos_conv, *pos_stra;
 } wo_shia_in;
 
 typedef struct {
@@ -145,6 +151,8 @@ typedef struct {
     float *sl_zmin, *sl_zcrit, *sl_zmax, *sl_bo, *sl_riskvector, *sl_slideocurrence; /* (N) */
     int32_t *sl_slideacumulate; /* (N) */
     int32_t *sl_slidencelltime; /* (n_reg) */
+    float *qsep_byrain;      /* (n_cont,2,n_reg) when separate_rain (:713-715, :767-769), may be NULL */
+    float *storage_conv, *storage_stra; /* (5,N) final shadow storages (module Storage_conv / Storage_stra), may be NULL */
 } wo_shia_out;
 
 int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out);

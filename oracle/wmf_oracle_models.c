@@ -275,6 +275,10 @@ static double sum_d(const float *a, size_t n)
     return s;
 }
 
+/* gfortran 5.3's inline MAX(0.0, x) as compiled in the reference object: 0 when x is NaN (an empty capillary tank makes
+   :486 a 0/0; checked against oracle/_ref) */
+#define WO_FMAX0(x) (((x) > 0.0f) ? (x) : 0.0f)
+
 /* modelosv2.f90:191-869 */
 int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
 {
@@ -291,6 +295,14 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
     /* Fluxes(3,N_cel+1) :340-344 (one spare column: the outlet's out-of-range receiver is never written here) */
     float *Fluxes = (in->separate_fluxes == 1) ? (float *)calloc(3 * ((size_t)N + 1), sizeof(float)) : NULL;
     if (Fluxes && out->qseparated) memset(out->qseparated, 0, sizeof(float) * 3 * (size_t)NC * T);
+    /* separate_rain :346-359: shadow storages (one spare column for the outlet's out-of-range receiver), Conv / Stra = 0 */
+    const int sepr = in->separate_rain == 1;
+    float *Sc = sepr ? (float *)calloc(5 * ((size_t)N + 1), sizeof(float)) : NULL;
+    float *Ss = sepr ? (float *)calloc(5 * ((size_t)N + 1), sizeof(float)) : NULL;
+    int32_t *Conv = sepr ? (int32_t *)calloc((size_t)N, sizeof(int32_t)) : NULL;
+    int32_t *Stra = sepr ? (int32_t *)calloc((size_t)N, sizeof(int32_t)) : NULL;
+    float hflux_c[4] = {0, 0, 0, 0}, hflux_s[4] = {0, 0, 0, 0};
+    if (sepr && out->qsep_byrain) memset(out->qsep_byrain, 0, sizeof(float) * 2 * (size_t)NC * T);
     sed_state SS;
     memset(&SS, 0, sizeof SS);
     SS.in = in;
@@ -359,6 +371,13 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
         } else {
             const int32_t *rec = in->rain + (size_t)(in->pos_evento[t] - 1) * N;
             for (int32_t i = 0; i < N; ++i) rain[i] = (float)rec[i] / 1000.0f;
+            /* :452-456 -- the rain types are read on wet steps only: a dry step keeps the previous step's Conv / Stra;
+               a record outside the file fails the read and leaves the vector as it was */
+            if (sepr) {
+                const int32_t rc = in->pos_conv[t], rs = in->pos_stra[t];
+                if (rc >= 1 && rc <= in->n_conv_records) memcpy(Conv, in->conv + (size_t)(rc - 1) * N, sizeof(int32_t) * (size_t)N);
+                if (rs >= 1 && rs <= in->n_stra_records) memcpy(Stra, in->stra + (size_t)(rs - 1) * N, sizeof(int32_t) * (size_t)N);
+            }
         }
         float rain_sum = 0.0f;
         for (int32_t i = 0; i < N; ++i) out->acum_rain[i] = out->acum_rain[i] + rain[i];
@@ -372,12 +391,20 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
             entradas = entradas + rain[c];
             entradas64 += (double)rain[c];
             rain_sum = rain_sum + rain[c];
+            float Co = 0.0f, St = 0.0f;
+            if (sepr) { Co = (float)(Conv[c] / 1000); St = (float)(Stra[c] / 1000); } /* integer division, :471-474 */
             /* vertical :478-512 */
             vflux[0] = fmaxf(0.0f, rain[c] - A3(H, 0, c) + A5(Sto, 0, c));
             A5(Sto, 0, c) = A5(Sto, 0, c) + rain[c] - vflux[0];
             float Evp_loss = fminf(in->evpserie[t] * A4(vspeed, 0, c) *
                                        powf(A5(Sto, 0, c) / A3(H, 0, c), 0.6f),
                                    A5(Sto, 0, c));
+            if (sepr) { /* :485-488, against the capillary tank BEFORE the evaporation is taken out; max(0., NaN) = 0 as the reference's compiled MAX */
+                const float ec = A5(Sc, 0, c) - Evp_loss * A5(Sc, 0, c) / A5(Sto, 0, c);
+                const float es = A5(Ss, 0, c) - Evp_loss * A5(Ss, 0, c) / A5(Sto, 0, c);
+                A5(Sc, 0, c) = WO_FMAX0(ec);
+                A5(Ss, 0, c) = WO_FMAX0(es);
+            }
             A5(Sto, 0, c) = A5(Sto, 0, c) - Evp_loss;
             for (int i = 0; i < 3; ++i) {
                 vflux[i + 1] = fminf(vflux[i], A4(vspeed, i + 1, c));
@@ -388,13 +415,29 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
                 A5(Sto, 2, c) = A5(Sto, 2, c) + Ret_aq;
                 A5(Sto, 3, c) = A5(Sto, 3, c) - Ret_aq;
             }
+            float Ret_sep = 0.0f;
             if (in->retorno_gr > 0.0f) {
                 float Ret = fmaxf(0.0f, A5(Sto, 2, c) - A3(H, 1, c));
+                Ret_sep = Ret;
                 A5(Sto, 1, c) = A5(Sto, 1, c) + Ret;
                 A5(Sto, 2, c) = A5(Sto, 2, c) - Ret;
                 if (out->retorned) out->retorned[c] = out->retorned[c] + Ret;
                 vflux[1] = vflux[1] + Ret;
                 vflux[2] = vflux[2] - Ret;
+            }
+            if (sepr) { /* :530-547; vflux(2:3) already carry the return flow (:510-511) and Ret is added again here */
+                A5(Sc, 0, c) = A5(Sc, 0, c) + (rain[c] - vflux[0]) * Co;
+                A5(Ss, 0, c) = A5(Ss, 0, c) + (rain[c] - vflux[0]) * St;
+                for (int i = 0; i < 3; ++i) {
+                    A5(Sc, i + 1, c) = A5(Sc, i + 1, c) + (vflux[i] - vflux[i + 1]) * Co;
+                    A5(Ss, i + 1, c) = A5(Ss, i + 1, c) + (vflux[i] - vflux[i + 1]) * St;
+                }
+                if (in->retorno_gr > 0.0f) {
+                    A5(Sc, 1, c) = A5(Sc, 1, c) + Ret_sep * Co;
+                    A5(Sc, 2, c) = A5(Sc, 2, c) - Ret_sep * Co;
+                    A5(Ss, 1, c) = A5(Ss, 1, c) + Ret_sep * St;
+                    A5(Ss, 2, c) = A5(Ss, 2, c) - Ret_sep * St;
+                }
             }
             if (vfl_map)
                 for (int i = 0; i < 4; ++i) A4(vfl_map, i, c) = vflux[i];
@@ -420,12 +463,28 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
                                       c, drenaid, ut);
                     }
                 }
+                if (sepr) { /* :580-592 */
+                    if (A5(Sto, i + 1, c) > 0.0f) {
+                        hflux_c[i] = hflux[i] * A5(Sc, i + 1, c) / A5(Sto, i + 1, c);
+                        hflux_s[i] = hflux[i] * A5(Ss, i + 1, c) / A5(Sto, i + 1, c);
+                    } else {
+                        hflux_c[i] = 0.0f;
+                        hflux_s[i] = 0.0f;
+                    }
+                    A5(Sc, i + 1, c) = A5(Sc, i + 1, c) - hflux_c[i];
+                    A5(Ss, i + 1, c) = A5(Ss, i + 1, c) - hflux_s[i];
+                }
                 A5(Sto, i + 1, c) = A5(Sto, i + 1, c) - hflux[i];
             }
             /* routing :599-719 */
             if (ut == 1) {
                 if (in->drena[c] != 0) {
                     for (int i = 0; i < 3; ++i) A5(Sto, i + 1, drenaid) = A5(Sto, i + 1, drenaid) + hflux[i];
+                    if (sepr)
+                        for (int i = 0; i < 3; ++i) { /* :605-608 */
+                            A5(Sc, i + 1, drenaid) = A5(Sc, i + 1, drenaid) + hflux_c[i];
+                            A5(Ss, i + 1, drenaid) = A5(Ss, i + 1, drenaid) + hflux_s[i];
+                        }
                 } else {
                     float s3 = (hflux[0] + hflux[1]) + hflux[2];
                     out->q[(size_t)t * NC + 0] = out->q[(size_t)t * NC + 0] + s3 * m3_mm[c];
@@ -435,6 +494,12 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
             } else if (ut > 1) {
                 if (drenaid < N) A5(Sto, 3, drenaid) = A5(Sto, 3, drenaid) + hflux[2] * (float)(3 - ut);
                 A5(Sto, 4, c) = A5(Sto, 4, c) + (hflux[0] + hflux[1]) + hflux[2] * (float)(ut - 2);
+                if (sepr) { /* :623-628 (the spare column takes the outlet's out-of-range write) */
+                    A5(Sc, 3, drenaid) = A5(Sc, 3, drenaid) + hflux_c[2] * (float)(3 - ut);
+                    A5(Ss, 3, drenaid) = A5(Ss, 3, drenaid) + hflux_s[2] * (float)(3 - ut);
+                    A5(Sc, 4, c) = A5(Sc, 4, c) + (hflux_c[0] + hflux_c[1]) + hflux_c[2] * (float)(ut - 2);
+                    A5(Ss, 4, c) = A5(Ss, 4, c) + (hflux_s[0] + hflux_s[1]) + hflux_s[2] * (float)(ut - 2);
+                }
                 section_area = wo_calc_speed(A5(Sto, 4, c) * m3_mm[c], A4(in->h_coef, 3, c) * in->calib[7],
                                              A4(in->h_exp, 3, c), in->stream_long[c], &A4(hspeed, 3, c), dt,
                                              in->calc_niter);
@@ -443,6 +508,17 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
                     Vsal_sed[0] = Vsal_sed[1] = Vsal_sed[2] = 0.0f;
                     sed_channel(&SS, A5(Sto, 4, c), A4(hspeed, 3, c), hflux[3] * m3_mm[c] / dt,
                                 in->stream_slope[c], section_area, c, drenaid, Vsal_sed);
+                }
+                if (sepr) { /* :645-655 */
+                    if (A5(Sto, 4, c) != 0.0f) {
+                        hflux_c[3] = hflux[3] * A5(Sc, 4, c) / A5(Sto, 4, c);
+                        hflux_s[3] = hflux[3] * A5(Ss, 4, c) / A5(Sto, 4, c);
+                    } else {
+                        hflux_c[3] = 0.0f;
+                        hflux_s[3] = 0.0f;
+                    }
+                    A5(Sc, 4, c) = A5(Sc, 4, c) - hflux_c[3];
+                    A5(Ss, 4, c) = A5(Ss, 4, c) - hflux_s[3];
                 }
                 /* separate_fluxes :658-665 -- note the ratio uses StoOut(5) BEFORE the outflow is taken out */
                 if (Fluxes) {
@@ -458,6 +534,10 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
                 A5(Sto, 4, c) = A5(Sto, 4, c) - hflux[3];
                 if (in->drena[c] != 0) {
                     A5(Sto, 4, drenaid) = A5(Sto, 4, drenaid) + hflux[3];
+                    if (sepr) { /* :683-686 */
+                        A5(Sc, 4, drenaid) = A5(Sc, 4, drenaid) + hflux_c[3];
+                        A5(Ss, 4, drenaid) = A5(Ss, 4, drenaid) + hflux_s[3];
+                    }
                     /* :674-680 -- and here AFTER; an empty channel zeroes the receiver's shares */
                     if (Fluxes) {
                         if (A5(Sto, 4, c) > 0.0f) {
@@ -473,6 +553,10 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
                         for (int i = 0; i < 3; ++i)
                             out->qseparated[((size_t)t * 3 + i) * NC + 0] =
                                 (A5(Sto, 4, c) > 0.0f) ? Fluxes[3 * (size_t)c + i] * (hflux[3] / A5(Sto, 4, c)) * m3_mm[c] / dt : 0.0f;
+                    }
+                    if (sepr && out->qsep_byrain) { /* :713-716 */
+                        out->qsep_byrain[((size_t)t * 2 + 0) * NC + 0] = hflux_c[3] * m3_mm[c] / dt;
+                        out->qsep_byrain[((size_t)t * 2 + 1) * NC + 0] = hflux_s[3] * m3_mm[c] / dt;
                     }
                     out->q[(size_t)t * NC + 0] = hflux[3] * m3_mm[c] / dt;
                     salidas = salidas + hflux[3];
@@ -493,6 +577,10 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
                     size_t k = (size_t)t * NC + (control_cont - 1);
                     if (ut > 1) {
                         out->q[k] = hflux[3] * m3_mm[c] / dt;
+                        if (sepr && out->qsep_byrain) { /* :767-770 */
+                            out->qsep_byrain[((size_t)t * 2 + 0) * NC + (control_cont - 1)] = hflux_c[3] * m3_mm[c] / dt;
+                            out->qsep_byrain[((size_t)t * 2 + 1) * NC + (control_cont - 1)] = hflux_s[3] * m3_mm[c] / dt;
+                        }
                         if (Fluxes && out->qseparated) /* :752-759 */
                             for (int i = 0; i < 3; ++i)
                                 out->qseparated[((size_t)t * 3 + i) * NC + (control_cont - 1)] =
@@ -583,6 +671,14 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
     free(m3_mm);
     free(Fluxes);
     free(rain);
+    if (sepr) {
+        if (out->storage_conv) memcpy(out->storage_conv, Sc, sizeof(float) * 5 * (size_t)N);
+        if (out->storage_stra) memcpy(out->storage_stra, Ss, sizeof(float) * 5 * (size_t)N);
+    }
+    free(Sc);
+    free(Ss);
+    free(Conv);
+    free(Stra);
     free(vfl_map);
     return 0;
 }

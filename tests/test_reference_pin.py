@@ -163,6 +163,13 @@ SHIA_CASES = {
     "separate_fluxes": (dict(rain_peak_mm=50.0), dict(separate_fluxes=1), ("qseparated",)),
     "dump_switches": (dict(retorno_gr=1, rain_peak_mm=40.0), dict(save_vfluxes=1, save_rc=1, save_retorno=1),
                       ("mean_vfluxes", "rc_coef")),
+    "separate_rain": (dict(rain_peak_mm=50.0, retorno_gr=1), dict(separate_rain=1),
+                      ("qsep_byrain", "storage_conv", "storage_stra")),
+    "separate_rain_kinematic": (dict(rain_peak_mm=50.0, speed_type=(2, 2, 1)), dict(separate_rain=1),
+                                ("qsep_byrain", "storage_conv", "storage_stra")),
+    # capillary tanks that start empty: (Storage_conv - Evp*Storage_conv/StoOut) is 0/0 and the compiled MAX(0., NaN) is 0
+    "separate_rain_empty_capillary": (dict(rain_peak_mm=50.0), dict(separate_rain=1, _empty_capillary=1),
+                                      ("qsep_byrain", "storage_conv", "storage_stra")),
 }
 
 
@@ -180,6 +187,12 @@ def test_shia_oracle_is_bit_identical_to_the_reference(ref, name, tmp_path):
     dumps = None
     if kw.get("retorno_gr"):
         inp["calib"][9] = 0.02                       # small gravitational capacity: tank 3 does spill back into tank 2
+    if flags.get("separate_rain"):
+        inp.update(synth.make_rain_types(inp, seed))
+    if inp.pop("_empty_capillary", 0):
+        st = np.array(inp["storage"], copy=True)
+        st[0, ::7] = 0.0
+        inp["storage"], inp["storage_constant"] = st, 0.0
     if name == "dump_switches":
         g = np.zeros(T, np.int32)
         g[[3, 20, T - 1]] = [1, 2, 3]

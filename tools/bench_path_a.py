@@ -19,6 +19,9 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", action="store_true", help="verify structural invariants on the host (slow for large N)")
     ap.add_argument("--extras", action="store_true", help="also time basin_map2basin, basin_basics, stream mask and geo_hand (resident)")
+    ap.add_argument("--cpu-ref", action="store_true", help="run the reference's own compiled Fortran (oracle/_ref) on the same "
+                    "raster: time find+cut+acum on one host core and require the GPU tables to be bit-identical to it")
+    ap.add_argument("--cpu-ref-max-cells", type=int, default=70_000_000)
     a = ap.parse_args()
     import torch
     from wmf_b200 import Context, CuModule, synth
@@ -38,6 +41,19 @@ def main():
         cu.ncols, cu.nrows, cu.xll, cu.yll, cu.dx, cu.dy, cu.dxp, cu.nodata = nc, nr, 0.0, 0.0, 30.0, 30.0, 30.0, synth.NODATA
         x, y = synth.outlet_xy(nc, nr, 0.0, 0.0, 30.0)
         d_dir = torch.from_numpy(np.ascontiguousarray(DIR.T)).cuda()
+        cpu = None
+        if a.cpu_ref and nc * nr <= a.cpu_ref_max_cells:
+            from oracle import ref
+            rc = ref.RefCu()
+            rc.ncols, rc.nrows, rc.xll, rc.yll, rc.dx, rc.dy, rc.dxp, rc.nodata = nc, nr, 0.0, 0.0, 30.0, 30.0, 30.0, synth.NODATA
+            t0 = time.perf_counter()
+            rn = rc.basin_find(x, y, DIR)
+            t1 = time.perf_counter()
+            rb = rc.basin_cut(rn)
+            t2 = time.perf_counter()
+            racum = rc.basin_acum(rb)
+            t3 = time.perf_counter()
+            cpu = dict(n=rn, b=rb, acum=racum, find_ms=1e3 * (t1 - t0), cut_ms=1e3 * (t2 - t1), acum_ms=1e3 * (t3 - t2))
         del DIR
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         best = None
@@ -62,6 +78,17 @@ def main():
                 "us_per_level_find": 1e3 * best[0] / max(levels, 1),
                 "achieved_gbs_28B": 28.0 * n / (total / 1e3) / 1e9, "frac_of_measured_hbm": 28.0 * n / (total / 1e3) / 1e9 / peak,
                 "gen_s": gen_s}
+        if cpu is not None:
+            assert cpu["n"] == n
+            same_b = bool((b.cpu().numpy().reshape(-1) == cpu["b"].reshape(-1, order="F")).all())
+            same_a = bool((acum.cpu().numpy().reshape(-1) == cpu["acum"]).all())
+            tot = cpu["find_ms"] + cpu["cut_ms"] + cpu["acum_ms"]
+            line.update({"cpu_reference": {"kind": "reference", "cores": 1, "find_ms": cpu["find_ms"], "cut_ms": cpu["cut_ms"],
+                                           "acum_ms": cpu["acum_ms"], "mcell_per_s": n / tot / 1e3,
+                                           "what": "the reference's own compiled Fortran (oracle/_ref), same raster"},
+                         "bit_exact_vs_reference": same_b and same_a, "speedup_vs_reference": tot / total})
+            assert same_b and same_a, "GPU tables differ from the reference"
+            cpu = None
         if a.extras:
             def timed(fn):
                 torch.cuda.synchronize()

@@ -250,6 +250,28 @@ def make_shia_inputs(structure, acum, hill_long, slope, *, dxp, dt=3600.0, n_reg
     return inp
 
 
+def make_rain_types(inp: dict, seed: int = 0) -> dict:
+    """Rain-type tables for ``separate_rain`` (modelosv2.f90:452-456, 471-474): for every rain record a convective and a
+    stratiform int32 map, stored like the rain (record r at row r-1, record 1 = zeros) and addressed by the same
+    per-step record numbers.  A cell counts as convective / stratiform when ``value / 1000`` (integer division) is not
+    zero: the maps hold 1000 (yes), 0 (no) and a few 500 (-> 0) and 2000 (-> factor 2) to pin that arithmetic."""
+    rain = np.asarray(inp["rain"])
+    R, N = rain.shape
+    cells = np.arange(N, dtype=np.int64)
+    conv = np.zeros((R, N), np.int32)
+    stra = np.zeros((R, N), np.int32)
+    for r in range(1, R):
+        u = u01(seed + 101, np.full(N, r, np.int64), cells)
+        wet = rain[r] > 0
+        c = wet & (u < 0.45)
+        conv[r, c] = 1000
+        stra[r, wet & ~c] = 1000
+        conv[r, wet & (u > 0.97)] = 500
+        stra[r, wet & (u < 0.02)] = 2000
+    return {"conv": conv, "stra": stra, "pos_conv": np.array(inp["pos_evento"], np.int32, copy=True),
+            "pos_stra": np.array(inp["pos_evento"], np.int32, copy=True), "separate_rain": 1}
+
+
 def make_ensemble_calibs(n_members: int, seed: int = 0) -> np.ndarray:
     """(M,11) calibration sets sampled uniformly in the Barbosa NSGA-II notebook ranges
     (Examples/Calibracion_Barbosa_NSGAII.ipynb cell 9), extended to the 11 entries shia_v1 needs."""
@@ -264,7 +286,7 @@ def make_ensemble_calibs(n_members: int, seed: int = 0) -> np.ndarray:
 def apply_to_models(models, inp: dict) -> None:
     """Load a ``make_shia_inputs`` dict into a ``models`` module object the way wmf.py's set_* methods do
     (attribute assignment, wmf.py:3024-3045, 3687-3695, 3882, 3952, 4046-4163)."""
-    skip = {"calib", "rain", "pos_evento", "n_reg", "nceldas", "stoin", "hspeedin"}
+    skip = {"calib", "rain", "pos_evento", "n_reg", "nceldas", "stoin", "hspeedin", "conv", "stra", "pos_conv", "pos_stra"}
     for k, v in inp.items():
         if k in skip:
             continue
