@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define WMF_ABI_VERSION 4
+#define WMF_ABI_VERSION 5
 
 enum {
     WMF_OK = 0,
@@ -147,6 +147,8 @@ typedef struct {
     /* module save_vfluxes / save_rc (modelosv2.f90:83, :392-426): vertical-flux dumps + mean_vfluxes, and the two
      * runoff-coefficient accumulators; save_retorno (above) returns the per-step return-flow map */
     int32_t save_vfluxes, save_rc;
+    /* module separate_rain (modelosv2.f90:91): convective / stratiform shadow storages and Qsep_byrain */
+    int32_t separate_rain;
 } wmf_shia_cfg;
 
 /* Arrays = module `models` allocatables (modelosv2.f90:53-113) in their f2py layouts. */
@@ -179,6 +181,12 @@ typedef struct {
     const int32_t *guarda_cond;
     /* module guarda_vfluxes (n_reg), same convention, for save_vfluxes = 1; NULL = no step is dumped (:399-401) */
     const int32_t *guarda_vfluxes;
+    /* separate_rain = 1: the rain-type maps, held in memory like `rain` (record r at conv + (r-1)*N, int32; a cell is
+     * convective / stratiform at a step when value / 1000 -- integer division -- is non-zero, modelosv2.f90:471-474) and
+     * the record of every step, posConv / posStra (n_reg, 1-based; read on wet steps only, :452-456) */
+    const int32_t *conv, *stra;
+    int32_t n_conv_records, n_stra_records;
+    const int32_t *pos_conv, *pos_stra;
 } wmf_shia_inputs;
 
 /* Outputs.  Any pointer may be NULL (= not wanted).  Shapes as returned by f2py (modelsmodule.c:375-408).
@@ -219,6 +227,9 @@ typedef struct {
     float *rc_coef;
     /* save_retorno = 1: Retorned of every step, (n_reg, N) -- record t of ruta_retorno (:820-823) */
     float *ret_snap;
+    /* separate_rain = 1: Qsep_byrain (n_cont, 2, n_reg) (modelosv2.f90:713-716, :767-770) and the final shadow storages,
+     * module Storage_conv / Storage_stra (5,N) */
+    float *qsep_byrain, *storage_conv, *storage_stra;
 } wmf_shia_outputs;
 
 /* shia_v1, modelosv2.f90:191-869 (+ calc_speed :1278-1293, sed_* :1298-1608, slide_* :1613-1707). */

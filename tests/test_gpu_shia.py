@@ -456,6 +456,52 @@ def test_separate_fluxes():
     np.testing.assert_array_equal(ret0[0], ret[0])
 
 
+@pytest.mark.parametrize("variant", ["linear_return", "kinematic", "empty_capillary"])
+def test_separate_rain(variant, tmp_path):
+    """separate_rain = 1 (modelosv2.f90:346-359, 452-456, 471-474, 485-488, 530-547, 580-592, 605-608, 623-628, 645-655,
+    683-686, 713-716, 767-770): convective / stratiform shadows of the five tanks and Qsep_byrain, including the stale rain
+    types of dry steps, the integer division by 1000 and the 0/0 of an empty capillary tank.  The oracle is bit-identical
+    to the reference's compiled Fortran on these cases (tests/test_reference_pin.py)."""
+    from wmf_b200 import ModelsModule, synth
+    from wmf_b200._models import write_rain_files
+    kw = dict(rain_peak_mm=50.0)
+    if variant == "linear_return":
+        kw.update(retorno_gr=1)
+    if variant == "kinematic":
+        kw.update(speed_type=(2, 2, 1))
+    bs, inp = build("G2", 100, 80, 28, n_reg=90, **kw)
+    if variant == "linear_return":
+        inp["calib"][9] = 0.02
+    if variant == "empty_capillary":
+        st = np.array(inp["storage"], copy=True)
+        st[0, ::7] = 0.0
+        inp["storage"], inp["storage_constant"] = st, 0.0
+    types = synth.make_rain_types(inp, 28)
+    ref = run_oracle(dict(inp, **types))
+    m = ModelsModule()
+    synth.apply_to_models(m, inp)
+    m.set_rain(inp["rain"], inp["pos_evento"])
+    m.separate_rain = 1
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    T, N = inp["n_reg"], bs["n"]
+    if variant == "kinematic":       # through the files, as wmf.py drives it (ruta_binConv, ruta_binStra, ruta_hdrConv, ruta_hdrStra)
+        paths = {}
+        for k in ("conv", "stra"):
+            paths[k] = (str(tmp_path / (k + ".bin")), str(tmp_path / (k + ".hdr")))
+            write_rain_files(paths[k][0], paths[k][1], types[k], np.concatenate([types["pos_" + k][:T], [1]]))
+        ret = m.shia_v1(None, None, inp["calib"], n_cont, 1, T, None, None, N, None, None, None,
+                        paths["conv"][0], paths["stra"][0], paths["conv"][1], paths["stra"][1])
+    else:
+        m.set_rain_types(types["conv"], types["stra"], types["pos_conv"], types["pos_stra"])
+        ret = m.shia_v1(None, None, inp["calib"], n_cont, 1, T, None, None, N)
+    compare_core(ret, m, ref, N)
+    assert ref["qsep_byrain"].max() > 0 and ret[10].shape == ref["qsep_byrain"].shape
+    close(ret[10], ref["qsep_byrain"], name="Qsep_byrain")
+    close(m.storage_conv, ref["storage_conv"], name="Storage_conv")
+    close(m.storage_stra, ref["storage_stra"], name="Storage_stra")
+    assert np.isfinite(m.storage_conv).all()
+
+
 def test_channel_cell_draining_into_hillslope_cell():
     """Unit types are user input: a channel cell may drain into a hillslope cell, whose tank 5 then fills and never
     drains (modelosv2.f90:617-621, 672): no kernel may assume that a hillslope cell's tank 5 is a constant of the run."""

@@ -41,7 +41,7 @@ class ShiaCfg(C.Structure):
         ("sl_gullienogullie", C.c_int32), ("sl_fs", C.c_float), ("sl_gammaw", C.c_float),
         ("n_members", C.c_int32),
         ("save_storage", C.c_int32), ("save_speed", C.c_int32), ("separate_fluxes", C.c_int32),
-        ("save_vfluxes", C.c_int32), ("save_rc", C.c_int32),
+        ("save_vfluxes", C.c_int32), ("save_rc", C.c_int32), ("separate_rain", C.c_int32),
     ]
 
 
@@ -61,6 +61,8 @@ class ShiaInputs(C.Structure):
         ("sl_zs", C.c_void_p), ("sl_gammas", C.c_void_p), ("sl_cohesion", C.c_void_p),
         ("sl_frictionangle", C.c_void_p), ("sl_radslope", C.c_void_p),
         ("guarda_cond", C.c_void_p), ("guarda_vfluxes", C.c_void_p),
+        ("conv", C.c_void_p), ("stra", C.c_void_p), ("n_conv_records", C.c_int32), ("n_stra_records", C.c_int32),
+        ("pos_conv", C.c_void_p), ("pos_stra", C.c_void_p),
     ]
 
 
@@ -70,7 +72,7 @@ _OUT_NAMES = [
     "vs", "vd", "vsc", "vdc", "volero", "voldepo", "erot", "dept",
     "sl_zmin", "sl_zcrit", "sl_zmax", "sl_bo", "sl_riskvector", "sl_slideocurrence",
     "sl_slideacumulate", "sl_slidencelltime", "sto_snap", "speed_snap", "qseparated",
-    "mean_vfluxes", "vfl_snap", "rc_coef", "ret_snap",
+    "mean_vfluxes", "vfl_snap", "rc_coef", "ret_snap", "qsep_byrain", "storage_conv", "storage_stra",
 ]
 
 

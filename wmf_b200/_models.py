@@ -46,7 +46,7 @@ _SCALARS_I = {"nceldas": 0, "ncols": 0, "nrows": 0, "verbose": 0, "rain_first_po
               "show_mean_speed": 0, "show_mean_retorno": 0, "show_area": 0, "separate_fluxes": 0,
               "separate_rain": 0, "sl_gullienogullie": 0}
 # switches whose sub-models are outside the hot path built here
-_UNSUPPORTED = ("sim_floods", "separate_rain")
+_UNSUPPORTED = ("sim_floods",)
 
 
 def read_rain_hdr(ruta_hdr: str, n_reg: int, rain_first_point: int = 1):
@@ -158,6 +158,7 @@ class ModelsModule:
         d["_s"] = dict(_SCALARS_F)
         d["_s"].update(_SCALARS_I)
         d["_rain_mem"] = None
+        d["_rain_types_mem"] = None
         d["_a"]["speed_type"] = np.ones(3, np.int32)
         d["_a"]["wi"] = np.zeros(3, np.float32)
         d["_a"]["diametro"] = np.zeros(3, np.float32)
@@ -228,6 +229,36 @@ class ModelsModule:
         (n_records,N) int32 mm*1000 (numpy or torch CUDA), record 1 must be the all-zero record,
         ``pos_evento`` (n_reg) 1-based.  ``shia_v1(None, None, ...)`` then uses it."""
         object.__getattribute__(self, "__dict__")["_rain_mem"] = (rain, np.ascontiguousarray(pos_evento, np.int32))
+
+    def set_rain_types(self, conv, stra, pos_conv, pos_stra):
+        """Extension (separate_rain = 1): hold the convective / stratiform maps in memory instead of the
+        ``ruta_binConv/ruta_hdrConv/ruta_binStra/ruta_hdrStra`` files.  ``conv`` / ``stra`` are (n_records,N) int32 like the
+        rain table, ``pos_conv`` / ``pos_stra`` (n_reg) 1-based record numbers (modelosv2.f90:452-456)."""
+        object.__getattribute__(self, "__dict__")["_rain_types_mem"] = (
+            np.ascontiguousarray(conv, np.int32), np.ascontiguousarray(stra, np.int32),
+            np.ascontiguousarray(pos_conv, np.int32), np.ascontiguousarray(pos_stra, np.int32))
+
+    def _load_rain_types(self, ruta_binconv, ruta_binstra, ruta_hdrconv, ruta_hdrstra, n_reg, n_cel):
+        """posConv / posStra from the two headers (rain_read_ascii_table_separate, modelosv2.f90:1004-1065: the ``id, record,
+        ...`` rows of the rain header format) and the records they name from the two direct-access binaries."""
+        d = object.__getattribute__(self, "__dict__")
+        if not ruta_binconv and d["_rain_types_mem"] is not None:
+            conv, stra, pc, ps = d["_rain_types_mem"]
+            if pc.size < n_reg or ps.size < n_reg:
+                raise ValueError("set_rain_types: pos_conv / pos_stra shorter than n_reg")
+            return conv, stra, pc[:n_reg].copy(), ps[:n_reg].copy()
+        if not (ruta_binconv and ruta_binstra and ruta_hdrconv and ruta_hdrstra):
+            raise ValueError("models.separate_rain = 1 needs ruta_binconv, ruta_binstra, ruta_hdrconv, ruta_hdrstra "
+                             "(modelosv2.f90:346-359) or set_rain_types()")
+        out = []
+        for rb, rh in ((ruta_binconv, ruta_hdrconv), (ruta_binstra, ruta_hdrstra)):
+            # the separate reader wants Nintervals + rain_first_point <= Ntotal (:1026), one row more than the rain reader
+            _, pos = read_rain_hdr(str(rh).strip(), n_reg + 1, int(self.rain_first_point))
+            pos = pos[:n_reg]
+            n_rec = os.path.getsize(str(rb).strip()) // (4 * n_cel)
+            table = np.fromfile(str(rb).strip(), dtype=np.int32, count=n_rec * n_cel).reshape(n_rec, n_cel)
+            out.append((table, pos))
+        return out[0][0], out[1][0], out[0][1], out[1][1]
 
     def make_resident(self, enable: bool = True):
         """Extension: upload every allocated module array to the GPU once (torch owns the buffers) so that repeated
@@ -302,7 +333,10 @@ class ModelsModule:
             raise ValueError("models.save_rc = 1 needs ruta_rc (modelosv2.f90:863-867)")
         if save_ret and not ruta_retorno:
             raise ValueError("models.save_retorno = 1 needs ruta_retorno (modelosv2.f90:820-823)")
-        out = self._run(calib[None, :], int(n_cont), int(n_conth), T, rain, pos, stoin, hspeedin)
+        types = None
+        if int(self.separate_rain) == 1:
+            types = self._load_rain_types(ruta_binconv, ruta_binstra, ruta_hdrconv, ruta_hdrstra, T, N)
+        out = self._run(calib[None, :], int(n_cont), int(n_conth), T, rain, pos, stoin, hspeedin, rain_types=types)
         # state dumps in the reference's direct-access format: record guarda_cond(t) of ruta_storage holds StoOut(5,N)
         # after step t; record t of ruta_speed holds hspeed(4,N)
         if save_sto:
@@ -327,7 +361,7 @@ class ModelsModule:
         zeros = lambda *s: np.zeros(s, np.float32, order="F")
         qsed = out.get("qsed", zeros(nc, 3, T))
         return (out["q"], qsed, out.get("qseparated", zeros(nc, 3, T)), out["hum"], out["st1"], out["st3"], out["balance"], out["speed"],
-                out["areacontrol"], out["stoout"], zeros(nc, 2, T))
+                out["areacontrol"], out["stoout"], out.get("qsep_byrain", zeros(nc, 2, T)))
 
     def _guarda(self, name, T):
         """guarda_vfluxes as shia_v1 sees it: allocated with >= n_reg entries, else "all zeros" (modelosv2.f90:399-409)."""
@@ -347,7 +381,8 @@ class ModelsModule:
             raise ValueError(f"models.{name} has shape {arr.shape}, expected ({K},{N})")
         return arr
 
-    def _run(self, calibs, n_cont, n_conth, T, rain, pos, stoin=None, hspeedin=None, device_out=False, want=None):
+    def _run(self, calibs, n_cont, n_conth, T, rain, pos, stoin=None, hspeedin=None, device_out=False, want=None,
+             rain_types=None):
         """Marshal module state into one wmf_shia_run call.  ``calibs`` is (M,11)."""
         c = self.ctx
         a = object.__getattribute__(self, "__dict__")["_a"]
@@ -375,6 +410,7 @@ class ModelsModule:
         cfg.save_rc = int(self.save_rc) if M == 1 else 0
         if M != 1:
             cfg.save_retorno = 0
+        cfg.separate_rain = 1 if (rain_types is not None and M == 1) else 0
         keep = []
         si = ShiaInputs()
 
@@ -433,6 +469,13 @@ class ModelsModule:
             g = np.ascontiguousarray(g.reshape(-1)[:T], np.int32)
             n_snap = int(np.count_nonzero(g > 0))
             put("guarda_cond", g)
+        if cfg.separate_rain == 1:
+            conv, stra, pc, ps = rain_types
+            for tab, nm in ((conv, "conv"), (stra, "stra")):
+                if tab.ndim != 2 or tab.shape[1] != N:
+                    raise ValueError(f"{nm} table must be (n_records,{N})")
+            put("conv", conv); put("stra", stra); put("pos_conv", pc); put("pos_stra", ps)
+            si.n_conv_records, si.n_stra_records = int(conv.shape[0]), int(stra.shape[0])
         n_vsnap = 0
         if cfg.save_vfluxes == 1:
             g = self._guarda("guarda_vfluxes", T)
@@ -470,6 +513,8 @@ class ModelsModule:
             out("stoout", (5, N)); out("hspeed_out", (4, N)); out("mean_rain", (1, T)); out("acum_rain", (1, N))
             if cfg.separate_fluxes == 1:
                 out("qseparated", (n_cont, 3, T))
+            if cfg.separate_rain == 1:
+                out("qsep_byrain", (n_cont, 2, T)); out("storage_conv", (5, N)); out("storage_stra", (5, N))
             if cfg.save_storage == 1:
                 out("sto_snap", (5, N, max(n_snap, 1)))
             if cfg.save_speed == 1:
@@ -509,6 +554,7 @@ class ModelsModule:
         if M == 1 and not device_out:
             d = object.__getattribute__(self, "__dict__")
             for k in ("mean_rain", "acum_rain", "mean_storage", "mean_speed", "mean_retorno", "mean_vfluxes", "rc_coef",
+                      "storage_conv", "storage_stra",
                       "retorned", "vs", "vd",
                       "vsc", "vdc", "volero", "voldepo", "sl_zmin", "sl_zcrit", "sl_zmax", "sl_bo", "sl_riskvector",
                       "sl_slideocurrence", "sl_slideacumulate", "sl_slidencelltime"):

@@ -103,6 +103,13 @@ struct ShiaP {
     int want_vmean;         // accumulate red[t][RQ_VFL1..4] = sum over the cells of the four vertical fluxes
     float *rc;              // [2][N] save_rc accumulators (:521-524)
     float *ret_snap;        // [T][N] return flow of every step (save_retorno, :820-823)
+    // separate_rain (:346-359, :452-456, :471-474, :485-488, :530-547, :580-592, :605-608, :623-628, :645-655, :683-686):
+    // convective / stratiform shadows of the five tanks
+    float *shc, *shs;             // [5][N][M] Storage_conv / Storage_stra
+    float4 *cvout4, *srout4;      // [2][K][N][M] shadow water sent downstream at each step of a time block (like outb4)
+    const int32_t *conv, *stra;   // rain-type tables, record r at (r-1)*N
+    const int32_t *effc, *effs;   // [T] record in force at step t (the last one read on a wet step), 0 = none yet
+    float *qsepr;                 // Qsep_byrain (n_cont, 2, n_reg)
     // separate_fluxes (:658-680, :697-704, :752-759): shares of runoff / subsurface / base flow in the channel tank
     float *flx;             // [3][N][M]
     float4 *flxout4;        // [2][K][N][M] (share sent downstream x3, flag: 1 add, 0 "receiver's shares := 0", 2 hillslope cell)
@@ -727,7 +734,7 @@ constexpr int TB_THREADS = TB_THREADS_N;
 #define TB_MIN_BLOCKS 4
 #endif
 
-template <int K, bool CHAN, bool KIN, bool SED, bool SLIDES, bool SNAP, bool SEPF>
+template <int K, bool CHAN, bool KIN, bool SED, bool SLIDES, bool SNAP, bool SEPF, bool SEPR>
 __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int jlo, const int jhi, const int tile,
                                         float *__restrict__ s_acc) {
     const int N = P.N, M = P.M;
@@ -847,6 +854,12 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
     }
     float rc1 = 0.f, rc2 = 0.f;           // save_rc accumulators
     if (SNAP && active && P.rc) { rc1 = P.rc[cell]; rc2 = P.rc[(size_t)N + cell]; }
+    float C0 = 0.f, C1 = 0.f, C2 = 0.f, C3 = 0.f, C4 = 0.f;  // separate_rain: convective shadow of the five tanks
+    float T0 = 0.f, T1 = 0.f, T2 = 0.f, T3 = 0.f, T4 = 0.f;  //                stratiform shadow
+    if (SEPR && active) {
+        C0 = P.shc[base]; C1 = P.shc[NM + base]; C2 = P.shc[2 * NM + base]; C3 = P.shc[3 * NM + base]; C4 = P.shc[4 * NM + base];
+        T0 = P.shs[base]; T1 = P.shs[NM + base]; T2 = P.shs[2 * NM + base]; T3 = P.shs[3 * NM + base]; T4 = P.shs[4 * NM + base];
+    }
     float F0 = 0.f, F1 = 0.f, F2 = 0.f;  // separate_fluxes: the channel tank's shares
     if (SEPF && CHAN && active) { F0 = P.flx[base]; F1 = P.flx[NM + base]; F2 = P.flx[2 * NM + base]; }
     const bool outlet = active && (cell == N - 1);
@@ -874,6 +887,17 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             const float vf1 = fmaxf(0.0f, R - H1 + S0);
             S0 = S0 + R - vf1;
             const float E = fminf(__ldg(P.evp + t) * vs1 * wmf_powf(S0 / H1, 0.6f), S0);
+            float Co = 0.0f, St = 0.0f;
+            if (SEPR) {
+                // rain types in force (:452-456 reads them on wet steps only; :471-474 integer division by 1000)
+                const int ec = __ldg(P.effc + t), es = __ldg(P.effs + t);
+                if (ec > 0) Co = (float)(__ldg(P.conv + (size_t)(ec - 1) * N + cell) / 1000);
+                if (es > 0) St = (float)(__ldg(P.stra + (size_t)(es - 1) * N + cell) / 1000);
+                // :485-488, against the capillary tank before the evaporation leaves; the compiled MAX(0., NaN) is 0
+                const float a = C0 - E * C0 / S0, bq = T0 - E * T0 / S0;
+                C0 = (a > 0.0f) ? a : 0.0f;
+                T0 = (bq > 0.0f) ? bq : 0.0f;
+            }
             S0 = S0 - E;
             // what the upstream neighbours sent this step, added in ascending cell order (:601,:617,:672) -- the
             // reference's children deposit into StoOut(2:5) before the cell itself is processed
@@ -899,6 +923,16 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                     const float4 f = *fp;
                     if (f.w == 1.0f) { F0 = F0 + f.x; F1 = F1 + f.y; F2 = F2 + f.z; }
                     else if (f.w == 0.0f) { F0 = 0.0f; F1 = 0.0f; F2 = 0.0f; }
+                }
+            }
+            if (SEPR) {  // the shadows the upstream cells sent this step, in cell order (:605-608, :623-625, :683-686)
+                const float4 *cp = P.cvout4 + ((size_t)(b & 1) * K + tt) * NM + (size_t)c0 * M + m;
+                const float4 *sp = P.srout4 + ((size_t)(b & 1) * K + tt) * NM + (size_t)c0 * M + m;
+#pragma unroll 1
+                for (int c = 0; c < nch; ++c, cp += M, sp += M) {
+                    const float4 a = *cp, bq = *sp;
+                    C1 = C1 + a.x; C2 = C2 + a.y; C3 = C3 + a.z; C4 = C4 + a.w;
+                    T1 = T1 + bq.x; T2 = T2 + bq.y; T3 = T3 + bq.z; T4 = T4 + bq.w;
                 }
             }
             if (SED) {
@@ -940,6 +974,18 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                 ret_acc = ret_acc + Ret;
                 ret_step = Ret;
             }
+            if (SEPR) {  // :530-547: vflux(2:3) already carry the return flow (:510-511), and Ret is applied once more
+                const bool rg = P.retorno_gr > 0.0f;
+                const float w2 = rg ? vf2 + ret_step : vf2, w3 = rg ? vf3 - ret_step : vf3;
+                C0 = C0 + (R - vf1) * Co; T0 = T0 + (R - vf1) * St;
+                C1 = C1 + (vf1 - w2) * Co; T1 = T1 + (vf1 - w2) * St;
+                C2 = C2 + (w2 - w3) * Co; T2 = T2 + (w2 - w3) * St;
+                C3 = C3 + (w3 - vf4) * Co; T3 = T3 + (w3 - vf4) * St;
+                if (rg) {
+                    C1 = C1 + ret_step * Co; C2 = C2 - ret_step * Co;
+                    T1 = T1 + ret_step * St; T2 = T2 - ret_step * St;
+                }
+            }
             if (SNAP) {  // the dumps that follow the vertical fluxes; vflux(2:3) carry the return flow (:509-510)
                 vx1 = vf1; vx4 = vf4;
                 vx2 = (P.retorno_gr > 0.0f) ? vf2 + ret_step : vf2;
@@ -954,8 +1000,10 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             float sal = vf4 + E;
             // hillslope outflows of tanks 2..4 (:553-595)
             float h0, h1, h2;
+            float hc[3] = {0.f, 0.f, 0.f}, hs[3] = {0.f, 0.f, 0.f};  // separate_rain: shadow outflows of tanks 2..4
             {
                 float Sk[3] = {S1, S2, S3}, hk[3];
+                float Ck[3] = {C1, C2, C3}, Tk[3] = {T1, T2, T3};
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     if (!KIN || P.st[k] == 1) {
@@ -968,8 +1016,17 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                             sed_hillslope_dev(P, SL, P.sed_factor, kv[0], Sk[0], __ldg(P.hill_slope + cell), qlin, cell, type);
                         }
                     }
+                    if (SEPR) {  // :580-592, in proportion to the tank before the outflow leaves
+                        if (Sk[k] > 0.0f) {
+                            hc[k] = hk[k] * Ck[k] / Sk[k];
+                            hs[k] = hk[k] * Tk[k] / Sk[k];
+                        }
+                        Ck[k] = Ck[k] - hc[k];
+                        Tk[k] = Tk[k] - hs[k];
+                    }
                     Sk[k] = Sk[k] - hk[k];
                 }
+                if (SEPR) { C1 = Ck[0]; C2 = Ck[1]; C3 = Ck[2]; T1 = Tk[0]; T2 = Tk[1]; T3 = Tk[2]; }
                 S1 = Sk[0]; S2 = Sk[1]; S3 = Sk[2];
                 h0 = hk[0]; h1 = hk[1]; h2 = hk[2];
             }
@@ -985,6 +1042,10 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                     sal = sal + s3;
                 }
                 if (rowq >= 0 && P.q) P.q[qoff_of() + rowq] = 0.0f;
+                if (SEPR) {
+                    P.cvout4[((size_t)(b & 1) * K + tt) * NM + base] = make_float4(hc[0], hc[1], hc[2], 0.0f);
+                    P.srout4[((size_t)(b & 1) * K + tt) * NM + base] = make_float4(hs[0], hs[1], hs[2], 0.0f);
+                }
                 if (SEPF) P.flxout4[((size_t)(b & 1) * K + tt) * NM + base] = make_float4(0.f, 0.f, 0.f, 2.0f);
                 if (SED && P.st[0] == 2) {  // hillslope cell: single VolDEPo / VolERO increment (:1426-1427)
                     vdep = vdep + SL.voldepo_add;
@@ -992,8 +1053,25 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                 }
             } else {
                 S4 = S4 + (h0 + h1) + h2 * (float)(type - 2);
+                if (SEPR) {  // :623-628
+                    C4 = C4 + (hc[0] + hc[1]) + hc[2] * (float)(type - 2);
+                    T4 = T4 + (hs[0] + hs[1]) + hs[2] * (float)(type - 2);
+                }
                 const float sec_area = calc_speed_dev(S4 * m3, ccoef, cexpo, Ls, vch, dt, P.niter);
                 const float h3 = fminf(sec_area * vch * dt / m3, S4);
+                if (SEPR) {  // :645-655 (the channel tank before the outflow leaves), :683-686, :713-716, :767-770
+                    float c3 = 0.0f, s3 = 0.0f;
+                    if (S4 != 0.0f) { c3 = h3 * C4 / S4; s3 = h3 * T4 / S4; }
+                    C4 = C4 - c3;
+                    T4 = T4 - s3;
+                    P.cvout4[((size_t)(b & 1) * K + tt) * NM + base] = make_float4(0.0f, 0.0f, hc[2] * (float)(3 - type), c3);
+                    P.srout4[((size_t)(b & 1) * K + tt) * NM + base] = make_float4(0.0f, 0.0f, hs[2] * (float)(3 - type), s3);
+                    if (P.qsepr && (outlet || rowq >= 0)) {
+                        const size_t k2 = ((size_t)m * P.T + t) * 2 * P.n_cont + (outlet ? 0 : (size_t)rowq);
+                        P.qsepr[k2] = c3 * m3 / dt;
+                        P.qsepr[k2 + P.n_cont] = s3 * m3 / dt;
+                    }
+                }
                 float Vsal[3] = {0.f, 0.f, 0.f};
                 if (SED) {
                     float vd2 = 0.f;
@@ -1161,6 +1239,10 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
         }
         if (SLIDES) P.sl_slid[cell] = sl_slid;
         if (SEPF && CHAN) { P.flx[base] = F0; P.flx[NM + base] = F1; P.flx[2 * NM + base] = F2; }
+        if (SEPR) {
+            P.shc[base] = C0; P.shc[NM + base] = C1; P.shc[2 * NM + base] = C2; P.shc[3 * NM + base] = C3; P.shc[4 * NM + base] = C4;
+            P.shs[base] = T0; P.shs[NM + base] = T1; P.shs[2 * NM + base] = T2; P.shs[3 * NM + base] = T3; P.shs[4 * NM + base] = T4;
+        }
         if (SNAP && P.rc) { P.rc[cell] = rc1; P.rc[(size_t)N + cell] = rc2; }
     }
     if (SED) {  // EROt / DEPt (:1403, :1420): global totals, fp64
@@ -1206,18 +1288,18 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
 
 // Every CTA carries the same mix of roles: its first `cpb` warps take 32-thread tiles of the channel list, the
 // others tiles of the hillslope list, so the SMs stay balanced although a channel thread costs ~4x a hillslope one.
-template <int K, bool KIN, bool SED, bool SLIDES, bool SNAP, bool SEPF>
-__global__ void __launch_bounds__(TB_THREADS, SED ? 2 : TB_MIN_BLOCKS)
+template <int K, bool KIN, bool SED, bool SLIDES, bool SNAP, bool SEPF, bool SEPR>
+__global__ void __launch_bounds__(TB_THREADS, (SED || SEPR) ? 2 : TB_MIN_BLOCKS)
 k_shia_tb(const __grid_constant__ ShiaP P, const int w, const int clo, const int chi, const int hlo, const int hhi,
           const int cpb, const int n_ctiles, const int n_htiles) {
     __shared__ float s_acc[K * TB_THREADS];
     const int wi = threadIdx.x >> 5;
     if (wi < cpb) {
         const int tile = (int)blockIdx.x * cpb + wi;
-        if (tile < n_ctiles) tb_role<K, true, KIN, SED, SLIDES, SNAP, SEPF>(P, w, clo, chi, tile, s_acc);
+        if (tile < n_ctiles) tb_role<K, true, KIN, SED, SLIDES, SNAP, SEPF, SEPR>(P, w, clo, chi, tile, s_acc);
     } else {
         const int tile = (int)blockIdx.x * (TB_THREADS / 32 - cpb) + (wi - cpb);
-        if (tile < n_htiles) tb_role<K, false, KIN, SED, SLIDES, SNAP, SEPF>(P, w, hlo, hhi, tile, s_acc);
+        if (tile < n_htiles) tb_role<K, false, KIN, SED, SLIDES, SNAP, SEPF, SEPR>(P, w, hlo, hhi, tile, s_acc);
     }
 }
 
@@ -1467,6 +1549,14 @@ __global__ void k_shia_epilogue(const double *__restrict__ red, const double *__
     if (mean_retorno) mean_retorno[t] = (float)(q(t, RQ_RET) / (double)n);
     if (mean_vfluxes)
         for (int k = 0; k < 4; ++k) mean_vfluxes[4 * (size_t)t + k] = (float)(q(t, RQ_VFL1 + k) / (double)n);
+}
+
+// Storage_conv / Storage_stra: SoA [5][N] state -> the (5,N) f2py layout
+__global__ void k_shadow_final(const float *__restrict__ sh, int N, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) out[5 * (size_t)i + k] = sh[(size_t)k * N + i];
 }
 
 // save_rc epilogue (:863-867): rc(1) = min(rc(1), rc(2)), SoA accumulators -> the (2,N) f2py layout
@@ -1755,7 +1845,7 @@ static void launch_wave(wmf_ctx *ctx, const ShiaP &P, int w, int lo, int hi) {
     ctx->launches++;
 }
 
-template <int K, bool SED = false, bool SLIDES = false, bool SNAP = false, bool SEPF = false>
+template <int K, bool SED = false, bool SLIDES = false, bool SNAP = false, bool SEPF = false, bool SEPR = false>
 static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int hlo, int hhi, bool pdl) {
     constexpr int WPB = TB_THREADS / 32;
     const int wc = (int)(((long long)(chi - clo) * P.M + 31) / 32), wh = (int)(((long long)(hhi - hlo) * P.M + 31) / 32);
@@ -1781,8 +1871,8 @@ static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     const bool kin = P.st[0] == 2 || P.st[1] == 2 || P.st[2] == 2;
-    if (kin) cudaLaunchKernelEx(&cfg, k_shia_tb<K, true, SED, SLIDES, SNAP, SEPF>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
-    else cudaLaunchKernelEx(&cfg, k_shia_tb<K, false, SED, SLIDES, SNAP, SEPF>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
+    if (kin) cudaLaunchKernelEx(&cfg, k_shia_tb<K, true, SED, SLIDES, SNAP, SEPF, SEPR>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
+    else cudaLaunchKernelEx(&cfg, k_shia_tb<K, false, SED, SLIDES, SNAP, SEPF, SEPR>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
     ctx->launches++;
 }
 
@@ -2006,11 +2096,14 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     const bool snap = (cfg->save_storage == 1 && out->sto_snap) || (cfg->save_speed == 1 && out->speed_snap) || vdump || rcdump || retdump;
     if (KT && (sed || slides || snap)) KT = (T >= 4) ? 4 : 0;  // sediment / slide / dump variants are built for K = 4 only
     const bool sepf = cfg->separate_fluxes == 1;
-    if (sepf) {
-        if (sed || slides || snap || !tb_ok || M != 1)
-            WMF_FAIL(ctx, WMF_ERR_ARG, "shia: separate_fluxes cannot be combined with sediments, slides, state dumps, show_* means or ensembles");
+    const bool sepr = cfg->separate_rain == 1;
+    if (sepf || sepr) {
+        if (sed || slides || snap || !tb_ok || M != 1 || (sepf && sepr))
+            WMF_FAIL(ctx, WMF_ERR_ARG, "shia: separate_fluxes / separate_rain cannot be combined with each other, sediments, slides, state dumps, show_* means or ensembles");
         KT = (T >= 4) ? 4 : 1;
     }
+    if (sepr && (!in->conv || !in->stra || !in->pos_conv || !in->pos_stra || in->n_conv_records < 1 || in->n_stra_records < 1))
+        WMF_FAIL(ctx, WMF_ERR_ARG, "shia: separate_rain = 1 needs the conv / stra tables and pos_conv / pos_stra");
     std::vector<int32_t> h_hfirst;
     int64_t n_hill = 0;
     if (KT) {
@@ -2047,6 +2140,40 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
             WMF_TRY(sc.alloc(&P.flxout4, (size_t)2 * KT * NM));
             CU_TRY(ctx, cudaMemsetAsync(P.flx, 0, sizeof(float) * 3 * NM, ctx->stream));  // Fluxes = 0 (:343)
         }
+        if (sepr) {
+            WMF_TRY(sc.alloc(&P.shc, 5 * NM));
+            WMF_TRY(sc.alloc(&P.shs, 5 * NM));
+            WMF_TRY(sc.alloc(&P.cvout4, (size_t)2 * KT * NM));
+            WMF_TRY(sc.alloc(&P.srout4, (size_t)2 * KT * NM));
+            CU_TRY(ctx, cudaMemsetAsync(P.shc, 0, sizeof(float) * 5 * NM, ctx->stream));  // Storage_conv = Storage_stra = 0 (:351-352)
+            CU_TRY(ctx, cudaMemsetAsync(P.shs, 0, sizeof(float) * 5 * NM, ctx->stream));
+            WMF_TRY(sc.in(in->conv, (size_t)in->n_conv_records * N, &P.conv));
+            WMF_TRY(sc.in(in->stra, (size_t)in->n_stra_records * N, &P.stra));
+            // record in force at every step: Conv / Stra are read on wet steps only (:452-456); a record outside the file
+            // fails the read and leaves the vector as it was
+            std::vector<int32_t> pe((size_t)T), pc((size_t)T), ps((size_t)T), eff((size_t)2 * T);
+            const int32_t *src[3] = {in->pos_evento, in->pos_conv, in->pos_stra};
+            int32_t *dst[3] = {pe.data(), pc.data(), ps.data()};
+            for (int k = 0; k < 3; ++k) {
+                if (Scope::on_device(src[k])) CU_TRY(ctx, cudaMemcpy(dst[k], src[k], sizeof(int32_t) * T, cudaMemcpyDeviceToHost));
+                else memcpy(dst[k], src[k], sizeof(int32_t) * T);
+            }
+            int32_t ec = 0, es = 0;
+            for (int t = 0; t < T; ++t) {
+                if (pe[t] != 1) {
+                    if (pc[t] >= 1 && pc[t] <= in->n_conv_records) ec = pc[t];
+                    if (ps[t] >= 1 && ps[t] <= in->n_stra_records) es = ps[t];
+                }
+                eff[t] = ec;
+                eff[(size_t)T + t] = es;
+            }
+            int32_t *d_eff;
+            WMF_TRY(sc.alloc(&d_eff, (size_t)2 * T));
+            CU_TRY(ctx, cudaMemcpyAsync(d_eff, eff.data(), sizeof(int32_t) * 2 * T, cudaMemcpyHostToDevice, ctx->stream));
+            CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // `eff` goes out of scope
+            P.effc = d_eff;
+            P.effs = d_eff + T;
+        }
         LAUNCH(ctx, k_state_init_tb, G, B, 0, use_stoin ? d_stoin : d_storage, use_stoin ? 0.0f : cfg->storage_constant, N, M, P.st4, P.s5);
     } else {
         WMF_TRY(sc.alloc(&P.outb, 8 * NM));
@@ -2064,6 +2191,10 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     if (sepf) {
         WMF_TRY(sc.out(out->qseparated, QN * 3, &P.qsep));
         if (P.qsep) CU_TRY(ctx, cudaMemsetAsync(P.qsep, 0, sizeof(float) * QN * 3, ctx->stream));
+    }
+    if (sepr) {
+        WMF_TRY(sc.out(out->qsep_byrain, QN * 2, &P.qsepr));
+        if (P.qsepr) CU_TRY(ctx, cudaMemsetAsync(P.qsepr, 0, sizeof(float) * QN * 2, ctx->stream));
     }
     if (P.q) CU_TRY(ctx, cudaMemsetAsync(P.q, 0, sizeof(float) * QN, ctx->stream));
     if (P.speed) CU_TRY(ctx, cudaMemsetAsync(P.speed, 0, sizeof(float) * QN, ctx->stream));
@@ -2216,6 +2347,11 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
             const int clo = lo - hlo, chi = hi - hhi;
             const bool pdl = use_pdl && launched_any;  // the first wave follows memsets and plan kernels: plain launch
             launched_any = true;
+            if (sepr) {  // separate_rain: K = 4 (or 1 for runs shorter than 4 steps)
+                if (KT == 4) launch_tb<4, false, false, false, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
+                else launch_tb<1, false, false, false, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
+                continue;
+            }
             if (sepf) {  // separate_fluxes: K = 4 (or 1 for runs shorter than 4 steps)
                 if (KT == 4) launch_tb<4, false, false, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
                 else launch_tb<1, false, false, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
@@ -2283,6 +2419,13 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
                d_balance, d_mean_rain, d_mean_storage, d_mean_speed, d_mean_retorno, d_mean_vfluxes);
     }
     if (d_rc_out) LAUNCH(ctx, k_rc_final, G, B, 0, P.rc, N, d_rc_out);
+    if (sepr) {
+        float *oc = nullptr, *os = nullptr;
+        WMF_TRY(sc.out(out->storage_conv, 5 * NM, &oc));
+        WMF_TRY(sc.out(out->storage_stra, 5 * NM, &os));
+        if (oc) LAUNCH(ctx, k_shadow_final, G, B, 0, P.shc, N, oc);
+        if (os) LAUNCH(ctx, k_shadow_final, G, B, 0, P.shs, N, os);
+    }
     if (sed) {
         float *vs, *vd, *vsc, *vdc, *ve, *vdp, *erot, *dept;
         WMF_TRY(sc.out(out->vs, 3 * NM, &vs)); WMF_TRY(sc.out(out->vd, 3 * NM, &vd));
