@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define WMF_ABI_VERSION 5
+#define WMF_ABI_VERSION 6
 
 enum {
     WMF_OK = 0,
@@ -240,6 +240,20 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
  * control row to score (wmf.py:875 uses Qsim[nodo]); scores: (M,2) = [nash, qpico]. */
 int wmf_eval_scores(wmf_ctx *ctx, const float *q, int32_t n_members, int32_t n_cont, int32_t n_reg,
                     int32_t row, const float *qobs, float *scores);
+
+/* Rainfall interpolation, cells model: rain_idw (modelosv2.f90:1195-1271) and rain_mit (:1104-1194).
+ * xy_basin (2,nceldas), coord (2,ncoord), rain (ncoord,nreg) in their f2py layouts; tin (3,ntin) 1-based station ids and
+ * tin_perte (nceldas) 1-based triangle of every cell for the TIN variant.  Instead of writing records to `ruta` the wet
+ * fields go to `table` (capacity rows x nceldas int32, mm*1000 truncated; host or device): row 0 = the all-zero record 1,
+ * row k-1 = record k -- exactly the table wmf_shia_inputs.rain takes, with pos_ids as pos_evento.  mean_rain / pos_ids
+ * (nreg) as the Fortran returns them (the field sums are accumulated in fp64).  *n_records = rows the table needs; with
+ * table = NULL only the statistics are computed (query the size first, or pass capacity = nreg + 1). */
+int wmf_rain_idw(wmf_ctx *ctx, const float *xy_basin, const float *coord, const float *rain, float pp,
+                 int32_t nceldas, int32_t ncoord, int32_t nreg, float umbral, int32_t *table, int32_t capacity,
+                 float *mean_rain, int32_t *pos_ids, int32_t *n_records);
+int wmf_rain_mit(wmf_ctx *ctx, const float *xy_basin, const float *coord, const float *rain, const int32_t *tin,
+                 const int32_t *tin_perte, int32_t nceldas, int32_t ncoord, int32_t ntin, int32_t nreg, float umbral,
+                 int32_t *table, int32_t capacity, float *mean_rain, int32_t *pos_ids, int32_t *n_records);
 
 /* calc_speed, modelosv2.f90:1278-1293 (one evaluation on the device; mirrors the f2py export) */
 int wmf_calc_speed(wmf_ctx *ctx, float sm, float coef, float expo, float elem_long, float dt,

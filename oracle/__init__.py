@@ -468,3 +468,36 @@ def calc_speed(sm, coef, expo, elem_long, speed, dt, calc_niter=5):
     area = lib().wo_calc_speed(C.c_float(sm), C.c_float(coef), C.c_float(expo), C.c_float(elem_long),
                                C.byref(s), C.c_float(dt), int(calc_niter))
     return float(area), float(s.value)
+
+
+def _rain_common(L, fn, args, n, T):
+    cap = T + 1
+    table = np.zeros((cap, n), np.int32)
+    mean, pos, mean64 = np.zeros(T, np.float32), np.zeros(T, np.int32), np.zeros(T, np.float64)
+    fn.restype = C.c_int32
+    nrec = fn(*args, _p(table, i32p), cap, _p(mean, f32p), _p(pos, i32p), _p(mean64, f64p))
+    if nrec < 1:
+        raise ValueError("oracle rain interpolation failed")
+    return dict(table=table[:nrec].copy(), mean_rain=mean, pos_ids=pos, mean_rain64=mean64)
+
+
+def rain_idw(xy_basin, coord, rain, pp, umbral):
+    """modelosv2.f90:1195-1271 (cells model).  xy_basin (2,N), coord (2,ncoord), rain (ncoord,nreg); returns the record
+    table the Fortran writes to ``ruta`` (row 0 = record 1 = zeros), meanRain, posIds (+ an fp64 twin of meanRain)."""
+    L = lib()
+    xy, co, r = _f(xy_basin), _f(coord), _f(rain)
+    n, nc, T = xy.shape[1], co.shape[1], r.shape[1]
+    assert xy.shape[0] == 2 and co.shape[0] == 2 and r.shape[0] == nc
+    args = (_p(xy, f32p), _p(co, f32p), _p(r, f32p), C.c_float(pp), n, nc, T, C.c_float(umbral))
+    return _rain_common(L, L.wo_rain_idw, args, n, T)
+
+
+def rain_mit(xy_basin, coord, rain, tin, tin_perte, umbral):
+    """modelosv2.f90:1104-1194 (cells model).  tin (3,ntin) 1-based station ids, tin_perte (N) 1-based triangle of each cell."""
+    L = lib()
+    xy, co, r = _f(xy_basin), _f(coord), _f(rain)
+    tn = _i(tin)
+    tp = np.ascontiguousarray(np.asarray(tin_perte).reshape(-1), np.int32)
+    n, nc, T = xy.shape[1], co.shape[1], r.shape[1]
+    args = (_p(xy, f32p), _p(co, f32p), _p(r, f32p), _p(tn, i32p), _p(tp, i32p), n, nc, tn.shape[1], T, C.c_float(umbral))
+    return _rain_common(L, L.wo_rain_mit, args, n, T)

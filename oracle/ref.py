@@ -471,3 +471,52 @@ def calc_speed(sm, coef, expo, elem_long, speed, dt, calc_niter=5):
     s, area = f32(speed), f32()
     _call(MODELS, "calc_speed", f32(sm), f32(coef), f32(expo), f32(elem_long), s, area)
     return area.value, s.value
+
+
+def _read_records(path, n):
+    raw = np.fromfile(path, np.int32)
+    return raw.reshape(-1, n)
+
+
+def rain_idw(xy_basin, coord, rain, pp, umbral, workdir=None):
+    """The reference's ``rain_idw`` (modelosv2.f90:1195-1271), cells model: returns what it writes to ``ruta`` as a record
+    table plus meanRain / posIds."""
+    xy, co, r = _f(xy_basin), _f(coord), _f(rain)
+    n, nc, T = xy.shape[1], co.shape[1], r.shape[1]
+    tmp = tempfile.TemporaryDirectory(prefix="wref_") if workdir is None else None
+    path = os.path.join(workdir or tmp.name, "idw.bin")
+    mean, pos = np.zeros(T, np.float32), np.zeros(T, np.int32)
+    mask = np.ones(n, np.int32)
+    _call(MODELS, "rain_idw", xy, co, r, f32(pp), i32(n), i32(nc), i32(T), i32(0), _ruta(path, 255), f32(umbral), mean, pos,
+          mask, 255)
+    out = dict(table=_read_records(path, n), mean_rain=mean, pos_ids=pos)
+    if tmp is not None:
+        tmp.cleanup()
+    return out
+
+
+def rain_mit(xy_basin, coord, rain, tin, tin_perte, umbral, workdir=None):
+    """The reference's ``rain_mit`` (modelosv2.f90:1104-1194), cells model."""
+    xy, co, r = _f(xy_basin), _f(coord), _f(rain)
+    tn = _i(tin)
+    tp = np.asfortranarray(np.asarray(tin_perte, np.int32).reshape(1, -1))
+    n, nc, T = xy.shape[1], co.shape[1], r.shape[1]
+    tmp = tempfile.TemporaryDirectory(prefix="wref_") if workdir is None else None
+    path = os.path.join(workdir or tmp.name, "mit.bin")
+    mean, pos = np.zeros(T, np.float32), np.zeros(T, np.int32)
+    mask = np.ones(n, np.int32)
+    _call(MODELS, "rain_mit", xy, co, r, tn, tp, i32(n), i32(0), i32(nc), i32(tn.shape[1]), i32(T), _ruta(path, 255),
+          f32(umbral), mean, pos, mask, 255)
+    out = dict(table=_read_records(path, n), mean_rain=mean, pos_ids=pos)
+    if tmp is not None:
+        tmp.cleanup()
+    return out
+
+
+def rain_pre_mit(xy_basin, tin, coord):
+    """``tin_perte = rain_pre_mit(xy_basin, tin, coord)`` (modelosv2.f90:1068-1101): the triangle holding every cell."""
+    xy, co, tn = _f(xy_basin), _f(coord), _i(tin)
+    n = xy.shape[1]
+    out = np.zeros((1, n), np.int32, order="F")
+    _call(MODELS, "rain_pre_mit", out, xy, tn, co, i32(n), i32(tn.shape[1]), i32(co.shape[1]))
+    return out.reshape(-1)

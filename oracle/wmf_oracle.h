@@ -160,6 +160,17 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out);
 float wo_calc_speed(float sm, float coef, float expo, float elem_long, float *speed, float dt,
                     int32_t calc_niter);
 
+/* rain_idw (modelosv2.f90:1195-1271) and rain_mit (:1104-1194), cells model (maskVector all ones).  Instead of writing
+ * records to `ruta`, the wet fields go to table (capacity rows x nceldas int32, mm*1000 truncated): row 0 = the all-zero
+ * record 1, row k-1 = record k.  mean_rain / pos_ids (nreg) as the Fortran returns them; mean_rain64 (may be NULL) is the
+ * fp64 twin of the sequential fp32 sum.  Returns the number of records written (>= 1), or -1 when capacity is too small. */
+int32_t wo_rain_idw(const float *xy_basin, const float *coord, const float *rain, float pp, int32_t nceldas,
+                    int32_t ncoord, int32_t nreg, float umbral, int32_t *table, int32_t capacity, float *mean_rain,
+                    int32_t *pos_ids, double *mean_rain64);
+int32_t wo_rain_mit(const float *xy_basin, const float *coord, const float *rain, const int32_t *tin,
+                    const int32_t *tin_perte, int32_t nceldas, int32_t ncoord, int32_t ntin, int32_t nreg, float umbral,
+                    int32_t *table, int32_t capacity, float *mean_rain, int32_t *pos_ids, double *mean_rain64);
+
 #ifdef __cplusplus
 }
 #endif

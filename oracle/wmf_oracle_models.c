@@ -278,6 +278,8 @@ static double sum_d(const float *a, size_t n)
 /* gfortran 5.3's inline MAX(0.0, x) as compiled in the reference object: 0 when x is NaN (an empty capillary tank makes
    :486 a 0/0; checked against oracle/_ref) */
 #define WO_FMAX0(x) (((x) > 0.0f) ? (x) : 0.0f)
+/* MAX(x, 0.0) with the operands the other way round (rain_idw / rain_mit); NaN behaviour checked against oracle/_ref */
+#define WO_MAXX0(x) (((x) > 0.0f) ? (x) : 0.0f)
 
 /* modelosv2.f90:191-869 */
 int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
@@ -681,4 +683,99 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
     free(Stra);
     free(vfl_map);
     return 0;
+}
+
+/* ---- rain interpolation, modelosv2.f90:1104-1271 (cells model) ---- */
+/* what both routines do with a finished field (:1166-1190, :1244-1268) */
+static int rain_store(const float *campo, int32_t n, float umbral, int32_t t, int32_t *cont, int32_t *table,
+                      int32_t capacity, float *mean_rain, int32_t *pos_ids, double *mean_rain64)
+{
+    float s = 0.0f;
+    double s64 = 0.0;
+    int32_t n_umbral = 0, n_pos = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        s += campo[i];
+        s64 += (double)campo[i];
+        if (campo[i] > umbral) ++n_umbral;
+        if (campo[i] > 0.0f) ++n_pos;
+    }
+    if (s > umbral && n_umbral > 0) {
+        mean_rain[t] = s / (float)n_pos;
+        if (mean_rain64) mean_rain64[t] = s64 / (double)n_pos;
+        if (*cont > capacity) return -1;
+        int32_t *rec = table + (size_t)(*cont - 1) * n;
+        for (int32_t i = 0; i < n; ++i) rec[i] = (int32_t)(campo[i] * 1000.0f); /* campoInt = campo*1000 truncates */
+        pos_ids[t] = *cont;
+        *cont = *cont + 1;
+    } else {
+        mean_rain[t] = 0.0f;
+        if (mean_rain64) mean_rain64[t] = 0.0;
+        pos_ids[t] = 1;
+    }
+    return 0;
+}
+
+/* modelosv2.f90:1195-1271 */
+int32_t wo_rain_idw(const float *xy_basin, const float *coord, const float *rain, float pp, int32_t nceldas,
+                    int32_t ncoord, int32_t nreg, float umbral, int32_t *table, int32_t capacity, float *mean_rain,
+                    int32_t *pos_ids, double *mean_rain64)
+{
+    if (capacity < 1) return -1;
+    float *W = (float *)malloc(sizeof(float) * (size_t)ncoord * nceldas); /* W(ncoord,nceldas) */
+    float *campo = (float *)malloc(sizeof(float) * (size_t)nceldas);
+    for (int32_t c = 0; c < nceldas; ++c) table[c] = 0; /* record 1 = zeros (:1224) */
+    for (int32_t i = 0; i < ncoord; ++i) /* :1227-1229 */
+        for (int32_t c = 0; c < nceldas; ++c) {
+            const float dxs = coord[2 * i] - xy_basin[2 * (size_t)c], dys = coord[2 * i + 1] - xy_basin[2 * (size_t)c + 1];
+            W[(size_t)c * ncoord + i] = 1.0f / powf(sqrtf(dxs * dxs + dys * dys), pp);
+        }
+    int32_t cont = 2, rc = 0;
+    for (int32_t t = 0; t < nreg && rc == 0; ++t) {
+        const float *r = rain + (size_t)t * ncoord;
+        for (int32_t c = 0; c < nceldas; ++c) { /* :1234-1242 */
+            float Wr = 0.0f, den = 0.0f;
+            for (int32_t i = 0; i < ncoord; ++i) {
+                if (r[i] > 0.0f) Wr = Wr + W[(size_t)c * ncoord + i] * r[i];
+                if (r[i] >= 0.0f) den = den + W[(size_t)c * ncoord + i];
+            }
+            const float q = Wr / den;
+            const float valor = WO_MAXX0(q);
+            campo[c] = (valor == valor - 1.0f) ? 0.0f : valor;
+        }
+        rc = rain_store(campo, nceldas, umbral, t, &cont, table, capacity, mean_rain, pos_ids, mean_rain64);
+    }
+    free(W);
+    free(campo);
+    return rc ? -1 : cont - 1;
+}
+
+/* modelosv2.f90:1104-1194 */
+int32_t wo_rain_mit(const float *xy_basin, const float *coord, const float *rain, const int32_t *tin,
+                    const int32_t *tin_perte, int32_t nceldas, int32_t ncoord, int32_t ntin, int32_t nreg, float umbral,
+                    int32_t *table, int32_t capacity, float *mean_rain, int32_t *pos_ids, double *mean_rain64)
+{
+    if (capacity < 1) return -1;
+    float *campo = (float *)malloc(sizeof(float) * (size_t)nceldas);
+    for (int32_t c = 0; c < nceldas; ++c) table[c] = 0;
+    int32_t cont = 2, rc = 0;
+    for (int32_t t = 0; t < nreg && rc == 0; ++t) {
+        const float *r = rain + (size_t)t * ncoord;
+        for (int32_t c = 0; c < nceldas; ++c) {
+            const int32_t tri = tin_perte[c] - 1;
+            const int32_t ia = tin[3 * tri] - 1, ib = tin[3 * tri + 1] - 1, ic = tin[3 * tri + 2] - 1;
+            const float ax = coord[2 * ia], ay = coord[2 * ia + 1], bx = coord[2 * ib], by = coord[2 * ib + 1];
+            const float cx = coord[2 * ic], cy = coord[2 * ic + 1];
+            const float coef1 = (bx - ax) * (cy - ay) - (cx - ax) * (by - ay); /* :1150 */
+            const float Cel_x = xy_basin[2 * (size_t)c], Cel_y = xy_basin[2 * (size_t)c + 1];
+            const float az = fmaxf(r[ia], 0.0f), bz = fmaxf(r[ib], 0.0f), cz = fmaxf(r[ic], 0.0f);
+            const float det1 = (cx - ax) * (Cel_y - ay), det2 = (by - ay) * (Cel_x - ax);
+            const float det3 = (cy - ay) * (Cel_x - ax), det4 = (Cel_y - ay) * (bx - ax);
+            const float coef2 = det1 * (bz - az) + det2 * (cz - az) - det3 * (bz - az) - det4 * (cz - az);
+            const float q = az - coef2 / coef1;
+            campo[c] = WO_MAXX0(q);
+        }
+        rc = rain_store(campo, nceldas, umbral, t, &cont, table, capacity, mean_rain, pos_ids, mean_rain64);
+    }
+    free(campo);
+    return rc ? -1 : cont - 1;
 }

@@ -259,3 +259,26 @@ def test_calc_speed(ref):
         a_ref, v_ref = ref.calc_speed(sm, coef, expo, L, v0, 300.0, 5)
         a_or, v_or = oracle.calc_speed(sm, coef, expo, L, v0, 300.0, 5)
         assert (np.float32(a_ref), np.float32(v_ref)) == (np.float32(a_or), np.float32(v_or))
+
+
+def test_rain_interpolation_oracle_is_bit_identical_to_the_reference(ref, tmp_path):
+    """rain_idw (modelosv2.f90:1195-1271), rain_mit (:1104-1194), rain_pre_mit (:1068-1101): record files, posIds and the
+    sequential fp32 meanRain, with missing readings (-999), an all-missing step (0/0) and a drizzle threshold."""
+    import oracle
+    from scipy.spatial import Delaunay
+    from wmf_b200 import synth
+    bs = make_basin("G2", 70, 60, 9)
+    x, y = bs["cu"].basin_coordxy(bs["basin"])
+    xy = np.asfortranarray(np.vstack([x, y]), dtype=np.float32)
+    coord, rain = synth.make_stations(70, 60, bs["dx"], 9, 40, 4)
+    for pp, umbral in ((1.0, 0.0), (2.0, 0.0), (1.7, 0.0), (2.0, 2.5)):
+        R, O = ref.rain_idw(xy, coord, rain, pp, umbral), oracle.rain_idw(xy, coord, rain, pp, umbral)
+        for k in ("table", "pos_ids", "mean_rain"):
+            same(R[k], O[k], f"rain_idw(pp={pp}, umbral={umbral}) {k}")
+        assert O["table"].shape[0] > 5 and (O["pos_ids"] == 1).any()
+    tin = np.asfortranarray((Delaunay(coord.T.astype(np.float64)).simplices.T + 1).astype(np.int32))
+    perte = ref.rain_pre_mit(xy, tin, coord)
+    assert perte.min() >= 1
+    R, O = ref.rain_mit(xy, coord, rain, tin, perte, 0.0), oracle.rain_mit(xy, coord, rain, tin, perte, 0.0)
+    for k in ("table", "pos_ids", "mean_rain"):
+        same(R[k], O[k], "rain_mit " + k)

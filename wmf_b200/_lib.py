@@ -89,7 +89,7 @@ EXPORTS = [
     "wmf_basin_2map_find", "wmf_basin_2map", "wmf_basin_float_var2map", "wmf_basin_stream_mask", "wmf_basin_stream_nod",
     "wmf_basin_stream_type", "wmf_geo_acum_to_cauce", "wmf_geo_hand", "wmf_geo_hand_global",
     "wmf_basin_time_to_out", "wmf_basin_propagate", "wmf_shia_run", "wmf_eval_scores",
-    "wmf_calc_speed", "wmf_last_kernel_ms", "wmf_last_shia_stats",
+    "wmf_calc_speed", "wmf_last_kernel_ms", "wmf_last_shia_stats", "wmf_rain_idw", "wmf_rain_mit",
 ]
 
 _lib = None
@@ -142,6 +142,8 @@ def load() -> C.CDLL:
     L.wmf_calc_speed.argtypes = [vp, f32, f32, f32, f32, f32, i32, f32p, f32p]
     L.wmf_last_kernel_ms.argtypes = [vp, f32p]
     L.wmf_last_shia_stats.argtypes = [vp, i32p, i32p]
+    L.wmf_rain_idw.argtypes = [vp, vp, vp, vp, f32, i32, i32, i32, f32, vp, i32, vp, vp, i32p]
+    L.wmf_rain_mit.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, i32, vp, vp, i32p]
     _lib = L
     return L
 

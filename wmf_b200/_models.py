@@ -299,6 +299,64 @@ class ModelsModule:
         remap[wet] = (np.searchsorted(uniq, pos[wet]) + 2).astype(np.int32)
         return table, remap
 
+    # ---- rainfall interpolation -----------------------------------------------------------------
+    def _rain_interp(self, which, xy_basin, coord, rain, extra, ruta, umbral, maskvector, resident):
+        c = self.ctx
+        xy = np.asfortranarray(xy_basin, dtype=np.float32)
+        co = np.asfortranarray(coord, dtype=np.float32)
+        r = np.asfortranarray(rain, dtype=np.float32)
+        if xy.ndim != 2 or xy.shape[0] != 2 or co.ndim != 2 or co.shape[0] != 2 or r.ndim != 2 or r.shape[0] != co.shape[1]:
+            raise ValueError("xy_basin must be (2,nceldas), coord (2,ncoord), rain (ncoord,nreg)")
+        N, ncoord, T = xy.shape[1], co.shape[1], r.shape[1]
+        if maskvector is not None and int(np.asarray(maskvector).sum()) != N:
+            raise NotImplementedError("rain interpolation by hills (sum(maskVector) != nceldas, modelosv2.f90:1124-1127) is "
+                                      "outside the B200 hot path (SURVEY.md 8f row 4)")
+        mean, pos = _pinned_empty((T,), np.float32), _pinned_empty((T,), np.int32)
+        nrec = C.c_int32(0)
+
+        def call(table_ptr, cap):
+            if which == "idw":
+                return c.L.wmf_rain_idw(c.h, ptr(xy), ptr(co), ptr(r), float(extra), N, ncoord, T, float(umbral), table_ptr, cap,
+                                        ptr(mean), ptr(pos), C.byref(nrec))
+            tin, perte = extra
+            return c.L.wmf_rain_mit(c.h, ptr(xy), ptr(co), ptr(r), ptr(tin), ptr(perte), N, ncoord, tin.shape[1], T,
+                                    float(umbral), table_ptr, cap, ptr(mean), ptr(pos), C.byref(nrec))
+
+        if resident:
+            import torch
+            c.check(call(None, 0))                               # how many wet fields are there
+            table = torch.empty((int(nrec.value), N), dtype=torch.int32, device=f"cuda:{c.device}")
+            c.check(call(ptr(table), int(nrec.value)))
+            self.set_rain(table, pos)
+        else:
+            c.check(call(None, 0))
+            table = _pinned_empty((N, int(nrec.value)), np.int32)     # F-order (N, records) = records of N ints
+            c.check(call(ptr(table), int(nrec.value)))
+            if ruta:
+                with open(str(ruta).strip(), "wb") as f:
+                    f.write(table.tobytes(order="F"))
+        return mean, pos
+
+    def rain_idw(self, xy_basin, coord, rain, pp, nhills, ruta, umbral, maskvector=None, nceldas=None, ncoord=None, nreg=None,
+                 resident=False):
+        """meanrain,posids = rain_idw(xy_basin,coord,rain,pp,nhills,ruta,umbral,maskvector,[nceldas,ncoord,nreg])
+        -- modelosv2.f90:1195-1271 (call site wmf.py:3408-3412).  The wet fields are written to ``ruta`` as the Fortran
+        does (record 1 = zeros).  Extension: ``resident=True`` keeps the record table on the GPU and installs it with
+        ``set_rain`` so that ``shia_v1(None, None, ...)`` runs on it without a file or a PCIe round trip."""
+        return self._rain_interp("idw", xy_basin, coord, rain, pp, ruta, umbral, maskvector, resident)
+
+    def rain_mit(self, xy_basin, coord, rain, tin, tin_perte, nhills, ruta, umbral, maskvector=None, nceldas=None, ncoord=None,
+                 ntin=None, nreg=None, resident=False):
+        """meanrain,posids = rain_mit(xy_basin,coord,rain,tin,tin_perte,nhills,ruta,umbral,maskvector,[nceldas,ncoord,ntin,nreg])
+        -- modelosv2.f90:1104-1194 (call site wmf.py:3335-3347)."""
+        tin = np.asfortranarray(tin, dtype=np.int32)
+        perte = np.ascontiguousarray(np.asarray(tin_perte).reshape(-1), np.int32)
+        if tin.ndim != 2 or tin.shape[0] != 3:
+            raise ValueError("tin must be (3,ntin)")
+        if perte.min() < 1 or perte.max() > tin.shape[1]:
+            raise ValueError("tin_perte must name a triangle (1..ntin) for every cell (wmf.py:3329)")
+        return self._rain_interp("mit", xy_basin, coord, rain, (tin, perte), ruta, umbral, maskvector, resident)
+
     # ---- the model ------------------------------------------------------------------------------
     def shia_v1(self, ruta_bin, ruta_hdr, calib, n_cont, n_conth, n_reg, stoin=None, hspeedin=None, n_cel=None,
                 ruta_storage=None, ruta_speed=None, ruta_vfluxes=None, ruta_binconv=None, ruta_binstra=None,

@@ -272,6 +272,31 @@ def make_rain_types(inp: dict, seed: int = 0) -> dict:
             "pos_stra": np.array(inp["pos_evento"], np.int32, copy=True), "separate_rain": 1}
 
 
+def make_stations(nc: int, nr: int, dx: float, n_stations: int = 12, n_reg: int = 100, seed: int = 0, corners: bool = True):
+    """Synthetic rain gauges over the raster's extent: (coord (2,ns) fp32, rain (ns,n_reg) fp32 mm per step).  A third of
+    the steps are dry everywhere, single readings are missing (-999, as the notebooks' series are) or zero, and one step has
+    every gauge missing.  ``corners`` appends the four map corners with the series of the nearest gauge, as
+    rain_interpolate_mit does (wmf.py:3298-3307), so that a Delaunay mesh of the gauges covers every cell."""
+    rng = np.random.default_rng(seed)
+    W, H = nc * dx, nr * dx
+    coord = np.vstack([rng.uniform(0.05 * W, 0.95 * W, n_stations), rng.uniform(0.05 * H, 0.95 * H, n_stations)])
+    rain = np.zeros((n_stations, n_reg), np.float32)
+    for t in range(n_reg):
+        if t % 3 == 0:
+            continue
+        rain[:, t] = rng.gamma(0.8, 4.0, n_stations)
+        rain[rng.random(n_stations) < 0.15, t] = -999.0
+        rain[rng.random(n_stations) < 0.2, t] = 0.0
+    if n_reg > 7:
+        rain[:, 7] = -999.0
+    if corners:
+        for cx, cy in ((0.0, 0.0), (0.0, H), (W, H), (W, 0.0)):
+            near = int(np.argmin((coord[0] - cx) ** 2 + (coord[1] - cy) ** 2))
+            coord = np.hstack([coord, [[cx], [cy]]])
+            rain = np.vstack([rain, rain[near]])
+    return np.asfortranarray(coord, dtype=np.float32), np.asfortranarray(rain, dtype=np.float32)
+
+
 def make_ensemble_calibs(n_members: int, seed: int = 0) -> np.ndarray:
     """(M,11) calibration sets sampled uniformly in the Barbosa NSGA-II notebook ranges
     (Examples/Calibracion_Barbosa_NSGAII.ipynb cell 9), extended to the 11 entries shia_v1 needs."""
