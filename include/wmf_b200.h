@@ -246,8 +246,9 @@ int wmf_eval_scores(wmf_ctx *ctx, const float *q, int32_t n_members, int32_t n_c
  * tin_perte (nceldas) 1-based triangle of every cell for the TIN variant.  Instead of writing records to `ruta` the wet
  * fields go to `table` (capacity rows x nceldas int32, mm*1000 truncated; host or device): row 0 = the all-zero record 1,
  * row k-1 = record k -- exactly the table wmf_shia_inputs.rain takes, with pos_ids as pos_evento.  mean_rain / pos_ids
- * (nreg) as the Fortran returns them (the field sums are accumulated in fp64).  *n_records = rows the table needs; with
- * table = NULL only the statistics are computed (query the size first, or pass capacity = nreg + 1). */
+ * (nreg) as the Fortran returns them (the field sums are accumulated in fp64).  *n_records = rows of the finished table.
+ * While interpolating the table must hold 1 + (number of steps with a positive reading) rows -- capacity = nreg + 1 always
+ * suffices; with table = NULL only the statistics are computed. */
 int wmf_rain_idw(wmf_ctx *ctx, const float *xy_basin, const float *coord, const float *rain, float pp,
                  int32_t nceldas, int32_t ncoord, int32_t nreg, float umbral, int32_t *table, int32_t capacity,
                  float *mean_rain, int32_t *pos_ids, int32_t *n_records);

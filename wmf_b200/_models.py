@@ -322,19 +322,19 @@ class ModelsModule:
             return c.L.wmf_rain_mit(c.h, ptr(xy), ptr(co), ptr(r), ptr(tin), ptr(perte), N, ncoord, tin.shape[1], T,
                                     float(umbral), table_ptr, cap, ptr(mean), ptr(pos), C.byref(nrec))
 
+        # rows needed while interpolating: record 1 + every step with a positive reading (the others are dry by construction)
+        cap = 1 + (int(np.count_nonzero((r > 0).any(axis=0))) if float(umbral) >= 0 else T)
         if resident:
             import torch
-            c.check(call(None, 0))                               # how many wet fields are there
-            table = torch.empty((int(nrec.value), N), dtype=torch.int32, device=f"cuda:{c.device}")
-            c.check(call(ptr(table), int(nrec.value)))
-            self.set_rain(table, pos)
+            table = torch.empty((cap, N), dtype=torch.int32, device=f"cuda:{c.device}")
+            c.check(call(ptr(table), cap))
+            self.set_rain(table[:int(nrec.value)], pos)
         else:
-            c.check(call(None, 0))
-            table = _pinned_empty((N, int(nrec.value)), np.int32)     # F-order (N, records) = records of N ints
-            c.check(call(ptr(table), int(nrec.value)))
+            table = _pinned_empty((N, cap), np.int32)                 # F-order (N, records) = records of N ints
+            c.check(call(ptr(table), cap))
             if ruta:
                 with open(str(ruta).strip(), "wb") as f:
-                    f.write(table.tobytes(order="F"))
+                    f.write(table[:, :int(nrec.value)].tobytes(order="F"))
         return mean, pos
 
     def rain_idw(self, xy_basin, coord, rain, pp, nhills, ruta, umbral, maskvector=None, nceldas=None, ncoord=None, nreg=None,

@@ -7,9 +7,11 @@
 //   k_idw_weights   W(i,cell) = 1 / sqrt(dx^2+dy^2)**pp, station-major so that a warp reads 32 consecutive cells
 //   k_rain_field    one thread per cell, RAIN_TCH time steps per thread in registers; the station loop is the outer
 //                   loop, so each weight is loaded once per RAIN_TCH steps and every (cell, step) sum runs over the
-//                   stations in the reference's order (bit-identical fields).  Pass 0 reduces sum / counts per step
-//                   (which steps are "wet" depends on them, :1244), pass 1 writes the wet records.
-// HBM roofline: pass 1 writes 4 B per wet cell-step and re-reads 4*ncoord B of weights per cell per RAIN_TCH steps.
+//                   stations in the reference's order (bit-identical fields).  Only the steps with a positive reading
+//                   somewhere are interpolated, in ONE pass: the record is written where it will most likely live while
+//                   the per-step sum / counts that decide "wet" (:1244) are reduced; the rare dry candidate is squeezed out.
+// Bound: fp32 issue (N * steps * stations * ~7 instructions, no FMA: the reference has none), not HBM: the kernel writes
+// 4 B per wet cell-step and re-reads 4*ncoord B of weights per cell per RAIN_TCH steps.
 #include "common.cuh"
 
 namespace {
@@ -34,20 +36,20 @@ __global__ void k_idw_weights(const float2 *__restrict__ xy, const float2 *__res
 }
 
 struct RainP {
-    int N, ncoord, T;
+    int N, ncoord, T;      // T = steps this launch works on (the candidate steps), padded row length Tp of rainT
+    int Tp;
     float umbral;
-    const float *rain;     // [T][ncoord]
+    const float *rainT;    // [ncoord][Tp]: the candidate steps' readings, station-major (16 consecutive steps = 4 x float4)
     const float *W;        // IDW: [ncoord][N]
     const float2 *xy, *coord;
     const int32_t *tin;    // MIT: (3,ntin) 1-based station ids
     const int32_t *perte;  // MIT: (N) 1-based triangle of each cell
-    double *sum;           // [T] pass 0
+    double *sum;           // [T] field sum of every candidate step
     int32_t *n_umbral, *n_pos;
-    const int32_t *slot;   // [T] pass 1: record (1-based) that receives step t, 1 = dry
-    int32_t *table;        // [n_records][N]
+    int32_t *table;        // [1 + T][N]: candidate j goes to row j + 1 (row 0 = the all-zero record 1); NULL = statistics only
 };
 
-template <int MODE, int PASS>
+template <int MODE>
 __global__ void __launch_bounds__(RAIN_THREADS) k_rain_field(const RainP P) {
     const int cell = blockIdx.x * RAIN_THREADS + threadIdx.x;
     const int t0 = blockIdx.y * RAIN_TCH;
@@ -61,16 +63,20 @@ __global__ void __launch_bounds__(RAIN_THREADS) k_rain_field(const RainP P) {
             float Wr[RAIN_TCH], den[RAIN_TCH];
 #pragma unroll
             for (int k = 0; k < RAIN_TCH; ++k) { Wr[k] = 0.0f; den[k] = 0.0f; }
-            const float *rp = P.rain + (size_t)t0 * P.ncoord;
+            const float4 *rp = reinterpret_cast<const float4 *>(P.rainT + t0);
+            const size_t row4 = (size_t)P.Tp / 4;
             for (int i = 0; i < P.ncoord; ++i) {
                 const float w = P.W[(size_t)i * P.N + cell];
+                float r[RAIN_TCH];   // the same addresses for the whole warp: four 128-bit broadcast loads
 #pragma unroll
-                for (int k = 0; k < RAIN_TCH; ++k) {
-                    if (k < nt) {
-                        const float r = __ldg(rp + (size_t)k * P.ncoord + i);   // same address for the whole warp
-                        if (r > 0.0f) Wr[k] = Wr[k] + w * r;
-                        if (r >= 0.0f) den[k] = den[k] + w;
-                    }
+                for (int q = 0; q < RAIN_TCH / 4; ++q) {
+                    const float4 v = __ldg(rp + (size_t)i * row4 + q);
+                    r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int k = 0; k < RAIN_TCH; ++k) {   // padding steps hold -1: they add nothing
+                    if (r[k] > 0.0f) Wr[k] = Wr[k] + w * r[k];
+                    if (r[k] >= 0.0f) den[k] = den[k] + w;
                 }
             }
 #pragma unroll
@@ -86,103 +92,129 @@ __global__ void __launch_bounds__(RAIN_THREADS) k_rain_field(const RainP P) {
             const float coef1 = (b.x - a.x) * (c.y - a.y) - (c.x - a.x) * (b.y - a.y);
             const float det1 = (c.x - a.x) * (p.y - a.y), det2 = (b.y - a.y) * (p.x - a.x);
             const float det3 = (c.y - a.y) * (p.x - a.x), det4 = (p.y - a.y) * (b.x - a.x);
+            const float *ra = P.rainT + (size_t)ia * P.Tp + t0, *rb = P.rainT + (size_t)ib * P.Tp + t0, *rc = P.rainT + (size_t)ic * P.Tp + t0;
 #pragma unroll
-            for (int k = 0; k < RAIN_TCH; ++k) {
-                if (k < nt) {
-                    const float *r = P.rain + (size_t)(t0 + k) * P.ncoord;
-                    const float az = fmaxf(__ldg(r + ia), 0.0f), bz = fmaxf(__ldg(r + ib), 0.0f), cz = fmaxf(__ldg(r + ic), 0.0f);
+            for (int q4 = 0; q4 < RAIN_TCH / 4; ++q4) {
+                const float4 va = __ldg(reinterpret_cast<const float4 *>(ra) + q4), vb = __ldg(reinterpret_cast<const float4 *>(rb) + q4),
+                             vc = __ldg(reinterpret_cast<const float4 *>(rc) + q4);
+                const float xa[4] = {va.x, va.y, va.z, va.w}, xb[4] = {vb.x, vb.y, vb.z, vb.w}, xc[4] = {vc.x, vc.y, vc.z, vc.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float az = fmaxf(xa[e], 0.0f), bz = fmaxf(xb[e], 0.0f), cz = fmaxf(xc[e], 0.0f);
                     const float coef2 = det1 * (bz - az) + det2 * (cz - az) - det3 * (bz - az) - det4 * (cz - az);
                     const float q = az - coef2 / coef1;
-                    campo[k] = (q > 0.0f) ? q : 0.0f;
+                    campo[4 * q4 + e] = (q > 0.0f) ? q : 0.0f;
                 }
             }
         }
     }
-    if (PASS == 0) {   // per-step sum and counts (:1244-1246): fp64 atomics, one per warp and step
-        const int lane = threadIdx.x & 31;
+    // per-step sum and counts (:1244-1246): fp64 atomics, one per warp and step
+    const int lane = threadIdx.x & 31;
 #pragma unroll
-        for (int k = 0; k < RAIN_TCH; ++k) {
-            if (k < nt) {
-                const float v = active ? campo[k] : 0.0f;
-                const double s = warp_sum_d((double)v);
-                const int nu = warp_sum_i((active && v > P.umbral) ? 1 : 0);
-                const int np = warp_sum_i((active && v > 0.0f) ? 1 : 0);
-                if (lane == 0) {
-                    if (s != 0.0) atomicAdd(P.sum + t0 + k, s);
-                    if (nu) atomicAdd(P.n_umbral + t0 + k, nu);
-                    if (np) atomicAdd(P.n_pos + t0 + k, np);
-                }
+    for (int k = 0; k < RAIN_TCH; ++k) {
+        if (k < nt) {
+            const float v = active ? campo[k] : 0.0f;
+            const double s = warp_sum_d((double)v);
+            const int nu = warp_sum_i((active && v > P.umbral) ? 1 : 0);
+            const int np = warp_sum_i((active && v > 0.0f) ? 1 : 0);
+            if (lane == 0) {
+                if (s != 0.0) atomicAdd(P.sum + t0 + k, s);
+                if (nu) atomicAdd(P.n_umbral + t0 + k, nu);
+                if (np) atomicAdd(P.n_pos + t0 + k, np);
             }
         }
-    } else if (active) {   // campoInt = campo*1000 (truncation), record `cont` of the file (:1251-1252)
+    }
+    if (active && P.table) {   // campoInt = campo*1000 (truncation), one record per candidate step (:1251-1252)
 #pragma unroll
-        for (int k = 0; k < RAIN_TCH; ++k) {
-            if (k < nt) {
-                const int s = __ldg(P.slot + t0 + k);
-                if (s > 1) P.table[(size_t)(s - 1) * P.N + cell] = (int32_t)(campo[k] * 1000.0f);
-            }
-        }
+        for (int k = 0; k < RAIN_TCH; ++k)
+            if (k < nt) P.table[(size_t)(t0 + k + 1) * P.N + cell] = (int32_t)(campo[k] * 1000.0f);
     }
 }
 
+// One pass: every step with a positive reading somewhere (a "candidate"; all other fields are identically zero, hence
+// dry) is interpolated straight into the record it will most likely own.  A candidate whose field fails the wet test
+// (:1244, only possible with umbral > 0) is squeezed out afterwards by moving the later records up.
 template <int MODE>
-int rain_run(wmf_ctx *ctx, RainP P, Scope &sc, float pp, int32_t *table, int32_t capacity, float *mean_rain, int32_t *pos_ids,
-             int32_t *n_records) {
-    const int N = P.N, T = P.T;
-    if (MODE == 0) {
-        float *W;
-        WMF_TRY(sc.alloc(&W, (size_t)P.ncoord * N));
-        LAUNCH(ctx, k_idw_weights, grid_for(N, 256), 256, 0, P.xy, P.coord, pp, N, P.ncoord, W);
-        P.W = W;
-    }
-    WMF_TRY(sc.alloc(&P.sum, (size_t)T));
-    WMF_TRY(sc.alloc(&P.n_umbral, (size_t)2 * T));
-    P.n_pos = P.n_umbral + T;
-    CU_TRY(ctx, cudaMemsetAsync(P.sum, 0, sizeof(double) * T, ctx->stream));
-    CU_TRY(ctx, cudaMemsetAsync(P.n_umbral, 0, sizeof(int32_t) * 2 * T, ctx->stream));
-    const dim3 grid((unsigned)grid_for(N, RAIN_THREADS), (unsigned)grid_for(T, RAIN_TCH));
-    auto k_pass0 = k_rain_field<MODE, 0>;
-    auto k_pass1 = k_rain_field<MODE, 1>;
-    LAUNCH(ctx, k_pass0, grid, RAIN_THREADS, 0, P);
-    std::vector<double> h_sum((size_t)T);
-    std::vector<int32_t> h_cnt((size_t)2 * T), h_slot((size_t)T);
-    CU_TRY(ctx, cudaMemcpyAsync(h_sum.data(), P.sum, sizeof(double) * T, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(h_cnt.data(), P.n_umbral, sizeof(int32_t) * 2 * T, cudaMemcpyDeviceToHost, ctx->stream));
+int rain_run(wmf_ctx *ctx, RainP P, Scope &sc, const float *rain_dev, float pp, int32_t *table, int32_t capacity, float *mean_rain,
+             int32_t *pos_ids, int32_t *n_records) {
+    const int N = P.N, T_all = P.T, ns = P.ncoord;
+    std::vector<float> h_rain((size_t)ns * T_all);
+    CU_TRY(ctx, cudaMemcpyAsync(h_rain.data(), rain_dev, sizeof(float) * h_rain.size(), cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> cand;
+    for (int t = 0; t < T_all; ++t) {
+        bool any = P.umbral < 0.0f;   // a negative threshold makes even an all-zero field "wet"
+        for (int i = 0; i < ns && !any; ++i) any = h_rain[(size_t)t * ns + i] > 0.0f;
+        if (any) cand.push_back(t);
+    }
+    const int C = (int)cand.size();
+    const int Tp = ((C + RAIN_TCH - 1) / RAIN_TCH) * RAIN_TCH;
+    if (table && capacity < C + 1)
+        WMF_FAIL(ctx, WMF_ERR_ARG, "rain interpolation: the table holds %d records, %d are needed while interpolating "
+                 "(1 + the steps with a positive reading; nreg + 1 always suffices)", capacity, C + 1);
+    std::vector<int32_t> h_pos((size_t)T_all, 1);
+    std::vector<float> h_mean((size_t)T_all, 0.0f);
     int32_t cont = 2;
-    std::vector<float> h_mean((size_t)T);
-    for (int t = 0; t < T; ++t) {   // :1244-1268
-        if ((float)h_sum[t] > P.umbral && h_cnt[t] > 0) {
-            h_mean[t] = (float)(h_sum[t] / (double)h_cnt[(size_t)T + t]);
-            h_slot[t] = cont++;
-        } else {
-            h_mean[t] = 0.0f;
-            h_slot[t] = 1;
+    int32_t *d_table = nullptr;
+    bool table_on_host = false;
+    if (table) {
+        table_on_host = !Scope::on_device(table);
+        if (table_on_host) WMF_TRY(sc.alloc(&d_table, (size_t)(C + 1) * N));
+        else d_table = table;
+        CU_TRY(ctx, cudaMemsetAsync(d_table, 0, sizeof(int32_t) * (size_t)N, ctx->stream));   // record 1 = zeros (:1224)
+    }
+    if (C > 0) {
+        std::vector<float> h_rT((size_t)ns * Tp, -1.0f);
+        for (int j = 0; j < C; ++j)
+            for (int i = 0; i < ns; ++i) h_rT[(size_t)i * Tp + j] = h_rain[(size_t)cand[j] * ns + i];
+        float *d_rT;
+        WMF_TRY(sc.alloc(&d_rT, h_rT.size()));
+        CU_TRY(ctx, cudaMemcpyAsync(d_rT, h_rT.data(), sizeof(float) * h_rT.size(), cudaMemcpyHostToDevice, ctx->stream));
+        P.rainT = d_rT; P.T = C; P.Tp = Tp;
+        if (MODE == 0) {
+            float *W;
+            WMF_TRY(sc.alloc(&W, (size_t)ns * N));
+            LAUNCH(ctx, k_idw_weights, grid_for(N, 256), 256, 0, P.xy, P.coord, pp, N, ns, W);
+            P.W = W;
+        }
+        WMF_TRY(sc.alloc(&P.sum, (size_t)C));
+        WMF_TRY(sc.alloc(&P.n_umbral, (size_t)2 * C));
+        P.n_pos = P.n_umbral + C;
+        CU_TRY(ctx, cudaMemsetAsync(P.sum, 0, sizeof(double) * C, ctx->stream));
+        CU_TRY(ctx, cudaMemsetAsync(P.n_umbral, 0, sizeof(int32_t) * 2 * C, ctx->stream));
+        P.table = d_table;
+        const dim3 grid((unsigned)grid_for(N, RAIN_THREADS), (unsigned)(Tp / RAIN_TCH));
+        LAUNCH(ctx, k_rain_field<MODE>, grid, RAIN_THREADS, 0, P);
+        std::vector<double> h_sum((size_t)C);
+        std::vector<int32_t> h_cnt((size_t)2 * C);
+        CU_TRY(ctx, cudaMemcpyAsync(h_sum.data(), P.sum, sizeof(double) * C, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaMemcpyAsync(h_cnt.data(), P.n_umbral, sizeof(int32_t) * 2 * C, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // also keeps h_rT alive until its copy is done
+        for (int j = 0; j < C; ++j) {   // :1244-1268
+            if ((float)h_sum[j] > P.umbral && h_cnt[j] > 0) {
+                h_mean[cand[j]] = (float)(h_sum[j] / (double)h_cnt[(size_t)C + j]);
+                if (d_table && cont != j + 2)   // a dry candidate came before: move this record up to its final row
+                    CU_TRY(ctx, cudaMemcpyAsync(d_table + (size_t)(cont - 1) * N, d_table + (size_t)(j + 1) * N, sizeof(int32_t) * (size_t)N,
+                                                cudaMemcpyDeviceToDevice, ctx->stream));
+                h_pos[cand[j]] = cont++;
+            }
         }
     }
     *n_records = cont - 1;
     float *d_mean;
-    int32_t *d_pos, *d_slot;
-    WMF_TRY(sc.alloc(&d_slot, (size_t)T));
-    CU_TRY(ctx, cudaMemcpyAsync(d_slot, h_slot.data(), sizeof(int32_t) * T, cudaMemcpyHostToDevice, ctx->stream));
-    WMF_TRY(sc.out(mean_rain, (size_t)T, &d_mean));
-    WMF_TRY(sc.out(pos_ids, (size_t)T, &d_pos));
-    if (d_mean) CU_TRY(ctx, cudaMemcpyAsync(d_mean, h_mean.data(), sizeof(float) * T, cudaMemcpyHostToDevice, ctx->stream));
-    if (d_pos) CU_TRY(ctx, cudaMemcpyAsync(d_pos, d_slot, sizeof(int32_t) * T, cudaMemcpyDeviceToDevice, ctx->stream));
-    if (table) {
-        if (capacity < *n_records)
-            WMF_FAIL(ctx, WMF_ERR_ARG, "rain interpolation: the table holds %d records, %d are needed", capacity, *n_records);
-        WMF_TRY(sc.out(table, (size_t)*n_records * N, &P.table));
-        CU_TRY(ctx, cudaMemsetAsync(P.table, 0, sizeof(int32_t) * (size_t)N, ctx->stream));   // record 1 = zeros (:1224)
-        P.slot = d_slot;
-        LAUNCH(ctx, k_pass1, grid, RAIN_THREADS, 0, P);
-    }
+    int32_t *d_pos;
+    WMF_TRY(sc.out(mean_rain, (size_t)T_all, &d_mean));
+    WMF_TRY(sc.out(pos_ids, (size_t)T_all, &d_pos));
+    if (d_mean) CU_TRY(ctx, cudaMemcpyAsync(d_mean, h_mean.data(), sizeof(float) * T_all, cudaMemcpyHostToDevice, ctx->stream));
+    if (d_pos) CU_TRY(ctx, cudaMemcpyAsync(d_pos, h_pos.data(), sizeof(int32_t) * T_all, cudaMemcpyHostToDevice, ctx->stream));
+    if (table_on_host)
+        CU_TRY(ctx, cudaMemcpyAsync(table, d_table, sizeof(int32_t) * (size_t)*n_records * N, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // the host vectors above go out of scope
     return sc.finish();
 }
 
-int rain_stage(wmf_ctx *ctx, Scope &sc, RainP &P, const float *xy_basin, const float *coord, const float *rain, int32_t nceldas,
-               int32_t ncoord, int32_t nreg, float umbral) {
+int rain_stage(wmf_ctx *ctx, Scope &sc, RainP &P, const float **rain_dev, const float *xy_basin, const float *coord, const float *rain,
+               int32_t nceldas, int32_t ncoord, int32_t nreg, float umbral) {
     if (!xy_basin || !coord || !rain || nceldas <= 0 || ncoord <= 0 || nreg <= 0)
         WMF_FAIL(ctx, WMF_ERR_ARG, "rain interpolation: bad sizes or null inputs");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -190,7 +222,7 @@ int rain_stage(wmf_ctx *ctx, Scope &sc, RainP &P, const float *xy_basin, const f
     const float *d_xy, *d_co;
     WMF_TRY(sc.in(xy_basin, (size_t)2 * nceldas, &d_xy));
     WMF_TRY(sc.in(coord, (size_t)2 * ncoord, &d_co));
-    WMF_TRY(sc.in(rain, (size_t)ncoord * nreg, &P.rain));
+    WMF_TRY(sc.in(rain, (size_t)ncoord * nreg, rain_dev));
     if ((reinterpret_cast<uintptr_t>(d_xy) | reinterpret_cast<uintptr_t>(d_co)) & 7)
         WMF_FAIL(ctx, WMF_ERR_ARG, "rain interpolation: xy_basin / coord must be 8-byte aligned");
     P.xy = reinterpret_cast<const float2 *>(d_xy);
@@ -208,8 +240,9 @@ int wmf_rain_idw(wmf_ctx *ctx, const float *xy_basin, const float *coord, const 
     if (!ctx || !n_records) return WMF_ERR_ARG;
     Scope sc(ctx);
     RainP P{};
-    WMF_TRY(rain_stage(ctx, sc, P, xy_basin, coord, rain, nceldas, ncoord, nreg, umbral));
-    return rain_run<0>(ctx, P, sc, pp, table, capacity, mean_rain, pos_ids, n_records);
+    const float *d_rain;
+    WMF_TRY(rain_stage(ctx, sc, P, &d_rain, xy_basin, coord, rain, nceldas, ncoord, nreg, umbral));
+    return rain_run<0>(ctx, P, sc, d_rain, pp, table, capacity, mean_rain, pos_ids, n_records);
 }
 
 int wmf_rain_mit(wmf_ctx *ctx, const float *xy_basin, const float *coord, const float *rain, const int32_t *tin,
@@ -218,10 +251,11 @@ int wmf_rain_mit(wmf_ctx *ctx, const float *xy_basin, const float *coord, const 
     if (!ctx || !n_records || !tin || !tin_perte || ntin <= 0) return WMF_ERR_ARG;
     Scope sc(ctx);
     RainP P{};
-    WMF_TRY(rain_stage(ctx, sc, P, xy_basin, coord, rain, nceldas, ncoord, nreg, umbral));
+    const float *d_rain;
+    WMF_TRY(rain_stage(ctx, sc, P, &d_rain, xy_basin, coord, rain, nceldas, ncoord, nreg, umbral));
     WMF_TRY(sc.in(tin, (size_t)3 * ntin, &P.tin));
     WMF_TRY(sc.in(tin_perte, (size_t)nceldas, &P.perte));
-    return rain_run<1>(ctx, P, sc, 0.0f, table, capacity, mean_rain, pos_ids, n_records);
+    return rain_run<1>(ctx, P, sc, d_rain, 0.0f, table, capacity, mean_rain, pos_ids, n_records);
 }
 
 }  // extern "C"
