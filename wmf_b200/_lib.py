@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwmf_b200.so")
+# WMF_B200_LIB: load another build of the same library (tuning experiments with different launch bounds)
+LIB_PATH = os.environ.get("WMF_B200_LIB") or os.path.join(_HERE, "libwmf_b200.so")
 
 f32p = C.POINTER(C.c_float)
 i32p = C.POINTER(C.c_int32)

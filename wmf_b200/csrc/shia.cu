@@ -733,6 +733,12 @@ constexpr int TB_THREADS = TB_THREADS_N;
 #ifndef TB_MIN_BLOCKS
 #define TB_MIN_BLOCKS 4
 #endif
+#ifndef TB_MIN_BLOCKS_KIN   // kinematic hillslope tanks (calc_speed: five dependent pow per tank and step): 85 registers instead
+#define TB_MIN_BLOCKS_KIN 3 // of 64 + 268 B of spills; C2 with speed_type = [2,2,1], 400 steps: 33.0 -> 31.3 ms (2 blocks: 37.6)
+#endif
+#ifndef TB_MIN_BLOCKS_SED   // sediment / separate_rain variants (1 block per SM: C5 with SED + slides 248 -> 273 ms)
+#define TB_MIN_BLOCKS_SED 2
+#endif
 
 template <int K, bool CHAN, bool KIN, bool SED, bool SLIDES, bool SNAP, bool SEPF, bool SEPR>
 __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int jlo, const int jhi, const int tile,
@@ -1289,7 +1295,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
 // Every CTA carries the same mix of roles: its first `cpb` warps take 32-thread tiles of the channel list, the
 // others tiles of the hillslope list, so the SMs stay balanced although a channel thread costs ~4x a hillslope one.
 template <int K, bool KIN, bool SED, bool SLIDES, bool SNAP, bool SEPF, bool SEPR>
-__global__ void __launch_bounds__(TB_THREADS, (SED || SEPR) ? 2 : TB_MIN_BLOCKS)
+__global__ void __launch_bounds__(TB_THREADS, (SED || SEPR) ? TB_MIN_BLOCKS_SED : (KIN ? TB_MIN_BLOCKS_KIN : TB_MIN_BLOCKS))
 k_shia_tb(const __grid_constant__ ShiaP P, const int w, const int clo, const int chi, const int hlo, const int hhi,
           const int cpb, const int n_ctiles, const int n_htiles) {
     __shared__ float s_acc[K * TB_THREADS];
