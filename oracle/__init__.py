@@ -307,6 +307,75 @@ class Cu:
         return out
 
 
+    # ---- sub-basin (hills) topology, cuencas.f90:1380-1438, 1835-2118 ----
+    def basin_stream_slope(self, basin_f, elev, lng, nodos, n_cauce):
+        b = _i(basin_f)
+        n = b.shape[1]
+        e, l = np.ascontiguousarray(elev, np.float32), np.ascontiguousarray(lng, np.float32)
+        nd = np.ascontiguousarray(nodos, np.int32)
+        s, ln = np.empty(n, np.float32), np.empty(n, np.float32)
+        g = self._geo()
+        self._L.wo_basin_stream_slope(C.byref(g), _p(b, i32p), _p(e, f32p), _p(l, f32p), _p(nd, i32p), int(n_cauce), n,
+                                      _p(s, f32p), _p(ln, f32p))
+        return s, ln
+
+    def basin_subbasin_nod(self, basin_f, acum, umbral):
+        b = _i(basin_f)
+        n = b.shape[1]
+        a = np.ascontiguousarray(acum, np.int32)
+        cauce, nodos = np.empty(n, np.int32), np.empty(n, np.int32)
+        nn = C.c_int32()
+        self._sub_basins = np.zeros(2 * n, np.int32)
+        self._L.wo_basin_subbasin_nod(_p(b, i32p), _p(a, i32p), n, int(umbral), _p(cauce, i32p), _p(nodos, i32p), C.byref(nn),
+                                      _p(self._sub_basins, i32p))
+        return cauce, nodos, nn.value
+
+    def basin_subbasin_cut(self, n_nodos):
+        return np.array(self._sub_basins[:2 * n_nodos].reshape(2, n_nodos, order="F"), order="F")
+
+    def basin_subbasin_find(self, basin_f, nodos, n_nodos):
+        b = _i(basin_f)
+        n = b.shape[1]
+        nd = np.ascontiguousarray(nodos, np.int32)
+        sub_pert = np.empty(n, np.int32)
+        self._L.wo_basin_subbasin_find(_p(b, i32p), _p(nd, i32p), n, _p(sub_pert, i32p))
+        return sub_pert, np.zeros(n_nodos, np.int32)
+
+    def basin_subbasin_horton(self, sub_basins, nceldas):
+        sb = _i(sub_basins)
+        nn = sb.shape[1]
+        sh, nh = np.empty(nn, np.int32), np.empty(nceldas, np.int32)
+        self._L.wo_basin_subbasin_horton(_p(sb, i32p), nn, int(nceldas), _p(sh, i32p), _p(nh, i32p))
+        return sh, nh
+
+    def basin_subbasin_long(self, sub_pert, cauce, lng, sub_basin, sub_horton):
+        sp, ca = np.ascontiguousarray(sub_pert, np.int32), np.ascontiguousarray(cauce, np.int32)
+        li = np.ascontiguousarray(np.asarray(lng), np.float32).astype(np.int32)        # f2py casts to the INTEGER dummy
+        sb, sh = _i(sub_basin), np.ascontiguousarray(sub_horton, np.int32)
+        nn = sb.shape[1]
+        out = np.empty(nn, np.float32)
+        mx, nmx = C.c_float(), C.c_int32()
+        self._L.wo_basin_subbasin_long(_p(sp, i32p), _p(ca, i32p), _p(li, i32p), _p(sb, i32p), _p(sh, i32p), nn, sp.size,
+                                       _p(out, f32p), C.byref(mx), C.byref(nmx))
+        return out, mx.value, nmx.value
+
+    def basin_subbasin_stream_prop(self, sub_pert, cauce, lng, slope, n_nodos):
+        sp, ca = np.ascontiguousarray(sub_pert, np.int32), np.ascontiguousarray(cauce, np.int32)
+        l, s = np.ascontiguousarray(lng, np.float32), np.ascontiguousarray(slope, np.float32)
+        ss, sl = np.empty(n_nodos, np.float32), np.empty(n_nodos, np.float32)
+        self._L.wo_basin_subbasin_stream_prop(_p(sp, i32p), _p(ca, i32p), _p(l, f32p), _p(s, f32p), sp.size, int(n_nodos),
+                                              _p(ss, f32p), _p(sl, f32p))
+        return ss, sl
+
+    def basin_subbasin_map2subbasin(self, sub_pert, var, n_nodos, cauce, sum_mean):
+        sp, ca = np.ascontiguousarray(sub_pert, np.int32), np.ascontiguousarray(cauce, np.int32)
+        v = np.ascontiguousarray(var, np.float32)
+        out = np.empty(n_nodos, np.float32)
+        self._L.wo_basin_subbasin_map2subbasin(_p(sp, i32p), _p(v, f32p), int(n_nodos), sp.size, _p(ca, i32p), int(sum_mean),
+                                               _p(out, f32p))
+        return out
+
+
 # keys of the SHIA input dict: name -> (ctype pointer, K)  (array of shape (K,N), or (N,) / (1,N) for K=1)
 _CELL_F = {
     "hill_long": 1, "hill_slope": 1, "stream_long": 1, "stream_slope": 1, "elem_area": 1,

@@ -301,6 +301,71 @@ class RefCu:
         return out
 
 
+    # ---- sub-basin (hills) topology, cuencas.f90:1380-1438, 1835-2118 ----
+    def basin_stream_slope(self, basin_f, elev, lng, nodos, n_cauce):
+        self._push()
+        b = _i(basin_f)
+        n = b.shape[1]
+        e, l = np.ascontiguousarray(elev, np.float32), np.ascontiguousarray(lng, np.float32)
+        nd = np.ascontiguousarray(nodos, np.int32)
+        s, ln = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        _call(CU, "basin_stream_slope", b, e, l, nd, i32(int(n_cauce)), s, ln, i32(n))
+        return s, ln
+
+    def basin_subbasin_nod(self, basin_f, acum, umbral):
+        b = _i(basin_f)
+        n = b.shape[1]
+        a = np.ascontiguousarray(acum, np.int32)
+        cauce, nodos = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        nn = i32()
+        _call(CU, "basin_subbasin_nod", b, a, i32(n), i32(int(umbral)), cauce, nodos, nn)
+        return cauce, nodos, nn.value
+
+    def basin_subbasin_cut(self, n_nodos):
+        out = np.zeros((2, n_nodos), np.int32, order="F")
+        _call(CU, "basin_subbasin_cut", i32(n_nodos), out)
+        return out
+
+    def basin_subbasin_find(self, basin_f, nodos, n_nodos):
+        b = _i(basin_f)
+        n = b.shape[1]
+        nd = np.ascontiguousarray(nodos, np.int32)
+        sub_pert, sub_basin = np.zeros(n, np.int32), np.zeros(n_nodos, np.int32)
+        _call(CU, "basin_subbasin_find", b, nd, sub_pert, sub_basin, i32(n_nodos), i32(n))
+        return sub_pert, sub_basin
+
+    def basin_subbasin_horton(self, sub_basins, nceldas):
+        sb = _i(sub_basins)
+        nn = sb.shape[1]
+        sh, nh = np.zeros(nn, np.int32), np.zeros(nceldas, np.int32)
+        _call(CU, "basin_subbasin_horton", sb, sh, nh, i32(nn), i32(int(nceldas)))
+        return sh, nh
+
+    def basin_subbasin_long(self, sub_pert, cauce, lng, sub_basin, sub_horton):
+        sp, ca = np.ascontiguousarray(sub_pert, np.int32), np.ascontiguousarray(cauce, np.int32)
+        li = np.ascontiguousarray(np.asarray(lng), np.float32).astype(np.int32)        # f2py casts to the INTEGER dummy
+        sb, sh = _i(sub_basin), np.ascontiguousarray(sub_horton, np.int32)
+        nn = sb.shape[1]
+        out = np.zeros(nn, np.float32)
+        mx, nmx = f32(), i32()
+        _call(CU, "basin_subbasin_long", sp, ca, li, sb, sh, out, mx, nmx, i32(nn), i32(sp.size))
+        return out, mx.value, nmx.value
+
+    def basin_subbasin_stream_prop(self, sub_pert, cauce, lng, slope, n_nodos):
+        sp, ca = np.ascontiguousarray(sub_pert, np.int32), np.ascontiguousarray(cauce, np.int32)
+        l, s = np.ascontiguousarray(lng, np.float32), np.ascontiguousarray(slope, np.float32)
+        ss, sl = np.zeros(n_nodos, np.float32), np.zeros(n_nodos, np.float32)
+        _call(CU, "basin_subbasin_stream_prop", sp, ca, l, s, ss, sl, i32(sp.size), i32(int(n_nodos)))
+        return ss, sl
+
+    def basin_subbasin_map2subbasin(self, sub_pert, var, n_nodos, cauce, sum_mean):
+        sp, ca = np.ascontiguousarray(sub_pert, np.int32), np.ascontiguousarray(cauce, np.int32)
+        v = np.ascontiguousarray(var, np.float32)
+        out = np.zeros(n_nodos, np.float32)
+        _call(CU, "basin_subbasin_map2subbasin", sp, v, out, i32(int(n_nodos)), i32(sp.size), ca, i32(int(sum_mean)))
+        return out
+
+
 # ---------------------------------------------------------------------------------------------- module models
 _CELL_F = {"hill_long": 1, "hill_slope": 1, "stream_long": 1, "stream_slope": 1, "elem_area": 1, "v_coef": 4, "h_coef": 4,
            "h_exp": 4, "max_capilar": 1, "max_gravita": 1, "max_aquifer": 1, "storage": 5}

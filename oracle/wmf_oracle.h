@@ -160,6 +160,21 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out);
 float wo_calc_speed(float sm, float coef, float expo, float elem_long, float *speed, float dt,
                     int32_t calc_niter);
 
+/* sub-basin (hills) topology: cuencas.f90:1380-1438, 1835-2118 (see wmf_oracle_cu.c for the quirks reproduced) */
+void wo_basin_stream_slope(const wo_geo *g, const int32_t *basin_f, const float *elev, const float *lng,
+                           const int32_t *nodos, int32_t n_cauce, int32_t n, float *stream_s, float *stream_l);
+void wo_basin_subbasin_nod(const int32_t *basin_f, const int32_t *acum, int32_t n, int32_t umbral, int32_t *cauce,
+                           int32_t *nodos_fin, int32_t *n_nodos, int32_t *sub_basins /* 2*n ints */);
+void wo_basin_subbasin_find(const int32_t *basin_f, const int32_t *nodos, int32_t n, int32_t *sub_pert);
+void wo_basin_subbasin_horton(const int32_t *sub_basins, int32_t n_nodos, int32_t n, int32_t *sub_horton, int32_t *nod_horton);
+void wo_basin_subbasin_long(const int32_t *sub_pert, const int32_t *cauce, const int32_t *lng_int, const int32_t *sub_basin,
+                            const int32_t *sub_horton, int32_t n_nodos, int32_t n, float *sub_basin_long, float *max_long,
+                            int32_t *nodo_max_long);
+void wo_basin_subbasin_stream_prop(const int32_t *sub_pert, const int32_t *cauce, const float *lng, const float *slope,
+                                   int32_t n, int32_t n_nodos, float *stream_slope, float *stream_long);
+void wo_basin_subbasin_map2subbasin(const int32_t *sub_pert, const float *var, int32_t n_nodos, int32_t n,
+                                    const int32_t *cauce, int32_t sum_mean, float *out);
+
 /* rain_idw (modelosv2.f90:1195-1271) and rain_mit (:1104-1194), cells model (maskVector all ones).  Instead of writing
  * records to `ruta`, the wet fields go to table (capacity rows x nceldas int32, mm*1000 truncated): row 0 = the all-zero
  * record 1, row k-1 = record k.  mean_rain / pos_ids (nreg) as the Fortran returns them; mean_rain64 (may be NULL) is the

@@ -432,3 +432,221 @@ void wo_basin_propagate(const int32_t *basin_f, const float *var, int32_t n, flo
         }
     }
 }
+
+/* ---- sub-basin (hills) topology, cuencas.f90:1380-1438, 1835-2118 ---- */
+
+/* basin_stream_slope, cuencas.f90:1380-1438.  celdas_tramo(2) is not written when the cell below a node is itself a node
+ * (:1414-1419), yet the assignment loop runs to cont = 2 (:1432-1435): the reference then writes this reach's values into
+ * whichever cell an earlier, longer reach left in celdas_tramo(2).  Before any such reach the entry is uninitialised
+ * (index 0 with a zeroed heap = one element before the arrays): that write is dropped here. */
+void wo_basin_stream_slope(const wo_geo *g, const int32_t *basin_f, const float *elev, const float *lng,
+                           const int32_t *nodos, int32_t n_cauce, int32_t n, float *stream_s, float *stream_l)
+{
+    const int32_t cap = n_cauce > 2 ? n_cauce : 2;
+    int32_t *tramo = (int32_t *)calloc((size_t)cap, sizeof(int32_t));   /* 1-based cell ids, 0 = never written */
+    float *ed = (float *)calloc(2 * (size_t)cap, sizeof(float));
+    for (int32_t i = 0; i < n; ++i) { stream_s[i] = g->nodata; stream_l[i] = g->nodata; }
+    for (int32_t i = 0; i < n; ++i) {
+        if (nodos[i] > 0 && BF(0, i) != 0) {
+            ed[0] = elev[i];
+            ed[1] = lng[i];
+            tramo[0] = i + 1;
+            int flag = 1;
+            int32_t cont = 1;
+            int32_t d = n - BF(0, i); /* 0-based */
+            while (flag == 1) {
+                if (nodos[d] == 0) {
+                    cont = cont + 1;
+                    ed[2 * (cont - 1)] = elev[d];
+                    ed[2 * (cont - 1) + 1] = ed[2 * (cont - 2) + 1] + lng[d];
+                    tramo[cont - 1] = d + 1;
+                } else {
+                    flag = 0;
+                    if (cont == 1) {
+                        cont = cont + 1;
+                        ed[2 * (cont - 1)] = elev[d];
+                        ed[2 * (cont - 1) + 1] = ed[2 * (cont - 2) + 1] + lng[d];
+                    }
+                }
+                d = n - BF(0, d); /* may step past the outlet (index n): never read again, flag is 0 by then */
+                if (d >= n) d = n - 1;
+            }
+            float S = fabsf((ed[0] - ed[2 * (cont - 1)]) / (ed[1] - ed[2 * (cont - 1) + 1]));
+            if (S <= 0.0f) S = 0.001f;
+            /* L_tramo is implicitly typed (module cu has no `implicit none`): a name starting with L is INTEGER, so the
+               reach length is truncated, and so is dxP in the fallback */
+            int32_t Li = (int32_t)ed[2 * (cont - 1) + 1];
+            if (Li <= 0) Li = (int32_t)g->dxp;
+            const float L = (float)Li;
+            for (int32_t j = 0; j < cont; ++j)
+                if (tramo[j] >= 1) { stream_s[tramo[j] - 1] = S; stream_l[tramo[j] - 1] = L; }
+        }
+    }
+    free(tramo);
+    free(ed);
+}
+
+/* basin_subbasin_nod, cuencas.f90:1835-1920 (+ the module global sub_basins_temp(2,n_nodos) that basin_subbasin_cut
+ * :1921-1930 returns): sub_basins must hold 2*n entries (only the first 2*n_nodos are meaningful). */
+void wo_basin_subbasin_nod(const int32_t *basin_f, const int32_t *acum, int32_t n, int32_t umbral, int32_t *cauce,
+                           int32_t *nodos_fin, int32_t *n_nodos, int32_t *sub_basins)
+{
+    int32_t *nodos = (int32_t *)calloc((size_t)n, sizeof(int32_t));
+    for (int32_t i = 0; i < n; ++i) cauce[i] = (acum[i] >= umbral) ? 1 : 0;
+    for (int32_t i = 0; i < n; ++i)
+        if (BF(0, i) != 0 && cauce[i] == 1) nodos[n - BF(0, i)] += 1;
+    for (int32_t i = 0; i < n; ++i)
+        if (nodos[i] < 2) nodos[i] = 0;
+    for (int32_t i = 0; i < n; ++i) nodos_fin[i] = 0;
+    nodos_fin[n - 1] = 1;
+    for (int32_t i = 0; i < n; ++i)
+        if (cauce[i] == 1) {
+            const int32_t d = n - BF(0, i); /* 0-based; == n for the outlet */
+            if (d < n && nodos[d] != 0) nodos_fin[i] = 1;
+        }
+    int32_t nn = 0;
+    for (int32_t i = 0; i < n; ++i) nn += nodos_fin[i];
+    *n_nodos = nn;
+#define SB(k, j) sub_basins[2 * (size_t)((j) - 1) + ((k) - 1)] /* sub_basins_temp(k,j), 1-based */
+    for (int32_t j = 1; j <= nn; ++j) { SB(1, j) = 0; SB(2, j) = 0; }
+    SB(1, nn) = n;
+    SB(2, nn) = 0;
+    int32_t cont = 1, cont2 = 0;
+    int flag1 = 1;
+    while (flag1) {
+        if (SB(1, nn - cont + 1) != 0) {
+            const int32_t posi = SB(1, nn - cont + 1); /* 1-based cell */
+            for (int32_t j = 1; j <= posi - 1; ++j) {
+                const int32_t c = posi - j; /* 1-based */
+                if (nodos_fin[c - 1] != 0) {
+                    int32_t d = n - BF(0, c - 1) + 1; /* 1-based */
+                    int flag2 = 1;
+                    while (flag2) {
+                        if (nodos_fin[d - 1] == 0) {
+                            if (d != posi) d = n - BF(0, d - 1) + 1;
+                        } else if (d == posi) {
+                            cont2 = cont2 + 1;
+                            SB(1, nn - cont2) = c;
+                            SB(2, nn - cont2) = cont;
+                            nodos_fin[c - 1] = cont2 + 1;
+                            flag2 = 0;
+                        } else {
+                            flag2 = 0;
+                        }
+                    }
+                }
+            }
+            cont = cont + 1;
+            if (cont > nn) flag1 = 0;
+        } else {
+            flag1 = 0;
+        }
+    }
+#undef SB
+    free(nodos);
+}
+
+/* basin_subbasin_find, cuencas.f90:1979-2010 (sub_basin is declared intent(out) but never assigned: not returned here) */
+void wo_basin_subbasin_find(const int32_t *basin_f, const int32_t *nodos, int32_t n, int32_t *sub_pert)
+{
+    for (int32_t i = 0; i < n; ++i) sub_pert[i] = nodos[i];
+    for (int32_t i = 0; i < n; ++i)
+        if (sub_pert[i] == 0) {
+            int32_t d = n - BF(0, i);
+            while (nodos[d] == 0) d = n - BF(0, d);
+            sub_pert[i] = nodos[d];
+        }
+}
+
+/* basin_subbasin_horton, cuencas.f90:1931-1978.  sub_basins (2,n_nodos); nod_horton (nceldas) is only written at the node
+ * cells (the Fortran leaves the rest uninitialised: zeros here); at most 10 tributaries are looked at (drenantes(10)). */
+void wo_basin_subbasin_horton(const int32_t *sub_basins, int32_t n_nodos, int32_t n, int32_t *sub_horton, int32_t *nod_horton)
+{
+#define SB(k, j) sub_basins[2 * (size_t)((j) - 1) + ((k) - 1)]
+    for (int32_t i = 0; i < n; ++i) nod_horton[i] = 0;
+    for (int32_t i = 1; i <= n_nodos; ++i) sub_horton[i - 1] = 0;
+    for (int32_t i = 1; i <= n_nodos; ++i) {
+        const int32_t posi = n_nodos - i + 1;
+        int32_t conteo = 0;
+        for (int32_t j = 1; j <= n_nodos; ++j) conteo += (SB(2, j) == posi);
+        if (conteo == 0) {
+            sub_horton[i - 1] = 1;
+            nod_horton[SB(1, i) - 1] = 1;
+        }
+    }
+    for (int32_t i = 1; i <= n_nodos; ++i)
+        if (sub_horton[i - 1] != 1) {
+            const int32_t posi = n_nodos - i + 1;
+            int32_t cont = 0, dren[10] = {0};
+            for (int32_t j = 1; j <= i - 1; ++j)
+                if (SB(2, j) == posi) {
+                    cont = cont + 1;
+                    if (cont <= 10) dren[cont - 1] = sub_horton[j - 1];
+                }
+            if (cont > 10) cont = 10;
+            int32_t mx = dren[0], mn = dren[0];
+            for (int32_t k = 1; k < cont; ++k) { if (dren[k] > mx) mx = dren[k]; if (dren[k] < mn) mn = dren[k]; }
+            sub_horton[i - 1] = (mx == mn) ? mx + 1 : mx;
+            nod_horton[SB(1, i) - 1] = sub_horton[i - 1];
+        }
+#undef SB
+}
+
+/* basin_subbasin_long, cuencas.f90:2011-2051.  `long` is declared INTEGER there: f2py truncates the cell lengths the caller
+ * passes (wmf.py:3670 hands over hill_long, fp32) before the sums. */
+void wo_basin_subbasin_long(const int32_t *sub_pert, const int32_t *cauce, const int32_t *lng_int, const int32_t *sub_basin,
+                            const int32_t *sub_horton, int32_t n_nodos, int32_t n, float *sub_basin_long, float *max_long,
+                            int32_t *nodo_max_long)
+{
+#define SB(k, j) sub_basin[2 * (size_t)((j) - 1) + ((k) - 1)]
+    for (int32_t i = 1; i <= n_nodos; ++i) {
+        const int32_t posi = n_nodos - i + 1;
+        float s = 0.0f;
+        for (int32_t c = 0; c < n; ++c)
+            if (cauce[c] * sub_pert[c] == posi) s += (float)(cauce[c] * lng_int[c]);
+        sub_basin_long[i - 1] = s;
+    }
+    *max_long = 0.0f;
+    *nodo_max_long = 0;
+    for (int32_t i = 1; i <= n_nodos; ++i)
+        if (sub_horton[i - 1] == 1) {
+            float acc = sub_basin_long[i - 1];
+            int32_t d = n_nodos - SB(2, i) + 1;
+            while (d >= 1 && d <= n_nodos && SB(2, d) >= 1) {
+                acc = acc + sub_basin_long[d - 1];
+                d = n_nodos - SB(2, d) + 1;
+            }
+            if (acc > *max_long) { *max_long = acc; *nodo_max_long = n_nodos - i + 1; }
+        }
+#undef SB
+}
+
+/* basin_subbasin_stream_prop, cuencas.f90:2093-2115 (indexes the hills by i, not by n_nodos-i+1; 0/0 = NaN for a hill
+ * without channel cells) */
+void wo_basin_subbasin_stream_prop(const int32_t *sub_pert, const int32_t *cauce, const float *lng, const float *slope,
+                                   int32_t n, int32_t n_nodos, float *stream_slope, float *stream_long)
+{
+    for (int32_t i = 1; i <= n_nodos; ++i) {
+        float sl = 0.0f, ss = 0.0f;
+        int32_t cnt = 0;
+        for (int32_t c = 0; c < n; ++c)
+            if (sub_pert[c] == i && cauce[c] == 1) { sl += lng[c]; ss += slope[c]; ++cnt; }
+        stream_long[i - 1] = sl;
+        stream_slope[i - 1] = ss / (float)cnt;
+    }
+}
+
+/* basin_subbasin_map2subbasin, cuencas.f90:2052-2092 */
+void wo_basin_subbasin_map2subbasin(const int32_t *sub_pert, const float *var, int32_t n_nodos, int32_t n,
+                                    const int32_t *cauce, int32_t sum_mean, float *out)
+{
+    for (int32_t i = 1; i <= n_nodos; ++i) {
+        const int32_t posi = n_nodos - i + 1;
+        float s = 0.0f, mx = -3.4028235e38f; /* maxval of an empty set is -huge */
+        int32_t cnt = 0;
+        for (int32_t c = 0; c < n; ++c)
+            if (sub_pert[c] == posi && cauce[c] == 1) { s += var[c]; ++cnt; if (var[c] > mx) mx = var[c]; }
+        if (cnt > 0) out[i - 1] = (sum_mean == 0) ? s / (float)cnt : (sum_mean == 1) ? s : (sum_mean == 2) ? mx : 0.0f;
+        else out[i - 1] = 0.0f;
+    }
+}

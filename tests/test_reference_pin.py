@@ -282,3 +282,44 @@ def test_rain_interpolation_oracle_is_bit_identical_to_the_reference(ref, tmp_pa
     R, O = ref.rain_mit(xy, coord, rain, tin, perte, 0.0), oracle.rain_mit(xy, coord, rain, tin, perte, 0.0)
     for k in ("table", "pos_ids", "mean_rain"):
         same(R[k], O[k], "rain_mit " + k)
+
+
+@pytest.mark.parametrize("kind,nc,nr,seed,thr", [("G2", 96, 80, 1, 30), ("G1", 70, 60, 2, 12), ("G2", 200, 150, 3, 60),
+                                                 ("G2", 120, 90, 4, 5)])
+def test_subbasin_topology_oracle_is_bit_identical_to_the_reference(ref, kind, nc, nr, seed, thr):
+    """The hills / sub-basin routines SimuBasin.__init__ and set_Geomorphology call even for the cells model
+    (wmf.py:3019-3023, 3664-3676): basin_subbasin_nod / find / cut / horton / long / stream_prop / map2subbasin
+    (cuencas.f90:1835-2118) and basin_stream_slope (:1380-1438), with their quirks -- the INTEGER `long` dummy, the
+    implicitly INTEGER L_tramo, celdas_tramo(2) left over from an earlier reach, at most 10 tributaries in the Horton pass."""
+    bs = make_basin(kind, nc, nr, seed)
+    b, n = bs["basin"], bs["n"]
+    v = basin_vectors(bs)
+    rc, oc = pair(ref, bs)
+    acum, lng, pend, elev = v["acum"], v["lng"], v["pend"], v["elev"]
+    r1, o1 = rc.basin_subbasin_nod(b, acum, thr), oc.basin_subbasin_nod(b, acum, thr)
+    assert r1[2] == o1[2] and r1[2] > 10
+    nn = r1[2]
+    same(r1[0], o1[0], "cauce")
+    same(r1[1], o1[1], "nodos_fin")
+    rf, of = rc.basin_subbasin_find(b, r1[1], nn), oc.basin_subbasin_find(b, o1[1], nn)
+    same(rf[0], of[0], "sub_pert")
+    rsb, osb = rc.basin_subbasin_cut(nn), oc.basin_subbasin_cut(nn)
+    same(rsb, osb, "sub_basins")
+    rh, oh = rc.basin_subbasin_horton(rsb, n), oc.basin_subbasin_horton(osb, n)
+    same(rh[0], oh[0], "sub_horton")
+    same(rh[1][rsb[0] - 1], oh[1][osb[0] - 1], "nod_horton at the node cells")
+    assert oh[0].max() >= 3
+    rl, ol = rc.basin_subbasin_long(rf[0], r1[0], lng, rsb, rh[0]), oc.basin_subbasin_long(of[0], o1[0], lng, osb, oh[0])
+    same(rl[0], ol[0], "sub_basin_long")
+    assert rl[1:] == ol[1:] and ol[1] > 0
+    rp, op = rc.basin_subbasin_stream_prop(rf[0], r1[0], lng, pend, nn), oc.basin_subbasin_stream_prop(of[0], o1[0], lng, pend, nn)
+    for a, c, nm in zip(rp, op, ("stream_slope", "stream_long")):
+        np.testing.assert_array_equal(a, c, err_msg=nm)             # NaN == NaN for hills without channel cells
+    for sm in (0, 1, 2):
+        same(rc.basin_subbasin_map2subbasin(rf[0], elev, nn, r1[0], sm), oc.basin_subbasin_map2subbasin(of[0], elev, nn, o1[0], sm),
+             f"map2subbasin({sm})")
+    cauce, nodos, _, _, n_cauce = oc.basin_stream_nod(b, acum, thr)
+    rs, os_ = rc.basin_stream_slope(b, elev, lng, nodos, n_cauce), oc.basin_stream_slope(b, elev, lng, nodos, n_cauce)
+    same(rs[0], os_[0], "stream_s")
+    same(rs[1], os_[1], "stream_l")
+    assert (os_[1][cauce == 1] == np.floor(os_[1][cauce == 1])).all()         # the implicitly INTEGER reach length
