@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define WMF_ABI_VERSION 6
+#define WMF_ABI_VERSION 7
 
 enum {
     WMF_OK = 0,
@@ -123,6 +123,32 @@ int wmf_basin_time_to_out(wmf_ctx *ctx, const int32_t *basin_f, const float *lng
 /* basin_propagate, cuencas.f90:1811-1833 */
 int wmf_basin_propagate(wmf_ctx *ctx, const int32_t *basin_f, const float *var, int32_t nceldas,
                         float *var_prop);
+
+/* Sub-basin (hills) topology: the routines SimuBasin.__init__ / set_Geomorphology call next to the basin cut
+ * (wmf.py:3019-3023, 3664-3676).  Layouts as f2py: sub_basins (2,n_nodos), vectors (nceldas) or (n_nodos). */
+/* basin_subbasin_nod, cuencas.f90:1835-1920; keeps sub_basins_temp in the context for basin_subbasin_cut (:1921-1930) */
+int wmf_basin_subbasin_nod(wmf_ctx *ctx, const int32_t *basin_f, const int32_t *acum, int32_t nceldas, int32_t umbral,
+                           int32_t *cauce, int32_t *nodos_fin, int32_t *n_nodos);
+int wmf_basin_subbasin_cut(wmf_ctx *ctx, int32_t n_nodos, int32_t *sub_basins);
+/* basin_subbasin_find, cuencas.f90:1979-2010 (its second output sub_basin is never assigned by the Fortran) */
+int wmf_basin_subbasin_find(wmf_ctx *ctx, const int32_t *basin_f, const int32_t *nodos, int32_t nceldas, int32_t *sub_pert);
+/* basin_subbasin_horton, cuencas.f90:1931-1978 */
+int wmf_basin_subbasin_horton(wmf_ctx *ctx, const int32_t *sub_basins, int32_t n_nodos, int32_t nceldas,
+                              int32_t *sub_horton, int32_t *nod_horton);
+/* basin_subbasin_long, cuencas.f90:2011-2051 (`lng` is truncated to integer as the Fortran's INTEGER dummy does) */
+int wmf_basin_subbasin_long(wmf_ctx *ctx, const int32_t *sub_pert, const int32_t *cauce, const float *lng,
+                            const int32_t *sub_basin, const int32_t *sub_horton, int32_t n_nodos, int32_t nceldas,
+                            float *sub_basin_long, float *max_long, int32_t *nodo_max_long);
+/* basin_subbasin_stream_prop, cuencas.f90:2093-2115 */
+int wmf_basin_subbasin_stream_prop(wmf_ctx *ctx, const int32_t *sub_pert, const int32_t *cauce, const float *lng,
+                                   const float *slope, int32_t nceldas, int32_t n_nodos, float *stream_slope,
+                                   float *stream_long);
+/* basin_subbasin_map2subbasin, cuencas.f90:2052-2092 (sum_mean: 0 mean, 1 sum, 2 max over the hill's channel cells) */
+int wmf_basin_subbasin_map2subbasin(wmf_ctx *ctx, const int32_t *sub_pert, const float *basin_var, int32_t n_nodos,
+                                    int32_t nceldas, const int32_t *cauce, int32_t sum_mean, float *subbasin_sum);
+/* basin_stream_slope, cuencas.f90:1380-1438 (uses the context's nodata and dxp) */
+int wmf_basin_stream_slope(wmf_ctx *ctx, const int32_t *basin_f, const float *basin_elev, const float *basin_long,
+                           const int32_t *nodos, int32_t nceldas, float *stream_s, float *stream_l);
 
 /* -------------------------------------------------------- Path B: `models` */
 /* Scalar switches = module `models` globals (modelosv2.f90:71-97) + shia_v1 sizes (:191-216). */

@@ -1,0 +1,76 @@
+"""GPU parity, sub-basin (hills) topology: basin_subbasin_nod / cut / find / horton / long / stream_prop / map2subbasin and
+basin_stream_slope (cuencas.f90:1380-1438, 1835-2118) through the C ABI vs the CPU oracle, which is bit-identical to the
+reference's compiled Fortran on them (tests/test_reference_pin.py).  Everything is bit-exact: the integer tables, and the
+fp32 sums because the kernels add in the reference's order."""
+import numpy as np
+import pytest
+
+from conftest import basin_vectors, geo_to, make_basin
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kind,nc,nr,seed,thr", [("G2", 96, 80, 1, 30), ("G1", 70, 60, 2, 12), ("G2", 300, 220, 3, 60),
+                                                 ("G2", 120, 90, 4, 5), ("G2", 400, 300, 5, 4000)])
+def test_subbasin_chain_as_simubasin_drives_it(kind, nc, nr, seed, thr):
+    import oracle
+    from wmf_b200 import CuModule
+    bs = make_basin(kind, nc, nr, seed)
+    b, n = bs["basin"], bs["n"]
+    v = basin_vectors(bs)
+    acum, lng, pend, elev = v["acum"], v["lng"], v["pend"], v["elev"]
+    oc = bs["cu"]
+    cu = CuModule()
+    geo_to(cu, bs)
+    # SimuBasin.__init__ (wmf.py:3019-3023)
+    o1 = oc.basin_subbasin_nod(b, acum, thr)
+    g1 = cu.basin_subbasin_nod(b, acum, thr, n)
+    assert g1[2] == o1[2]
+    nn = o1[2]
+    np.testing.assert_array_equal(g1[0], o1[0])
+    np.testing.assert_array_equal(g1[1], o1[1])
+    of = oc.basin_subbasin_find(b, o1[1], nn)
+    gf = cu.basin_subbasin_find(b, g1[1], nn, n)
+    np.testing.assert_array_equal(gf[0], of[0])
+    osb, gsb = oc.basin_subbasin_cut(nn), cu.basin_subbasin_cut(nn)
+    np.testing.assert_array_equal(gsb, osb)
+    with pytest.raises(Exception):
+        cu.basin_subbasin_cut(nn)                      # sub_basins_temp is deallocated by the cut (cuencas.f90:1929)
+    # set_Geomorphology (wmf.py:3664-3676)
+    cauce, nodos, _, _, n_cauce = oc.basin_stream_nod(b, acum, thr)
+    os_, gs = oc.basin_stream_slope(b, elev, lng, nodos, n_cauce), cu.basin_stream_slope(b, elev, lng, nodos, n_cauce, n)
+    np.testing.assert_array_equal(gs[0], os_[0])
+    np.testing.assert_array_equal(gs[1], os_[1])
+    oh, gh = oc.basin_subbasin_horton(osb, n), cu.basin_subbasin_horton(gsb, n, nn)
+    np.testing.assert_array_equal(gh[0], oh[0])
+    np.testing.assert_array_equal(gh[1], oh[1])
+    ol = oc.basin_subbasin_long(of[0], o1[0], lng, osb, oh[0])
+    gl = cu.basin_subbasin_long(gf[0], g1[0], lng, gsb, gh[0], nn, n)
+    np.testing.assert_array_equal(gl[0], ol[0])
+    assert gl[1:] == ol[1:]
+    op = oc.basin_subbasin_stream_prop(of[0], o1[0], lng, pend, nn)
+    gp = cu.basin_subbasin_stream_prop(gf[0], g1[0], lng, pend, nn, n)
+    np.testing.assert_array_equal(gp[0], op[0])
+    np.testing.assert_array_equal(gp[1], op[1])
+    for sm in (0, 1, 2):
+        np.testing.assert_array_equal(cu.basin_subbasin_map2subbasin(gf[0], elev, nn, g1[0], sm, n),
+                                      oc.basin_subbasin_map2subbasin(of[0], elev, nn, o1[0], sm))
+
+
+def test_subbasin_against_the_reference_itself():
+    from oracle import ref
+    from wmf_b200 import CuModule
+    if not ref.available():
+        pytest.skip("oracle/_ref did not travel")
+    bs = make_basin("G2", 260, 200, 8)
+    b, n = bs["basin"], bs["n"]
+    v = basin_vectors(bs)
+    rc, cu = ref.RefCu(), CuModule()
+    geo_to(rc, bs)
+    geo_to(cu, bs)
+    r1, g1 = rc.basin_subbasin_nod(b, v["acum"], 40), cu.basin_subbasin_nod(b, v["acum"], 40)
+    assert r1[2] == g1[2]
+    np.testing.assert_array_equal(g1[1], r1[1])
+    rf, gf = rc.basin_subbasin_find(b, r1[1], r1[2]), cu.basin_subbasin_find(b, g1[1], g1[2])
+    np.testing.assert_array_equal(gf[0], rf[0])
+    np.testing.assert_array_equal(cu.basin_subbasin_cut(g1[2]), rc.basin_subbasin_cut(r1[2]))

@@ -269,6 +269,94 @@ class CuModule:
                                          C.byref(nn), C.byref(ncau)))
         return cauce, nodos, traz, nn.value, ncau.value
 
+    # ---- sub-basin (hills) topology: called by SimuBasin.__init__ / set_Geomorphology (wmf.py:3019-3023, 3664-3676) ----
+    def basin_subbasin_nod(self, basin_f, acum, umbral, nceldas=None):
+        """cauce,nodos_fin,n_nodos = basin_subbasin_nod(basin_f,acum,umbral,[nceldas])   -- cuencas.f90:1835-1920"""
+        b, n, res = self._table(basin_f)
+        a = self._vec(acum, n, np.int32, "acum")
+        c = self.ctx
+        dev = getattr(b, "device", None)
+        cauce, nodos = (self._new(res, (n,), np.int32, dev) for _ in range(2))
+        nn = C.c_int32()
+        c.check(c.L.wmf_basin_subbasin_nod(c.h, ptr(b), ptr(a), n, int(umbral), ptr(cauce), ptr(nodos), C.byref(nn)))
+        return cauce, nodos, nn.value
+
+    def basin_subbasin_cut(self, n_nodos):
+        """sub_basins = basin_subbasin_cut(n_nodos)   -- cuencas.f90:1921-1930"""
+        c = self.ctx
+        out = np.empty((2, int(n_nodos)), np.int32, order="F")
+        c.check(c.L.wmf_basin_subbasin_cut(c.h, int(n_nodos), ptr(out)))
+        return out
+
+    def basin_subbasin_find(self, basin_f, nodos, n_nodos, nceldas=None):
+        """sub_pert,sub_basin = basin_subbasin_find(basin_f,nodos,n_nodos,[nceldas])   -- cuencas.f90:1979-2010 (the Fortran
+        never assigns sub_basin: zeros)"""
+        b, n, res = self._table(basin_f)
+        nd = self._vec(nodos, n, np.int32, "nodos")
+        c = self.ctx
+        sub_pert = self._new(res, (n,), np.int32, getattr(b, "device", None))
+        c.check(c.L.wmf_basin_subbasin_find(c.h, ptr(b), ptr(nd), n, ptr(sub_pert)))
+        return sub_pert, np.zeros(int(n_nodos), np.int32)
+
+    def basin_subbasin_horton(self, sub_basins, nceldas, n_nodos=None):
+        """sub_horton,nod_horton = basin_subbasin_horton(sub_basins,nceldas,[n_nodos])   -- cuencas.f90:1931-1978"""
+        sb = np.asfortranarray(sub_basins, dtype=np.int32)
+        if sb.ndim != 2 or sb.shape[0] != 2:
+            raise _f2py_error(f"sub_basins must have shape (2,n_nodos), got {sb.shape}")
+        c = self.ctx
+        sh, nh = np.empty(sb.shape[1], np.int32), np.empty(int(nceldas), np.int32)
+        c.check(c.L.wmf_basin_subbasin_horton(c.h, ptr(sb), sb.shape[1], int(nceldas), ptr(sh), ptr(nh)))
+        return sh, nh
+
+    def basin_subbasin_long(self, sub_pert, cauce, long, sub_basin, sub_horton, n_nodos=None, nceldas=None):
+        """sub_basin_long,max_long,nodo_max_long = basin_subbasin_long(sub_pert,cauce,long,sub_basin,sub_horton,[n_nodos,nceldas])
+        -- cuencas.f90:2011-2051"""
+        sp = np.ascontiguousarray(np.asarray(sub_pert).reshape(-1), np.int32)
+        n = sp.size
+        ca, lg = self._vec(cauce, n, np.int32, "cauce"), self._vec(long, n, np.float32, "long")
+        sb = np.asfortranarray(sub_basin, dtype=np.int32)
+        shn = self._vec(sub_horton, sb.shape[1], np.int32, "sub_horton")
+        c = self.ctx
+        out = np.empty(sb.shape[1], np.float32)
+        mx, nmx = C.c_float(), C.c_int32()
+        c.check(c.L.wmf_basin_subbasin_long(c.h, ptr(sp), ptr(ca), ptr(lg), ptr(sb), ptr(shn), sb.shape[1], n, ptr(out),
+                                            C.byref(mx), C.byref(nmx)))
+        return out, mx.value, nmx.value
+
+    def basin_subbasin_stream_prop(self, sub_pert, cauce, long, slope, n_nodos, nceldas=None):
+        """stream_slope,stream_long = basin_subbasin_stream_prop(sub_pert,cauce,long,slope,n_nodos,[nceldas])
+        -- cuencas.f90:2093-2115"""
+        sp = np.ascontiguousarray(np.asarray(sub_pert).reshape(-1), np.int32)
+        n = sp.size
+        ca = self._vec(cauce, n, np.int32, "cauce")
+        lg, sl = self._vec(long, n, np.float32, "long"), self._vec(slope, n, np.float32, "slope")
+        c = self.ctx
+        ss, slo = np.empty(int(n_nodos), np.float32), np.empty(int(n_nodos), np.float32)
+        c.check(c.L.wmf_basin_subbasin_stream_prop(c.h, ptr(sp), ptr(ca), ptr(lg), ptr(sl), n, int(n_nodos), ptr(ss), ptr(slo)))
+        return ss, slo
+
+    def basin_subbasin_map2subbasin(self, sub_pert, basin_var, n_nodos, cauce, sum_mean, nceldas=None):
+        """subbasin_sum = basin_subbasin_map2subbasin(sub_pert,basin_var,n_nodos,cauce,sum_mean,[nceldas])   -- cuencas.f90:2052-2092"""
+        sp = np.ascontiguousarray(np.asarray(sub_pert).reshape(-1), np.int32)
+        n = sp.size
+        v, ca = self._vec(basin_var, n, np.float32, "basin_var"), self._vec(cauce, n, np.int32, "cauce")
+        c = self.ctx
+        out = np.empty(int(n_nodos), np.float32)
+        c.check(c.L.wmf_basin_subbasin_map2subbasin(c.h, ptr(sp), ptr(v), int(n_nodos), n, ptr(ca), int(sum_mean), ptr(out)))
+        return out
+
+    def basin_stream_slope(self, basin_f, basin_elev, basin_long, nodos, n_cauce, nceldas=None):
+        """stream_s,stream_l = basin_stream_slope(basin_f,basin_elev,basin_long,nodos,n_cauce,[nceldas])   -- cuencas.f90:1380-1438"""
+        b, n, res = self._table(basin_f)
+        e, lg = self._vec(basin_elev, n, np.float32, "basin_elev"), self._vec(basin_long, n, np.float32, "basin_long")
+        nd = self._vec(nodos, n, np.int32, "nodos")
+        c = self.ctx
+        self._push_geo()
+        dev = getattr(b, "device", None)
+        ss, sl = (self._new(res, (n,), np.float32, dev) for _ in range(2))
+        c.check(c.L.wmf_basin_stream_slope(c.h, ptr(b), ptr(e), ptr(lg), ptr(nd), n, ptr(ss), ptr(sl)))
+        return ss, sl
+
     def basin_stream_type(self, basin_f, acum, umbrales, numbrales=None, nceldas=None):
         """stream_types = basin_stream_type(basin_f,acum,umbrales,[numbrales,nceldas])   -- cuencas.f90:1439-1463"""
         res = is_torch_cuda(acum)

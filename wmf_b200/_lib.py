@@ -91,6 +91,8 @@ EXPORTS = [
     "wmf_basin_stream_type", "wmf_geo_acum_to_cauce", "wmf_geo_hand", "wmf_geo_hand_global",
     "wmf_basin_time_to_out", "wmf_basin_propagate", "wmf_shia_run", "wmf_eval_scores",
     "wmf_calc_speed", "wmf_last_kernel_ms", "wmf_last_shia_stats", "wmf_rain_idw", "wmf_rain_mit",
+    "wmf_basin_subbasin_nod", "wmf_basin_subbasin_cut", "wmf_basin_subbasin_find", "wmf_basin_subbasin_horton",
+    "wmf_basin_subbasin_long", "wmf_basin_subbasin_stream_prop", "wmf_basin_subbasin_map2subbasin", "wmf_basin_stream_slope",
 ]
 
 _lib = None
@@ -143,6 +145,14 @@ def load() -> C.CDLL:
     L.wmf_calc_speed.argtypes = [vp, f32, f32, f32, f32, f32, i32, f32p, f32p]
     L.wmf_last_kernel_ms.argtypes = [vp, f32p]
     L.wmf_last_shia_stats.argtypes = [vp, i32p, i32p]
+    L.wmf_basin_subbasin_nod.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32p]
+    L.wmf_basin_subbasin_cut.argtypes = [vp, i32, vp]
+    L.wmf_basin_subbasin_find.argtypes = [vp, vp, vp, i32, vp]
+    L.wmf_basin_subbasin_horton.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.wmf_basin_subbasin_long.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, f32p, i32p]
+    L.wmf_basin_subbasin_stream_prop.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp]
+    L.wmf_basin_subbasin_map2subbasin.argtypes = [vp, vp, vp, i32, i32, vp, i32, vp]
+    L.wmf_basin_stream_slope.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
     L.wmf_rain_idw.argtypes = [vp, vp, vp, vp, f32, i32, i32, i32, f32, vp, i32, vp, vp, i32p]
     L.wmf_rain_mit.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, i32, vp, vp, i32p]
     _lib = L

@@ -31,6 +31,9 @@ struct wmf_ctx {
     int32_t *q_par = nullptr;  // queue position (1-based) of the cell it drains to; 0 for the outlet
     int64_t q_cap = 0;
     int32_t find_n = 0, find_nc = 0, find_nr = 0, find_depth = 0;
+    // basin_subbasin_nod state (the reference's module global sub_basins_temp(2,n_nodos), returned by basin_subbasin_cut)
+    int32_t *sub_basins = nullptr;
+    int32_t sub_n = 0;
     // timing of the last shia run
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
