@@ -74,3 +74,41 @@ def test_subbasin_against_the_reference_itself():
     rf, gf = rc.basin_subbasin_find(b, r1[1], r1[2]), cu.basin_subbasin_find(b, g1[1], g1[2])
     np.testing.assert_array_equal(gf[0], rf[0])
     np.testing.assert_array_equal(cu.basin_subbasin_cut(g1[2]), rc.basin_subbasin_cut(r1[2]))
+
+
+def test_shia_on_the_hills_topology():
+    """modelType = 'hills' (wmf.py:3696-3708): the model elements are the sub-basins, every one a channel element
+    (unit_type = 3), drained through sub_basins(2,:).  The hills table built on the GPU feeds the same SHIA kernels."""
+    import oracle
+    from wmf_b200 import CuModule, ModelsModule, synth
+    bs = make_basin("G2", 240, 200, 9)
+    b, n = bs["basin"], bs["n"]
+    v = basin_vectors(bs)
+    cu = CuModule()
+    geo_to(cu, bs)
+    cauce, nodos, nn = cu.basin_subbasin_nod(b, v["acum"], 25, n)
+    hills_own, _ = cu.basin_subbasin_find(b, nodos, nn, n)
+    hills = cu.basin_subbasin_cut(nn)
+    sub_horton, _ = cu.basin_subbasin_horton(hills, n, nn)
+    sub_long, max_long, _ = cu.basin_subbasin_long(hills_own, cauce, v["lng"], hills, sub_horton, nn, n)
+    s_slope, s_long = cu.basin_subbasin_stream_prop(hills_own, cauce, v["lng"], v["pend"], nn, n)
+    assert nn > 100 and max_long > 0
+    structure = np.zeros((3, nn), np.int32, order="F")
+    structure[0] = hills[1]                                               # models.drena = hills[1] (wmf.py:3698)
+    cells = np.bincount(hills_own, minlength=nn + 1)[1:][::-1]            # cells of the hill in column i (hill id nn-i)
+    length = np.maximum(sub_long, 30.0).astype(np.float32)
+    slope = np.nan_to_num(s_slope[::-1], nan=0.01).astype(np.float32)
+    inp = synth.make_shia_inputs(structure, np.full(nn, 10 ** 6), length, np.maximum(slope, 1e-3), dxp=30.0, n_reg=80, seed=9,
+                                 n_control=8)
+    inp["elem_area"] = (cells * 30.0 ** 2).astype(np.float32)[None, :]
+    assert (np.asarray(inp["unit_type"]) == 3).all()
+    ref = oracle.shia_v1(inp)
+    m = ModelsModule()
+    synth.apply_to_models(m, inp)
+    m.set_rain(inp["rain"], inp["pos_evento"])
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    ret = m.shia_v1(None, None, inp["calib"], n_cont, 1, 80, None, None, nn)
+    for got, want, nm in ((ret[0], ref["q"], "Q"), (ret[9], ref["stoout"], "StoOut")):
+        got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+        assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max(), nm
+    assert ref["q"][0].max() > 0
