@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define WMF_ABI_VERSION 7
+#define WMF_ABI_VERSION 8
 
 enum {
     WMF_OK = 0,
@@ -275,6 +275,9 @@ int wmf_eval_scores(wmf_ctx *ctx, const float *q, int32_t n_members, int32_t n_c
  * (nreg) as the Fortran returns them (the field sums are accumulated in fp64).  *n_records = rows of the finished table.
  * While interpolating the table must hold 1 + (number of steps with a positive reading) rows -- capacity = nreg + 1 always
  * suffices; with table = NULL only the statistics are computed. */
+/* rain_pre_mit, modelosv2.f90:1068-1101: tin_perte (nceldas) = 1-based triangle of every cell, 0 = none */
+int wmf_rain_pre_mit(wmf_ctx *ctx, const float *xy_basin, const int32_t *tin, const float *coord, int32_t nceldas,
+                     int32_t ntin, int32_t ncoord, int32_t *tin_perte);
 int wmf_rain_idw(wmf_ctx *ctx, const float *xy_basin, const float *coord, const float *rain, float pp,
                  int32_t nceldas, int32_t ncoord, int32_t nreg, float umbral, int32_t *table, int32_t capacity,
                  float *mean_rain, int32_t *pos_ids, int32_t *n_records);

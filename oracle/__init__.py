@@ -570,3 +570,12 @@ def rain_mit(xy_basin, coord, rain, tin, tin_perte, umbral):
     n, nc, T = xy.shape[1], co.shape[1], r.shape[1]
     args = (_p(xy, f32p), _p(co, f32p), _p(r, f32p), _p(tn, i32p), _p(tp, i32p), n, nc, tn.shape[1], T, C.c_float(umbral))
     return _rain_common(L, L.wo_rain_mit, args, n, T)
+
+
+def rain_pre_mit(xy_basin, tin, coord):
+    """tin_perte = rain_pre_mit(xy_basin,tin,coord)   -- modelosv2.f90:1068-1101"""
+    L = lib()
+    xy, co, tn = _f(xy_basin), _f(coord), _i(tin)
+    out = np.zeros(xy.shape[1], np.int32)
+    L.wo_rain_pre_mit(_p(xy, f32p), _p(tn, i32p), _p(co, f32p), xy.shape[1], tn.shape[1], _p(out, i32p))
+    return out

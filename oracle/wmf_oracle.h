@@ -160,6 +160,9 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out);
 float wo_calc_speed(float sm, float coef, float expo, float elem_long, float *speed, float dt,
                     int32_t calc_niter);
 
+/* rain_pre_mit, modelosv2.f90:1068-1101 */
+void wo_rain_pre_mit(const float *xy_basin, const int32_t *tin, const float *coord, int32_t nceldas, int32_t ntin,
+                     int32_t *tin_perte);
 /* sub-basin (hills) topology: cuencas.f90:1380-1438, 1835-2118 (see wmf_oracle_cu.c for the quirks reproduced) */
 void wo_basin_stream_slope(const wo_geo *g, const int32_t *basin_f, const float *elev, const float *lng,
                            const int32_t *nodos, int32_t n_cauce, int32_t n, float *stream_s, float *stream_l);

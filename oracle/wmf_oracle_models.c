@@ -779,3 +779,24 @@ int32_t wo_rain_mit(const float *xy_basin, const float *coord, const float *rain
     free(campo);
     return rc ? -1 : cont - 1;
 }
+
+/* rain_pre_mit, modelosv2.f90:1068-1101: the triangle of every cell; the test is only s > 0 and t > 0 (not s + t < 1) and the
+ * last triangle that passes wins; a cell no triangle claims keeps 0 (the Fortran leaves it unassigned) */
+void wo_rain_pre_mit(const float *xy_basin, const int32_t *tin, const float *coord, int32_t nceldas, int32_t ntin,
+                     int32_t *tin_perte)
+{
+    for (int32_t c = 0; c < nceldas; ++c) {
+        const float px = xy_basin[2 * (size_t)c], py = xy_basin[2 * (size_t)c + 1];
+        int32_t own = 0;
+        for (int32_t k = 0; k < ntin; ++k) {
+            const int32_t i0 = tin[3 * k] - 1, i1 = tin[3 * k + 1] - 1, i2 = tin[3 * k + 2] - 1;
+            const float p0x = coord[2 * i0], p1x = coord[2 * i1], p2x = coord[2 * i2];
+            const float p0y = coord[2 * i0 + 1], p1y = coord[2 * i1 + 1], p2y = coord[2 * i2 + 1];
+            const float Area = fabsf(1.0f / 2.0f * (-p1y * p2x + p0y * (-p1x + p2x) + p0x * (p1y - p2y) + p1x * p2y));
+            const float s = 1.0f / (2.0f * Area) * (p0y * p2x - p0x * p2y + (p2y - p0y) * px + (p0x - p2x) * py);
+            const float t = 1.0f / (2.0f * Area) * (p0x * p1y - p0y * p1x + (p0y - p1y) * px + (p1x - p0x) * py);
+            if (s > 0.0f && t > 0.0f) own = k + 1;
+        }
+        tin_perte[c] = own;
+    }
+}

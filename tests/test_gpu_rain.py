@@ -79,6 +79,8 @@ def test_rain_mit(tmp_path):
     assert perte.min() >= 1
     want = oracle.rain_mit(xy, coord, rain, tin, perte, 0.0)
     m = ModelsModule()
+    # rain_pre_mit on the GPU: bit-exact against the oracle's (its looser test -- only s > 0 and t > 0 -- picks other triangles)
+    np.testing.assert_array_equal(m.rain_pre_mit(xy, tin, coord).reshape(-1), oracle.rain_pre_mit(xy, tin, coord))
     path = str(tmp_path / "mit.bin")
     mean, pos = m.rain_mit(xy, coord, rain, tin, perte[None, :], 0, path, 0.0, np.ones(bs["n"]))
     check(mean, pos, np.fromfile(path, np.int32).reshape(-1, bs["n"]), want)

@@ -279,6 +279,7 @@ def test_rain_interpolation_oracle_is_bit_identical_to_the_reference(ref, tmp_pa
     tin = np.asfortranarray((Delaunay(coord.T.astype(np.float64)).simplices.T + 1).astype(np.int32))
     perte = ref.rain_pre_mit(xy, tin, coord)
     assert perte.min() >= 1
+    same(perte, oracle.rain_pre_mit(xy, tin, coord), "rain_pre_mit")
     R, O = ref.rain_mit(xy, coord, rain, tin, perte, 0.0), oracle.rain_mit(xy, coord, rain, tin, perte, 0.0)
     for k in ("table", "pos_ids", "mean_rain"):
         same(R[k], O[k], "rain_mit " + k)

@@ -121,6 +121,20 @@ def main():
             del acum_map, red, hand_g
             line.update({"map2basin_ms": t_m2b, "basics_ms": t_bas, "stream_type_ms": t_typ, "geo_hand_ms": t_hand,
                          "basics_gbs_40B": 40.0 * n / (t_bas / 1e3) / 1e9, "geo_hand_gbs_40B": 40.0 * n / (t_hand / 1e3) / 1e9})
+            # sub-basin (hills) topology as SimuBasin.__init__ / set_Geomorphology drive it (wmf.py:3019-3023, 3664-3676)
+            thr = 500
+            t_nod, (cau2, nodos_fin, nn) = timed(lambda: cu.basin_subbasin_nod(b, acum, thr))
+            t_find, (hills_own, _) = timed(lambda: cu.basin_subbasin_find(b, nodos_fin, nn))
+            hills = cu.basin_subbasin_cut(nn)
+            cu.basin_subbasin_nod(b, acum, thr)
+            t_hort, (sub_h, _) = timed(lambda: cu.basin_subbasin_horton(hills, n, nn))
+            ho, ca, lg, pe = (x.cpu().numpy() for x in (hills_own, cau2, lng, pend))
+            t_long, _ = timed(lambda: cu.basin_subbasin_long(ho, ca, lg, hills, sub_h, nn, n))
+            t_prop, _ = timed(lambda: cu.basin_subbasin_stream_prop(ho, ca, lg, pe, nn, n))
+            ca3, nod3, _, _, ncau = cu.basin_stream_nod(b, acum, thr)
+            t_ssl, _ = timed(lambda: cu.basin_stream_slope(b, elev, lng, nod3, ncau))
+            line.update({"subbasin": {"threshold": thr, "n_nodos": int(nn), "nod_ms": t_nod, "find_ms": t_find, "horton_ms": t_hort,
+                                      "long_ms_host_arrays": t_long, "stream_prop_ms_host_arrays": t_prop, "stream_slope_ms": t_ssl}})
             del d_dem, d_dirf, demv, dirv, ac2, lng, pend, elev, cauce, hand, hdnd, aq
         if a.check:
             bb = b.cpu().numpy().reshape(-1, 3)

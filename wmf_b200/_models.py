@@ -337,6 +337,17 @@ class ModelsModule:
                     f.write(table[:, :int(nrec.value)].tobytes(order="F"))
         return mean, pos
 
+    def rain_pre_mit(self, xy_basin, tin, coord, nceldas=None, ntin=None, ncoord=None):
+        """tin_perte = rain_pre_mit(xy_basin,tin,coord,[nceldas,ntin,ncoord])   -- modelosv2.f90:1068-1101"""
+        c = self.ctx
+        xy, co = np.asfortranarray(xy_basin, dtype=np.float32), np.asfortranarray(coord, dtype=np.float32)
+        tn = np.asfortranarray(tin, dtype=np.int32)
+        if xy.ndim != 2 or xy.shape[0] != 2 or co.ndim != 2 or co.shape[0] != 2 or tn.ndim != 2 or tn.shape[0] != 3:
+            raise ValueError("xy_basin must be (2,nceldas), tin (3,ntin), coord (2,ncoord)")
+        out = np.zeros((1, xy.shape[1]), np.int32, order="F")
+        c.check(c.L.wmf_rain_pre_mit(c.h, ptr(xy), ptr(tn), ptr(co), xy.shape[1], tn.shape[1], co.shape[1], ptr(out)))
+        return out
+
     def rain_idw(self, xy_basin, coord, rain, pp, nhills, ruta, umbral, maskvector=None, nceldas=None, ncoord=None, nreg=None,
                  resident=False):
         """meanrain,posids = rain_idw(xy_basin,coord,rain,pp,nhills,ruta,umbral,maskvector,[nceldas,ncoord,nreg])

@@ -230,9 +230,46 @@ int rain_stage(wmf_ctx *ctx, Scope &sc, RainP &P, const float **rain_dev, const 
     return WMF_OK;
 }
 
+// rain_pre_mit, modelosv2.f90:1068-1101: one thread per cell scans the triangles; the last one with s > 0 and t > 0 wins
+__global__ void k_pre_mit(const float2 *__restrict__ xy, const int32_t *__restrict__ tin, const float2 *__restrict__ coord, int N,
+                          int ntin, int32_t *__restrict__ perte) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= N) return;
+    const float2 p = xy[cell];
+    int own = 0;
+    for (int k = 0; k < ntin; ++k) {
+        const float2 p0 = __ldg(coord + __ldg(tin + 3 * k) - 1), p1 = __ldg(coord + __ldg(tin + 3 * k + 1) - 1),
+                     p2 = __ldg(coord + __ldg(tin + 3 * k + 2) - 1);
+        const float Area = fabsf(1.0f / 2.0f * (-p1.y * p2.x + p0.y * (-p1.x + p2.x) + p0.x * (p1.y - p2.y) + p1.x * p2.y));
+        const float inv = 1.0f / (2.0f * Area);
+        const float s = inv * (p0.y * p2.x - p0.x * p2.y + (p2.y - p0.y) * p.x + (p0.x - p2.x) * p.y);
+        const float t = inv * (p0.x * p1.y - p0.y * p1.x + (p0.y - p1.y) * p.x + (p1.x - p0.x) * p.y);
+        if (s > 0.0f && t > 0.0f) own = k + 1;
+    }
+    perte[cell] = own;
+}
+
 }  // namespace
 
 extern "C" {
+
+int wmf_rain_pre_mit(wmf_ctx *ctx, const float *xy_basin, const int32_t *tin, const float *coord, int32_t nceldas, int32_t ntin,
+                     int32_t ncoord, int32_t *tin_perte) {
+    if (!ctx || !xy_basin || !tin || !coord || !tin_perte || nceldas <= 0 || ntin <= 0 || ncoord <= 0) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    const float *d_xy, *d_co;
+    const int32_t *d_t;
+    int32_t *d_p;
+    WMF_TRY(sc.in(xy_basin, (size_t)2 * nceldas, &d_xy));
+    WMF_TRY(sc.in(coord, (size_t)2 * ncoord, &d_co));
+    WMF_TRY(sc.in(tin, (size_t)3 * ntin, &d_t));
+    WMF_TRY(sc.out(tin_perte, (size_t)nceldas, &d_p));
+    LAUNCH(ctx, k_pre_mit, grid_for(nceldas, 256), 256, 0, reinterpret_cast<const float2 *>(d_xy), d_t,
+           reinterpret_cast<const float2 *>(d_co), nceldas, ntin, d_p);
+    return sc.finish();
+}
+
 
 int wmf_rain_idw(wmf_ctx *ctx, const float *xy_basin, const float *coord, const float *rain, float pp, int32_t nceldas,
                  int32_t ncoord, int32_t nreg, float umbral, int32_t *table, int32_t capacity, float *mean_rain,

@@ -222,40 +222,35 @@ __global__ void k_hz_sort_asc(const int32_t *__restrict__ cstart, const int32_t 
         l[q + 1] = v;
     }
 }
-__global__ void __launch_bounds__(1024) k_hz_relax(const int32_t *__restrict__ sb, const int32_t *__restrict__ cstart,
-                                                   const int32_t *__restrict__ cc, const int32_t *__restrict__ child, int nn,
-                                                   volatile int32_t *__restrict__ sh, int32_t *__restrict__ nod_horton) {
-    __shared__ int s_changed;
-    for (int j = threadIdx.x; j < nn; j += blockDim.x)
-        if (cc[j] == 0) { sh[j] = 1; nod_horton[sb[2 * (size_t)j] - 1] = 1; }     // no tributary: order 1 (:1942-1949)
-    __syncthreads();
-    for (;;) {
-        if (threadIdx.x == 0) s_changed = 0;
-        __syncthreads();
-        for (int j = threadIdx.x; j < nn; j += blockDim.x) {
-            if (sh[j] != 0) continue;
-            const int32_t *l = child + cstart[j];
-            // the reference looks only at tributaries in columns below its own (j < i) and keeps at most ten (drenantes(10))
-            int cont = 0, mx = 0, mn = 0;
-            bool ready = true;
-            for (int q = 0; q < cc[j] && cont < 10; ++q) {
-                if (l[q] >= j) break;
-                const int o = sh[l[q]];
-                if (o == 0) { ready = false; break; }
-                mx = cont ? max(mx, o) : o;
-                mn = cont ? min(mn, o) : o;
-                ++cont;
-            }
-            if (!ready) continue;
-            const int o = (mx == mn) ? mx + 1 : mx;
-            sh[j] = o;
-            nod_horton[sb[2 * (size_t)j] - 1] = o;
-            s_changed = 1;
-        }
-        __syncthreads();
-        if (!s_changed) break;
-        __syncthreads();
+// one relaxation sweep over all nodes: a node whose (first ten) tributaries are all ordered gets its own order; the host
+// repeats the sweep until nothing changes (as many sweeps as the node tree is high)
+__global__ void k_hz_leaves(const int32_t *__restrict__ sb, const int32_t *__restrict__ cc, int nn, int32_t *__restrict__ sh,
+                            int32_t *__restrict__ nod_horton) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nn && cc[j] == 0) { sh[j] = 1; nod_horton[sb[2 * (size_t)j] - 1] = 1; }     // no tributary: order 1 (:1942-1949)
+}
+__global__ void k_hz_sweep(const int32_t *__restrict__ sb, const int32_t *__restrict__ cstart, const int32_t *__restrict__ cc,
+                           const int32_t *__restrict__ child, int nn, const int32_t *__restrict__ sh_in, int32_t *__restrict__ sh_out,
+                           int32_t *__restrict__ nod_horton, int32_t *__restrict__ changed) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nn) return;
+    const int cur = sh_in[j];
+    if (cur != 0) { sh_out[j] = cur; return; }
+    const int32_t *l = child + cstart[j];
+    // the reference looks only at tributaries in columns below its own (j < i) and keeps at most ten (drenantes(10))
+    int cont = 0, mx = 0, mn = 0;
+    for (int q = 0; q < cc[j] && cont < 10; ++q) {
+        if (l[q] >= j) break;
+        const int o = sh_in[l[q]];
+        if (o == 0) { sh_out[j] = 0; return; }
+        mx = cont ? max(mx, o) : o;
+        mn = cont ? min(mn, o) : o;
+        ++cont;
     }
+    const int o = (mx == mn) ? mx + 1 : mx;
+    sh_out[j] = o;
+    nod_horton[sb[2 * (size_t)j] - 1] = o;
+    *changed = 1;
 }
 
 // ---------------------------------------------------------------- basin_subbasin_long, longest path (:2033-2050)
@@ -295,11 +290,13 @@ __global__ void k_m2s_final(const float *__restrict__ red, const int32_t *__rest
 struct Reach { float S, L; int32_t cont, second; };
 // one thread per start node (nodos > 0, not the outlet): slope and (INTEGER) length of the reach down to the next node
 __global__ void k_ss_walk(const int32_t *__restrict__ b, const float *__restrict__ elev, const float *__restrict__ lng,
-                          const int32_t *__restrict__ nodos, int n, float dxp, Reach *__restrict__ reach, int32_t *__restrict__ lastsec) {
+                          const int32_t *__restrict__ nodos, int n, float dxp, Reach *__restrict__ reach, int32_t *__restrict__ lastsec,
+                          int32_t *__restrict__ owner) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     lastsec[i] = -1;
     if (!(nodos[i] > 0 && DRAIN(b, i) != 0)) return;
+    atomicMax(owner + i, i);               // the reach's cells are claimed on the way down: the largest start node wins
     const float e0 = elev[i], d0 = lng[i];
     float e = e0, dist = d0;
     int cont = 1, second = -1;
@@ -310,6 +307,7 @@ __global__ void k_ss_walk(const int32_t *__restrict__ b, const float *__restrict
             e = elev[d];
             dist = dist + lng[d];
             if (cont == 2) second = d;
+            atomicMax(owner + d, i);
         } else {
             if (cont == 1) { cont = 2; e = elev[d]; dist = dist + lng[d]; }    // celdas_tramo(2) is NOT written here
             break;
@@ -323,27 +321,23 @@ __global__ void k_ss_walk(const int32_t *__restrict__ b, const float *__restrict
     reach[i] = Reach{S, (float)Li, cont, second};
     if (second >= 0) lastsec[i] = i;       // this reach leaves a cell in celdas_tramo(2)
 }
-// claim = the largest start node writing a cell: the reach's own cells, or -- when the cell below the start node is a node --
-// the cell the latest earlier reach left in celdas_tramo(2)
-__global__ void k_ss_claim(const int32_t *__restrict__ b, const int32_t *__restrict__ nodos, const Reach *__restrict__ reach,
-                           const int32_t *__restrict__ lastsec_scan, int n, int pass, int32_t *__restrict__ owner,
-                           float *__restrict__ ss, float *__restrict__ sl) {
+// when the cell below a start node is itself a node, the reference's assignment loop also writes the cell the latest earlier
+// reach left in celdas_tramo(2): one more claim
+__global__ void k_ss_stale(const int32_t *__restrict__ b, const int32_t *__restrict__ nodos, const Reach *__restrict__ reach,
+                           const int32_t *__restrict__ lastsec_scan, int n, int32_t *__restrict__ owner) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (!(nodos[i] > 0 && DRAIN(b, i) != 0)) return;
-    const Reach r = reach[i];
-    auto touch = [&](int c) {
-        if (pass == 0) atomicMax(owner + c, i);
-        else if (owner[c] == i) { ss[c] = r.S; sl[c] = r.L; }
-    };
-    touch(i);
-    if (r.second >= 0) {
-        int d = r.second;
-        for (int k = 2; k <= r.cont; ++k) { touch(d); d = n - DRAIN(b, d); }
-    } else {
-        const int prev = i > 0 ? lastsec_scan[i - 1] : -1;    // latest start node before i that wrote celdas_tramo(2)
-        if (prev >= 0) touch(reach[prev].second);
-    }
+    if (i >= n || i == 0) return;
+    if (!(nodos[i] > 0 && DRAIN(b, i) != 0) || reach[i].second >= 0) return;
+    const int prev = lastsec_scan[i - 1];
+    if (prev >= 0) atomicMax(owner + reach[prev].second, i);
+}
+// every claimed cell takes the slope and length of the reach that owns it
+__global__ void k_ss_write(const int32_t *__restrict__ owner, const Reach *__restrict__ reach, int n, float *__restrict__ ss,
+                           float *__restrict__ sl) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int o = owner[c];
+    if (o >= 0) { ss[c] = reach[o].S; sl[c] = reach[o].L; }
 }
 __global__ void k_fill2(float *a, float *b2, float v, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -446,7 +440,23 @@ int wmf_basin_subbasin_horton(wmf_ctx *ctx, const int32_t *sub_basins, int32_t n
     WMF_TRY(wmf_device_exclusive_scan_i32(ctx, sc, cc, cstart, (int64_t)nn + 1, nullptr));
     LAUNCH(ctx, k_hz_fill, GN, 256, 0, d_sb, cstart, nn, fillp, child);
     LAUNCH(ctx, k_hz_sort_asc, GN, 256, 0, cstart, cc, nn, child);
-    LAUNCH(ctx, k_hz_relax, 1, 1024, 0, d_sb, cstart, cc, child, nn, d_sh, d_nh);
+    LAUNCH(ctx, k_hz_leaves, GN, 256, 0, d_sb, cc, nn, d_sh, d_nh);
+    int32_t *sh2, *d_changed;
+    WMF_TRY(sc.alloc(&sh2, (size_t)nn));
+    WMF_TRY(sc.alloc(&d_changed, 1));
+    int32_t *a = d_sh, *b2 = sh2;
+    for (int it = 0; it < nn + 2; it += 8) {            // eight sweeps between two looks at the flag
+        CU_TRY(ctx, cudaMemsetAsync(d_changed, 0, sizeof(int32_t), ctx->stream));
+        for (int k = 0; k < 8; ++k) {
+            LAUNCH(ctx, k_hz_sweep, GN, 256, 0, d_sb, cstart, cc, child, nn, a, b2, d_nh, d_changed);
+            int32_t *t = a; a = b2; b2 = t;
+        }
+        int32_t h_changed = 0;
+        CU_TRY(ctx, cudaMemcpyAsync(&h_changed, d_changed, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!h_changed) break;
+    }
+    // an even number of sweeps per round: the current orders are back in d_sh
     return sc.finish();
 }
 
@@ -548,15 +558,15 @@ int wmf_basin_stream_slope(wmf_ctx *ctx, const int32_t *basin_f, const float *ba
     CU_TRY(ctx, cudaMemsetAsync(owner, 0xff, sizeof(int32_t) * (size_t)n, ctx->stream));    // -1
     const int G = grid_for(n, 256);
     LAUNCH(ctx, k_fill2, G, 256, 0, d_ss, d_sl, ctx->geo.nodata, n);                        // stream_s = stream_l = noData (:1393-1394)
-    LAUNCH(ctx, k_ss_walk, G, 256, 0, d_b, d_e, d_l, d_n, n, ctx->geo.dxp, reach, lastsec);
+    LAUNCH(ctx, k_ss_walk, G, 256, 0, d_b, d_e, d_l, d_n, n, ctx->geo.dxp, reach, lastsec, owner);
     size_t tmp_bytes = 0;
     cub::DeviceScan::InclusiveScan(nullptr, tmp_bytes, lastsec, lastscan, cub::Max(), n, ctx->stream);
     void *tmp;
     WMF_TRY(sc.alloc(&tmp, tmp_bytes));
     CU_TRY(ctx, cub::DeviceScan::InclusiveScan(tmp, tmp_bytes, lastsec, lastscan, cub::Max(), n, ctx->stream));
     ctx->launches += 2;
-    LAUNCH(ctx, k_ss_claim, G, 256, 0, d_b, d_n, reach, lastscan, n, 0, owner, d_ss, d_sl);
-    LAUNCH(ctx, k_ss_claim, G, 256, 0, d_b, d_n, reach, lastscan, n, 1, owner, d_ss, d_sl);
+    LAUNCH(ctx, k_ss_stale, G, 256, 0, d_b, d_n, reach, lastscan, n, owner);
+    LAUNCH(ctx, k_ss_write, G, 256, 0, owner, reach, n, d_ss, d_sl);
     return sc.finish();
 }
 
