@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define WMF_ABI_VERSION 8
+#define WMF_ABI_VERSION 9
 
 enum {
     WMF_OK = 0,
@@ -123,6 +123,10 @@ int wmf_basin_time_to_out(wmf_ctx *ctx, const int32_t *basin_f, const float *lng
 /* basin_propagate, cuencas.f90:1811-1833 */
 int wmf_basin_propagate(wmf_ctx *ctx, const int32_t *basin_f, const float *var, int32_t nceldas,
                         float *var_prop);
+
+/* stream_find_to_corr, cuencas.f90:372-417 (SimuBasin.__init__ with useCauceMap, wmf.py:2998-3000) */
+int wmf_stream_find_to_corr(wmf_ctx *ctx, float x, float y, const int32_t *dir, const int32_t *cauce, int32_t nc,
+                            int32_t nf, float *lat, float *lon);
 
 /* Sub-basin (hills) topology: the routines SimuBasin.__init__ / set_Geomorphology call next to the basin cut
  * (wmf.py:3019-3023, 3664-3676).  Layouts as f2py: sub_basins (2,n_nodos), vectors (nceldas) or (n_nodos). */

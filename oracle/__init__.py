@@ -307,6 +307,15 @@ class Cu:
         return out
 
 
+    def stream_find_to_corr(self, x, y, dem, dir_map, cauce):
+        """lat,lon = stream_find_to_corr(x,y,dem,dir,cauce,[nc,nf])   -- cuencas.f90:372-417"""
+        d, ca = _i(dir_map), _i(cauce)
+        lat, lon = C.c_float(), C.c_float()
+        g = self._geo()
+        self._L.wo_stream_find_to_corr(C.byref(g), C.c_float(x), C.c_float(y), _p(d, i32p), _p(ca, i32p), d.shape[0], d.shape[1],
+                                       C.byref(lat), C.byref(lon))
+        return lat.value, lon.value
+
     # ---- sub-basin (hills) topology, cuencas.f90:1380-1438, 1835-2118 ----
     def basin_stream_slope(self, basin_f, elev, lng, nodos, n_cauce):
         b = _i(basin_f)

@@ -301,6 +301,13 @@ class RefCu:
         return out
 
 
+    def stream_find_to_corr(self, x, y, dem, dir_map, cauce):
+        self._push()
+        de, d, ca = _f(dem), _i(dir_map), _i(cauce)
+        lat, lon = f32(), f32()
+        _call(CU, "stream_find_to_corr", f32(x), f32(y), de, d, ca, i32(d.shape[0]), i32(d.shape[1]), lat, lon)
+        return lat.value, lon.value
+
     # ---- sub-basin (hills) topology, cuencas.f90:1380-1438, 1835-2118 ----
     def basin_stream_slope(self, basin_f, elev, lng, nodos, n_cauce):
         self._push()

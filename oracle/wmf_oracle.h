@@ -160,6 +160,9 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out);
 float wo_calc_speed(float sm, float coef, float expo, float elem_long, float *speed, float dt,
                     int32_t calc_niter);
 
+/* stream_find_to_corr, cuencas.f90:372-417 */
+void wo_stream_find_to_corr(const wo_geo *g, float x, float y, const int32_t *dir, const int32_t *cauce, int32_t nc, int32_t nf,
+                            float *lat, float *lon);
 /* rain_pre_mit, modelosv2.f90:1068-1101 */
 void wo_rain_pre_mit(const float *xy_basin, const int32_t *tin, const float *coord, int32_t nceldas, int32_t ntin,
                      int32_t *tin_perte);

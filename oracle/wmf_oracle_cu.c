@@ -650,3 +650,35 @@ void wo_basin_subbasin_map2subbasin(const int32_t *sub_pert, const float *var, i
         else out[i - 1] = 0.0f;
     }
 }
+
+/* stream_find_to_corr, cuencas.f90:372-417: walk down DIR from (x,y) until a cell of the channel map (or the edge of the
+ * map / a nodata direction) is reached and return that cell's centre.  `dire` changes inside the 3x3 scan, so one sweep
+ * can take several steps; lat/lon stay unassigned (0 here) when the start cell matches no direction. */
+void wo_stream_find_to_corr(const wo_geo *g, float x, float y, const int32_t *dir, const int32_t *cauce, int32_t nc, int32_t nf,
+                            float *lat, float *lon)
+{
+    int32_t col, fil;
+    wo_coord2fil_col(g, x, y, &col, &fil);
+    *lat = 0.0f;
+    *lon = 0.0f;
+#define RM(a, c, f) a[(size_t)((f) - 1) * nc + ((c) - 1)]
+    if (col < 1 || col > nc || fil < 1 || fil > nf) return;
+    int32_t dire = RM(dir, col, fil);
+    int flag = 1;
+    while (flag == 1) {
+        for (int kf = 1; kf <= 3; ++kf)
+            for (int kc = 1; kc <= 3; ++kc) {
+                const int32_t envia = 9 - 3 * kf + kc;
+                if (dire == envia) {
+                    col = col + kc - 2;
+                    fil = fil + kf - 2;
+                    if (col < 1 || col > nc || fil < 1 || fil > nf) { dire = -1; } /* the Fortran reads outside the map here */
+                    else dire = RM(dir, col, fil);
+                    *lat = g->xll + g->dx * ((float)col - 0.5f);
+                    *lon = g->yll + g->dx * ((float)(g->nrows - fil) + 0.5f);
+                }
+            }
+        if (col > nc || fil > nf || col <= 0 || fil <= 0 || (float)dire == g->nodata || dire <= 0 || RM(cauce, col, fil) != 0) flag = 0;
+    }
+#undef RM
+}

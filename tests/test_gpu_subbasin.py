@@ -112,3 +112,24 @@ def test_shia_on_the_hills_topology():
         got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
         assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max(), nm
     assert ref["q"][0].max() > 0
+
+
+def test_stream_find_to_corr():
+    """cuencas.f90:372-417: the outlet moved down the flow directions onto the channel map (SimuBasin(useCauceMap=...))."""
+    from wmf_b200 import CuModule
+    bs = make_basin("G2", 120, 90, 4)
+    v = basin_vectors(bs)
+    oc = bs["cu"]
+    cu = CuModule()
+    geo_to(cu, bs)
+    amap = oc.basin_float_var2map(bs["basin"], v["acum"].astype(np.float32), 120, 90)
+    cauce = np.asfortranarray((amap > 40).astype(np.int32))
+    rng = np.random.default_rng(0)
+    moved = 0
+    for _ in range(40):
+        c, f = int(rng.integers(2, 119)), int(rng.integers(2, 89))
+        x, y = 30.0 * (c - 0.5), 30.0 * (90 - f + 0.5)
+        want = oc.stream_find_to_corr(x, y, bs["DEM"], bs["DIR"], cauce)
+        assert cu.stream_find_to_corr(x, y, bs["DEM"], bs["DIR"], cauce, 120, 90) == want
+        moved += want != (np.float32(x), np.float32(y))
+    assert moved > 20

@@ -324,3 +324,17 @@ def test_subbasin_topology_oracle_is_bit_identical_to_the_reference(ref, kind, n
     same(rs[0], os_[0], "stream_s")
     same(rs[1], os_[1], "stream_l")
     assert (os_[1][cauce == 1] == np.floor(os_[1][cauce == 1])).all()         # the implicitly INTEGER reach length
+
+
+def test_stream_find_to_corr_oracle_is_bit_identical_to_the_reference(ref):
+    import oracle
+    bs = make_basin("G2", 120, 90, 4)
+    rc, oc = pair(ref, bs)
+    v = basin_vectors(bs)
+    amap = oc.basin_float_var2map(bs["basin"], v["acum"].astype(np.float32), 120, 90)
+    cauce = (amap > 40).astype(np.int32)
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        c, f = int(rng.integers(2, 119)), int(rng.integers(2, 89))
+        x, y = 30.0 * (c - 0.5), 30.0 * (90 - f + 0.5)
+        assert rc.stream_find_to_corr(x, y, bs["DEM"], bs["DIR"], cauce) == oc.stream_find_to_corr(x, y, bs["DEM"], bs["DIR"], cauce)

@@ -269,6 +269,15 @@ class CuModule:
                                          C.byref(nn), C.byref(ncau)))
         return cauce, nodos, traz, nn.value, ncau.value
 
+    def stream_find_to_corr(self, x, y, dem, dir, cauce, nc=None, nf=None):
+        """lat,lon = stream_find_to_corr(x,y,dem,dir,cauce,[nc,nf])   -- cuencas.f90:372-417 (wmf.py:2998-3000)"""
+        c = self._push_geo()
+        di, ncc, nrr = self._raster(dir, np.int32, "dir")
+        ca, _, _ = self._raster(cauce, np.int32, "cauce")
+        lat, lon = C.c_float(), C.c_float()
+        c.check(c.L.wmf_stream_find_to_corr(c.h, float(x), float(y), ptr(di), ptr(ca), ncc, nrr, C.byref(lat), C.byref(lon)))
+        return lat.value, lon.value
+
     # ---- sub-basin (hills) topology: called by SimuBasin.__init__ / set_Geomorphology (wmf.py:3019-3023, 3664-3676) ----
     def basin_subbasin_nod(self, basin_f, acum, umbral, nceldas=None):
         """cauce,nodos_fin,n_nodos = basin_subbasin_nod(basin_f,acum,umbral,[nceldas])   -- cuencas.f90:1835-1920"""

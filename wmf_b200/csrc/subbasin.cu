@@ -344,9 +344,56 @@ __global__ void k_fill2(float *a, float *b2, float v, int n) {
     if (i < n) { a[i] = v; b2[i] = v; }
 }
 
+// stream_find_to_corr, cuencas.f90:372-417: one thread walks down DIR to the first cell of the channel map
+__global__ void k_find_to_corr(const int32_t *__restrict__ dir, const int32_t *__restrict__ cauce, int nc, int nf, int col, int fil,
+                               wmf_geo g, float *__restrict__ out) {
+    float lat = 0.0f, lon = 0.0f;
+    if (col >= 1 && col <= nc && fil >= 1 && fil <= nf) {
+        int dire = dir[(size_t)(fil - 1) * nc + (col - 1)];
+        bool go = true;
+        while (go) {
+            for (int kf = 1; kf <= 3; ++kf)
+                for (int kc = 1; kc <= 3; ++kc)
+                    if (dire == 9 - 3 * kf + kc) {      // `dire` changes inside the scan: a sweep can take several steps
+                        col = col + kc - 2;
+                        fil = fil + kf - 2;
+                        dire = (col < 1 || col > nc || fil < 1 || fil > nf) ? -1 : dir[(size_t)(fil - 1) * nc + (col - 1)];
+                        lat = g.xll + g.dx * ((float)col - 0.5f);
+                        lon = g.yll + g.dx * ((float)(g.nrows - fil) + 0.5f);
+                    }
+            if (col > nc || fil > nf || col <= 0 || fil <= 0 || (float)dire == g.nodata || dire <= 0 ||
+                cauce[(size_t)(fil - 1) * nc + (col - 1)] != 0)
+                go = false;
+        }
+    }
+    out[0] = lat;
+    out[1] = lon;
+}
+
 }  // namespace
 
 extern "C" {
+
+int wmf_stream_find_to_corr(wmf_ctx *ctx, float x, float y, const int32_t *dir, const int32_t *cauce, int32_t nc, int32_t nf,
+                            float *lat, float *lon) {
+    if (!ctx || !dir || !cauce || !lat || !lon || nc <= 0 || nf <= 0) return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    const int32_t *d_d, *d_c;
+    float *d_o, h[2];
+    WMF_TRY(sc.in(dir, (size_t)nc * nf, &d_d));
+    WMF_TRY(sc.in(cauce, (size_t)nc * nf, &d_c));
+    WMF_TRY(sc.alloc(&d_o, 2));
+    int32_t col, fil;
+    WMF_TRY(wmf_coord2fil_col(ctx, x, y, &col, &fil));
+    LAUNCH(ctx, k_find_to_corr, 1, 1, 0, d_d, d_c, nc, nf, col, fil, ctx->geo, d_o);
+    CU_TRY(ctx, cudaMemcpyAsync(h, d_o, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    WMF_TRY(sc.finish());
+    *lat = h[0];
+    *lon = h[1];
+    return WMF_OK;
+}
+
 
 int wmf_basin_subbasin_nod(wmf_ctx *ctx, const int32_t *basin_f, const int32_t *acum, int32_t n, int32_t umbral, int32_t *cauce,
                            int32_t *nodos_fin, int32_t *n_nodos) {
