@@ -10,8 +10,8 @@
 //                   stations in the reference's order (bit-identical fields).  Only the steps with a positive reading
 //                   somewhere are interpolated, in ONE pass: the record is written where it will most likely live while
 //                   the per-step sum / counts that decide "wet" (:1244) are reduced; the rare dry candidate is squeezed out.
-// Bound: fp32 issue (N * steps * stations * ~7 instructions, no FMA: the reference has none), not HBM: the kernel writes
-// 4 B per wet cell-step and re-reads 4*ncoord B of weights per cell per RAIN_TCH steps.
+// Work: N * steps * stations * ~7 fp32 instructions (no FMA: the reference has none) against 4 B written per wet cell-step;
+// the time chunk is the fastest block index so that a tile's weights are read from DRAM once.
 #include "common.cuh"
 
 namespace {
@@ -51,8 +51,11 @@ struct RainP {
 
 template <int MODE>
 __global__ void __launch_bounds__(RAIN_THREADS) k_rain_field(const RainP P) {
-    const int cell = blockIdx.x * RAIN_THREADS + threadIdx.x;
-    const int t0 = blockIdx.y * RAIN_TCH;
+    // time chunk fastest: the blocks that share a tile of cells (and its weights) run next to each other, so the weights
+    // are read from DRAM once instead of once per time chunk
+    const int nchunks = P.Tp / RAIN_TCH;
+    const int cell = (int)(blockIdx.x / nchunks) * RAIN_THREADS + threadIdx.x;
+    const int t0 = (int)(blockIdx.x % nchunks) * RAIN_TCH;
     const int nt = min(RAIN_TCH, P.T - t0);
     const bool active = cell < P.N;
     float campo[RAIN_TCH];
@@ -65,18 +68,26 @@ __global__ void __launch_bounds__(RAIN_THREADS) k_rain_field(const RainP P) {
             for (int k = 0; k < RAIN_TCH; ++k) { Wr[k] = 0.0f; den[k] = 0.0f; }
             const float4 *rp = reinterpret_cast<const float4 *>(P.rainT + t0);
             const size_t row4 = (size_t)P.Tp / 4;
-            for (int i = 0; i < P.ncoord; ++i) {
-                const float w = P.W[(size_t)i * P.N + cell];
-                float r[RAIN_TCH];   // the same addresses for the whole warp: four 128-bit broadcast loads
+            constexpr int SU = 4;   // stations per trip: their weights are requested together, the sums stay in station order
+            for (int i0 = 0; i0 < P.ncoord; i0 += SU) {
+                float w[SU];
 #pragma unroll
-                for (int q = 0; q < RAIN_TCH / 4; ++q) {
-                    const float4 v = __ldg(rp + (size_t)i * row4 + q);
-                    r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
-                }
+                for (int u = 0; u < SU; ++u) w[u] = (i0 + u < P.ncoord) ? P.W[(size_t)(i0 + u) * P.N + cell] : 0.0f;
 #pragma unroll
-                for (int k = 0; k < RAIN_TCH; ++k) {   // padding steps hold -1: they add nothing
-                    if (r[k] > 0.0f) Wr[k] = Wr[k] + w * r[k];
-                    if (r[k] >= 0.0f) den[k] = den[k] + w;
+                for (int u = 0; u < SU; ++u) {
+                    if (i0 + u < P.ncoord) {
+                        float r[RAIN_TCH];   // the same addresses for the whole warp: four 128-bit broadcast loads
+#pragma unroll
+                        for (int q = 0; q < RAIN_TCH / 4; ++q) {
+                            const float4 v = __ldg(rp + (size_t)(i0 + u) * row4 + q);
+                            r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+                        }
+#pragma unroll
+                        for (int k = 0; k < RAIN_TCH; ++k) {   // padding steps hold -1: they add nothing
+                            if (r[k] > 0.0f) Wr[k] = Wr[k] + w[u] * r[k];
+                            if (r[k] >= 0.0f) den[k] = den[k] + w[u];
+                        }
+                    }
                 }
             }
 #pragma unroll
@@ -183,7 +194,9 @@ int rain_run(wmf_ctx *ctx, RainP P, Scope &sc, const float *rain_dev, float pp, 
         CU_TRY(ctx, cudaMemsetAsync(P.sum, 0, sizeof(double) * C, ctx->stream));
         CU_TRY(ctx, cudaMemsetAsync(P.n_umbral, 0, sizeof(int32_t) * 2 * C, ctx->stream));
         P.table = d_table;
-        const dim3 grid((unsigned)grid_for(N, RAIN_THREADS), (unsigned)(Tp / RAIN_TCH));
+        const long long nblocks = (long long)grid_for(N, RAIN_THREADS) * (Tp / RAIN_TCH);
+        if (nblocks > 0x7fffffffLL) WMF_FAIL(ctx, WMF_ERR_ARG, "rain interpolation: %lld blocks exceed the grid limit", nblocks);
+        const dim3 grid((unsigned)nblocks);
         LAUNCH(ctx, k_rain_field<MODE>, grid, RAIN_THREADS, 0, P);
         std::vector<double> h_sum((size_t)C);
         std::vector<int32_t> h_cnt((size_t)2 * C);
