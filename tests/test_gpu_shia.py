@@ -518,3 +518,27 @@ def test_channel_cell_draining_into_hillslope_cell():
     ref = run_oracle(inp)
     compare_core(ret, m, ref, bs["n"])
     assert ret[9][4, par] > inp["storage"][4, par]          # its channel tank did receive water
+
+
+def test_run_scenarios_concurrent_contexts(time_block):
+    """wmf_b200.ensemble.run_scenarios: storm scenarios on several contexts of one GPU give exactly the results of running
+    them one after the other."""
+    from wmf_b200 import ModelsModule, synth
+    from wmf_b200.ensemble import run_scenarios
+    bs, inp = build("G2", 90, 70, 33, n_reg=60, speed_type=(2, 1, 1))
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    rains = [np.ascontiguousarray(np.roll(inp["rain"], 7 * k, axis=1)) for k in range(5)]
+
+    def setup(m):
+        synth.apply_to_models(m, inp)
+
+    def run_one(m, rain):
+        m.set_rain(rain, inp["pos_evento"])
+        return m.shia_v1(None, None, inp["calib"], n_cont, 1, 60, None, None, bs["n"])[0].copy()
+
+    par = run_scenarios(setup, rains, run_one, concurrency=3)
+    m = ModelsModule()
+    setup(m)
+    for k, rain in enumerate(rains):
+        np.testing.assert_array_equal(par[k], run_one(m, rain))
+    assert not np.array_equal(par[0], par[1])
