@@ -143,6 +143,34 @@ def bench_path_a(cu, wl, reps=3):
             "path_a_levels": cu.basin_find_depth(), "path_a_workload": f"{wl['nc']}x{wl['nr']} G2 raster, find+cut+acum"}
 
 
+def bench_gauges_chain(cu, m, wl, n_cont, reps=2):
+    """Extra: the workflow that starts from rain gauges -- rain_idw on the GPU (record table stays in HBM) followed by the
+    SHIA run on it: what replaces rain_interpolate_idw + run_shia (wmf.py:3395-3420, 4337-4641) without any rain field
+    crossing PCIe."""
+    import torch
+    from wmf_b200 import synth
+    cx, cy = cu.basin_coordxy(wl["basin"])
+    xy = np.asfortranarray(np.vstack([cx, cy]), dtype=np.float32)
+    coord, rain = synth.make_stations(wl["nc"], wl["nr"], float(cu.dx), 46, wl["T"], 0)
+    inp, n = wl["inp"], wl["n"]
+    saved = object.__getattribute__(m, "__dict__")["_rain_mem"]
+    best_i = best_c = None
+    for _ in range(reps + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        m.rain_idw(xy, coord, rain, 2.0, 0, None, 0.0, None, resident=True)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        ret = m.shia_v1(None, None, inp["calib"], n_cont, 1, wl["T"], None, None, n)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        best_i = t1 - t0 if best_i is None else min(best_i, t1 - t0)
+        best_c = t2 - t0 if best_c is None else min(best_c, t2 - t0)
+    object.__getattribute__(m, "__dict__")["_rain_mem"] = saved
+    assert np.isfinite(ret[0]).all()
+    return {"rain_idw_ms": 1e3 * best_i, "rain_idw_stations": int(coord.shape[1]), "gauges_to_hydrograph_ms": 1e3 * best_c}
+
+
 def cpu_kind():
     """"reference" when the reference's own compiled Fortran is loadable (oracle/_ref/libwmf_ref.so, built from the
     objects in the reference tree and shipped to the GPU box), else "port" (the C restatement in oracle/)."""
@@ -155,8 +183,14 @@ def cpu_prepare(wl, sample_steps, workdir):
     written to the .bin / .hdr pair the Fortran reads record by record (modelosv2.f90:444-449), outside the timed call."""
     inp = dict(wl["inp"])
     inp["n_reg"] = sample_steps
-    inp["pos_evento"] = np.ascontiguousarray(inp["pos_evento"][:sample_steps])
+    pos = np.ascontiguousarray(inp["pos_evento"][:sample_steps])
     inp["evpserie"] = inp["evpserie"][:sample_steps]
+    # keep only the rain records the sample touches (record 1 = zeros stays first)
+    keep = np.unique(np.concatenate([[1], pos]))
+    remap = np.zeros(int(inp["rain"].shape[0]) + 1, np.int32)
+    remap[keep] = np.arange(1, keep.size + 1)
+    inp["rain"] = np.ascontiguousarray(inp["rain"][keep - 1])
+    inp["pos_evento"] = remap[pos]
     files = None
     if cpu_kind() == "reference":
         from oracle import ref
@@ -365,6 +399,7 @@ def run_ours(args):
         peak, peak_kind = peaks()
         achieved = BYTES_PER_CELL_STEP * cell_steps / (wave / 1e3) / 1e9
         extra = bench_path_a(cu, wl)
+        extra.update(bench_gauges_chain(cu, m, wl, n_cont))
         extra.update({"levels": n_levels, "waves_per_run": n_waves, "wave_kernel_ms_per_run": wave,
                       "setup_and_epilogue_ms_per_run": ms - wave})
         cpu_steps = max(2, min(T, args.cpu_sample_steps))
