@@ -80,6 +80,10 @@ class ShiaIn(C.Structure):
         ("sl_radslope", f32p),
         ("conv", i32p), ("stra", i32p), ("n_conv_records", C.c_int32), ("n_stra_records", C.c_int32),
         ("pos_conv", i32p), ("pos_stra", i32p),
+        ("sim_floods", C.c_int32), ("flood_sec_tam", C.c_int32),
+        ("flood_dw", C.c_float), ("flood_dsed", C.c_float), ("flood_av", C.c_float), ("flood_cmax", C.c_float),
+        ("flood_umbral", C.c_float), ("flood_step", C.c_float), ("flood_hmax", C.c_float),
+        ("flood_w", f32p), ("flood_d50", f32p), ("flood_slope", f32p), ("flood_sections", f32p), ("flood_sec_cells", f32p),
     ]
 
 
@@ -98,6 +102,8 @@ class ShiaOut(C.Structure):
         ("sl_riskvector", f32p), ("sl_slideocurrence", f32p),
         ("sl_slideacumulate", i32p), ("sl_slidencelltime", i32p),
         ("qsep_byrain", f32p), ("storage_conv", f32p), ("storage_stra", f32p),
+        ("flood_flood", i32p), ("flood_h", f32p), ("flood_ufr", f32p), ("flood_cr", f32p), ("flood_q", f32p),
+        ("flood_qsed", f32p), ("flood_speed", f32p), ("flood_profundidad", f32p), ("flood_scalars", f32p),
     ]
 
 
@@ -466,6 +472,17 @@ def shia_v1(inp: dict, fast: bool = False) -> dict:
             pk = np.ascontiguousarray(inp["pos_" + k], dtype=np.int32)
             assert pk.size >= T
             put("pos_" + k, pk, i32p)
+    floods = int(inp.get("sim_floods", 0)) == 1
+    if floods:                           # HydroFlash (modelosv2.f90:728-743, 1711-1822)
+        si.sim_floods = 1
+        for k in ("flood_dw", "flood_dsed", "flood_av", "flood_cmax", "flood_umbral", "flood_step", "flood_hmax"):
+            setattr(si, k, float(inp[k]))
+        for k in ("flood_w", "flood_d50", "flood_slope"):
+            put(k, _cellarr(inp[k], 1, N, np.float32), f32p)
+        sec = np.asfortranarray(inp["flood_sections"], dtype=np.float32)
+        si.flood_sec_tam = sec.shape[0]
+        put("flood_sections", np.ascontiguousarray(sec.ravel(order="F")), f32p)
+        put("flood_sec_cells", np.ascontiguousarray(np.asfortranarray(inp["flood_sec_cells"], dtype=np.float32).ravel(order="F")), f32p)
     sed = si.sim_sediments == 1
     sl = si.sim_slides == 1
     if sed:
@@ -516,6 +533,12 @@ def shia_v1(inp: dict, fast: bool = False) -> dict:
     out("mean_retorno64", (T,), np.float64, f64p)
     out("mean_vfluxes64", (4, T), np.float64, f64p)
     out("vfluxes_last", (4, N))
+    if floods:
+        out("flood_flood", (N,), np.int32, i32p)
+        for k in ("flood_h", "flood_ufr", "flood_cr", "flood_q", "flood_qsed", "flood_speed"):
+            out(k, (N,))
+        out("flood_profundidad", (si.flood_sec_tam, N))
+        out("flood_scalars", (3,))
     if si.separate_rain == 1:
         out("qsep_byrain", (n_cont, 2, T))
         out("storage_conv", (5, N))

@@ -464,6 +464,20 @@ def shia_v1(inp: dict, workdir: str | None = None, dumps: dict | None = None, ra
         for k, K in _SL_F.items():
             _set_alloc(MODELS, k, _cell2(inp[k], K, N, np.float32), np.float32)
 
+    floods = int(inp.get("sim_floods", 0)) == 1
+    _FLOOD_OUT = ("flood_q", "flood_qsed", "flood_speed", "flood_h", "flood_ufr", "flood_cr", "flood_eval", "flood_flood",
+                  "flood_loc_hand", "flood_slope", "flood_profundidad")
+    if floods:                           # HydroFlash: flood_allocate keeps whatever is allocated -> start from a fresh module
+        for k in _FLOOD_OUT:
+            _free_alloc(MODELS, k)
+        for k, mod in (("flood_dw", "flood_dw"), ("flood_dsed", "flood_dsed"), ("flood_av", "flood_av"), ("flood_cmax", "flood_cmax"),
+                       ("flood_umbral", "flood_umbral"), ("flood_step", "flood_step"), ("flood_hmax", "flood_hmax")):
+            _set_scalar(MODELS, mod, float(inp[k]), f32)
+        _set_scalar(MODELS, "flood_max_iter", int(inp.get("flood_max_iter", 10)), i32)
+        for k in ("flood_w", "flood_d50", "flood_slope"):
+            _set_alloc(MODELS, k, _cell2(inp[k], 1, N, np.float32), np.float32)
+        _set_alloc(MODELS, "flood_sections", np.asfortranarray(inp["flood_sections"], dtype=np.float32), np.float32)
+        _set_alloc(MODELS, "flood_sec_cells", np.asfortranarray(inp["flood_sec_cells"], dtype=np.float32), np.float32)
     tmp = None
     blank_path = ""
     if rain_files is not None:
@@ -516,6 +530,13 @@ def shia_v1(inp: dict, workdir: str | None = None, dumps: dict | None = None, ra
         v = _get_alloc(MODELS, k, rank, np.float32)
         if v is not None:
             res[k] = v.reshape(-1) if (rank == 2 and v.shape[0] == 1) else v
+    if floods:
+        res["flood_flood"] = _get_alloc(MODELS, "flood_flood", 2, np.int32).reshape(-1)
+        for k in ("flood_h", "flood_ufr", "flood_cr", "flood_q", "flood_qsed", "flood_speed"):
+            res[k] = _get_alloc(MODELS, k, 2, np.float32).reshape(-1)
+        res["flood_profundidad"] = _get_alloc(MODELS, "flood_profundidad", 2, np.float32)
+        res["flood_scalars"] = np.array([_get_scalar(MODELS, "flood_rdf", f32), _get_scalar(MODELS, "flood_area", f32),
+                                         _get_scalar(MODELS, "flood_diff", f32)], np.float32)
     if int(inp.get("separate_rain", 0)) == 1:
         res["storage_conv"] = _get_alloc(MODELS, "storage_conv", 2, np.float32)
         res["storage_stra"] = _get_alloc(MODELS, "storage_stra", 2, np.float32)

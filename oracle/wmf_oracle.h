@@ -116,6 +116,11 @@ typedef struct {
     const int32_t *conv, *stra;
     int32_t n_conv_records, n_stra_records;
     const int32_t *pos_conv, *pos_stra;
+    /* HydroFlash flood sub-model (modelosv2.f90:728-743, 1711-1822): module switches and maps */
+    int32_t sim_floods, flood_sec_tam;  /* flood_sec_tam = rows of flood_sections */
+    float flood_dw, flood_dsed, flood_av, flood_cmax, flood_umbral, flood_step, flood_hmax;
+    const float *flood_w, *flood_d50, *flood_slope;   /* (N) */
+    const float *flood_sections, *flood_sec_cells;    /* (flood_sec_tam, N): cross-section elevations and the cells they lie on */
 } wo_shia_in;
 
 typedef struct {
@@ -153,6 +158,10 @@ typedef struct {
     int32_t *sl_slidencelltime; /* (n_reg) */
     float *qsep_byrain;      /* (n_cont,2,n_reg) when separate_rain (:713-715, :767-769), may be NULL */
     float *storage_conv, *storage_stra; /* (5,N) final shadow storages (module Storage_conv / Storage_stra), may be NULL */
+    /* floods: module flood_flood (N) int, flood_h / ufr / Cr / Q / Qsed / speed (N), flood_profundidad (sec_tam,N),
+       flood_scalars = {flood_rdf, flood_area, flood_diff} after the last evaluation; all may be NULL */
+    int32_t *flood_flood;
+    float *flood_h, *flood_ufr, *flood_cr, *flood_q, *flood_qsed, *flood_speed, *flood_profundidad, *flood_scalars;
 } wo_shia_out;
 
 int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out);

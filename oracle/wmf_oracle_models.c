@@ -281,6 +281,55 @@ static double sum_d(const float *a, size_t n)
 /* MAX(x, 0.0) with the operands the other way round (rain_idw / rain_mit); NaN behaviour checked against oracle/_ref */
 #define WO_MAXX0(x) (((x) > 0.0f) ? (x) : 0.0f)
 
+/* HydroFlash: flood_params (modelosv2.f90:1730-1749) + flood_debris_flow2 (:1786-1822) for one channel cell at one step */
+static void flood_cell(const wo_shia_in *in, wo_shia_out *out, int32_t c, float Q, float speed, float *dif_buf)
+{
+    const int32_t S = in->flood_sec_tam, N = in->n_cel;
+    const float d50 = in->flood_d50[c], dw = in->flood_dw, dsed = in->flood_dsed, cmax = in->flood_cmax;
+    out->flood_q[c] = Q;
+    out->flood_speed[c] = speed;
+    float h = Q / (speed * in->flood_w[c]);
+    if (h > in->flood_hmax) h = in->flood_hmax;
+    out->flood_h[c] = h;
+    const float ufr = speed / (5.75f * logf(h / d50) + 6.25f);
+    out->flood_ufr[c] = ufr;
+    const float cr = cmax * powf(0.06f * h, 0.2f / ufr);
+    out->flood_cr[c] = cr;
+    const float rdf = (1.0f / d50) * powf((9.81f / 0.0128f) * (cr + (1.0f - cr) * (dw / dsed)), 0.5f) *
+                      (powf(cmax / cr, 1.0f / 3.0f) - 1.0f);
+    const float Qsed = Q * (1.0f + (cr / (1.0f - cr)));
+    out->flood_qsed[c] = Qsed;
+    /* flood_debris_flow2 */
+    float area = 0.0f, Qp = 0.0f, dif = 0.0f;
+    int32_t i = 1;
+    const float *sec = in->flood_sections + (size_t)S * c;
+    const float fondo = sec[S / 2];
+    for (int32_t k = 0; k < S; ++k) dif_buf[k] = 0.0f; /* `diferencias` is uninitialised when the loop never runs: zeros */
+    while (Qp < Qsed && (float)i * in->flood_step < 50.0f) {
+        dif = (float)i * in->flood_step;
+        const float linea = fondo + dif;
+        float sum = 0.0f;
+        for (int32_t k = 0; k < S; ++k) {
+            dif_buf[k] = linea - sec[k];
+            if (dif_buf[k] > 0.0f) sum += dif_buf[k];
+        }
+        area = sum * in->dxp;
+        Qp = ((2.0f / 5.0f) * rdf * powf((float)i * in->flood_step, 3.0f / 2.0f) * in->flood_slope[c] * (1.0f / 2.0f)) * area;
+        i = i + 1;
+    }
+    if (out->flood_profundidad) memcpy(out->flood_profundidad + (size_t)S * c, dif_buf, sizeof(float) * (size_t)S);
+    const float *cells = in->flood_sec_cells + (size_t)S * c;
+    for (int32_t k = 0; k < S; ++k)
+        if (dif_buf[k] > 0.0f) {
+            const int32_t pos = (int32_t)cells[k];
+            if (pos >= 1 && pos <= N) out->flood_flood[pos - 1] = 1;
+        }
+    out->flood_flood[c] = 2;
+    /* flood_debris_flow2 never assigns its first output `areas` (it computes the local `area`): flood_area keeps its value */
+    (void)area;
+    if (out->flood_scalars) { out->flood_scalars[0] = rdf; out->flood_scalars[2] = dif; }
+}
+
 /* modelosv2.f90:191-869 */
 int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
 {
@@ -305,6 +354,16 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
     int32_t *Stra = sepr ? (int32_t *)calloc((size_t)N, sizeof(int32_t)) : NULL;
     float hflux_c[4] = {0, 0, 0, 0}, hflux_s[4] = {0, 0, 0, 0};
     if (sepr && out->qsep_byrain) memset(out->qsep_byrain, 0, sizeof(float) * 2 * (size_t)NC * T);
+    float *flood_dif = NULL;
+    if (in->sim_floods == 1) { /* flood_allocate :1711-1729: flood_eval = flood_flood = 0; the other maps start at zero here */
+        flood_dif = (float *)calloc((size_t)(in->flood_sec_tam > 0 ? in->flood_sec_tam : 1), sizeof(float));
+        for (int32_t i = 0; i < N; ++i) {
+            out->flood_flood[i] = 0;
+            out->flood_h[i] = out->flood_ufr[i] = out->flood_cr[i] = out->flood_q[i] = out->flood_qsed[i] = out->flood_speed[i] = 0.0f;
+        }
+        if (out->flood_profundidad) memset(out->flood_profundidad, 0, sizeof(float) * (size_t)in->flood_sec_tam * N);
+        if (out->flood_scalars) out->flood_scalars[0] = out->flood_scalars[1] = out->flood_scalars[2] = 0.0f;
+    }
     sed_state SS;
     memset(&SS, 0, sizeof SS);
     SS.in = in;
@@ -573,6 +632,9 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
             }
             /* slides :723 */
             if (in->sim_slides == 1) slide_ocurrence(in, out, t, c, A5(Sto, 2, c), A3(H, 1, c));
+            /* floods :728-743 -- channel cells of type 3 flowing faster than the threshold */
+            if (in->sim_floods == 1 && ut == 3 && A4(hspeed, 3, c) * in->flood_av > in->flood_umbral)
+                flood_cell(in, out, c, hflux[3] * m3_mm[c] / dt, A4(hspeed, 3, c) * in->flood_av, flood_dif);
             /* records :749-787 */
             if (in->control[c] != 0) {
                 if (control_cont <= NC) {
@@ -677,6 +739,7 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
         if (out->storage_conv) memcpy(out->storage_conv, Sc, sizeof(float) * 5 * (size_t)N);
         if (out->storage_stra) memcpy(out->storage_stra, Ss, sizeof(float) * 5 * (size_t)N);
     }
+    free(flood_dif);
     free(Sc);
     free(Ss);
     free(Conv);

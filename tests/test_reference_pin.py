@@ -338,3 +338,22 @@ def test_stream_find_to_corr_oracle_is_bit_identical_to_the_reference(ref):
         c, f = int(rng.integers(2, 119)), int(rng.integers(2, 89))
         x, y = 30.0 * (c - 0.5), 30.0 * (90 - f + 0.5)
         assert rc.stream_find_to_corr(x, y, bs["DEM"], bs["DIR"], cauce) == oc.stream_find_to_corr(x, y, bs["DEM"], bs["DIR"], cauce)
+
+
+@pytest.mark.parametrize("seed,kw", [(12, dict(rain_peak_mm=60.0)), (13, dict(rain_peak_mm=90.0, speed_type=(2, 1, 1)))])
+def test_hydroflash_oracle_is_bit_identical_to_the_reference(ref, seed, kw):
+    """sim_floods = 1 (modelosv2.f90:728-743, flood_params :1730-1749, flood_debris_flow2 :1786-1822): the flooded-cell map,
+    the hydraulic maps of the evaluated channel cells, the flooded cross sections and flood_rdf / flood_diff of the last
+    evaluation (flood_area is never assigned by the Fortran)."""
+    import oracle
+    from wmf_b200 import synth
+    bs = make_basin("G2", 90, 70, seed)
+    v = basin_vectors(bs)
+    inp = synth.make_shia_inputs(bs["basin"], v["acum"], v["lng"], v["pend"], dxp=30.0, n_reg=60, seed=seed, thresholds=(20, 150), **kw)
+    inp.update(synth.make_flood_inputs(inp, v["elev"], v["pend"], 4, seed))
+    R, O = ref.shia_v1(inp), oracle.shia_v1(inp)
+    for k in CORE + ("flood_flood", "flood_h", "flood_ufr", "flood_cr", "flood_q", "flood_qsed", "flood_speed", "flood_profundidad",
+                     "flood_scalars"):
+        same(R[k], O[k], "floods: " + k)
+    counts = np.bincount(O["flood_flood"], minlength=3)
+    assert counts[1] > 100 and counts[2] > 100 and np.isfinite(O["flood_profundidad"]).all()

@@ -297,6 +297,26 @@ def make_stations(nc: int, nr: int, dx: float, n_stations: int = 12, n_reg: int 
     return np.asfortranarray(coord, dtype=np.float32), np.asfortranarray(rain, dtype=np.float32)
 
 
+def make_flood_inputs(inp: dict, elev, slope, half_width: int = 4, seed: int = 0) -> dict:
+    """HydroFlash inputs (wmf.py:3768-3805, modelosv2.f90:1711-1822): channel width, d50, slope, and for every cell a cross
+    section of ``2*half_width+1`` elevations (valley shape around the cell's own elevation) with the cells it lies on.
+    The velocity factor / threshold are chosen so that a good share of the type-3 cells are evaluated."""
+    N = int(inp["nceldas"])
+    rng = np.random.default_rng(seed + 77)
+    S = 2 * half_width + 1
+    k = np.abs(np.arange(S) - half_width)[:, None].astype(np.float32)
+    rise = rng.uniform(0.2, 1.5, (1, N)).astype(np.float32)
+    sections = (np.asarray(elev, np.float32).reshape(1, N) + k * rise * rng.uniform(0.6, 1.4, (S, N)).astype(np.float32))
+    offs = (np.arange(S) - half_width)[:, None] * rng.integers(1, 40, (1, N))
+    cells = np.clip(np.arange(1, N + 1)[None, :] + offs, 1, N).astype(np.float32)
+    return {"sim_floods": 1, "flood_dw": 1000.0, "flood_dsed": 2600.0, "flood_av": 100.0, "flood_cmax": 0.75,
+            "flood_umbral": 0.7, "flood_step": 0.25, "flood_hmax": 5.0, "flood_max_iter": 10,
+            "flood_w": rng.uniform(2.0, 10.0, (1, N)).astype(np.float32), "flood_d50": rng.uniform(0.01, 0.1, (1, N)).astype(np.float32),
+            "flood_slope": np.sin(np.arctan(np.maximum(np.asarray(slope, np.float32), 1e-3))).reshape(1, N).astype(np.float32),
+            "flood_sections": np.asfortranarray(sections, dtype=np.float32),
+            "flood_sec_cells": np.asfortranarray(cells, dtype=np.float32)}
+
+
 def make_ensemble_calibs(n_members: int, seed: int = 0) -> np.ndarray:
     """(M,11) calibration sets sampled uniformly in the Barbosa NSGA-II notebook ranges
     (Examples/Calibracion_Barbosa_NSGAII.ipynb cell 9), extended to the 11 entries shia_v1 needs."""
