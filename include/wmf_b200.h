@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define WMF_ABI_VERSION 9
+#define WMF_ABI_VERSION 10
 
 enum {
     WMF_OK = 0,
@@ -179,6 +179,10 @@ typedef struct {
     int32_t save_vfluxes, save_rc;
     /* module separate_rain (modelosv2.f90:91): convective / stratiform shadow storages and Qsep_byrain */
     int32_t separate_rain;
+    /* HydroFlash flood sub-model (modelosv2.f90:79, :160-183, :728-743, :1711-1822): module sim_floods and flood_* scalars;
+     * flood_sec_tam = rows of flood_sections */
+    int32_t sim_floods, flood_sec_tam;
+    float flood_dw, flood_dsed, flood_av, flood_cmax, flood_umbral, flood_step, flood_hmax;
 } wmf_shia_cfg;
 
 /* Arrays = module `models` allocatables (modelosv2.f90:53-113) in their f2py layouts. */
@@ -217,6 +221,8 @@ typedef struct {
     const int32_t *conv, *stra;
     int32_t n_conv_records, n_stra_records;
     const int32_t *pos_conv, *pos_stra;
+    /* sim_floods = 1: module flood_w, flood_d50, flood_slope (N); flood_sections, flood_sec_cells (flood_sec_tam, N) */
+    const float *flood_w, *flood_d50, *flood_slope, *flood_sections, *flood_sec_cells;
 } wmf_shia_inputs;
 
 /* Outputs.  Any pointer may be NULL (= not wanted).  Shapes as returned by f2py (modelsmodule.c:375-408).
@@ -260,6 +266,11 @@ typedef struct {
     /* separate_rain = 1: Qsep_byrain (n_cont, 2, n_reg) (modelosv2.f90:713-716, :767-770) and the final shadow storages,
      * module Storage_conv / Storage_stra (5,N) */
     float *qsep_byrain, *storage_conv, *storage_stra;
+    /* sim_floods = 1: module flood_flood (N) int32 (0 dry, 1 flooded by a section, 2 evaluated channel cell), the maps of
+     * the evaluated cells' last evaluation flood_h / ufr / Cr / Q / Qsed / speed (N), flood_profundidad (flood_sec_tam, N)
+     * and flood_scalars[3] = {flood_rdf, flood_area (never assigned by the Fortran: 0), flood_diff} of the last evaluation */
+    int32_t *flood_flood;
+    float *flood_h, *flood_ufr, *flood_cr, *flood_q, *flood_qsed, *flood_speed, *flood_profundidad, *flood_scalars;
 } wmf_shia_outputs;
 
 /* shia_v1, modelosv2.f90:191-869 (+ calc_speed :1278-1293, sed_* :1298-1608, slide_* :1613-1707). */

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.load()
     for s in declared:
         assert hasattr(L, s), s
-    assert L.wmf_abi_version() == 9
+    assert L.wmf_abi_version() == 10
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -72,11 +72,6 @@ def test_unsupported_switches_fail_loudly():
     from wmf_b200 import ModelsModule
     m = ModelsModule()
     m.drena = np.zeros((3, 2), np.int32)
-    for flag in ("sim_floods",):
-        setattr(m, flag, 1)
-        with pytest.raises(NotImplementedError):
-            m.shia_v1(None, None, np.ones(11), 1, 1, 1)
-        setattr(m, flag, 0)
     with pytest.raises(ValueError):
         m.shia_v1("x.bin", "x.hdr", np.ones(10), 1, 1, 1)      # calib(11) required (modelosv2.f90:201)
 

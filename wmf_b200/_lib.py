@@ -43,6 +43,9 @@ class ShiaCfg(C.Structure):
         ("n_members", C.c_int32),
         ("save_storage", C.c_int32), ("save_speed", C.c_int32), ("separate_fluxes", C.c_int32),
         ("save_vfluxes", C.c_int32), ("save_rc", C.c_int32), ("separate_rain", C.c_int32),
+        ("sim_floods", C.c_int32), ("flood_sec_tam", C.c_int32),
+        ("flood_dw", C.c_float), ("flood_dsed", C.c_float), ("flood_av", C.c_float), ("flood_cmax", C.c_float),
+        ("flood_umbral", C.c_float), ("flood_step", C.c_float), ("flood_hmax", C.c_float),
     ]
 
 
@@ -64,6 +67,8 @@ class ShiaInputs(C.Structure):
         ("guarda_cond", C.c_void_p), ("guarda_vfluxes", C.c_void_p),
         ("conv", C.c_void_p), ("stra", C.c_void_p), ("n_conv_records", C.c_int32), ("n_stra_records", C.c_int32),
         ("pos_conv", C.c_void_p), ("pos_stra", C.c_void_p),
+        ("flood_w", C.c_void_p), ("flood_d50", C.c_void_p), ("flood_slope", C.c_void_p), ("flood_sections", C.c_void_p),
+        ("flood_sec_cells", C.c_void_p),
     ]
 
 
@@ -74,6 +79,7 @@ _OUT_NAMES = [
     "sl_zmin", "sl_zcrit", "sl_zmax", "sl_bo", "sl_riskvector", "sl_slideocurrence",
     "sl_slideacumulate", "sl_slidencelltime", "sto_snap", "speed_snap", "qseparated",
     "mean_vfluxes", "vfl_snap", "rc_coef", "ret_snap", "qsep_byrain", "storage_conv", "storage_stra",
+    "flood_flood", "flood_h", "flood_ufr", "flood_cr", "flood_q", "flood_qsed", "flood_speed", "flood_profundidad", "flood_scalars",
 ]
 
 

@@ -36,17 +36,20 @@ _ARRAYS = {
     "vd": (np.float32, 3), "vs": (np.float32, 3), "vsc": (np.float32, 3), "vdc": (np.float32, 3),
     "sl_zs": (np.float32, 1), "sl_gammas": (np.float32, 1), "sl_cohesion": (np.float32, 1),
     "sl_frictionangle": (np.float32, 1), "sl_radslope": (np.float32, 1),
+    "flood_w": (np.float32, 1), "flood_d50": (np.float32, 1), "flood_slope": (np.float32, 1),
+    "flood_sections": (np.float32, -1), "flood_sec_cells": (np.float32, -1),      # (flood_sec_tam, N)
     "speed_type": (np.int32, 0), "wi": (np.float32, 0), "diametro": (np.float32, 0),
 }
-_SCALARS_F = {"dt": 60.0, "dxp": 1.0, "retorno_gr": 0.0, "retorno_aq": 0.0, "storage_constant": 0.0,
+_SCALARS_F = {"flood_rdf": 0.0, "flood_area": 0.0, "flood_diff": 0.0, "flood_dw": 1000.0, "flood_dsed": 2600.0, "flood_av": 1.0 / 200.0, "flood_cmax": 0.75, "flood_umbral": 3.0,
+              "flood_step": 1.0, "flood_hmax": 5.0, "dt": 60.0, "dxp": 1.0, "retorno_gr": 0.0, "retorno_aq": 0.0, "storage_constant": 0.0,
               "sed_factor": 1.0, "sl_fs": 1.0, "sl_gammaw": 9.8, "xll": 0.0, "yll": 0.0, "nodata": -9999.0, "dx": 1.0}
-_SCALARS_I = {"nceldas": 0, "ncols": 0, "nrows": 0, "verbose": 0, "rain_first_point": 1, "calc_niter": 5,
+_SCALARS_I = {"flood_max_iter": 10, "nceldas": 0, "ncols": 0, "nrows": 0, "verbose": 0, "rain_first_point": 1, "calc_niter": 5,
               "sim_sediments": 0, "sim_slides": 0, "sim_floods": 0, "save_storage": 0, "save_speed": 0,
               "save_retorno": 0, "save_vfluxes": 0, "save_rc": 0, "show_storage": 0, "show_speed": 0,
               "show_mean_speed": 0, "show_mean_retorno": 0, "show_area": 0, "separate_fluxes": 0,
               "separate_rain": 0, "sl_gullienogullie": 0}
 # switches whose sub-models are outside the hot path built here
-_UNSUPPORTED = ("sim_floods",)
+_UNSUPPORTED = ()
 
 
 def read_rain_hdr(ruta_hdr: str, n_reg: int, rain_first_point: int = 1):
@@ -480,6 +483,7 @@ class ModelsModule:
         if M != 1:
             cfg.save_retorno = 0
         cfg.separate_rain = 1 if (rain_types is not None and M == 1) else 0
+        cfg.sim_floods = int(self.sim_floods) if M == 1 else 0
         keep = []
         si = ShiaInputs()
 
@@ -545,6 +549,17 @@ class ModelsModule:
                     raise ValueError(f"{nm} table must be (n_records,{N})")
             put("conv", conv); put("stra", stra); put("pos_conv", pc); put("pos_stra", ps)
             si.n_conv_records, si.n_stra_records = int(conv.shape[0]), int(stra.shape[0])
+        if cfg.sim_floods == 1:              # HydroFlash (modelosv2.f90:728-743, 1711-1822)
+            for k in ("flood_dw", "flood_dsed", "flood_av", "flood_cmax", "flood_umbral", "flood_step", "flood_hmax"):
+                setattr(cfg, k, float(getattr(self, k)))
+            for k in ("flood_w", "flood_d50", "flood_slope"):
+                put(k, self._cell(k, 1, N, np.float32))
+            sec = a.get("flood_sections")
+            if sec is None or sec.ndim != 2 or sec.shape[1] != N:
+                raise ValueError(f"models.flood_sections must be (flood_sec_tam,{N})")
+            cfg.flood_sec_tam = int(sec.shape[0])
+            put("flood_sections", sec)
+            put("flood_sec_cells", self._cell("flood_sec_cells", sec.shape[0], N, np.float32))
         n_vsnap = 0
         if cfg.save_vfluxes == 1:
             g = self._guarda("guarda_vfluxes", T)
@@ -584,6 +599,11 @@ class ModelsModule:
                 out("qseparated", (n_cont, 3, T))
             if cfg.separate_rain == 1:
                 out("qsep_byrain", (n_cont, 2, T)); out("storage_conv", (5, N)); out("storage_stra", (5, N))
+            if cfg.sim_floods == 1:
+                out("flood_flood", (1, N), np.int32)
+                for k in ("flood_h", "flood_ufr", "flood_cr", "flood_q", "flood_qsed", "flood_speed"):
+                    out(k, (1, N))
+                out("flood_profundidad", (cfg.flood_sec_tam, N)); out("flood_scalars", (3,))
             if cfg.save_storage == 1:
                 out("sto_snap", (5, N, max(n_snap, 1)))
             if cfg.save_speed == 1:
@@ -623,7 +643,8 @@ class ModelsModule:
         if M == 1 and not device_out:
             d = object.__getattribute__(self, "__dict__")
             for k in ("mean_rain", "acum_rain", "mean_storage", "mean_speed", "mean_retorno", "mean_vfluxes", "rc_coef",
-                      "storage_conv", "storage_stra",
+                      "storage_conv", "storage_stra", "flood_flood", "flood_h", "flood_ufr", "flood_cr", "flood_q", "flood_qsed",
+                      "flood_speed", "flood_profundidad",
                       "retorned", "vs", "vd",
                       "vsc", "vdc", "volero", "voldepo", "sl_zmin", "sl_zcrit", "sl_zmax", "sl_bo", "sl_riskvector",
                       "sl_slideocurrence", "sl_slideacumulate", "sl_slidencelltime"):
@@ -634,4 +655,6 @@ class ModelsModule:
                         d[k] = res[k]
             if "erot" in res:
                 d["erot"], d["dept"] = res["erot"], res["dept"]
+            if "flood_scalars" in res:
+                d["_s"]["flood_rdf"], d["_s"]["flood_diff"] = float(res["flood_scalars"][0]), float(res["flood_scalars"][2])
         return res

@@ -110,6 +110,15 @@ struct ShiaP {
     const int32_t *conv, *stra;   // rain-type tables, record r at (r-1)*N
     const int32_t *effc, *effs;   // [T] record in force at step t (the last one read on a wet step), 0 = none yet
     float *qsepr;                 // Qsep_byrain (n_cont, 2, n_reg)
+    // HydroFlash flood sub-model (:728-743, :1711-1822)
+    float fl_dw, fl_dsed, fl_av, fl_cmax, fl_umbral, fl_step, fl_hmax;
+    int fl_S;                                   // rows of flood_sections
+    const float *fl_w, *fl_d50, *fl_slope;      // [N]
+    const float *fl_sections, *fl_cells;        // [N][S] (f2py (S,N))
+    float *fl_out;                              // [8][N]: h, ufr, Cr, Q, Qsed, speed, rdf, dif of the cell's last evaluation
+    int32_t *fl_last;                           // [N] step of the cell's last evaluation, -1 = never
+    float *fl_prof;                             // [N][S] flood_profundidad
+    unsigned long long *fl_key;                 // [N] ((step * N + writer cell) << 2 | value): the last writer of flood_flood wins
     // separate_fluxes (:658-680, :697-704, :752-759): shares of runoff / subsurface / base flow in the channel tank
     float *flx;             // [3][N][M]
     float4 *flxout4;        // [2][K][N][M] (share sent downstream x3, flag: 1 add, 0 "receiver's shares := 0", 2 hillslope cell)
@@ -740,7 +749,62 @@ constexpr int TB_THREADS = TB_THREADS_N;
 #define TB_MIN_BLOCKS_SED 2
 #endif
 
-template <int K, bool CHAN, bool KIN, bool SED, bool SLIDES, bool SNAP, bool SEPF, bool SEPR>
+// x**y and log(x) as the reference's libm evaluates them in fp32 (glibc: correctly rounded in all but a vanishing share of
+// cases): double precision, rounded once.  The flood loop compares against them, so a last-bit difference would change counts.
+__device__ __forceinline__ float powf_cr(float x, float y) { return (float)pow((double)x, (double)y); }
+__device__ __forceinline__ float logf_cr(float x) { return (float)log((double)x); }
+
+// flood_params (:1730-1749) + flood_debris_flow2 (:1786-1822) for one type-3 channel cell at one step
+__device__ __noinline__ void flood_dev(const ShiaP &P, int cell, int t, float Q, float speed) {
+    const int N = P.N, S = P.fl_S;
+    const float d50 = __ldg(P.fl_d50 + cell), cmax = P.fl_cmax;
+    float h = Q / (speed * __ldg(P.fl_w + cell));
+    if (h > P.fl_hmax) h = P.fl_hmax;
+    const float ufr = speed / (5.75f * logf_cr(h / d50) + 6.25f);
+    const float cr = cmax * powf_cr(0.06f * h, 0.2f / ufr);
+    const float rdf = (1.0f / d50) * powf_cr((9.81f / 0.0128f) * (cr + (1.0f - cr) * (P.fl_dw / P.fl_dsed)), 0.5f) *
+                      (powf_cr(cmax / cr, 1.0f / 3.0f) - 1.0f);
+    const float Qsed = Q * (1.0f + (cr / (1.0f - cr)));
+    const float *sec = P.fl_sections + (size_t)S * cell;
+    const float fondo = sec[S / 2];
+    const float slope = __ldg(P.fl_slope + cell);
+    float Qp = 0.0f, dif = 0.0f, linea = 0.0f;
+    int i = 1;
+    bool ran = false;
+    while (Qp < Qsed && (float)i * P.fl_step < 50.0f) {
+        dif = (float)i * P.fl_step;
+        linea = fondo + dif;
+        float sum = 0.0f;
+        for (int k = 0; k < S; ++k) {
+            const float d = linea - sec[k];
+            if (d > 0.0f) sum = sum + d;
+        }
+        const float area = sum * P.dxp;
+        Qp = ((2.0f / 5.0f) * rdf * powf_cr((float)i * P.fl_step, 3.0f / 2.0f) * slope * (1.0f / 2.0f)) * area;
+        i = i + 1;
+        ran = true;
+    }
+    // flood_profundidad(:,celda) = diferencias of the last trip (zeros when the loop never ran); the flooded cells of the
+    // section get 1, the channel cell itself 2; later (step, cell) events overwrite earlier ones
+    const unsigned long long ev = ((unsigned long long)t * (unsigned long long)N + (unsigned long long)cell) << 2;
+    float *prof = P.fl_prof + (size_t)S * cell;
+    const float *cells = P.fl_cells + (size_t)S * cell;
+    for (int k = 0; k < S; ++k) {
+        const float d = ran ? linea - sec[k] : 0.0f;
+        prof[k] = d;
+        if (d > 0.0f) {
+            const int pos = (int)cells[k];
+            if (pos >= 1 && pos <= N) atomicMax(P.fl_key + (pos - 1), ev | 1ull);
+        }
+    }
+    atomicMax(P.fl_key + cell, ev | 2ull);
+    float *o = P.fl_out;
+    o[cell] = h; o[(size_t)N + cell] = ufr; o[2 * (size_t)N + cell] = cr; o[3 * (size_t)N + cell] = Q;
+    o[4 * (size_t)N + cell] = Qsed; o[5 * (size_t)N + cell] = speed; o[6 * (size_t)N + cell] = rdf; o[7 * (size_t)N + cell] = dif;
+    P.fl_last[cell] = t;
+}
+
+template <int K, bool CHAN, bool KIN, bool SED, bool SLIDES, bool SNAP, bool SEPF, bool SEPR, bool FLOOD>
 __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int jlo, const int jhi, const int tile,
                                         float *__restrict__ s_acc) {
     const int N = P.N, M = P.M;
@@ -1065,6 +1129,8 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                 }
                 const float sec_area = calc_speed_dev(S4 * m3, ccoef, cexpo, Ls, vch, dt, P.niter);
                 const float h3 = fminf(sec_area * vch * dt / m3, S4);
+                if (FLOOD && type == 3 && vch * P.fl_av > P.fl_umbral)   // :728-743 (reads only this step's outflow and speed)
+                    flood_dev(P, cell, t, h3 * m3 / dt, vch * P.fl_av);
                 if (SEPR) {  // :645-655 (the channel tank before the outflow leaves), :683-686, :713-716, :767-770
                     float c3 = 0.0f, s3 = 0.0f;
                     if (S4 != 0.0f) { c3 = h3 * C4 / S4; s3 = h3 * T4 / S4; }
@@ -1294,7 +1360,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
 
 // Every CTA carries the same mix of roles: its first `cpb` warps take 32-thread tiles of the channel list, the
 // others tiles of the hillslope list, so the SMs stay balanced although a channel thread costs ~4x a hillslope one.
-template <int K, bool KIN, bool SED, bool SLIDES, bool SNAP, bool SEPF, bool SEPR>
+template <int K, bool KIN, bool SED, bool SLIDES, bool SNAP, bool SEPF, bool SEPR, bool FLOOD>
 __global__ void __launch_bounds__(TB_THREADS, (SED || SEPR) ? TB_MIN_BLOCKS_SED : (KIN ? TB_MIN_BLOCKS_KIN : TB_MIN_BLOCKS))
 k_shia_tb(const __grid_constant__ ShiaP P, const int w, const int clo, const int chi, const int hlo, const int hhi,
           const int cpb, const int n_ctiles, const int n_htiles) {
@@ -1302,10 +1368,10 @@ k_shia_tb(const __grid_constant__ ShiaP P, const int w, const int clo, const int
     const int wi = threadIdx.x >> 5;
     if (wi < cpb) {
         const int tile = (int)blockIdx.x * cpb + wi;
-        if (tile < n_ctiles) tb_role<K, true, KIN, SED, SLIDES, SNAP, SEPF, SEPR>(P, w, clo, chi, tile, s_acc);
+        if (tile < n_ctiles) tb_role<K, true, KIN, SED, SLIDES, SNAP, SEPF, SEPR, FLOOD>(P, w, clo, chi, tile, s_acc);
     } else {
         const int tile = (int)blockIdx.x * (TB_THREADS / 32 - cpb) + (wi - cpb);
-        if (tile < n_htiles) tb_role<K, false, KIN, SED, SLIDES, SNAP, SEPF, SEPR>(P, w, hlo, hhi, tile, s_acc);
+        if (tile < n_htiles) tb_role<K, false, KIN, SED, SLIDES, SNAP, SEPF, SEPR, FLOOD>(P, w, hlo, hhi, tile, s_acc);
     }
 }
 
@@ -1555,6 +1621,25 @@ __global__ void k_shia_epilogue(const double *__restrict__ red, const double *__
     if (mean_retorno) mean_retorno[t] = (float)(q(t, RQ_RET) / (double)n);
     if (mean_vfluxes)
         for (int k = 0; k < 4; ++k) mean_vfluxes[4 * (size_t)t + k] = (float)(q(t, RQ_VFL1 + k) / (double)n);
+}
+
+// floods epilogue: flood_flood from the last-writer keys; the cell of the very last evaluation (largest (step, cell))
+__global__ void k_flood_final(const unsigned long long *__restrict__ key, const int32_t *__restrict__ last, int N,
+                              int32_t *__restrict__ flood, unsigned long long *__restrict__ best) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    if (flood) flood[i] = (int32_t)(key[i] & 3ull);
+    if (last[i] >= 0) atomicMax(best, ((unsigned long long)last[i] << 32) | (unsigned)i);
+}
+__global__ void k_flood_scalars(const unsigned long long *__restrict__ best, const float *__restrict__ o, const int32_t *__restrict__ last,
+                                int N, float *__restrict__ sc) {
+    if (threadIdx.x || blockIdx.x) return;
+    sc[0] = sc[1] = sc[2] = 0.0f;
+    const int c = (int)(*best & 0xffffffffull);
+    if (last[c] >= 0) {                    // best == 0 is also what "no evaluation at all" leaves behind
+        sc[0] = o[6 * (size_t)N + c];      // flood_rdf
+        sc[2] = o[7 * (size_t)N + c];      // flood_diff (flood_area is never assigned by the Fortran)
+    }
 }
 
 // Storage_conv / Storage_stra: SoA [5][N] state -> the (5,N) f2py layout
@@ -1851,7 +1936,7 @@ static void launch_wave(wmf_ctx *ctx, const ShiaP &P, int w, int lo, int hi) {
     ctx->launches++;
 }
 
-template <int K, bool SED = false, bool SLIDES = false, bool SNAP = false, bool SEPF = false, bool SEPR = false>
+template <int K, bool SED = false, bool SLIDES = false, bool SNAP = false, bool SEPF = false, bool SEPR = false, bool FLOOD = false>
 static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int hlo, int hhi, bool pdl) {
     constexpr int WPB = TB_THREADS / 32;
     const int wc = (int)(((long long)(chi - clo) * P.M + 31) / 32), wh = (int)(((long long)(hhi - hlo) * P.M + 31) / 32);
@@ -1877,8 +1962,8 @@ static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     const bool kin = P.st[0] == 2 || P.st[1] == 2 || P.st[2] == 2;
-    if (kin) cudaLaunchKernelEx(&cfg, k_shia_tb<K, true, SED, SLIDES, SNAP, SEPF, SEPR>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
-    else cudaLaunchKernelEx(&cfg, k_shia_tb<K, false, SED, SLIDES, SNAP, SEPF, SEPR>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
+    if (kin) cudaLaunchKernelEx(&cfg, k_shia_tb<K, true, SED, SLIDES, SNAP, SEPF, SEPR, FLOOD>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
+    else cudaLaunchKernelEx(&cfg, k_shia_tb<K, false, SED, SLIDES, SNAP, SEPF, SEPR, FLOOD>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
     ctx->launches++;
 }
 
@@ -2103,6 +2188,14 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     if (KT && (sed || slides || snap)) KT = (T >= 4) ? 4 : 0;  // sediment / slide / dump variants are built for K = 4 only
     const bool sepf = cfg->separate_fluxes == 1;
     const bool sepr = cfg->separate_rain == 1;
+    const bool floods = cfg->sim_floods == 1;
+    if (floods) {
+        if (sed || slides || snap || !tb_ok || M != 1 || sepf || sepr)
+            WMF_FAIL(ctx, WMF_ERR_ARG, "shia: sim_floods cannot be combined with sediments, slides, state dumps, show_* means, separate_* or ensembles");
+        if (!in->flood_w || !in->flood_d50 || !in->flood_slope || !in->flood_sections || !in->flood_sec_cells || cfg->flood_sec_tam < 1)
+            WMF_FAIL(ctx, WMF_ERR_ARG, "shia: sim_floods = 1 needs flood_w, flood_d50, flood_slope, flood_sections, flood_sec_cells");
+        KT = (T >= 4) ? 4 : 1;
+    }
     if (sepf || sepr) {
         if (sed || slides || snap || !tb_ok || M != 1 || (sepf && sepr))
             WMF_FAIL(ctx, WMF_ERR_ARG, "shia: separate_fluxes / separate_rain cannot be combined with each other, sediments, slides, state dumps, show_* means or ensembles");
@@ -2179,6 +2272,23 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
             CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // `eff` goes out of scope
             P.effc = d_eff;
             P.effs = d_eff + T;
+        }
+        if (floods) {
+            const int S = cfg->flood_sec_tam;
+            P.fl_dw = cfg->flood_dw; P.fl_dsed = cfg->flood_dsed; P.fl_av = cfg->flood_av; P.fl_cmax = cfg->flood_cmax;
+            P.fl_umbral = cfg->flood_umbral; P.fl_step = cfg->flood_step; P.fl_hmax = cfg->flood_hmax; P.fl_S = S;
+            WMF_TRY(sc.in(in->flood_w, (size_t)N, &P.fl_w)); WMF_TRY(sc.in(in->flood_d50, (size_t)N, &P.fl_d50));
+            WMF_TRY(sc.in(in->flood_slope, (size_t)N, &P.fl_slope));
+            WMF_TRY(sc.in(in->flood_sections, (size_t)S * N, &P.fl_sections));
+            WMF_TRY(sc.in(in->flood_sec_cells, (size_t)S * N, &P.fl_cells));
+            WMF_TRY(sc.alloc(&P.fl_out, (size_t)8 * N)); WMF_TRY(sc.alloc(&P.fl_last, (size_t)N));
+            WMF_TRY(sc.alloc(&P.fl_key, (size_t)N));
+            WMF_TRY(sc.out(out->flood_profundidad, (size_t)S * N, &P.fl_prof));
+            if (!P.fl_prof) WMF_TRY(sc.alloc(&P.fl_prof, (size_t)S * N));
+            CU_TRY(ctx, cudaMemsetAsync(P.fl_out, 0, sizeof(float) * 8 * (size_t)N, ctx->stream));
+            CU_TRY(ctx, cudaMemsetAsync(P.fl_last, 0xff, sizeof(int32_t) * (size_t)N, ctx->stream));
+            CU_TRY(ctx, cudaMemsetAsync(P.fl_key, 0, sizeof(unsigned long long) * (size_t)N, ctx->stream));
+            CU_TRY(ctx, cudaMemsetAsync(P.fl_prof, 0, sizeof(float) * (size_t)S * N, ctx->stream));
         }
         LAUNCH(ctx, k_state_init_tb, G, B, 0, use_stoin ? d_stoin : d_storage, use_stoin ? 0.0f : cfg->storage_constant, N, M, P.st4, P.s5);
     } else {
@@ -2353,6 +2463,11 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
             const int clo = lo - hlo, chi = hi - hhi;
             const bool pdl = use_pdl && launched_any;  // the first wave follows memsets and plan kernels: plain launch
             launched_any = true;
+            if (floods) {  // HydroFlash: K = 4 (or 1 for runs shorter than 4 steps)
+                if (KT == 4) launch_tb<4, false, false, false, false, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
+                else launch_tb<1, false, false, false, false, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
+                continue;
+            }
             if (sepr) {  // separate_rain: K = 4 (or 1 for runs shorter than 4 steps)
                 if (KT == 4) launch_tb<4, false, false, false, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
                 else launch_tb<1, false, false, false, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
@@ -2425,6 +2540,23 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
                d_balance, d_mean_rain, d_mean_storage, d_mean_speed, d_mean_retorno, d_mean_vfluxes);
     }
     if (d_rc_out) LAUNCH(ctx, k_rc_final, G, B, 0, P.rc, N, d_rc_out);
+    if (floods) {
+        int32_t *d_ff = nullptr;
+        float *d_sc = nullptr;
+        unsigned long long *best;
+        WMF_TRY(sc.out(out->flood_flood, (size_t)N, &d_ff));
+        WMF_TRY(sc.alloc(&best, 1));
+        CU_TRY(ctx, cudaMemsetAsync(best, 0, sizeof(unsigned long long), ctx->stream));
+        LAUNCH(ctx, k_flood_final, G, B, 0, P.fl_key, P.fl_last, N, d_ff, best);
+        float *outs[6] = {out->flood_h, out->flood_ufr, out->flood_cr, out->flood_q, out->flood_qsed, out->flood_speed};
+        for (int k = 0; k < 6; ++k) {
+            float *d;
+            WMF_TRY(sc.out(outs[k], (size_t)N, &d));
+            if (d) CU_TRY(ctx, cudaMemcpyAsync(d, P.fl_out + (size_t)k * N, sizeof(float) * (size_t)N, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        WMF_TRY(sc.out(out->flood_scalars, 3, &d_sc));
+        if (d_sc) LAUNCH(ctx, k_flood_scalars, 1, 32, 0, best, P.fl_out, P.fl_last, N, d_sc);
+    }
     if (sepr) {
         float *oc = nullptr, *os = nullptr;
         WMF_TRY(sc.out(out->storage_conv, 5 * NM, &oc));
