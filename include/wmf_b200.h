@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define WMF_ABI_VERSION 10
+#define WMF_ABI_VERSION 11
 
 enum {
     WMF_OK = 0,
@@ -293,9 +293,13 @@ int wmf_eval_scores(wmf_ctx *ctx, const float *q, int32_t n_members, int32_t n_c
 /* rain_pre_mit, modelosv2.f90:1068-1101: tin_perte (nceldas) = 1-based triangle of every cell, 0 = none */
 int wmf_rain_pre_mit(wmf_ctx *ctx, const float *xy_basin, const int32_t *tin, const float *coord, int32_t nceldas,
                      int32_t ntin, int32_t ncoord, int32_t *tin_perte);
+/* rain_idw also has the hills model: mask_vector (nceldas) = hill of every cell (1..nhills), nhills > 0: the records then hold
+ * nhills values, column i = hill nhills-i+1 = the SUM of the hill's cell values (what the Fortran computes, :1214-1216,
+ * :1257-1259 with module models' basin_subbasin_map2subbasin(..., sum_mean = 2)).  mask_vector = NULL, nhills = 0: cells.
+ * (rain_mit's hills branch needs sum(maskVector) == nhills, :1126, which no hill table satisfies: cells only.) */
 int wmf_rain_idw(wmf_ctx *ctx, const float *xy_basin, const float *coord, const float *rain, float pp,
                  int32_t nceldas, int32_t ncoord, int32_t nreg, float umbral, int32_t *table, int32_t capacity,
-                 float *mean_rain, int32_t *pos_ids, int32_t *n_records);
+                 float *mean_rain, int32_t *pos_ids, int32_t *n_records, const int32_t *mask_vector, int32_t nhills);
 int wmf_rain_mit(wmf_ctx *ctx, const float *xy_basin, const float *coord, const float *rain, const int32_t *tin,
                  const int32_t *tin_perte, int32_t nceldas, int32_t ncoord, int32_t ntin, int32_t nreg, float umbral,
                  int32_t *table, int32_t capacity, float *mean_rain, int32_t *pos_ids, int32_t *n_records);

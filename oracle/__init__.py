@@ -571,37 +571,41 @@ def calc_speed(sm, coef, expo, elem_long, speed, dt, calc_niter=5):
     return float(area), float(s.value)
 
 
-def _rain_common(L, fn, args, n, T):
+def _rain_common(L, fn, args, n, T, mask, nhills):
     cap = T + 1
-    table = np.zeros((cap, n), np.int32)
+    width = nhills if nhills else n
+    table = np.zeros((cap, width), np.int32)
     mean, pos, mean64 = np.zeros(T, np.float32), np.zeros(T, np.int32), np.zeros(T, np.float64)
+    mk = np.ascontiguousarray(mask, np.int32) if nhills else None
     fn.restype = C.c_int32
-    nrec = fn(*args, _p(table, i32p), cap, _p(mean, f32p), _p(pos, i32p), _p(mean64, f64p))
+    nrec = fn(*args, _p(table, i32p), cap, _p(mean, f32p), _p(pos, i32p), _p(mean64, f64p),
+              _p(mk, i32p) if nhills else None, int(nhills))
     if nrec < 1:
         raise ValueError("oracle rain interpolation failed")
     return dict(table=table[:nrec].copy(), mean_rain=mean, pos_ids=pos, mean_rain64=mean64)
 
 
-def rain_idw(xy_basin, coord, rain, pp, umbral):
-    """modelosv2.f90:1195-1271 (cells model).  xy_basin (2,N), coord (2,ncoord), rain (ncoord,nreg); returns the record
-    table the Fortran writes to ``ruta`` (row 0 = record 1 = zeros), meanRain, posIds (+ an fp64 twin of meanRain)."""
+def rain_idw(xy_basin, coord, rain, pp, umbral, mask=None, nhills=0):
+    """modelosv2.f90:1195-1271.  xy_basin (2,N), coord (2,ncoord), rain (ncoord,nreg); returns the record table the Fortran
+    writes to ``ruta`` (row 0 = record 1 = zeros), meanRain, posIds (+ an fp64 twin of meanRain).  ``mask`` / ``nhills``:
+    the hills model (records of nhills values)."""
     L = lib()
     xy, co, r = _f(xy_basin), _f(coord), _f(rain)
     n, nc, T = xy.shape[1], co.shape[1], r.shape[1]
     assert xy.shape[0] == 2 and co.shape[0] == 2 and r.shape[0] == nc
     args = (_p(xy, f32p), _p(co, f32p), _p(r, f32p), C.c_float(pp), n, nc, T, C.c_float(umbral))
-    return _rain_common(L, L.wo_rain_idw, args, n, T)
+    return _rain_common(L, L.wo_rain_idw, args, n, T, mask, nhills)
 
 
-def rain_mit(xy_basin, coord, rain, tin, tin_perte, umbral):
-    """modelosv2.f90:1104-1194 (cells model).  tin (3,ntin) 1-based station ids, tin_perte (N) 1-based triangle of each cell."""
+def rain_mit(xy_basin, coord, rain, tin, tin_perte, umbral, mask=None, nhills=0):
+    """modelosv2.f90:1104-1194.  tin (3,ntin) 1-based station ids, tin_perte (N) 1-based triangle of each cell."""
     L = lib()
     xy, co, r = _f(xy_basin), _f(coord), _f(rain)
     tn = _i(tin)
     tp = np.ascontiguousarray(np.asarray(tin_perte).reshape(-1), np.int32)
     n, nc, T = xy.shape[1], co.shape[1], r.shape[1]
     args = (_p(xy, f32p), _p(co, f32p), _p(r, f32p), _p(tn, i32p), _p(tp, i32p), n, nc, tn.shape[1], T, C.c_float(umbral))
-    return _rain_common(L, L.wo_rain_mit, args, n, T)
+    return _rain_common(L, L.wo_rain_mit, args, n, T, mask, nhills)
 
 
 def rain_pre_mit(xy_basin, tin, coord):

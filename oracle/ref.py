@@ -571,7 +571,7 @@ def _read_records(path, n):
     return raw.reshape(-1, n)
 
 
-def rain_idw(xy_basin, coord, rain, pp, umbral, workdir=None):
+def rain_idw(xy_basin, coord, rain, pp, umbral, workdir=None, mask=None, nhills=0):
     """The reference's ``rain_idw`` (modelosv2.f90:1195-1271), cells model: returns what it writes to ``ruta`` as a record
     table plus meanRain / posIds."""
     xy, co, r = _f(xy_basin), _f(coord), _f(rain)
@@ -579,16 +579,16 @@ def rain_idw(xy_basin, coord, rain, pp, umbral, workdir=None):
     tmp = tempfile.TemporaryDirectory(prefix="wref_") if workdir is None else None
     path = os.path.join(workdir or tmp.name, "idw.bin")
     mean, pos = np.zeros(T, np.float32), np.zeros(T, np.int32)
-    mask = np.ones(n, np.int32)
-    _call(MODELS, "rain_idw", xy, co, r, f32(pp), i32(n), i32(nc), i32(T), i32(0), _ruta(path, 255), f32(umbral), mean, pos,
+    mask = np.ones(n, np.int32) if not nhills else np.ascontiguousarray(mask, np.int32)
+    _call(MODELS, "rain_idw", xy, co, r, f32(pp), i32(n), i32(nc), i32(T), i32(int(nhills)), _ruta(path, 255), f32(umbral), mean, pos,
           mask, 255)
-    out = dict(table=_read_records(path, n), mean_rain=mean, pos_ids=pos)
+    out = dict(table=_read_records(path, nhills if nhills else n), mean_rain=mean, pos_ids=pos)
     if tmp is not None:
         tmp.cleanup()
     return out
 
 
-def rain_mit(xy_basin, coord, rain, tin, tin_perte, umbral, workdir=None):
+def rain_mit(xy_basin, coord, rain, tin, tin_perte, umbral, workdir=None, mask=None, nhills=0):
     """The reference's ``rain_mit`` (modelosv2.f90:1104-1194), cells model."""
     xy, co, r = _f(xy_basin), _f(coord), _f(rain)
     tn = _i(tin)
@@ -597,10 +597,10 @@ def rain_mit(xy_basin, coord, rain, tin, tin_perte, umbral, workdir=None):
     tmp = tempfile.TemporaryDirectory(prefix="wref_") if workdir is None else None
     path = os.path.join(workdir or tmp.name, "mit.bin")
     mean, pos = np.zeros(T, np.float32), np.zeros(T, np.int32)
-    mask = np.ones(n, np.int32)
-    _call(MODELS, "rain_mit", xy, co, r, tn, tp, i32(n), i32(0), i32(nc), i32(tn.shape[1]), i32(T), _ruta(path, 255),
+    mask = np.ones(n, np.int32) if not nhills else np.ascontiguousarray(mask, np.int32)
+    _call(MODELS, "rain_mit", xy, co, r, tn, tp, i32(n), i32(int(nhills)), i32(nc), i32(tn.shape[1]), i32(T), _ruta(path, 255),
           f32(umbral), mean, pos, mask, 255)
-    out = dict(table=_read_records(path, n), mean_rain=mean, pos_ids=pos)
+    out = dict(table=_read_records(path, nhills if nhills else n), mean_rain=mean, pos_ids=pos)
     if tmp is not None:
         tmp.cleanup()
     return out

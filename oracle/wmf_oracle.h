@@ -196,10 +196,11 @@ void wo_basin_subbasin_map2subbasin(const int32_t *sub_pert, const float *var, i
  * fp64 twin of the sequential fp32 sum.  Returns the number of records written (>= 1), or -1 when capacity is too small. */
 int32_t wo_rain_idw(const float *xy_basin, const float *coord, const float *rain, float pp, int32_t nceldas,
                     int32_t ncoord, int32_t nreg, float umbral, int32_t *table, int32_t capacity, float *mean_rain,
-                    int32_t *pos_ids, double *mean_rain64);
+                    int32_t *pos_ids, double *mean_rain64, const int32_t *mask /* hill of every cell or NULL */, int32_t nhills);
 int32_t wo_rain_mit(const float *xy_basin, const float *coord, const float *rain, const int32_t *tin,
                     const int32_t *tin_perte, int32_t nceldas, int32_t ncoord, int32_t ntin, int32_t nreg, float umbral,
-                    int32_t *table, int32_t capacity, float *mean_rain, int32_t *pos_ids, double *mean_rain64);
+                    int32_t *table, int32_t capacity, float *mean_rain, int32_t *pos_ids, double *mean_rain64,
+                    const int32_t *mask, int32_t nhills);
 
 #ifdef __cplusplus
 }

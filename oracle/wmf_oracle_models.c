@@ -750,8 +750,23 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out)
 
 /* ---- rain interpolation, modelosv2.f90:1104-1271 (cells model) ---- */
 /* what both routines do with a finished field (:1166-1190, :1244-1268) */
+/* hills mode (maskVector = hill id of every cell): basin_subbasin_map2subbasin of module models (:1841-1877) is called with
+ * sum_mean = celdas_hills = 2, i.e. the hill's value is the SUM of its cells' rainfall, added in ascending cell order; column
+ * i of the record is hill n_hills - i + 1 */
+static void rain_to_hills(const float *campo, int32_t n, const int32_t *mask, int32_t nhills, int32_t *rec)
+{
+    for (int32_t i = 1; i <= nhills; ++i) {
+        const int32_t posi = nhills - i + 1;
+        float s = 0.0f;
+        int32_t cnt = 0;
+        for (int32_t c = 0; c < n; ++c)
+            if (mask[c] == posi) { s += campo[c]; ++cnt; }
+        rec[i - 1] = (int32_t)((cnt > 0 ? s : 0.0f) * 1000.0f);
+    }
+}
+
 static int rain_store(const float *campo, int32_t n, float umbral, int32_t t, int32_t *cont, int32_t *table,
-                      int32_t capacity, float *mean_rain, int32_t *pos_ids, double *mean_rain64)
+                      int32_t capacity, float *mean_rain, int32_t *pos_ids, double *mean_rain64, const int32_t *mask, int32_t nhills)
 {
     float s = 0.0f;
     double s64 = 0.0;
@@ -766,8 +781,10 @@ static int rain_store(const float *campo, int32_t n, float umbral, int32_t t, in
         mean_rain[t] = s / (float)n_pos;
         if (mean_rain64) mean_rain64[t] = s64 / (double)n_pos;
         if (*cont > capacity) return -1;
-        int32_t *rec = table + (size_t)(*cont - 1) * n;
-        for (int32_t i = 0; i < n; ++i) rec[i] = (int32_t)(campo[i] * 1000.0f); /* campoInt = campo*1000 truncates */
+        int32_t *rec = table + (size_t)(*cont - 1) * (nhills > 0 ? nhills : n);
+        if (nhills > 0) rain_to_hills(campo, n, mask, nhills, rec);
+        else
+            for (int32_t i = 0; i < n; ++i) rec[i] = (int32_t)(campo[i] * 1000.0f); /* campoInt = campo*1000 truncates */
         pos_ids[t] = *cont;
         *cont = *cont + 1;
     } else {
@@ -781,12 +798,12 @@ static int rain_store(const float *campo, int32_t n, float umbral, int32_t t, in
 /* modelosv2.f90:1195-1271 */
 int32_t wo_rain_idw(const float *xy_basin, const float *coord, const float *rain, float pp, int32_t nceldas,
                     int32_t ncoord, int32_t nreg, float umbral, int32_t *table, int32_t capacity, float *mean_rain,
-                    int32_t *pos_ids, double *mean_rain64)
+                    int32_t *pos_ids, double *mean_rain64, const int32_t *mask, int32_t nhills)
 {
     if (capacity < 1) return -1;
     float *W = (float *)malloc(sizeof(float) * (size_t)ncoord * nceldas); /* W(ncoord,nceldas) */
     float *campo = (float *)malloc(sizeof(float) * (size_t)nceldas);
-    for (int32_t c = 0; c < nceldas; ++c) table[c] = 0; /* record 1 = zeros (:1224) */
+    for (int32_t c = 0; c < (nhills > 0 ? nhills : nceldas); ++c) table[c] = 0; /* record 1 = zeros (:1224) */
     for (int32_t i = 0; i < ncoord; ++i) /* :1227-1229 */
         for (int32_t c = 0; c < nceldas; ++c) {
             const float dxs = coord[2 * i] - xy_basin[2 * (size_t)c], dys = coord[2 * i + 1] - xy_basin[2 * (size_t)c + 1];
@@ -805,7 +822,7 @@ int32_t wo_rain_idw(const float *xy_basin, const float *coord, const float *rain
             const float valor = WO_MAXX0(q);
             campo[c] = (valor == valor - 1.0f) ? 0.0f : valor;
         }
-        rc = rain_store(campo, nceldas, umbral, t, &cont, table, capacity, mean_rain, pos_ids, mean_rain64);
+        rc = rain_store(campo, nceldas, umbral, t, &cont, table, capacity, mean_rain, pos_ids, mean_rain64, mask, nhills);
     }
     free(W);
     free(campo);
@@ -815,11 +832,12 @@ int32_t wo_rain_idw(const float *xy_basin, const float *coord, const float *rain
 /* modelosv2.f90:1104-1194 */
 int32_t wo_rain_mit(const float *xy_basin, const float *coord, const float *rain, const int32_t *tin,
                     const int32_t *tin_perte, int32_t nceldas, int32_t ncoord, int32_t ntin, int32_t nreg, float umbral,
-                    int32_t *table, int32_t capacity, float *mean_rain, int32_t *pos_ids, double *mean_rain64)
+                    int32_t *table, int32_t capacity, float *mean_rain, int32_t *pos_ids, double *mean_rain64,
+                    const int32_t *mask, int32_t nhills)
 {
     if (capacity < 1) return -1;
     float *campo = (float *)malloc(sizeof(float) * (size_t)nceldas);
-    for (int32_t c = 0; c < nceldas; ++c) table[c] = 0;
+    for (int32_t c = 0; c < (nhills > 0 ? nhills : nceldas); ++c) table[c] = 0;
     int32_t cont = 2, rc = 0;
     for (int32_t t = 0; t < nreg && rc == 0; ++t) {
         const float *r = rain + (size_t)t * ncoord;
@@ -837,7 +855,7 @@ int32_t wo_rain_mit(const float *xy_basin, const float *coord, const float *rain
             const float q = az - coef2 / coef1;
             campo[c] = WO_MAXX0(q);
         }
-        rc = rain_store(campo, nceldas, umbral, t, &cont, table, capacity, mean_rain, pos_ids, mean_rain64);
+        rc = rain_store(campo, nceldas, umbral, t, &cont, table, capacity, mean_rain, pos_ids, mean_rain64, mask, nhills);
     }
     free(campo);
     return rc ? -1 : cont - 1;

@@ -87,7 +87,7 @@ def test_rain_mit(tmp_path):
     with pytest.raises(ValueError):
         m.rain_mit(xy, coord, rain, tin, np.zeros(bs["n"]), 0, path, 0.0, np.ones(bs["n"]))
     with pytest.raises(NotImplementedError):
-        m.rain_idw(xy, coord, rain, 1.0, 5, path, 0.0, np.zeros(bs["n"]))         # hills model
+        m.rain_mit(xy, coord, rain, tin, perte[None, :], 5, path, 0.0, np.full(bs["n"], 2))     # hills branch of rain_mit: unreachable
 
 
 def test_resident_table_feeds_shia_without_leaving_the_gpu():
@@ -110,3 +110,25 @@ def test_resident_table_feeds_shia_without_leaving_the_gpu():
     q, qr = np.asarray(ret[0], np.float64), np.asarray(ref_run["q"], np.float64)
     assert np.abs(q - qr).max() <= 1e-5 * np.abs(qr).max() and qr.max() > 0
     np.testing.assert_array_equal(m.acum_rain.reshape(-1), ref_run["acum_rain"])
+
+
+def test_rain_idw_by_hills(tmp_path):
+    """The hills model of rain_idw (modelosv2.f90:1210-1216, 1257-1259): records of nhills values, each the SUM of the hill's
+    cells in ascending cell order (module models' basin_subbasin_map2subbasin with sum_mean = 2), column i = hill nhills-i+1."""
+    import oracle
+    from conftest import basin_vectors
+    from wmf_b200 import CuModule, ModelsModule
+    bs, xy, coord, rain = setup_case(seed=7)
+    v = basin_vectors(bs)
+    oc = bs["cu"]
+    cauce, nodos, nn = oc.basin_subbasin_nod(bs["basin"], v["acum"], 25)
+    hills_own, _ = oc.basin_subbasin_find(bs["basin"], nodos, nn)
+    want = oracle.rain_idw(xy, coord, rain, 2.0, 0.0, mask=hills_own, nhills=nn)
+    m = ModelsModule()
+    path = str(tmp_path / "idw_hills.bin")
+    mean, pos = m.rain_idw(xy, coord, rain, 2.0, nn, path, 0.0, hills_own, bs["n"], coord.shape[1], rain.shape[1])
+    table = np.fromfile(path, np.int32).reshape(-1, nn)
+    np.testing.assert_array_equal(pos, want["pos_ids"])
+    np.testing.assert_array_equal(table, want["table"])
+    np.testing.assert_allclose(mean, want["mean_rain64"], rtol=1e-6, atol=1e-9)
+    assert nn > 50 and table.shape[1] == nn and table.max() > 0

@@ -276,6 +276,14 @@ def test_rain_interpolation_oracle_is_bit_identical_to_the_reference(ref, tmp_pa
         for k in ("table", "pos_ids", "mean_rain"):
             same(R[k], O[k], f"rain_idw(pp={pp}, umbral={umbral}) {k}")
         assert O["table"].shape[0] > 5 and (O["pos_ids"] == 1).any()
+    # the hills model of rain_idw: records of nhills sums
+    v = basin_vectors(bs)
+    cauce, nodos, nn = bs["cu"].basin_subbasin_nod(bs["basin"], v["acum"], 20)
+    hills_own, _ = bs["cu"].basin_subbasin_find(bs["basin"], nodos, nn)
+    R, O = ref.rain_idw(xy, coord, rain, 2.0, 0.0, mask=hills_own, nhills=nn), oracle.rain_idw(xy, coord, rain, 2.0, 0.0, mask=hills_own, nhills=nn)
+    for k in ("table", "pos_ids", "mean_rain"):
+        same(R[k], O[k], "rain_idw by hills " + k)
+    assert O["table"].shape[1] == nn
     tin = np.asfortranarray((Delaunay(coord.T.astype(np.float64)).simplices.T + 1).astype(np.int32))
     perte = ref.rain_pre_mit(xy, tin, coord)
     assert perte.min() >= 1

@@ -161,7 +161,7 @@ def load() -> C.CDLL:
     L.wmf_basin_stream_slope.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
     L.wmf_stream_find_to_corr.argtypes = [vp, f32, f32, vp, vp, i32, i32, f32p, f32p]
     L.wmf_rain_pre_mit.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
-    L.wmf_rain_idw.argtypes = [vp, vp, vp, vp, f32, i32, i32, i32, f32, vp, i32, vp, vp, i32p]
+    L.wmf_rain_idw.argtypes = [vp, vp, vp, vp, f32, i32, i32, i32, f32, vp, i32, vp, vp, i32p, vp, i32]
     L.wmf_rain_mit.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, i32, vp, vp, i32p]
     _lib = L
     return L

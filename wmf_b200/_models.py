@@ -303,7 +303,7 @@ class ModelsModule:
         return table, remap
 
     # ---- rainfall interpolation -----------------------------------------------------------------
-    def _rain_interp(self, which, xy_basin, coord, rain, extra, ruta, umbral, maskvector, resident):
+    def _rain_interp(self, which, xy_basin, coord, rain, extra, ruta, umbral, maskvector, resident, nhills=0):
         c = self.ctx
         xy = np.asfortranarray(xy_basin, dtype=np.float32)
         co = np.asfortranarray(coord, dtype=np.float32)
@@ -311,16 +311,23 @@ class ModelsModule:
         if xy.ndim != 2 or xy.shape[0] != 2 or co.ndim != 2 or co.shape[0] != 2 or r.ndim != 2 or r.shape[0] != co.shape[1]:
             raise ValueError("xy_basin must be (2,nceldas), coord (2,ncoord), rain (ncoord,nreg)")
         N, ncoord, T = xy.shape[1], co.shape[1], r.shape[1]
-        if maskvector is not None and int(np.asarray(maskvector).sum()) != N:
-            raise NotImplementedError("rain interpolation by hills (sum(maskVector) != nceldas, modelosv2.f90:1124-1127) is "
-                                      "outside the B200 hot path (SURVEY.md 8f row 4)")
+        mask, n_hills = None, 0
+        if maskvector is not None and int(np.asarray(maskvector).sum()) != N:      # the hills model (:1210-1214)
+            if which != "idw":
+                raise NotImplementedError("rain_mit by hills: the reference takes that branch only when sum(maskVector) == nhills "
+                                          "(modelosv2.f90:1126), which no hill table satisfies")
+            mask = np.ascontiguousarray(np.asarray(maskvector).reshape(-1), np.int32)
+            n_hills = int(nhills)
+            if mask.size != N or n_hills < 1 or mask.min() < 0 or mask.max() > n_hills:
+                raise ValueError("maskVector must give the hill (1..nhills) of every cell")
+        width = n_hills if n_hills else N
         mean, pos = _pinned_empty((T,), np.float32), _pinned_empty((T,), np.int32)
         nrec = C.c_int32(0)
 
         def call(table_ptr, cap):
             if which == "idw":
                 return c.L.wmf_rain_idw(c.h, ptr(xy), ptr(co), ptr(r), float(extra), N, ncoord, T, float(umbral), table_ptr, cap,
-                                        ptr(mean), ptr(pos), C.byref(nrec))
+                                        ptr(mean), ptr(pos), C.byref(nrec), ptr(mask), n_hills)
             tin, perte = extra
             return c.L.wmf_rain_mit(c.h, ptr(xy), ptr(co), ptr(r), ptr(tin), ptr(perte), N, ncoord, tin.shape[1], T,
                                     float(umbral), table_ptr, cap, ptr(mean), ptr(pos), C.byref(nrec))
@@ -329,11 +336,11 @@ class ModelsModule:
         cap = 1 + (int(np.count_nonzero((r > 0).any(axis=0))) if float(umbral) >= 0 else T)
         if resident:
             import torch
-            table = torch.empty((cap, N), dtype=torch.int32, device=f"cuda:{c.device}")
+            table = torch.empty((cap, width), dtype=torch.int32, device=f"cuda:{c.device}")
             c.check(call(ptr(table), cap))
             self.set_rain(table[:int(nrec.value)], pos)
         else:
-            table = _pinned_empty((N, cap), np.int32)                 # F-order (N, records) = records of N ints
+            table = _pinned_empty((width, cap), np.int32)             # F-order (values, records) = one record after the other
             c.check(call(ptr(table), cap))
             if ruta:
                 with open(str(ruta).strip(), "wb") as f:
@@ -357,7 +364,7 @@ class ModelsModule:
         -- modelosv2.f90:1195-1271 (call site wmf.py:3408-3412).  The wet fields are written to ``ruta`` as the Fortran
         does (record 1 = zeros).  Extension: ``resident=True`` keeps the record table on the GPU and installs it with
         ``set_rain`` so that ``shia_v1(None, None, ...)`` runs on it without a file or a PCIe round trip."""
-        return self._rain_interp("idw", xy_basin, coord, rain, pp, ruta, umbral, maskvector, resident)
+        return self._rain_interp("idw", xy_basin, coord, rain, pp, ruta, umbral, maskvector, resident, nhills)
 
     def rain_mit(self, xy_basin, coord, rain, tin, tin_perte, nhills, ruta, umbral, maskvector=None, nceldas=None, ncoord=None,
                  ntin=None, nreg=None, resident=False):

@@ -178,3 +178,8 @@ __device__ __forceinline__ int block_scan_excl(int v, int *sm, int *total) {
 // entry points implemented in the other translation units
 int wmf_device_exclusive_scan_i32(wmf_ctx *ctx, Scope &sc, const int32_t *in, int32_t *out, int64_t n,
                                   int64_t *total_host /* may be null */);
+
+// cells gathered per hill in ascending cell order (subbasin.cu): order[hstart[h] .. +hist[h]) = the cells whose sub_pert is h
+// (and whose cauce is 1 when cauce is given), h = 1..n_hills
+int wmf_hill_groups(wmf_ctx *ctx, Scope &sc, const int32_t *sub_pert, const int32_t *cauce /* may be null */, int n, int n_hills,
+                    int32_t **order, int32_t **hstart, int32_t **hist);

@@ -47,6 +47,7 @@ struct RainP {
     double *sum;           // [T] field sum of every candidate step
     int32_t *n_umbral, *n_pos;
     int32_t *table;        // [1 + T][N]: candidate j goes to row j + 1 (row 0 = the all-zero record 1); NULL = statistics only
+    int as_float;          // hills model: keep the fp32 field (its bits) in `table`; the hills kernel sums and converts
 };
 
 template <int MODE>
@@ -138,8 +139,24 @@ __global__ void __launch_bounds__(RAIN_THREADS) k_rain_field(const RainP P) {
     if (active && P.table) {   // campoInt = campo*1000 (truncation), one record per candidate step (:1251-1252)
 #pragma unroll
         for (int k = 0; k < RAIN_TCH; ++k)
-            if (k < nt) P.table[(size_t)(t0 + k + 1) * P.N + cell] = (int32_t)(campo[k] * 1000.0f);
+            if (k < nt) P.table[(size_t)(t0 + k + 1) * P.N + cell] = P.as_float ? __float_as_int(campo[k]) : (int32_t)(campo[k] * 1000.0f);
     }
+}
+
+// hills model (maskVector = hill of every cell): module models' basin_subbasin_map2subbasin is called with sum_mean = 2
+// (modelosv2.f90:1841-1877): the hill's value is the SUM of its cells' rainfall in ascending cell order; column i of the
+// record is hill n_hills - i + 1.  One thread per (hill, record).
+__global__ void k_rain_hills(const int32_t *__restrict__ field, const int32_t *__restrict__ order, const int32_t *__restrict__ hstart,
+                             const int32_t *__restrict__ hist, int N, int nhills, int nrec, int32_t *__restrict__ table) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int j = blockIdx.y + 1;                      // record row (row 0 = zeros)
+    if (h > nhills || j >= nrec) return;
+    const int m = hist[h];
+    const int32_t *l = order + hstart[h];
+    const int32_t *f = field + (size_t)j * N;
+    float s = 0.0f;
+    for (int q = 0; q < m; ++q) s = s + __int_as_float(f[l[q]]);
+    table[(size_t)j * nhills + (nhills - h)] = (int32_t)((m > 0 ? s : 0.0f) * 1000.0f);
 }
 
 // One pass: every step with a positive reading somewhere (a "candidate"; all other fields are identically zero, hence
@@ -147,8 +164,9 @@ __global__ void __launch_bounds__(RAIN_THREADS) k_rain_field(const RainP P) {
 // (:1244, only possible with umbral > 0) is squeezed out afterwards by moving the later records up.
 template <int MODE>
 int rain_run(wmf_ctx *ctx, RainP P, Scope &sc, const float *rain_dev, float pp, int32_t *table, int32_t capacity, float *mean_rain,
-             int32_t *pos_ids, int32_t *n_records) {
+             int32_t *pos_ids, int32_t *n_records, const int32_t *mask = nullptr, int nhills = 0) {
     const int N = P.N, T_all = P.T, ns = P.ncoord;
+    const int W = nhills > 0 ? nhills : N;             // values per record
     std::vector<float> h_rain((size_t)ns * T_all);
     CU_TRY(ctx, cudaMemcpyAsync(h_rain.data(), rain_dev, sizeof(float) * h_rain.size(), cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -166,13 +184,14 @@ int rain_run(wmf_ctx *ctx, RainP P, Scope &sc, const float *rain_dev, float pp, 
     std::vector<int32_t> h_pos((size_t)T_all, 1);
     std::vector<float> h_mean((size_t)T_all, 0.0f);
     int32_t cont = 2;
-    int32_t *d_table = nullptr;
+    int32_t *d_table = nullptr, *d_field = nullptr;
     bool table_on_host = false;
     if (table) {
         table_on_host = !Scope::on_device(table);
-        if (table_on_host) WMF_TRY(sc.alloc(&d_table, (size_t)(C + 1) * N));
+        if (table_on_host) WMF_TRY(sc.alloc(&d_table, (size_t)(C + 1) * W));
         else d_table = table;
-        CU_TRY(ctx, cudaMemsetAsync(d_table, 0, sizeof(int32_t) * (size_t)N, ctx->stream));   // record 1 = zeros (:1224)
+        CU_TRY(ctx, cudaMemsetAsync(d_table, 0, sizeof(int32_t) * (size_t)W, ctx->stream));   // record 1 = zeros (:1224)
+        if (nhills > 0) WMF_TRY(sc.alloc(&d_field, (size_t)(C + 1) * N));                     // the cell fields, fp32
     }
     if (C > 0) {
         std::vector<float> h_rT((size_t)ns * Tp, -1.0f);
@@ -193,11 +212,20 @@ int rain_run(wmf_ctx *ctx, RainP P, Scope &sc, const float *rain_dev, float pp, 
         P.n_pos = P.n_umbral + C;
         CU_TRY(ctx, cudaMemsetAsync(P.sum, 0, sizeof(double) * C, ctx->stream));
         CU_TRY(ctx, cudaMemsetAsync(P.n_umbral, 0, sizeof(int32_t) * 2 * C, ctx->stream));
-        P.table = d_table;
+        P.table = nhills > 0 ? d_field : d_table;
+        P.as_float = nhills > 0 ? 1 : 0;
         const long long nblocks = (long long)grid_for(N, RAIN_THREADS) * (Tp / RAIN_TCH);
         if (nblocks > 0x7fffffffLL) WMF_FAIL(ctx, WMF_ERR_ARG, "rain interpolation: %lld blocks exceed the grid limit", nblocks);
         const dim3 grid((unsigned)nblocks);
         LAUNCH(ctx, k_rain_field<MODE>, grid, RAIN_THREADS, 0, P);
+        if (nhills > 0 && d_table) {
+            const int32_t *d_mask;
+            int32_t *order, *hstart, *hist;
+            WMF_TRY(sc.in(mask, (size_t)N, &d_mask));
+            WMF_TRY(wmf_hill_groups(ctx, sc, d_mask, nullptr, N, nhills, &order, &hstart, &hist));
+            const dim3 hg((unsigned)grid_for(nhills, 128), (unsigned)C);
+            LAUNCH(ctx, k_rain_hills, hg, 128, 0, d_field, order, hstart, hist, N, nhills, C + 1, d_table);
+        }
         std::vector<double> h_sum((size_t)C);
         std::vector<int32_t> h_cnt((size_t)2 * C);
         CU_TRY(ctx, cudaMemcpyAsync(h_sum.data(), P.sum, sizeof(double) * C, cudaMemcpyDeviceToHost, ctx->stream));
@@ -207,7 +235,7 @@ int rain_run(wmf_ctx *ctx, RainP P, Scope &sc, const float *rain_dev, float pp, 
             if ((float)h_sum[j] > P.umbral && h_cnt[j] > 0) {
                 h_mean[cand[j]] = (float)(h_sum[j] / (double)h_cnt[(size_t)C + j]);
                 if (d_table && cont != j + 2)   // a dry candidate came before: move this record up to its final row
-                    CU_TRY(ctx, cudaMemcpyAsync(d_table + (size_t)(cont - 1) * N, d_table + (size_t)(j + 1) * N, sizeof(int32_t) * (size_t)N,
+                    CU_TRY(ctx, cudaMemcpyAsync(d_table + (size_t)(cont - 1) * W, d_table + (size_t)(j + 1) * W, sizeof(int32_t) * (size_t)W,
                                                 cudaMemcpyDeviceToDevice, ctx->stream));
                 h_pos[cand[j]] = cont++;
             }
@@ -221,7 +249,7 @@ int rain_run(wmf_ctx *ctx, RainP P, Scope &sc, const float *rain_dev, float pp, 
     if (d_mean) CU_TRY(ctx, cudaMemcpyAsync(d_mean, h_mean.data(), sizeof(float) * T_all, cudaMemcpyHostToDevice, ctx->stream));
     if (d_pos) CU_TRY(ctx, cudaMemcpyAsync(d_pos, h_pos.data(), sizeof(int32_t) * T_all, cudaMemcpyHostToDevice, ctx->stream));
     if (table_on_host)
-        CU_TRY(ctx, cudaMemcpyAsync(table, d_table, sizeof(int32_t) * (size_t)*n_records * N, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaMemcpyAsync(table, d_table, sizeof(int32_t) * (size_t)*n_records * W, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // the host vectors above go out of scope
     return sc.finish();
 }
@@ -286,13 +314,13 @@ int wmf_rain_pre_mit(wmf_ctx *ctx, const float *xy_basin, const int32_t *tin, co
 
 int wmf_rain_idw(wmf_ctx *ctx, const float *xy_basin, const float *coord, const float *rain, float pp, int32_t nceldas,
                  int32_t ncoord, int32_t nreg, float umbral, int32_t *table, int32_t capacity, float *mean_rain,
-                 int32_t *pos_ids, int32_t *n_records) {
-    if (!ctx || !n_records) return WMF_ERR_ARG;
+                 int32_t *pos_ids, int32_t *n_records, const int32_t *mask_vector, int32_t nhills) {
+    if (!ctx || !n_records || nhills < 0 || (nhills > 0 && !mask_vector)) return WMF_ERR_ARG;
     Scope sc(ctx);
     RainP P{};
     const float *d_rain;
     WMF_TRY(rain_stage(ctx, sc, P, &d_rain, xy_basin, coord, rain, nceldas, ncoord, nreg, umbral));
-    return rain_run<0>(ctx, P, sc, d_rain, pp, table, capacity, mean_rain, pos_ids, n_records);
+    return rain_run<0>(ctx, P, sc, d_rain, pp, table, capacity, mean_rain, pos_ids, n_records, mask_vector, nhills);
 }
 
 int wmf_rain_mit(wmf_ctx *ctx, const float *xy_basin, const float *coord, const float *rain, const int32_t *tin,

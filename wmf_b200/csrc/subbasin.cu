@@ -146,7 +146,7 @@ __global__ void k_hill_keys(const int32_t *__restrict__ sub_pert, const int32_t 
     int h = 0;
     if (i < n) {
         h = sub_pert[i];
-        on = cauce[i] == 1 && h >= 1 && h <= nn;
+        on = (!cauce || cauce[i] == 1) && h >= 1 && h <= nn;
         key[i] = on ? (uint32_t)h : 0u;
         val[i] = i;
         if (on) atomicAdd(hist + h, 1);
@@ -371,6 +371,14 @@ __global__ void k_find_to_corr(const int32_t *__restrict__ dir, const int32_t *_
 }
 
 }  // namespace
+
+int wmf_hill_groups(wmf_ctx *ctx, Scope &sc, const int32_t *sub_pert, const int32_t *cauce, int n, int n_hills, int32_t **order,
+                    int32_t **hstart, int32_t **hist) {
+    HillGroups g;
+    WMF_TRY(hill_groups(ctx, sc, sub_pert, cauce, n, n_hills, &g));
+    *order = g.order; *hstart = g.hstart; *hist = g.hist;
+    return WMF_OK;
+}
 
 extern "C" {
 
