@@ -57,7 +57,51 @@ KEEP = ("q", "stoout", "hum", "st1", "st3", "balance", "balance64", "speed", "ar
         "vsc", "vdc", "volero", "voldepo", "retorned", "sl_riskvector", "sl_slideocurrence", "sl_slidencelltime")
 
 
+def build_topo_case():
+    """Small basin + gauges for the sub-basin / rain-interpolation fixture (inputs only)."""
+    from conftest import basin_vectors, make_basin
+    from wmf_b200 import synth
+    bs = make_basin("G2", 60, 48, 21)
+    v = basin_vectors(bs)
+    x, y = bs["cu"].basin_coordxy(bs["basin"])
+    xy = np.asfortranarray(np.vstack([x, y]), dtype=np.float32)
+    coord, rain = synth.make_stations(60, 48, bs["dx"], 7, 24, 21)
+    return bs, v, xy, coord, rain
+
+
+def run_topo(cu, mod, bs, v, xy, coord, rain, thr=15):
+    """The sub-basin chain and rain_idw (cells and hills) through ``cu`` (RefCu / oracle.Cu) and ``mod`` (oracle.ref / oracle)."""
+    b, n = bs["basin"], bs["n"]
+    cauce, nodos, nn = cu.basin_subbasin_nod(b, v["acum"], thr)
+    sub_pert, _ = cu.basin_subbasin_find(b, nodos, nn)
+    sb = cu.basin_subbasin_cut(nn)
+    sh, nh = cu.basin_subbasin_horton(sb, n)
+    sl, mx, nmx = cu.basin_subbasin_long(sub_pert, cauce, v["lng"], sb, sh)
+    pslope, plong = cu.basin_subbasin_stream_prop(sub_pert, cauce, v["lng"], v["pend"], nn)
+    c2, nod2, _, _, ncau = cu.basin_stream_nod(b, v["acum"], thr)
+    ss, sll = cu.basin_stream_slope(b, v["elev"], v["lng"], nod2, ncau)
+    idw = mod.rain_idw(xy, coord, rain, 2.0, 0.0)
+    idwh = mod.rain_idw(xy, coord, rain, 2.0, 0.0, mask=sub_pert, nhills=nn)
+    return {"t_cauce": cauce, "t_nodos_fin": nodos, "t_sub_pert": sub_pert, "t_sub_basins": sb, "t_sub_horton": sh,
+            "t_nod_horton_nodes": nh[sb[0] - 1], "t_sub_basin_long": sl, "t_max_long": np.array([mx, nmx], np.float64),
+            "t_hill_slope": pslope, "t_hill_long": plong, "t_stream_s": ss, "t_stream_l": sll,
+            "r_table": idw["table"], "r_pos": idw["pos_ids"], "r_mean": idw["mean_rain"],
+            "r_table_hills": idwh["table"], "thr": np.array([thr])}
+
+
 def main():
+    import oracle
+    from oracle import ref as refmod
+    bs, v, xy, coord, rain = build_topo_case()
+    rcu = refmod.RefCu()
+    o = bs["cu"]
+    rcu.ncols, rcu.nrows, rcu.xll, rcu.yll, rcu.dx, rcu.dy, rcu.dxp, rcu.nodata = o.ncols, o.nrows, o.xll, o.yll, o.dx, o.dy, o.dxp, o.nodata
+    R, O = run_topo(rcu, refmod, bs, v, xy, coord, rain), run_topo(o, oracle, bs, v, xy, coord, rain)
+    for k in R:
+        assert np.array_equal(np.asarray(R[k]), np.asarray(O[k]), equal_nan=True), ("topo_rain", k)
+    R["source"] = np.array(["reference Fortran objects via oracle/_ref"])
+    np.savez_compressed(os.path.join(HERE, "topo_rain.npz"), **R)
+    print("topo_rain", {k: np.asarray(a).shape for k, a in R.items()})
     for name in CASES:
         bs, v, inp, flags = build_case(name)
         orc = run_oracle(inp, flags)

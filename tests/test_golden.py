@@ -80,3 +80,55 @@ def test_cuda_matches_golden(name):
         close(ret[1], g["o_qsed"], 5e-5, "Qsed")
         close(m.vd, g["o_vd"], 5e-5, "Vd")
         np.testing.assert_array_equal(m.sl_riskvector.reshape(-1), g["o_sl_riskvector"])
+
+
+TOPO_KEYS = ("t_cauce", "t_nodos_fin", "t_sub_pert", "t_sub_basins", "t_sub_horton", "t_nod_horton_nodes", "t_sub_basin_long",
+             "t_max_long", "t_hill_slope", "t_hill_long", "t_stream_s", "t_stream_l", "r_table", "r_pos", "r_mean", "r_table_hills")
+
+
+def test_oracle_reproduces_topo_rain_golden():
+    """Sub-basin chain + rain_idw (cells and hills): the reference's vectors against today's restatement."""
+    import oracle
+    g = load("topo_rain")
+    bs, v, xy, coord, rain = mg.build_topo_case()
+    O = mg.run_topo(bs["cu"], oracle, bs, v, xy, coord, rain, int(g["thr"][0]))
+    for k in TOPO_KEYS:
+        np.testing.assert_array_equal(np.asarray(O[k]), g[k], err_msg=k)
+
+
+@pytest.mark.gpu
+def test_cuda_matches_topo_rain_golden():
+    from conftest import geo_to
+    from wmf_b200 import CuModule, ModelsModule
+    g = load("topo_rain")
+    bs, v, xy, coord, rain = mg.build_topo_case()
+    b, n, thr = bs["basin"], bs["n"], int(g["thr"][0])
+    cu, m = CuModule(), ModelsModule()
+    geo_to(cu, bs)
+    cauce, nodos, nn = cu.basin_subbasin_nod(b, v["acum"], thr, n)
+    np.testing.assert_array_equal(nodos, g["t_nodos_fin"])
+    sub_pert, _ = cu.basin_subbasin_find(b, nodos, nn, n)
+    np.testing.assert_array_equal(sub_pert, g["t_sub_pert"])
+    sb = cu.basin_subbasin_cut(nn)
+    np.testing.assert_array_equal(sb, g["t_sub_basins"])
+    sh, nh = cu.basin_subbasin_horton(sb, n, nn)
+    np.testing.assert_array_equal(sh, g["t_sub_horton"])
+    sl, mx, nmx = cu.basin_subbasin_long(sub_pert, cauce, v["lng"], sb, sh, nn, n)
+    np.testing.assert_array_equal(sl, g["t_sub_basin_long"])
+    assert [mx, nmx] == g["t_max_long"].tolist()
+    ps, pl = cu.basin_subbasin_stream_prop(sub_pert, cauce, v["lng"], v["pend"], nn, n)
+    np.testing.assert_array_equal(ps, g["t_hill_slope"])
+    np.testing.assert_array_equal(pl, g["t_hill_long"])
+    c2, nod2, _, _, ncau = cu.basin_stream_nod(b, v["acum"], thr, n)
+    ss, sll = cu.basin_stream_slope(b, v["elev"], v["lng"], nod2, ncau, n)
+    np.testing.assert_array_equal(ss, g["t_stream_s"])
+    np.testing.assert_array_equal(sll, g["t_stream_l"])
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        p1, p2 = os.path.join(d, "c.bin"), os.path.join(d, "h.bin")
+        mean, pos = m.rain_idw(xy, coord, rain, 2.0, 0, p1, 0.0, np.ones(n))
+        m.rain_idw(xy, coord, rain, 2.0, nn, p2, 0.0, sub_pert)
+        np.testing.assert_array_equal(np.fromfile(p1, np.int32).reshape(-1, n), g["r_table"])
+        np.testing.assert_array_equal(np.fromfile(p2, np.int32).reshape(-1, nn), g["r_table_hills"])
+    np.testing.assert_array_equal(pos, g["r_pos"])
+    np.testing.assert_allclose(mean, g["r_mean"], rtol=1e-6, atol=1e-9)
