@@ -40,8 +40,8 @@ sys.path.insert(0, ROOT)
 BYTES_PER_CELL_STEP = 144.0      # algorithmic bytes of one cell-step of a single run
 # dram__bytes_read.sum + dram__bytes_write.sum per k_shia_tb launch from the ncu --set full capture under profiles/
 # (cold-cache replay of a mid-run wave, 1.33e6 cell-steps in that launch); None until a capture exists
-TRAFFIC_PER_LAUNCH = 59.7e6
-TRAFFIC_NOTE = ("ncu --set full, one mid-run launch of 1359 CTAs = 1.33e6 cell-steps (cold-cache replay): 56.5 MB read + 3.2 MB "
+TRAFFIC_PER_LAUNCH = 60.0e6
+TRAFFIC_NOTE = ("ncu --set full, one mid-run launch of 1359 CTAs = 1.33e6 cell-steps (cold-cache replay): 56.5 MB read + 3.5 MB "
                 "written = 45 B per cell-step against 144 algorithmic; see profiles/README.md")
 WORKLOADS = {
     # name: (ncols, nrows, steps, generator)
