@@ -137,3 +137,24 @@ def test_every_export_has_ctypes_argtypes():
     L = _lib.load()
     missing = [s for s in _lib.EXPORTS if getattr(L, s).argtypes is None and s != "wmf_abi_version"]
     assert not missing, missing
+
+
+def test_every_f2py_module_attribute_exists():
+    """modelsmodule.c:3721-3856 lists the 140 names the f2py module `models` exposes; each must be readable on the drop-in
+    object (None for an unallocated array, as f2py).  Checked against the reference's generated wrapper when the tree is here."""
+    import re
+    path = "/root/reference/build/src.win-amd64-3.7/modelsmodule.c"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    from wmf_b200 import ModelsModule
+    lines = open(path, encoding="latin-1").read().splitlines()[3714:3860]
+    names = re.findall(r'\{"([a-z_0-9]+)"', "\n".join(lines))
+    assert len(names) >= 136
+    m = ModelsModule()
+    missing = []
+    for n in names:
+        try:
+            getattr(m, n)
+        except AttributeError:
+            missing.append(n)
+    assert not missing, missing

@@ -38,9 +38,13 @@ _ARRAYS = {
     "sl_frictionangle": (np.float32, 1), "sl_radslope": (np.float32, 1),
     "flood_w": (np.float32, 1), "flood_d50": (np.float32, 1), "flood_slope": (np.float32, 1),
     "flood_sections": (np.float32, -1), "flood_sec_cells": (np.float32, -1),      # (flood_sec_tam, N)
+    # module arrays the hot path does not read but f2py exposes (modelsmodule.c:3721-3856): kept so that assignments and reads behave
+    "flood_hand": (np.float32, 1), "flood_aquien": (np.int32, 1), "flood_eval": (np.int32, 1), "flood_loc_hand": (np.float32, 1),
+    "idevento": (np.int32, 0), "posevento": (np.int32, 0), "posconv": (np.int32, 0), "posstra": (np.int32, 0),
+    "speed_map": (np.float32, -1), "fluxes": (np.float32, 3), "vfluxes": (np.float32, 4), "ero": (np.float32, 0), "dep": (np.float32, 0),
     "speed_type": (np.int32, 0), "wi": (np.float32, 0), "diametro": (np.float32, 0),
 }
-_SCALARS_F = {"flood_rdf": 0.0, "flood_area": 0.0, "flood_diff": 0.0, "flood_dw": 1000.0, "flood_dsed": 2600.0, "flood_av": 1.0 / 200.0, "flood_cmax": 0.75, "flood_umbral": 3.0,
+_SCALARS_F = {"g": 9.8, "qskr": 0.0, "qlin_sed": 0.0, "flood_sec_tam": 0.0, "flood_rdf": 0.0, "flood_area": 0.0, "flood_diff": 0.0, "flood_dw": 1000.0, "flood_dsed": 2600.0, "flood_av": 1.0 / 200.0, "flood_cmax": 0.75, "flood_umbral": 3.0,
               "flood_step": 1.0, "flood_hmax": 5.0, "dt": 60.0, "dxp": 1.0, "retorno_gr": 0.0, "retorno_aq": 0.0, "storage_constant": 0.0,
               "sed_factor": 1.0, "sl_fs": 1.0, "sl_gammaw": 9.8, "xll": 0.0, "yll": 0.0, "nodata": -9999.0, "dx": 1.0}
 _SCALARS_I = {"flood_max_iter": 10, "nceldas": 0, "ncols": 0, "nrows": 0, "verbose": 0, "rain_first_point": 1, "calc_niter": 5,
@@ -48,6 +52,11 @@ _SCALARS_I = {"flood_max_iter": 10, "nceldas": 0, "ncols": 0, "nrows": 0, "verbo
               "save_retorno": 0, "save_vfluxes": 0, "save_rc": 0, "show_storage": 0, "show_speed": 0,
               "show_mean_speed": 0, "show_mean_retorno": 0, "show_area": 0, "separate_fluxes": 0,
               "separate_rain": 0, "sl_gullienogullie": 0}
+# module arrays shia_v1 allocates and fills (read back by wmf.py:4548-4601); None until a run has produced them
+_RESULTS = {"retorned", "mean_rain", "acum_rain", "mean_storage", "mean_speed", "mean_retorno", "mean_vfluxes", "rc_coef",
+            "storage_conv", "storage_stra", "volero", "voldepo", "erot", "dept", "sl_riskvector", "sl_slideocurrence",
+            "sl_slideacumulate", "sl_slidencelltime", "sl_zcrit", "sl_zmin", "sl_zmax", "sl_bo", "flood_q", "flood_qsed",
+            "flood_h", "flood_flood", "flood_speed", "flood_ufr", "flood_cr", "flood_profundidad"}
 # switches whose sub-models are outside the hot path built here
 _UNSUPPORTED = ()
 
@@ -94,6 +103,12 @@ def read_float_basin_ncol(ruta: str, record: int, n_cel: int, n_col: int):
         return np.asfortranarray(v.reshape((n_col, n_cel), order="F")), 0
     except OSError:
         return np.zeros((n_col, n_cel), np.float32, order="F"), 1
+
+
+def read_float_basin(ruta: str, record: int, n_cel: int):
+    """vect,res = read_float_basin(ruta,record,n_cel)   -- modelosv2.f90:875-890 (one value per cell)."""
+    v, res = read_float_basin_ncol(ruta, record, n_cel, 1)
+    return np.ascontiguousarray(v.reshape(-1)), res
 
 
 def write_int_basin(ruta: str, vect, record: int, n_cel=None, n_col=None):
@@ -176,6 +191,10 @@ class ModelsModule:
             return np.int32(v) if name in _SCALARS_I else np.float32(v)
         if name in _ARRAYS:
             return None                    # f2py: unallocated allocatable reads as None
+        if name in _RESULTS:
+            return None                    # a result array no run has produced yet: unallocated
+        if name in ("rute_speed", "rute_storage"):
+            return ""                      # character*500 module variables nothing in the hot path reads
         raise AttributeError(name)
 
     def __setattr__(self, name, value):
@@ -215,6 +234,7 @@ class ModelsModule:
     # ---- helpers kept from the f2py export list ----------------------------------------------------
     read_int_basin = staticmethod(read_int_basin)
     read_float_basin_ncol = staticmethod(read_float_basin_ncol)
+    read_float_basin = staticmethod(read_float_basin)
     write_int_basin = staticmethod(write_int_basin)
     write_float_basin = staticmethod(write_float_basin)
 
@@ -416,6 +436,9 @@ class ModelsModule:
         if int(self.separate_rain) == 1:
             types = self._load_rain_types(ruta_binconv, ruta_binstra, ruta_hdrconv, ruta_hdrstra, T, N)
         out = self._run(calib[None, :], int(n_cont), int(n_conth), T, rain, pos, stoin, hspeedin, rain_types=types)
+        a["posevento"] = np.array(pos, np.int32, copy=True)          # module posEvento as rain_read_ascii_table leaves it
+        if types is not None:
+            a["posconv"], a["posstra"] = np.array(types[2], np.int32, copy=True), np.array(types[3], np.int32, copy=True)
         # state dumps in the reference's direct-access format: record guarda_cond(t) of ruta_storage holds StoOut(5,N)
         # after step t; record t of ruta_speed holds hspeed(4,N)
         if save_sto:
