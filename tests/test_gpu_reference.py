@@ -87,3 +87,40 @@ def test_shia_against_the_reference(ref, case):
         close(m.vd, R["vd"], "Vd", rtol=5e-5)
         np.testing.assert_array_equal(np.asarray(m.sl_riskvector).reshape(-1), R["sl_riskvector"])
         np.testing.assert_array_equal(np.asarray(m.sl_slideocurrence).reshape(-1), R["sl_slideocurrence"])
+
+
+def test_dump_files_against_the_reference(ref, tmp_path):
+    """save_storage / save_speed / save_vfluxes / save_retorno / save_rc: the direct-access files the reference's own Fortran
+    writes (its write_float_basin calls, modelosv2.f90:799-823, 863-867) against the files the drop-in writes: same sizes, same
+    record numbering, values within the north-star tolerance."""
+    import os
+    from wmf_b200 import ModelsModule, synth
+    bs = make_basin("G2", 100, 80, 35)
+    v = basin_vectors(bs)
+    T = 50
+    inp = synth.make_shia_inputs(bs["basin"], v["acum"], v["lng"], v["pend"], dxp=30.0, n_reg=T, seed=35, speed_type=(2, 1, 1),
+                                 retorno_gr=1, rain_peak_mm=40.0)
+    inp["calib"][9] = 0.02
+    guarda = np.zeros(T, np.int32)
+    guarda[[5, 21, 49]] = [1, 2, 3]
+    flags = dict(save_storage=1, save_speed=1, save_vfluxes=1, save_retorno=1, save_rc=1)
+    names = ("ruta_storage", "ruta_speed", "ruta_vfluxes", "ruta_retorno", "ruta_rc")
+    rdir, gdir = tmp_path / "ref", tmp_path / "gpu"
+    os.makedirs(rdir), os.makedirs(gdir)
+    rpaths = {k: str(rdir / (k + ".bin")) for k in names}
+    gpaths = {k: str(gdir / (k + ".bin")) for k in names}
+    ref.shia_v1(dict(inp, guarda_cond=guarda, guarda_vfluxes=guarda, **flags), dumps=rpaths)
+    m = ModelsModule()
+    synth.apply_to_models(m, inp)
+    for k, val in flags.items():
+        setattr(m, k, val)
+    m.guarda_cond, m.guarda_vfluxes = guarda, guarda
+    m.set_rain(inp["rain"], inp["pos_evento"])
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    m.shia_v1(None, None, inp["calib"], n_cont, 1, T, None, None, bs["n"], gpaths["ruta_storage"], gpaths["ruta_speed"],
+              gpaths["ruta_vfluxes"], None, None, None, None, gpaths["ruta_retorno"], gpaths["ruta_rc"])
+    for k in names:
+        assert os.path.getsize(gpaths[k]) == os.path.getsize(rpaths[k]), k
+        g, r = np.fromfile(gpaths[k], np.float32), np.fromfile(rpaths[k], np.float32)
+        assert np.abs(r).max() > 0, k
+        close(g, r, k)
