@@ -132,3 +132,20 @@ def test_rain_idw_by_hills(tmp_path):
     np.testing.assert_array_equal(table, want["table"])
     np.testing.assert_allclose(mean, want["mean_rain64"], rtol=1e-6, atol=1e-9)
     assert nn > 50 and table.shape[1] == nn and table.max() > 0
+
+
+def test_rain_idw_gauge_on_a_cell_centre(tmp_path):
+    """A gauge exactly on a cell centre gives that cell an infinite weight: the masked sums must then really skip the
+    stations without data (inf * 0), so the library falls back from its mask-free fast path; same records as the oracle."""
+    import oracle
+    from wmf_b200 import ModelsModule
+    bs, xy, coord, rain = setup_case(seed=8)
+    coord = np.array(coord, copy=True, order="F")
+    coord[:, 2] = xy[:, 1234]
+    coord[:, 5] = xy[:, 77]
+    want = oracle.rain_idw(xy, coord, rain, 2.0, 0.0)
+    m = ModelsModule()
+    path = str(tmp_path / "idw.bin")
+    mean, pos = m.rain_idw(xy, coord, rain, 2.0, 0, path, 0.0, np.ones(bs["n"]))
+    np.testing.assert_array_equal(pos, want["pos_ids"])
+    np.testing.assert_array_equal(np.fromfile(path, np.int32).reshape(-1, bs["n"]), want["table"])
