@@ -131,4 +131,5 @@ def test_cuda_matches_topo_rain_golden():
         np.testing.assert_array_equal(np.fromfile(p1, np.int32).reshape(-1, n), g["r_table"])
         np.testing.assert_array_equal(np.fromfile(p2, np.int32).reshape(-1, nn), g["r_table_hills"])
     np.testing.assert_array_equal(pos, g["r_pos"])
-    np.testing.assert_allclose(mean, g["r_mean"], rtol=1e-6, atol=1e-9)
+    # the reference's meanRain is a sequential fp32 sum over the cells (error up to ~N*eps/2); the GPU sums in fp64
+    np.testing.assert_allclose(mean, g["r_mean"], rtol=n * 6e-8, atol=1e-9)
