@@ -1,0 +1,59 @@
+"""GPU parity on random partial basins x random switch combinations (conftest.fuzz_case): the cases on which the oracle is
+checked bit for bit against the reference's Fortran (tests/test_reference_pin.py::test_fuzz_shia_against_the_reference) are
+run through the CUDA path and compared with the oracle at the north-star tolerance."""
+import numpy as np
+import pytest
+
+from conftest import fuzz_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", range(16))
+def test_fuzz_shia_gpu_vs_oracle(case, tmp_path):
+    import oracle
+    from test_gpu_shia import close, compare_core
+    from wmf_b200 import ModelsModule, synth
+    fc = fuzz_case(case)
+    if fc is None:
+        pytest.skip("the random outlet caught a tiny basin")
+    inp, mode, extra, n, T = dict(fc["inp"]), fc["mode"], fc["extra"], fc["n"], fc["T"]
+    if mode in ("sepf", "sepr"):          # the separations run in the time-blocked kernel, which does not produce the per-step means
+        for k in ("show_storage", "show_mean_speed", "show_mean_retorno"):
+            inp[k] = 0
+    ref = oracle.shia_v1(inp)
+    m = ModelsModule()
+    synth.apply_to_models(m, inp)
+    m.set_rain(inp["rain"], inp["pos_evento"])
+    if mode == "sepr":
+        m.set_rain_types(inp["conv"], inp["stra"], inp["pos_conv"], inp["pos_stra"])
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    n_conth = max(1, int(np.count_nonzero(inp["control_h"])))
+    paths = [None] * 9
+    if mode == "dumps":
+        paths[2], paths[8] = str(tmp_path / "vf.bin"), str(tmp_path / "rc.bin")        # ruta_vfluxes, ruta_rc
+    ret = m.shia_v1(None, None, inp["calib"], n_cont, n_conth, T, None, None, n, *paths)
+    compare_core(ret, m, ref, n)
+    if inp.get("show_speed"):
+        close(ret[7], ref["speed"], name="Speed")
+    if inp.get("show_storage"):
+        close(m.mean_storage, ref["mean_storage64"], name="mean_storage")
+    if inp.get("show_mean_speed"):
+        close(m.mean_speed, ref["mean_speed64"], name="mean_speed")
+    if mode == "sepf":
+        close(ret[2], ref["qseparated"], name="Qseparated")
+    if mode == "sepr":
+        close(ret[10], ref["qsep_byrain"], name="Qsep_byrain")
+        close(m.storage_conv, ref["storage_conv"], name="Storage_conv")
+    if mode == "dumps":
+        close(m.mean_vfluxes, ref["mean_vfluxes64"], name="mean_vfluxes")
+        close(m.rc_coef, ref["rc_coef"], name="rc_coef")
+    if mode in ("sed", "sed_slides"):
+        close(ret[1], ref["qsed"], rtol=5e-5, name="Qsed")
+        for k in ("vs", "vd", "vsc", "vdc"):
+            close(getattr(m, k), ref[k], rtol=5e-5, afloor=1e-6, name=k)
+        close(m.voldepo, ref["voldepo"], rtol=5e-5, afloor=1e-6, name="VolDEPo")
+    if mode in ("slides", "sed_slides"):
+        np.testing.assert_array_equal(np.asarray(m.sl_riskvector).reshape(-1), ref["sl_riskvector"])
+        np.testing.assert_array_equal(np.asarray(m.sl_slideocurrence).reshape(-1), ref["sl_slideocurrence"])
+        np.testing.assert_array_equal(np.asarray(m.sl_slidencelltime).reshape(-1), ref["sl_slidencelltime"])
