@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define WMF_ABI_VERSION 11
+#define WMF_ABI_VERSION 12
 
 enum {
     WMF_OK = 0,
@@ -124,6 +124,13 @@ int wmf_basin_time_to_out(wmf_ctx *ctx, const int32_t *basin_f, const float *lng
 int wmf_basin_propagate(wmf_ctx *ctx, const int32_t *basin_f, const float *var, int32_t nceldas,
                         float *var_prop);
 
+/* basin_point2var (cuencas.f90:1230-1261) and basin_stream_point2stream (:1524-1577): control points onto the basin table /
+ * the stream network (set_Control -> Points_Points2Stream, wmf.py:2096-2103, 4021).  xy_coord (2,ncoord), xy_new (2,ncoord). */
+int wmf_basin_point2var(wmf_ctx *ctx, const int32_t *basin_f, const int32_t *id_coord, const float *xy_coord,
+                        int32_t ncoord, int32_t nceldas, int32_t *res_coord, int32_t *basin_pts);
+int wmf_basin_stream_point2stream(wmf_ctx *ctx, const int32_t *basin_f, const int32_t *cauce, const int32_t *id_coord,
+                                  const float *xy_coord, int32_t ncoord, int32_t nceldas, int32_t *res_coord,
+                                  int32_t *basin_pts, float *xy_new);
 /* stream_find_to_corr, cuencas.f90:372-417 (SimuBasin.__init__ with useCauceMap, wmf.py:2998-3000) */
 int wmf_stream_find_to_corr(wmf_ctx *ctx, float x, float y, const int32_t *dir, const int32_t *cauce, int32_t nc,
                             int32_t nf, float *lat, float *lon);

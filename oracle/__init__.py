@@ -313,6 +313,30 @@ class Cu:
         return out
 
 
+    def basin_point2var(self, basin_f, id_coord, xy_coord):
+        """res_coord,basin_pts = basin_point2var(basin_f,id_coord,xy_coord,[ncoord,nceldas])   -- cuencas.f90:1230-1261"""
+        b = _i(basin_f)
+        n = b.shape[1]
+        ids, xy = np.ascontiguousarray(id_coord, np.int32), _f(xy_coord)
+        res, pts = np.zeros(ids.size, np.int32), np.zeros(n, np.int32)
+        g = self._geo()
+        self._L.wo_basin_point2var(C.byref(g), _p(b, i32p), _p(ids, i32p), _p(xy, f32p), ids.size, n, _p(res, i32p), _p(pts, i32p))
+        return res, pts
+
+    def basin_stream_point2stream(self, basin_f, cauce, id_coord, xy_coord):
+        """res_coord,basin_pts,xy_new = basin_stream_point2stream(basin_f,cauce,id_coord,xy_coord,[ncoord,nceldas])
+        -- cuencas.f90:1524-1577"""
+        b = _i(basin_f)
+        n = b.shape[1]
+        ca = np.ascontiguousarray(cauce, np.int32)
+        ids, xy = np.ascontiguousarray(id_coord, np.int32), _f(xy_coord)
+        res, pts = np.zeros(ids.size, np.int32), np.zeros(n, np.int32)
+        xyn = np.zeros((2, ids.size), np.float32, order="F")
+        g = self._geo()
+        self._L.wo_basin_stream_point2stream(C.byref(g), _p(b, i32p), _p(ca, i32p), _p(ids, i32p), _p(xy, f32p), ids.size, n,
+                                             _p(res, i32p), _p(pts, i32p), _p(xyn, f32p))
+        return res, pts, xyn
+
     def stream_find_to_corr(self, x, y, dem, dir_map, cauce):
         """lat,lon = stream_find_to_corr(x,y,dem,dir,cauce,[nc,nf])   -- cuencas.f90:372-417"""
         d, ca = _i(dir_map), _i(cauce)

@@ -301,6 +301,26 @@ class RefCu:
         return out
 
 
+    def basin_point2var(self, basin_f, id_coord, xy_coord):
+        self._push()
+        b = _i(basin_f)
+        n = b.shape[1]
+        ids, xy = np.ascontiguousarray(id_coord, np.int32), _f(xy_coord)
+        res, pts = np.zeros(ids.size, np.int32), np.zeros(n, np.int32)
+        _call(CU, "basin_point2var", b, ids, xy, res, pts, i32(ids.size), i32(n))
+        return res, pts
+
+    def basin_stream_point2stream(self, basin_f, cauce, id_coord, xy_coord):
+        self._push()
+        b = _i(basin_f)
+        n = b.shape[1]
+        ca = np.ascontiguousarray(cauce, np.int32)
+        ids, xy = np.ascontiguousarray(id_coord, np.int32), _f(xy_coord)
+        res, pts = np.zeros(ids.size, np.int32), np.zeros(n, np.int32)
+        xyn = np.zeros((2, ids.size), np.float32, order="F")
+        _call(CU, "basin_stream_point2stream", b, ca, ids, xy, res, pts, xyn, i32(ids.size), i32(n))
+        return res, pts, xyn
+
     def stream_find_to_corr(self, x, y, dem, dir_map, cauce):
         self._push()
         de, d, ca = _f(dem), _i(dir_map), _i(cauce)

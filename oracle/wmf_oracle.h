@@ -169,6 +169,12 @@ int wo_shia_v1(const wo_shia_in *in, wo_shia_out *out);
 float wo_calc_speed(float sm, float coef, float expo, float elem_long, float *speed, float dt,
                     int32_t calc_niter);
 
+/* basin_point2var :1230-1261, basin_stream_point2stream :1524-1577 (control points onto the basin / the stream network) */
+void wo_basin_point2var(const wo_geo *g, const int32_t *basin_f, const int32_t *id_coord, const float *xy_coord, int32_t ncoord,
+                        int32_t n, int32_t *res_coord, int32_t *basin_pts);
+void wo_basin_stream_point2stream(const wo_geo *g, const int32_t *basin_f, const int32_t *cauce, const int32_t *id_coord,
+                                  const float *xy_coord, int32_t ncoord, int32_t n, int32_t *res_coord, int32_t *basin_pts,
+                                  float *xy_new);
 /* stream_find_to_corr, cuencas.f90:372-417 */
 void wo_stream_find_to_corr(const wo_geo *g, float x, float y, const int32_t *dir, const int32_t *cauce, int32_t nc, int32_t nf,
                             float *lat, float *lon);

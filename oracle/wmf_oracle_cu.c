@@ -682,3 +682,59 @@ void wo_stream_find_to_corr(const wo_geo *g, float x, float y, const int32_t *di
     }
 #undef RM
 }
+
+/* find_xy_in_basin, cuencas.f90:2659-2678: 1-based position of (col,fil) in the basin table, 0 when outside */
+static int32_t find_xy_in_basin(const int32_t *basin_f, int32_t col, int32_t fil, int32_t n)
+{
+    for (int32_t i = 0; i < n; ++i)
+        if (BF(1, i) == col && BF(2, i) == fil) return i + 1;
+    return 0;
+}
+
+/* basin_point2var, cuencas.f90:1230-1261 (basin_pts is never zeroed by the Fortran: zeros here) */
+void wo_basin_point2var(const wo_geo *g, const int32_t *basin_f, const int32_t *id_coord, const float *xy_coord, int32_t ncoord,
+                        int32_t n, int32_t *res_coord, int32_t *basin_pts)
+{
+    for (int32_t i = 0; i < n; ++i) basin_pts[i] = 0;
+    for (int32_t i = 0; i < ncoord; ++i) {
+        const float x = (xy_coord[2 * i] - g->xll) / g->dx;
+        const int32_t x_col = (int32_t)ceilf(x);
+        const float y = (float)g->nrows - (xy_coord[2 * i + 1] - g->yll) / g->dx;
+        const int32_t y_fil = (int32_t)ceilf(y);
+        const int32_t posit = find_xy_in_basin(basin_f, x_col, y_fil, n);
+        if (posit > 0) { res_coord[i] = 0; basin_pts[posit - 1] = id_coord[i]; }
+        else res_coord[i] = 1;
+    }
+}
+
+/* basin_stream_point2stream, cuencas.f90:1524-1577 */
+void wo_basin_stream_point2stream(const wo_geo *g, const int32_t *basin_f, const int32_t *cauce, const int32_t *id_coord,
+                                  const float *xy_coord, int32_t ncoord, int32_t n, int32_t *res_coord, int32_t *basin_pts,
+                                  float *xy_new)
+{
+    for (int32_t i = 0; i < n; ++i) basin_pts[i] = 0;
+    for (int32_t i = 0; i < 2 * ncoord; ++i) xy_new[i] = g->nodata;
+    for (int32_t i = 0; i < ncoord; ++i) {
+        const float x = (xy_coord[2 * i] - g->xll) / g->dx;
+        const int32_t x_col = (int32_t)ceilf(x);
+        const float y = (float)g->nrows - (xy_coord[2 * i + 1] - g->yll) / g->dx;
+        const int32_t y_fil = (int32_t)ceilf(y);
+        int32_t posit = find_xy_in_basin(basin_f, x_col, y_fil, n);
+        if (posit > 0) {
+            res_coord[i] = 1;
+            if (cauce[posit - 1] > 0) {
+                res_coord[i] = 2;
+                basin_pts[posit - 1] = id_coord[i];
+            } else {
+                while (cauce[posit - 1] == 0 && posit < n) posit = n + 1 - BF(0, posit - 1);
+                if (posit < n) { basin_pts[posit - 1] = id_coord[i]; res_coord[i] = 2; }
+            }
+        } else {
+            res_coord[i] = 0;
+        }
+        if (res_coord[i] == 2) {
+            xy_new[2 * i] = g->xll + g->dx * ((float)BF(1, posit - 1) - 0.5f);
+            xy_new[2 * i + 1] = g->yll + g->dx * ((float)(g->nrows - BF(2, posit - 1)) + 0.5f);
+        }
+    }
+}

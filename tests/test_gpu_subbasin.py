@@ -133,3 +133,25 @@ def test_stream_find_to_corr():
         assert cu.stream_find_to_corr(x, y, bs["DEM"], bs["DIR"], cauce, 120, 90) == want
         moved += want != (np.float32(x), np.float32(y))
     assert moved > 20
+
+
+def test_control_point_placement():
+    """basin_point2var / basin_stream_point2stream (cuencas.f90:1230-1261, 1524-1577) as set_Control uses them."""
+    from wmf_b200 import CuModule
+    bs = make_basin("G2", 120, 90, 4)
+    v = basin_vectors(bs)
+    oc = bs["cu"]
+    cu = CuModule()
+    geo_to(cu, bs)
+    cauce = (v["acum"] >= 40).astype(np.int32)
+    rng = np.random.default_rng(1)
+    xy = np.asfortranarray(np.vstack([rng.uniform(-100, 3700, 60), rng.uniform(-100, 2800, 60)]), dtype=np.float32)
+    xy[:, 7] = xy[:, 3]                                   # two points on one cell: the later id wins
+    ids = np.arange(101, 161, dtype=np.int32)
+    want = oc.basin_stream_point2stream(bs["basin"], cauce, ids, xy)
+    got = cu.basin_stream_point2stream(bs["basin"], cauce, ids, xy, 60, bs["n"])
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g, w)
+    assert np.bincount(want[0], minlength=3)[2] > 30 and np.bincount(want[0], minlength=3)[0] > 0
+    for g, w in zip(cu.basin_point2var(bs["basin"], ids, xy, 60, bs["n"]), oc.basin_point2var(bs["basin"], ids, xy)):
+        np.testing.assert_array_equal(g, w)

@@ -390,3 +390,20 @@ def test_fuzz_shia_against_the_reference(ref, case, tmp_path):
     for k, fl in (("mean_storage", "show_storage"), ("mean_speed", "show_mean_speed"), ("mean_retorno", "show_mean_retorno")):
         if flags.get(fl) and R.get(k) is not None:
             np.testing.assert_array_equal(np.asarray(R[k]).reshape(-1), np.asarray(O[k]).reshape(-1), err_msg=f"case {case}: {k}")
+
+
+def test_control_point_placement_oracle_is_bit_identical_to_the_reference(ref):
+    """basin_point2var (cuencas.f90:1230-1261) and basin_stream_point2stream (:1524-1577): points inside / outside the basin,
+    on and off the stream network."""
+    bs = make_basin("G2", 120, 90, 4)
+    rc, oc = pair(ref, bs)
+    v = basin_vectors(bs)
+    cauce = (v["acum"] >= 40).astype(np.int32)
+    rng = np.random.default_rng(1)
+    xy = np.asfortranarray(np.vstack([rng.uniform(-100, 3700, 60), rng.uniform(-100, 2800, 60)]), dtype=np.float32)
+    ids = np.arange(101, 161, dtype=np.int32)
+    for a, c, nm in zip(rc.basin_stream_point2stream(bs["basin"], cauce, ids, xy), oc.basin_stream_point2stream(bs["basin"], cauce, ids, xy),
+                        ("res_coord", "basin_pts", "xy_new")):
+        same(a, c, "basin_stream_point2stream " + nm)
+    for a, c, nm in zip(rc.basin_point2var(bs["basin"], ids, xy), oc.basin_point2var(bs["basin"], ids, xy), ("res_coord", "basin_pts")):
+        same(a, c, "basin_point2var " + nm)

@@ -269,6 +269,33 @@ class CuModule:
                                          C.byref(nn), C.byref(ncau)))
         return cauce, nodos, traz, nn.value, ncau.value
 
+    def basin_point2var(self, basin_f, id_coord, xy_coord, ncoord=None, nceldas=None):
+        """res_coord,basin_pts = basin_point2var(basin_f,id_coord,xy_coord,[ncoord,nceldas])   -- cuencas.f90:1230-1261"""
+        b, n, _ = self._table(basin_f)
+        c = self._push_geo()
+        ids = np.ascontiguousarray(np.asarray(id_coord).reshape(-1), np.int32)
+        xy = np.asfortranarray(xy_coord, dtype=np.float32)
+        if xy.ndim != 2 or xy.shape != (2, ids.size):
+            raise _f2py_error(f"xy_coord must have shape (2,{ids.size}), got {xy.shape}")
+        res, pts = np.empty(ids.size, np.int32), np.empty(n, np.int32)
+        c.check(c.L.wmf_basin_point2var(c.h, ptr(b), ptr(ids), ptr(xy), ids.size, n, ptr(res), ptr(pts)))
+        return res, pts
+
+    def basin_stream_point2stream(self, basin_f, cauce, id_coord, xy_coord, ncoord=None, nceldas=None):
+        """res_coord,basin_pts,xy_new = basin_stream_point2stream(basin_f,cauce,id_coord,xy_coord,[ncoord,nceldas])
+        -- cuencas.f90:1524-1577 (set_Control -> Points_Points2Stream, wmf.py:2096-2103)"""
+        b, n, _ = self._table(basin_f)
+        c = self._push_geo()
+        ca = self._vec(cauce, n, np.int32, "cauce")
+        ids = np.ascontiguousarray(np.asarray(id_coord).reshape(-1), np.int32)
+        xy = np.asfortranarray(xy_coord, dtype=np.float32)
+        if xy.ndim != 2 or xy.shape != (2, ids.size):
+            raise _f2py_error(f"xy_coord must have shape (2,{ids.size}), got {xy.shape}")
+        res, pts = np.empty(ids.size, np.int32), np.empty(n, np.int32)
+        xyn = np.empty((2, ids.size), np.float32, order="F")
+        c.check(c.L.wmf_basin_stream_point2stream(c.h, ptr(b), ptr(ca), ptr(ids), ptr(xy), ids.size, n, ptr(res), ptr(pts), ptr(xyn)))
+        return res, pts, xyn
+
     def stream_find_to_corr(self, x, y, dem, dir, cauce, nc=None, nf=None):
         """lat,lon = stream_find_to_corr(x,y,dem,dir,cauce,[nc,nf])   -- cuencas.f90:372-417 (wmf.py:2998-3000)"""
         c = self._push_geo()

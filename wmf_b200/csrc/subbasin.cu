@@ -370,6 +370,80 @@ __global__ void k_find_to_corr(const int32_t *__restrict__ dir, const int32_t *_
     out[1] = lon;
 }
 
+// find_xy_in_basin (cuencas.f90:2659-2678) for a batch of points: posit[j] = smallest 1-based index of the cell at (col,fil)
+__global__ void k_find_xy(const int32_t *__restrict__ b, int n, const int32_t *__restrict__ cf, int npts, int32_t *__restrict__ posit) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int col = b[3 * (size_t)i + 1], fil = b[3 * (size_t)i + 2];
+    for (int j = 0; j < npts; ++j)
+        if (cf[2 * j] == col && cf[2 * j + 1] == fil) atomicMin(posit + j, i + 1);
+}
+// basin_point2var (:1230-1261) / basin_stream_point2stream (:1524-1577): the points are handled in order by one thread, as
+// the Fortran does (a later point overwrites an earlier one that lands on the same cell)
+__global__ void k_points(const int32_t *__restrict__ b, const int32_t *__restrict__ cauce, const int32_t *__restrict__ ids,
+                         const int32_t *__restrict__ posit, int npts, int n, wmf_geo g, int32_t *__restrict__ res,
+                         int32_t *__restrict__ pts, float *__restrict__ xy_new) {
+    if (threadIdx.x || blockIdx.x) return;
+    for (int i = 0; i < npts; ++i) {
+        int p = posit[i] <= n ? posit[i] : 0;
+        if (!cauce) {                       // basin_point2var
+            if (p > 0) { res[i] = 0; pts[p - 1] = ids[i]; }
+            else res[i] = 1;
+            continue;
+        }
+        int r = 0;
+        if (p > 0) {
+            r = 1;
+            if (cauce[p - 1] > 0) { r = 2; pts[p - 1] = ids[i]; }
+            else {
+                while (cauce[p - 1] == 0 && p < n) p = n + 1 - b[3 * (size_t)(p - 1)];
+                if (p < n) { pts[p - 1] = ids[i]; r = 2; }
+            }
+        }
+        res[i] = r;
+        if (r == 2) {
+            xy_new[2 * i] = g.xll + g.dx * ((float)b[3 * (size_t)(p - 1) + 1] - 0.5f);
+            xy_new[2 * i + 1] = g.yll + g.dx * ((float)(g.nrows - b[3 * (size_t)(p - 1) + 2]) + 0.5f);
+        } else {
+            xy_new[2 * i] = g.nodata;
+            xy_new[2 * i + 1] = g.nodata;
+        }
+    }
+}
+// column / row of every point: x_col = ceiling((x-xll)/dx), y_fil = ceiling(nrows - (y-yll)/dx), in fp32 as the Fortran
+__global__ void k_point_colfil(const float *__restrict__ xy, int npts, wmf_geo g, int32_t *__restrict__ cf, int32_t *__restrict__ posit) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= npts) return;
+    cf[2 * j] = (int32_t)ceilf((xy[2 * j] - g.xll) / g.dx);
+    cf[2 * j + 1] = (int32_t)ceilf((float)g.nrows - (xy[2 * j + 1] - g.yll) / g.dx);
+    posit[j] = 0x7fffffff;
+}
+
+int points_run(wmf_ctx *ctx, const int32_t *basin_f, const int32_t *cauce, const int32_t *id_coord, const float *xy_coord, int32_t ncoord,
+               int32_t n, int32_t *res_coord, int32_t *basin_pts, float *xy_new, bool stream) {
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    const int32_t *d_b, *d_ca = nullptr, *d_id;
+    const float *d_xy;
+    int32_t *d_res, *d_pts, *cf, *posit;
+    float *d_new = nullptr;
+    WMF_TRY(sc.in(basin_f, (size_t)3 * n, &d_b));
+    if (stream) WMF_TRY(sc.in(cauce, (size_t)n, &d_ca));
+    WMF_TRY(sc.in(id_coord, (size_t)ncoord, &d_id));
+    WMF_TRY(sc.in(xy_coord, (size_t)2 * ncoord, &d_xy));
+    WMF_TRY(sc.out(res_coord, (size_t)ncoord, &d_res));
+    WMF_TRY(sc.out(basin_pts, (size_t)n, &d_pts));
+    if (stream) WMF_TRY(sc.out(xy_new, (size_t)2 * ncoord, &d_new));
+    if (stream && !d_new) WMF_TRY(sc.alloc(&d_new, (size_t)2 * ncoord));
+    WMF_TRY(sc.alloc(&cf, (size_t)2 * ncoord));
+    WMF_TRY(sc.alloc(&posit, (size_t)ncoord));
+    CU_TRY(ctx, cudaMemsetAsync(d_pts, 0, sizeof(int32_t) * (size_t)n, ctx->stream));
+    LAUNCH(ctx, k_point_colfil, grid_for(ncoord, 128), 128, 0, d_xy, ncoord, ctx->geo, cf, posit);
+    LAUNCH(ctx, k_find_xy, grid_for(n, 256), 256, 0, d_b, n, cf, ncoord, posit);
+    LAUNCH(ctx, k_points, 1, 32, 0, d_b, d_ca, d_id, posit, ncoord, n, ctx->geo, d_res, d_pts, d_new);
+    return sc.finish();
+}
+
 }  // namespace
 
 int wmf_hill_groups(wmf_ctx *ctx, Scope &sc, const int32_t *sub_pert, const int32_t *cauce, int n, int n_hills, int32_t **order,
@@ -623,6 +697,24 @@ int wmf_basin_stream_slope(wmf_ctx *ctx, const int32_t *basin_f, const float *ba
     LAUNCH(ctx, k_ss_stale, G, 256, 0, d_b, d_n, reach, lastscan, n, owner);
     LAUNCH(ctx, k_ss_write, G, 256, 0, owner, reach, n, d_ss, d_sl);
     return sc.finish();
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int wmf_basin_point2var(wmf_ctx *ctx, const int32_t *basin_f, const int32_t *id_coord, const float *xy_coord, int32_t ncoord,
+                        int32_t nceldas, int32_t *res_coord, int32_t *basin_pts) {
+    if (!ctx || !basin_f || !id_coord || !xy_coord || !res_coord || !basin_pts || ncoord <= 0 || nceldas <= 0) return WMF_ERR_ARG;
+    return points_run(ctx, basin_f, nullptr, id_coord, xy_coord, ncoord, nceldas, res_coord, basin_pts, nullptr, false);
+}
+
+int wmf_basin_stream_point2stream(wmf_ctx *ctx, const int32_t *basin_f, const int32_t *cauce, const int32_t *id_coord,
+                                  const float *xy_coord, int32_t ncoord, int32_t nceldas, int32_t *res_coord, int32_t *basin_pts,
+                                  float *xy_new) {
+    if (!ctx || !basin_f || !cauce || !id_coord || !xy_coord || !res_coord || !basin_pts || !xy_new || ncoord <= 0 || nceldas <= 0)
+        return WMF_ERR_ARG;
+    return points_run(ctx, basin_f, cauce, id_coord, xy_coord, ncoord, nceldas, res_coord, basin_pts, xy_new, true);
 }
 
 }  // extern "C"
