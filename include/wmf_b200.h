@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define WMF_ABI_VERSION 12
+#define WMF_ABI_VERSION 13
 
 enum {
     WMF_OK = 0,
@@ -131,6 +131,11 @@ int wmf_basin_point2var(wmf_ctx *ctx, const int32_t *basin_f, const int32_t *id_
 int wmf_basin_stream_point2stream(wmf_ctx *ctx, const int32_t *basin_f, const int32_t *cauce, const int32_t *id_coord,
                                   const float *xy_coord, int32_t ncoord, int32_t nceldas, int32_t *res_coord,
                                   int32_t *basin_pts, float *xy_new);
+/* basin_stream_sections, cuencas.f90:1464-1523: the cross sections HydroFlash reads (GetGeo_Sections, wmf.py:1564-1587):
+ * secciones / secciones_cel (2*num_celdas+1, nceldas); dem is the (ncols,nrows) raster */
+int wmf_basin_stream_sections(wmf_ctx *ctx, const int32_t *basin_f, const int32_t *cauces, const int32_t *directions,
+                              const float *dem, int32_t num_celdas, int32_t nceldas, int32_t ncols, int32_t nrows,
+                              float *secciones, int32_t *secciones_cel);
 /* stream_find_to_corr, cuencas.f90:372-417 (SimuBasin.__init__ with useCauceMap, wmf.py:2998-3000) */
 int wmf_stream_find_to_corr(wmf_ctx *ctx, float x, float y, const int32_t *dir, const int32_t *cauce, int32_t nc,
                             int32_t nf, float *lat, float *lon);

@@ -337,6 +337,19 @@ class Cu:
                                              _p(res, i32p), _p(pts, i32p), _p(xyn, f32p))
         return res, pts, xyn
 
+    def basin_stream_sections(self, basin_f, cauces, directions, dem, num_celdas):
+        """secciones,secciones_cel = basin_stream_sections(basin_f,cauces,directions,dem,num_celdas,[nceldas,ncols,nrows])
+        -- cuencas.f90:1464-1523"""
+        b = _i(basin_f)
+        n = b.shape[1]
+        ca, di = np.ascontiguousarray(cauces, np.int32), np.ascontiguousarray(directions, np.int32)
+        d = _f(dem)
+        S = 2 * int(num_celdas) + 1
+        sec, cel = np.zeros((S, n), np.float32, order="F"), np.zeros((S, n), np.int32, order="F")
+        self._L.wo_basin_stream_sections(_p(b, i32p), _p(ca, i32p), _p(di, i32p), _p(d, f32p), int(num_celdas), n, d.shape[0],
+                                         d.shape[1], _p(sec, f32p), _p(cel, i32p))
+        return sec, cel
+
     def stream_find_to_corr(self, x, y, dem, dir_map, cauce):
         """lat,lon = stream_find_to_corr(x,y,dem,dir,cauce,[nc,nf])   -- cuencas.f90:372-417"""
         d, ca = _i(dir_map), _i(cauce)

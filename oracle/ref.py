@@ -321,6 +321,16 @@ class RefCu:
         _call(CU, "basin_stream_point2stream", b, ca, ids, xy, res, pts, xyn, i32(ids.size), i32(n))
         return res, pts, xyn
 
+    def basin_stream_sections(self, basin_f, cauces, directions, dem, num_celdas):
+        b = _i(basin_f)
+        n = b.shape[1]
+        ca, di = np.ascontiguousarray(cauces, np.int32), np.ascontiguousarray(directions, np.int32)
+        d = _f(dem)
+        S = 2 * int(num_celdas) + 1
+        sec, cel = np.zeros((S, n), np.float32, order="F"), np.zeros((S, n), np.int32, order="F")
+        _call(CU, "basin_stream_sections", b, ca, di, d, i32(int(num_celdas)), i32(n), i32(d.shape[0]), i32(d.shape[1]), sec, cel)
+        return sec, cel
+
     def stream_find_to_corr(self, x, y, dem, dir_map, cauce):
         self._push()
         de, d, ca = _f(dem), _i(dir_map), _i(cauce)

@@ -175,6 +175,9 @@ void wo_basin_point2var(const wo_geo *g, const int32_t *basin_f, const int32_t *
 void wo_basin_stream_point2stream(const wo_geo *g, const int32_t *basin_f, const int32_t *cauce, const int32_t *id_coord,
                                   const float *xy_coord, int32_t ncoord, int32_t n, int32_t *res_coord, int32_t *basin_pts,
                                   float *xy_new);
+/* basin_stream_sections, cuencas.f90:1464-1523 */
+void wo_basin_stream_sections(const int32_t *basin_f, const int32_t *cauces, const int32_t *directions, const float *dem,
+                              int32_t num_celdas, int32_t n, int32_t ncols, int32_t nrows, float *secciones, int32_t *secciones_cel);
 /* stream_find_to_corr, cuencas.f90:372-417 */
 void wo_stream_find_to_corr(const wo_geo *g, float x, float y, const int32_t *dir, const int32_t *cauce, int32_t nc, int32_t nf,
                             float *lat, float *lon);

@@ -738,3 +738,40 @@ void wo_basin_stream_point2stream(const wo_geo *g, const int32_t *basin_f, const
         }
     }
 }
+
+/* basin_stream_sections, cuencas.f90:1464-1523: for every channel cell a cross section of 2*num_celdas+1 raster cells
+ * perpendicular-ish to its flow direction: elevations and the basin positions of those cells (0 = not in the basin,
+ * -9999 = outside the map).  find_xy_in_basin is answered from a raster lookup built once (same result, first match). */
+void wo_basin_stream_sections(const int32_t *basin_f, const int32_t *cauces, const int32_t *directions, const float *dem,
+                              int32_t num_celdas, int32_t n, int32_t ncols, int32_t nrows, float *secciones, int32_t *secciones_cel)
+{
+    const int32_t S = 2 * num_celdas + 1;
+    int32_t *look = (int32_t *)calloc((size_t)ncols * nrows, sizeof(int32_t));
+    for (int32_t i = n - 1; i >= 0; --i) {
+        const int32_t c = BF(1, i), f = BF(2, i);
+        if (c >= 1 && c <= ncols && f >= 1 && f <= nrows) look[(size_t)(f - 1) * ncols + (c - 1)] = i + 1;
+    }
+    for (size_t k = 0; k < (size_t)S * n; ++k) { secciones[k] = 0.0f; secciones_cel[k] = 0; }
+    for (int32_t i = 0; i < n; ++i) {
+        if (cauces[i] != 1) continue;
+        int32_t colMov = 0, filMov = 0;
+        const int32_t d = directions[i];
+        if (d == 4 || d == 6) filMov = 1;
+        else if (d == 8 || d == 2) colMov = 1;
+        else if (d == 7 || d == 3) { colMov = 1; filMov = -1; }
+        else if (d == 1 || d == 9) { colMov = 1; filMov = 1; }
+        const int32_t col = BF(1, i), fil = BF(2, i);
+        int32_t cont = 0;
+        for (int32_t j = -num_celdas; j <= num_celdas; ++j, ++cont) {
+            const int32_t c = col + j * colMov, f = fil + j * filMov;
+            if (c >= 1 && c <= ncols && f >= 1 && f <= nrows) {
+                secciones[(size_t)S * i + cont] = dem[(size_t)(f - 1) * ncols + (c - 1)];
+                secciones_cel[(size_t)S * i + cont] = look[(size_t)(f - 1) * ncols + (c - 1)];
+            } else {
+                secciones[(size_t)S * i + cont] = -9999.0f;
+                secciones_cel[(size_t)S * i + cont] = -9999;
+            }
+        }
+    }
+    free(look);
+}

@@ -155,3 +155,17 @@ def test_control_point_placement():
     assert np.bincount(want[0], minlength=3)[2] > 30 and np.bincount(want[0], minlength=3)[0] > 0
     for g, w in zip(cu.basin_point2var(bs["basin"], ids, xy, 60, bs["n"]), oc.basin_point2var(bs["basin"], ids, xy)):
         np.testing.assert_array_equal(g, w)
+
+
+def test_stream_sections():
+    """basin_stream_sections (cuencas.f90:1464-1523): the HydroFlash cross sections, bit-exact."""
+    from wmf_b200 import CuModule
+    bs = make_basin("G2", 90, 70, 6)
+    v = basin_vectors(bs)
+    cu = CuModule()
+    geo_to(cu, bs)
+    cauce = (v["acum"] >= 30).astype(np.int32)
+    want = bs["cu"].basin_stream_sections(bs["basin"], cauce, v["dirv"], bs["DEM"], 4)
+    got = cu.basin_stream_sections(bs["basin"], cauce, v["dirv"], bs["DEM"], 4, bs["n"], 90, 70)
+    np.testing.assert_array_equal(got[0], want[0])
+    np.testing.assert_array_equal(got[1], want[1])

@@ -407,3 +407,16 @@ def test_control_point_placement_oracle_is_bit_identical_to_the_reference(ref):
         same(a, c, "basin_stream_point2stream " + nm)
     for a, c, nm in zip(rc.basin_point2var(bs["basin"], ids, xy), oc.basin_point2var(bs["basin"], ids, xy), ("res_coord", "basin_pts")):
         same(a, c, "basin_point2var " + nm)
+
+
+def test_stream_sections_oracle_is_bit_identical_to_the_reference(ref):
+    """basin_stream_sections (cuencas.f90:1464-1523), the cross sections HydroFlash reads."""
+    bs = make_basin("G2", 90, 70, 6)
+    rc, oc = pair(ref, bs)
+    v = basin_vectors(bs)
+    cauce = (v["acum"] >= 30).astype(np.int32)
+    for num in (2, 4):
+        r, o = rc.basin_stream_sections(bs["basin"], cauce, v["dirv"], bs["DEM"], num), oc.basin_stream_sections(bs["basin"], cauce, v["dirv"], bs["DEM"], num)
+        same(r[0], o[0], "secciones")
+        same(r[1], o[1], "secciones_cel")
+        assert (o[1] == -9999).any() and (o[1] > 0).any()

@@ -296,6 +296,18 @@ class CuModule:
         c.check(c.L.wmf_basin_stream_point2stream(c.h, ptr(b), ptr(ca), ptr(ids), ptr(xy), ids.size, n, ptr(res), ptr(pts), ptr(xyn)))
         return res, pts, xyn
 
+    def basin_stream_sections(self, basin_f, cauces, directions, dem, num_celdas, nceldas=None, ncols=None, nrows=None):
+        """secciones,secciones_cel = basin_stream_sections(basin_f,cauces,directions,dem,num_celdas,[nceldas,ncols,nrows])
+        -- cuencas.f90:1464-1523 (GetGeo_Sections, wmf.py:1585-1587)"""
+        b, n, _ = self._table(basin_f)
+        c = self.ctx
+        ca, di = self._vec(cauces, n, np.int32, "cauces"), self._vec(directions, n, np.int32, "directions")
+        d, ncc, nrr = self._raster(dem, np.float32, "dem")
+        S = 2 * int(num_celdas) + 1
+        sec, cel = np.empty((S, n), np.float32, order="F"), np.empty((S, n), np.int32, order="F")
+        c.check(c.L.wmf_basin_stream_sections(c.h, ptr(b), ptr(ca), ptr(di), ptr(d), int(num_celdas), n, ncc, nrr, ptr(sec), ptr(cel)))
+        return sec, cel
+
     def stream_find_to_corr(self, x, y, dem, dir, cauce, nc=None, nf=None):
         """lat,lon = stream_find_to_corr(x,y,dem,dir,cauce,[nc,nf])   -- cuencas.f90:372-417 (wmf.py:2998-3000)"""
         c = self._push_geo()

@@ -99,7 +99,7 @@ EXPORTS = [
     "wmf_calc_speed", "wmf_last_kernel_ms", "wmf_last_shia_stats", "wmf_rain_idw", "wmf_rain_mit", "wmf_rain_pre_mit",
     "wmf_basin_subbasin_nod", "wmf_basin_subbasin_cut", "wmf_basin_subbasin_find", "wmf_basin_subbasin_horton",
     "wmf_basin_subbasin_long", "wmf_basin_subbasin_stream_prop", "wmf_basin_subbasin_map2subbasin", "wmf_basin_stream_slope", "wmf_stream_find_to_corr",
-    "wmf_basin_point2var", "wmf_basin_stream_point2stream",
+    "wmf_basin_point2var", "wmf_basin_stream_point2stream", "wmf_basin_stream_sections",
 ]
 
 _lib = None
@@ -162,6 +162,7 @@ def load() -> C.CDLL:
     L.wmf_basin_stream_slope.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
     L.wmf_basin_point2var.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
     L.wmf_basin_stream_point2stream.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]
+    L.wmf_basin_stream_sections.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]
     L.wmf_stream_find_to_corr.argtypes = [vp, f32, f32, vp, vp, i32, i32, f32p, f32p]
     L.wmf_rain_pre_mit.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
     L.wmf_rain_idw.argtypes = [vp, vp, vp, vp, f32, i32, i32, i32, f32, vp, i32, vp, vp, i32p, vp, i32]

@@ -419,6 +419,45 @@ __global__ void k_point_colfil(const float *__restrict__ xy, int npts, wmf_geo g
     posit[j] = 0x7fffffff;
 }
 
+// basin_stream_sections, cuencas.f90:1464-1523: raster lookup of the basin positions (first match = smallest index), then one
+// thread per (cell, sample of the cross section)
+__global__ void k_sec_lookup(const int32_t *__restrict__ b, int n, int nc, int nr, int32_t *__restrict__ look) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = b[3 * (size_t)i + 1], f = b[3 * (size_t)i + 2];
+    if (c >= 1 && c <= nc && f >= 1 && f <= nr) atomicMin(look + (size_t)(f - 1) * nc + (c - 1), i + 1);
+}
+__global__ void k_sections(const int32_t *__restrict__ b, const int32_t *__restrict__ cauces, const int32_t *__restrict__ dirs,
+                           const float *__restrict__ dem, const int32_t *__restrict__ look, int num, int n, int nc, int nr,
+                           float *__restrict__ sec, int32_t *__restrict__ cel) {
+    const int S = 2 * num + 1;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)n * S) return;
+    const int i = (int)(g / S), k = (int)(g % S);
+    float e = 0.0f;
+    int p = 0;
+    if (cauces[i] == 1) {
+        int colMov = 0, filMov = 0;
+        const int d = dirs[i];
+        if (d == 4 || d == 6) filMov = 1;
+        else if (d == 8 || d == 2) colMov = 1;
+        else if (d == 7 || d == 3) { colMov = 1; filMov = -1; }
+        else if (d == 1 || d == 9) { colMov = 1; filMov = 1; }
+        const int j = k - num;
+        const int c = b[3 * (size_t)i + 1] + j * colMov, f = b[3 * (size_t)i + 2] + j * filMov;
+        if (c >= 1 && c <= nc && f >= 1 && f <= nr) {
+            e = dem[(size_t)(f - 1) * nc + (c - 1)];
+            const int l = look[(size_t)(f - 1) * nc + (c - 1)];
+            p = (l == 0x7f7f7f7f) ? 0 : l;
+        } else {
+            e = -9999.0f;
+            p = -9999;
+        }
+    }
+    sec[g] = e;
+    cel[g] = p;
+}
+
 int points_run(wmf_ctx *ctx, const int32_t *basin_f, const int32_t *cauce, const int32_t *id_coord, const float *xy_coord, int32_t ncoord,
                int32_t n, int32_t *res_coord, int32_t *basin_pts, float *xy_new, bool stream) {
     CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -718,3 +757,26 @@ int wmf_basin_stream_point2stream(wmf_ctx *ctx, const int32_t *basin_f, const in
 }
 
 }  // extern "C"
+
+extern "C" int wmf_basin_stream_sections(wmf_ctx *ctx, const int32_t *basin_f, const int32_t *cauces, const int32_t *directions,
+                                         const float *dem, int32_t num_celdas, int32_t nceldas, int32_t ncols, int32_t nrows,
+                                         float *secciones, int32_t *secciones_cel) {
+    if (!ctx || !basin_f || !cauces || !directions || !dem || !secciones || !secciones_cel || num_celdas < 0 || nceldas <= 0 ||
+        ncols <= 0 || nrows <= 0)
+        return WMF_ERR_ARG;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    Scope sc(ctx);
+    const int S = 2 * num_celdas + 1, n = nceldas;
+    const int32_t *d_b, *d_c, *d_d;
+    const float *d_dem;
+    float *d_s;
+    int32_t *d_p, *look;
+    WMF_TRY(sc.in(basin_f, (size_t)3 * n, &d_b)); WMF_TRY(sc.in(cauces, (size_t)n, &d_c)); WMF_TRY(sc.in(directions, (size_t)n, &d_d));
+    WMF_TRY(sc.in(dem, (size_t)ncols * nrows, &d_dem));
+    WMF_TRY(sc.out(secciones, (size_t)S * n, &d_s)); WMF_TRY(sc.out(secciones_cel, (size_t)S * n, &d_p));
+    WMF_TRY(sc.alloc(&look, (size_t)ncols * nrows));
+    CU_TRY(ctx, cudaMemsetAsync(look, 0x7f, sizeof(int32_t) * (size_t)ncols * nrows, ctx->stream));   // 0x7f7f7f7f: "no cell yet"
+    LAUNCH(ctx, k_sec_lookup, grid_for(n, 256), 256, 0, d_b, n, ncols, nrows, look);
+    LAUNCH(ctx, k_sections, grid_for((int64_t)n * S, 256), 256, 0, d_b, d_c, d_d, d_dem, look, num_celdas, n, ncols, nrows, d_s, d_p);
+    return sc.finish();
+}
