@@ -1,26 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the SHIA/TETIS hot path (BASELINE.json configs[1], "C2").
+"""bench.py -- the reference's headline metric on B200: "Mcell/s D8 flow-acc; SHIA cell-steps/s (ensemble) at 1/2/4/8 B200
+vs host CPU" (BASELINE.json).
 
     python bench.py --gpus N --steps K --warmup W             # our CUDA path, one rank per GPU (torchrun for N>1)
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm on the host cores
 
-A "step" is one complete SHIA run (modelosv2.f90:191-869): ~1M-cell synthetic basin x 1000 hourly steps of
-synthetic rainfall, i.e. ~1.04e9 cell-steps.  With N>1 every rank runs the same basin with its own calibration
-set (one ensemble member per GPU -- the path shards by member, no data-path collective) and the per-member
-objective scores are gathered over NCCL; value = N * cell-steps / max-over-ranks time  ("weak" scaling).
+Headline workload (every N): **C4**, BASELINE.json configs[3] -- an NSGA-II calibration population on the ~250k-cell basin
+(512 x 512 G2 raster, 260 100 cells), 1000 hourly steps, 512 parameter sets PER GPU (weak scaling: 8 GPUs = the 4096-member
+target), evaluated through the public multi-GPU call `wmf_b200.ensemble.evaluate_population` (the replacement of
+wmf.py:872-878 `__ejec_parallel__` + `__eval_nash__`/`__eval_q_pico__`): members shard over the ranks with no data-path
+collective, the per-member scores are all-gathered over NCCL.  A "step" is one evaluation of the whole population.
 
 Numbers on the JSON line
-  value      cell-steps/s, inputs resident in HBM, timed with CUDA events on the launch stream
-  e2e        the same run through the public drop-in call models.shia_v1(...) with HOST (pinned) buffers:
-             host->device copies of every input and device->host reads of every output are inside the timed region
-  roofline   dominant kernel k_shia_tb (time-blocked wavefront): algorithmic bytes (144 B/cell-step, SURVEY 8d /
-             DESIGN.md) / CUDA-event time of the wave launches, against the measured HBM copy bandwidth
-             (MEASURED_PEAKS.json).  The kernel keeps a cell's state in registers for K steps and its per-step
-             traffic is served from L2, so its DRAM traffic (`traffic`, from ncu) is well below the algorithmic bytes.
-  cpu_baseline  the reference's own compiled Fortran (oracle/_ref: the gfortran -O3 -funroll-loops objects shipped in
-             the reference tree, kind "reference"; the oracle's C port when that library is absent), 1 thread as the
-             reference runs, on a bounded sample
-  extra      Path A (basin_find+basin_cut+basin_acum) Mcell/s on the same raster, and run statistics
+  value      member-cell-steps/s = ranks x members x cells x steps / max-over-ranks time; rain and maps resident in HBM;
+             timed with CUDA events on the launch stream
+  e2e        the same call with HOST inputs (pinned rain table, numpy maps): every rank uploads 1/N of the rain records
+             and the ranks all-gather the rest over NVLink; scores come back to the host.  Copies inside the timed region.
+  roofline   dominant kernel k_shia_tb<K,...> (time-blocked wavefront, member-minor layout): algorithmic bytes
+             (80 B per member-cell-step, SURVEY 8d / DESIGN.md) / CUDA-event time of the wave launches, against the
+             measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the reference's own compiled Fortran (oracle/_ref, kind "reference"; the oracle's C port when that library
+             is absent) running whole members of the same population on ONE core; the hydrographs it produces are compared
+             with the GPU's inside the bench (`extra.parity_vs_cpu`)
+  extra      c2: the single-basin run of BASELINE configs[1] (1 044 484 cells x 1000 steps, 144 B/cell-step roofline, its
+             own e2e through models.shia_v1 with host buffers) -- N=1 only;
+             path_a: "Mcell/s D8 flow-acc" on C1 (512 x 512) and C3 (20000 x 20000): basin_find + basin_cut + basin_acum,
+             per-call ms, levels, roofline at 28 B/cell, cpu_baseline of the reference on the same raster, bit-exactness
+`--workload c2 | c5` make the single-basin run (C5: SED sediments + landslides) the headline instead.
 """
 from __future__ import annotations
 
@@ -29,6 +35,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -37,53 +44,72 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BYTES_PER_CELL_STEP = 144.0      # algorithmic bytes of one cell-step of a single run
-# dram__bytes_read.sum + dram__bytes_write.sum per k_shia_tb launch from the ncu --set full capture under profiles/
-# (cold-cache replay of a mid-run wave, 1.33e6 cell-steps in that launch); None until a capture exists
-TRAFFIC_PER_LAUNCH = 60.0e6
-TRAFFIC_NOTE = ("ncu --set full, one mid-run launch of 1359 CTAs = 1.33e6 cell-steps (cold-cache replay): 56.5 MB read + 3.5 MB "
-                "written = 45 B per cell-step against 144 algorithmic; see profiles/README.md")
-WORKLOADS = {
-    # name: (ncols, nrows, steps, generator)
-    "c2": (1024, 1024, 1000, "G2"),      # BASELINE.json configs[1]
-    "c2-small": (258, 258, 200, "G2"),   # smoke-sized variant for quick checks
-    "c5": (1448, 1448, 288, "G2"),       # BASELINE.json configs[4] basin: ~2.1 M cells, 12 m, 5-minute steps (tools/profile_shia.py)
+# algorithmic bytes
+BYTES_PER_CELL_STEP = 144.0            # one cell-step of a single run
+BYTES_PER_MEMBER_CELL_STEP = 80.0      # one member-cell-step of an ensemble (statics amortised over the members of a cell)
+BYTES_SED, BYTES_SLIDES = 120.0, 28.0  # what the sediment / landslide sub-models add per cell-step
+BYTES_PER_CELL_PATH_A = 28.0           # basin_find + basin_cut 16 B, basin_acum 12 B per basin cell
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the ncu --set full captures under
+# profiles/ (cold-cache replay of one mid-run launch); None until a capture exists
+TRAFFIC = {
+    "single": (60.0e6, "ncu --set full, one mid-run launch of k_shia_tb<4,...> on C2 = 1.33e6 cell-steps (cold-cache replay): "
+                       "56.5 MB read + 3.5 MB written = 45 B per cell-step against 144 algorithmic; profiles/README.md"),
+    "ensemble": (None, "no ncu capture of the member-minor variant yet"),
 }
-# per-workload overrides of (cell size [m], time step [s], unit-type thresholds on acum)
-WORKLOAD_GEO = {"c5": (12.0, 300.0, (200, 2000))}
+WORKLOADS = {
+    # BASELINE.json configs[3]: calibration ensemble on the ~250k-cell basin
+    "c4": dict(nc=512, nr=512, T=1000, kind="ensemble", members=512, batch=256),
+    "c4-small": dict(nc=130, nr=130, T=120, kind="ensemble", members=16, batch=8),
+    # BASELINE.json configs[1]: one basin, one run
+    "c2": dict(nc=1024, nr=1024, T=1000, kind="single"),
+    "c2-small": dict(nc=258, nr=258, T=200, kind="single"),
+    # BASELINE.json configs[4] basin: ~2.1 M cells, 12 m, 5-minute steps, kinematic hillslopes, sediments + landslides
+    "c5": dict(nc=1448, nr=1448, T=288, kind="single", dx=12.0, dt=300.0, thresholds=(200, 2000), speed_type=(2, 2, 1),
+               sediments=True, slides=True),
+}
 DX = 30.0
 
 
+def wl_cfg(name):
+    c = dict(gen="G2", dx=DX, dt=3600.0, thresholds=(30, 500), speed_type=(1, 1, 1), sediments=False, slides=False)
+    c.update(WORKLOADS[name])
+    return c
+
+
 def peaks():
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured"
-    except Exception:
-        return 6650.0, "fallback"
+    """(HBM GB/s, how) -- MEASURED_PEAKS.json when the driver wrote it, else the profiling guide's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (torch copy, read+write bytes)"
+        except Exception:
+            pass
+    return 6300.0, "fallback: B200_PROFILING.md measured copy bandwidth"
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
-
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi SM clock + throttle reasons sampled during the timed region (the profiling recipe's clocks line)."""
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.th = index, [], None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,clocks_throttle_reasons.hw_slowdown,"
+                 "clocks_throttle_reasons.hw_thermal_slowdown,clocks_throttle_reasons.sw_thermal_slowdown,"
+                 "clocks_throttle_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
+            return
+        self.th = threading.Thread(target=self._read, daemon=True)
+        self.th.start()
 
     def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
 
     def stop(self):
         if not self.proc:
@@ -94,83 +120,122 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        mhz = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        mhz, mx = [], []
+        for r in self.rows:
+            try:
+                mhz.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                pass
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith("active")})
         return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(mhz)}
 
 
+def trace_basin(cu, DIR, DEM, nc, nr, dx):
+    """basin_find -> basin_cut -> map2basin -> basin_basics with the module object ``cu`` (ours, or the CPU reference's)."""
+    from wmf_b200 import synth
+    cu.ncols, cu.nrows, cu.xll, cu.yll, cu.dx, cu.dy, cu.dxp, cu.nodata = nc, nr, 0.0, 0.0, dx, dx, dx, synth.NODATA
+    x, y = synth.outlet_xy(nc, nr, 0.0, 0.0, dx)
+    n = cu.basin_find(x, y, DIR, nc, nr) if hasattr(cu, "ctx") else cu.basin_find(x, y, DIR)
+    b = cu.basin_cut(n)
+    dv = cu.basin_map2basin(b, DIR.astype(np.float32), 0.0, 0.0, dx, dx, synth.NODATA).astype(np.int32)
+    de = cu.basin_map2basin(b, DEM, 0.0, 0.0, dx, dx, synth.NODATA)
+    acum, lng, pend, _ = cu.basin_basics(b, de, dv)
+    return x, y, n, b, acum, lng, pend
+
+
+def make_inputs(cfg, b, acum, lng, pend, T=None):
+    from wmf_b200 import synth
+    return synth.make_shia_inputs(b, acum, lng, pend, dxp=cfg["dx"], dt=cfg["dt"], n_reg=T or cfg["T"], seed=0,
+                                  thresholds=cfg["thresholds"], speed_type=cfg["speed_type"], n_control=16,
+                                  sediments=cfg["sediments"], slides=cfg["slides"])
+
+
 def build_workload(name: str, cu, rank: int = 0, verbose: bool = False):
     """Synthetic basin + SHIA inputs of workload ``name``; the topology is traced with OUR Path-A kernels."""
     from wmf_b200 import synth
-    nc, nr, T, gen = WORKLOADS[name]
-    DX, dt, thresholds = WORKLOAD_GEO.get(name, (30.0, 3600.0, (30, 500)))
+    cfg = wl_cfg(name)
+    nc, nr, T = cfg["nc"], cfg["nr"], cfg["T"]
     t0 = time.time()
-    DIR, DEM = synth.make_raster(gen, nc, nr, seed=0)
-    cu.ncols, cu.nrows, cu.xll, cu.yll, cu.dx, cu.dy, cu.dxp, cu.nodata = nc, nr, 0.0, 0.0, DX, DX, DX, synth.NODATA
-    x, y = synth.outlet_xy(nc, nr, 0.0, 0.0, DX)
-    n = cu.basin_find(x, y, DIR, nc, nr)
-    b = cu.basin_cut(n)
-    dv = cu.basin_map2basin(b, DIR.astype(np.float32), 0.0, 0.0, DX, DX, synth.NODATA).astype(np.int32)
-    de = cu.basin_map2basin(b, DEM, 0.0, 0.0, DX, DX, synth.NODATA)
-    acum, lng, pend, _ = cu.basin_basics(b, de, dv)
-    inp = synth.make_shia_inputs(b, acum, lng, pend, dxp=DX, dt=dt, n_reg=T, seed=0, thresholds=thresholds,
-                                 speed_type=(1, 1, 1), n_control=16)
+    DIR, DEM = synth.make_raster(cfg["gen"], nc, nr, seed=0)
+    x, y, n, b, acum, lng, pend = trace_basin(cu, DIR, DEM, nc, nr, cfg["dx"])
+    inp = make_inputs(cfg, b, acum, lng, pend)
     if verbose:
         print(f"[bench] workload {name}: {n} cells, {T} steps, {inp['rain'].shape[0]} rain records, "
               f"built in {time.time() - t0:.1f}s", file=sys.stderr)
-    return dict(DIR=DIR, DEM=DEM, x=x, y=y, n=n, basin=b, inp=inp, T=T, nc=nc, nr=nr)
+    return dict(name=name, cfg=cfg, DIR=DIR, DEM=DEM, x=x, y=y, n=n, basin=b, inp=inp, T=T, nc=nc, nr=nr)
 
 
-def bench_path_a(cu, wl, reps=3):
-    """Mcell/s of basin_find + basin_cut + basin_acum with DIR resident in HBM (extra, not the headline)."""
-    import torch
-    d_dir = torch.from_numpy(np.ascontiguousarray(wl["DIR"].T)).cuda()
-    best = None
-    for _ in range(reps):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        n = cu.basin_find(wl["x"], wl["y"], d_dir)
-        b = cu.basin_cut(n, resident=True)
-        acum = cu.basin_acum(b)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    assert int(acum[-1].item()) == n
-    return {"path_a_mcell_per_s": n / best / 1e6, "path_a_ms": best * 1e3, "path_a_cells": n,
-            "path_a_levels": cu.basin_find_depth(), "path_a_workload": f"{wl['nc']}x{wl['nr']} G2 raster, find+cut+acum"}
-
-
-def bench_gauges_chain(cu, m, wl, n_cont, reps=2):
-    """Extra: the workflow that starts from rain gauges -- rain_idw on the GPU (record table stays in HBM) followed by the
-    SHIA run on it: what replaces rain_interpolate_idw + run_shia (wmf.py:3395-3420, 4337-4641) without any rain field
-    crossing PCIe."""
+# ---------------------------------------------------------------------------------------------------------------------
+# Path A: "Mcell/s D8 flow-acc"
+# ---------------------------------------------------------------------------------------------------------------------
+def bench_path_a(cu, nc, nr, reps=3, cpu=True, gen="G2", seed=0):
+    """basin_find + basin_cut + basin_acum on a ``nc x nr`` raster resident in HBM: Mcell/s, per-call ms, roofline at
+    28 B/cell, and -- ``cpu`` -- the reference's CPU path on the same raster with a bit-exactness check of both tables."""
     import torch
     from wmf_b200 import synth
-    cx, cy = cu.basin_coordxy(wl["basin"])
-    xy = np.asfortranarray(np.vstack([cx, cy]), dtype=np.float32)
-    coord, rain = synth.make_stations(wl["nc"], wl["nr"], float(cu.dx), 46, wl["T"], 0)
-    inp, n = wl["inp"], wl["n"]
-    saved = object.__getattribute__(m, "__dict__")["_rain_mem"]
-    best_i = best_c = None
-    for _ in range(reps + 1):
+    dev = f"cuda:{cu.ctx.device}"
+    d_dir = synth.make_dir_torch(gen, nc, nr, seed, device=dev)
+    cu.ncols, cu.nrows, cu.xll, cu.yll, cu.dx, cu.dy, cu.dxp, cu.nodata = nc, nr, 0.0, 0.0, DX, DX, DX, synth.NODATA
+    x, y = synth.outlet_xy(nc, nr, 0.0, 0.0, DX)
+    best = None
+    for _ in range(reps + 1):                      # first pass warms the memory pools
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        m.rain_idw(xy, coord, rain, 2.0, 0, None, 0.0, None, resident=True)
-        torch.cuda.synchronize()
+        n = cu.basin_find(x, y, d_dir)
         t1 = time.perf_counter()
-        ret = m.shia_v1(None, None, inp["calib"], n_cont, 1, wl["T"], None, None, n)
+        b = cu.basin_cut(n, resident=True)
         torch.cuda.synchronize()
         t2 = time.perf_counter()
-        best_i = t1 - t0 if best_i is None else min(best_i, t1 - t0)
-        best_c = t2 - t0 if best_c is None else min(best_c, t2 - t0)
-    object.__getattribute__(m, "__dict__")["_rain_mem"] = saved
-    assert np.isfinite(ret[0]).all()
-    return {"rain_idw_ms": 1e3 * best_i, "rain_idw_stations": int(coord.shape[1]), "gauges_to_hydrograph_ms": 1e3 * best_c}
+        acum = cu.basin_acum(b)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        ts = (t1 - t0, t2 - t1, t3 - t2)
+        if best is None or sum(ts) < sum(best):
+            best = ts
+    assert int(acum[-1].item()) == n
+    tot = sum(best)
+    peak, peak_kind = peaks()
+    ach = BYTES_PER_CELL_PATH_A * n / tot / 1e9
+    res = {"raster": f"{nc}x{nr} {gen}", "cells": int(n), "levels": int(cu.basin_find_depth()),
+           "mcell_per_s": n / tot / 1e6, "ms": tot * 1e3,
+           "ms_find": best[0] * 1e3, "ms_cut": best[1] * 1e3, "ms_acum": best[2] * 1e3,
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "bytes_per_cell": BYTES_PER_CELL_PATH_A, "peak_kind": peak_kind, "traffic": None},
+           "timing": "host clock around the three synchronous C-ABI calls, DIR resident in HBM, best of %d" % reps}
+    if cpu:
+        from oracle import ref as _ref
+        import oracle
+        kind = cpu_kind()
+        ocu = _ref.RefCu() if kind == "reference" else oracle.Cu(fast=True)
+        ocu.ncols, ocu.nrows, ocu.xll, ocu.yll, ocu.dx, ocu.dy, ocu.dxp, ocu.nodata = nc, nr, 0.0, 0.0, DX, DX, DX, synth.NODATA
+        h_dir = d_dir.cpu().numpy().T                  # (ncols, nrows) F-ordered view, as wmf.py passes it
+        t0 = time.perf_counter()
+        n_c = ocu.basin_find(x, y, h_dir)
+        b_c = ocu.basin_cut(n_c)
+        a_c = ocu.basin_acum(b_c)
+        t_cpu = time.perf_counter() - t0
+        same = (n_c == n)
+        if same:                                       # compared on the device, in slabs
+            step = 1 << 26
+            bc, ac = np.ascontiguousarray(np.asarray(b_c).T), np.asarray(a_c).reshape(-1)
+            for s in range(0, n, step):
+                e = min(n, s + step)
+                same = same and bool(torch.equal(b[s:e], torch.from_numpy(bc[s:e]).to(dev)))
+                same = same and bool(torch.equal(acum[s:e], torch.from_numpy(np.ascontiguousarray(ac[s:e])).to(dev)))
+        res["cpu_baseline"] = {"value": n_c / t_cpu / 1e6, "unit": "Mcell/s", "cores": 1, "kind": kind,
+                               "sample": f"the whole {nc}x{nr} raster, find+cut+acum in {t_cpu:.2f} s, single thread as the reference runs"}
+        res["bit_exact_vs_cpu"] = bool(same)
+        res["speedup_vs_cpu"] = (n / tot) / (n_c / t_cpu)
+    del d_dir, b, acum
+    torch.cuda.empty_cache()
+    return res
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm
+# ---------------------------------------------------------------------------------------------------------------------
 def cpu_kind():
     """"reference" when the reference's own compiled Fortran is loadable (oracle/_ref/libwmf_ref.so, built from the
     objects in the reference tree and shipped to the GPU box), else "port" (the C restatement in oracle/)."""
@@ -178,13 +243,15 @@ def cpu_kind():
     return "reference" if ref.available() else "port"
 
 
-def cpu_prepare(wl, sample_steps, workdir):
+def cpu_prepare(wl, sample_steps, workdir, calib=None):
     """Inputs of a CPU sample: the first ``sample_steps`` steps of the workload; for the reference arm the rain table is
     written to the .bin / .hdr pair the Fortran reads record by record (modelosv2.f90:444-449), outside the timed call."""
     inp = dict(wl["inp"])
     inp["n_reg"] = sample_steps
     pos = np.ascontiguousarray(inp["pos_evento"][:sample_steps])
     inp["evpserie"] = inp["evpserie"][:sample_steps]
+    if calib is not None:
+        inp["calib"] = np.asarray(calib, np.float32)
     # keep only the rain records the sample touches (record 1 = zeros stays first)
     keep = np.unique(np.concatenate([[1], pos]))
     remap = np.zeros(int(inp["rain"].shape[0]) + 1, np.int32)
@@ -200,18 +267,23 @@ def cpu_prepare(wl, sample_steps, workdir):
     return inp, files
 
 
-def cpu_sample(wl, sample_steps, workdir):
-    """(cell-steps/s, seconds) of the reference's CPU path on the first ``sample_steps`` steps of the workload, 1 thread."""
-    inp, files = cpu_prepare(wl, sample_steps, workdir)
+def cpu_run(wl, sample_steps, workdir, calib=None):
+    """(cell-steps/s, seconds, result dict) of the reference's CPU path on the first ``sample_steps`` steps, 1 thread."""
+    inp, files = cpu_prepare(wl, sample_steps, workdir, calib)
     t0 = time.perf_counter()
     if files is not None:
         from oracle import ref
-        ref.shia_v1(inp, rain_files=files)
+        out = ref.shia_v1(inp, rain_files=files)
     else:
         import oracle
-        oracle.shia_v1(inp, fast=True)
+        out = oracle.shia_v1(inp, fast=True)
     dt = time.perf_counter() - t0
-    return wl["n"] * sample_steps / dt, dt
+    return wl["n"] * sample_steps / dt, dt, out
+
+
+def cpu_sample(wl, sample_steps, workdir):
+    v, dt, _ = cpu_run(wl, sample_steps, workdir)
+    return v, dt
 
 
 def cpu_label():
@@ -221,20 +293,32 @@ def cpu_label():
 
 
 def _ref_worker(args):
-    name, sample_steps, workdir = args
+    sample_steps, workdir, k = args
     os.environ["CUDA_VISIBLE_DEVICES"] = ""
     import oracle  # noqa: F401
     wl = _REF_WL[0]
-    return cpu_sample(wl, sample_steps, workdir)
+    cal = _REF_WL[1]
+    v, dt, _ = cpu_run(wl, sample_steps, workdir, None if cal is None else cal[k % cal.shape[0]])
+    return v, dt
 
 
-_REF_WL = [None]
+_REF_WL = [None, None]
+
+
+def describe(name, cfg, n, T):
+    if cfg["kind"] == "ensemble":
+        return (f"{name}: NSGA-II calibration ensemble (BASELINE configs[3]), SHIA/TETIS 5-tank model, {n}-cell synthetic basin "
+                f"({cfg['nc']}x{cfg['nr']} G2 raster), {T} hourly steps, {cfg['members']} parameter sets per GPU")
+    sub = " + SED sediments + landslides, kinematic hillslope speeds" if cfg["sediments"] else ""
+    return (f"{name}: SHIA/TETIS 5-tank run{sub}, {n}-cell synthetic basin ({cfg['nc']}x{cfg['nr']} G2 raster), "
+            f"{T} steps of {cfg['dt']:.0f} s")
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation (its own compiled Fortran through oracle/_ref when that
-    library is present, else the oracle port) on the host cores.  The reference's only parallelism is one process per ensemble member (wmf.py:872-878), so all cores
-    run one member each, on a bounded sample of the workload's steps."""
+    library is present, else the oracle port) on the host cores.  The reference's only parallelism is one process per
+    ensemble member (wmf.py:872-878 Pool.map), so all cores run one member each -- for the ensemble workload with that
+    member's own parameter set -- on a bounded sample of the workload's steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -242,22 +326,16 @@ def run_reference(args):
     import oracle
     oracle.build()
     name = args.workload
-    nc, nr, T, gen = WORKLOADS[name]
-    # the topology must come from somewhere that is not our GPU code: the oracle traces it
+    cfg = wl_cfg(name)
+    nc, nr, T = cfg["nc"], cfg["nr"], cfg["T"]
+    # the topology must come from somewhere that is not our GPU code: the CPU reference traces it
     from wmf_b200 import synth
-    DIR, DEM = synth.make_raster(gen, nc, nr, seed=0)
+    DIR, DEM = synth.make_raster(cfg["gen"], nc, nr, seed=0)
     from oracle import ref as _ref
     ocu = _ref.RefCu() if _ref.available() else oracle.Cu(fast=True)
-    ocu.ncols, ocu.nrows, ocu.xll, ocu.yll, ocu.dx, ocu.dy, ocu.dxp, ocu.nodata = nc, nr, 0.0, 0.0, DX, DX, DX, synth.NODATA
-    x, y = synth.outlet_xy(nc, nr, 0.0, 0.0, DX)
-    n = ocu.basin_find(x, y, DIR)
-    b = ocu.basin_cut(n)
-    dv = ocu.basin_map2basin(b, DIR.astype(np.float32), 0.0, 0.0, DX, DX, synth.NODATA).astype(np.int32)
-    de = ocu.basin_map2basin(b, DEM, 0.0, 0.0, DX, DX, synth.NODATA)
-    acum, lng, pend, _ = ocu.basin_basics(b, de, dv)
+    x, y, n, b, acum, lng, pend = trace_basin(ocu, DIR, DEM, nc, nr, cfg["dx"])
     sample_steps = max(2, min(T, args.ref_sample_steps))
-    inp = synth.make_shia_inputs(b, acum, lng, pend, dxp=DX, dt=3600.0, n_reg=T, seed=0, thresholds=(30, 500),
-                                 speed_type=(1, 1, 1), n_control=16)
+    inp = make_inputs(cfg, b, acum, lng, pend)
     # keep only the rain records the sample touches (memory: every worker holds a copy)
     pos = inp["pos_evento"][:sample_steps]
     keep = np.unique(np.concatenate([[1], pos]))
@@ -267,15 +345,15 @@ def run_reference(args):
     inp["pos_evento"] = np.concatenate([remap[pos], np.ones(T - sample_steps, np.int32)])
     _REF_WL[0] = dict(inp=inp, n=n)
     cores = os.cpu_count() or 1
+    _REF_WL[1] = synth.make_ensemble_calibs(max(cores, 2), seed=0) if cfg["kind"] == "ensemble" else None
     ctx = mp.get_context("fork")
     times = []
-    import tempfile
     tmp = tempfile.TemporaryDirectory(prefix="wmf_ref_")
     cpu_prepare(_REF_WL[0], sample_steps, tmp.name)          # writes the rain files once, before the pool forks
     with ctx.Pool(cores) as pool:
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            pool.map(_ref_worker, [(name, sample_steps, tmp.name)] * cores)
+            pool.map(_ref_worker, [(sample_steps, tmp.name, k) for k in range(cores)])
             dt = time.perf_counter() - t0
             if it >= args.warmup:
                 times.append(dt)
@@ -285,8 +363,7 @@ def run_reference(args):
         "impl": "reference", "metric": "shia_cell_steps_per_s", "value": value, "unit": "cell-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name}: SHIA/TETIS 5-tank run, {n}-cell synthetic basin ({nc}x{nr} G2 raster), "
-                               f"{T} hourly steps", "cells": n, "steps_per_run": T},
+        "config": {"workload": describe(name, cfg, n, T), "cells": n, "steps_per_run": T},
         "cpu_baseline": {"value": value, "unit": "cell-steps/s", "cores": cores, "kind": cpu_kind(),
                          "sample": f"first {sample_steps} of {T} steps of the same basin and rainfall, one ensemble member "
                                    f"per core ({cores} processes, as wmf.py:872-878 does); {cpu_label()}"},
@@ -294,6 +371,203 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     emit(line)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arms
+# ---------------------------------------------------------------------------------------------------------------------
+_STATIC_KEYS = ("drena", "unit_type", "hill_long", "stream_long", "elem_area", "max_capilar", "max_gravita", "max_aquifer",
+                "hill_slope", "stream_slope", "v_coef", "h_coef", "h_exp", "storage", "control", "control_h", "krus", "crus",
+                "prus", "parliac", "sl_zs", "sl_gammas", "sl_cohesion", "sl_frictionangle", "sl_radslope")
+
+
+def static_bytes(m):
+    a = object.__getattribute__(m, "__dict__")["_a"]
+    return sum(v.nbytes for k, v in a.items() if k in _STATIC_KEYS)
+
+
+def time_single(args, env, wl, warmup, steps, e2e_steps):
+    """One basin, one run per step (C2 / C5): resident arm through the marshalling layer with device buffers, e2e arm
+    through the drop-in call models.shia_v1 with pinned host buffers."""
+    import torch
+    import torch.distributed as dist
+    from wmf_b200 import ModelsModule, synth
+    ctx, stream, world, rank, local = env["ctx"], env["stream"], env["world"], env["rank"], env["local"]
+    m = ModelsModule(ctx)
+    inp, n, T = wl["inp"], wl["n"], wl["T"]
+    synth.apply_to_models(m, inp)
+    calibs = synth.make_ensemble_calibs(max(world, 1), seed=0)
+    calib = calibs[rank % calibs.shape[0]][None, :].copy()          # one ensemble member per GPU
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    m.make_resident()
+    d_rain = torch.from_numpy(inp["rain"]).to(f"cuda:{local}")
+    pos = inp["pos_evento"]
+    want = {"q", "stoout", "balance", "mean_rain"}
+    if wl["cfg"]["sediments"]:
+        want |= {"qsed", "vs", "vd", "vsc", "vdc", "volero", "voldepo", "erot", "dept"}
+    if wl["cfg"]["slides"]:
+        want |= {"sl_slideocurrence", "sl_slideacumulate", "sl_slidencelltime", "sl_riskvector", "sl_zcrit", "sl_zmin", "sl_zmax", "sl_bo"}
+    qobs = [None]
+
+    def step_resident():
+        out = m._run(calib, n_cont, 1, T, d_rain, pos, device_out=True, want=want)
+        if qobs[0] is None:
+            qobs[0] = out["q"][:, 0].contiguous()                    # "observed" series = this member's first run
+        scores = torch.empty((1, 2), dtype=torch.float32, device=f"cuda:{local}")
+        ctx.check(ctx.L.wmf_eval_scores(ctx.h, out["q"].data_ptr(), 1, n_cont, T, 0, qobs[0].data_ptr(), scores.data_ptr()))
+        if world > 1:                                                # the only collective: gather the members' scores
+            allsc = [torch.empty_like(scores) for _ in range(world)]
+            with torch.cuda.stream(stream):
+                dist.all_gather(allsc, scores)
+        return out
+
+    for _ in range(warmup):
+        step_resident()
+    env["barrier"]()
+    env["clock_start"]()
+    l0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wave_ms = []
+    ev0.record(stream)
+    for _ in range(steps):
+        step_resident()
+        wave_ms.append(ctx.last_kernel_ms())
+    ev1.record(stream)
+    env["barrier"]()
+    clocks = env["clock_stop"]()
+    launches = ctx.launches - l0
+    ms = ev0.elapsed_time(ev1) / steps
+    n_levels, n_waves = ctx.last_shia_stats()
+    # --- e2e arm: the drop-in call with host buffers (pinned), copies inside the timed region ---
+    m.make_resident(False)
+    pin_rain = torch.from_numpy(inp["rain"]).pin_memory()
+    m.set_rain(pin_rain.numpy(), pos)
+    h2d = static_bytes(m) + pin_rain.numel() * 4 + T * 8 + 44
+    d2h = 4 * (n_cont * T * 3 + 3 * T + T + 5 * n + 4 * n + T + n)
+    if wl["cfg"]["sediments"]:
+        d2h += 4 * (n_cont * 3 * T + 14 * n + 6)
+    if wl["cfg"]["slides"]:
+        d2h += 4 * (7 * n + T)
+
+    def step_e2e():
+        return m.shia_v1(None, None, calib[0], n_cont, 1, T, None, None, n)
+
+    for _ in range(max(warmup, 3)):            # also fills torch's pinned-memory cache for the output buffers
+        step_e2e()
+    env["barrier"]()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        ret = step_e2e()
+    e1.record(stream)
+    env["barrier"]()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / e2e_steps
+    assert np.isfinite(ret[0]).all()
+    ms, e2e_ms, wave = env["max_over_ranks"]([ms, e2e_ms, float(np.mean(wave_ms))])
+    del d_rain
+    bpc = BYTES_PER_CELL_STEP + (BYTES_SED if wl["cfg"]["sediments"] else 0.0) + (BYTES_SLIDES if wl["cfg"]["slides"] else 0.0)
+    return dict(ms=ms, e2e_ms=e2e_ms, wave_ms=wave, launches=int(launches), h2d=int(h2d), d2h=int(d2h), levels=n_levels,
+                waves=n_waves, units=float(n) * T, bytes_per_unit=bpc, clocks=clocks, models=m, n_cont=n_cont,
+                kernel="k_shia_tb<4,%s,%s,%s>" % tuple(str(bool(v)).lower() for v in (
+                    any(s == 2 for s in wl["cfg"]["speed_type"]), wl["cfg"]["sediments"], wl["cfg"]["slides"])))
+
+
+def time_ensemble(args, env, wl, warmup, steps, e2e_steps):
+    """The calibration population through wmf_b200.ensemble.evaluate_population: cfg['members'] parameter sets per rank."""
+    import torch
+    from wmf_b200 import ModelsModule, synth
+    from wmf_b200.ensemble import evaluate_population
+    ctx, stream, world, rank, local = env["ctx"], env["stream"], env["world"], env["rank"], env["local"]
+    cfg = wl["cfg"]
+    m = ModelsModule(ctx)
+    inp, n, T = wl["inp"], wl["n"], wl["T"]
+    synth.apply_to_models(m, inp)
+    P = cfg["members"] * world
+    calibs = synth.make_ensemble_calibs(P, seed=0)
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    pos = inp["pos_evento"]
+    m.make_resident()
+    d_rain = torch.from_numpy(inp["rain"]).to(f"cuda:{local}")
+    # "observations": the hydrograph of parameter set 0 at the outlet (its Nash score must come back as 1)
+    q0 = m._run(calibs[:1], n_cont, 1, T, d_rain, pos, want={"q"})["q"][0].copy()
+    stats = {}
+
+    def step_resident():
+        return evaluate_population(m, calibs, q0, n_cont, T, d_rain, pos, row=0, members_per_launch=cfg["batch"], stats=stats)
+
+    for _ in range(warmup):
+        step_resident()
+    env["barrier"]()
+    env["clock_start"]()
+    l0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stats.clear()
+    ev0.record(stream)
+    for _ in range(steps):
+        sc = step_resident()
+    ev1.record(stream)
+    env["barrier"]()
+    clocks = env["clock_stop"]()
+    launches = ctx.launches - l0
+    ms = ev0.elapsed_time(ev1) / steps
+    wave = stats.get("wave_ms", 0.0) / steps
+    n_waves = stats.get("waves", 0) // steps
+    n_levels = ctx.last_shia_stats()[0]
+    sc_h = sc.cpu().numpy()
+    assert sc_h.shape == (P, 2) and abs(float(sc_h[0, 0]) - 1.0) < 1e-6, "member 0 must reproduce its own hydrograph (Nash = 1)"
+    # --- e2e arm: host inputs; the rain table crosses PCIe once per evaluation, 1/world of it per rank ---
+    m.make_resident(False)
+    pin_rain = torch.from_numpy(inp["rain"]).pin_memory().numpy()
+    h2d = static_bytes(m) + (pin_rain.size * 4 + world - 1) // world + T * 8 + calibs[rank::world].nbytes + T * 4
+    d2h = 4 * 2 * P
+
+    def step_e2e():
+        return evaluate_population(m, calibs, q0, n_cont, T, pin_rain, pos, row=0, members_per_launch=cfg["batch"]).cpu().numpy()
+
+    for _ in range(max(1, min(warmup, 2))):
+        step_e2e()
+    env["barrier"]()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        sc2 = step_e2e()
+    e1.record(stream)
+    env["barrier"]()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / e2e_steps
+    assert np.array_equal(sc2, sc_h, equal_nan=True), "host-buffer evaluation differs from the resident one"
+    ms, e2e_ms, wave = env["max_over_ranks"]([ms, e2e_ms, wave])
+    m.make_resident()
+    return dict(ms=ms, e2e_ms=e2e_ms, wave_ms=wave, launches=int(launches), h2d=int(h2d), d2h=int(d2h), levels=n_levels,
+                waves=n_waves, units=float(n) * T * cfg["members"], bytes_per_unit=BYTES_PER_MEMBER_CELL_STEP, clocks=clocks,
+                models=m, n_cont=n_cont, calibs=calibs, d_rain=d_rain, scores=sc_h,
+                kernel="k_shia_tb<K,...> member-minor (K = 16, 8 or 4 by the ring-memory rule)")
+
+
+def ensemble_parity(args, env, wl, res, workdir):
+    """cpu_baseline of the ensemble workload = whole members of the population run by the reference's CPU path on one
+    core; their hydrographs double as an in-bench parity check of the GPU's (north-star tolerance 1e-5)."""
+    import torch
+    m, calibs, n_cont, T = res["models"], res["calibs"], res["n_cont"], wl["T"]
+    rng = np.random.default_rng(1)
+    picks = sorted(int(k) for k in rng.choice(calibs.shape[0], size=max(1, args.cpu_members), replace=False))
+    out = m._run(np.ascontiguousarray(calibs[picks]), n_cont, 1, T, res["d_rain"], wl["inp"]["pos_evento"], device_out=True,
+                 want={"q"}, ensemble=True)
+    q = out["q"].cpu().numpy().reshape(len(picks), T, n_cont)
+    secs, worst = 0.0, 0.0
+    for j, k in enumerate(picks):
+        v, dt, ref = cpu_run(wl, T, workdir, calib=calibs[k])
+        secs += dt
+        want, got = np.asarray(ref["q"], np.float64), q[j].T.astype(np.float64)
+        tol = 1e-5 * np.abs(want) + 1e-7 * np.abs(want).max()
+        worst = max(worst, float((np.abs(got - want) / tol).max()))
+    value = wl["n"] * T * len(picks) / secs
+    return ({"value": value, "unit": "cell-steps/s", "cores": 1, "kind": cpu_kind(),
+             "sample": f"{len(picks)} whole members of the population (parameter sets {picks}, {T} steps each, {secs:.1f} s), "
+                       f"single thread as the reference runs one member; {cpu_label()}"},
+            {"members": picks, "worst_error_in_units_of_tolerance_1e-5": worst, "pass": bool(worst <= 1.0),
+             "what": "Q at the outlet and 16 control points, every step, GPU ensemble launch vs the CPU reference"})
 
 
 def run_ours(args):
@@ -307,129 +581,98 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    from wmf_b200 import Context, CuModule, ModelsModule, synth
+    from wmf_b200 import Context, CuModule
     ctx = Context(local)
-    cu, m = CuModule(ctx), ModelsModule(ctx)
+    cu = CuModule(ctx)
     wl = build_workload(args.workload, cu, rank, verbose=(rank == 0))
-    inp, n, T = wl["inp"], wl["n"], wl["T"]
-    synth.apply_to_models(m, inp)
-    calibs = synth.make_ensemble_calibs(max(world, 1), seed=0)
-    calib = calibs[rank % calibs.shape[0]][None, :].copy()          # one ensemble member per GPU
-    n_cont = int(np.count_nonzero(inp["control"])) + 1
-    # --- resident arm: everything in HBM before the clock starts ---
+    cfg, n, T = wl["cfg"], wl["n"], wl["T"]
     stream = torch.cuda.Stream()
     ctx.use_stream(stream.cuda_stream)
-    m.make_resident()
-    d_rain = torch.from_numpy(inp["rain"]).to(f"cuda:{local}")
-    pos = inp["pos_evento"]
-    want = {"q", "stoout", "balance", "mean_rain"}
-    qobs = None
-
-    def step_resident():
-        nonlocal qobs
-        out = m._run(calib, n_cont, 1, T, d_rain, pos, device_out=True, want=want)
-        if qobs is None:
-            qobs = out["q"][:, 0].contiguous()                       # "observed" series = this member's first run
-        scores = torch.empty((1, 2), dtype=torch.float32, device=f"cuda:{local}")
-        ctx.check(ctx.L.wmf_eval_scores(ctx.h, out["q"].data_ptr(), 1, n_cont, T, 0, qobs.data_ptr(), scores.data_ptr()))
-        if world > 1:                                                # the only collective: gather the members' scores
-            allsc = [torch.empty_like(scores) for _ in range(world)]
-            with torch.cuda.stream(stream):
-                dist.all_gather(allsc, scores)
-        return out
+    sampler = ClockSampler(local)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_resident()
-    sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    l0 = ctx.launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wave_ms = []
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step_resident()
-        wave_ms.append(ctx.last_kernel_ms())
-    ev1.record(stream)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    launches = ctx.launches - l0
-    ms = ev0.elapsed_time(ev1) / args.steps
-    n_levels, n_waves = ctx.last_shia_stats()
-    # --- e2e arm: the drop-in call with host buffers (pinned), copies inside the timed region ---
-    m.make_resident(False)
-    pin_rain = torch.from_numpy(inp["rain"]).pin_memory()
-    m.set_rain(pin_rain.numpy(), pos)
-    a = object.__getattribute__(m, "__dict__")["_a"]
-    h2d = sum(v.nbytes for k, v in a.items() if k in ("drena", "unit_type", "hill_long", "stream_long", "elem_area",
-                                                        "max_capilar", "max_gravita", "max_aquifer", "hill_slope",
-                                                        "stream_slope", "v_coef", "h_coef", "h_exp", "storage", "control",
-                                                        "control_h")) + pin_rain.numel() * 4 + T * 8 + 44
-    d2h = 4 * (n_cont * T * 3 + 3 * T + T + 5 * n + 4 * n + T + n)
+    def max_over_ranks(vals):
+        tt = torch.tensor(vals, dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return [float(v) for v in tt.cpu()]
 
-    def step_e2e():
-        return m.shia_v1(None, None, calib[0], n_cont, 1, T, None, None, n)
-
-    for _ in range(max(args.warmup, 3)):       # also fills torch's pinned-memory cache for the output buffers
-        step_e2e()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k_e2e = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(k_e2e):
-        ret = step_e2e()
-    e1.record(stream)
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / k_e2e
-    assert np.isfinite(ret[0]).all()
-    # --- max over ranks ---
-    tt = torch.tensor([ms, e2e_ms, float(np.mean(wave_ms))], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, wave = (float(v) for v in tt.cpu())
+    env = dict(ctx=ctx, stream=stream, world=world, rank=rank, local=local, barrier=barrier, max_over_ranks=max_over_ranks,
+               clock_start=(sampler.start if rank == 0 else (lambda: None)),
+               clock_stop=(sampler.stop if rank == 0 else (lambda: None)))
+    timer = time_ensemble if cfg["kind"] == "ensemble" else time_single
+    res = timer(args, env, wl, args.warmup, args.steps, max(1, min(args.steps, 5)))
     if rank == 0:
-        cell_steps = float(n) * T
         peak, peak_kind = peaks()
-        achieved = BYTES_PER_CELL_STEP * cell_steps / (wave / 1e3) / 1e9
-        extra = bench_path_a(cu, wl)
-        extra.update(bench_gauges_chain(cu, m, wl, n_cont))
-        extra.update({"levels": n_levels, "waves_per_run": n_waves, "wave_kernel_ms_per_run": wave,
-                      "setup_and_epilogue_ms_per_run": ms - wave})
-        cpu_steps = max(2, min(T, args.cpu_sample_steps))
-        import tempfile
+        ms, e2e_ms, wave, units = res["ms"], res["e2e_ms"], res["wave_ms"], res["units"]
+        achieved = res["bytes_per_unit"] * units / (wave / 1e3) / 1e9
+        traffic, traffic_note = TRAFFIC[cfg["kind"]] if not cfg["sediments"] else (None, "no ncu capture of this variant yet")
+        extra = {"levels": res["levels"], "waves_per_run": res["waves"], "wave_kernel_ms_per_step": wave,
+                 "setup_and_epilogue_ms_per_step": ms - wave}
         with tempfile.TemporaryDirectory(prefix="wmf_cpu_") as tmpd:
-            cpu_v, cpu_s = cpu_sample(wl, cpu_steps, tmpd)
+            if cfg["kind"] == "ensemble":
+                cpu_b, parity = ensemble_parity(args, env, wl, res, tmpd)
+                extra["parity_vs_cpu"] = parity
+            else:
+                cpu_steps = max(2, min(T, args.cpu_sample_steps))
+                cpu_v, cpu_s = cpu_sample(wl, cpu_steps, tmpd)
+                cpu_b = {"value": cpu_v, "unit": "cell-steps/s", "cores": 1, "kind": cpu_kind(),
+                         "sample": f"first {cpu_steps} of {T} steps of the same basin ({cpu_s:.1f} s), single thread as the "
+                                   f"reference runs; {cpu_label()}"}
         line = {
-            "metric": "shia_cell_steps_per_s", "value": world * cell_steps / (ms / 1e3), "unit": "cell-steps/s",
+            "metric": "shia_cell_steps_per_s", "value": world * units / (ms / 1e3), "unit": "cell-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: SHIA/TETIS 5-tank run, {n}-cell synthetic basin "
-                                   f"({wl['nc']}x{wl['nr']} G2 raster), {T} hourly steps, 1 ensemble member per GPU",
-                       "cells": n, "steps_per_run": T, "members_per_gpu": 1,
-                       "l2": "inputs larger than L2 (rain table %.2f GB + %.0f MB state/maps)" % (
-                           inp["rain"].nbytes / 1e9, 150.0 * n / 1e6)},
-            "e2e": {"value": world * cell_steps / (e2e_ms / 1e3), "unit": "cell-steps/s",
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
-            "gpu_launches": int(launches),
+            "config": {"workload": describe(args.workload, cfg, n, T), "cells": n, "steps_per_run": T,
+                       "members_per_gpu": cfg.get("members", 1),
+                       "l2": "state and outflow ring of a launch (%.1f GB) are larger than L2" % (
+                           (cfg.get("batch", 1) * n * 36 * 2) / 1e9) if cfg["kind"] == "ensemble" else
+                             "inputs larger than L2 (rain table %.2f GB + %.0f MB state/maps)" % (
+                                 wl["inp"]["rain"].nbytes / 1e9, 150.0 * n / 1e6)},
+            "e2e": {"value": world * units / (e2e_ms / 1e3), "unit": "cell-steps/s",
+                    "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"], "ms_per_step": e2e_ms},
+            "gpu_launches": res["launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC_PER_LAUNCH, "peak_kind": peak_kind, "kernel": "k_shia_tb<4,false,false,false>",
-                         "bytes_per_cell_step": BYTES_PER_CELL_STEP, "launches_per_run": n_waves,
-                         "achieved_per_launch_bytes": BYTES_PER_CELL_STEP * cell_steps / max(n_waves, 1),
-                         "traffic_note": TRAFFIC_NOTE},
-            "cpu_baseline": {"value": cpu_v, "unit": "cell-steps/s", "cores": 1, "kind": cpu_kind(),
-                             "sample": f"first {cpu_steps} of {T} steps of the same basin ({cpu_s:.1f} s), single thread "
-                                       f"as the reference runs; {cpu_label()}"},
-            "clocks": clocks, "extra": extra,
+                         "traffic": traffic, "peak_kind": peak_kind, "kernel": res["kernel"],
+                         "bytes_per_unit": res["bytes_per_unit"], "launches_per_step": res["waves"],
+                         "achieved_per_launch_bytes": res["bytes_per_unit"] * units / max(res["waves"], 1),
+                         "traffic_note": traffic_note},
+            "cpu_baseline": cpu_b, "clocks": res["clocks"], "extra": extra,
         }
+        if world == 1 and not args.no_extras:
+            res.pop("d_rain", None)
+            res.pop("models", None)
+            torch.cuda.empty_cache()
+            if cfg["kind"] == "ensemble":          # the single-basin run of BASELINE configs[1] as a second field
+                wl2 = build_workload("c2", cu, 0, verbose=True)
+                r2 = time_single(args, dict(env, clock_start=lambda: None, clock_stop=lambda: None), wl2, 3, 5, 3)
+                u2 = r2["units"]
+                ach2 = r2["bytes_per_unit"] * u2 / (r2["wave_ms"] / 1e3) / 1e9
+                with tempfile.TemporaryDirectory(prefix="wmf_cpu_") as tmpd:
+                    cpu_v, cpu_s = cpu_sample(wl2, min(wl2["T"], args.cpu_sample_steps), tmpd)
+                extra["c2"] = {
+                    "workload": describe("c2", wl2["cfg"], wl2["n"], wl2["T"]), "value": u2 / (r2["ms"] / 1e3), "unit": "cell-steps/s",
+                    "ms_per_step": r2["ms"], "wave_kernel_ms": r2["wave_ms"], "levels": r2["levels"], "waves_per_run": r2["waves"],
+                    "e2e": {"value": u2 / (r2["e2e_ms"] / 1e3), "unit": "cell-steps/s", "ms_per_step": r2["e2e_ms"],
+                            "h2d_bytes_per_step": r2["h2d"], "d2h_bytes_per_step": r2["d2h"]},
+                    "roofline": {"bound": "hbm", "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak,
+                                 "traffic": TRAFFIC["single"][0], "kernel": r2["kernel"], "bytes_per_unit": r2["bytes_per_unit"],
+                                 "traffic_note": TRAFFIC["single"][1]},
+                    "cpu_baseline": {"value": cpu_v, "unit": "cell-steps/s", "cores": 1, "kind": cpu_kind(),
+                                     "sample": f"first {min(wl2['T'], args.cpu_sample_steps)} steps ({cpu_s:.1f} s), single thread"}}
+                del r2, wl2
+                torch.cuda.empty_cache()
+            pa = {"c1": bench_path_a(cu, 512, 512, reps=5)}
+            if not args.skip_c3:
+                pa["c3"] = bench_path_a(cu, 20000, 20000, reps=2, cpu=not args.skip_c3_cpu)
+            extra["path_a"] = pa
         emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -459,9 +702,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c2-small"])
-    ap.add_argument("--cpu-sample-steps", type=int, default=120, help="steps of the workload timed on one CPU core")
-    ap.add_argument("--ref-sample-steps", type=int, default=40, help="steps per reference-arm iteration")
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample-steps", type=int, default=120, help="single-run workloads: steps timed on one CPU core")
+    ap.add_argument("--cpu-members", type=int, default=2, help="ensemble workload: whole members re-run on one CPU core")
+    ap.add_argument("--ref-sample-steps", type=int, default=100, help="steps per reference-arm iteration (per member)")
+    ap.add_argument("--no-extras", action="store_true", help="skip extra.c2 and extra.path_a")
+    ap.add_argument("--skip-c3", action="store_true", help="skip the 20000 x 20000 Path A raster")
+    ap.add_argument("--skip-c3-cpu", action="store_true", help="C3 without the CPU reference run (13 GB of host memory, ~30 s)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

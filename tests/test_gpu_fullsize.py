@@ -127,3 +127,119 @@ def test_path_b_schedules_agree_bit_for_bit_on_c2(monkeypatch):
     r2 = _run(b, T - T1, stoin=r1["stoout"], hspeedin=r1["hspeed_out"], device_rain=d_rain)
     np.testing.assert_array_equal(np.concatenate([r1["q"], r2["q"]], axis=1), ref["q"])
     np.testing.assert_array_equal(r2["stoout"], ref["stoout"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Oracle parity at BASELINE.json's sizes (the oracle's -O3 build: same IEEE arithmetic, bit-identical to the parity build
+# and to the reference's compiled Fortran, tests/test_reference_pin.py).  CPU side: 10-40 s per test.
+# ---------------------------------------------------------------------------------------------------------------------
+def _excess(got, want, rtol=1e-5, afloor=1e-7):
+    """Worst |got-want| in units of the tolerance rtol*|want| + afloor*max|want| (<= 1 passes)."""
+    got, want = np.asarray(got, np.float64).reshape(-1), np.asarray(want, np.float64).reshape(-1)
+    assert got.shape == want.shape
+    return float((np.abs(got - want) / (rtol * np.abs(want) + afloor * np.abs(want).max() + 1e-300)).max())
+
+
+def test_c2_basin_200_steps_vs_oracle():
+    """C2 (1 044 484 cells) x 200 steps through models.shia_v1 with host buffers against the oracle: Q at the outlet and
+    the 16 control points, StoOut of every cell and tank within 1e-5; Acum_rain bit-exact."""
+    import oracle
+    from wmf_b200 import ModelsModule, synth
+    T = 200
+    wl, inp = _c2_inputs(T)
+    m = ModelsModule()
+    synth.apply_to_models(m, inp)
+    m.set_rain(inp["rain"], inp["pos_evento"])
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    ret = m.shia_v1(None, None, inp["calib"], n_cont, 1, T, None, None, wl["n"])
+    ref = oracle.shia_v1(inp, fast=True)
+    assert ref["q"][0].max() > 1.0
+    assert _excess(ret[0], ref["q"]) <= 1.0, "Q"
+    assert _excess(ret[9], ref["stoout"]) <= 1.0, "StoOut"
+    np.testing.assert_array_equal(np.asarray(m.acum_rain).reshape(-1), ref["acum_rain"])
+
+
+def test_path_a_8192_bit_exact_vs_oracle():
+    """find + cut + acum on an 8192 x 8192 raster (67 M cells, 8190 BFS levels): bit-exact against the oracle's FIFO search."""
+    import torch
+    import oracle
+    from wmf_b200 import CuModule, synth
+    nc = nr = int(os.environ.get("WMF_TEST_PATHA_ORACLE_SIZE", 8192))
+    DIR, _ = synth.make_raster("G2", nc, nr, seed=2)
+    cu, oc = CuModule(), oracle.Cu(fast=True)
+    for c in (cu, oc):
+        c.ncols, c.nrows, c.xll, c.yll, c.dx, c.dy, c.dxp, c.nodata = nc, nr, 0.0, 0.0, 30.0, 30.0, 30.0, synth.NODATA
+    x, y = synth.outlet_xy(nc, nr, 0.0, 0.0, 30.0)
+    d_dir = torch.from_numpy(np.ascontiguousarray(DIR.T)).cuda()
+    n = cu.basin_find(x, y, d_dir)
+    b = cu.basin_cut(n, resident=True)
+    acum = cu.basin_acum(b)
+    n_o = oc.basin_find(x, y, DIR)
+    assert n == n_o == (nc - 2) * (nr - 2)
+    b_o = oc.basin_cut(n_o)
+    assert bool((b.cpu().numpy().T == b_o).all()), "basin_f differs from the oracle"
+    a_o = oc.basin_acum(b_o)
+    assert bool((acum.cpu().numpy().reshape(-1) == np.asarray(a_o).reshape(-1)).all()), "acum differs from the oracle"
+
+
+def test_c4_shape_ensemble_64_members_vs_oracle():
+    """C4 shape: 64 calibration sets on the 260 100-cell basin x 200 steps in ONE launch sequence (member-minor layout);
+    4 members re-run one by one by the oracle, hydrographs at every control point within 1e-5."""
+    import torch
+    import oracle
+    from wmf_b200 import CuModule, ModelsModule, synth
+    nc = nr = 512
+    T, M = 200, 64
+    cu = CuModule()
+    DIR, DEM = synth.make_raster("G2", nc, nr, seed=0)
+    cu.ncols, cu.nrows, cu.xll, cu.yll, cu.dx, cu.dy, cu.dxp, cu.nodata = nc, nr, 0.0, 0.0, 30.0, 30.0, 30.0, synth.NODATA
+    x, y = synth.outlet_xy(nc, nr, 0.0, 0.0, 30.0)
+    n = cu.basin_find(x, y, DIR, nc, nr)
+    b = cu.basin_cut(n)
+    dv = cu.basin_map2basin(b, DIR.astype(np.float32), 0.0, 0.0, 30.0, 30.0, synth.NODATA).astype(np.int32)
+    de = cu.basin_map2basin(b, DEM, 0.0, 0.0, 30.0, 30.0, synth.NODATA)
+    acum, lng, pend, _ = cu.basin_basics(b, de, dv)
+    inp = synth.make_shia_inputs(b, acum, lng, pend, dxp=30.0, dt=3600.0, n_reg=T, seed=0, n_control=16)
+    m = ModelsModule()
+    synth.apply_to_models(m, inp)
+    m.make_resident()
+    d_rain = torch.from_numpy(inp["rain"]).cuda()
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    calibs = synth.make_ensemble_calibs(M, seed=0)
+    out = m._run(calibs, n_cont, 1, T, d_rain, inp["pos_evento"], device_out=True, want={"q"})
+    q = out["q"].cpu().numpy().reshape(M, T, n_cont)
+    for k in (0, 17, 40, 63):
+        ref = oracle.shia_v1(dict(inp, calib=calibs[k]), fast=True)
+        assert ref["q"][0].max() > 0
+        assert _excess(q[k].T, ref["q"]) <= 1.0, f"member {k}"
+
+
+def test_c5_basin_sediments_slides_48_steps_vs_oracle():
+    """C5: the 2.09 M-cell 12 m basin, 5-minute steps, kinematic hillslope speeds, SED sediments + landslides, 48 steps:
+    Q, StoOut, Qsed, the four sediment stores, VolERO / VolDEPo within 1e-5; landslide maps identical."""
+    import bench
+    import oracle
+    from wmf_b200 import CuModule, ModelsModule, synth
+    T = 48
+    cu = CuModule()
+    wl = bench.build_workload("c5", cu)
+    b, n = wl["basin"], wl["n"]
+    dv = cu.basin_map2basin(b, wl["DIR"].astype(np.float32), 0.0, 0.0, 12.0, 12.0, synth.NODATA).astype(np.int32)
+    de = cu.basin_map2basin(b, wl["DEM"], 0.0, 0.0, 12.0, 12.0, synth.NODATA)
+    acum, lng, pend, _ = cu.basin_basics(b, de, dv)
+    inp = synth.make_shia_inputs(b, acum, lng, pend, dxp=12.0, dt=300.0, n_reg=T, seed=0, thresholds=(200, 2000),
+                                 speed_type=(2, 2, 1), n_control=16, sediments=True, slides=True, rain_peak_mm=40.0)
+    m = ModelsModule()
+    synth.apply_to_models(m, inp)
+    m.set_rain(inp["rain"], inp["pos_evento"])
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    ret = m.shia_v1(None, None, inp["calib"], n_cont, 1, T, None, None, n)
+    ref = oracle.shia_v1(inp, fast=True)
+    assert ref["qsed"].max() > 0 and ref["voldepo"].max() > 0
+    worst = {"q": _excess(ret[0], ref["q"]), "stoout": _excess(ret[9], ref["stoout"]), "qsed": _excess(ret[1], ref["qsed"])}
+    for k in ("vs", "vd", "vsc", "vdc", "volero", "voldepo"):
+        worst[k] = _excess(getattr(m, k), ref[k])
+    assert max(worst.values()) <= 1.0, worst
+    np.testing.assert_array_equal(np.asarray(m.sl_riskvector).reshape(-1), ref["sl_riskvector"])
+    np.testing.assert_array_equal(np.asarray(m.sl_slideocurrence).reshape(-1), ref["sl_slideocurrence"])
+    np.testing.assert_array_equal(np.asarray(m.sl_slidencelltime).reshape(-1), ref["sl_slidencelltime"])

@@ -49,10 +49,10 @@ def test_fuzz_shia_gpu_vs_oracle(case, tmp_path):
         close(m.mean_vfluxes, ref["mean_vfluxes64"], name="mean_vfluxes")
         close(m.rc_coef, ref["rc_coef"], name="rc_coef")
     if mode in ("sed", "sed_slides"):
-        close(ret[1], ref["qsed"], rtol=5e-5, name="Qsed")
+        close(ret[1], ref["qsed"], name="Qsed")
         for k in ("vs", "vd", "vsc", "vdc"):
-            close(getattr(m, k), ref[k], rtol=5e-5, afloor=1e-6, name=k)
-        close(m.voldepo, ref["voldepo"], rtol=5e-5, afloor=1e-6, name="VolDEPo")
+            close(getattr(m, k), ref[k], name=k)
+        close(m.voldepo, ref["voldepo"], name="VolDEPo")
     if mode in ("slides", "sed_slides"):
         np.testing.assert_array_equal(np.asarray(m.sl_riskvector).reshape(-1), ref["sl_riskvector"])
         np.testing.assert_array_equal(np.asarray(m.sl_slideocurrence).reshape(-1), ref["sl_slideocurrence"])

@@ -83,8 +83,8 @@ def test_shia_against_the_reference(ref, case):
     if case == "separate_fluxes":
         close(ret[2], R["qseparated"], "Qseparated")
     if case == "sed_slides":
-        close(ret[1], R["qsed"], "Qsed", rtol=5e-5)
-        close(m.vd, R["vd"], "Vd", rtol=5e-5)
+        close(ret[1], R["qsed"], "Qsed")
+        close(m.vd, R["vd"], "Vd")
         np.testing.assert_array_equal(np.asarray(m.sl_riskvector).reshape(-1), R["sl_riskvector"])
         np.testing.assert_array_equal(np.asarray(m.sl_slideocurrence).reshape(-1), R["sl_slideocurrence"])
 

@@ -296,7 +296,9 @@ class ModelsModule:
         for name, arr in d["_a"].items():
             if isinstance(arr, np.ndarray) and arr.size:
                 flat = np.ascontiguousarray(arr.ravel(order="F"))
-                dev[id(arr)] = torch.from_numpy(flat).to(f"cuda:{self.ctx.device}")
+                # keyed by attribute name and holding the very ndarray the copy was made from: a device copy is used only
+                # while models.<name> still IS that array (assignment replaces the ndarray, see __setattr__)
+                dev[name] = (arr, torch.from_numpy(flat).to(f"cuda:{self.ctx.device}"))
         d["_dev"] = dev
 
     def _load_rain(self, ruta_bin, ruta_hdr, n_reg, n_cel):
@@ -409,6 +411,7 @@ class ModelsModule:
             if int(getattr(self, k)) == 1:
                 raise NotImplementedError(f"models.{k} = 1 selects a sub-model that is outside the B200 hot path "
                                           "(SURVEY.md 8f); set it to 0")
+        self._check_switch_combination()
         a = object.__getattribute__(self, "__dict__")["_a"]
         if "drena" not in a:
             raise ValueError("models.drena is not allocated")
@@ -465,6 +468,30 @@ class ModelsModule:
         return (out["q"], qsed, out.get("qseparated", zeros(nc, 3, T)), out["hum"], out["st1"], out["st3"], out["balance"], out["speed"],
                 out["areacontrol"], out["stoout"], out.get("qsep_byrain", zeros(nc, 2, T)))
 
+    def _check_switch_combination(self):
+        """The reference runs any combination of its switches in one ``shia_v1`` call.  The CUDA kernels cover every switch,
+        but not every PAIR of them ("Switch combinations"): the unsupported ones are refused here, before any
+        GPU work, instead of failing half way or -- worse -- returning a dump nobody wrote."""
+        on = lambda k: int(getattr(self, k)) == 1
+        means = [k for k in ("show_storage", "show_mean_speed") if on(k)]
+        if float(self.retorno_gr) == 1.0 and on("show_mean_retorno"):
+            means.append("show_mean_retorno")
+        dumps = [k for k in ("save_storage", "save_speed", "save_vfluxes", "save_rc", "save_retorno") if on(k)]
+        subs = [k for k in ("sim_sediments", "sim_slides") if on(k)]
+        sep = [k for k in ("separate_fluxes", "separate_rain") if on(k)]
+
+        def refuse(a, b):
+            raise NotImplementedError(f"models.{a} = 1 together with models.{b} = 1: this pair of switches is not built into "
+                                      "one CUDA kernel yet (DESIGN.md, 'Switch combinations'); run the two outputs in two calls")
+        if on("sim_floods"):
+            for k in subs + dumps + means + sep:
+                refuse("sim_floods", k)
+        for sk in sep:
+            for k in subs + dumps + means:
+                refuse(sk, k)
+        if len(sep) == 2:
+            refuse(sep[0], sep[1])
+
     def _guarda(self, name, T):
         """guarda_vfluxes as shia_v1 sees it: allocated with >= n_reg entries, else "all zeros" (modelosv2.f90:399-409)."""
         g = object.__getattribute__(self, "__dict__")["_a"].get(name)
@@ -484,8 +511,10 @@ class ModelsModule:
         return arr
 
     def _run(self, calibs, n_cont, n_conth, T, rain, pos, stoin=None, hspeedin=None, device_out=False, want=None,
-             rain_types=None):
-        """Marshal module state into one wmf_shia_run call.  ``calibs`` is (M,11)."""
+             rain_types=None, ensemble=False):
+        """Marshal module state into one wmf_shia_run call.  ``calibs`` is (M,11).  ``ensemble=True`` runs the plain
+        hydrological configuration an ensemble launch uses (dumps, separations, floods off; outputs laid out with a
+        member axis) whatever M is, so that a population evaluates the same model in every chunk size."""
         c = self.ctx
         a = object.__getattribute__(self, "__dict__")["_a"]
         N = a["drena"].shape[1]
@@ -505,39 +534,44 @@ class ModelsModule:
         cfg.diametro = (C.c_float * 3)(*[float(v) for v in a["diametro"]])
         cfg.sl_fs, cfg.sl_gammaw = float(self.sl_fs), float(self.sl_gammaw)
         cfg.n_members = M
-        cfg.save_storage = int(self.save_storage) if M == 1 else 0
-        cfg.save_speed = int(self.save_speed) if M == 1 else 0
-        cfg.separate_fluxes = int(self.separate_fluxes) if M == 1 else 0
-        cfg.save_vfluxes = int(self.save_vfluxes) if M == 1 else 0
-        cfg.save_rc = int(self.save_rc) if M == 1 else 0
-        if M != 1:
+        single = (M == 1) and not ensemble
+        cfg.save_storage = int(self.save_storage) if single else 0
+        cfg.save_speed = int(self.save_speed) if single else 0
+        cfg.separate_fluxes = int(self.separate_fluxes) if single else 0
+        cfg.save_vfluxes = int(self.save_vfluxes) if single else 0
+        cfg.save_rc = int(self.save_rc) if single else 0
+        if not single:
             cfg.save_retorno = 0
-        cfg.separate_rain = 1 if (rain_types is not None and M == 1) else 0
-        cfg.sim_floods = int(self.sim_floods) if M == 1 else 0
+            cfg.show_storage = cfg.show_mean_speed = cfg.show_mean_retorno = 0
+        cfg.separate_rain = 1 if (rain_types is not None and single) else 0
+        cfg.sim_floods = int(self.sim_floods) if single else 0
         keep = []
         si = ShiaInputs()
 
         dev = object.__getattribute__(self, "__dict__").get("_dev") or {}
 
-        def put(field, arr):
-            # a device-resident copy made by make_resident() is used in place (no host->device traffic)
-            if arr is not None and id(arr) in dev:
-                arr = dev[id(arr)]
+        def put(field, arr, name=None):
+            # a device-resident copy made by make_resident() is used in place (no host->device traffic); only module
+            # arrays are looked up, by name, and only while the module attribute is still the array that was uploaded
+            if name is not None and arr is not None:
+                ent = dev.get(name)
+                if ent is not None and ent[0] is arr:
+                    arr = ent[1]
             keep.append(arr)
             setattr(si, field, ptr(arr))
 
-        put("drena", self._cell("drena", 3, N, np.int32))
+        put("drena", self._cell("drena", 3, N, np.int32), "drena")
         si.drena_stride = 3
-        put("unit_type", self._cell("unit_type", 1, N, np.int32))
+        put("unit_type", self._cell("unit_type", 1, N, np.int32), "unit_type")
         for k in ("hill_long", "stream_long", "elem_area", "max_capilar", "max_gravita", "max_aquifer"):
-            put(k, self._cell(k, 1, N, np.float32))
+            put(k, self._cell(k, 1, N, np.float32), k)
         for k in ("hill_slope", "stream_slope"):
-            put(k, self._cell(k, 1, N, np.float32, required=False))
+            put(k, self._cell(k, 1, N, np.float32, required=False), k)
         for k in ("v_coef", "h_coef", "h_exp"):
-            put(k, self._cell(k, 4, N, np.float32))
-        put("storage", self._cell("storage", 5, N, np.float32))
-        put("control", self._cell("control", 1, N, np.int32, required=False))
-        put("control_h", self._cell("control_h", 1, N, np.int32, required=False))
+            put(k, self._cell(k, 4, N, np.float32), k)
+        put("storage", self._cell("storage", 5, N, np.float32), "storage")
+        put("control", self._cell("control", 1, N, np.int32, required=False), "control")
+        put("control_h", self._cell("control_h", 1, N, np.int32, required=False), "control_h")
         evp = a.get("evpserie")
         if evp is None or evp.size < T:
             raise ValueError("models.evpserie must hold n_reg values (wmf.py:4487-4490)")
@@ -583,7 +617,7 @@ class ModelsModule:
             for k in ("flood_dw", "flood_dsed", "flood_av", "flood_cmax", "flood_umbral", "flood_step", "flood_hmax"):
                 setattr(cfg, k, float(getattr(self, k)))
             for k in ("flood_w", "flood_d50", "flood_slope"):
-                put(k, self._cell(k, 1, N, np.float32))
+                put(k, self._cell(k, 1, N, np.float32), k)
             sec = a.get("flood_sections")
             if sec is None or sec.ndim != 2 or sec.shape[1] != N:
                 raise ValueError(f"models.flood_sections must be (flood_sec_tam,{N})")
@@ -598,13 +632,13 @@ class ModelsModule:
         sed, sl = cfg.sim_sediments == 1, cfg.sim_slides == 1
         if sed:
             for k in ("krus", "crus", "prus"):
-                put(k, self._cell(k, 1, N, np.float32))
-            put("parliac", self._cell("parliac", 3, N, np.float32))
+                put(k, self._cell(k, 1, N, np.float32), k)
+            put("parliac", self._cell("parliac", 3, N, np.float32), "parliac")
             if "vd" in a and not getattr(self, "_reset_vd", False):
                 put("vd_init", self._cell("vd", 3, N, np.float32))
         if sl:
             for k in ("sl_zs", "sl_gammas", "sl_cohesion", "sl_frictionangle", "sl_radslope"):
-                put(k, self._cell(k, 1, N, np.float32))
+                put(k, self._cell(k, 1, N, np.float32), k)
 
         so = ShiaOutputs()
         res = {}
@@ -621,7 +655,7 @@ class ModelsModule:
             res[name] = arr
             setattr(so, name, ptr(arr))
 
-        if M == 1:
+        if single:
             out("q", (n_cont, T)); out("hum", (n_conth, T)); out("st1", (n_conth, T)); out("st3", (n_conth, T))
             out("balance", (T,)); out("speed", (n_cont, T)); out("areacontrol", (n_cont, T))
             out("stoout", (5, N)); out("hspeed_out", (4, N)); out("mean_rain", (1, T)); out("acum_rain", (1, N))
@@ -670,7 +704,7 @@ class ModelsModule:
             out("hspeed_out", (4, N, M))
         c.check(c.L.wmf_shia_run(c.h, C.byref(cfg), C.byref(si), C.byref(so)))
         # module-global results the reference leaves behind (read back at wmf.py:4548-4601)
-        if M == 1 and not device_out:
+        if single and not device_out:
             d = object.__getattribute__(self, "__dict__")
             for k in ("mean_rain", "acum_rain", "mean_storage", "mean_speed", "mean_retorno", "mean_vfluxes", "rc_coef",
                       "storage_conv", "storage_stra", "flood_flood", "flood_h", "flood_ufr", "flood_cr", "flood_q", "flood_qsed",

@@ -169,7 +169,9 @@ __device__ __forceinline__ void sed_hillslope_dev(const ShiaP &P, SedLocal &S, f
     float qsSUStot = 0.f, qsBMtot = 0.f, qsSUS[3] = {0, 0, 0}, qsBM[3] = {0, 0, 0}, qsERO[3] = {0, 0, 0};
     float SUStot = 0.f, DEPtot = 0.f, Te[3];
     S.DEP[0] = S.DEP[1] = S.DEP[2] = 0.f;
-    const float Qskr = alfa * powf(So, 1.664f) * powf(qlin, 2.035f) * P.krus[cell] * P.crus[cell] * P.prus[cell] * dxp * dt;
+    // the two powers go through double precision: totXSScap / REScap below are differences of nearly equal terms, and a
+    // 1.4 ulp (wmf_powf) or 4 ulp (CUDA powf) error in Qskr reaches 1e-5 in Vs / VolDEPo (tests/test_pow_emulation.py)
+    const float Qskr = alfa * wmf_powf_dd(So, 1.664f) * wmf_powf_dd(qlin, 2.035f) * P.krus[cell] * P.crus[cell] * P.prus[cell] * dxp * dt;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         if (S2 / 1000.0f > P.wi[i] * dt)
@@ -1337,6 +1339,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             const int b0 = __shfl_sync(full, b, __ffs(act) - 1);
             const bool uni = __all_sync(full, !active || b == b0);
             const int sub = blockIdx.x & (RED_SUB - 1);
+            __syncwarp();  // the lanes read each other's s_acc slots below
             if (uni) {
                 constexpr int G = 32 / K;  // lanes per step
                 const int s = lane / G, part = lane % G;
@@ -1554,8 +1557,12 @@ __global__ void k_state_final(const ShiaP P, float *__restrict__ stoout, float *
 }
 
 // per-record basin total of the rain field in mm (fp64), used for Mean_Rain (:797) and `entradas` (:469)
-__global__ void __launch_bounds__(256) k_rain_record_sum(const int32_t *__restrict__ rain, int n, double *__restrict__ recsum) {
-    const int r = blockIdx.y;
+// (records no step refers to are skipped: a streamed table never received them; blockIdx.y + r0 = record, so that
+// tables with more than 65535 records are covered by several launches)
+__global__ void __launch_bounds__(256) k_rain_record_sum(const int32_t *__restrict__ rain, int n, int r0,
+                                                         const int32_t *__restrict__ used, double *__restrict__ recsum) {
+    const int r = r0 + blockIdx.y;
+    if (!used[r]) return;
     const int32_t *rec = rain + (size_t)r * n;
     double s = 0.0;
     // 128-bit loads where the record is 16-byte aligned (n % 4 == 0 or r == 0), scalar tail / fallback otherwise
@@ -2046,7 +2053,7 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     RainStream rs;
     WMF_TRY(rs.begin(ctx, sc, in->rain, in->n_records, N, &P.rain));
     // pos_evento is needed on both sides: validate on the host
-    std::vector<int32_t> h_pos((size_t)T);
+    std::vector<int32_t> h_pos((size_t)T), h_used;
     if (Scope::on_device(in->pos_evento)) {
         CU_TRY(ctx, cudaMemcpyAsync(h_pos.data(), in->pos_evento, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, ctx->stream));
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2517,8 +2524,15 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     WMF_TRY(rs.wait_all(ctx));
     // rain statistics that do not depend on the model state
     if (per_run) {
-        dim3 rg((unsigned)std::min(grid_for(N, 1024), 128), (unsigned)in->n_records);
-        LAUNCH(ctx, k_rain_record_sum, rg, 256, 0, P.rain, N, d_recsum);
+        h_used.assign((size_t)in->n_records, 0);       // (function scope: alive until the final synchronisation)
+        for (int t = 0; t < T; ++t) h_used[h_pos[t] - 1] = 1;
+        int32_t *d_used;
+        WMF_TRY(sc.alloc(&d_used, (size_t)in->n_records));
+        CU_TRY(ctx, cudaMemcpyAsync(d_used, h_used.data(), sizeof(int32_t) * (size_t)in->n_records, cudaMemcpyHostToDevice, ctx->stream));
+        for (int r0 = 0; r0 < in->n_records; r0 += 65535) {
+            dim3 rg((unsigned)std::min(grid_for(N, 1024), 128), (unsigned)std::min(65535, in->n_records - r0));
+            LAUNCH(ctx, k_rain_record_sum, rg, 256, 0, P.rain, N, r0, d_used, d_recsum);
+        }
         if (d_acum_rain) LAUNCH(ctx, k_acum_rain, G, B, 0, P.rain, P.pos, N, T, d_acum_rain);
     }
     ctx->last_levels = Lmax + 1;

@@ -79,3 +79,10 @@ WMF_HD float wmf_powf(float x, float y) {
     const float pl = fmaf(y, l, fmaf(y, a, -ph));
     return wmf_exp2_hl(ph, pl);
 }
+
+// x**y evaluated in double precision and rounded once to fp32 (relative error of the double result ~2^-45, i.e. the
+// correctly rounded fp32 power except for values within ~1e-6 ulp of a rounding boundary).  The reference's build calls
+// glibc's powf, which computes in double as well and is correctly rounded in all but a few percent of the cases.  Used
+// where the model subtracts nearly equal powers (sed_hillslope: excess transport capacity = Qskr - supply,
+// modelosv2.f90:1339-1395), so that a 1.4 ulp pow would show up as 1e-5 in the result; y must not be 0.
+WMF_HD float wmf_powf_dd(float x, float y) { return (float)exp2((double)y * log2((double)x)); }

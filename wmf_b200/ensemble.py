@@ -60,13 +60,46 @@ def gather_scores(local_scores, n_members: int, device=None):
     return out
 
 
+def share_rain(rain, device):
+    """Device copy of a HOST rain table ``(n_records, N)`` int32 for an ensemble evaluation.
+
+    Every rank of an ensemble reads the same table.  Instead of N ranks pulling N identical copies through the host's
+    memory and their PCIe links, rank r uploads records ``r::world`` only (from page-locked memory when the caller pinned
+    the table) and one NCCL all-gather over NVLink hands every rank the rest; the records are then put back in order on the
+    device.  Bit-identical to a plain upload (integer copies).  A single process just uploads."""
+    import torch
+    dist, rank, world = _dist()
+    h = torch.as_tensor(np.ascontiguousarray(rain, dtype=np.int32)) if not hasattr(rain, "is_cuda") else rain
+    if world == 1:
+        return h.to(device, non_blocking=True)
+    R, N = h.shape
+    per = (R + world - 1) // world
+    mine = torch.zeros((per, N), dtype=torch.int32, device=device)
+    part = h[rank::world]
+    mine[: part.shape[0]].copy_(part, non_blocking=True)
+    parts = torch.empty((world, per, N), dtype=torch.int32, device=device)
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(parts.view(world * per, N), mine)
+    else:                                   # gloo (CPU tests of the record bookkeeping)
+        lst = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(lst, mine)
+        parts = torch.stack(lst, 0)
+    # parts[r, j] = record r + j*world  ->  record order
+    return parts.permute(1, 0, 2).reshape(per * world, N)[:R].contiguous()
+
+
 def evaluate_population(models, calibs, qobs, n_cont, n_reg, rain, pos_evento, row: int = 0,
-                        members_per_launch: int = 64, run_batch=None):
+                        members_per_launch: int = 64, run_batch=None, stats: dict | None = None):
     """Scores ``[nash, qpico]`` of every calibration set in ``calibs`` (P,11) against ``qobs`` (n_reg), sharded over the
     ranks of the initialised process group (or run locally when there is none).  Returns a (P,2) torch tensor.
 
+    ``rain`` may be a torch CUDA tensor (used in place) or a host array: a host table is uploaded ONCE per evaluation
+    (``share_rain``: 1/world of the records per rank + an NVLink all-gather), and the module's static maps are made
+    resident for the duration of the call, so that the launches of a rank share them.
     ``run_batch(calib_batch) -> (m,2) scores`` may be injected (CPU tests of the sharding / gather logic); by default
-    a batch is one ``wmf_shia_run`` with ``n_members = m`` followed by ``wmf_eval_scores``, all resident on the GPU."""
+    a batch is one ``wmf_shia_run`` with ``n_members = m`` followed by ``wmf_eval_scores``, all resident on the GPU.
+    ``stats`` (optional dict) accumulates ``wave_ms`` (CUDA-event time of the wavefront launches), ``waves`` and
+    ``batches`` of this rank; asking for it synchronises after every batch."""
     import torch
     calibs = np.ascontiguousarray(np.asarray(calibs, dtype=np.float32))
     if calibs.ndim != 2 or calibs.shape[1] != 11:
@@ -75,25 +108,44 @@ def evaluate_population(models, calibs, qobs, n_cont, n_reg, rain, pos_evento, r
     _, rank, world = _dist()
     mine = shard_members(P, rank, world)
     dev = None
+    drop_resident = False
     if run_batch is None:
         c = models.ctx
         dev = torch.device(f"cuda:{c.device}")
         d_qobs = torch.as_tensor(np.ascontiguousarray(qobs, np.float32), device=dev)
         if d_qobs.numel() != n_reg:
             raise ValueError("qobs must hold n_reg values")
+        if int(models.sim_sediments) == 1 or int(models.sim_slides) == 1:
+            raise NotImplementedError("evaluate_population scores hydrographs: run it with models.sim_sediments = "
+                                      "models.sim_slides = 0 (storm scenarios with sediments go through run_scenarios)")
+        ch = getattr(models, "control_h", None)
+        n_conth = max(1, int(np.count_nonzero(ch))) if ch is not None else 1
+        if not hasattr(rain, "is_cuda") or not rain.is_cuda:
+            rain = share_rain(rain, dev)
+        if not object.__getattribute__(models, "__dict__").get("_dev"):
+            models.make_resident()
+            drop_resident = True
 
         def run_batch(cb):
             m = cb.shape[0]
-            # wmf_shia_run treats n_members == 1 as the single-run layout, which is the same memory for q
-            out = models._run(cb, n_cont, 1, n_reg, rain, pos_evento, device_out=True, want={"q"})
+            # the ensemble configuration (plain hydrology, member-minor outputs) for every chunk size, one member included
+            out = models._run(cb, n_cont, n_conth, n_reg, rain, pos_evento, device_out=True, want={"q"}, ensemble=True)
             sc = torch.empty((m, 2), dtype=torch.float32, device=dev)
             c.check(c.L.wmf_eval_scores(c.h, out["q"].data_ptr(), m, n_cont, n_reg, row, d_qobs.data_ptr(), sc.data_ptr()))
+            if stats is not None:
+                stats["wave_ms"] = stats.get("wave_ms", 0.0) + c.last_kernel_ms()
+                stats["waves"] = stats.get("waves", 0) + c.last_shia_stats()[1]
+                stats["batches"] = stats.get("batches", 0) + 1
             return sc
 
-    chunks = []
-    for s in range(0, mine.size, max(1, members_per_launch)):
-        idx = mine[s: s + members_per_launch]
-        chunks.append(torch.as_tensor(run_batch(calibs[idx]), dtype=torch.float32))
+    try:
+        chunks = []
+        for s in range(0, mine.size, max(1, members_per_launch)):
+            idx = mine[s: s + members_per_launch]
+            chunks.append(torch.as_tensor(run_batch(calibs[idx]), dtype=torch.float32))
+    finally:
+        if drop_resident:
+            models.make_resident(False)
     if chunks:
         local = torch.cat(chunks, 0)
     else:

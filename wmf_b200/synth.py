@@ -106,6 +106,59 @@ def make_raster(kind: str, nc: int, nr: int, seed: int = 0, chunk_rows: int = 20
     return dir_rc.T, dem_rc.T   # (ncols, nrows), F-contiguous views
 
 
+def make_dir_torch(kind: str, nc: int, nr: int, seed: int = 0, device="cuda", chunk_rows: int = 4096):
+    """The DIR raster of ``make_raster`` built with torch ops on ``device`` (bit-identical; CPU-side generation of a
+    20000 x 20000 raster takes minutes).  Returns an int32 tensor of shape (nrows, ncols) = the resident layout of a
+    ``(ncols, nrows)`` f2py raster (element (col,row) at ``row*ncols + col``)."""
+    import torch
+    assert nc >= 5 and nr >= 4 and kind in ("G1", "G2")
+    oc, orow = outlet_colrow(nc, nr)
+    M32 = 0xFFFFFFFF
+
+    def h32(sd, a, b):
+        # int64 arithmetic wraps modulo 2^64, so the low 32 bits of every product are those of the uint64 version
+        h = (a * 0x9E3779B1 + b * 0x85EBCA77 + ((int(sd) * 0xC2B2AE3D + 0x27D4EB2F) & M32)) & M32
+        h = h ^ (h >> 16)
+        h = (h * 0x85EBCA6B) & M32
+        h = h ^ (h >> 13)
+        h = (h * 0xC2B2AE35) & M32
+        return h ^ (h >> 16)
+
+    out = torch.empty((nr, nc), dtype=torch.int32, device=device)
+    cols = torch.arange(1, nc + 1, dtype=torch.int64, device=device)[None, :]
+    nod = int(NODATA)
+    for r0 in range(1, nr + 1, chunk_rows):
+        r1 = min(nr + 1, r0 + chunk_rows)
+        rows = torch.arange(r0, r1, dtype=torch.int64, device=device)[:, None]
+        interior = (cols >= 2) & (cols <= nc - 1) & (rows >= 2) & (rows <= nr - 1)
+        h = h32(seed, cols.expand(r1 - r0, nc), rows.expand(r1 - r0, nc))
+        if kind == "G1":
+            choice = h % 3 + 1
+            choice = torch.where((cols == 2) & (choice == 1), 2, choice)
+            choice = torch.where((cols == nc - 1) & (choice == 3), 2, choice)
+            side = torch.where(cols < oc, 6, torch.where(cols > oc, 4, 2)).expand(r1 - r0, nc)
+            d = torch.where((rows == nr - 1).expand(r1 - r0, nc), side, choice)
+        else:
+            dc, dr = cols - oc, rows - orow
+            cheb = torch.maximum(dc.abs(), dr.abs())
+            valid = []
+            for mx, my in _MOVES:
+                c2, r2 = cols + mx, rows + my
+                inside = (c2 >= 2) & (c2 <= nc - 1) & (r2 >= 2) & (r2 <= nr - 1)
+                valid.append(inside & (torch.maximum((dc + mx).abs(), (dr + my).abs()) < cheb))
+            cnt = torch.zeros_like(cheb)
+            for v in valid:
+                cnt = cnt + v
+            pick = h % cnt.clamp(min=1)
+            d = torch.full_like(cheb, 2)
+            run = torch.zeros_like(cheb)
+            for (mx, my), v in zip(_MOVES, valid):
+                d = torch.where(v & (run == pick), 5 - 3 * my + mx, d)
+                run = run + v
+        out[r0 - 1:r1 - 1] = torch.where(interior, d, nod).to(torch.int32)
+    return out
+
+
 def make_partial_raster(nc: int, nr: int, seed: int = 0, noise: float = 1.8, p_hole: float = 0.03):
     """Random D8 raster whose outlet catches only PART of the map: (DIR int32 (nc,nr), outlet (col,row) 1-based).
 
