@@ -29,6 +29,8 @@ struct wmf_ctx {
     // basin_find state (the reference's module global basin_temp)
     int32_t *q_lin = nullptr;  // BFS queue: linear raster index (row*nc+col, 0-based) per queue position
     int32_t *q_par = nullptr;  // queue position (1-based) of the cell it drains to; 0 for the outlet
+    int32_t *q_acum = nullptr; // cells draining through each queue position (tile path only; what basin_acum returns for this table)
+    bool q_acum_valid = false;
     int64_t q_cap = 0;
     int32_t find_n = 0, find_nc = 0, find_nr = 0, find_depth = 0;
     // basin_subbasin_nod state (the reference's module global sub_basins_temp(2,n_nodos), returned by basin_subbasin_cut)
@@ -178,6 +180,11 @@ __device__ __forceinline__ int block_scan_excl(int v, int *sm, int *total) {
 // entry points implemented in the other translation units
 int wmf_device_exclusive_scan_i32(wmf_ctx *ctx, Scope &sc, const int32_t *in, int32_t *out, int64_t n,
                                   int64_t *total_host /* may be null */);
+
+// basin_find without a level-by-level search (pathfind.cu): fills ctx->q_lin / q_par / q_acum
+int wmf_pathfind(wmf_ctx *ctx, Scope &sc, const int32_t *d_dir, int nc, int nr, int lin0, int32_t *n_out, int32_t *depth_out);
+// basin_acum of the table the last basin_find produced (verified drain id by drain id); *used = 1 when it applied
+int wmf_pathfind_acum_cached(wmf_ctx *ctx, Scope &sc, const int32_t *d_basin_f, int n, int32_t *d_acum, int *used);
 
 // cells gathered per hill in ascending cell order (subbasin.cu): order[hstart[h] .. +hist[h]) = the cells whose sub_pert is h
 // (and whose cauce is 1 when cauce is given), h = 1..n_hills

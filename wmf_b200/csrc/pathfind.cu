@@ -1,0 +1,737 @@
+// pathfind.cu -- basin_find (cuencas.f90:525-591) and the accumulation it implies (:659-680) WITHOUT a level-by-level
+// search: every stage is a streaming pass over the raster or over the tile-boundary graph.
+//
+// The reference's FIFO queue visits the basin by level (hops to the outlet) and, inside a level, in the order of the DFS
+// preorder taken with the children in the 3x3 probe order (kf outer, kc inner, :555-571).  With
+//      size(v) = cells draining through v (== basin_acum, :659-680)
+//      off(c)  = 1 + sum of size(s) over the siblings s of c probed before c
+//      pre(v)  = pre(parent) + off(v),  depth(v) = depth(parent) + 1,   pre(outlet) = depth(outlet) = 0
+// the queue position of v is its rank under (depth, pre), and basin_f(1,.) is the queue position of the parent.
+// size / depth / pre are leaf-to-root and root-to-leaf sums on a tree that is ~20 000 levels deep for a 20000^2 raster, so
+// they are computed by TILES: a 64x64 tile is solved in shared memory by pointer doubling (<= 12 rounds), the paths that
+// leave a tile form a graph over the tiles' perimeter cells only (~2 % of the raster, a few hundred hops deep), which is
+// solved by a barrier-free climb (sizes) and by pointer jumping (depth, pre), and a last pass adds the two.  The ranking is
+// a scatter by preorder (a permutation: no histogram) followed by a stable LSD radix sort on the depth.
+//
+//   k_pf_local1   tile: local terminal of every perimeter cell, cells collected by every exit cell          (4 B/cell read)
+//   k_pf_bg_*     boundary graph: next exit cell, global size of the exit cells ("last arriver climbs")
+//   k_pf_local2   tile: global size of every cell (external inflows added), sibling offsets, local hops and
+//                 preorder sums to the terminal                                                             (4 r + 12 w)
+//   k_pf_bd_*     boundary graph: depth / preorder of the exit cells (pointer jumping)
+//   k_pf_emit     cell: depth, preorder -> key/value written at position preorder                           (8 r + 8 w)
+//   k_rs_*        stable 8-bit LSD radix passes on the depth (2 for depths < 65536)                        (20 B per pass)
+//   k_pf_final_*  queue order: raster index, parent position (run-length expansion of the child counts), size
+//
+// oracle/tile_model.py restates the same decomposition on the CPU (tests/test_tile_model.py checks it against the
+// reference's queue); tests/test_gpu_topo.py / test_gpu_fullsize.py compare this path with the oracle bit for bit.
+#include <limits.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <string>
+
+#include "common.cuh"
+
+namespace pf {
+
+constexpr int TS = 64;                 // tile edge
+constexpr int TC = TS * TS;            // cells per tile
+constexpr int NSLOT = 256;             // node slots per tile (252 perimeter cells)
+constexpr int NPERIM = 4 * TS - 4;
+constexpr int NTHR = 512;              // threads per tile CTA
+constexpr int CPT = TC / NTHR;         // cells per thread
+constexpr int MAXROUNDS = 12;          // 2^12 = longest possible path inside a tile
+constexpr int ROOT_OUT = -1, DEAD = -2;
+constexpr unsigned short NONE16 = 0xFFFF;
+constexpr unsigned T_ROOT_OUT = 0xFFFEu, T_DEAD = 0xFFFFu;
+constexpr int EW = TS + 2;             // tile + halo ring
+
+__device__ __forceinline__ int perim_index(int ly, int lx) {
+    if (ly == 0) return lx;
+    if (ly == TS - 1) return TS + lx;
+    if (lx == 0) return 2 * TS + ly - 1;
+    return 2 * TS + (TS - 2) + ly - 1;  // lx == TS - 1
+}
+__device__ __forceinline__ void perim_cell(int k, int &ly, int &lx) {
+    if (k < TS) { ly = 0; lx = k; }
+    else if (k < 2 * TS) { ly = TS - 1; lx = k - TS; }
+    else if (k < 2 * TS + TS - 2) { ly = k - 2 * TS + 1; lx = 0; }
+    else { ly = k - (2 * TS + TS - 2) + 1; lx = TS - 1; }
+}
+__device__ __forceinline__ int node_of(int gr, int gc, int ntx) {
+    return ((gr >> 6) * ntx + (gc >> 6)) * NSLOT + perim_index(gr & (TS - 1), gc & (TS - 1));
+}
+__device__ __forceinline__ void code_move(int d, int &dc, int &dr) {  // keypad 7 8 9 / 4 5 6 / 1 2 3, rows grow downwards
+    dc = (d - 1) % 3 - 1;
+    dr = 1 - (d - 1) / 3;
+}
+// effective direction code of raster cell (gr, gc): 0 = no downstream (outside the raster, not a D8 code, points off the
+// map, or the outlet -- the search never follows the outlet's own direction, cuencas.f90:552-589)
+__device__ __forceinline__ int eff_code(const int32_t *__restrict__ dir, int nc, int nr, int gr, int gc, int lin0) {
+    if (gr < 0 || gr >= nr || gc < 0 || gc >= nc) return 0;
+    const int lin = gr * nc + gc;
+    if (lin == lin0) return 0;
+    const int d = __ldg(dir + lin);
+    if (d < 1 || d > 9 || d == 5) return 0;
+    int dc, dr;
+    code_move(d, dc, dr);
+    const int tc = gc + dc, tr = gr + dr;
+    if (tc < 0 || tc >= nc || tr < 0 || tr >= nr) return 0;
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stage A: per tile, where the perimeter cells' paths leave the tile and how many cells every exit cell collects
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHR, 2)
+k_pf_local1(const int32_t *__restrict__ dir, int nc, int nr, int ntx, int lin0, int32_t *__restrict__ pterm,
+            int32_t *__restrict__ bdown, uint32_t *__restrict__ lsize) {
+    __shared__ unsigned char code[TC];
+    __shared__ unsigned short T[TC];
+    __shared__ unsigned cnt[NSLOT];
+    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int r0 = (tile / ntx) * TS, c0 = (tile % ntx) * TS;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int li = k * NTHR + tid, ly = li >> 6, lx = li & (TS - 1);
+        const int d = eff_code(dir, nc, nr, r0 + ly, c0 + lx, lin0);
+        int t = li;
+        if (d) {
+            int dc, dr;
+            code_move(d, dc, dr);
+            const int ny = ly + dr, nx = lx + dc;
+            if (ny >= 0 && ny < TS && nx >= 0 && nx < TS) t = ny * TS + nx;
+        }
+        code[li] = (unsigned char)d;
+        T[li] = (unsigned short)t;
+    }
+    if (tid < NSLOT) cnt[tid] = 0;
+    __syncthreads();
+    // pointer jumping to the local terminal (T == self).  Unsynchronised in-place updates are safe here: T[x] always is
+    // x itself or a cell further down x's path, whatever mix of old and new values a thread reads.
+    for (int round = 0; round < MAXROUNDS; ++round) {
+        int changed = 0;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const int li = k * NTHR + tid;
+            const int t = T[li], tt = T[t];
+            if (tt != t) { T[li] = (unsigned short)tt; changed = 1; }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int li = k * NTHR + tid;
+        const int t = T[li];
+        if (T[t] == t && code[t] != 0) atomicAdd(&cnt[perim_index(t >> 6, t & (TS - 1))], 1u);  // an exit cell collects me
+    }
+    __syncthreads();
+    if (tid < NSLOT) {
+        const int node = tile * NSLOT + tid;
+        int pt = DEAD, bd = -1;
+        unsigned ls = 0;
+        if (tid < NPERIM) {
+            int ly, lx;
+            perim_cell(tid, ly, lx);
+            const int li = ly * TS + lx;
+            const int t = T[li];
+            if (T[t] == t) {  // (cells of a cycle inside the tile never reach a terminal: dead)
+                if (code[t] != 0) pt = perim_index(t >> 6, t & (TS - 1));
+                else {
+                    const int gr = r0 + (t >> 6), gc = c0 + (t & (TS - 1));
+                    pt = (gr < nr && gc < nc && gr * nc + gc == lin0) ? ROOT_OUT : DEAD;
+                }
+            }
+            if (t == li && code[li] != 0) {  // an exit cell: its downstream neighbour lies in another tile
+                int dc, dr;
+                code_move(code[li], dc, dr);
+                bd = node_of(r0 + ly + dr, c0 + lx + dc, ntx);
+                ls = cnt[tid];
+            }
+        }
+        pterm[node] = pt;
+        bdown[node] = bd;
+        lsize[node] = ls;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stage B: the boundary graph (exit cell -> the exit cell its water reaches next) and the global size of the exit cells
+// ---------------------------------------------------------------------------------------------------------------------
+// w[x] = (arrivals - tributaries) << 32 | cells collected so far   (as k_acum_climb in topo.cu)
+__global__ void k_pf_bg_init(int n_nodes, const int32_t *__restrict__ pterm, const int32_t *__restrict__ bdown,
+                             const uint32_t *__restrict__ lsize, int32_t *__restrict__ bnext,
+                             unsigned long long *__restrict__ w) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_nodes) return;
+    const int bd = bdown[x];
+    int nx = DEAD;
+    if (bd >= 0) {
+        const int pt = pterm[bd];
+        nx = pt >= 0 ? (bd & ~(NSLOT - 1)) + pt : pt;
+    }
+    bnext[x] = nx;
+    w[x] = (unsigned long long)lsize[x];
+}
+__global__ void k_pf_bg_count(int n_nodes, const int32_t *__restrict__ bnext, unsigned long long *__restrict__ w) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_nodes) return;
+    const int nx = bnext[x];
+    if (nx >= 0) atomicAdd(&w[nx], 0xFFFFFFFF00000000ull);
+}
+__global__ void k_pf_bg_leaves(int n_nodes, const int32_t *__restrict__ bdown, const unsigned long long *__restrict__ w,
+                               unsigned char *__restrict__ leaf) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_nodes) return;
+    leaf[x] = (bdown[x] >= 0 && (unsigned)(w[x] >> 32) == 0u) ? 1 : 0;
+}
+__global__ void k_pf_bg_climb(int n_nodes, const int32_t *__restrict__ bnext, const unsigned char *__restrict__ leaf,
+                              unsigned long long *__restrict__ w) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_nodes || !leaf[x]) return;
+    unsigned v = (unsigned)w[x];  // a leaf's total is final: nobody adds to it
+    int cur = x;
+    for (;;) {
+        const int p = bnext[cur];
+        if (p < 0) break;
+        const unsigned long long old = atomicAdd(&w[p], (1ull << 32) + (unsigned long long)v);
+        if ((unsigned)(old >> 32) != 0xFFFFFFFFu) break;  // not the last tributary to arrive
+        v = (unsigned)old + v;
+        cur = p;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stage C: per tile, global sizes, sibling offsets, hops and preorder sums to the local terminal
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int halo_slot(int ey, int ex) {  // (ey, ex) in [-1, TS], on the halo ring
+    if (ey == -1) return ex + 1;
+    if (ey == TS) return EW + ex + 1;
+    if (ex == -1) return 2 * EW + ey;
+    return 2 * EW + TS + ey;  // ex == TS
+}
+constexpr int NHALO = 2 * EW + 2 * TS;
+
+struct Local2Smem {
+    uint32_t bufA[TC], bufB[TC];
+    unsigned short j0[TC], j1[TC];
+    uint32_t hG[NHALO];
+    unsigned char code[EW * EW];
+};
+
+__global__ void __launch_bounds__(NTHR, 2)
+k_pf_local2(const int32_t *__restrict__ dir, int nc, int nr, int ntx, int lin0, const unsigned long long *__restrict__ w,
+            uint32_t *__restrict__ S, uint2 *__restrict__ LR, uint32_t *__restrict__ boff, uint2 *__restrict__ eho) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Local2Smem &sm = *reinterpret_cast<Local2Smem *>(smem_raw);
+    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int r0 = (tile / ntx) * TS, c0 = (tile % ntx) * TS;
+    // the 3x3 probe order of cuencas.f90:555-571 and the code a neighbour must carry to be a child
+    constexpr int PDC[8] = {-1, 0, 1, -1, 1, -1, 0, 1}, PDR[8] = {-1, -1, -1, 0, 0, 1, 1, 1}, PCODE[8] = {3, 2, 1, 6, 4, 9, 8, 7};
+    for (int idx = tid; idx < EW * EW; idx += NTHR) {
+        const int ey = idx / EW - 1, ex = idx % EW - 1;
+        sm.code[idx] = (unsigned char)eff_code(dir, nc, nr, r0 + ey, c0 + ex, lin0);
+    }
+    __syncthreads();
+    uint32_t *Ac = sm.bufA, *An = sm.bufB;
+    unsigned short *Jc = sm.j0, *Jn = sm.j1;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int li = k * NTHR + tid, ly = li >> 6, lx = li & (TS - 1);
+        const int d = sm.code[(ly + 1) * EW + lx + 1];
+        int j = NONE16;
+        if (d) {
+            int dc, dr;
+            code_move(d, dc, dr);
+            const int ny = ly + dr, nx = lx + dc;
+            if (ny >= 0 && ny < TS && nx >= 0 && nx < TS) j = ny * TS + nx;
+        }
+        Jc[li] = (unsigned short)j;
+        Ac[li] = 1u;
+    }
+    __syncthreads();
+    // what enters from the neighbouring tiles: a halo cell pointing at one of my cells is an exit cell of its own tile
+    for (int h = tid; h < NHALO; h += NTHR) {
+        int ey, ex;
+        if (h < EW) { ey = -1; ex = h - 1; }
+        else if (h < 2 * EW) { ey = TS; ex = h - EW - 1; }
+        else if (h < 2 * EW + TS) { ey = h - 2 * EW; ex = -1; }
+        else { ey = h - 2 * EW - TS; ex = TS; }
+        const int d = sm.code[(ey + 1) * EW + ex + 1];
+        unsigned g = 0;
+        if (d) {
+            int dc, dr;
+            code_move(d, dc, dr);
+            const int ty = ey + dr, tx = ex + dc;
+            if (ty >= 0 && ty < TS && tx >= 0 && tx < TS) {
+                g = (unsigned)w[node_of(r0 + ey, c0 + ex, ntx)];
+                atomicAdd(&Ac[ty * TS + tx], g);
+            }
+        }
+        sm.hG[h] = g;
+    }
+    __syncthreads();
+    // leaf-to-root sums by doubling: J_k(u) = the cell 2^k steps down u's path inside the tile (or none),
+    // A_k(v) = sum over the cells less than 2^k steps above v;  A_{k+1}(v) = A_k(v) + sum_{J_k(u) = v} A_k(u)
+    for (int round = 0; round < MAXROUNDS; ++round) {
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) An[k * NTHR + tid] = Ac[k * NTHR + tid];
+        __syncthreads();
+        int live = 0;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const int li = k * NTHR + tid;
+            const int j = Jc[li];
+            int jn = NONE16;
+            if (j != NONE16) {
+                atomicAdd(&An[j], Ac[li]);
+                jn = Jc[j];
+                live |= (jn != NONE16);
+            }
+            Jn[li] = (unsigned short)jn;
+        }
+        { uint32_t *t = Ac; Ac = An; An = t; }
+        { unsigned short *t = Jc; Jc = Jn; Jn = t; }
+        if (!__syncthreads_or(live)) break;
+    }
+    // Ac = global size of every cell of the tile (== basin_acum for the cells of the basin)
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int li = k * NTHR + tid, gr = r0 + (li >> 6), gc = c0 + (li & (TS - 1));
+        if (gr < nr && gc < nc) S[(size_t)gr * nc + gc] = Ac[li];
+        An[li] = 0u;  // becomes off(), then the preorder sum to the terminal
+    }
+    __syncthreads();
+    // sibling offsets: the cell that is drained into numbers its tributaries in probe order
+    unsigned nchpack = 0;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int li = k * NTHR + tid, ly = li >> 6, lx = li & (TS - 1);
+        unsigned run = 1u, nch = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int ey = ly + PDR[q], ex = lx + PDC[q];
+            if (sm.code[(ey + 1) * EW + ex + 1] == PCODE[q]) {
+                if (ey >= 0 && ey < TS && ex >= 0 && ex < TS) {
+                    An[ey * TS + ex] = run;
+                    run += Ac[ey * TS + ex];
+                } else {
+                    boff[node_of(r0 + ey, c0 + ex, ntx)] = run;
+                    run += sm.hG[halo_slot(ey, ex)];
+                }
+                ++nch;
+            }
+        }
+        nchpack |= nch << (4 * k);
+    }
+    __syncthreads();
+    // root-to-leaf sums by pointer jumping: T = cell reached so far, H = hops to it, O (in An) = sum of off() over the
+    // cells passed (the terminal's own offset belongs to the boundary graph)
+    unsigned short *T = sm.j0, *H = sm.j1;
+    uint32_t *O = An;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int li = k * NTHR + tid, ly = li >> 6, lx = li & (TS - 1);
+        const int d = sm.code[(ly + 1) * EW + lx + 1];
+        int t = li;
+        if (d) {
+            int dc, dr;
+            code_move(d, dc, dr);
+            const int ny = ly + dr, nx = lx + dc;
+            if (ny >= 0 && ny < TS && nx >= 0 && nx < TS) t = ny * TS + nx;
+        }
+        T[li] = (unsigned short)t;
+        H[li] = (unsigned short)(t != li ? 1 : 0);
+    }
+    __syncthreads();
+    for (int round = 0; round < MAXROUNDS; ++round) {
+        int t1[CPT], t2[CPT];
+        unsigned hh[CPT], oo[CPT];
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const int li = k * NTHR + tid;
+            t1[k] = T[li];
+            t2[k] = T[t1[k]];
+            hh[k] = H[t1[k]];
+            oo[k] = O[t1[k]];
+        }
+        __syncthreads();
+        int changed = 0;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const int li = k * NTHR + tid;
+            if (t2[k] != t1[k]) changed = 1;
+            if (t1[k] != li) {  // (a terminal adds its own zeros)
+                T[li] = (unsigned short)t2[k];
+                H[li] = (unsigned short)(H[li] + hh[k]);
+                O[li] = O[li] + oo[k];
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int li = k * NTHR + tid, ly = li >> 6, lx = li & (TS - 1);
+        const int gr = r0 + ly, gc = c0 + lx;
+        const int t = T[li];
+        unsigned tc = T_DEAD;
+        if (T[t] == t) {
+            if (sm.code[((t >> 6) + 1) * EW + (t & (TS - 1)) + 1] != 0) tc = (unsigned)perim_index(t >> 6, t & (TS - 1));
+            else {
+                const int tr = r0 + (t >> 6), tcc = c0 + (t & (TS - 1));
+                tc = (tr < nr && tcc < nc && tr * nc + tcc == lin0) ? T_ROOT_OUT : T_DEAD;
+            }
+        }
+        const unsigned h = H[li] & 0xFFFu, o = O[li], nch = (nchpack >> (4 * k)) & 15u;   // (h <= 4095 unless the cell is dead)
+        if (gr < nr && gc < nc) LR[(size_t)gr * nc + gc] = make_uint2(tc | (h << 16) | (nch << 28), o);
+        if (ly == 0 || ly == TS - 1 || lx == 0 || lx == TS - 1) eho[tile * NSLOT + perim_index(ly, lx)] = make_uint2(h, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stage D: depth and preorder of the exit cells
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void k_pf_bd_init(int n_nodes, const int32_t *__restrict__ bdown, const int32_t *__restrict__ bnext,
+                             const uint32_t *__restrict__ boff, const uint2 *__restrict__ eho, int32_t *__restrict__ nx,
+                             uint2 *__restrict__ dp) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_nodes) return;
+    const int bd = bdown[x];
+    int n = DEAD;
+    uint2 v = make_uint2(0u, 0u);
+    if (bd >= 0) {
+        n = bnext[x];
+        const uint2 e = eho[bd];
+        v = make_uint2(1u + e.x, boff[x] + e.y);  // one hop into the next tile + that cell's way to its terminal
+    }
+    nx[x] = n;
+    dp[x] = v;
+}
+__global__ void k_pf_bd_jump(int n_nodes, const int32_t *__restrict__ nx_in, const uint2 *__restrict__ dp_in,
+                             int32_t *__restrict__ nx_out, uint2 *__restrict__ dp_out, int *__restrict__ more) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_nodes) return;
+    int n = nx_in[x];
+    uint2 v = dp_in[x];
+    if (n >= 0) {
+        const int n2 = nx_in[n];
+        const uint2 u = dp_in[n];
+        v.x += u.x;
+        v.y += u.y;
+        n = n2;
+        if (n2 >= 0) *more = 1;
+    }
+    nx_out[x] = n;
+    dp_out[x] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stage E: every cell of the basin writes (depth | children << 28, raster index) at position preorder
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pf_emit(const uint2 *__restrict__ LR, int nc, int nr, int ntx, const int32_t *__restrict__ nx, const uint2 *__restrict__ dp,
+          uint32_t n_basin, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, unsigned *__restrict__ stat /* [0] max depth, [1] errors */) {
+    const int gc = blockIdx.x * TS + (threadIdx.x & (TS - 1));
+    const int gr = blockIdx.y * 4 + (threadIdx.x >> 6);
+    unsigned depth = 0;
+    bool ok = false;
+    if (gc < nc && gr < nr) {
+        const size_t lin = (size_t)gr * nc + gc;
+        const uint2 lr = LR[lin];
+        const unsigned tc = lr.x & 0xFFFFu, h = (lr.x >> 16) & 0xFFFu, nch = lr.x >> 28;
+        unsigned pre = 0;
+        if (tc == T_ROOT_OUT) { depth = h; pre = lr.y; ok = true; }
+        else if (tc != T_DEAD) {
+            const int node = ((gr >> 6) * ntx + blockIdx.x) * NSLOT + (int)tc;
+            if (nx[node] == ROOT_OUT) {
+                const uint2 v = dp[node];
+                depth = v.x + h;
+                pre = v.y + lr.y;
+                ok = true;
+            }
+        }
+        if (ok) {
+            if (pre < n_basin && depth < (1u << 28)) {
+                keys[pre] = depth | (nch << 28);
+                vals[pre] = (uint32_t)lin;
+            } else {
+                atomicAdd(&stat[1], 1u);
+                depth = 0;
+            }
+        }
+    }
+    unsigned m = ok ? depth : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&stat[0], m);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stable LSD radix pass, 8 bits: per-tile digit histograms, one device scan, ranked scatter
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256, RS_WARPS = RS_THREADS / 32, RS_TILE = 4096, RS_PER_WARP = RS_TILE / RS_WARPS, RS_SUB = RS_PER_WARP / 32;
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_hist(const uint32_t *__restrict__ keys, uint32_t n, int shift, int nblk, int32_t *__restrict__ hist /* [256][nblk] */) {
+    __shared__ unsigned h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t base = (size_t)blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
+        const size_t idx = base + i;
+        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nblk + blockIdx.x] = (int32_t)h[threadIdx.x];
+}
+
+// every warp owns 512 consecutive items of the tile, so "warp, sub-step, lane" is the input order: stable
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n, int shift, int nblk,
+             const int32_t *__restrict__ hist_scan, uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
+    __shared__ unsigned wh[RS_WARPS][256];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&wh[0][0])[i] = 0;
+    __syncthreads();
+    const size_t base = (size_t)blockIdx.x * RS_TILE + (size_t)wid * RS_PER_WARP;
+    uint32_t k[RS_SUB], v[RS_SUB];
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int s = 0; s < RS_SUB; ++s) {
+        const size_t idx = base + s * 32 + lane;
+        const bool valid = idx < n;
+        k[s] = valid ? keys[idx] : 0u;
+        v[s] = valid ? vals[idx] : 0u;
+        const int d = valid ? (int)((k[s] >> shift) & 255u) : 256 + lane;   // invalid lanes match nobody
+        const unsigned m = __match_any_sync(0xffffffffu, d);
+        if (valid && (m & lt) == 0) wh[wid][d] += __popc(m);   // the lowest lane of every digit group
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // digit `tid`: where each warp's items of that digit start in the output
+        unsigned run = (unsigned)hist_scan[(size_t)tid * nblk + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            const unsigned c = wh[w][tid];
+            wh[w][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < RS_SUB; ++s) {
+        const size_t idx = base + s * 32 + lane;
+        const bool valid = idx < n;
+        const int d = valid ? (int)((k[s] >> shift) & 255u) : 256 + lane;
+        const unsigned m = __match_any_sync(0xffffffffu, d);
+        unsigned pos = 0;
+        if (valid) pos = wh[wid][d] + __popc(m & lt);
+        __syncwarp();
+        if (valid && (m & lt) == 0) wh[wid][d] += __popc(m);
+        __syncwarp();
+        if (valid) {
+            keys_out[pos] = k[s];
+            vals_out[pos] = v[s];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stage F: queue order -> q_par (position of the parent, 1-based), q_acum
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int FN_THREADS = 256, FN_ITEMS = 16, FN_TILE = FN_THREADS * FN_ITEMS;
+
+__global__ void __launch_bounds__(FN_THREADS)
+k_pf_final_sums(const uint32_t *__restrict__ keys, uint32_t n, int32_t *__restrict__ blk_sum) {
+    __shared__ int sm[33];
+    const size_t base = (size_t)blockIdx.x * FN_TILE + (size_t)threadIdx.x * FN_ITEMS;
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < FN_ITEMS; ++i)
+        if (base + i < n) s += (int)(keys[base + i] >> 28);
+    int tot;
+    block_scan_excl(s, sm, &tot);
+    if (threadIdx.x == 0) blk_sum[blockIdx.x] = tot;
+}
+
+// the children of queue position j occupy positions [cs(j), cs(j) + nch(j)), cs(j) = 1 + children of the positions before j
+__global__ void __launch_bounds__(FN_THREADS)
+k_pf_final_write(const uint32_t *__restrict__ keys, const int32_t *__restrict__ q_lin, uint32_t n,
+                 const int32_t *__restrict__ blk_scan, const uint32_t *__restrict__ S, int32_t *__restrict__ q_par,
+                 int32_t *__restrict__ q_acum, unsigned *__restrict__ stat) {
+    __shared__ int sm[33];
+    const size_t base = (size_t)blockIdx.x * FN_TILE + (size_t)threadIdx.x * FN_ITEMS;
+    int c[FN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < FN_ITEMS; ++i) {
+        c[i] = (base + i < n) ? (int)(keys[base + i] >> 28) : 0;
+        s += c[i];
+    }
+    int tot;
+    const int ex = block_scan_excl(s, sm, &tot);
+    long long cs = 1ll + blk_scan[blockIdx.x] + ex;
+#pragma unroll
+    for (int i = 0; i < FN_ITEMS; ++i) {
+        const size_t j = base + i;
+        if (j < n) {
+            for (int q = 0; q < c[i]; ++q) {
+                if (cs + q < (long long)n) q_par[cs + q] = (int32_t)(j + 1);
+                else atomicAdd(&stat[1], 1u);
+            }
+            cs += c[i];
+            q_acum[j] = (int32_t)S[q_lin[j]];
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) q_par[0] = 0;
+}
+
+// basin_acum on the table basin_find itself produced: the sizes are already known.  ok[0] = 0 when a drain id differs.
+__global__ void k_pf_acum_cached(const int32_t *__restrict__ basin_f, const int32_t *__restrict__ q_par,
+                                 const int32_t *__restrict__ q_acum, int n, int32_t *__restrict__ acum, int *__restrict__ bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = n - 1 - i;
+    if (basin_f[3 * (size_t)i] != q_par[p]) *bad = 1;
+    acum[i] = q_acum[p];
+}
+
+static void dump(wmf_ctx *ctx, const char *dir, const char *name, const void *dev, size_t bytes) {
+    if (!dir) return;
+    std::vector<char> h(bytes);
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(h.data(), dev, bytes, cudaMemcpyDeviceToHost);
+    const std::string path = std::string(dir) + "/pf_" + name + ".bin";
+    if (FILE *f = fopen(path.c_str(), "wb")) { fwrite(h.data(), 1, bytes, f); fclose(f); }
+}
+
+}  // namespace pf
+
+// Host side.  Leaves the queue in ctx->q_lin / q_par (what basin_cut reads) and the sizes in ctx->q_acum.
+int wmf_pathfind(wmf_ctx *ctx, Scope &sc, const int32_t *d_dir, int nc, int nr, int lin0, int32_t *n_out, int32_t *depth_out) {
+    using namespace pf;
+    const char *dumpdir = getenv("WMF_PF_DUMP");
+    const int ntx = (nc + TS - 1) / TS, nty = (nr + TS - 1) / TS;
+    const long long ntiles_ll = (long long)ntx * nty;
+    if (ntiles_ll * NSLOT >= INT_MAX) WMF_FAIL(ctx, WMF_ERR_ARG, "basin_find: raster too large for the tile graph");
+    const int ntiles = (int)ntiles_ll, n_nodes = ntiles * NSLOT;
+    const size_t cells = (size_t)nc * nr;
+    int32_t *pterm, *bdown, *bnext, *nxA, *nxB;
+    uint32_t *lsize, *boff, *S;
+    unsigned long long *w;
+    unsigned char *leaf;
+    uint2 *eho, *dpA, *dpB, *LR;
+    unsigned *stat;
+    int *more;
+    WMF_TRY(sc.alloc(&pterm, (size_t)n_nodes)); WMF_TRY(sc.alloc(&bdown, (size_t)n_nodes)); WMF_TRY(sc.alloc(&bnext, (size_t)n_nodes));
+    WMF_TRY(sc.alloc(&lsize, (size_t)n_nodes)); WMF_TRY(sc.alloc(&boff, (size_t)n_nodes)); WMF_TRY(sc.alloc(&w, (size_t)n_nodes));
+    WMF_TRY(sc.alloc(&leaf, (size_t)n_nodes)); WMF_TRY(sc.alloc(&eho, (size_t)n_nodes));
+    WMF_TRY(sc.alloc(&nxA, (size_t)n_nodes)); WMF_TRY(sc.alloc(&nxB, (size_t)n_nodes));
+    WMF_TRY(sc.alloc(&dpA, (size_t)n_nodes)); WMF_TRY(sc.alloc(&dpB, (size_t)n_nodes));
+    WMF_TRY(sc.alloc(&S, cells)); WMF_TRY(sc.alloc(&LR, cells));
+    WMF_TRY(sc.alloc(&stat, 2)); WMF_TRY(sc.alloc(&more, 1));
+    CU_TRY(ctx, cudaMemsetAsync(stat, 0, 2 * sizeof(unsigned), ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(boff, 0, sizeof(uint32_t) * (size_t)n_nodes, ctx->stream));
+    const int B = 256, GN = grid_for(n_nodes, B);
+    // A
+    LAUNCH(ctx, k_pf_local1, ntiles, NTHR, 0, d_dir, nc, nr, ntx, lin0, pterm, bdown, lsize);
+    // B
+    LAUNCH(ctx, k_pf_bg_init, GN, B, 0, n_nodes, pterm, bdown, lsize, bnext, w);
+    LAUNCH(ctx, k_pf_bg_count, GN, B, 0, n_nodes, bnext, w);
+    LAUNCH(ctx, k_pf_bg_leaves, GN, B, 0, n_nodes, bdown, w, leaf);
+    LAUNCH(ctx, k_pf_bg_climb, GN, B, 0, n_nodes, bnext, leaf, w);
+    // C
+    CU_TRY(ctx, cudaFuncSetAttribute(k_pf_local2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Local2Smem)));
+    LAUNCH(ctx, k_pf_local2, ntiles, NTHR, sizeof(Local2Smem), d_dir, nc, nr, ntx, lin0, w, S, LR, boff, eho);
+    uint32_t n_basin = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&n_basin, S + lin0, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    // D
+    LAUNCH(ctx, k_pf_bd_init, GN, B, 0, n_nodes, bdown, bnext, boff, eho, nxA, dpA);
+    for (int round = 0; round < 40; ++round) {
+        CU_TRY(ctx, cudaMemsetAsync(more, 0, sizeof(int), ctx->stream));
+        LAUNCH(ctx, k_pf_bd_jump, GN, B, 0, n_nodes, nxA, dpA, nxB, dpB, more);
+        std::swap(nxA, nxB);
+        std::swap(dpA, dpB);
+        int h_more = 0;
+        CU_TRY(ctx, cudaMemcpyAsync(&h_more, more, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!h_more) break;  // (what is still pending after 40 doublings is a cycle across tiles: not in the basin)
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_basin == 0 || n_basin > cells) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "basin_find: inconsistent basin size %u", n_basin);
+    if (dumpdir) {
+        dump(ctx, dumpdir, "pterm", pterm, 4 * (size_t)n_nodes); dump(ctx, dumpdir, "bdown", bdown, 4 * (size_t)n_nodes);
+        dump(ctx, dumpdir, "lsize", lsize, 4 * (size_t)n_nodes); dump(ctx, dumpdir, "bnext", bnext, 4 * (size_t)n_nodes);
+        dump(ctx, dumpdir, "w", w, 8 * (size_t)n_nodes); dump(ctx, dumpdir, "boff", boff, 4 * (size_t)n_nodes);
+        dump(ctx, dumpdir, "eho", eho, 8 * (size_t)n_nodes); dump(ctx, dumpdir, "nx", nxA, 4 * (size_t)n_nodes);
+        dump(ctx, dumpdir, "dp", dpA, 8 * (size_t)n_nodes); dump(ctx, dumpdir, "S", S, 4 * cells); dump(ctx, dumpdir, "LR", LR, 8 * cells);
+    }
+    // E
+    const uint32_t n = n_basin;
+    uint32_t *k0, *k1, *v0, *v1;
+    WMF_TRY(sc.alloc(&k0, (size_t)n)); WMF_TRY(sc.alloc(&k1, (size_t)n));
+    WMF_TRY(sc.alloc(&v0, (size_t)n)); WMF_TRY(sc.alloc(&v1, (size_t)n));
+    CU_TRY(ctx, cudaMemsetAsync(k0, 0xff, sizeof(uint32_t) * (size_t)n, ctx->stream));  // a slot nobody writes shows up as depth 2^28-1
+    {
+        dim3 grid((unsigned)ntx, (unsigned)((nr + 3) / 4));
+        LAUNCH(ctx, k_pf_emit, grid, 256, 0, LR, nc, nr, ntx, nxA, dpA, n, k0, v0, stat);
+    }
+    unsigned h_stat[2] = {0, 0};
+    CU_TRY(ctx, cudaMemcpyAsync(h_stat, stat, sizeof h_stat, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_stat[1]) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "basin_find: %u cells fell outside the preorder range (internal error or depth >= 2^28)", h_stat[1]);
+    const unsigned maxdepth = h_stat[0];
+    if (dumpdir) { dump(ctx, dumpdir, "keys0", k0, 4 * (size_t)n); dump(ctx, dumpdir, "vals0", v0, 4 * (size_t)n); }
+    // sort by depth, stable: the order inside a level stays the preorder
+    int bits = 0;
+    while (bits < 28 && (maxdepth >> bits) != 0) ++bits;
+    const int passes = (bits + 7) / 8;
+    const int nblk = (int)(((size_t)n + RS_TILE - 1) / RS_TILE);
+    int32_t *hist = nullptr, *hist_scan = nullptr;
+    if (passes) {
+        WMF_TRY(sc.alloc(&hist, (size_t)256 * nblk));
+        WMF_TRY(sc.alloc(&hist_scan, (size_t)256 * nblk));
+    }
+    uint32_t *kin = k0, *vin = v0, *kout = k1, *vout = v1;
+    for (int p = 0; p < passes; ++p) {
+        uint32_t *vdst = (p == passes - 1) ? reinterpret_cast<uint32_t *>(ctx->q_lin) : vout;
+        LAUNCH(ctx, k_rs_hist, nblk, RS_THREADS, 0, kin, n, 8 * p, nblk, hist);
+        WMF_TRY(wmf_device_exclusive_scan_i32(ctx, sc, hist, hist_scan, (int64_t)256 * nblk, nullptr));
+        LAUNCH(ctx, k_rs_scatter, nblk, RS_THREADS, 0, kin, vin, n, 8 * p, nblk, hist_scan, kout, vdst);
+        std::swap(kin, kout);
+        vin = vdst;
+        vout = (vdst == v1) ? v0 : v1;
+    }
+    if (!passes) CU_TRY(ctx, cudaMemcpyAsync(ctx->q_lin, v0, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    // F
+    const int fblk = (int)(((size_t)n + FN_TILE - 1) / FN_TILE);
+    int32_t *blk_sum, *blk_scan;
+    WMF_TRY(sc.alloc(&blk_sum, (size_t)fblk));
+    WMF_TRY(sc.alloc(&blk_scan, (size_t)fblk));
+    LAUNCH(ctx, k_pf_final_sums, fblk, FN_THREADS, 0, kin, n, blk_sum);
+    WMF_TRY(wmf_device_exclusive_scan_i32(ctx, sc, blk_sum, blk_scan, fblk, nullptr));
+    LAUNCH(ctx, k_pf_final_write, fblk, FN_THREADS, 0, kin, ctx->q_lin, n, blk_scan, S, ctx->q_par, ctx->q_acum, stat);
+    CU_TRY(ctx, cudaMemcpyAsync(h_stat, stat, sizeof h_stat, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, cudaGetLastError());
+    if (h_stat[1]) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "basin_find: the child counts do not add up to the basin size (internal error)");
+    *n_out = (int32_t)n;
+    *depth_out = (int32_t)maxdepth + 1;
+    return WMF_OK;
+}
+
+// basin_acum for the very table basin_find produced (checked drain id by drain id); returns 1 in *used when it applied
+int wmf_pathfind_acum_cached(wmf_ctx *ctx, Scope &sc, const int32_t *d_basin_f, int n, int32_t *d_acum, int *used) {
+    *used = 0;
+    if (!ctx->q_acum_valid || n != ctx->find_n || !ctx->q_acum) return WMF_OK;
+    int *bad;
+    WMF_TRY(sc.alloc(&bad, 1));
+    CU_TRY(ctx, cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+    LAUNCH(ctx, pf::k_pf_acum_cached, grid_for(n, 256), 256, 0, d_basin_f, ctx->q_par, ctx->q_acum, n, d_acum, bad);
+    int h_bad = 1;
+    CU_TRY(ctx, cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *used = h_bad ? 0 : 1;
+    return WMF_OK;
+}

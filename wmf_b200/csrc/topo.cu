@@ -793,6 +793,16 @@ static int acum_device(wmf_ctx *ctx, Scope &sc, const int32_t *d_drain, int stri
     return WMF_OK;
 }
 
+// basin_acum of a (3,N) table: the sizes basin_find computed on its way when the table is the one it produced (every
+// drain id is compared), the barrier-free climb for any other upstream-first table
+static int acum_table(wmf_ctx *ctx, Scope &sc, const int32_t *d_b, int n, int32_t *d_acum) {
+    int used = 0;
+    const char *e = getenv("WMF_ACUM_ALGO");
+    if (!e || strcmp(e, "climb") != 0) WMF_TRY(wmf_pathfind_acum_cached(ctx, sc, d_b, n, d_acum, &used));
+    if (used) return WMF_OK;
+    return acum_device(ctx, sc, d_b, 3, n, d_acum);
+}
+
 static int acum_var_device(wmf_ctx *ctx, Scope &sc, const int32_t *d_drain, int stride, int n, const float *d_var,
                            float *d_out, int positive_only) {
     int32_t *cnt, *start, *cursor, *child, *pending;
@@ -835,12 +845,15 @@ int wmf_basin_find(wmf_ctx *ctx, float x, float y, const int32_t *dir, int32_t n
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         if (ctx->q_lin) cudaFree(ctx->q_lin);
         if (ctx->q_par) cudaFree(ctx->q_par);
-        ctx->q_lin = ctx->q_par = nullptr;
+        if (ctx->q_acum) cudaFree(ctx->q_acum);
+        ctx->q_lin = ctx->q_par = ctx->q_acum = nullptr;
         ctx->q_cap = 0;
         CU_TRY(ctx, cudaMalloc(&ctx->q_lin, sizeof(int32_t) * (size_t)celTot));
         CU_TRY(ctx, cudaMalloc(&ctx->q_par, sizeof(int32_t) * (size_t)celTot));
+        CU_TRY(ctx, cudaMalloc(&ctx->q_acum, sizeof(int32_t) * (size_t)celTot));
         ctx->q_cap = celTot;
     }
+    ctx->q_acum_valid = false;
     if (coli <= 0 || fili <= 0) {
         // outlet outside the map: the Fortran returns a one-cell "basin" holding (-999 | col, -999 | fil)
         ctx->find_n = 1;
@@ -858,11 +871,23 @@ int wmf_basin_find(wmf_ctx *ctx, float x, float y, const int32_t *dir, int32_t n
     Scope sc(ctx);
     const int32_t *d_dir;
     WMF_TRY(sc.in(dir, (size_t)celTot, &d_dir));
+    const int lin0 = (fili - 1) * nc + (coli - 1);
+    // WMF_FIND_ALGO = tiles (default: tile decomposition, pathfind.cu) | bfs (the level-by-level search below, kept as
+    // the cross-check)
+    const char *algo = getenv("WMF_FIND_ALGO");
+    if (!algo || strcmp(algo, "bfs") != 0) {
+        int32_t n = 0, depth = 0;
+        WMF_TRY(wmf_pathfind(ctx, sc, d_dir, nc, nr, lin0, &n, &depth));
+        ctx->find_n = n;
+        ctx->find_depth = depth;
+        ctx->q_acum_valid = true;
+        *nceldas = n;
+        return WMF_OK;
+    }
     FindState *st;
     unsigned long long *slots;
     WMF_TRY(sc.alloc((void **)&st, sizeof(FindState)));
     WMF_TRY(sc.alloc(&slots, (size_t)2 * FIND_MAX_CTAS));
-    const int lin0 = (fili - 1) * nc + (coli - 1);
     LAUNCH(ctx, k_find_seed, 1, 1, 0, ctx->q_lin, ctx->q_par, lin0, slots, st);
     int occ = 0;
     CU_TRY(ctx, cudaFuncSetAttribute(k_basin_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIND_SMEM));
@@ -932,7 +957,7 @@ int wmf_basin_acum(wmf_ctx *ctx, const int32_t *basin_f, int32_t n, int32_t *acu
     int32_t *d_a;
     WMF_TRY(sc.in(basin_f, (size_t)3 * n, &d_b));
     WMF_TRY(sc.out(acum, (size_t)n, &d_a));
-    WMF_TRY(acum_device(ctx, sc, d_b, 3, n, d_a));
+    WMF_TRY(acum_table(ctx, sc, d_b, n, d_a));
     ctx->scalars[0] = (float)n * (ctx->geo.dxp * ctx->geo.dxp) / 1e6f;  // cuencas.f90:679
     return sc.finish();
 }
@@ -982,7 +1007,7 @@ int wmf_basin_basics(wmf_ctx *ctx, const int32_t *basin_f, const float *dem, con
     WMF_TRY(sc.out(lng, (size_t)n, &d_l));
     WMF_TRY(sc.out(pend, (size_t)n, &d_p));
     WMF_TRY(sc.out(elev, (size_t)n, &d_e));
-    WMF_TRY(acum_device(ctx, sc, d_b, 3, n, d_a));
+    WMF_TRY(acum_table(ctx, sc, d_b, n, d_a));
     LAUNCH(ctx, k_basics_cell, grid_for(n, 256), 256, 0, d_b, d_dem, d_dir, n, g.dxp, d_l, d_p, d_e);
     // scalars: means in fp64, centroid = median column / row (the Fortran sorts X and Y, cuencas.f90:650-657)
     double *d_sums;
