@@ -14,6 +14,25 @@ struct wmf_geo {
     float xll = 0.f, yll = 0.f, dx = 1.f, dy = 1.f, dxp = 1.f, nodata = -9999.f;
 };
 
+// The plan of a SHIA sweep (shia.cu: shia_build_plan), kept between runs of the same basin
+struct wmf_shia_plan {
+    bool valid = false;
+    int N = 0;
+    unsigned long long hash = 0;   // checksum of drain ids, unit types, control points
+    int32_t Lmax = 0;
+    int64_t nq = 0, nh = 0, n_hill = 0;
+    uint32_t *tw = nullptr;
+    int32_t *cs = nullptr, *hidx = nullptr, *cidx = nullptr, *ctrl_cells = nullptr, *ctrlh_cells = nullptr;
+    std::vector<int32_t> h_first, h_hfirst;
+    void release() {
+        void *p[] = {tw, cs, hidx, cidx, ctrl_cells, ctrlh_cells};
+        for (void *q : p)
+            if (q) cudaFree(q);
+        tw = nullptr; cs = hidx = cidx = ctrl_cells = ctrlh_cells = nullptr;
+        valid = false;
+    }
+};
+
 struct wmf_ctx {
     int device = 0;
     int num_sms = 148;
@@ -36,6 +55,7 @@ struct wmf_ctx {
     // basin_subbasin_nod state (the reference's module global sub_basins_temp(2,n_nodos), returned by basin_subbasin_cut)
     int32_t *sub_basins = nullptr;
     int32_t sub_n = 0;
+    wmf_shia_plan plan;
     // timing of the last shia run
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;

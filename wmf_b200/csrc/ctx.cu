@@ -39,6 +39,7 @@ int wmf_ctx_destroy(wmf_ctx *ctx) {
     if (ctx->q_lin) cudaFree(ctx->q_lin);
     if (ctx->q_par) cudaFree(ctx->q_par);
     if (ctx->q_acum) cudaFree(ctx->q_acum);
+    ctx->plan.release();
     if (ctx->sub_basins) cudaFree(ctx->sub_basins);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

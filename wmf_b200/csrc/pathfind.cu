@@ -428,21 +428,27 @@ __global__ void k_pf_bd_jump(int n_nodes, const int32_t *__restrict__ nx_in, con
 // ---------------------------------------------------------------------------------------------------------------------
 // stage E: every cell of the basin writes (depth | children << 28, raster index) at position preorder
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// One CTA per tile: the DFS preorder is spatially local (the next cell in preorder is the first tributary, or the next
+// sibling of a near ancestor), so the cells of a tile own long runs of consecutive preorder positions; written by one
+// CTA within microseconds they merge into full sectors in L2.
+__global__ void __launch_bounds__(NTHR)
 k_pf_emit(const uint2 *__restrict__ LR, int nc, int nr, int ntx, const int32_t *__restrict__ nx, const uint2 *__restrict__ dp,
           uint32_t n_basin, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, unsigned *__restrict__ stat /* [0] max depth, [1] errors */) {
-    const int gc = blockIdx.x * TS + (threadIdx.x & (TS - 1));
-    const int gr = blockIdx.y * 4 + (threadIdx.x >> 6);
-    unsigned depth = 0;
-    bool ok = false;
-    if (gc < nc && gr < nr) {
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    const int r0 = (tile / ntx) * TS, c0 = (tile % ntx) * TS;
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int li = k * NTHR + tid, gr = r0 + (li >> 6), gc = c0 + (li & (TS - 1));
+        if (gc >= nc || gr >= nr) continue;
         const size_t lin = (size_t)gr * nc + gc;
         const uint2 lr = LR[lin];
         const unsigned tc = lr.x & 0xFFFFu, h = (lr.x >> 16) & 0xFFFu, nch = lr.x >> 28;
-        unsigned pre = 0;
+        unsigned depth = 0, pre = 0;
+        bool ok = false;
         if (tc == T_ROOT_OUT) { depth = h; pre = lr.y; ok = true; }
         else if (tc != T_DEAD) {
-            const int node = ((gr >> 6) * ntx + blockIdx.x) * NSLOT + (int)tc;
+            const int node = tile * NSLOT + (int)tc;
             if (nx[node] == ROOT_OUT) {
                 const uint2 v = dp[node];
                 depth = v.x + h;
@@ -454,16 +460,33 @@ k_pf_emit(const uint2 *__restrict__ LR, int nc, int nr, int ntx, const int32_t *
             if (pre < n_basin && depth < (1u << 28)) {
                 keys[pre] = depth | (nch << 28);
                 vals[pre] = (uint32_t)lin;
+                m = max(m, depth);
             } else {
                 atomicAdd(&stat[1], 1u);
-                depth = 0;
             }
         }
     }
-    unsigned m = ok ? depth : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0 && m) atomicMax(&stat[0], m);
+}
+
+// The reference's search treats the outlet like any other cell: if the cell the outlet itself drains to belongs to the
+// basin, the outlet is found again as a tributary and the queue never ends (cuencas.f90:552-589).  stat[2] = 1 then.
+__global__ void k_pf_outlet_check(const int32_t *__restrict__ dir, const uint2 *__restrict__ LR, int nc, int nr, int ntx, int lin0,
+                                  const int32_t *__restrict__ nx, unsigned *__restrict__ stat) {
+    const int d = dir[lin0];
+    if (d < 1 || d > 9 || d == 5) return;
+    int dc, dr;
+    code_move(d, dc, dr);
+    const int gr = lin0 / nc + dr, gc = lin0 % nc + dc;
+    if (gr < 0 || gr >= nr || gc < 0 || gc >= nc) return;
+    const uint2 lr = LR[(size_t)gr * nc + gc];
+    const unsigned tc = lr.x & 0xFFFFu;
+    bool in_basin = false;
+    if (tc == T_ROOT_OUT) in_basin = true;
+    else if (tc != T_DEAD) in_basin = nx[((gr >> 6) * ntx + (gc >> 6)) * NSLOT + (int)tc] == ROOT_OUT;
+    if (in_basin) stat[2] = 1u;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -630,8 +653,8 @@ int wmf_pathfind(wmf_ctx *ctx, Scope &sc, const int32_t *d_dir, int nc, int nr, 
     WMF_TRY(sc.alloc(&nxA, (size_t)n_nodes)); WMF_TRY(sc.alloc(&nxB, (size_t)n_nodes));
     WMF_TRY(sc.alloc(&dpA, (size_t)n_nodes)); WMF_TRY(sc.alloc(&dpB, (size_t)n_nodes));
     WMF_TRY(sc.alloc(&S, cells)); WMF_TRY(sc.alloc(&LR, cells));
-    WMF_TRY(sc.alloc(&stat, 2)); WMF_TRY(sc.alloc(&more, 1));
-    CU_TRY(ctx, cudaMemsetAsync(stat, 0, 2 * sizeof(unsigned), ctx->stream));
+    WMF_TRY(sc.alloc(&stat, 4)); WMF_TRY(sc.alloc(&more, 1));
+    CU_TRY(ctx, cudaMemsetAsync(stat, 0, 4 * sizeof(unsigned), ctx->stream));
     CU_TRY(ctx, cudaMemsetAsync(boff, 0, sizeof(uint32_t) * (size_t)n_nodes, ctx->stream));
     const int B = 256, GN = grid_for(n_nodes, B);
     // A
@@ -673,13 +696,12 @@ int wmf_pathfind(wmf_ctx *ctx, Scope &sc, const int32_t *d_dir, int nc, int nr, 
     WMF_TRY(sc.alloc(&k0, (size_t)n)); WMF_TRY(sc.alloc(&k1, (size_t)n));
     WMF_TRY(sc.alloc(&v0, (size_t)n)); WMF_TRY(sc.alloc(&v1, (size_t)n));
     CU_TRY(ctx, cudaMemsetAsync(k0, 0xff, sizeof(uint32_t) * (size_t)n, ctx->stream));  // a slot nobody writes shows up as depth 2^28-1
-    {
-        dim3 grid((unsigned)ntx, (unsigned)((nr + 3) / 4));
-        LAUNCH(ctx, k_pf_emit, grid, 256, 0, LR, nc, nr, ntx, nxA, dpA, n, k0, v0, stat);
-    }
-    unsigned h_stat[2] = {0, 0};
+    LAUNCH(ctx, k_pf_emit, ntiles, NTHR, 0, LR, nc, nr, ntx, nxA, dpA, n, k0, v0, stat);
+    LAUNCH(ctx, k_pf_outlet_check, 1, 1, 0, d_dir, LR, nc, nr, ntx, lin0, nxA, stat);
+    unsigned h_stat[4] = {0, 0, 0, 0};
     CU_TRY(ctx, cudaMemcpyAsync(h_stat, stat, sizeof h_stat, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_stat[2]) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "basin_find: the DIR map is cyclic -- the cell the outlet drains to drains back into the outlet");
     if (h_stat[1]) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "basin_find: %u cells fell outside the preorder range (internal error or depth >= 2^28)", h_stat[1]);
     const unsigned maxdepth = h_stat[0];
     if (dumpdir) { dump(ctx, dumpdir, "keys0", k0, 4 * (size_t)n); dump(ctx, dumpdir, "vals0", v0, 4 * (size_t)n); }

@@ -1505,6 +1505,26 @@ __global__ void k_compact(const int32_t *__restrict__ flag, const int32_t *__res
     if (i < n && flag[i]) list[pos[i]] = i;
 }
 
+// 64-bit order-independent checksum of the arrays a plan is derived from (drain ids, unit types, control points): the key
+// of the plan cache.  Every element is mixed with its position, the mixes are summed.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+__global__ void k_plan_hash(const int32_t *__restrict__ drena, int stride, const int32_t *__restrict__ unit_type,
+                            const int32_t *__restrict__ control, const int32_t *__restrict__ control_h, int n,
+                            unsigned long long *__restrict__ out) {
+    unsigned long long h = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long a = (unsigned)drena[(size_t)i * stride], b = (unsigned)unit_type[i];
+        const unsigned long long c = control ? (control[i] != 0) : 0, d = control_h ? (control_h[i] != 0) : 0;
+        h += mix64(((unsigned long long)i << 32) ^ a) + mix64(((unsigned long long)i << 36) ^ (b << 2) ^ (c << 1) ^ d ^ 0x9e3779b97f4a7c15ull);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, h);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // init / finalize
 // ---------------------------------------------------------------------------------------------------
@@ -1999,6 +2019,98 @@ static int tb_steps(int T, bool eligible, long long cells_x_members, int Lmax, i
     return 1;
 }
 
+// The plan of a sweep: hop level of every cell (pointer doubling), child ranges, packed topology words, the sorted lists
+// of control cells and the hillslope / channel role lists.  Depends on the drain ids, unit types and control points only;
+// wmf_shia_run keeps it in the context and rebuilds it when their checksum changes.
+static int shia_build_plan(wmf_ctx *ctx, Scope &sc, const int32_t *drena, int stride, int N, const int32_t *d_unit,
+                           const int32_t *d_control, const int32_t *d_controlh, wmf_shia_plan &pl) {
+    int32_t *lev_a, *lev_b, *jmp_a, *jmp_b, *nch, *cmin, *cmax, *cs, *level_first, *fq, *fh, *posq, *posh;
+    uint32_t *tw;
+    int *d_err;
+    WMF_TRY(sc.alloc(&lev_a, (size_t)N)); WMF_TRY(sc.alloc(&lev_b, (size_t)N));
+    WMF_TRY(sc.alloc(&jmp_a, (size_t)N)); WMF_TRY(sc.alloc(&jmp_b, (size_t)N));
+    WMF_TRY(sc.alloc(&nch, (size_t)N)); WMF_TRY(sc.alloc(&cmin, (size_t)N)); WMF_TRY(sc.alloc(&cmax, (size_t)N));
+    WMF_TRY(sc.alloc(&cs, (size_t)N)); WMF_TRY(sc.alloc(&tw, (size_t)N));
+    WMF_TRY(sc.alloc(&fq, (size_t)N)); WMF_TRY(sc.alloc(&fh, (size_t)N));
+    WMF_TRY(sc.alloc(&posq, (size_t)N)); WMF_TRY(sc.alloc(&posh, (size_t)N));
+    WMF_TRY(sc.alloc(&d_err, 2));
+    CU_TRY(ctx, cudaMemsetAsync(d_err, 0, 2 * sizeof(int), ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(nch, 0, sizeof(int32_t) * (size_t)N, ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(cmin, 0x7f, sizeof(int32_t) * (size_t)N, ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(cmax, 0, sizeof(int32_t) * (size_t)N, ctx->stream));
+    const int B = 256, G = grid_for(N, B);
+    LAUNCH(ctx, k_plan_init, G, B, 0, drena, stride, N, lev_a, jmp_a, nch, cmin, cmax, d_err);
+    int herr = 0;
+    WMF_TRY(read_flag(ctx, d_err, &herr));
+    if (herr == 1) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "shia: drena is not upstream-first (need 0 <= id < n and parent index > cell index)");
+    if (herr == 2) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "shia: drena has an outlet (id 0) that is not the last cell");
+    {
+        int32_t dlast = 1;
+        CU_TRY(ctx, cudaMemcpyAsync(&dlast, drena + (size_t)(N - 1) * stride, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (dlast != 0) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "shia: the last cell must be the outlet (drena == 0)");
+    }
+    for (int round = 0; round < 40; ++round) {
+        CU_TRY(ctx, cudaMemsetAsync(d_err + 1, 0, sizeof(int), ctx->stream));
+        LAUNCH(ctx, k_plan_jump, G, B, 0, lev_a, jmp_a, N, lev_b, jmp_b, d_err + 1);
+        std::swap(lev_a, lev_b);
+        std::swap(jmp_a, jmp_b);
+        int more = 0;
+        WMF_TRY(read_flag(ctx, d_err + 1, &more));
+        if (!more) break;
+    }
+    int32_t Lmax = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&Lmax, lev_a, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (Lmax < 0 || Lmax >= (1 << 24)) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "shia: tree depth %d unsupported", Lmax);
+    WMF_TRY(sc.alloc(&level_first, (size_t)Lmax + 2));
+    CU_TRY(ctx, cudaMemsetAsync(level_first, 0xff, sizeof(int32_t) * ((size_t)Lmax + 2), ctx->stream));
+    LAUNCH(ctx, k_plan_pack, G, B, 0, lev_a, nch, cmin, cmax, d_unit, d_control, d_controlh, N, tw, cs, level_first, fq, fh, d_err);
+    WMF_TRY(read_flag(ctx, d_err, &herr));
+    if (herr == 3 || herr == 5)
+        WMF_FAIL(ctx, WMF_ERR_TOPOLOGY,
+                 "shia: cells are not in basin_find order (levels must be non-increasing and the cells draining into one cell "
+                 "contiguous); pass the structure produced by basin_find/basin_cut");
+    if (herr == 4 || herr == 6) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "shia: more than 15 cells drain into one cell, or depth >= 2^24");
+    if (herr == 7) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: unit_type must be 1, 2 or 3");
+    std::vector<int32_t> h_first((size_t)Lmax + 2);
+    CU_TRY(ctx, cudaMemcpyAsync(h_first.data(), level_first, sizeof(int32_t) * ((size_t)Lmax + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    int64_t nq = 0, nh = 0;
+    WMF_TRY(wmf_device_exclusive_scan_i32(ctx, sc, fq, posq, N, &nq));
+    WMF_TRY(wmf_device_exclusive_scan_i32(ctx, sc, fh, posh, N, &nh));
+    int32_t *ctrl_cells, *ctrlh_cells;
+    WMF_TRY(sc.alloc(&ctrl_cells, (size_t)nq + 1));
+    WMF_TRY(sc.alloc(&ctrlh_cells, (size_t)nh + 1));
+    LAUNCH(ctx, k_compact, G, B, 0, fq, posq, N, ctrl_cells);
+    LAUNCH(ctx, k_compact, G, B, 0, fh, posh, N, ctrlh_cells);
+    // role lists of the time-blocked kernel
+    int32_t *is_h, *hpos, *d_hfirst;
+    int64_t n_hill = 0;
+    WMF_TRY(sc.alloc(&is_h, (size_t)N)); WMF_TRY(sc.alloc(&hpos, (size_t)N));
+    WMF_TRY(sc.alloc(&d_hfirst, (size_t)Lmax + 2));
+    LAUNCH(ctx, k_role_flags, G, B, 0, tw, N, is_h);
+    WMF_TRY(wmf_device_exclusive_scan_i32(ctx, sc, is_h, hpos, N, &n_hill));
+    CU_TRY(ctx, cudaMalloc(&pl.hidx, sizeof(int32_t) * (size_t)N));
+    CU_TRY(ctx, cudaMalloc(&pl.cidx, sizeof(int32_t) * (size_t)N));
+    LAUNCH(ctx, k_role_lists, G, B, 0, is_h, hpos, N, pl.hidx, pl.cidx);
+    LAUNCH(ctx, k_role_level_first, grid_for(Lmax + 1, B), B, 0, level_first, hpos, Lmax + 1, d_hfirst);
+    pl.h_hfirst.assign((size_t)Lmax + 2, 0);
+    CU_TRY(ctx, cudaMemcpyAsync(pl.h_hfirst.data(), d_hfirst, sizeof(int32_t) * ((size_t)Lmax + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    pl.h_first.swap(h_first);
+    // the plan outlives this call: its arrays move from the call's arena to buffers the context owns
+    CU_TRY(ctx, cudaMalloc(&pl.tw, sizeof(uint32_t) * (size_t)N));
+    CU_TRY(ctx, cudaMalloc(&pl.cs, sizeof(int32_t) * (size_t)N));
+    CU_TRY(ctx, cudaMalloc(&pl.ctrl_cells, sizeof(int32_t) * ((size_t)nq + 1)));
+    CU_TRY(ctx, cudaMalloc(&pl.ctrlh_cells, sizeof(int32_t) * ((size_t)nh + 1)));
+    CU_TRY(ctx, cudaMemcpyAsync(pl.tw, tw, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(pl.cs, cs, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(pl.ctrl_cells, ctrl_cells, sizeof(int32_t) * ((size_t)nq + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(pl.ctrlh_cells, ctrlh_cells, sizeof(int32_t) * ((size_t)nh + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // h_first / h_hfirst are complete
+    pl.Lmax = Lmax; pl.nq = nq; pl.nh = nh; pl.n_hill = n_hill;
+    return WMF_OK;
+}
+
 extern "C" {
 
 int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *in, wmf_shia_outputs *out) {
@@ -2109,70 +2221,34 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     // the small inputs are queued; now the first rain records start to travel while the sweep is planned
     WMF_TRY(rs.early(ctx, h_pos));
     mark("stage");
-    // ---- plan ----
-    int32_t *lev_a, *lev_b, *jmp_a, *jmp_b, *nch, *cmin, *cmax, *cs, *level_first, *fq, *fh, *posq, *posh;
-    uint32_t *tw;
-    int *d_err;
-    WMF_TRY(sc.alloc(&lev_a, (size_t)N)); WMF_TRY(sc.alloc(&lev_b, (size_t)N));
-    WMF_TRY(sc.alloc(&jmp_a, (size_t)N)); WMF_TRY(sc.alloc(&jmp_b, (size_t)N));
-    WMF_TRY(sc.alloc(&nch, (size_t)N)); WMF_TRY(sc.alloc(&cmin, (size_t)N)); WMF_TRY(sc.alloc(&cmax, (size_t)N));
-    WMF_TRY(sc.alloc(&cs, (size_t)N)); WMF_TRY(sc.alloc(&tw, (size_t)N));
-    WMF_TRY(sc.alloc(&fq, (size_t)N)); WMF_TRY(sc.alloc(&fh, (size_t)N));
-    WMF_TRY(sc.alloc(&posq, (size_t)N)); WMF_TRY(sc.alloc(&posh, (size_t)N));
-    WMF_TRY(sc.alloc(&d_err, 2));
-    CU_TRY(ctx, cudaMemsetAsync(d_err, 0, 2 * sizeof(int), ctx->stream));
-    CU_TRY(ctx, cudaMemsetAsync(nch, 0, sizeof(int32_t) * (size_t)N, ctx->stream));
-    CU_TRY(ctx, cudaMemsetAsync(cmin, 0x7f, sizeof(int32_t) * (size_t)N, ctx->stream));
-    CU_TRY(ctx, cudaMemsetAsync(cmax, 0, sizeof(int32_t) * (size_t)N, ctx->stream));
-    const int B = 256, G = grid_for(N, B);
-    LAUNCH(ctx, k_plan_init, G, B, 0, P.drena, stride, N, lev_a, jmp_a, nch, cmin, cmax, d_err);
-    int herr = 0;
-    WMF_TRY(read_flag(ctx, d_err, &herr));
-    if (herr == 1) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "shia: drena is not upstream-first (need 0 <= id < n and parent index > cell index)");
-    if (herr == 2) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "shia: drena has an outlet (id 0) that is not the last cell");
+    // ---- plan: levels, child ranges, role lists -- cached on a checksum of the arrays it derives from ----
+    // (a calibration loop or an ensemble re-runs the same basin thousands of times: nothing is re-planned, no allocation
+    // and a single 8-byte read-back per run)
+    wmf_shia_plan &pl = ctx->plan;
     {
-        int32_t dlast = 1;
-        CU_TRY(ctx, cudaMemcpyAsync(&dlast, P.drena + (size_t)(N - 1) * stride, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        unsigned long long *d_hash, h_hash = 0;
+        WMF_TRY(sc.alloc(&d_hash, 1));
+        CU_TRY(ctx, cudaMemsetAsync(d_hash, 0, sizeof(unsigned long long), ctx->stream));
+        LAUNCH(ctx, k_plan_hash, std::min(grid_for(N, 256), ctx->num_sms * 8), 256, 0, P.drena, stride, d_unit, d_control, d_controlh, N, d_hash);
+        CU_TRY(ctx, cudaMemcpyAsync(&h_hash, d_hash, sizeof h_hash, cudaMemcpyDeviceToHost, ctx->stream));
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        if (dlast != 0) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "shia: the last cell must be the outlet (drena == 0)");
+        const bool hit = pl.valid && pl.N == N && pl.hash == h_hash && !(getenv("WMF_SHIA_PLAN_CACHE") && atoi(getenv("WMF_SHIA_PLAN_CACHE")) == 0);
+        if (!hit) {
+            pl.release();
+            WMF_TRY(shia_build_plan(ctx, sc, P.drena, stride, N, d_unit, d_control, d_controlh, pl));
+            pl.N = N;
+            pl.hash = h_hash;
+            pl.valid = true;
+        }
     }
-    for (int round = 0; round < 40; ++round) {
-        CU_TRY(ctx, cudaMemsetAsync(d_err + 1, 0, sizeof(int), ctx->stream));
-        LAUNCH(ctx, k_plan_jump, G, B, 0, lev_a, jmp_a, N, lev_b, jmp_b, d_err + 1);
-        std::swap(lev_a, lev_b);
-        std::swap(jmp_a, jmp_b);
-        int more = 0;
-        WMF_TRY(read_flag(ctx, d_err + 1, &more));
-        if (!more) break;
-    }
-    int32_t Lmax = 0;
-    CU_TRY(ctx, cudaMemcpyAsync(&Lmax, lev_a, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (Lmax < 0 || Lmax >= (1 << 24)) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "shia: tree depth %d unsupported", Lmax);
-    WMF_TRY(sc.alloc(&level_first, (size_t)Lmax + 2));
-    CU_TRY(ctx, cudaMemsetAsync(level_first, 0xff, sizeof(int32_t) * ((size_t)Lmax + 2), ctx->stream));
-    LAUNCH(ctx, k_plan_pack, G, B, 0, lev_a, nch, cmin, cmax, d_unit, d_control, d_controlh, N, tw, cs, level_first, fq, fh, d_err);
-    WMF_TRY(read_flag(ctx, d_err, &herr));
-    if (herr == 3 || herr == 5)
-        WMF_FAIL(ctx, WMF_ERR_TOPOLOGY,
-                 "shia: cells are not in basin_find order (levels must be non-increasing and the cells draining into one cell "
-                 "contiguous); pass the structure produced by basin_find/basin_cut");
-    if (herr == 4 || herr == 6) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "shia: more than 15 cells drain into one cell, or depth >= 2^24");
-    if (herr == 7) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: unit_type must be 1, 2 or 3");
-    std::vector<int32_t> h_first((size_t)Lmax + 2);
-    CU_TRY(ctx, cudaMemcpyAsync(h_first.data(), level_first, sizeof(int32_t) * ((size_t)Lmax + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    int64_t nq = 0, nh = 0;
-    WMF_TRY(wmf_device_exclusive_scan_i32(ctx, sc, fq, posq, N, &nq));
-    WMF_TRY(wmf_device_exclusive_scan_i32(ctx, sc, fh, posh, N, &nh));
+    const int32_t Lmax = pl.Lmax;
+    const int64_t nq = pl.nq, nh = pl.nh, n_hill = pl.n_hill;
+    const std::vector<int32_t> &h_first = pl.h_first, &h_hfirst = pl.h_hfirst;
     if (nq + 1 > cfg->n_cont) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: %lld control cells need n_cont >= %lld, got %d", (long long)nq, (long long)nq + 1, cfg->n_cont);
     if (nh > cfg->n_conth) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: %lld humidity control cells but n_conth = %d", (long long)nh, cfg->n_conth);
-    int32_t *ctrl_cells, *ctrlh_cells;
-    WMF_TRY(sc.alloc(&ctrl_cells, (size_t)nq + 1));
-    WMF_TRY(sc.alloc(&ctrlh_cells, (size_t)nh + 1));
-    LAUNCH(ctx, k_compact, G, B, 0, fq, posq, N, ctrl_cells);
-    LAUNCH(ctx, k_compact, G, B, 0, fh, posh, N, ctrlh_cells);
-    P.tw = tw; P.cs = cs; P.Lmax = Lmax;
-    P.ctrl_cells = ctrl_cells; P.ctrlh_cells = ctrlh_cells; P.n_ctrl = (int)nq; P.n_ctrlh = (int)nh;
+    const int B = 256, G = grid_for(N, B);
+    P.tw = pl.tw; P.cs = pl.cs; P.Lmax = Lmax;
+    P.ctrl_cells = pl.ctrl_cells; P.ctrlh_cells = pl.ctrlh_cells; P.n_ctrl = (int)nq; P.n_ctrlh = (int)nh;
 
     // ---- which kernel: the time-blocked wavefront unless an output only the one-step kernel produces is wanted ----
     const bool per_run = (M == 1);
@@ -2210,20 +2286,8 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     }
     if (sepr && (!in->conv || !in->stra || !in->pos_conv || !in->pos_stra || in->n_conv_records < 1 || in->n_stra_records < 1))
         WMF_FAIL(ctx, WMF_ERR_ARG, "shia: separate_rain = 1 needs the conv / stra tables and pos_conv / pos_stra");
-    std::vector<int32_t> h_hfirst;
-    int64_t n_hill = 0;
     if (KT) {
-        int32_t *is_h, *hpos, *hidx, *cidx, *d_hfirst;
-        WMF_TRY(sc.alloc(&is_h, (size_t)N)); WMF_TRY(sc.alloc(&hpos, (size_t)N));
-        WMF_TRY(sc.alloc(&hidx, (size_t)N)); WMF_TRY(sc.alloc(&cidx, (size_t)N));
-        WMF_TRY(sc.alloc(&d_hfirst, (size_t)Lmax + 2));
-        LAUNCH(ctx, k_role_flags, G, B, 0, tw, N, is_h);
-        WMF_TRY(wmf_device_exclusive_scan_i32(ctx, sc, is_h, hpos, N, &n_hill));
-        LAUNCH(ctx, k_role_lists, G, B, 0, is_h, hpos, N, hidx, cidx);
-        LAUNCH(ctx, k_role_level_first, grid_for(Lmax + 1, B), B, 0, level_first, hpos, Lmax + 1, d_hfirst);
-        h_hfirst.resize((size_t)Lmax + 2);
-        CU_TRY(ctx, cudaMemcpyAsync(h_hfirst.data(), d_hfirst, sizeof(int32_t) * ((size_t)Lmax + 1), cudaMemcpyDeviceToHost, ctx->stream));
-        P.hidx = hidx; P.cidx = cidx;
+        P.hidx = pl.hidx; P.cidx = pl.cidx;
         P.nb = (T + KT - 1) / KT;
         P.bal_direct = 1;
     }
