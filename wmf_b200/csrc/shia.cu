@@ -747,6 +747,36 @@ constexpr int TB_THREADS = TB_THREADS_N;
 #ifndef TB_MIN_BLOCKS_KIN   // kinematic hillslope tanks (calc_speed: five dependent pow per tank and step): 85 registers instead
 #define TB_MIN_BLOCKS_KIN 3 // of 64 + 268 B of spills; C2 with speed_type = [2,2,1], 400 steps: 33.0 -> 31.3 ms (2 blocks: 37.6)
 #endif
+// Asynchronous staging of a time block's inputs (WMF_TB_STAGE=0 compiles it out for A/B runs): everything a thread reads
+// during its K steps -- the float4 its first two tributaries sent at each step and the K rain values -- was written by the
+// previous wave, so it is requested with cp.async right after griddepcontrol.wait and lands in shared memory while the
+// first step computes; no registers are held for it.  Blocks of up to 4 steps (36 KB per 256-thread CTA at K = 4).
+#ifndef WMF_TB_STAGE
+#define WMF_TB_STAGE 1
+#endif
+__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+template <int MAXN>
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {  // wait until at most n (0..MAXN) groups are pending
+    if constexpr (MAXN > 0) {
+        if (n >= MAXN) { cp_async_wait<MAXN>(); return; }
+        cp_async_wait_dyn<MAXN - 1>(n);
+    } else {
+        cp_async_wait<0>();
+    }
+}
+template <int K>
+struct TbStage {
+    static constexpr bool on = (WMF_TB_STAGE != 0) && (K <= 4);
+};
+
 #ifndef TB_MIN_BLOCKS_SED   // sediment / separate_rain variants (1 block per SM: C5 with SED + slides 248 -> 273 ms)
 #define TB_MIN_BLOCKS_SED 2
 #endif
@@ -808,7 +838,8 @@ __device__ __noinline__ void flood_dev(const ShiaP &P, int cell, int t, float Q,
 
 template <int K, bool CHAN, bool KIN, bool SED, bool SLIDES, bool SNAP, bool SEPF, bool SEPR, bool FLOOD>
 __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int jlo, const int jhi, const int tile,
-                                        float *__restrict__ s_acc) {
+                                        float *__restrict__ s_acc, float4 *__restrict__ s_kid, int32_t *__restrict__ s_rain) {
+    constexpr bool STAGE = TbStage<K>::on;
     const int N = P.N, M = P.M;
     const long long g = (long long)tile * 32 + (threadIdx.x & 31);
     int j, m;
@@ -937,6 +968,21 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
     const bool outlet = active && (cell == N - 1);
     const float4 *ob_in = P.outb4 + (size_t)(b & 1) * K * NM + (size_t)c0 * M + m;
     float4 *ob_out = P.outb4 + (size_t)(b & 1) * K * NM + base;
+    if (STAGE) {  // one commit group per step, waited for at the step that consumes it
+#pragma unroll
+        for (int tt = 0; tt < K; ++tt) {
+            if (tt < nt) {
+                const int p = __ldg(P.pos + t0 + tt);
+                if (p != 1) cp_async_4(s_rain + tt * TB_THREADS + threadIdx.x, P.rain + (size_t)(p - 1) * N + cell);
+            }
+            cp_async_commit();      // group 2 tt: the rain value of step tt (needed first)
+            if (tt < nt) {
+                if (nch > 0) cp_async_16(s_kid + (2 * tt) * TB_THREADS + threadIdx.x, ob_in + (size_t)tt * NM);
+                if (nch > 1) cp_async_16(s_kid + (2 * tt + 1) * TB_THREADS + threadIdx.x, ob_in + (size_t)tt * NM + M);
+            }
+            cp_async_commit();      // group 2 tt + 1: what the first two tributaries sent at step tt (needed after the surface tank)
+        }
+    }
     // ---- the K steps of the block ----
 #pragma unroll 1
     for (int tt = 0; tt < K; ++tt) {
@@ -949,12 +995,17 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             // the surface-tank update (which needs only the rain) so that their latency hides behind its pow chain.
             const float4 *ob = ob_in;
             float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), obb = oa;
-            if (nch > 0) oa = ob[0];
-            if (nch > 1) obb = ob[M];
+            if (!STAGE) {
+                if (nch > 0) oa = ob[0];
+                if (nch > 1) obb = ob[M];
+            }
             // rain (:444-449)
             const int p = __ldg(P.pos + t);
             float R = 0.0f;
-            if (p != 1) R = div_by_1000((float)__ldg(P.rain + (size_t)(p - 1) * N + cell));
+            if (STAGE) {
+                cp_async_wait_dyn<2 * K - 1>(2 * (K - 1 - tt) + 1);
+                if (p != 1) R = div_by_1000((float)s_rain[tt * TB_THREADS + threadIdx.x]);
+            } else if (p != 1) R = div_by_1000((float)__ldg(P.rain + (size_t)(p - 1) * N + cell));
             // vertical cascade, surface tank (:478-486)
             const float vf1 = fmaxf(0.0f, R - H1 + S0);
             S0 = S0 + R - vf1;
@@ -971,6 +1022,11 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                 T0 = (bq > 0.0f) ? bq : 0.0f;
             }
             S0 = S0 - E;
+            if (STAGE) {
+                cp_async_wait_dyn<2 * K - 1>(2 * (K - 1 - tt));
+                if (nch > 0) oa = s_kid[(2 * tt) * TB_THREADS + threadIdx.x];
+                if (nch > 1) obb = s_kid[(2 * tt + 1) * TB_THREADS + threadIdx.x];
+            }
             // what the upstream neighbours sent this step, added in ascending cell order (:601,:617,:672) -- the
             // reference's children deposit into StoOut(2:5) before the cell itself is processed
             if (nch > 0) {
@@ -1368,13 +1424,15 @@ __global__ void __launch_bounds__(TB_THREADS, (SED || SEPR) ? TB_MIN_BLOCKS_SED 
 k_shia_tb(const __grid_constant__ ShiaP P, const int w, const int clo, const int chi, const int hlo, const int hhi,
           const int cpb, const int n_ctiles, const int n_htiles) {
     __shared__ float s_acc[K * TB_THREADS];
+    __shared__ float4 s_kid[TbStage<K>::on ? 2 * K * TB_THREADS : 1];
+    __shared__ int32_t s_rain[TbStage<K>::on ? K * TB_THREADS : 1];
     const int wi = threadIdx.x >> 5;
     if (wi < cpb) {
         const int tile = (int)blockIdx.x * cpb + wi;
-        if (tile < n_ctiles) tb_role<K, true, KIN, SED, SLIDES, SNAP, SEPF, SEPR, FLOOD>(P, w, clo, chi, tile, s_acc);
+        if (tile < n_ctiles) tb_role<K, true, KIN, SED, SLIDES, SNAP, SEPF, SEPR, FLOOD>(P, w, clo, chi, tile, s_acc, s_kid, s_rain);
     } else {
         const int tile = (int)blockIdx.x * (TB_THREADS / 32 - cpb) + (wi - cpb);
-        if (tile < n_htiles) tb_role<K, false, KIN, SED, SLIDES, SNAP, SEPF, SEPR, FLOOD>(P, w, hlo, hhi, tile, s_acc);
+        if (tile < n_htiles) tb_role<K, false, KIN, SED, SLIDES, SNAP, SEPF, SEPR, FLOOD>(P, w, hlo, hhi, tile, s_acc, s_kid, s_rain);
     }
 }
 
