@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define WMF_ABI_VERSION 13
+#define WMF_ABI_VERSION 14
 
 enum {
     WMF_OK = 0,
@@ -195,6 +195,9 @@ typedef struct {
      * flood_sec_tam = rows of flood_sections */
     int32_t sim_floods, flood_sec_tam;
     float flood_dw, flood_dsed, flood_av, flood_cmax, flood_umbral, flood_step, flood_hmax;
+    /* storm-scenario ensembles (BASELINE configs[4]; the reference forks one process per scenario, wmf.py:872-878): when 1,
+     * pos_evento is (n_members, n_reg) row-major and member m reads the rain record pos_evento[m][t] of the shared table */
+    int32_t pos_per_member;
 } wmf_shia_cfg;
 
 /* Arrays = module `models` allocatables (modelosv2.f90:53-113) in their f2py layouts. */

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.load()
     for s in declared:
         assert hasattr(L, s), s
-    assert L.wmf_abi_version() == 13
+    assert L.wmf_abi_version() == 14
 
 
 def test_no_cpu_fallback_without_gpu():

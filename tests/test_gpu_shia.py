@@ -578,3 +578,38 @@ def test_hydroflash_floods(kin):
     assert same_level.mean() > 0.995
     assert abs(float(m.flood_diff) - float(ref["flood_scalars"][2])) < 1e-6
     close(np.float32(m.flood_rdf), ref["flood_scalars"][0], name="flood_rdf")
+
+
+def test_scenario_ensemble_with_sediments_and_slides():
+    """Storm scenarios as a member axis (BASELINE configs[4]): three scenarios = three sequences of the same rain records
+    run in ONE launch sequence with sediments + landslides; each is compared with a single oracle run of that sequence."""
+    from wmf_b200 import ModelsModule, synth
+    bs, inp = build("G2", 110, 90, 5, n_reg=60, speed_type=(2, 2, 1), sediments=True, slides=True, rain_peak_mm=60.0)
+    N, T = bs["n"], 60
+    pos = np.asarray(inp["pos_evento"], np.int32)
+    scen = np.stack([pos, np.roll(pos, 7), pos[::-1].copy()]).astype(np.int32)
+    m = ModelsModule()
+    synth.apply_to_models(m, inp)
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    n_conth = max(1, int(np.count_nonzero(inp["control_h"])))
+    calibs = np.tile(np.asarray(inp["calib"], np.float32)[None, :], (3, 1))
+    out = m._run(calibs, n_cont, n_conth, T, inp["rain"], scen)
+    assert out["q"].shape == (n_cont, T, 3) and out["vs"].shape == (3, N, 3) and out["sl_slideocurrence"].shape == (N, 3)
+    slid_any = 0
+    for k in range(3):
+        ref = run_oracle(dict(inp, pos_evento=scen[k]))
+        close(out["q"][:, :, k], ref["q"], name=f"Q scenario {k}")
+        close(out["stoout"][:, :, k], ref["stoout"], name=f"StoOut scenario {k}")
+        close(out["qsed"][:, :, :, k], ref["qsed"], name=f"Qsed scenario {k}")
+        for nm in ("vs", "vd", "vsc", "vdc"):
+            close(out[nm][:, :, k], ref[nm], name=f"{nm} scenario {k}")
+        close(out["volero"][:, k], ref["volero"], name=f"VolERO scenario {k}")
+        close(out["voldepo"][:, k], ref["voldepo"], name=f"VolDEPo scenario {k}")
+        close(out["erot"][:, k], ref["erot64"], name=f"EROt scenario {k}")
+        close(out["dept"][:, k], ref["dept64"], name=f"DEPt scenario {k}")
+        np.testing.assert_array_equal(out["sl_slideocurrence"][:, k], ref["sl_slideocurrence"])
+        np.testing.assert_array_equal(out["sl_slideacumulate"][:, k], ref["sl_slideacumulate"])
+        np.testing.assert_array_equal(out["sl_slidencelltime"][:, k], ref["sl_slidencelltime"])
+        slid_any += int(np.count_nonzero(ref["sl_slideocurrence"]))
+    assert slid_any > 0
+    assert not np.array_equal(out["q"][:, :, 0], out["q"][:, :, 1])

@@ -46,6 +46,7 @@ class ShiaCfg(C.Structure):
         ("sim_floods", C.c_int32), ("flood_sec_tam", C.c_int32),
         ("flood_dw", C.c_float), ("flood_dsed", C.c_float), ("flood_av", C.c_float), ("flood_cmax", C.c_float),
         ("flood_umbral", C.c_float), ("flood_step", C.c_float), ("flood_hmax", C.c_float),
+        ("pos_per_member", C.c_int32),
     ]
 
 

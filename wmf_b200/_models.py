@@ -597,7 +597,12 @@ class ModelsModule:
             n_records = rain.shape[0]
         put("rain", rain)
         si.n_records = int(n_records)
-        put("pos_evento", np.ascontiguousarray(pos, np.int32))
+        pos = np.ascontiguousarray(pos, np.int32)
+        if pos.ndim == 2:                     # storm scenarios: member m follows its own sequence of rain records, pos[m, t]
+            if pos.shape != (M, T) or M == 1:
+                raise ValueError(f"per-member pos_evento must be ({M},{T}) with more than one member")
+            cfg.pos_per_member = 1
+        put("pos_evento", pos)
         n_snap = 0
         if cfg.save_storage == 1:
             g = a.get("guarda_cond")
@@ -702,6 +707,17 @@ class ModelsModule:
             out("q", (n_cont, T, M))
             out("stoout", (5, N, M))
             out("hspeed_out", (4, N, M))
+            if sed:                           # the member axis comes last (slowest in memory), as for q
+                out("qsed", (n_cont, 3, T, M))
+                for k in ("vs", "vd", "vsc", "vdc"):
+                    out(k, (3, N, M))
+                out("volero", (N, M)); out("voldepo", (N, M)); out("erot", (3, M)); out("dept", (3, M))
+            if sl:
+                for k in ("sl_zmin", "sl_zcrit", "sl_zmax", "sl_bo", "sl_riskvector"):
+                    out(k, (1, N))
+                out("sl_slideocurrence", (N, M))
+                out("sl_slideacumulate", (N, M), np.int32)
+                out("sl_slidencelltime", (T, M), np.int32)
         c.check(c.L.wmf_shia_run(c.h, C.byref(cfg), C.byref(si), C.byref(so)))
         # module-global results the reference leaves behind (read back at wmf.py:4548-4601)
         if single and not device_out:

@@ -59,6 +59,7 @@ struct ShiaP {
     const float *calib;  // (M,11)
     const int32_t *rain;
     const int32_t *pos;
+    int pos_stride;       // 0: every member reads pos[t]; T: member m reads pos[m*T + t] (storm-scenario ensembles)
     // state (SoA member-minor)
     float *sto;   // [5][N][M]
     float *hsp;   // [4][N][M]
@@ -73,17 +74,18 @@ struct ShiaP {
     float *sed;      // [12][N][M]: Vs(3) Vd(3) Vsc(3) Vdc(3)
     float *sedout;   // [2][12][N][M]: hillslope->parent sus(3) bm(3) ero(3), channel->parent (3)
     float *volero, *voldepo;  // [N][M]
-    double *sedtot;  // [6] EROt(3), DEPt(3)
+    double *sedtot;  // [6] EROt(3), DEPt(3): one-step kernel (atomics)
+    double *sedacc;  // [6][N][M] the same totals per (cell, member), time-blocked kernel (summed at the end, no atomics)
     // slides
     int sl_gullie;
     float sl_fs, sl_gammaw;
     const float *sl_zs, *sl_gammas, *sl_cohesion, *sl_friction, *sl_radslope;
     const float *sl_zcrit, *sl_risk;
     const float *sl_cosr, *sl_sinr, *sl_tanfa;  // cos/sin of the slope angle, tan of the friction angle
-    int32_t *sl_slid;       // [N] own failure flag
-    int32_t *sl_marktime;   // [N] first step at which an upstream failure marked this cell (INT_MAX = never)
-    int32_t *sl_acum;       // [N]
-    int32_t *sl_ncelltime;  // [T]
+    int32_t *sl_slid;       // [N][M] own failure flag
+    int32_t *sl_marktime;   // [N][M] first step at which an upstream failure marked this cell (INT_MAX = never)
+    int32_t *sl_acum;       // [N][M]
+    int32_t *sl_ncelltime;  // [M][T]
     const int32_t *drena;   // original drain ids (for the downstream marking walk)
     int drena_stride;
     // time-blocked wavefront (k_shia_tb): cell lists by role, AoS state, per-step outflow ring
@@ -163,7 +165,8 @@ struct SedLocal {
 };
 
 // modelosv2.f90:1321-1428
-__device__ __forceinline__ void sed_hillslope_dev(const ShiaP &P, SedLocal &S, float alfa, float v2, float S2, float So,
+// aSo = alfa * So**1.664, the first product of Qskr (:1339): constant per cell, the callers compute it once per time block
+__device__ __forceinline__ void sed_hillslope_dev(const ShiaP &P, SedLocal &S, float aSo, float v2, float S2,
                                                   float qlin, int cell, int tipo) {
     const float dt = P.dt, dxp = P.dxp;
     float qsSUStot = 0.f, qsBMtot = 0.f, qsSUS[3] = {0, 0, 0}, qsBM[3] = {0, 0, 0}, qsERO[3] = {0, 0, 0};
@@ -171,7 +174,7 @@ __device__ __forceinline__ void sed_hillslope_dev(const ShiaP &P, SedLocal &S, f
     S.DEP[0] = S.DEP[1] = S.DEP[2] = 0.f;
     // the two powers go through double precision: totXSScap / REScap below are differences of nearly equal terms, and a
     // 1.4 ulp (wmf_powf) or 4 ulp (CUDA powf) error in Qskr reaches 1e-5 in Vs / VolDEPo (tests/test_pow_emulation.py)
-    const float Qskr = alfa * wmf_powf_dd(So, 1.664f) * wmf_powf_dd(qlin, 2.035f) * P.krus[cell] * P.crus[cell] * P.prus[cell] * dxp * dt;
+    const float Qskr = aSo * wmf_powf_dd(qlin, 2.035f) * P.krus[cell] * P.crus[cell] * P.prus[cell] * dxp * dt;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         if (S2 / 1000.0f > P.wi[i] * dt)
@@ -452,7 +455,7 @@ k_shia_wave(const __grid_constant__ ShiaP P, const int w, const int lo, const in
                 P.hsp[k * NM + base] = v;
                 if (SED && k == 0) {
                     const float qlin = h[0] * m3 / (dt * P.dxp);
-                    sed_hillslope_dev(P, SL, P.sed_factor, v, S[1], __ldg(P.hill_slope + cell), qlin, cell, type);
+                    sed_hillslope_dev(P, SL, P.sed_factor * wmf_powf_dd(__ldg(P.hill_slope + cell), 1.664f), v, S[1], qlin, cell, type);
                 }
             }
             S[k + 1] = S[k + 1] - h[k];
@@ -747,12 +750,16 @@ constexpr int TB_THREADS = TB_THREADS_N;
 #ifndef TB_MIN_BLOCKS_KIN   // kinematic hillslope tanks (calc_speed: five dependent pow per tank and step): 85 registers instead
 #define TB_MIN_BLOCKS_KIN 3 // of 64 + 268 B of spills; C2 with speed_type = [2,2,1], 400 steps: 33.0 -> 31.3 ms (2 blocks: 37.6)
 #endif
-// Asynchronous staging of a time block's inputs (WMF_TB_STAGE=0 compiles it out for A/B runs): everything a thread reads
-// during its K steps -- the float4 its first two tributaries sent at each step and the K rain values -- was written by the
-// previous wave, so it is requested with cp.async right after griddepcontrol.wait and lands in shared memory while the
-// first step computes; no registers are held for it.  Blocks of up to 4 steps (36 KB per 256-thread CTA at K = 4).
+// Asynchronous staging of a time block's inputs (compile with -DWMF_TB_STAGE=1): everything a thread reads during its K
+// steps -- the float4 its first two tributaries sent at each step and the K rain values -- was written by the previous
+// wave, so it can be requested with cp.async right after griddepcontrol.wait and land in shared memory while the first
+// step computes, holding no registers.  Blocks of up to 4 steps (36 KB per 256-thread CTA at K = 4).
+// MEASURED AND REJECTED (round 2, profiles/README.md): C2 wave loop 28.47 -> 30.06 ms.  The staged kernel executes 12 %
+// more warp instructions per CTA (copy issue, wait ladders, shared loads) and its long-scoreboard stalls per issued
+// instruction do not fall (3.5 before and after): the tributary and rain loads were already hidden behind the surface
+// tank's pow chain; what remains are the state / static-map loads at the head of a block.  Off by default.
 #ifndef WMF_TB_STAGE
-#define WMF_TB_STAGE 1
+#define WMF_TB_STAGE 0
 #endif
 __device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -946,14 +953,16 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
         vdep = P.voldepo[base];
         vero = P.volero[base];
     }
+    float sed_aSo = 0.f;  // alfa * So**1.664 (:1339), once per time block
+    if (SED && KIN && active && P.st[0] == 2) sed_aSo = P.sed_factor * wmf_powf_dd(__ldg(P.hill_slope + cell), 1.664f);
     // slides (:1649-1707): own failure flag and the step at which an upstream failure reached this cell.  Every mark
     // with a step of this block or earlier was made by a wave before this one, so one read per block is enough.
     int sl_slid = 0, sl_mark = INT_MAX;
     bool sl_risky = false;
     if (SLIDES && active) {
         sl_risky = __ldg(P.sl_risk + cell) == 2.0f;
-        sl_slid = P.sl_slid[cell];
-        sl_mark = P.sl_marktime[cell];
+        sl_slid = P.sl_slid[base];
+        sl_mark = P.sl_marktime[base];
     }
     float rc1 = 0.f, rc2 = 0.f;           // save_rc accumulators
     if (SNAP && active && P.rc) { rc1 = P.rc[cell]; rc2 = P.rc[(size_t)N + cell]; }
@@ -972,7 +981,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
 #pragma unroll
         for (int tt = 0; tt < K; ++tt) {
             if (tt < nt) {
-                const int p = __ldg(P.pos + t0 + tt);
+                const int p = __ldg(P.pos + (size_t)m * P.pos_stride + t0 + tt);
                 if (p != 1) cp_async_4(s_rain + tt * TB_THREADS + threadIdx.x, P.rain + (size_t)(p - 1) * N + cell);
             }
             cp_async_commit();      // group 2 tt: the rain value of step tt (needed first)
@@ -1000,7 +1009,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                 if (nch > 1) obb = ob[M];
             }
             // rain (:444-449)
-            const int p = __ldg(P.pos + t);
+            const int p = __ldg(P.pos + (size_t)m * P.pos_stride + t);
             float R = 0.0f;
             if (STAGE) {
                 cp_async_wait_dyn<2 * K - 1>(2 * (K - 1 - tt) + 1);
@@ -1141,7 +1150,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                         hk[k] = fminf(sec * kv[k] * dt / m3, Sk[k]);
                         if (SED && k == 0) {  // the reference calls sed_hillslope from inside the kinematic case only (:569-575)
                             const float qlin = hk[0] * m3 / (dt * P.dxp);
-                            sed_hillslope_dev(P, SL, P.sed_factor, kv[0], Sk[0], __ldg(P.hill_slope + cell), qlin, cell, type);
+                            sed_hillslope_dev(P, SL, sed_aSo, kv[0], Sk[0], qlin, cell, type);
                         }
                     }
                     if (SEPR) {  // :580-592, in proportion to the tank before the outflow leaves
@@ -1284,7 +1293,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                 }
                 if (fail) {
                     sl_slid = 1;
-                    atomicAdd(P.sl_acum + cell, 1);
+                    atomicAdd(P.sl_acum + base, 1);
                     int marks = 1;
                     if (P.sl_gullie == 1 && type <= 2) {  // slide_hill2gullie (:1683-1707)
                         int local = cell, ltype = type;
@@ -1294,14 +1303,14 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                             const int dir = N - dd;
                             const int dtype = (__ldg(P.tw + dir) >> 4) & 3;
                             if (dtype > ltype) break;
-                            atomicMin(P.sl_marktime + dir, t);
-                            atomicAdd(P.sl_acum + dir, 1);
+                            atomicMin(P.sl_marktime + (size_t)dir * M + m, t);
+                            atomicAdd(P.sl_acum + (size_t)dir * M + m, 1);
                             ++marks;
                             local = dir;
                             ltype = dtype;
                         }
                     }
-                    atomicAdd(P.sl_ncelltime + t, marks);
+                    atomicAdd(P.sl_ncelltime + (size_t)m * P.T + t, marks);
                 }
             }
             if (SED) {
@@ -1367,7 +1376,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             P.voldepo[base] = vdep;
             P.volero[base] = vero;
         }
-        if (SLIDES) P.sl_slid[cell] = sl_slid;
+        if (SLIDES) P.sl_slid[base] = sl_slid;
         if (SEPF && CHAN) { P.flx[base] = F0; P.flx[NM + base] = F1; P.flx[2 * NM + base] = F2; }
         if (SEPR) {
             P.shc[base] = C0; P.shc[NM + base] = C1; P.shc[2 * NM + base] = C2; P.shc[3 * NM + base] = C3; P.shc[4 * NM + base] = C4;
@@ -1375,15 +1384,11 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
         }
         if (SNAP && P.rc) { P.rc[cell] = rc1; P.rc[(size_t)N + cell] = rc2; }
     }
-    if (SED) {  // EROt / DEPt (:1403, :1420): global totals, fp64
+    if (SED && active) {  // EROt / DEPt (:1403, :1420): fp64 running totals per (cell, member), summed over the cells at the end
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const double a = warp_sum_d(ero_acc[i]);
-            const double c = warp_sum_d(dep_acc[i]);
-            if ((threadIdx.x & 31) == 0) {
-                if (a != 0.0) atomicAdd(P.sedtot + i, a);
-                if (c != 0.0) atomicAdd(P.sedtot + 3 + i, c);
-            }
+            if (ero_acc[i] != 0.0) P.sedacc[(size_t)i * NM + base] += ero_acc[i];
+            if (dep_acc[i] != 0.0) P.sedacc[(size_t)(3 + i) * NM + base] += dep_acc[i];
         }
     }
     // ---- per-step balance terms: one fp64 atomic per (warp, step) ----
@@ -1771,15 +1776,48 @@ __global__ void k_slide_allocate(const ShiaP P, float *__restrict__ zmin, float 
     if (zs < zmn && rs < b) rv = 0.0f;
     if (zs > zmx && rs > b) rv = 1.0f;
     zmin[i] = zmn; zcrit[i] = zcr; zmax[i] = zmx; bo[i] = b; risk[i] = rv;
-    P.sl_slid[i] = 0;
-    P.sl_marktime[i] = INT_MAX;
-    P.sl_acum[i] = 0;
 }
 
-__global__ void k_slide_final(const ShiaP P, float *__restrict__ occ) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.N) return;
-    occ[i] = (P.sl_marktime[i] != INT_MAX) ? 3.0f : (P.sl_slid[i] ? 1.0f : 0.0f);
+// outputs carry the member axis last in f2py terms: (1, N, M) -> [m][i]
+__global__ void k_slide_final(const ShiaP P, float *__restrict__ occ, int32_t *__restrict__ acum_out) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)P.N * P.M) return;
+    const int i = (int)(g / P.M), m = (int)(g % P.M);
+    const size_t o = (size_t)m * P.N + i;
+    if (occ) occ[o] = (P.sl_marktime[g] != INT_MAX) ? 3.0f : (P.sl_slid[g] ? 1.0f : 0.0f);
+    if (acum_out) acum_out[o] = P.sl_acum[g];
+}
+__global__ void k_slide_state_init(const ShiaP P) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)P.N * P.M) return;
+    P.sl_slid[g] = 0;
+    P.sl_marktime[g] = INT_MAX;
+    P.sl_acum[g] = 0;
+}
+// sum of sedacc over the cells: one block per (member, quantity); EROt / DEPt as (3, M) -> [m][3]
+__global__ void __launch_bounds__(256) k_sed_totals(const double *__restrict__ sedacc, int n, int M, float *__restrict__ erot,
+                                                    float *__restrict__ dept) {
+    const int m = blockIdx.x, q = blockIdx.y;
+    const size_t NM = (size_t)n * M;
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a += sedacc[(size_t)q * NM + (size_t)i * M + m];
+    a = warp_sum_d(a);
+    __shared__ double sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += sm[k];
+        if (q < 3) { if (erot) erot[3 * m + q] = (float)t; }
+        else if (dept) dept[3 * m + (q - 3)] = (float)t;
+    }
+}
+// [N][M] -> [m][i]
+__global__ void k_member_major_f32(const float *__restrict__ src, int n, int M, float *__restrict__ dst) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)n * M) return;
+    const int i = (int)(g / M), m = (int)(g % M);
+    dst[(size_t)m * n + i] = src[g];
 }
 
 __global__ void k_sed_init(const float *__restrict__ vd_init, int n, int M, float *__restrict__ sed) {
@@ -1793,14 +1831,17 @@ __global__ void k_sed_init(const float *__restrict__ vd_init, int n, int M, floa
 }
 
 // SoA [12][N] -> the four (3,N) arrays
-__global__ void k_sed_final(const float *__restrict__ sed, int n, float *vs, float *vd, float *vsc, float *vdc) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// (3, N, M) outputs -> [m][i][k]
+__global__ void k_sed_final(const float *__restrict__ sed, int n, int M, float *vs, float *vd, float *vsc, float *vdc) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)n * M) return;
+    const int i = (int)(g / M), m = (int)(g % M);
+    const size_t NM = (size_t)n * M, o = 3 * ((size_t)m * n + i);
     for (int k = 0; k < 3; ++k) {
-        if (vs) vs[3 * (size_t)i + k] = sed[(size_t)(0 + k) * n + i];
-        if (vd) vd[3 * (size_t)i + k] = sed[(size_t)(3 + k) * n + i];
-        if (vsc) vsc[3 * (size_t)i + k] = sed[(size_t)(6 + k) * n + i];
-        if (vdc) vdc[3 * (size_t)i + k] = sed[(size_t)(9 + k) * n + i];
+        if (vs) vs[o + k] = sed[(size_t)(0 + k) * NM + g];
+        if (vd) vd[o + k] = sed[(size_t)(3 + k) * NM + g];
+        if (vsc) vsc[o + k] = sed[(size_t)(6 + k) * NM + g];
+        if (vdc) vdc[o + k] = sed[(size_t)(9 + k) * NM + g];
     }
 }
 
@@ -1920,11 +1961,10 @@ struct RainStream {
     }
     // Before anything else of the run is queued: the record groups the sweep reads first go out whole (all cells), so the
     // link is busy while the other inputs are staged and the plan is built.  pos[t] = 1-based record of step t.
-    int early(wmf_ctx *ctx, const std::vector<int32_t> &pos) {
+    int early(wmf_ctx *ctx, const std::vector<int32_t> &pos, int T) {   // pos: one or several sequences of T steps
         if (!active) return WMF_OK;
-        const int T = (int)pos.size();
         tmin.assign((size_t)n_records, INT_MAX);
-        for (int t = T - 1; t >= 0; --t) tmin[pos[t] - 1] = t;
+        for (size_t k = 0; k < pos.size(); ++k) tmin[pos[k] - 1] = std::min(tmin[pos[k] - 1], (int)(k % T));
         int n_rg, n_cg;
         tile_grid(&n_rg, &n_cg);
         rg = std::max(1, (n_records + n_rg - 1) / n_rg);
@@ -2188,7 +2228,7 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
         WMF_FAIL(ctx, WMF_ERR_ARG, "shia: sim_sediments=1 needs krus, crus, prus, parliac, hill_slope, stream_slope");
     if (slides && (!in->sl_zs || !in->sl_gammas || !in->sl_cohesion || !in->sl_frictionangle || !in->sl_radslope))
         WMF_FAIL(ctx, WMF_ERR_ARG, "shia: sim_slides=1 needs the sl_* soil maps");
-    if (M > 1 && (sed || slides)) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: ensembles with sediments / slides are not supported yet");
+    const bool pos_pm = cfg->pos_per_member == 1 && M > 1;   // storm scenarios: one record sequence per member
     const int stride = in->drena_stride > 0 ? in->drena_stride : 1;
     if ((long long)N * M >= (1LL << 40)) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: ensemble too large");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -2223,16 +2263,18 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     RainStream rs;
     WMF_TRY(rs.begin(ctx, sc, in->rain, in->n_records, N, &P.rain));
     // pos_evento is needed on both sides: validate on the host
-    std::vector<int32_t> h_pos((size_t)T), h_used;
+    const size_t n_pos = pos_pm ? (size_t)M * T : (size_t)T;
+    std::vector<int32_t> h_pos(n_pos), h_used;
     if (Scope::on_device(in->pos_evento)) {
-        CU_TRY(ctx, cudaMemcpyAsync(h_pos.data(), in->pos_evento, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaMemcpyAsync(h_pos.data(), in->pos_evento, sizeof(int32_t) * n_pos, cudaMemcpyDeviceToHost, ctx->stream));
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     } else {
-        memcpy(h_pos.data(), in->pos_evento, sizeof(int32_t) * T);
+        memcpy(h_pos.data(), in->pos_evento, sizeof(int32_t) * n_pos);
     }
-    for (int t = 0; t < T; ++t)
-        if (h_pos[t] < 1 || h_pos[t] > in->n_records)
-            WMF_FAIL(ctx, WMF_ERR_ARG, "shia: pos_evento(%d)=%d outside 1..n_records=%d", t + 1, h_pos[t], in->n_records);
+    for (size_t k = 0; k < n_pos; ++k)
+        if (h_pos[k] < 1 || h_pos[k] > in->n_records)
+            WMF_FAIL(ctx, WMF_ERR_ARG, "shia: pos_evento(%d)=%d outside 1..n_records=%d", (int)(k % T) + 1, h_pos[k], in->n_records);
+    P.pos_stride = pos_pm ? T : 0;
     // ---- stage inputs ----
     const int32_t *d_unit, *d_control, *d_controlh;
     WMF_TRY(sc.in(in->drena, (size_t)N * stride - (stride - 1), &P.drena));
@@ -2254,7 +2296,7 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     WMF_TRY(sc.in(in->elem_area, (size_t)N, &P.elem_area));
     WMF_TRY(sc.in(in->evpserie, (size_t)T, &P.evp));
     WMF_TRY(sc.in(in->calib, (size_t)11 * M, &P.calib));
-    WMF_TRY(sc.in(in->pos_evento, (size_t)T, &P.pos));
+    WMF_TRY(sc.in(in->pos_evento, n_pos, &P.pos));
     const float *d_storage = nullptr, *d_stoin = nullptr, *d_hspeedin = nullptr;
     // StoIn / HspeedIn are honoured when their first element is > 0 (:271, :285)
     auto first_positive = [&](const float *p, bool *res) -> int {
@@ -2277,7 +2319,7 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     P.hs_state = use_hsin ? 1 : 0;
 
     // the small inputs are queued; now the first rain records start to travel while the sweep is planned
-    WMF_TRY(rs.early(ctx, h_pos));
+    WMF_TRY(rs.early(ctx, h_pos, T));
     mark("stage");
     // ---- plan: levels, child ranges, role lists -- cached on a checksum of the arrays it derives from ----
     // (a calibration loop or an ensemble re-runs the same basin thousands of times: nothing is re-planned, no allocation
@@ -2327,6 +2369,8 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     const bool retdump = cfg->save_retorno == 1 && out->ret_snap;
     const bool snap = (cfg->save_storage == 1 && out->sto_snap) || (cfg->save_speed == 1 && out->speed_snap) || vdump || rcdump || retdump;
     if (KT && (sed || slides || snap)) KT = (T >= 4) ? 4 : 0;  // sediment / slide / dump variants are built for K = 4 only
+    if (M > 1 && (sed || slides) && KT == 0)
+        WMF_FAIL(ctx, WMF_ERR_ARG, "shia: ensembles with sediments / slides run in the time-blocked kernel: n_reg >= 4 and no per-step means");
     const bool sepf = cfg->separate_fluxes == 1;
     const bool sepr = cfg->separate_rain == 1;
     const bool floods = cfg->sim_floods == 1;
@@ -2545,6 +2589,10 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
         CU_TRY(ctx, cudaMemsetAsync(P.volero, 0, sizeof(float) * NM, ctx->stream));
         CU_TRY(ctx, cudaMemsetAsync(P.voldepo, 0, sizeof(float) * NM, ctx->stream));
         CU_TRY(ctx, cudaMemsetAsync(P.sedtot, 0, sizeof(double) * 6, ctx->stream));
+        if (KT) {
+            WMF_TRY(sc.alloc(&P.sedacc, 6 * NM));
+            CU_TRY(ctx, cudaMemsetAsync(P.sedacc, 0, sizeof(double) * 6 * NM, ctx->stream));
+        }
         if (!KT) CU_TRY(ctx, cudaMemsetAsync(P.sedout, 0, sizeof(float) * 24 * NM, ctx->stream));
         LAUNCH(ctx, k_sed_init, grid_for((long long)NM, B), B, 0, d_vd0, N, M, P.sed);
         WMF_TRY(sc.out(out->qsed, QN * 3, &P.qsed));
@@ -2558,12 +2606,11 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
         WMF_TRY(sc.in(in->sl_radslope, (size_t)N, &P.sl_radslope));
         WMF_TRY(sc.alloc(&d_zmin, (size_t)N)); WMF_TRY(sc.alloc(&d_zcrit, (size_t)N)); WMF_TRY(sc.alloc(&d_zmax, (size_t)N));
         WMF_TRY(sc.alloc(&d_bo, (size_t)N)); WMF_TRY(sc.alloc(&d_risk, (size_t)N));
-        WMF_TRY(sc.alloc(&P.sl_slid, (size_t)N)); WMF_TRY(sc.alloc(&P.sl_marktime, (size_t)N));
-        WMF_TRY(sc.out(out->sl_slideacumulate, (size_t)N, &P.sl_acum));
-        if (!P.sl_acum) WMF_TRY(sc.alloc(&P.sl_acum, (size_t)N));
-        WMF_TRY(sc.out(out->sl_slidencelltime, (size_t)T, &P.sl_ncelltime));
-        if (!P.sl_ncelltime) WMF_TRY(sc.alloc(&P.sl_ncelltime, (size_t)T));
-        CU_TRY(ctx, cudaMemsetAsync(P.sl_ncelltime, 0, sizeof(int32_t) * (size_t)T, ctx->stream));
+        WMF_TRY(sc.alloc(&P.sl_slid, NM)); WMF_TRY(sc.alloc(&P.sl_marktime, NM)); WMF_TRY(sc.alloc(&P.sl_acum, NM));
+        WMF_TRY(sc.out(out->sl_slidencelltime, (size_t)M * T, &P.sl_ncelltime));
+        if (!P.sl_ncelltime) WMF_TRY(sc.alloc(&P.sl_ncelltime, (size_t)M * T));
+        CU_TRY(ctx, cudaMemsetAsync(P.sl_ncelltime, 0, sizeof(int32_t) * (size_t)M * T, ctx->stream));
+        LAUNCH(ctx, k_slide_state_init, grid_for((long long)NM, B), B, 0, P);
         float *d_cosr, *d_sinr, *d_tanfa;
         WMF_TRY(sc.alloc(&d_cosr, (size_t)N)); WMF_TRY(sc.alloc(&d_sinr, (size_t)N)); WMF_TRY(sc.alloc(&d_tanfa, (size_t)N));
         LAUNCH(ctx, k_slide_allocate, G, B, 0, P, d_zmin, d_zcrit, d_zmax, d_bo, d_risk, d_cosr, d_sinr, d_tanfa);
@@ -2704,13 +2751,17 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
         float *vs, *vd, *vsc, *vdc, *ve, *vdp, *erot, *dept;
         WMF_TRY(sc.out(out->vs, 3 * NM, &vs)); WMF_TRY(sc.out(out->vd, 3 * NM, &vd));
         WMF_TRY(sc.out(out->vsc, 3 * NM, &vsc)); WMF_TRY(sc.out(out->vdc, 3 * NM, &vdc));
-        LAUNCH(ctx, k_sed_final, G, B, 0, P.sed, N, vs, vd, vsc, vdc);
+        LAUNCH(ctx, k_sed_final, grid_for((long long)NM, B), B, 0, P.sed, N, M, vs, vd, vsc, vdc);
         WMF_TRY(sc.out(out->volero, NM, &ve)); WMF_TRY(sc.out(out->voldepo, NM, &vdp));
-        if (ve) CU_TRY(ctx, cudaMemcpyAsync(ve, P.volero, sizeof(float) * NM, cudaMemcpyDeviceToDevice, ctx->stream));
-        if (vdp) CU_TRY(ctx, cudaMemcpyAsync(vdp, P.voldepo, sizeof(float) * NM, cudaMemcpyDeviceToDevice, ctx->stream));
-        WMF_TRY(sc.out(out->erot, 3, &erot)); WMF_TRY(sc.out(out->dept, 3, &dept));
-        if (erot) LAUNCH(ctx, k_d2f, 1, 32, 0, P.sedtot, 3, erot);
-        if (dept) LAUNCH(ctx, k_d2f, 1, 32, 0, P.sedtot + 3, 3, dept);
+        if (ve) LAUNCH(ctx, k_member_major_f32, grid_for((long long)NM, B), B, 0, P.volero, N, M, ve);
+        if (vdp) LAUNCH(ctx, k_member_major_f32, grid_for((long long)NM, B), B, 0, P.voldepo, N, M, vdp);
+        WMF_TRY(sc.out(out->erot, (size_t)3 * M, &erot)); WMF_TRY(sc.out(out->dept, (size_t)3 * M, &dept));
+        if (KT) {
+            if (erot || dept) LAUNCH(ctx, k_sed_totals, dim3((unsigned)M, 6), 256, 0, P.sedacc, N, M, erot, dept);
+        } else {
+            if (erot) LAUNCH(ctx, k_d2f, 1, 32, 0, P.sedtot, 3, erot);
+            if (dept) LAUNCH(ctx, k_d2f, 1, 32, 0, P.sedtot + 3, 3, dept);
+        }
     }
     if (slides) {
         float *o;
@@ -2724,8 +2775,10 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
         WMF_TRY(copy_out(out->sl_zmin, d_zmin)); WMF_TRY(copy_out(out->sl_zcrit, d_zcrit));
         WMF_TRY(copy_out(out->sl_zmax, d_zmax)); WMF_TRY(copy_out(out->sl_bo, d_bo));
         WMF_TRY(copy_out(out->sl_riskvector, d_risk));
-        WMF_TRY(sc.out(out->sl_slideocurrence, (size_t)N, &o));
-        if (o) LAUNCH(ctx, k_slide_final, G, B, 0, P, o);
+        int32_t *oa;
+        WMF_TRY(sc.out(out->sl_slideocurrence, NM, &o));
+        WMF_TRY(sc.out(out->sl_slideacumulate, NM, &oa));
+        if (o || oa) LAUNCH(ctx, k_slide_final, grid_for((long long)NM, B), B, 0, P, o, oa);
     }
     if (per_run && out->retorned && cfg->retorno_gr == 1.0f && (cfg->show_mean_retorno == 1 || cfg->save_retorno == 1)) {
         // the Fortran zeroes Retorned after every step in this mode (:841-843)

@@ -153,6 +153,34 @@ def evaluate_population(models, calibs, qobs, n_cont, n_reg, rain, pos_evento, r
     return gather_scores(local, P, device=local.device)
 
 
+def run_scenario_ensemble(models, calib, pos_scenarios, n_cont, n_reg, rain, n_conth: int = 1, scenarios_per_launch: int = 8,
+                          device_out: bool = False, want=None):
+    """Storm scenarios as a member axis (BASELINE config 5): scenario ``s`` follows its own sequence ``pos_scenarios[s]``
+    (n_reg 1-based record numbers) through ONE shared table of rain records ``rain`` (n_records, N); topology, maps and
+    parameters are shared, sediments and landslides may be on.  ``scenarios_per_launch`` scenarios run in one wavefront
+    launch sequence (member-minor state: the waves of a basin whose single run leaves the GPU half empty fill it), the
+    scenarios of the initialised process group's ranks are sharded round robin like calibration members.
+
+    Returns ``(indices, outputs)``: the scenario indices this rank ran and, per launch, the dict ``models._run`` returns
+    (arrays with the scenario axis last).  The reference runs one process per scenario (wmf.py:872-878)."""
+    pos = np.ascontiguousarray(np.asarray(pos_scenarios, dtype=np.int32))
+    if pos.ndim != 2 or pos.shape[1] != n_reg:
+        raise ValueError("pos_scenarios must be (n_scenarios, n_reg)")
+    _, rank, world = _dist()
+    mine = shard_members(pos.shape[0], rank, world)
+    cal = np.ascontiguousarray(np.asarray(calib, np.float32).reshape(-1))
+    outs = []
+    for s in range(0, mine.size, max(1, scenarios_per_launch)):
+        idx = mine[s: s + scenarios_per_launch]
+        if idx.size == 1:       # a lone scenario is an ordinary single run
+            outs.append(models._run(cal[None, :], n_cont, n_conth, n_reg, rain, pos[idx[0]], device_out=device_out, want=want,
+                                    ensemble=True))
+        else:
+            outs.append(models._run(np.tile(cal[None, :], (idx.size, 1)), n_cont, n_conth, n_reg, rain, pos[idx],
+                                    device_out=device_out, want=want))
+    return mine, outs
+
+
 def run_scenarios(setup, scenarios, run_one, concurrency: int = 3, device: int | None = None):
     """Storm-scenario ensembles on ONE GPU (BASELINE config 5): scenarios differ in rainfall (or in anything else) and are
     independent runs -- the reference would fork one process per scenario (wmf.py:872-878).  Here ``concurrency`` workers,
