@@ -613,3 +613,41 @@ def test_scenario_ensemble_with_sediments_and_slides():
         slid_any += int(np.count_nonzero(ref["sl_slideocurrence"]))
     assert slid_any > 0
     assert not np.array_equal(out["q"][:, :, 0], out["q"][:, :, 1])
+
+
+def test_eval_scores_against_the_references_own_functions():
+    """wmf_eval_scores vs `__eval_nash__` / `__eval_q_pico__` of wmf.py itself (wmf.py:749-754, 775-781): the golden table was
+    produced by executing the reference's unmodified source (tests/golden/make_eval_scores.py), NaN gaps in the observations."""
+    import torch
+    from wmf_b200 import _lib
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eval_scores.npz"))
+    qobs, qsim, want = g["qobs"], g["qsim"], g["scores"]
+    M, T = qsim.shape
+    c = _lib.default_context()
+    dev = f"cuda:{c.device}"
+    d_q = torch.from_numpy(np.ascontiguousarray(qsim)).to(dev)         # (M, T) with n_cont = 1: member slowest
+    d_o = torch.from_numpy(qobs).to(dev)
+    sc = torch.empty((M, 2), dtype=torch.float32, device=dev)
+    c.check(c.L.wmf_eval_scores(c.h, d_q.data_ptr(), M, 1, T, 0, d_o.data_ptr(), sc.data_ptr()))
+    got = sc.cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(got[:, 0], want[:, 0], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(got[:, 1], want[:, 1], rtol=2e-6, atol=2e-5)
+    assert want[0, 0] > 0.999
+
+
+def test_nsga2_generation_loop_on_the_gpu():
+    """calib_nsga2 (the loop of SimuBasin.Calib_NSGAII, wmf.py:4662-4733) with every generation evaluated in one ensemble
+    launch sequence: the calibration that produced the "observations" must be matched better and better."""
+    from wmf_b200 import ModelsModule, nsga2, synth
+    bs, inp = build("G2", 72, 60, 22, n_reg=50)
+    m = ModelsModule()
+    synth.apply_to_models(m, inp)
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    _, ret = run_gpu(inp)
+    qobs = ret[0][0].copy()
+    base = np.asarray(inp["calib"], np.float64)
+    el = nsga2.NsgaElement(**{g: (0.5 * base[k], 1.5 * base[k]) if base[k] > 0 else (0.0, 0.0) for k, g in enumerate(nsga2.GENES)})
+    ev = nsga2.make_gpu_evaluator(m, qobs, n_cont, inp["n_reg"], inp["rain"], inp["pos_evento"], row=0, members_per_launch=16)
+    pop, fit, hist = nsga2.calib_nsga2(ev, el, pop_size=16, ngen=3, seed=0)
+    assert pop.shape == (16, 11) and np.isfinite(fit).all()
+    assert hist[-1][:, 0].max() >= hist[0][:, 0].max() and hist[-1][:, 0].max() > 0.5

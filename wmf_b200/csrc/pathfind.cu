@@ -325,10 +325,12 @@ k_pf_local2(const int32_t *__restrict__ dir, int nc, int nr, int ntx, int lin0, 
         nchpack |= nch << (4 * k);
     }
     __syncthreads();
-    // root-to-leaf sums by pointer jumping: T = cell reached so far, H = hops to it, O (in An) = sum of off() over the
-    // cells passed (the terminal's own offset belongs to the boundary graph)
-    unsigned short *T = sm.j0, *H = sm.j1;
-    uint32_t *O = An;
+    // root-to-leaf sums by pointer jumping on one 64-bit word per cell: (T = cell reached so far | H = hops to it << 16 |
+    // O = sum of off() over the cells passed << 32; the terminal's own offset belongs to the boundary graph).  A word is
+    // read and written whole, so it always describes a valid jump and the updates need no read / write phases: a cell adds
+    // the word of the cell it points at, whichever version of it it sees, until that cell is a terminal (T == itself).
+    int tv[CPT];
+    unsigned offv[CPT];
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
         const int li = k * NTHR + tid, ly = li >> 6, lx = li & (TS - 1);
@@ -340,49 +342,49 @@ k_pf_local2(const int32_t *__restrict__ dir, int nc, int nr, int ntx, int lin0, 
             const int ny = ly + dr, nx = lx + dc;
             if (ny >= 0 && ny < TS && nx >= 0 && nx < TS) t = ny * TS + nx;
         }
-        T[li] = (unsigned short)t;
-        H[li] = (unsigned short)(t != li ? 1 : 0);
+        tv[k] = t;
+        offv[k] = (t != li) ? An[li] : 0u;
     }
     __syncthreads();
-    for (int round = 0; round < MAXROUNDS; ++round) {
-        int t1[CPT], t2[CPT];
-        unsigned hh[CPT], oo[CPT];
+    unsigned long long *P64 = reinterpret_cast<unsigned long long *>(sm.bufA);   // bufA + bufB: 4096 words
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int li = k * NTHR + tid;
+        P64[li] = (unsigned long long)tv[k] | ((unsigned long long)(tv[k] != li ? 1u : 0u) << 16) | ((unsigned long long)offv[k] << 32);
+    }
+    __syncthreads();
+    unsigned done = 0;
+    for (int round = 0; round <= MAXROUNDS; ++round) {
+        int wrote = 0;
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
+            if ((done >> k) & 1u) continue;
             const int li = k * NTHR + tid;
-            t1[k] = T[li];
-            t2[k] = T[t1[k]];
-            hh[k] = H[t1[k]];
-            oo[k] = O[t1[k]];
+            const unsigned long long p = P64[li];
+            const int t = (int)(p & 0xFFFFu);
+            const unsigned long long q = P64[t];
+            if ((int)(q & 0xFFFFu) == t) { done |= 1u << k; continue; }   // t is a terminal (my own word when I am one)
+            const unsigned long long hsum = ((p >> 16) + (q >> 16)) & 0xFFFFu, osum = ((p >> 32) + (q >> 32)) & 0xFFFFFFFFu;
+            P64[li] = (q & 0xFFFFu) | (hsum << 16) | (osum << 32);
+            wrote = 1;
         }
-        __syncthreads();
-        int changed = 0;
-#pragma unroll
-        for (int k = 0; k < CPT; ++k) {
-            const int li = k * NTHR + tid;
-            if (t2[k] != t1[k]) changed = 1;
-            if (t1[k] != li) {  // (a terminal adds its own zeros)
-                T[li] = (unsigned short)t2[k];
-                H[li] = (unsigned short)(H[li] + hh[k]);
-                O[li] = O[li] + oo[k];
-            }
-        }
-        if (!__syncthreads_or(changed)) break;
+        if (!__syncthreads_or(wrote)) break;
     }
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
         const int li = k * NTHR + tid, ly = li >> 6, lx = li & (TS - 1);
         const int gr = r0 + ly, gc = c0 + lx;
-        const int t = T[li];
+        const unsigned long long p = P64[li];
+        const int t = (int)(p & 0xFFFFu);
         unsigned tc = T_DEAD;
-        if (T[t] == t) {
+        if ((int)(P64[t] & 0xFFFFu) == t) {
             if (sm.code[((t >> 6) + 1) * EW + (t & (TS - 1)) + 1] != 0) tc = (unsigned)perim_index(t >> 6, t & (TS - 1));
             else {
                 const int tr = r0 + (t >> 6), tcc = c0 + (t & (TS - 1));
                 tc = (tr < nr && tcc < nc && tr * nc + tcc == lin0) ? T_ROOT_OUT : T_DEAD;
             }
         }
-        const unsigned h = H[li] & 0xFFFu, o = O[li], nch = (nchpack >> (4 * k)) & 15u;   // (h <= 4095 unless the cell is dead)
+        const unsigned h = (unsigned)(p >> 16) & 0xFFFu, o = (unsigned)(p >> 32), nch = (nchpack >> (4 * k)) & 15u;   // (h <= 4095 unless dead)
         if (gr < nr && gc < nc) LR[(size_t)gr * nc + gc] = make_uint2(tc | (h << 16) | (nch << 28), o);
         if (ly == 0 || ly == TS - 1 || lx == 0 || lx == TS - 1) eho[tile * NSLOT + perim_index(ly, lx)] = make_uint2(h, o);
     }
