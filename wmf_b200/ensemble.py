@@ -70,8 +70,14 @@ def share_rain(rain, device):
     import torch
     dist, rank, world = _dist()
     h = torch.as_tensor(np.ascontiguousarray(rain, dtype=np.int32)) if not hasattr(rain, "is_cuda") else rain
+    def settle(t):
+        # the library launches on the context's own stream: what torch queued on its current stream must have landed
+        if t.is_cuda:
+            torch.cuda.current_stream(t.device).synchronize()
+        return t
+
     if world == 1:
-        return h.to(device, non_blocking=True)
+        return settle(h.to(device, non_blocking=True))
     R, N = h.shape
     per = (R + world - 1) // world
     mine = torch.zeros((per, N), dtype=torch.int32, device=device)
@@ -85,7 +91,7 @@ def share_rain(rain, device):
         dist.all_gather(lst, mine)
         parts = torch.stack(lst, 0)
     # parts[r, j] = record r + j*world  ->  record order
-    return parts.permute(1, 0, 2).reshape(per * world, N)[:R].contiguous()
+    return settle(parts.permute(1, 0, 2).reshape(per * world, N)[:R].contiguous())
 
 
 def evaluate_population(models, calibs, qobs, n_cont, n_reg, rain, pos_evento, row: int = 0,
