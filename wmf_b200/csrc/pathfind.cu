@@ -62,8 +62,11 @@ __device__ __forceinline__ int node_of(int gr, int gc, int ntx) {
     return ((gr >> 6) * ntx + (gc >> 6)) * NSLOT + perim_index(gr & (TS - 1), gc & (TS - 1));
 }
 __device__ __forceinline__ void code_move(int d, int &dc, int &dr) {  // keypad 7 8 9 / 4 5 6 / 1 2 3, rows grow downwards
-    dc = (d - 1) % 3 - 1;
-    dr = 1 - (d - 1) / 3;
+    // dc = (d - 1) % 3 - 1, dr = 1 - (d - 1) / 3 for d = 1..9, from two 2-bit tables (value + 1 at bits 2d, 2d + 1)
+    constexpr unsigned DC = (0u << 2) | (1u << 4) | (2u << 6) | (0u << 8) | (1u << 10) | (2u << 12) | (0u << 14) | (1u << 16) | (2u << 18);
+    constexpr unsigned DR = (2u << 2) | (2u << 4) | (2u << 6) | (1u << 8) | (1u << 10) | (1u << 12) | (0u << 14) | (0u << 16) | (0u << 18);
+    dc = (int)((DC >> (2 * d)) & 3u) - 1;
+    dr = (int)((DR >> (2 * d)) & 3u) - 1;
 }
 // effective direction code of raster cell (gr, gc): 0 = no downstream (outside the raster, not a D8 code, points off the
 // map, or the outlet -- the search never follows the outlet's own direction, cuencas.f90:552-589)
@@ -228,9 +231,15 @@ k_pf_local2(const int32_t *__restrict__ dir, int nc, int nr, int ntx, int lin0, 
     const int r0 = (tile / ntx) * TS, c0 = (tile % ntx) * TS;
     // the 3x3 probe order of cuencas.f90:555-571 and the code a neighbour must carry to be a child
     constexpr int PDC[8] = {-1, 0, 1, -1, 1, -1, 0, 1}, PDR[8] = {-1, -1, -1, 0, 0, 1, 1, 1}, PCODE[8] = {3, 2, 1, 6, 4, 9, 8, 7};
-    for (int idx = tid; idx < EW * EW; idx += NTHR) {
-        const int ey = idx / EW - 1, ex = idx % EW - 1;
-        sm.code[idx] = (unsigned char)eff_code(dir, nc, nr, r0 + ey, c0 + ex, lin0);
+    {   // (row, column) of the extended tile advance by NTHR cells per trip without a division
+        constexpr int DY = NTHR / EW, DX = NTHR % EW;
+        int ey = tid / EW, ex = tid % EW;
+        for (int idx = tid; idx < EW * EW; idx += NTHR) {
+            sm.code[idx] = (unsigned char)eff_code(dir, nc, nr, r0 + ey - 1, c0 + ex - 1, lin0);
+            ex += DX;
+            ey += DY;
+            if (ex >= EW) { ex -= EW; ++ey; }
+        }
     }
     __syncthreads();
     uint32_t *Ac = sm.bufA, *An = sm.bufB;
@@ -364,8 +373,11 @@ k_pf_local2(const int32_t *__restrict__ dir, int nc, int nr, int ntx, int lin0, 
             const int t = (int)(p & 0xFFFFu);
             const unsigned long long q = P64[t];
             if ((int)(q & 0xFFFFu) == t) { done |= 1u << k; continue; }   // t is a terminal (my own word when I am one)
-            const unsigned long long hsum = ((p >> 16) + (q >> 16)) & 0xFFFFu, osum = ((p >> 32) + (q >> 32)) & 0xFFFFFFFFu;
-            P64[li] = (q & 0xFFFFu) | (hsum << 16) | (osum << 32);
+            // (hops stay below 2^16 -- a path inside a tile has at most 4095 -- so the low words add without a carry into T)
+            const unsigned plo = (unsigned)p, qlo = (unsigned)q;
+            const unsigned lo = (qlo & 0xFFFFu) | ((plo & 0xFFFF0000u) + (qlo & 0xFFFF0000u));
+            const unsigned hi = (unsigned)(p >> 32) + (unsigned)(q >> 32);
+            P64[li] = (unsigned long long)lo | ((unsigned long long)hi << 32);
             wrote = 1;
         }
         if (!__syncthreads_or(wrote)) break;
@@ -395,7 +407,7 @@ k_pf_local2(const int32_t *__restrict__ dir, int nc, int nr, int ntx, int lin0, 
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void k_pf_bd_init(int n_nodes, const int32_t *__restrict__ bdown, const int32_t *__restrict__ bnext,
                              const uint32_t *__restrict__ boff, const uint2 *__restrict__ eho, int32_t *__restrict__ nx,
-                             uint2 *__restrict__ dp) {
+                             uint2 *__restrict__ dp, unsigned char *__restrict__ age) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n_nodes) return;
     const int bd = bdown[x];
@@ -408,11 +420,17 @@ __global__ void k_pf_bd_init(int n_nodes, const int32_t *__restrict__ bdown, con
     }
     nx[x] = n;
     dp[x] = v;
+    age[x] = (bd >= 0) ? 0 : 2;
 }
+// Only exit cells are ever looked up (by k_pf_emit and by other exit cells), so the other perimeter slots are skipped; a
+// node whose jump has ended is copied into the other buffer once more (age 1 -> 2) and then left alone.
 __global__ void k_pf_bd_jump(int n_nodes, const int32_t *__restrict__ nx_in, const uint2 *__restrict__ dp_in,
-                             int32_t *__restrict__ nx_out, uint2 *__restrict__ dp_out, int *__restrict__ more) {
+                             int32_t *__restrict__ nx_out, uint2 *__restrict__ dp_out, unsigned char *__restrict__ age,
+                             int *__restrict__ more) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n_nodes) return;
+    const unsigned char a = age[x];
+    if (a >= 2) return;
     int n = nx_in[x];
     uint2 v = dp_in[x];
     if (n >= 0) {
@@ -422,6 +440,8 @@ __global__ void k_pf_bd_jump(int n_nodes, const int32_t *__restrict__ nx_in, con
         v.y += u.y;
         n = n2;
         if (n2 >= 0) *more = 1;
+    } else {
+        age[x] = a + 1;
     }
     nx_out[x] = n;
     dp_out[x] = v;
@@ -439,29 +459,41 @@ k_pf_emit(const uint2 *__restrict__ LR, int nc, int nr, int ntx, const int32_t *
     const int tile = blockIdx.x, tid = threadIdx.x;
     const int r0 = (tile / ntx) * TS, c0 = (tile % ntx) * TS;
     unsigned m = 0;
+    uint2 lr[CPT];
+    int nxv[CPT];
+    uint2 dpv[CPT];
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
         const int li = k * NTHR + tid, gr = r0 + (li >> 6), gc = c0 + (li & (TS - 1));
-        if (gc >= nc || gr >= nr) continue;
-        const size_t lin = (size_t)gr * nc + gc;
-        const uint2 lr = LR[lin];
-        const unsigned tc = lr.x & 0xFFFFu, h = (lr.x >> 16) & 0xFFFu, nch = lr.x >> 28;
+        lr[k] = (gc < nc && gr < nr) ? __ldg(LR + (size_t)gr * nc + gc) : make_uint2(T_DEAD, 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const unsigned tc = lr[k].x & 0xFFFFu;
+        nxv[k] = DEAD;
+        dpv[k] = make_uint2(0u, 0u);
+        if (tc < T_ROOT_OUT) {
+            const int node = tile * NSLOT + (int)tc;
+            nxv[k] = __ldg(nx + node);
+            dpv[k] = __ldg(dp + node);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int li = k * NTHR + tid, gr = r0 + (li >> 6), gc = c0 + (li & (TS - 1));
+        const unsigned tc = lr[k].x & 0xFFFFu, h = (lr[k].x >> 16) & 0xFFFu, nch = lr[k].x >> 28;
         unsigned depth = 0, pre = 0;
         bool ok = false;
-        if (tc == T_ROOT_OUT) { depth = h; pre = lr.y; ok = true; }
-        else if (tc != T_DEAD) {
-            const int node = tile * NSLOT + (int)tc;
-            if (nx[node] == ROOT_OUT) {
-                const uint2 v = dp[node];
-                depth = v.x + h;
-                pre = v.y + lr.y;
-                ok = true;
-            }
+        if (tc == T_ROOT_OUT) { depth = h; pre = lr[k].y; ok = true; }
+        else if (tc != T_DEAD && nxv[k] == ROOT_OUT) {
+            depth = dpv[k].x + h;
+            pre = dpv[k].y + lr[k].y;
+            ok = true;
         }
         if (ok) {
             if (pre < n_basin && depth < (1u << 28)) {
                 keys[pre] = depth | (nch << 28);
-                vals[pre] = (uint32_t)lin;
+                vals[pre] = (uint32_t)((size_t)gr * nc + gc);
                 m = max(m, depth);
             } else {
                 atomicAdd(&stat[1], 1u);
@@ -492,121 +524,182 @@ __global__ void k_pf_outlet_check(const int32_t *__restrict__ dir, const uint2 *
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// stable LSD radix pass, 8 bits: per-tile digit histograms, one device scan, ranked scatter
+// stable LSD radix pass, 8 bits: per-tile digit histograms, one device scan, ranked scatter through shared memory
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int RS_THREADS = 256, RS_WARPS = RS_THREADS / 32, RS_TILE = 4096, RS_PER_WARP = RS_TILE / RS_WARPS, RS_SUB = RS_PER_WARP / 32;
+constexpr int RS_THREADS = 512, RS_WARPS = RS_THREADS / 32, RS_TILE = 4096, RS_PER_WARP = RS_TILE / RS_WARPS, RS_SUB = RS_PER_WARP / 32;
 
 __global__ void __launch_bounds__(RS_THREADS)
 k_rs_hist(const uint32_t *__restrict__ keys, uint32_t n, int shift, int nblk, int32_t *__restrict__ hist /* [256][nblk] */) {
     __shared__ unsigned h[256];
-    h[threadIdx.x] = 0;
+    if (threadIdx.x < 256) h[threadIdx.x] = 0;
     __syncthreads();
     const size_t base = (size_t)blockIdx.x * RS_TILE;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
-        const size_t idx = base + i;
-        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255u], 1u);
+    constexpr int V = RS_TILE / (4 * RS_THREADS);   // 128-bit loads per thread (the tile start is 16-byte aligned)
+    uint4 q[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const size_t idx = base + 4 * ((size_t)i * RS_THREADS + threadIdx.x);
+        if (idx + 3 < n) q[i] = __ldg(reinterpret_cast<const uint4 *>(keys + idx));
+        else {
+            q[i].x = idx < n ? keys[idx] : 0xFFFFFFFFu;
+            q[i].y = idx + 1 < n ? keys[idx + 1] : 0xFFFFFFFFu;
+            q[i].z = idx + 2 < n ? keys[idx + 2] : 0xFFFFFFFFu;
+            q[i].w = 0xFFFFFFFFu;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const size_t idx = base + 4 * ((size_t)i * RS_THREADS + threadIdx.x);
+        const uint32_t kk[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (idx + c < n) atomicAdd(&h[(kk[c] >> shift) & 255u], 1u);
     }
     __syncthreads();
-    hist[(size_t)threadIdx.x * nblk + blockIdx.x] = (int32_t)h[threadIdx.x];
+    if (threadIdx.x < 256) hist[(size_t)threadIdx.x * nblk + blockIdx.x] = (int32_t)h[threadIdx.x];
 }
 
-// every warp owns 512 consecutive items of the tile, so "warp, sub-step, lane" is the input order: stable
-__global__ void __launch_bounds__(RS_THREADS)
+// Every warp owns 512 consecutive items of the tile, so "warp, sub-step, lane" is the input order: the ranks are stable.
+// The tile is first sorted by digit inside shared memory; the copy-out then writes each digit's run with consecutive
+// threads on consecutive addresses (runs of ~16 items instead of 4-byte writes all over the output).
+struct RsSmem {
+    uint32_t k[RS_TILE], v[RS_TILE];
+    unsigned wh[RS_WARPS][256];
+    unsigned gbase[256];
+    int scan[33];
+};
+
+__global__ void __launch_bounds__(RS_THREADS, 3)
 k_rs_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n, int shift, int nblk,
              const int32_t *__restrict__ hist_scan, uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
-    __shared__ unsigned wh[RS_WARPS][256];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RsSmem &sm = *reinterpret_cast<RsSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&wh[0][0])[i] = 0;
+    for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&sm.wh[0][0])[i] = 0;
     __syncthreads();
-    const size_t base = (size_t)blockIdx.x * RS_TILE + (size_t)wid * RS_PER_WARP;
+    const size_t tile0 = (size_t)blockIdx.x * RS_TILE, base = tile0 + (size_t)wid * RS_PER_WARP;
     uint32_t k[RS_SUB], v[RS_SUB];
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
     for (int s = 0; s < RS_SUB; ++s) {
         const size_t idx = base + s * 32 + lane;
         const bool valid = idx < n;
-        k[s] = valid ? keys[idx] : 0u;
-        v[s] = valid ? vals[idx] : 0u;
+        k[s] = valid ? __ldg(keys + idx) : 0u;
+        v[s] = valid ? __ldg(vals + idx) : 0u;
+    }
+#pragma unroll
+    for (int s = 0; s < RS_SUB; ++s) {
+        const bool valid = base + s * 32 + lane < n;
         const int d = valid ? (int)((k[s] >> shift) & 255u) : 256 + lane;   // invalid lanes match nobody
         const unsigned m = __match_any_sync(0xffffffffu, d);
-        if (valid && (m & lt) == 0) wh[wid][d] += __popc(m);   // the lowest lane of every digit group
+        if (valid && (m & lt) == 0) sm.wh[wid][d] += __popc(m);   // the lowest lane of every digit group
         __syncwarp();
     }
     __syncthreads();
-    {   // digit `tid`: where each warp's items of that digit start in the output
-        unsigned run = (unsigned)hist_scan[(size_t)tid * nblk + blockIdx.x];
+    // digit `tid`: where each warp's items of that digit start inside the sorted tile, and where the run goes globally
+    unsigned tot = 0;
+    if (tid < 256) {
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) tot += sm.wh[w][tid];
+    }
+    int cta_tot;
+    const int start = block_scan_excl((int)tot, sm.scan, &cta_tot);
+    if (tid < 256) {
+        unsigned run = (unsigned)start;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) {
-            const unsigned c = wh[w][tid];
-            wh[w][tid] = run;
+            const unsigned c = sm.wh[w][tid];
+            sm.wh[w][tid] = run;
             run += c;
         }
+        sm.gbase[tid] = (unsigned)hist_scan[(size_t)tid * nblk + blockIdx.x] - (unsigned)start;
     }
     __syncthreads();
 #pragma unroll
     for (int s = 0; s < RS_SUB; ++s) {
-        const size_t idx = base + s * 32 + lane;
-        const bool valid = idx < n;
+        const bool valid = base + s * 32 + lane < n;
         const int d = valid ? (int)((k[s] >> shift) & 255u) : 256 + lane;
         const unsigned m = __match_any_sync(0xffffffffu, d);
         unsigned pos = 0;
-        if (valid) pos = wh[wid][d] + __popc(m & lt);
+        if (valid) pos = sm.wh[wid][d] + __popc(m & lt);
         __syncwarp();
-        if (valid && (m & lt) == 0) wh[wid][d] += __popc(m);
+        if (valid && (m & lt) == 0) sm.wh[wid][d] += __popc(m);
         __syncwarp();
         if (valid) {
-            keys_out[pos] = k[s];
-            vals_out[pos] = v[s];
+            sm.k[pos] = k[s];
+            sm.v[pos] = v[s];
         }
+    }
+    __syncthreads();
+    for (int i = tid; i < cta_tot; i += RS_THREADS) {
+        const uint32_t kk = sm.k[i];
+        const unsigned g = sm.gbase[(kk >> shift) & 255u] + (unsigned)i;
+        keys_out[g] = kk;
+        vals_out[g] = sm.v[i];
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // stage F: queue order -> q_par (position of the parent, 1-based), q_acum
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int FN_THREADS = 256, FN_ITEMS = 16, FN_TILE = FN_THREADS * FN_ITEMS;
+constexpr int FN_THREADS = 256, FN_WARPS = FN_THREADS / 32, FN_TILE = 2048, FN_PER_WARP = FN_TILE / FN_WARPS, FN_SUB = FN_PER_WARP / 32;
 
 __global__ void __launch_bounds__(FN_THREADS)
 k_pf_final_sums(const uint32_t *__restrict__ keys, uint32_t n, int32_t *__restrict__ blk_sum) {
     __shared__ int sm[33];
-    const size_t base = (size_t)blockIdx.x * FN_TILE + (size_t)threadIdx.x * FN_ITEMS;
+    const size_t base = (size_t)blockIdx.x * FN_TILE;
     int s = 0;
-#pragma unroll
-    for (int i = 0; i < FN_ITEMS; ++i)
-        if (base + i < n) s += (int)(keys[base + i] >> 28);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < FN_TILE; i += FN_THREADS)
+        if (base + i < n) s += (int)(__ldg(keys + base + i) >> 28);
     int tot;
     block_scan_excl(s, sm, &tot);
     if (threadIdx.x == 0) blk_sum[blockIdx.x] = tot;
 }
 
-// the children of queue position j occupy positions [cs(j), cs(j) + nch(j)), cs(j) = 1 + children of the positions before j
-__global__ void __launch_bounds__(FN_THREADS)
+// the children of queue position j occupy positions [cs(j), cs(j) + nch(j)), cs(j) = 1 + children of the positions before j.
+// A warp takes 512 consecutive positions, 32 at a time: loads, the size gather and the parent writes are coalesced
+// (consecutive lanes own consecutive child ranges).
+__global__ void __launch_bounds__(FN_THREADS, 4)
 k_pf_final_write(const uint32_t *__restrict__ keys, const int32_t *__restrict__ q_lin, uint32_t n,
                  const int32_t *__restrict__ blk_scan, const uint32_t *__restrict__ S, int32_t *__restrict__ q_par,
                  int32_t *__restrict__ q_acum, unsigned *__restrict__ stat) {
-    __shared__ int sm[33];
-    const size_t base = (size_t)blockIdx.x * FN_TILE + (size_t)threadIdx.x * FN_ITEMS;
-    int c[FN_ITEMS];
-    int s = 0;
+    __shared__ int wtot[FN_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t base = (size_t)blockIdx.x * FN_TILE + (size_t)wid * FN_PER_WARP;
+    int c[FN_SUB], ex[FN_SUB];
+    int run = 0;
 #pragma unroll
-    for (int i = 0; i < FN_ITEMS; ++i) {
-        c[i] = (base + i < n) ? (int)(keys[base + i] >> 28) : 0;
-        s += c[i];
+    for (int s = 0; s < FN_SUB; ++s) {
+        const size_t j = base + s * 32 + lane;
+        c[s] = (j < n) ? (int)(__ldg(keys + j) >> 28) : 0;
+        const int incl = warp_scan_incl(c[s]);
+        ex[s] = run + incl - c[s];
+        run += __shfl_sync(0xffffffffu, incl, 31);
     }
-    int tot;
-    const int ex = block_scan_excl(s, sm, &tot);
-    long long cs = 1ll + blk_scan[blockIdx.x] + ex;
+    if (lane == 0) wtot[wid] = run;
+    __syncthreads();
+    long long cs0 = 1ll + blk_scan[blockIdx.x];
+    for (int w = 0; w < wid; ++w) cs0 += wtot[w];
+    int32_t lin[FN_SUB];
 #pragma unroll
-    for (int i = 0; i < FN_ITEMS; ++i) {
-        const size_t j = base + i;
+    for (int s = 0; s < FN_SUB; ++s) {
+        const size_t j = base + s * 32 + lane;
+        lin[s] = (j < n) ? __ldg(q_lin + j) : -1;
+    }
+    uint32_t sz[FN_SUB];
+#pragma unroll
+    for (int s = 0; s < FN_SUB; ++s) sz[s] = (lin[s] >= 0) ? __ldg(S + lin[s]) : 0u;
+#pragma unroll
+    for (int s = 0; s < FN_SUB; ++s) {
+        const size_t j = base + s * 32 + lane;
         if (j < n) {
-            for (int q = 0; q < c[i]; ++q) {
+            const long long cs = cs0 + ex[s];
+            for (int q = 0; q < c[s]; ++q) {
                 if (cs + q < (long long)n) q_par[cs + q] = (int32_t)(j + 1);
                 else atomicAdd(&stat[1], 1u);
             }
-            cs += c[i];
-            q_acum[j] = (int32_t)S[q_lin[j]];
+            q_acum[j] = (int32_t)sz[s];
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) q_par[0] = 0;
@@ -672,10 +765,10 @@ int wmf_pathfind(wmf_ctx *ctx, Scope &sc, const int32_t *d_dir, int nc, int nr, 
     uint32_t n_basin = 0;
     CU_TRY(ctx, cudaMemcpyAsync(&n_basin, S + lin0, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     // D
-    LAUNCH(ctx, k_pf_bd_init, GN, B, 0, n_nodes, bdown, bnext, boff, eho, nxA, dpA);
+    LAUNCH(ctx, k_pf_bd_init, GN, B, 0, n_nodes, bdown, bnext, boff, eho, nxA, dpA, leaf /* reused as the age */);
     for (int round = 0; round < 40; ++round) {
         CU_TRY(ctx, cudaMemsetAsync(more, 0, sizeof(int), ctx->stream));
-        LAUNCH(ctx, k_pf_bd_jump, GN, B, 0, n_nodes, nxA, dpA, nxB, dpB, more);
+        LAUNCH(ctx, k_pf_bd_jump, GN, B, 0, n_nodes, nxA, dpA, nxB, dpB, leaf, more);
         std::swap(nxA, nxB);
         std::swap(dpA, dpB);
         int h_more = 0;
@@ -718,11 +811,12 @@ int wmf_pathfind(wmf_ctx *ctx, Scope &sc, const int32_t *d_dir, int nc, int nr, 
         WMF_TRY(sc.alloc(&hist_scan, (size_t)256 * nblk));
     }
     uint32_t *kin = k0, *vin = v0, *kout = k1, *vout = v1;
+    if (passes) CU_TRY(ctx, cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
     for (int p = 0; p < passes; ++p) {
         uint32_t *vdst = (p == passes - 1) ? reinterpret_cast<uint32_t *>(ctx->q_lin) : vout;
         LAUNCH(ctx, k_rs_hist, nblk, RS_THREADS, 0, kin, n, 8 * p, nblk, hist);
         WMF_TRY(wmf_device_exclusive_scan_i32(ctx, sc, hist, hist_scan, (int64_t)256 * nblk, nullptr));
-        LAUNCH(ctx, k_rs_scatter, nblk, RS_THREADS, 0, kin, vin, n, 8 * p, nblk, hist_scan, kout, vdst);
+        LAUNCH(ctx, k_rs_scatter, nblk, RS_THREADS, sizeof(RsSmem), kin, vin, n, 8 * p, nblk, hist_scan, kout, vdst);
         std::swap(kin, kout);
         vin = vdst;
         vout = (vdst == v1) ? v0 : v1;
