@@ -54,7 +54,13 @@ BYTES_PER_CELL_PATH_A = 28.0           # basin_find + basin_cut 16 B, basin_acum
 TRAFFIC = {
     "single": (60.0e6, "ncu --set full, one mid-run launch of k_shia_tb<4,...> on C2 = 1.33e6 cell-steps (cold-cache replay): "
                        "56.5 MB read + 3.5 MB written = 45 B per cell-step against 144 algorithmic; profiles/README.md"),
-    "ensemble": (None, "no ncu capture of the member-minor variant yet"),
+    # per member-cell-step; scaled to the average launch of the timed run in run_ours()
+    "ensemble": (31.8, "ncu --set full, one mid-run launch of k_shia_tb<16,...> (C4 shape, 256 members, 47636 CTAs x 256 threads x 16 "
+                       "steps = 1.95e8 member-cell-steps, cold-cache replay): 3.11 GB read + 3.09 GB written = 31.8 B per "
+                       "member-cell-step against 80 algorithmic (the outflow ring is produced and consumed through L2); this "
+                       "figure x the member-cell-steps of an average launch; profiles/ncu_k_shia_tb_ensemble_r2_raw.txt"),
+    "c5": (None, "ncu captures of k_shia_tb<4,KIN,SED,SLIDES> are under profiles/ (ncu_k_shia_tb_c5_*_r2_raw.txt): a mid-run "
+                 "launch of 415 CTAs moved 58 MB; not scaled to the average launch"),
 }
 WORKLOADS = {
     # BASELINE.json configs[3]: calibration ensemble on the ~250k-cell basin
@@ -610,7 +616,9 @@ def run_ours(args):
         peak, peak_kind = peaks()
         ms, e2e_ms, wave, units = res["ms"], res["e2e_ms"], res["wave_ms"], res["units"]
         achieved = res["bytes_per_unit"] * units / (wave / 1e3) / 1e9
-        traffic, traffic_note = TRAFFIC[cfg["kind"]] if not cfg["sediments"] else (None, "no ncu capture of this variant yet")
+        traffic, traffic_note = TRAFFIC[cfg["kind"]] if not cfg["sediments"] else TRAFFIC["c5"]
+        if cfg["kind"] == "ensemble":
+            traffic = traffic * units / max(res["waves"], 1)
         extra = {"levels": res["levels"], "waves_per_run": res["waves"], "wave_kernel_ms_per_step": wave,
                  "setup_and_epilogue_ms_per_step": ms - wave}
         with tempfile.TemporaryDirectory(prefix="wmf_cpu_") as tmpd:

@@ -46,7 +46,7 @@ def _worker(rank, world, port, P, q):
         got = evaluate_population(None, calibs, None, 3, 10, None, None, members_per_launch=3, run_batch=run_batch)
         want = _fake_scores(calibs)
         ok = bool(np.array_equal(got.numpy(), want)) and sum(calls) == shard_members(P, rank, world).size and max(calls) <= 3
-        # the shared rain upload: every rank contributes records rank::world, all ranks end up with the whole table
+        # the shared rain upload: every rank contributes one block of records, all ranks end up with the whole table
         from wmf_b200.ensemble import share_rain
         for R in (1, 2, P, 2 * P + 1):
             table = rng.integers(0, 90000, (R, 37)).astype(np.int32)

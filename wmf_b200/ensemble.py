@@ -64,12 +64,14 @@ def share_rain(rain, device):
     """Device copy of a HOST rain table ``(n_records, N)`` int32 for an ensemble evaluation.
 
     Every rank of an ensemble reads the same table.  Instead of N ranks pulling N identical copies through the host's
-    memory and their PCIe links, rank r uploads records ``r::world`` only (from page-locked memory when the caller pinned
-    the table) and one NCCL all-gather over NVLink hands every rank the rest; the records are then put back in order on the
-    device.  Bit-identical to a plain upload (integer copies).  A single process just uploads."""
+    memory and their PCIe links, rank r uploads one contiguous block of ``ceil(R / world)`` records only (a single DMA
+    from page-locked memory when the caller pinned the table) and one NCCL all-gather over NVLink hands every rank the
+    other blocks, already in record order.  Bit-identical to a plain upload (integer copies).  A single process just
+    uploads."""
     import torch
     dist, rank, world = _dist()
     h = torch.as_tensor(np.ascontiguousarray(rain, dtype=np.int32)) if not hasattr(rain, "is_cuda") else rain
+
     def settle(t):
         # the library launches on the context's own stream: what torch queued on its current stream must have landed
         if t.is_cuda:
@@ -80,18 +82,20 @@ def share_rain(rain, device):
         return settle(h.to(device, non_blocking=True))
     R, N = h.shape
     per = (R + world - 1) // world
-    mine = torch.zeros((per, N), dtype=torch.int32, device=device)
-    part = h[rank::world]
-    mine[: part.shape[0]].copy_(part, non_blocking=True)
-    parts = torch.empty((world, per, N), dtype=torch.int32, device=device)
+    full = torch.empty((world * per, N), dtype=torch.int32, device=device)
+    lo, hi = min(R, rank * per), min(R, (rank + 1) * per)
+    mine = torch.empty((per, N), dtype=torch.int32, device=device)
+    if hi > lo:
+        mine[: hi - lo].copy_(h[lo:hi], non_blocking=True)
+    if hi - lo < per:
+        mine[hi - lo:].zero_()
     if dist.get_backend() == "nccl":
-        dist.all_gather_into_tensor(parts.view(world * per, N), mine)
-    else:                                   # gloo (CPU tests of the record bookkeeping)
+        dist.all_gather_into_tensor(full, mine)
+    else:                                                # gloo (CPU tests of the record bookkeeping)
         lst = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(lst, mine)
-        parts = torch.stack(lst, 0)
-    # parts[r, j] = record r + j*world  ->  record order
-    return settle(parts.permute(1, 0, 2).reshape(per * world, N)[:R].contiguous())
+        full = torch.cat(lst, 0)
+    return settle(full[:R])
 
 
 def evaluate_population(models, calibs, qobs, n_cont, n_reg, rain, pos_evento, row: int = 0,
