@@ -18,9 +18,7 @@ def test_fuzz_shia_gpu_vs_oracle(case, tmp_path):
     if fc is None:
         pytest.skip("the random outlet caught a tiny basin")
     inp, mode, extra, n, T = dict(fc["inp"]), fc["mode"], fc["extra"], fc["n"], fc["T"]
-    if mode in ("sepf", "sepr"):          # the separations run in the time-blocked kernel, which does not produce the per-step means
-        for k in ("show_storage", "show_mean_speed", "show_mean_retorno"):
-            inp[k] = 0
+    # (separate_* together with the per-step means: two launch sequences behind one shia_v1 call, _models._switch_passes)
     ref = oracle.shia_v1(inp)
     m = ModelsModule()
     synth.apply_to_models(m, inp)

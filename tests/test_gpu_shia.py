@@ -456,6 +456,53 @@ def test_separate_fluxes():
     np.testing.assert_array_equal(ret0[0], ret[0])
 
 
+def test_switch_combinations_in_one_call(tmp_path):
+    """The reference runs any combination of its switches in ONE shia_v1 call (wmf.py:4634-4637 returns QsepDict and
+    QsediDict of the same run; SimuBasin(SeparateFluxes='si', SaveStorage='si', ShowStorage='si') is an ordinary
+    configuration).  separate_fluxes + separate_rain + sediments + slides + a storage dump + the per-step means together:
+    every output against the oracle's single run, which is bit-identical to the reference's Fortran for each of them."""
+    from wmf_b200 import ModelsModule, synth
+    from wmf_b200._models import read_float_basin_ncol
+    bs, inp = build("G2", 100, 80, 31, n_reg=72, rain_peak_mm=60.0, speed_type=(2, 2, 1), sediments=True, slides=True)
+    types = synth.make_rain_types(inp, 31)
+    T, N = inp["n_reg"], bs["n"]
+    guarda = np.zeros(T, np.int32)
+    guarda[[10, 40, T - 1]] = [1, 2, 3]
+    flags = dict(separate_fluxes=1, separate_rain=1, sim_sediments=1, sim_slides=1, save_storage=1, show_storage=1,
+                 show_mean_speed=1, show_speed=1)
+    ref = run_oracle(dict(inp, **types), {k: v for k, v in flags.items() if k != "save_storage"})   # (the dump is checked below)
+    m = ModelsModule()
+    synth.apply_to_models(m, inp)
+    for k, v in flags.items():
+        setattr(m, k, v)
+    m.guarda_cond = guarda
+    m.set_rain(inp["rain"], inp["pos_evento"])
+    m.set_rain_types(types["conv"], types["stra"], types["pos_conv"], types["pos_stra"])
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    n_conth = max(1, int(np.count_nonzero(inp["control_h"])))
+    sto = str(tmp_path / "sto.StObin")
+    ret = m.shia_v1(None, None, inp["calib"], n_cont, n_conth, T, None, None, N, sto)
+    compare_core(ret, m, ref, N)
+    assert ref["qseparated"].max() > 0 and ref["qsep_byrain"].max() > 0 and ref["qsed"].max() > 0
+    close(ret[2], ref["qseparated"], name="Qseparated")
+    close(ret[10], ref["qsep_byrain"], name="Qsep_byrain")
+    close(m.storage_conv, ref["storage_conv"], name="Storage_conv")
+    close(m.storage_stra, ref["storage_stra"], name="Storage_stra")
+    close(ret[1], ref["qsed"], name="Qsed")
+    for k in ("vs", "vd", "vsc", "vdc"):
+        close(getattr(m, k), ref[k], name=k)
+    close(m.voldepo, ref["voldepo"], name="VolDEPo")
+    np.testing.assert_array_equal(np.asarray(m.sl_slideocurrence).reshape(-1), ref["sl_slideocurrence"])
+    close(ret[7], ref["speed"], name="Speed")
+    close(m.mean_storage, ref["mean_storage64"], name="mean_storage")
+    close(m.mean_speed, ref["mean_speed64"], name="mean_speed")
+    rec, _ = read_float_basin_ncol(sto, 3, N, 5)               # the dump of the last step is the final storage
+    close(rec, ref["stoout"], name="storage dump, record 3")
+    # the switches are as the caller left them
+    for k, v in flags.items():
+        assert int(getattr(m, k)) == v
+
+
 @pytest.mark.parametrize("variant", ["linear_return", "kinematic", "empty_capillary"])
 def test_separate_rain(variant, tmp_path):
     """separate_rain = 1 (modelosv2.f90:346-359, 452-456, 471-474, 485-488, 530-547, 580-592, 605-608, 623-628, 645-655,

@@ -411,7 +411,11 @@ class ModelsModule:
             if int(getattr(self, k)) == 1:
                 raise NotImplementedError(f"models.{k} = 1 selects a sub-model that is outside the B200 hot path "
                                           "(SURVEY.md 8f); set it to 0")
-        self._check_switch_combination()
+        extra = self._switch_passes()
+        if extra:
+            return self._shia_v1_passes(extra, (ruta_bin, ruta_hdr, calib, n_cont, n_conth, n_reg, stoin, hspeedin, n_cel,
+                                                ruta_storage, ruta_speed, ruta_vfluxes, ruta_binconv, ruta_binstra,
+                                                ruta_hdrconv, ruta_hdrstra, ruta_retorno, ruta_rc))
         a = object.__getattribute__(self, "__dict__")["_a"]
         if "drena" not in a:
             raise ValueError("models.drena is not allocated")
@@ -468,29 +472,47 @@ class ModelsModule:
         return (out["q"], qsed, out.get("qseparated", zeros(nc, 3, T)), out["hum"], out["st1"], out["st3"], out["balance"], out["speed"],
                 out["areacontrol"], out["stoout"], out.get("qsep_byrain", zeros(nc, 2, T)))
 
-    def _check_switch_combination(self):
-        """The reference runs any combination of its switches in one ``shia_v1`` call.  The CUDA kernels cover every switch,
-        but not every PAIR of them ("Switch combinations"): the unsupported ones are refused here, before any
-        GPU work, instead of failing half way or -- worse -- returning a dump nobody wrote."""
-        on = lambda k: int(getattr(self, k)) == 1
-        means = [k for k in ("show_storage", "show_mean_speed") if on(k)]
-        if float(self.retorno_gr) == 1.0 and on("show_mean_retorno"):
-            means.append("show_mean_retorno")
-        dumps = [k for k in ("save_storage", "save_speed", "save_vfluxes", "save_rc", "save_retorno") if on(k)]
-        subs = [k for k in ("sim_sediments", "sim_slides") if on(k)]
-        sep = [k for k in ("separate_fluxes", "separate_rain") if on(k)]
+    # switches one launch sequence of wmf_shia_run carries together ("Switch combinations")
+    _BASE_SWITCHES = ("sim_sediments", "sim_slides", "save_storage", "save_speed", "save_vfluxes", "save_rc", "save_retorno",
+                      "show_storage", "show_mean_speed", "show_mean_retorno")
+    _SOLO_SWITCHES = ("separate_fluxes", "separate_rain", "sim_floods")
 
-        def refuse(a, b):
-            raise NotImplementedError(f"models.{a} = 1 together with models.{b} = 1: this pair of switches is not built into "
-                                      "one CUDA kernel yet (DESIGN.md, 'Switch combinations'); run the two outputs in two calls")
-        if on("sim_floods"):
-            for k in subs + dumps + means + sep:
-                refuse("sim_floods", k)
-        for sk in sep:
-            for k in subs + dumps + means:
-                refuse(sk, k)
-        if len(sep) == 2:
-            refuse(sep[0], sep[1])
+    def _switch_passes(self):
+        """The reference runs any combination of its switches in one ``shia_v1`` call (wmf.py:4634-4637 returns the
+        separated fluxes AND the sediment series of the same run).  One ``wmf_shia_run`` carries sediments, landslides,
+        every ``save_*`` dump and the ``show_*`` means together, but ``separate_fluxes``, ``separate_rain`` and
+        ``sim_floods`` each have a kernel variant of their own.  All of them are diagnostics computed FROM the hydrology --
+        none feeds back into the tanks or the routing -- so a combination is the union of the outputs of runs over the same
+        hydrology: the first pass runs the base group, every further switch gets a pass of its own and contributes only the
+        outputs it owns.  Returns the switches that need such an extra pass ([] = one pass does it)."""
+        on = lambda k: int(getattr(self, k)) == 1
+        solo = [k for k in self._SOLO_SWITCHES if on(k)]
+        base = [k for k in self._BASE_SWITCHES if on(k) and not (k == "show_mean_retorno" and float(self.retorno_gr) != 1.0)]
+        if len(solo) + (1 if base else 0) <= 1:
+            return []
+        return solo if base else solo[1:]
+
+    def _shia_v1_passes(self, extra, args):
+        """shia_v1 for a combination of switches no single kernel variant carries: see ``_switch_passes``."""
+        saved = {k: int(getattr(self, k)) for k in self._BASE_SWITCHES + self._SOLO_SWITCHES}
+        try:
+            for k in extra:
+                setattr(self, k, 0)
+            ret = list(self.shia_v1(*args))                       # base group (or the first solo switch): Q, storages, dumps, ...
+            for k in saved:
+                setattr(self, k, 0)
+            for k in extra:                                       # one pass per remaining switch, everything else off
+                setattr(self, k, 1)
+                r = self.shia_v1(*args)
+                setattr(self, k, 0)
+                if k == "separate_fluxes":
+                    ret[2] = r[2]                                 # Qseparated
+                elif k == "separate_rain":
+                    ret[10] = r[10]                               # Qsep_byrain (Storage_conv / Storage_stra stay in the module)
+        finally:
+            for k, v in saved.items():
+                setattr(self, k, v)
+        return tuple(ret)
 
     def _guarda(self, name, T):
         """guarda_vfluxes as shia_v1 sees it: allocated with >= n_reg entries, else "all zeros" (modelosv2.f90:399-409)."""
