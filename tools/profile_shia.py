@@ -18,6 +18,9 @@ def main():
     ap.add_argument("--slides", action="store_true", help="enable the landslide sub-model")
     ap.add_argument("--kin", action="store_true", help="kinematic hillslope speeds speed_type=[2,2,1] without sub-models")
     ap.add_argument("--steps", type=int, default=0, help="override the number of steps")
+    ap.add_argument("--no-sed", action="store_true", help="switch the workload's sediments off (c5)")
+    ap.add_argument("--no-slides", action="store_true", help="switch the workload's landslides off (c5)")
+    ap.add_argument("--linear", action="store_true", help="linear hillslope speeds speed_type=[1,1,1] (needs --no-sed)")
     a = ap.parse_args()
     import torch
     import bench
@@ -45,6 +48,14 @@ def main():
                     "sl_cohesion": rng.uniform(2, 10, n).astype(np.float32)[None, :],
                     "sl_frictionangle": np.deg2rad(rng.uniform(25, 35, n)).astype(np.float32)[None, :],
                     "sl_radslope": np.deg2rad(rng.uniform(20, 50, n)).astype(np.float32)[None, :]})
+    if a.no_sed:
+        inp["sim_sediments"] = 0
+    if a.no_slides:
+        inp["sim_slides"] = 0
+    if a.linear:
+        inp["speed_type"] = [1, 1, 1]
+    a.sed = a.sed or int(inp.get("sim_sediments", 0)) == 1
+    a.slides = a.slides or int(inp.get("sim_slides", 0)) == 1
     synth.apply_to_models(m, inp)
     m.make_resident()
     d_rain = torch.from_numpy(inp["rain"]).cuda()
