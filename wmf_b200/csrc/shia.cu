@@ -96,6 +96,10 @@ struct ShiaP {
     float4 *outb4;          // [2][K][N][M] what a cell sends downstream at each step of its time block
     int bal_direct;         // red[t][RQ_SAL] holds sum(dS + outputs), balance = that - inputs
     float4 *sedout4;        // [2][K][3][N][M] sediment a cell sends downstream: sus(3) bm(3) ero(3) chan(3)
+    float4 *sedstg4;        // [2][K][2][N][M] what the sediment kernel needs from the hydrology of a step: (speed of tank 2, tank 2
+                            // before its outflow, qlin, 1 = sed_hillslope runs) and (channel tank before its outflow, channel
+                            // speed, discharge, section area)
+    const float *sed_aso;   // [N] sed_factor * So**1.664 (:1339), constant over a run
     // state dumps (single runs): snap_slot[t] = row of sto_snap that receives StoOut after step t, or -1
     const int32_t *snap_slot;
     float *sto_snap;        // [n_snap][N][5]
@@ -784,8 +788,11 @@ struct TbStage {
     static constexpr bool on = (WMF_TB_STAGE != 0) && (K <= 4);
 };
 
-#ifndef TB_MIN_BLOCKS_SED   // sediment / separate_rain variants (1 block per SM: C5 with SED + slides 248 -> 273 ms)
+#ifndef TB_MIN_BLOCKS_SED   // separate_rain variants (and, until the sediments got their own kernel, the SED ones)
 #define TB_MIN_BLOCKS_SED 2
+#endif
+#ifndef SED_MIN_BLOCKS      // k_sed_tb
+#define SED_MIN_BLOCKS 3
 #endif
 
 // x**y and log(x) as the reference's libm evaluates them in fp32 (glibc: correctly rounded in all but a vanishing share of
@@ -938,23 +945,9 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
         if (CHAN) vch = P.hsp[3 * NM + base];
         if (P.retorned) ret_acc = P.retorned[cell];
     }
-    // sediments (:1298-1608): the four 3-fraction stores and the two volume maps ride in registers for the block
-    SedLocal SL;
-    float vdep = 0.f, vero = 0.f;
-    double ero_acc[3] = {0.0, 0.0, 0.0}, dep_acc[3] = {0.0, 0.0, 0.0};
-    if (SED && active) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            SL.Vs[k] = P.sed[(0 + k) * NM + base];
-            SL.Vd[k] = P.sed[(3 + k) * NM + base];
-            SL.Vsc[k] = P.sed[(6 + k) * NM + base];
-            SL.Vdc[k] = P.sed[(9 + k) * NM + base];
-        }
-        vdep = P.voldepo[base];
-        vero = P.volero[base];
-    }
-    float sed_aSo = 0.f;  // alfa * So**1.664 (:1339), once per time block
-    if (SED && KIN && active && P.st[0] == 2) sed_aSo = P.sed_factor * wmf_powf_dd(__ldg(P.hill_slope + cell), 1.664f);
+    // sediments (:1298-1608) run in their own kernel (k_sed_tb, launched after every wave of this one): this kernel only
+    // stages what they read from the hydrology of each step
+    float4 *stg = SED ? P.sedstg4 + (size_t)(b & 1) * K * 2 * NM + base : nullptr;
     // slides (:1649-1707): own failure flag and the step at which an upstream failure reached this cell.  Every mark
     // with a step of this block or earlier was made by a wave before this one, so one read per block is enough.
     int sl_slid = 0, sl_mark = INT_MAX;
@@ -1072,26 +1065,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                     T1 = T1 + bq.x; T2 = T2 + bq.y; T3 = T3 + bq.z; T4 = T4 + bq.w;
                 }
             }
-            if (SED) {
-#pragma unroll
-                for (int k = 0; k < 12; ++k) SL.up[k] = 0.f;
-                SL.ero_add[0] = SL.ero_add[1] = SL.ero_add[2] = 0.f;
-                SL.dep_add[0] = SL.dep_add[1] = SL.dep_add[2] = 0.f;
-                SL.volero_add = SL.voldepo_add = 0.f;
-                const float4 *so = P.sedout4 + ((size_t)(b & 1) * K + tt) * 3 * NM + (size_t)c0 * M + m;
-#pragma unroll 1
-                for (int c = 0; c < nch; ++c, so += M) {
-                    const float4 f0 = so[0], f1 = so[NM], f2 = so[2 * NM];
-                    const float u[12] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w};
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        SL.Vs[i] = SL.Vs[i] + u[0 + i];
-                        SL.Vs[i] = SL.Vs[i] + u[3 + i];
-                        SL.Vs[i] = SL.Vs[i] + u[6 + i];
-                        SL.Vsc[i] = SL.Vsc[i] + u[9 + i];
-                    }
-                }
-            }
+            float4 stg_h = make_float4(0.f, 0.f, 0.f, 0.f);  // (no sed_hillslope unless tank 2 is kinematic, :569-575)
             const float vf2 = fminf(vf1, vs2);
             S1 = S1 + vf1 - vf2;
             const float vf3 = fminf(vf2, vs3);
@@ -1148,10 +1122,8 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                     } else {
                         const float sec = calc_speed_dev(Sk[k] * m3, kc[k], ke[k], Lh, kv[k], dt, P.niter);
                         hk[k] = fminf(sec * kv[k] * dt / m3, Sk[k]);
-                        if (SED && k == 0) {  // the reference calls sed_hillslope from inside the kinematic case only (:569-575)
-                            const float qlin = hk[0] * m3 / (dt * P.dxp);
-                            sed_hillslope_dev(P, SL, sed_aSo, kv[0], Sk[0], qlin, cell, type);
-                        }
+                        if (SED && k == 0)   // the reference calls sed_hillslope from inside the kinematic case only (:569-575)
+                            stg_h = make_float4(kv[0], Sk[0], hk[0] * m3 / (dt * P.dxp), 1.0f);
                     }
                     if (SEPR) {  // :580-592, in proportion to the tank before the outflow leaves
                         if (Sk[k] > 0.0f) {
@@ -1184,10 +1156,6 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                     P.srout4[((size_t)(b & 1) * K + tt) * NM + base] = make_float4(hs[0], hs[1], hs[2], 0.0f);
                 }
                 if (SEPF) P.flxout4[((size_t)(b & 1) * K + tt) * NM + base] = make_float4(0.f, 0.f, 0.f, 2.0f);
-                if (SED && P.st[0] == 2) {  // hillslope cell: single VolDEPo / VolERO increment (:1426-1427)
-                    vdep = vdep + SL.voldepo_add;
-                    vero = vero + SL.volero_add;
-                }
             } else {
                 S4 = S4 + (h0 + h1) + h2 * (float)(type - 2);
                 if (SEPR) {  // :623-628
@@ -1211,23 +1179,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                         P.qsepr[k2 + P.n_cont] = s3 * m3 / dt;
                     }
                 }
-                float Vsal[3] = {0.f, 0.f, 0.f};
-                if (SED) {
-                    float vd2 = 0.f;
-                    sed_channel_dev(P, SL, S4, vch, h3 * m3 / dt, __ldg(P.stream_slope + cell), sec_area, Vsal, &vd2);
-                    // VolDEPo(celda) is incremented twice in a step for a channel cell (:1427 then :1607)
-                    vdep = vdep + SL.voldepo_add;
-                    vdep = vdep + vd2;
-                    vero = vero + SL.volero_add;
-                    if (P.qsed) {
-                        if (outlet)
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) P.qsed[(((size_t)m * P.T + t) * 3 + i) * P.n_cont] = Vsal[i];
-                        if (rowq >= 0)
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) P.qsed[(((size_t)m * P.T + t) * 3 + i) * P.n_cont + rowq] = Vsal[i];
-                    }
-                }
+                if (SED) stg[(size_t)(2 * tt + 1) * NM] = make_float4(S4, vch, h3 * m3 / dt, sec_area);   // what sed_channel reads (:1537-1608)
                 if (SEPF) {  // :658-665 (the ratio uses the channel tank BEFORE the outflow is taken out)
                     F0 = F0 + h0; F1 = F1 + h1; F2 = F2 + h2;
                     if (S4 > 0.0f) {
@@ -1313,14 +1265,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                     atomicAdd(P.sl_ncelltime + (size_t)m * P.T + t, marks);
                 }
             }
-            if (SED) {
-                float4 *so = P.sedout4 + ((size_t)(b & 1) * K + tt) * 3 * NM + base;
-                so[0] = make_float4(SL.up[0], SL.up[1], SL.up[2], SL.up[3]);
-                so[NM] = make_float4(SL.up[4], SL.up[5], SL.up[6], SL.up[7]);
-                so[2 * NM] = make_float4(SL.up[8], SL.up[9], SL.up[10], SL.up[11]);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) { ero_acc[i] += (double)SL.ero_add[i]; dep_acc[i] += (double)SL.dep_add[i]; }
-            }
+            if (SED) stg[(size_t)(2 * tt) * NM] = stg_h;
             *ob_out = o;
             if (SNAP && P.sto_snap) {  // save_storage (:799-803)
                 const int sl = __ldg(P.snap_slot + t);
@@ -1365,17 +1310,6 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             if (KIN && P.st[k] == 2) P.hsp[k * NM + base] = kv[k];
         if (CHAN) P.hsp[3 * NM + base] = vch;
         if (P.retorned) P.retorned[cell] = ret_acc;
-        if (SED) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                P.sed[(0 + k) * NM + base] = SL.Vs[k];
-                P.sed[(3 + k) * NM + base] = SL.Vd[k];
-                P.sed[(6 + k) * NM + base] = SL.Vsc[k];
-                P.sed[(9 + k) * NM + base] = SL.Vdc[k];
-            }
-            P.voldepo[base] = vdep;
-            P.volero[base] = vero;
-        }
         if (SLIDES) P.sl_slid[base] = sl_slid;
         if (SEPF && CHAN) { P.flx[base] = F0; P.flx[NM + base] = F1; P.flx[2 * NM + base] = F2; }
         if (SEPR) {
@@ -1383,13 +1317,6 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             P.shs[base] = T0; P.shs[NM + base] = T1; P.shs[2 * NM + base] = T2; P.shs[3 * NM + base] = T3; P.shs[4 * NM + base] = T4;
         }
         if (SNAP && P.rc) { P.rc[cell] = rc1; P.rc[(size_t)N + cell] = rc2; }
-    }
-    if (SED && active) {  // EROt / DEPt (:1403, :1420): fp64 running totals per (cell, member), summed over the cells at the end
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            if (ero_acc[i] != 0.0) P.sedacc[(size_t)i * NM + base] += ero_acc[i];
-            if (dep_acc[i] != 0.0) P.sedacc[(size_t)(3 + i) * NM + base] += dep_acc[i];
-        }
     }
     // ---- per-step balance terms: one fp64 atomic per (warp, step) ----
     if (P.want_red) {
@@ -1425,7 +1352,7 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
 // Every CTA carries the same mix of roles: its first `cpb` warps take 32-thread tiles of the channel list, the
 // others tiles of the hillslope list, so the SMs stay balanced although a channel thread costs ~4x a hillslope one.
 template <int K, bool KIN, bool SED, bool SLIDES, bool SNAP, bool SEPF, bool SEPR, bool FLOOD>
-__global__ void __launch_bounds__(TB_THREADS, (SED || SEPR) ? TB_MIN_BLOCKS_SED : (KIN ? TB_MIN_BLOCKS_KIN : TB_MIN_BLOCKS))
+__global__ void __launch_bounds__(TB_THREADS, SEPR ? TB_MIN_BLOCKS_SED : (KIN ? TB_MIN_BLOCKS_KIN : TB_MIN_BLOCKS))
 k_shia_tb(const __grid_constant__ ShiaP P, const int w, const int clo, const int chi, const int hlo, const int hhi,
           const int cpb, const int n_ctiles, const int n_htiles) {
     __shared__ float s_acc[K * TB_THREADS];
@@ -1439,6 +1366,155 @@ k_shia_tb(const __grid_constant__ ShiaP P, const int w, const int clo, const int
         const int tile = (int)blockIdx.x * (TB_THREADS / 32 - cpb) + (wi - cpb);
         if (tile < n_htiles) tb_role<K, false, KIN, SED, SLIDES, SNAP, SEPF, SEPR, FLOOD>(P, w, hlo, hhi, tile, s_acc, s_kid, s_rain);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// sediments of a time block (sed_hillslope :1321-1428, sed_channel :1537-1608) -- the second kernel of every wave
+// ---------------------------------------------------------------------------------------------------------------------
+// The SED transport reads the hydrology (speeds, storages, discharge of the step) but never writes it, so it does not have
+// to live in the hydrology's registers: compiled into k_shia_tb it made a 128-register, 137 KB kernel that ran with a
+// quarter of the warp slots and instruction-fetch stalls (profiles/README.md, "C5: where the time goes").  k_shia_tb now
+// stages two float4 per cell-step and this kernel -- same waves, same role tiles, same time blocks -- carries the four
+// 3-fraction stores in registers for the K steps of the block.  Same arithmetic, statement by statement, as before.
+template <int K, bool CHAN>
+__device__ __forceinline__ void sed_role(const ShiaP &P, const int w, const int jlo, const int jhi, const int tile) {
+    const int N = P.N, M = P.M;
+    const long long g = (long long)tile * 32 + (threadIdx.x & 31);
+    int j, m;
+    if (M == 1) { j = jlo + (int)g; m = 0; }
+    else { j = jlo + (int)(g / M); m = (int)(g % M); }
+    bool active = j < jhi;
+    int cell = 0, b = -1;
+    uint32_t tw = 0;
+    if (active) {
+        cell = __ldg((CHAN ? P.cidx : P.hidx) + j);
+        tw = __ldg(P.tw + cell);
+        b = w - (P.Lmax - (int)(tw >> 8));
+        active = (b >= 0) && (b < P.nb);
+    }
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int t0 = b * K;
+    const int nt = active ? min(K, P.T - t0) : 0;
+    const size_t NM = (size_t)N * M;
+    const size_t base = (size_t)cell * M + m;
+    const int type = (tw >> 4) & 3, nch = tw & 15;
+    int c0 = 0, rowq = -1;
+    float aSo = 0.f, So_ch = 0.f;
+    if (active) {
+        if (nch) c0 = __ldg(P.cs + cell);
+        if (tw & TW_CTRLQ) {
+            rowq = 1 + find_row(P.ctrl_cells, P.n_ctrl, cell);
+            if (rowq >= P.n_cont) rowq = -1;
+        }
+        if (P.st[0] == 2) aSo = __ldg(P.sed_aso + cell);
+        if (CHAN) So_ch = __ldg(P.stream_slope + cell);
+    }
+    const bool outlet = active && (cell == N - 1);
+    // the hydrology kernel of this wave (staging) and the sediment kernel of the previous wave (tributaries) are complete
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!active) return;
+    SedLocal SL;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        SL.Vs[k] = P.sed[(0 + k) * NM + base];
+        SL.Vd[k] = P.sed[(3 + k) * NM + base];
+        SL.Vsc[k] = P.sed[(6 + k) * NM + base];
+        SL.Vdc[k] = P.sed[(9 + k) * NM + base];
+    }
+    float vdep = P.voldepo[base], vero = P.volero[base];
+    double ero_acc[3] = {0.0, 0.0, 0.0}, dep_acc[3] = {0.0, 0.0, 0.0};
+    const float4 *stg = P.sedstg4 + (size_t)(b & 1) * K * 2 * NM + base;
+    const float4 *so_in = P.sedout4 + (size_t)(b & 1) * K * 3 * NM + (size_t)c0 * M + m;
+    float4 *so_out = P.sedout4 + (size_t)(b & 1) * K * 3 * NM + base;
+#pragma unroll 1
+    for (int tt = 0; tt < nt; ++tt, stg += 2 * NM, so_in += 3 * NM, so_out += 3 * NM) {
+        const int t = t0 + tt;
+        const float4 sh = stg[0];
+        float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (CHAN) sc = stg[NM];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) SL.up[k] = 0.f;
+        SL.ero_add[0] = SL.ero_add[1] = SL.ero_add[2] = 0.f;
+        SL.dep_add[0] = SL.dep_add[1] = SL.dep_add[2] = 0.f;
+        SL.volero_add = SL.voldepo_add = 0.f;
+        // what the upstream cells sent this step, in ascending cell order (:1373-1377, :1401, :1418, :1601)
+        const float4 *so = so_in;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c, so += M) {
+            const float4 f0 = so[0], f1 = so[NM], f2 = so[2 * NM];
+            const float u[12] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                SL.Vs[i] = SL.Vs[i] + u[0 + i];
+                SL.Vs[i] = SL.Vs[i] + u[3 + i];
+                SL.Vs[i] = SL.Vs[i] + u[6 + i];
+                SL.Vsc[i] = SL.Vsc[i] + u[9 + i];
+            }
+        }
+        if (sh.w != 0.0f) sed_hillslope_dev(P, SL, aSo, sh.x, sh.y, sh.z, cell, type);
+        if (!CHAN) {
+            if (P.st[0] == 2) {  // hillslope cell: single VolDEPo / VolERO increment (:1426-1427)
+                vdep = vdep + SL.voldepo_add;
+                vero = vero + SL.volero_add;
+            }
+        } else {
+            float Vsal[3] = {0.f, 0.f, 0.f};
+            float vd2 = 0.f;
+            sed_channel_dev(P, SL, sc.x, sc.y, sc.z, So_ch, sc.w, Vsal, &vd2);
+            // VolDEPo(celda) is incremented twice in a step for a channel cell (:1427 then :1607)
+            vdep = vdep + SL.voldepo_add;
+            vdep = vdep + vd2;
+            vero = vero + SL.volero_add;
+            if (P.qsed) {
+                if (outlet)
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) P.qsed[(((size_t)m * P.T + t) * 3 + i) * P.n_cont] = Vsal[i];
+                if (rowq >= 0)
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) P.qsed[(((size_t)m * P.T + t) * 3 + i) * P.n_cont + rowq] = Vsal[i];
+            }
+        }
+        so_out[0] = make_float4(SL.up[0], SL.up[1], SL.up[2], SL.up[3]);
+        so_out[NM] = make_float4(SL.up[4], SL.up[5], SL.up[6], SL.up[7]);
+        so_out[2 * NM] = make_float4(SL.up[8], SL.up[9], SL.up[10], SL.up[11]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { ero_acc[i] += (double)SL.ero_add[i]; dep_acc[i] += (double)SL.dep_add[i]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        P.sed[(0 + k) * NM + base] = SL.Vs[k];
+        P.sed[(3 + k) * NM + base] = SL.Vd[k];
+        P.sed[(6 + k) * NM + base] = SL.Vsc[k];
+        P.sed[(9 + k) * NM + base] = SL.Vdc[k];
+    }
+    P.voldepo[base] = vdep;
+    P.volero[base] = vero;
+    // EROt / DEPt (:1403, :1420): fp64 running totals per (cell, member), summed over the cells at the end
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (ero_acc[i] != 0.0) P.sedacc[(size_t)i * NM + base] += ero_acc[i];
+        if (dep_acc[i] != 0.0) P.sedacc[(size_t)(3 + i) * NM + base] += dep_acc[i];
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(TB_THREADS, SED_MIN_BLOCKS)
+k_sed_tb(const __grid_constant__ ShiaP P, const int w, const int clo, const int chi, const int hlo, const int hhi,
+         const int cpb, const int n_ctiles, const int n_htiles) {
+    const int wi = threadIdx.x >> 5;
+    if (wi < cpb) {
+        const int tile = (int)blockIdx.x * cpb + wi;
+        if (tile < n_ctiles) sed_role<K, true>(P, w, clo, chi, tile);
+    } else {
+        const int tile = (int)blockIdx.x * (TB_THREADS / 32 - cpb) + (wi - cpb);
+        if (tile < n_htiles) sed_role<K, false>(P, w, hlo, hhi, tile);
+    }
+}
+
+// sed_factor * So**1.664 (:1339) per cell, once per run
+__global__ void k_sed_aso(const float *__restrict__ hill_slope, float sed_factor, int n, float *__restrict__ aso) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) aso[i] = sed_factor * wmf_powf_dd(hill_slope[i], 1.664f);
 }
 
 // role lists: is_h[i] = 1 for hillslope cells; hpos = exclusive scan of is_h
@@ -2062,7 +2138,7 @@ static void launch_wave(wmf_ctx *ctx, const ShiaP &P, int w, int lo, int hi) {
 }
 
 template <int K, bool SED = false, bool SLIDES = false, bool SNAP = false, bool SEPF = false, bool SEPR = false, bool FLOOD = false>
-static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int hlo, int hhi, bool pdl) {
+static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int hlo, int hhi, bool pdl, bool pdl_sed = true) {
     constexpr int WPB = TB_THREADS / 32;
     const int wc = (int)(((long long)(chi - clo) * P.M + 31) / 32), wh = (int)(((long long)(hhi - hlo) * P.M + 31) / 32);
     if (wc + wh == 0) return;
@@ -2090,6 +2166,11 @@ static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int
     if (kin) cudaLaunchKernelEx(&cfg, k_shia_tb<K, true, SED, SLIDES, SNAP, SEPF, SEPR, FLOOD>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
     else cudaLaunchKernelEx(&cfg, k_shia_tb<K, false, SED, SLIDES, SNAP, SEPF, SEPR, FLOOD>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
     ctx->launches++;
+    if constexpr (SED) {  // the sediments of the same wave: same tiles, same time blocks, right behind the hydrology
+        cfg.numAttrs = pdl_sed ? 1 : 0;
+        cudaLaunchKernelEx(&cfg, k_sed_tb<K>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
+        ctx->launches++;
+    }
 }
 
 // Steps per time block of k_shia_tb; 0 = use the one-step-per-launch kernel k_shia_wave.
@@ -2581,8 +2662,17 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
         const float *d_vd0;
         WMF_TRY(sc.in(in->vd_init, (size_t)3 * N, &d_vd0));
         WMF_TRY(sc.alloc(&P.sed, 12 * NM));
-        if (KT) WMF_TRY(sc.alloc(&P.sedout4, (size_t)2 * KT * 3 * NM));
-        else WMF_TRY(sc.alloc(&P.sedout, 24 * NM));
+        if (KT) {
+            WMF_TRY(sc.alloc(&P.sedout4, (size_t)2 * KT * 3 * NM));
+            WMF_TRY(sc.alloc(&P.sedstg4, (size_t)2 * KT * 2 * NM));
+            float *aso;
+            WMF_TRY(sc.alloc(&aso, (size_t)N));
+            if (cfg->speed_type[0] == 2) {
+                if (!P.hill_slope) WMF_FAIL(ctx, WMF_ERR_ARG, "shia: sediments with a kinematic tank 2 need hill_slope");
+                LAUNCH(ctx, k_sed_aso, G, B, 0, P.hill_slope, P.sed_factor, N, aso);
+            }
+            P.sed_aso = aso;
+        } else WMF_TRY(sc.alloc(&P.sedout, 24 * NM));
         WMF_TRY(sc.alloc(&P.volero, NM));
         WMF_TRY(sc.alloc(&P.voldepo, NM));
         WMF_TRY(sc.alloc(&P.sedtot, 6));
@@ -2655,15 +2745,15 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
                 continue;
             }
             if (snap) {  // state dumps: K = 4 variants with the snapshot stores compiled in
-                if (sed && slides) launch_tb<4, true, true, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
-                else if (sed) launch_tb<4, true, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
+                if (sed && slides) launch_tb<4, true, true, true>(ctx, P, w, clo, chi, hlo, hhi, pdl, use_pdl);
+                else if (sed) launch_tb<4, true, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl, use_pdl);
                 else if (slides) launch_tb<4, false, true, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
                 else launch_tb<4, false, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
                 continue;
             }
             if (sed || slides) {
-                if (sed && slides) launch_tb<4, true, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
-                else if (sed) launch_tb<4, true, false>(ctx, P, w, clo, chi, hlo, hhi, pdl);
+                if (sed && slides) launch_tb<4, true, true>(ctx, P, w, clo, chi, hlo, hhi, pdl, use_pdl);
+                else if (sed) launch_tb<4, true, false>(ctx, P, w, clo, chi, hlo, hhi, pdl, use_pdl);
                 else launch_tb<4, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
                 continue;
             }
