@@ -1426,12 +1426,25 @@ __device__ __forceinline__ void sed_role(const ShiaP &P, const int w, const int 
     const float4 *stg = P.sedstg4 + (size_t)(b & 1) * K * 2 * NM + base;
     const float4 *so_in = P.sedout4 + (size_t)(b & 1) * K * 3 * NM + (size_t)c0 * M + m;
     float4 *so_out = P.sedout4 + (size_t)(b & 1) * K * 3 * NM + base;
+    // Everything a step reads was written before this kernel started (the staging by this wave's hydrology kernel, the
+    // tributaries' sediment by the previous wave), so the inputs of step tt + 1 -- the staged values and what the first
+    // tributary sent -- are requested while step tt computes.
+    float4 n_sh = make_float4(0.f, 0.f, 0.f, 0.f), n_sc = n_sh, n_f0 = n_sh, n_f1 = n_sh, n_f2 = n_sh;
+    if (nt > 0) {
+        n_sh = stg[0];
+        if (CHAN) n_sc = stg[NM];
+        if (nch > 0) { n_f0 = so_in[0]; n_f1 = so_in[NM]; n_f2 = so_in[2 * NM]; }
+    }
 #pragma unroll 1
     for (int tt = 0; tt < nt; ++tt, stg += 2 * NM, so_in += 3 * NM, so_out += 3 * NM) {
         const int t = t0 + tt;
-        const float4 sh = stg[0];
-        float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (CHAN) sc = stg[NM];
+        const float4 sh = n_sh, sc = n_sc;
+        float4 f0 = n_f0, f1 = n_f1, f2 = n_f2;
+        if (tt + 1 < nt) {
+            n_sh = stg[2 * NM];
+            if (CHAN) n_sc = stg[3 * NM];
+            if (nch > 0) { n_f0 = so_in[3 * NM]; n_f1 = so_in[4 * NM]; n_f2 = so_in[5 * NM]; }
+        }
 #pragma unroll
         for (int k = 0; k < 12; ++k) SL.up[k] = 0.f;
         SL.ero_add[0] = SL.ero_add[1] = SL.ero_add[2] = 0.f;
@@ -1440,8 +1453,8 @@ __device__ __forceinline__ void sed_role(const ShiaP &P, const int w, const int 
         // what the upstream cells sent this step, in ascending cell order (:1373-1377, :1401, :1418, :1601)
         const float4 *so = so_in;
 #pragma unroll 1
-        for (int c = 0; c < nch; ++c, so += M) {
-            const float4 f0 = so[0], f1 = so[NM], f2 = so[2 * NM];
+        for (int c = 0; c < nch; ++c) {
+            if (c > 0) { so += M; f0 = so[0]; f1 = so[NM]; f2 = so[2 * NM]; }
             const float u[12] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w};
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
