@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--no-sed", action="store_true", help="switch the workload's sediments off (c5)")
     ap.add_argument("--no-slides", action="store_true", help="switch the workload's landslides off (c5)")
     ap.add_argument("--linear", action="store_true", help="linear hillslope speeds speed_type=[1,1,1] (needs --no-sed)")
+    ap.add_argument("--no-gullie", action="store_true", help="landslides without the downstream marking (sl_gullienogullie = 0)")
     a = ap.parse_args()
     import torch
     import bench
@@ -54,6 +55,8 @@ def main():
         inp["sim_slides"] = 0
     if a.linear:
         inp["speed_type"] = [1, 1, 1]
+    if a.no_gullie:
+        inp["sl_gullienogullie"] = 0
     a.sed = a.sed or int(inp.get("sim_sediments", 0)) == 1
     a.slides = a.slides or int(inp.get("sim_slides", 0)) == 1
     synth.apply_to_models(m, inp)

@@ -86,6 +86,9 @@ struct ShiaP {
     int32_t *sl_marktime;   // [N][M] first step at which an upstream failure marked this cell (INT_MAX = never)
     int32_t *sl_acum;       // [N][M]
     int32_t *sl_ncelltime;  // [M][T]
+    int2 *sl_ring;          // [2][N][M] time-blocked kernel: (earliest step of this block at which a failure walk passes the cell,
+                            // number of such walks | unit type << 30), handed downstream like the water (slide_hill2gullie)
+    const int32_t *sl_len;  // [N] cells the marking walk that starts at a cell visits (:1683-1707): static
     const int32_t *drena;   // original drain ids (for the downstream marking walk)
     int drena_stride;
     // time-blocked wavefront (k_shia_tb): cell lists by role, AoS state, per-step outflow ring
@@ -951,11 +954,27 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
     // slides (:1649-1707): own failure flag and the step at which an upstream failure reached this cell.  Every mark
     // with a step of this block or earlier was made by a wave before this one, so one read per block is enough.
     int sl_slid = 0, sl_mark = INT_MAX;
+    int sl_mt_in = INT_MAX, sl_cnt_in = 0, sl_fail_t = INT_MAX;   // walks arriving from upstream in this block; own failure step
     bool sl_risky = false;
     if (SLIDES && active) {
         sl_risky = __ldg(P.sl_risk + cell) == 2.0f;
         sl_slid = P.sl_slid[base];
         sl_mark = P.sl_marktime[base];
+        // slide_hill2gullie (:1683-1707) without the walk: a failure marks every cell downstream of it while the unit type
+        // does not grow.  Marks travel with the wavefront instead: every cell hands its parent the earliest failure step of
+        // this time block among the walks that pass through it, and how many they are; the parent takes them when its own
+        // type is not larger than the sender's.  (The tributaries processed this block in the previous wave.)
+        if (P.sl_gullie == 1) {
+            const int2 *rin = P.sl_ring + (size_t)(b & 1) * NM + (size_t)c0 * M + m;
+            for (int c = 0; c < nch; ++c, rin += M) {
+                const int2 e = *rin;
+                if (type <= (int)((unsigned)e.y >> 30)) {
+                    sl_mt_in = min(sl_mt_in, e.x);
+                    sl_cnt_in += e.y & 0x3FFFFFFF;
+                }
+            }
+            sl_mark = min(sl_mark, sl_mt_in);
+        }
     }
     float rc1 = 0.f, rc2 = 0.f;           // save_rc accumulators
     if (SNAP && active && P.rc) { rc1 = P.rc[cell]; rc2 = P.rc[(size_t)N + cell]; }
@@ -1243,25 +1262,10 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
                     const float Den = gs * zs * sr * cr;
                     if (Num / Den <= P.sl_fs) fail = true;
                 }
-                if (fail) {
+                if (fail) {   // the cell itself + the cells its walk marks (a static count, k_slide_len)
                     sl_slid = 1;
-                    atomicAdd(P.sl_acum + base, 1);
-                    int marks = 1;
-                    if (P.sl_gullie == 1 && type <= 2) {  // slide_hill2gullie (:1683-1707)
-                        int local = cell, ltype = type;
-                        for (;;) {
-                            const int dd = P.drena[(size_t)local * P.drena_stride];
-                            if (dd == 0) break;
-                            const int dir = N - dd;
-                            const int dtype = (__ldg(P.tw + dir) >> 4) & 3;
-                            if (dtype > ltype) break;
-                            atomicMin(P.sl_marktime + (size_t)dir * M + m, t);
-                            atomicAdd(P.sl_acum + (size_t)dir * M + m, 1);
-                            ++marks;
-                            local = dir;
-                            ltype = dtype;
-                        }
-                    }
+                    sl_fail_t = t;
+                    const int marks = 1 + ((P.sl_gullie == 1 && type <= 2) ? __ldg(P.sl_len + cell) : 0);
                     atomicAdd(P.sl_ncelltime + (size_t)m * P.T + t, marks);
                 }
             }
@@ -1310,7 +1314,16 @@ __device__ __forceinline__ void tb_role(const ShiaP &P, const int w, const int j
             if (KIN && P.st[k] == 2) P.hsp[k * NM + base] = kv[k];
         if (CHAN) P.hsp[3 * NM + base] = vch;
         if (P.retorned) P.retorned[cell] = ret_acc;
-        if (SLIDES) P.sl_slid[base] = sl_slid;
+        if (SLIDES) {
+            const int own = (sl_fail_t != INT_MAX) ? 1 : 0;
+            P.sl_slid[base] = sl_slid;
+            if (sl_mt_in != INT_MAX) P.sl_marktime[base] = sl_mark;
+            if (sl_cnt_in + own) P.sl_acum[base] += sl_cnt_in + own;     // only this thread writes the cell's counter
+            if (P.sl_gullie == 1) {
+                const int walks = sl_cnt_in + ((own && type <= 2) ? 1 : 0);
+                P.sl_ring[(size_t)(b & 1) * NM + base] = make_int2(min(sl_mt_in, type <= 2 ? sl_fail_t : INT_MAX), walks | (type << 30));
+            }
+        }
         if (SEPF && CHAN) { P.flx[base] = F0; P.flx[NM + base] = F1; P.flx[2 * NM + base] = F2; }
         if (SEPR) {
             P.shc[base] = C0; P.shc[NM + base] = C1; P.shc[2 * NM + base] = C2; P.shc[3 * NM + base] = C3; P.shc[4 * NM + base] = C4;
@@ -1876,6 +1889,27 @@ __global__ void k_slide_final(const ShiaP P, float *__restrict__ occ, int32_t *_
     if (occ) occ[o] = (P.sl_marktime[g] != INT_MAX) ? 3.0f : (P.sl_slid[g] ? 1.0f : 0.0f);
     if (acum_out) acum_out[o] = P.sl_acum[g];
 }
+// cells the marking walk from a cell visits (slide_hill2gullie :1683-1707): downstream while the unit type does not grow
+__global__ void k_slide_len(const int32_t *__restrict__ drena, int stride, const uint32_t *__restrict__ tw, int n,
+                            int32_t *__restrict__ len) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int local = i, ltype = (__ldg(tw + i) >> 4) & 3, cnt = 0;
+    if (ltype <= 2) {
+        for (;;) {
+            const int dd = drena[(size_t)local * stride];
+            if (dd == 0) break;
+            const int dir = n - dd;
+            const int dtype = (__ldg(tw + dir) >> 4) & 3;
+            if (dtype > ltype) break;
+            ++cnt;
+            local = dir;
+            ltype = dtype;
+        }
+    }
+    len[i] = cnt;
+}
+
 __global__ void k_slide_state_init(const ShiaP P) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (long long)P.N * P.M) return;
@@ -2714,6 +2748,13 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
         if (!P.sl_ncelltime) WMF_TRY(sc.alloc(&P.sl_ncelltime, (size_t)M * T));
         CU_TRY(ctx, cudaMemsetAsync(P.sl_ncelltime, 0, sizeof(int32_t) * (size_t)M * T, ctx->stream));
         LAUNCH(ctx, k_slide_state_init, grid_for((long long)NM, B), B, 0, P);
+        if (KT && cfg->sl_gullienogullie == 1) {
+            int32_t *len;
+            WMF_TRY(sc.alloc(&len, (size_t)N));
+            WMF_TRY(sc.alloc(&P.sl_ring, 2 * NM));
+            LAUNCH(ctx, k_slide_len, G, B, 0, P.drena, stride, P.tw, N, len);
+            P.sl_len = len;
+        }
         float *d_cosr, *d_sinr, *d_tanfa;
         WMF_TRY(sc.alloc(&d_cosr, (size_t)N)); WMF_TRY(sc.alloc(&d_sinr, (size_t)N)); WMF_TRY(sc.alloc(&d_tanfa, (size_t)N));
         LAUNCH(ctx, k_slide_allocate, G, B, 0, P, d_zmin, d_zcrit, d_zmax, d_bo, d_risk, d_cosr, d_sinr, d_tanfa);
