@@ -2496,7 +2496,11 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     const bool rcdump = cfg->save_rc == 1 && out->rc_coef;
     const bool retdump = cfg->save_retorno == 1 && out->ret_snap;
     const bool snap = (cfg->save_storage == 1 && out->sto_snap) || (cfg->save_speed == 1 && out->speed_snap) || vdump || rcdump || retdump;
-    if (KT && (sed || slides || snap)) KT = (T >= 4) ? 4 : 0;  // sediment / slide / dump variants are built for K = 4 only
+    if (KT && (sed || slides || snap)) {  // sediment / slide variants are built for K = 4 and 8, dump variants for K = 4
+        const char *e = getenv("WMF_SHIA_K");
+        const bool k8 = !snap && T >= 8 && ((e && atoi(e) == 8) || (!e && M >= 4));
+        KT = k8 ? 8 : ((T >= 4) ? 4 : 0);
+    }
     if (M > 1 && (sed || slides) && KT == 0)
         WMF_FAIL(ctx, WMF_ERR_ARG, "shia: ensembles with sediments / slides run in the time-blocked kernel: n_reg >= 4 and no per-step means");
     const bool sepf = cfg->separate_fluxes == 1;
@@ -2806,6 +2810,12 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
                 continue;
             }
             if (sed || slides) {
+                if (KT == 8) {
+                    if (sed && slides) launch_tb<8, true, true>(ctx, P, w, clo, chi, hlo, hhi, pdl, use_pdl);
+                    else if (sed) launch_tb<8, true, false>(ctx, P, w, clo, chi, hlo, hhi, pdl, use_pdl);
+                    else launch_tb<8, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
+                    continue;
+                }
                 if (sed && slides) launch_tb<4, true, true>(ctx, P, w, clo, chi, hlo, hhi, pdl, use_pdl);
                 else if (sed) launch_tb<4, true, false>(ctx, P, w, clo, chi, hlo, hhi, pdl, use_pdl);
                 else launch_tb<4, false, true>(ctx, P, w, clo, chi, hlo, hhi, pdl);
