@@ -476,7 +476,8 @@ def time_single(args, env, wl, warmup, steps, e2e_steps):
     return dict(ms=ms, e2e_ms=e2e_ms, wave_ms=wave, launches=int(launches), h2d=int(h2d), d2h=int(d2h), levels=n_levels,
                 waves=n_waves, units=float(n) * T, bytes_per_unit=bpc, clocks=clocks, models=m, n_cont=n_cont,
                 kernel="k_shia_tb<4,%s,%s,%s>" % tuple(str(bool(v)).lower() for v in (
-                    any(s == 2 for s in wl["cfg"]["speed_type"]), wl["cfg"]["sediments"], wl["cfg"]["slides"])))
+                    any(s == 2 for s in wl["cfg"]["speed_type"]), wl["cfg"]["sediments"], wl["cfg"]["slides"])) + (
+                    " + k_sed_tb<4> behind every wave" if wl["cfg"]["sediments"] else ""))
 
 
 def time_ensemble(args, env, wl, warmup, steps, e2e_steps):
