@@ -40,6 +40,11 @@ struct wmf_ctx {
     bool own_stream = true;
     cudaStream_t copy_stream = nullptr;          // host->device streaming of big inputs next to the compute stream
     std::vector<cudaEvent_t> copy_events;
+    // sediment kernels next to the hydrology kernels of the following wave (shia.cu, launch_tb): second stream + event rings
+    cudaStream_t sed_stream = nullptr;
+    cudaEvent_t sed_ev_h[4] = {nullptr, nullptr, nullptr, nullptr}, sed_ev_s[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool sed_two_streams = false;   // this run
+    long long sed_seq = 0;          // waves with a sediment kernel launched so far in this run
     cudaMemPool_t pool = nullptr;
     char err[512] = {0};
     int64_t launches = 0;

@@ -45,6 +45,11 @@ int wmf_ctx_destroy(wmf_ctx *ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->sed_stream) cudaStreamDestroy(ctx->sed_stream);
+    for (int i = 0; i < 4; ++i) {
+        if (ctx->sed_ev_h[i]) cudaEventDestroy(ctx->sed_ev_h[i]);
+        if (ctx->sed_ev_s[i]) cudaEventDestroy(ctx->sed_ev_s[i]);
+    }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return WMF_OK;

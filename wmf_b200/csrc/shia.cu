@@ -2209,14 +2209,28 @@ static void launch_tb(wmf_ctx *ctx, const ShiaP &P, int w, int clo, int chi, int
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
+    // Two streams (ensembles): the sediment kernel of wave w runs next to the hydrology kernel of wave w + 1 -- one is bound
+    // by memory latency, the other by instruction issue.  The staging and sediment rings are two time blocks deep, so the
+    // hydrology of wave w + 2 waits for the sediments of wave w.
+    const bool two = SED && ctx->sed_two_streams;
+    if (two && ctx->sed_seq >= 2) cudaStreamWaitEvent(ctx->stream, ctx->sed_ev_s[(ctx->sed_seq - 2) & 3], 0);
     const bool kin = P.st[0] == 2 || P.st[1] == 2 || P.st[2] == 2;
     if (kin) cudaLaunchKernelEx(&cfg, k_shia_tb<K, true, SED, SLIDES, SNAP, SEPF, SEPR, FLOOD>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
     else cudaLaunchKernelEx(&cfg, k_shia_tb<K, false, SED, SLIDES, SNAP, SEPF, SEPR, FLOOD>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
     ctx->launches++;
     if constexpr (SED) {  // the sediments of the same wave: same tiles, same time blocks, right behind the hydrology
         cfg.numAttrs = pdl_sed ? 1 : 0;
+        if (two) {
+            const int k = (int)(ctx->sed_seq & 3);
+            cudaEventRecord(ctx->sed_ev_h[k], ctx->stream);
+            cudaStreamWaitEvent(ctx->sed_stream, ctx->sed_ev_h[k], 0);
+            cfg.stream = ctx->sed_stream;
+            cfg.numAttrs = 0;
+        }
         cudaLaunchKernelEx(&cfg, k_sed_tb<K>, P, w, clo, chi, hlo, hhi, cpb, wc, wh);
         ctx->launches++;
+        if (two) cudaEventRecord(ctx->sed_ev_s[ctx->sed_seq & 3], ctx->sed_stream);
+        ctx->sed_seq++;
     }
 }
 
@@ -2774,6 +2788,19 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     const int n_waves = (KT ? P.nb : T) + Lmax;
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     WMF_TRY(rs.schedule(ctx, h_first, Lmax, h_pos, KT ? KT : 1));
+    ctx->sed_seq = 0;
+    ctx->sed_two_streams = false;
+    if (KT && sed) {
+        const char *e = getenv("WMF_SED_STREAMS");
+        ctx->sed_two_streams = e ? atoi(e) == 2 : true;   // C5: one scenario 122 -> 106 ms, eight 8.07 -> 8.46 G cell-steps/s
+        if (ctx->sed_two_streams && !ctx->sed_stream) {
+            CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->sed_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 4; ++i) {
+                CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->sed_ev_h[i], cudaEventDisableTiming));
+                CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->sed_ev_s[i], cudaEventDisableTiming));
+            }
+        }
+    }
     if (KT) {
         const int nb = P.nb;
         bool launched_any = false, use_pdl = true;
@@ -2842,6 +2869,8 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
             else launch_wave<false, false>(ctx, P, w, lo, hi);
         }
     }
+    if (ctx->sed_two_streams && ctx->sed_seq > 0)   // the epilogue reads what the last sediment kernel wrote
+        CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->sed_ev_s[(ctx->sed_seq - 1) & 3], 0));
     CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     CU_TRY(ctx, cudaGetLastError());
     WMF_TRY(rs.wait_all(ctx));
