@@ -627,6 +627,30 @@ def test_hydroflash_floods(kin):
     close(np.float32(m.flood_rdf), ref["flood_scalars"][0], name="flood_rdf")
 
 
+def test_hydroflash_together_with_other_switches():
+    """sim_floods next to separate_fluxes and the per-step means in ONE shia_v1 call (three launch sequences behind it,
+    _models._switch_passes): every output against the oracle's single run."""
+    from conftest import basin_vectors, make_basin
+    from wmf_b200 import synth
+    bs = make_basin("G2", 110, 84, 41)
+    v = basin_vectors(bs)
+    inp = synth.make_shia_inputs(bs["basin"], v["acum"], v["lng"], v["pend"], dxp=30.0, n_reg=80, seed=41, thresholds=(20, 150),
+                                 rain_peak_mm=70.0)
+    inp.update(synth.make_flood_inputs(inp, v["elev"], v["pend"], 4, 41))
+    flags = dict(separate_fluxes=1, show_storage=1, show_mean_speed=1)
+    m, ret = run_gpu(inp, flags)
+    ref = run_oracle(inp, flags)
+    compare_core(ret, m, ref, bs["n"])
+    close(ret[2], ref["qseparated"], name="Qseparated")
+    close(m.mean_storage, ref["mean_storage64"], name="mean_storage")
+    got = np.asarray(m.flood_flood).reshape(-1)
+    assert np.count_nonzero(ref["flood_flood"] == 2) > 100
+    assert np.count_nonzero(got != ref["flood_flood"]) <= 2
+    ev = ref["flood_flood"] == 2
+    close(np.asarray(m.flood_q).reshape(-1)[ev], ref["flood_q"][ev], name="flood_q")
+    assert int(m.sim_floods) == 1 and int(m.separate_fluxes) == 1 and int(m.show_storage) == 1
+
+
 def test_scenario_ensemble_with_sediments_and_slides():
     """Storm scenarios as a member axis (BASELINE configs[4]): three scenarios = three sequences of the same rain records
     run in ONE launch sequence with sediments + landslides; each is compared with a single oracle run of that sequence."""

@@ -12,8 +12,11 @@
 // Two kernels implement it:
 //   k_shia_tb    the product path: K steps per launch per thread (state in registers for the block, parameters
 //                derived once per block, programmatic dependent launch between waves, hillslope and channel cells
-//                in different warps); template flags add sediments, slides, state dumps and flux separation.
+//                in different warps); template flags add slides (marks handed downstream through a per-block ring, no
+//                walk), state dumps, flux separation and the staging of what the sediments read.
 //                AoS state: float4 st4[cell][member] (tanks 1-4) + s5; ring float4 outb4[2][K][cell][member].
+//   k_sed_tb     the SED sediments of a time block (sed_hillslope, sed_channel): launched behind every wave of k_shia_tb
+//                on a second stream, next to the hydrology of the following wave; same tiles, same time blocks.
 //   k_shia_wave  the first generation, one step per launch, SoA state[tank][cell][member]; serves the per-step
 //                mean outputs (show_storage, show_mean_speed, mean_retorno) and cross-checks k_shia_tb in the tests.
 // Static maps are read in their f2py (K,N) layout (one aligned float4 per cell); rainfall records stay resident in HBM
