@@ -447,6 +447,44 @@ __global__ void k_pf_bd_jump(int n_nodes, const int32_t *__restrict__ nx_in, con
     dp_out[x] = v;
 }
 
+// Small boundary graphs (C1: 64 tiles): all the jump rounds in ONE CTA, __syncthreads() between rounds instead of a launch, a
+// flag read-back and a host synchronisation per round.  The result is left in (nx_a, dp_a).
+constexpr int BDS_THREADS = 1024, BDS_MAX_NODES = 1 << 16;
+__global__ void __launch_bounds__(BDS_THREADS)
+k_pf_bd_jump_small(int n_nodes, int32_t *__restrict__ nx_a, uint2 *__restrict__ dp_a, int32_t *__restrict__ nx_b,
+                   uint2 *__restrict__ dp_b, const int32_t *__restrict__ bdown) {
+    int32_t *nin = nx_a, *nout = nx_b;
+    uint2 *din = dp_a, *dout = dp_b;
+    for (int round = 0; round < 40; ++round) {
+        int more = 0;
+        for (int x = threadIdx.x; x < n_nodes; x += BDS_THREADS) {
+            if (bdown[x] < 0) continue;      // only exit cells are ever looked up
+            int n = nin[x];
+            uint2 v = din[x];
+            if (n >= 0) {
+                const int n2 = nin[n];
+                const uint2 u = din[n];
+                v.x += u.x;
+                v.y += u.y;
+                n = n2;
+                if (n2 >= 0) more = 1;
+            }
+            nout[x] = n;
+            dout[x] = v;
+        }
+        { int32_t *t = nin; nin = nout; nout = t; }
+        { uint2 *t = din; din = dout; dout = t; }
+        if (!__syncthreads_or(more)) break;  // (also orders this round's global writes before the next round's reads)
+    }
+    if (nin != nx_a) {   // an odd number of rounds: the result sits in the second buffer
+        for (int x = threadIdx.x; x < n_nodes; x += BDS_THREADS) {
+            if (bdown[x] < 0) continue;
+            nx_a[x] = nin[x];
+            dp_a[x] = din[x];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // stage E: every cell of the basin writes (depth | children << 28, raster index) at position preorder
 // ---------------------------------------------------------------------------------------------------------------------
@@ -766,7 +804,9 @@ int wmf_pathfind(wmf_ctx *ctx, Scope &sc, const int32_t *d_dir, int nc, int nr, 
     CU_TRY(ctx, cudaMemcpyAsync(&n_basin, S + lin0, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     // D
     LAUNCH(ctx, k_pf_bd_init, GN, B, 0, n_nodes, bdown, bnext, boff, eho, nxA, dpA, leaf /* reused as the age */);
-    for (int round = 0; round < 40; ++round) {
+    const bool small_graph = n_nodes <= BDS_MAX_NODES;
+    if (small_graph) LAUNCH(ctx, k_pf_bd_jump_small, 1, BDS_THREADS, 0, n_nodes, nxA, dpA, nxB, dpB, bdown);
+    for (int round = 0; round < 40 && !small_graph; ++round) {
         CU_TRY(ctx, cudaMemsetAsync(more, 0, sizeof(int), ctx->stream));
         LAUNCH(ctx, k_pf_bd_jump, GN, B, 0, n_nodes, nxA, dpA, nxB, dpB, leaf, more);
         std::swap(nxA, nxB);
