@@ -405,25 +405,27 @@ k_pf_local2(const int32_t *__restrict__ dir, int nc, int nr, int ntx, int lin0, 
 // ---------------------------------------------------------------------------------------------------------------------
 // stage D: depth and preorder of the exit cells
 // ---------------------------------------------------------------------------------------------------------------------
+// Only exit cells (a third of the perimeter slots) take part from here on: they are renumbered densely, in slot order
+// (cmap = exclusive scan of "is an exit cell"), and the jump rounds run over the dense arrays.
+__global__ void k_pf_exit_flag(int n_nodes, const int32_t *__restrict__ bdown, int32_t *__restrict__ flag) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < n_nodes) flag[x] = bdown[x] >= 0 ? 1 : 0;
+}
 __global__ void k_pf_bd_init(int n_nodes, const int32_t *__restrict__ bdown, const int32_t *__restrict__ bnext,
-                             const uint32_t *__restrict__ boff, const uint2 *__restrict__ eho, int32_t *__restrict__ nx,
-                             uint2 *__restrict__ dp, unsigned char *__restrict__ age) {
+                             const uint32_t *__restrict__ boff, const uint2 *__restrict__ eho, const int32_t *__restrict__ cmap,
+                             int32_t *__restrict__ nx, uint2 *__restrict__ dp, unsigned char *__restrict__ age) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n_nodes) return;
     const int bd = bdown[x];
-    int n = DEAD;
-    uint2 v = make_uint2(0u, 0u);
-    if (bd >= 0) {
-        n = bnext[x];
-        const uint2 e = eho[bd];
-        v = make_uint2(1u + e.x, boff[x] + e.y);  // one hop into the next tile + that cell's way to its terminal
-    }
-    nx[x] = n;
-    dp[x] = v;
-    age[x] = (bd >= 0) ? 0 : 2;
+    if (bd < 0) return;
+    const int c = cmap[x];
+    const int n = bnext[x];
+    const uint2 e = eho[bd];
+    nx[c] = n >= 0 ? cmap[n] : n;
+    dp[c] = make_uint2(1u + e.x, boff[x] + e.y);  // one hop into the next tile + that cell's way to its terminal
+    age[c] = 0;
 }
-// Only exit cells are ever looked up (by k_pf_emit and by other exit cells), so the other perimeter slots are skipped; a
-// node whose jump has ended is copied into the other buffer once more (age 1 -> 2) and then left alone.
+// A node whose jump has ended is copied into the other buffer once more (age 1 -> 2) and then left alone.
 __global__ void k_pf_bd_jump(int n_nodes, const int32_t *__restrict__ nx_in, const uint2 *__restrict__ dp_in,
                              int32_t *__restrict__ nx_out, uint2 *__restrict__ dp_out, unsigned char *__restrict__ age,
                              int *__restrict__ more) {
@@ -451,14 +453,14 @@ __global__ void k_pf_bd_jump(int n_nodes, const int32_t *__restrict__ nx_in, con
 // flag read-back and a host synchronisation per round.  The result is left in (nx_a, dp_a).
 constexpr int BDS_THREADS = 1024, BDS_MAX_NODES = 1 << 16;
 __global__ void __launch_bounds__(BDS_THREADS)
-k_pf_bd_jump_small(int n_nodes, int32_t *__restrict__ nx_a, uint2 *__restrict__ dp_a, int32_t *__restrict__ nx_b,
-                   uint2 *__restrict__ dp_b, const int32_t *__restrict__ bdown) {
+k_pf_bd_jump_small(int n_slots, const int32_t *__restrict__ cmap, const int32_t *__restrict__ flag, int32_t *__restrict__ nx_a,
+                   uint2 *__restrict__ dp_a, int32_t *__restrict__ nx_b, uint2 *__restrict__ dp_b) {
+    const int n_nodes = cmap[n_slots - 1] + flag[n_slots - 1];   // exit cells
     int32_t *nin = nx_a, *nout = nx_b;
     uint2 *din = dp_a, *dout = dp_b;
     for (int round = 0; round < 40; ++round) {
         int more = 0;
         for (int x = threadIdx.x; x < n_nodes; x += BDS_THREADS) {
-            if (bdown[x] < 0) continue;      // only exit cells are ever looked up
             int n = nin[x];
             uint2 v = din[x];
             if (n >= 0) {
@@ -478,7 +480,6 @@ k_pf_bd_jump_small(int n_nodes, int32_t *__restrict__ nx_a, uint2 *__restrict__ 
     }
     if (nin != nx_a) {   // an odd number of rounds: the result sits in the second buffer
         for (int x = threadIdx.x; x < n_nodes; x += BDS_THREADS) {
-            if (bdown[x] < 0) continue;
             nx_a[x] = nin[x];
             dp_a[x] = din[x];
         }
@@ -492,7 +493,8 @@ k_pf_bd_jump_small(int n_nodes, int32_t *__restrict__ nx_a, uint2 *__restrict__ 
 // sibling of a near ancestor), so the cells of a tile own long runs of consecutive preorder positions; written by one
 // CTA within microseconds they merge into full sectors in L2.
 __global__ void __launch_bounds__(NTHR)
-k_pf_emit(const uint2 *__restrict__ LR, int nc, int nr, int ntx, const int32_t *__restrict__ nx, const uint2 *__restrict__ dp,
+k_pf_emit(const uint2 *__restrict__ LR, int nc, int nr, int ntx, const int32_t *__restrict__ cmap, const int32_t *__restrict__ nx,
+          const uint2 *__restrict__ dp,
           uint32_t n_basin, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, unsigned *__restrict__ stat /* [0] max depth, [1] errors */) {
     const int tile = blockIdx.x, tid = threadIdx.x;
     const int r0 = (tile / ntx) * TS, c0 = (tile % ntx) * TS;
@@ -511,7 +513,7 @@ k_pf_emit(const uint2 *__restrict__ LR, int nc, int nr, int ntx, const int32_t *
         nxv[k] = DEAD;
         dpv[k] = make_uint2(0u, 0u);
         if (tc < T_ROOT_OUT) {
-            const int node = tile * NSLOT + (int)tc;
+            const int node = __ldg(cmap + tile * NSLOT + (int)tc);
             nxv[k] = __ldg(nx + node);
             dpv[k] = __ldg(dp + node);
         }
@@ -546,7 +548,7 @@ k_pf_emit(const uint2 *__restrict__ LR, int nc, int nr, int ntx, const int32_t *
 // The reference's search treats the outlet like any other cell: if the cell the outlet itself drains to belongs to the
 // basin, the outlet is found again as a tributary and the queue never ends (cuencas.f90:552-589).  stat[2] = 1 then.
 __global__ void k_pf_outlet_check(const int32_t *__restrict__ dir, const uint2 *__restrict__ LR, int nc, int nr, int ntx, int lin0,
-                                  const int32_t *__restrict__ nx, unsigned *__restrict__ stat) {
+                                  const int32_t *__restrict__ cmap, const int32_t *__restrict__ nx, unsigned *__restrict__ stat) {
     const int d = dir[lin0];
     if (d < 1 || d > 9 || d == 5) return;
     int dc, dr;
@@ -557,7 +559,7 @@ __global__ void k_pf_outlet_check(const int32_t *__restrict__ dir, const uint2 *
     const unsigned tc = lr.x & 0xFFFFu;
     bool in_basin = false;
     if (tc == T_ROOT_OUT) in_basin = true;
-    else if (tc != T_DEAD) in_basin = nx[((gr >> 6) * ntx + (gc >> 6)) * NSLOT + (int)tc] == ROOT_OUT;
+    else if (tc != T_DEAD) in_basin = nx[cmap[((gr >> 6) * ntx + (gc >> 6)) * NSLOT + (int)tc]] == ROOT_OUT;
     if (in_basin) stat[2] = 1u;
 }
 
@@ -753,6 +755,16 @@ __global__ void k_pf_acum_cached(const int32_t *__restrict__ basin_f, const int3
     acum[i] = q_acum[p];
 }
 
+// debug dumps only: the dense (nx, dp) back on the perimeter slots
+__global__ void k_pf_expand(int n_nodes, const int32_t *__restrict__ bdown, const int32_t *__restrict__ cmap, const int32_t *__restrict__ nx,
+                            const uint2 *__restrict__ dp, int32_t *__restrict__ nx_full, uint2 *__restrict__ dp_full) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_nodes) return;
+    const bool e = bdown[x] >= 0;
+    nx_full[x] = e ? nx[cmap[x]] : DEAD;
+    dp_full[x] = e ? dp[cmap[x]] : make_uint2(0u, 0u);
+}
+
 static void dump(wmf_ctx *ctx, const char *dir, const char *name, const void *dev, size_t bytes) {
     if (!dir) return;
     std::vector<char> h(bytes);
@@ -803,12 +815,18 @@ int wmf_pathfind(wmf_ctx *ctx, Scope &sc, const int32_t *d_dir, int nc, int nr, 
     uint32_t n_basin = 0;
     CU_TRY(ctx, cudaMemcpyAsync(&n_basin, S + lin0, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     // D
-    LAUNCH(ctx, k_pf_bd_init, GN, B, 0, n_nodes, bdown, bnext, boff, eho, nxA, dpA, leaf /* reused as the age */);
     const bool small_graph = n_nodes <= BDS_MAX_NODES;
-    if (small_graph) LAUNCH(ctx, k_pf_bd_jump_small, 1, BDS_THREADS, 0, n_nodes, nxA, dpA, nxB, dpB, bdown);
+    int32_t *flag, *cmap;
+    WMF_TRY(sc.alloc(&flag, (size_t)n_nodes)); WMF_TRY(sc.alloc(&cmap, (size_t)n_nodes));
+    LAUNCH(ctx, k_pf_exit_flag, GN, B, 0, n_nodes, bdown, flag);
+    int64_t n_exit = n_nodes;   // (small graphs read the count on the device: no host round trip)
+    WMF_TRY(wmf_device_exclusive_scan_i32(ctx, sc, flag, cmap, n_nodes, small_graph ? nullptr : &n_exit));
+    LAUNCH(ctx, k_pf_bd_init, GN, B, 0, n_nodes, bdown, bnext, boff, eho, cmap, nxA, dpA, leaf /* reused as the age */);
+    if (small_graph) LAUNCH(ctx, k_pf_bd_jump_small, 1, BDS_THREADS, 0, n_nodes, cmap, flag, nxA, dpA, nxB, dpB);
+    const int GE = grid_for(std::max<int64_t>(n_exit, 1), B);
     for (int round = 0; round < 40 && !small_graph; ++round) {
         CU_TRY(ctx, cudaMemsetAsync(more, 0, sizeof(int), ctx->stream));
-        LAUNCH(ctx, k_pf_bd_jump, GN, B, 0, n_nodes, nxA, dpA, nxB, dpB, leaf, more);
+        LAUNCH(ctx, k_pf_bd_jump, GE, B, 0, (int)n_exit, nxA, dpA, nxB, dpB, leaf, more);
         std::swap(nxA, nxB);
         std::swap(dpA, dpB);
         int h_more = 0;
@@ -822,8 +840,9 @@ int wmf_pathfind(wmf_ctx *ctx, Scope &sc, const int32_t *d_dir, int nc, int nr, 
         dump(ctx, dumpdir, "pterm", pterm, 4 * (size_t)n_nodes); dump(ctx, dumpdir, "bdown", bdown, 4 * (size_t)n_nodes);
         dump(ctx, dumpdir, "lsize", lsize, 4 * (size_t)n_nodes); dump(ctx, dumpdir, "bnext", bnext, 4 * (size_t)n_nodes);
         dump(ctx, dumpdir, "w", w, 8 * (size_t)n_nodes); dump(ctx, dumpdir, "boff", boff, 4 * (size_t)n_nodes);
-        dump(ctx, dumpdir, "eho", eho, 8 * (size_t)n_nodes); dump(ctx, dumpdir, "nx", nxA, 4 * (size_t)n_nodes);
-        dump(ctx, dumpdir, "dp", dpA, 8 * (size_t)n_nodes); dump(ctx, dumpdir, "S", S, 4 * cells); dump(ctx, dumpdir, "LR", LR, 8 * cells);
+        LAUNCH(ctx, k_pf_expand, GN, B, 0, n_nodes, bdown, cmap, nxA, dpA, nxB, dpB);
+        dump(ctx, dumpdir, "eho", eho, 8 * (size_t)n_nodes); dump(ctx, dumpdir, "nx", nxB, 4 * (size_t)n_nodes);
+        dump(ctx, dumpdir, "dp", dpB, 8 * (size_t)n_nodes); dump(ctx, dumpdir, "S", S, 4 * cells); dump(ctx, dumpdir, "LR", LR, 8 * cells);
     }
     // E
     const uint32_t n = n_basin;
@@ -831,8 +850,8 @@ int wmf_pathfind(wmf_ctx *ctx, Scope &sc, const int32_t *d_dir, int nc, int nr, 
     WMF_TRY(sc.alloc(&k0, (size_t)n)); WMF_TRY(sc.alloc(&k1, (size_t)n));
     WMF_TRY(sc.alloc(&v0, (size_t)n)); WMF_TRY(sc.alloc(&v1, (size_t)n));
     CU_TRY(ctx, cudaMemsetAsync(k0, 0xff, sizeof(uint32_t) * (size_t)n, ctx->stream));  // a slot nobody writes shows up as depth 2^28-1
-    LAUNCH(ctx, k_pf_emit, ntiles, NTHR, 0, LR, nc, nr, ntx, nxA, dpA, n, k0, v0, stat);
-    LAUNCH(ctx, k_pf_outlet_check, 1, 1, 0, d_dir, LR, nc, nr, ntx, lin0, nxA, stat);
+    LAUNCH(ctx, k_pf_emit, ntiles, NTHR, 0, LR, nc, nr, ntx, cmap, nxA, dpA, n, k0, v0, stat);
+    LAUNCH(ctx, k_pf_outlet_check, 1, 1, 0, d_dir, LR, nc, nr, ntx, lin0, cmap, nxA, stat);
     unsigned h_stat[4] = {0, 0, 0, 0};
     CU_TRY(ctx, cudaMemcpyAsync(h_stat, stat, sizeof h_stat, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
