@@ -492,32 +492,29 @@ k_pf_bd_jump_small(int n_slots, const int32_t *__restrict__ cmap, const int32_t 
 // One CTA per tile: the DFS preorder is spatially local (the next cell in preorder is the first tributary, or the next
 // sibling of a near ancestor), so the cells of a tile own long runs of consecutive preorder positions; written by one
 // CTA within microseconds they merge into full sectors in L2.
-__global__ void __launch_bounds__(NTHR)
-k_pf_emit(const uint2 *__restrict__ LR, int nc, int nr, int ntx, const int32_t *__restrict__ cmap, const int32_t *__restrict__ nx,
-          const uint2 *__restrict__ dp,
+__global__ void __launch_bounds__(NTHR, 3)
+k_pf_emit(const uint2 *__restrict__ LR, int nc, int nr, int ntx, const int32_t *__restrict__ cmap, int n_exit,
+          const int32_t *__restrict__ nx, const uint2 *__restrict__ dp,
           uint32_t n_basin, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, unsigned *__restrict__ stat /* [0] max depth, [1] errors */) {
+    // depth / preorder of the tile's (at most 252) exit cells, once per tile instead of three dependent gathers per cell
+    __shared__ uint2 s_dp[NSLOT];
+    __shared__ int s_nx[NSLOT];
     const int tile = blockIdx.x, tid = threadIdx.x;
     const int r0 = (tile / ntx) * TS, c0 = (tile % ntx) * TS;
     unsigned m = 0;
     uint2 lr[CPT];
-    int nxv[CPT];
-    uint2 dpv[CPT];
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
         const int li = k * NTHR + tid, gr = r0 + (li >> 6), gc = c0 + (li & (TS - 1));
         lr[k] = (gc < nc && gr < nr) ? __ldg(LR + (size_t)gr * nc + gc) : make_uint2(T_DEAD, 0u);
     }
-#pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-        const unsigned tc = lr[k].x & 0xFFFFu;
-        nxv[k] = DEAD;
-        dpv[k] = make_uint2(0u, 0u);
-        if (tc < T_ROOT_OUT) {
-            const int node = __ldg(cmap + tile * NSLOT + (int)tc);
-            nxv[k] = __ldg(nx + node);
-            dpv[k] = __ldg(dp + node);
-        }
+    if (tid < NSLOT) {
+        const int node = __ldg(cmap + tile * NSLOT + tid);   // (slots that are no exit cells are never looked up)
+        const bool ok = node < n_exit;
+        s_nx[tid] = ok ? __ldg(nx + node) : DEAD;
+        s_dp[tid] = ok ? __ldg(dp + node) : make_uint2(0u, 0u);
     }
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
         const int li = k * NTHR + tid, gr = r0 + (li >> 6), gc = c0 + (li & (TS - 1));
@@ -525,9 +522,10 @@ k_pf_emit(const uint2 *__restrict__ LR, int nc, int nr, int ntx, const int32_t *
         unsigned depth = 0, pre = 0;
         bool ok = false;
         if (tc == T_ROOT_OUT) { depth = h; pre = lr[k].y; ok = true; }
-        else if (tc != T_DEAD && nxv[k] == ROOT_OUT) {
-            depth = dpv[k].x + h;
-            pre = dpv[k].y + lr[k].y;
+        else if (tc != T_DEAD && s_nx[tc] == ROOT_OUT) {
+            const uint2 v = s_dp[tc];
+            depth = v.x + h;
+            pre = v.y + lr[k].y;
             ok = true;
         }
         if (ok) {
@@ -850,7 +848,7 @@ int wmf_pathfind(wmf_ctx *ctx, Scope &sc, const int32_t *d_dir, int nc, int nr, 
     WMF_TRY(sc.alloc(&k0, (size_t)n)); WMF_TRY(sc.alloc(&k1, (size_t)n));
     WMF_TRY(sc.alloc(&v0, (size_t)n)); WMF_TRY(sc.alloc(&v1, (size_t)n));
     CU_TRY(ctx, cudaMemsetAsync(k0, 0xff, sizeof(uint32_t) * (size_t)n, ctx->stream));  // a slot nobody writes shows up as depth 2^28-1
-    LAUNCH(ctx, k_pf_emit, ntiles, NTHR, 0, LR, nc, nr, ntx, cmap, nxA, dpA, n, k0, v0, stat);
+    LAUNCH(ctx, k_pf_emit, ntiles, NTHR, 0, LR, nc, nr, ntx, cmap, (int)n_exit, nxA, dpA, n, k0, v0, stat);
     LAUNCH(ctx, k_pf_outlet_check, 1, 1, 0, d_dir, LR, nc, nr, ntx, lin0, cmap, nxA, stat);
     unsigned h_stat[4] = {0, 0, 0, 0};
     CU_TRY(ctx, cudaMemcpyAsync(h_stat, stat, sizeof h_stat, cudaMemcpyDeviceToHost, ctx->stream));
