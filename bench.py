@@ -24,6 +24,8 @@ Numbers on the JSON line
              with the GPU's inside the bench (`extra.parity_vs_cpu`)
   extra      c2: the single-basin run of BASELINE configs[1] (1 044 484 cells x 1000 steps, 144 B/cell-step roofline, its
              own e2e through models.shia_v1 with host buffers) -- N=1 only;
+             c5: BASELINE configs[4], SED sediments + landslides on the 2.09 M-cell basin: one storm, and 8 storm scenarios as
+             one launch sequence, with the reference's Fortran on a few steps -- N=1 only;
              path_a: "Mcell/s D8 flow-acc" on C1 (512 x 512) and C3 (20000 x 20000): basin_find + basin_cut + basin_acum,
              per-call ms, levels, roofline at 28 B/cell, cpu_baseline of the reference on the same raster, bit-exactness
 `--workload c2 | c5` make the single-basin run (C5: SED sediments + landslides) the headline instead.
@@ -577,6 +579,55 @@ def ensemble_parity(args, env, wl, res, workdir):
              "what": "Q at the outlet and 16 control points, every step, GPU ensemble launch vs the CPU reference"})
 
 
+def bench_c5(args, env, cu, peak):
+    """BASELINE configs[4] as a second field: SED sediments + landslides on the 2.09 M-cell 12 m basin, one storm through the
+    resident marshalling layer and 8 storm scenarios as ONE launch sequence (scenario = member axis,
+    ensemble.run_scenario_ensemble); CUDA-event time of the launches, the reference's Fortran on a few steps next to it."""
+    import torch
+    from wmf_b200 import ModelsModule, synth
+    from wmf_b200.ensemble import run_scenario_ensemble
+    ctx = env["ctx"]
+    wl = build_workload("c5", cu, 0, verbose=True)
+    inp, n, T = wl["inp"], wl["n"], wl["T"]
+    m = ModelsModule(ctx)
+    synth.apply_to_models(m, inp)
+    m.make_resident()
+    d_rain = torch.from_numpy(inp["rain"]).to(f"cuda:{env['local']}")
+    n_cont = int(np.count_nonzero(inp["control"])) + 1
+    pos = np.asarray(inp["pos_evento"], np.int32)
+    want = {"q", "stoout", "qsed", "sl_slideocurrence"}
+    calib = np.asarray(inp["calib"], np.float32)[None, :]
+    res = {"workload": describe("c5", wl["cfg"], n, T)}
+    for label, S in (("one_scenario", 1), ("eight_scenarios", 8)):
+        scen = np.stack([np.roll(pos, 11 * k) for k in range(S)]).astype(np.int32)   # the storm arriving 11 steps later each
+        best_wall, best_ev = None, None
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if S == 1:
+                m._run(calib, n_cont, 1, T, d_rain, pos, device_out=True, want=want)
+            else:
+                run_scenario_ensemble(m, inp["calib"], scen, n_cont, T, d_rain, scenarios_per_launch=S, device_out=True, want=want)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if best_wall is None or dt < best_wall:
+                best_wall, best_ev = dt, ctx.last_kernel_ms()
+        bpc = BYTES_PER_CELL_STEP + BYTES_SED + BYTES_SLIDES
+        ach = bpc * n * T * S / (best_ev / 1e3) / 1e9
+        res[label] = {"scenarios": S, "ms_per_scenario": 1e3 * best_wall / S, "value": n * T * S / best_wall, "unit": "cell-steps/s",
+                      "launch_ms": best_ev,
+                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                   "bytes_per_unit": bpc, "kernel": "k_shia_tb<K,KIN,SED,SLIDES> + k_sed_tb<K> (K = 4, 8 from 4 members on)"}}
+    with tempfile.TemporaryDirectory(prefix="wmf_cpu_") as tmpd:
+        steps = max(2, min(T, args.cpu_sample_steps // 12))
+        cpu_v, cpu_s = cpu_sample(wl, steps, tmpd)
+    res["cpu_baseline"] = {"value": cpu_v, "unit": "cell-steps/s", "cores": 1, "kind": cpu_kind(),
+                           "sample": f"first {steps} of {T} steps of one scenario ({cpu_s:.1f} s), single thread; {cpu_label()}"}
+    del d_rain, m
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -675,6 +726,8 @@ def run_ours(args):
                                      "sample": f"first {min(wl2['T'], args.cpu_sample_steps)} steps ({cpu_s:.1f} s), single thread"}}
                 del r2, wl2
                 torch.cuda.empty_cache()
+            if not args.skip_c5:
+                extra["c5"] = bench_c5(args, env, cu, peak)
             pa = {"c1": bench_path_a(cu, 512, 512, reps=5)}
             if not args.skip_c3:
                 pa["c3"] = bench_path_a(cu, 20000, 20000, reps=2, cpu=not args.skip_c3_cpu)
@@ -717,6 +770,7 @@ def main():
     ap.add_argument("--ref-sample-steps", type=int, default=100, help="steps per reference-arm iteration (per member)")
     ap.add_argument("--no-extras", action="store_true", help="skip extra.c2 and extra.path_a")
     ap.add_argument("--skip-c3", action="store_true", help="skip the 20000 x 20000 Path A raster")
+    ap.add_argument("--skip-c5", action="store_true", help="skip extra.c5 (sediments + landslides, storm scenarios)")
     ap.add_argument("--skip-c3-cpu", action="store_true", help="C3 without the CPU reference run (13 GB of host memory, ~30 s)")
     args = ap.parse_args()
     if args.impl == "reference":
