@@ -191,6 +191,32 @@ def test_slides(gullie):
         np.testing.assert_array_equal(m.sl_slidencelltime, ref["sl_slidencelltime"])
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_slide_marks_with_scrambled_unit_types(seed):
+    """slide_hill2gullie (modelosv2.f90:1683-1707) marks downstream "while the unit type does not grow".  wmf.py derives the
+    types from the accumulated area, so they never decrease downstream; here a fifth of them is re-drawn at random (hillslope
+    cells below channel cells, gullies below rivers), which exercises every branch of the rule the wavefront ring implements:
+    the landslide maps, counters and per-step cell counts must still be the oracle's."""
+    bs, inp = build("G2", 100, 84, 30 + seed, n_reg=90, slides=True, retorno_gr=1, rain_peak_mm=70.0)
+    rng = np.random.default_rng(seed)
+    ut = np.array(inp["unit_type"], copy=True)
+    pick = rng.random(ut.shape[1]) < 0.2
+    pick[-1] = False                                           # the outlet stays a channel cell
+    ut[0, pick] = rng.integers(1, 4, int(pick.sum()))
+    inp["unit_type"] = ut
+    inp["sl_gullienogullie"] = 1
+    m, ret = run_gpu(inp)
+    ref = run_oracle(inp)
+    close(ret[0], ref["q"], name="Q")
+    np.testing.assert_array_equal(m.sl_riskvector.reshape(-1), ref["sl_riskvector"])
+    assert ref["sl_slidencelltime"].sum() > 0 and (ref["sl_slideocurrence"] == 3.0).any()
+    occ_diff = (m.sl_slideocurrence.reshape(-1) != ref["sl_slideocurrence"]).sum()
+    assert occ_diff <= max(2, bs["n"] // 2000), occ_diff
+    if occ_diff == 0:
+        np.testing.assert_array_equal(m.sl_slideacumulate.reshape(-1), ref["sl_slideacumulate"])
+        np.testing.assert_array_equal(m.sl_slidencelltime, ref["sl_slidencelltime"])
+
+
 def test_sediments_and_slides_together():
     bs, inp = build("G1", 90, 120, 7, n_reg=90, speed_type=(2, 2, 1), sediments=True, slides=True)
     m, ret = run_gpu(inp)
