@@ -625,11 +625,16 @@ k_rs_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
         k[s] = valid ? __ldg(keys + idx) : 0u;
         v[s] = valid ? __ldg(vals + idx) : 0u;
     }
+    // one match per item: its rank among the warp's earlier items of the same digit (running per-warp counters), kept in a
+    // register until the digit bases are known
+    unsigned rk[RS_SUB];
 #pragma unroll
     for (int s = 0; s < RS_SUB; ++s) {
         const bool valid = base + s * 32 + lane < n;
         const int d = valid ? (int)((k[s] >> shift) & 255u) : 256 + lane;   // invalid lanes match nobody
         const unsigned m = __match_any_sync(0xffffffffu, d);
+        rk[s] = valid ? sm.wh[wid][d] + __popc(m & lt) : 0u;
+        __syncwarp();
         if (valid && (m & lt) == 0) sm.wh[wid][d] += __popc(m);   // the lowest lane of every digit group
         __syncwarp();
     }
@@ -655,15 +660,8 @@ k_rs_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
     __syncthreads();
 #pragma unroll
     for (int s = 0; s < RS_SUB; ++s) {
-        const bool valid = base + s * 32 + lane < n;
-        const int d = valid ? (int)((k[s] >> shift) & 255u) : 256 + lane;
-        const unsigned m = __match_any_sync(0xffffffffu, d);
-        unsigned pos = 0;
-        if (valid) pos = sm.wh[wid][d] + __popc(m & lt);
-        __syncwarp();
-        if (valid && (m & lt) == 0) sm.wh[wid][d] += __popc(m);
-        __syncwarp();
-        if (valid) {
+        if (base + s * 32 + lane < n) {
+            const unsigned pos = sm.wh[wid][(k[s] >> shift) & 255u] + rk[s];
             sm.k[pos] = k[s];
             sm.v[pos] = v[s];
         }
