@@ -222,7 +222,7 @@ struct Local2Smem {
     unsigned char code[EW * EW];
 };
 
-__global__ void __launch_bounds__(NTHR, 2)
+__global__ void __launch_bounds__(NTHR, 3)
 k_pf_local2(const int32_t *__restrict__ dir, int nc, int nr, int ntx, int lin0, const unsigned long long *__restrict__ w,
             uint32_t *__restrict__ S, uint2 *__restrict__ LR, uint32_t *__restrict__ boff, uint2 *__restrict__ eho) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
