@@ -222,7 +222,7 @@ struct Local2Smem {
     unsigned char code[EW * EW];
 };
 
-__global__ void __launch_bounds__(NTHR, 3)
+__global__ void __launch_bounds__(NTHR, 4)
 k_pf_local2(const int32_t *__restrict__ dir, int nc, int nr, int ntx, int lin0, const unsigned long long *__restrict__ w,
             uint32_t *__restrict__ S, uint2 *__restrict__ LR, uint32_t *__restrict__ boff, uint2 *__restrict__ eho) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -696,7 +696,7 @@ k_pf_final_sums(const uint32_t *__restrict__ keys, uint32_t n, int32_t *__restri
 // the children of queue position j occupy positions [cs(j), cs(j) + nch(j)), cs(j) = 1 + children of the positions before j.
 // A warp takes 512 consecutive positions, 32 at a time: loads, the size gather and the parent writes are coalesced
 // (consecutive lanes own consecutive child ranges).
-__global__ void __launch_bounds__(FN_THREADS, 4)
+__global__ void __launch_bounds__(FN_THREADS, 6)
 k_pf_final_write(const uint32_t *__restrict__ keys, const int32_t *__restrict__ q_lin, uint32_t n,
                  const int32_t *__restrict__ blk_scan, const uint32_t *__restrict__ S, int32_t *__restrict__ q_par,
                  int32_t *__restrict__ q_acum, unsigned *__restrict__ stat) {
