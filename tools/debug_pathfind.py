@@ -113,7 +113,8 @@ def main():
         dp = dp.reshape(-1, 2)
         cmp("Dn", dp[:, 0], st["Dn"], live_exit)
         cmp("Pn", dp[:, 1], st["Pn"], live_exit)
-    k0, v0 = load("keys0", np.uint32), load("vals0", np.uint32)
+    it0 = load("items0", np.uint32)                 # interleaved (key, value) pairs at position preorder
+    k0, v0 = (it0[0::2], it0[1::2]) if it0 is not None else (None, None)
     if k0 is not None and k0.size == n_o:
         # position = preorder: depth of the cell stored there, raster index
         dep = {int(l): int(dd) for dd, l in zip(_depths(qp), ql)}

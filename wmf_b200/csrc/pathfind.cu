@@ -495,7 +495,8 @@ k_pf_bd_jump_small(int n_slots, const int32_t *__restrict__ cmap, const int32_t 
 __global__ void __launch_bounds__(NTHR, 3)
 k_pf_emit(const uint2 *__restrict__ LR, int nc, int nr, int ntx, const int32_t *__restrict__ cmap, int n_exit,
           const int32_t *__restrict__ nx, const uint2 *__restrict__ dp,
-          uint32_t n_basin, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, unsigned *__restrict__ stat /* [0] max depth, [1] errors */) {
+          uint32_t n_basin, uint2 *__restrict__ items /* (depth | children << 28, raster index) at position preorder */,
+          unsigned *__restrict__ stat /* [0] max depth, [1] errors */) {
     // depth / preorder of the tile's (at most 252) exit cells, once per tile instead of three dependent gathers per cell
     __shared__ uint2 s_dp[NSLOT];
     __shared__ int s_nx[NSLOT];
@@ -530,8 +531,7 @@ k_pf_emit(const uint2 *__restrict__ LR, int nc, int nr, int ntx, const int32_t *
         }
         if (ok) {
             if (pre < n_basin && depth < (1u << 28)) {
-                keys[pre] = depth | (nch << 28);
-                vals[pre] = (uint32_t)((size_t)gr * nc + gc);
+                items[pre] = make_uint2(depth | (nch << 28), (uint32_t)((size_t)gr * nc + gc));   // one 8-byte store
                 m = max(m, depth);
             } else {
                 atomicAdd(&stat[1], 1u);
@@ -566,12 +566,30 @@ __global__ void k_pf_outlet_check(const int32_t *__restrict__ dir, const uint2 *
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 512, RS_WARPS = RS_THREADS / 32, RS_TILE = 4096, RS_PER_WARP = RS_TILE / RS_WARPS, RS_SUB = RS_PER_WARP / 32;
 
+// (IL: the first pass reads the interleaved (key, value) pairs k_pf_emit wrote)
+template <bool IL>
 __global__ void __launch_bounds__(RS_THREADS)
 k_rs_hist(const uint32_t *__restrict__ keys, uint32_t n, int shift, int nblk, int32_t *__restrict__ hist /* [256][nblk] */) {
     __shared__ unsigned h[256];
     if (threadIdx.x < 256) h[threadIdx.x] = 0;
     __syncthreads();
     const size_t base = (size_t)blockIdx.x * RS_TILE;
+    if (IL) {
+        const uint2 *items = reinterpret_cast<const uint2 *>(keys);
+        constexpr int PT = RS_TILE / RS_THREADS;
+        uint32_t kk[PT];
+#pragma unroll
+        for (int i = 0; i < PT; ++i) {
+            const size_t idx = base + (size_t)i * RS_THREADS + threadIdx.x;
+            kk[i] = idx < n ? __ldg(items + idx).x : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < PT; ++i)
+            if (base + (size_t)i * RS_THREADS + threadIdx.x < n) atomicAdd(&h[(kk[i] >> shift) & 255u], 1u);
+        __syncthreads();
+        if (threadIdx.x < 256) hist[(size_t)threadIdx.x * nblk + blockIdx.x] = (int32_t)h[threadIdx.x];
+        return;
+    }
     constexpr int V = RS_TILE / (4 * RS_THREADS);   // 128-bit loads per thread (the tile start is 16-byte aligned)
     uint4 q[V];
 #pragma unroll
@@ -607,6 +625,7 @@ struct RsSmem {
     int scan[33];
 };
 
+template <bool IL>
 __global__ void __launch_bounds__(RS_THREADS, 3)
 k_rs_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n, int shift, int nblk,
              const int32_t *__restrict__ hist_scan, uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
@@ -622,8 +641,14 @@ k_rs_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ val
     for (int s = 0; s < RS_SUB; ++s) {
         const size_t idx = base + s * 32 + lane;
         const bool valid = idx < n;
-        k[s] = valid ? __ldg(keys + idx) : 0u;
-        v[s] = valid ? __ldg(vals + idx) : 0u;
+        if (IL) {
+            const uint2 it = valid ? __ldg(reinterpret_cast<const uint2 *>(keys) + idx) : make_uint2(0u, 0u);
+            k[s] = it.x;
+            v[s] = it.y;
+        } else {
+            k[s] = valid ? __ldg(keys + idx) : 0u;
+            v[s] = valid ? __ldg(vals + idx) : 0u;
+        }
     }
     // one match per item: its rank among the warp's earlier items of the same digit (running per-warp counters), kept in a
     // register until the digit bases are known
@@ -842,11 +867,12 @@ int wmf_pathfind(wmf_ctx *ctx, Scope &sc, const int32_t *d_dir, int nc, int nr, 
     }
     // E
     const uint32_t n = n_basin;
-    uint32_t *k0, *k1, *v0, *v1;
-    WMF_TRY(sc.alloc(&k0, (size_t)n)); WMF_TRY(sc.alloc(&k1, (size_t)n));
-    WMF_TRY(sc.alloc(&v0, (size_t)n)); WMF_TRY(sc.alloc(&v1, (size_t)n));
-    CU_TRY(ctx, cudaMemsetAsync(k0, 0xff, sizeof(uint32_t) * (size_t)n, ctx->stream));  // a slot nobody writes shows up as depth 2^28-1
-    LAUNCH(ctx, k_pf_emit, ntiles, NTHR, 0, LR, nc, nr, ntx, cmap, (int)n_exit, nxA, dpA, n, k0, v0, stat);
+    uint2 *items;
+    uint32_t *k1, *v1;
+    WMF_TRY(sc.alloc(&items, (size_t)n)); WMF_TRY(sc.alloc(&k1, (size_t)n)); WMF_TRY(sc.alloc(&v1, (size_t)n));
+    uint32_t *k0 = reinterpret_cast<uint32_t *>(items), *v0 = k0 + n;   // the pairs are dead after the first pass: reused as split arrays
+    CU_TRY(ctx, cudaMemsetAsync(items, 0xff, sizeof(uint2) * (size_t)n, ctx->stream));  // a slot nobody writes shows up as depth 2^28-1
+    LAUNCH(ctx, k_pf_emit, ntiles, NTHR, 0, LR, nc, nr, ntx, cmap, (int)n_exit, nxA, dpA, n, items, stat);
     LAUNCH(ctx, k_pf_outlet_check, 1, 1, 0, d_dir, LR, nc, nr, ntx, lin0, cmap, nxA, stat);
     unsigned h_stat[4] = {0, 0, 0, 0};
     CU_TRY(ctx, cudaMemcpyAsync(h_stat, stat, sizeof h_stat, cudaMemcpyDeviceToHost, ctx->stream));
@@ -854,29 +880,29 @@ int wmf_pathfind(wmf_ctx *ctx, Scope &sc, const int32_t *d_dir, int nc, int nr, 
     if (h_stat[2]) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "basin_find: the DIR map is cyclic -- the cell the outlet drains to drains back into the outlet");
     if (h_stat[1]) WMF_FAIL(ctx, WMF_ERR_TOPOLOGY, "basin_find: %u cells fell outside the preorder range (internal error or depth >= 2^28)", h_stat[1]);
     const unsigned maxdepth = h_stat[0];
-    if (dumpdir) { dump(ctx, dumpdir, "keys0", k0, 4 * (size_t)n); dump(ctx, dumpdir, "vals0", v0, 4 * (size_t)n); }
+    if (dumpdir) dump(ctx, dumpdir, "items0", items, 8 * (size_t)n);
     // sort by depth, stable: the order inside a level stays the preorder
     int bits = 0;
     while (bits < 28 && (maxdepth >> bits) != 0) ++bits;
-    const int passes = (bits + 7) / 8;
+    const int passes = std::max(1, (bits + 7) / 8);   // (at least one: it also splits the pairs into keys and values)
     const int nblk = (int)(((size_t)n + RS_TILE - 1) / RS_TILE);
     int32_t *hist = nullptr, *hist_scan = nullptr;
-    if (passes) {
-        WMF_TRY(sc.alloc(&hist, (size_t)256 * nblk));
-        WMF_TRY(sc.alloc(&hist_scan, (size_t)256 * nblk));
-    }
+    WMF_TRY(sc.alloc(&hist, (size_t)256 * nblk));
+    WMF_TRY(sc.alloc(&hist_scan, (size_t)256 * nblk));
     uint32_t *kin = k0, *vin = v0, *kout = k1, *vout = v1;
-    if (passes) CU_TRY(ctx, cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+    CU_TRY(ctx, cudaFuncSetAttribute(k_rs_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+    CU_TRY(ctx, cudaFuncSetAttribute(k_rs_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
     for (int p = 0; p < passes; ++p) {
         uint32_t *vdst = (p == passes - 1) ? reinterpret_cast<uint32_t *>(ctx->q_lin) : vout;
-        LAUNCH(ctx, k_rs_hist, nblk, RS_THREADS, 0, kin, n, 8 * p, nblk, hist);
+        if (p == 0) LAUNCH(ctx, k_rs_hist<true>, nblk, RS_THREADS, 0, kin, n, 8 * p, nblk, hist);
+        else LAUNCH(ctx, k_rs_hist<false>, nblk, RS_THREADS, 0, kin, n, 8 * p, nblk, hist);
         WMF_TRY(wmf_device_exclusive_scan_i32(ctx, sc, hist, hist_scan, (int64_t)256 * nblk, nullptr));
-        LAUNCH(ctx, k_rs_scatter, nblk, RS_THREADS, sizeof(RsSmem), kin, vin, n, 8 * p, nblk, hist_scan, kout, vdst);
+        if (p == 0) LAUNCH(ctx, k_rs_scatter<true>, nblk, RS_THREADS, sizeof(RsSmem), kin, vin, n, 8 * p, nblk, hist_scan, kout, vdst);
+        else LAUNCH(ctx, k_rs_scatter<false>, nblk, RS_THREADS, sizeof(RsSmem), kin, vin, n, 8 * p, nblk, hist_scan, kout, vdst);
         std::swap(kin, kout);
         vin = vdst;
         vout = (vdst == v1) ? v0 : v1;
     }
-    if (!passes) CU_TRY(ctx, cudaMemcpyAsync(ctx->q_lin, v0, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
     // F
     const int fblk = (int)(((size_t)n + FN_TILE - 1) / FN_TILE);
     int32_t *blk_sum, *blk_scan;
