@@ -871,7 +871,9 @@ int wmf_pathfind(wmf_ctx *ctx, Scope &sc, const int32_t *d_dir, int nc, int nr, 
     uint32_t *k1, *v1;
     WMF_TRY(sc.alloc(&items, (size_t)n)); WMF_TRY(sc.alloc(&k1, (size_t)n)); WMF_TRY(sc.alloc(&v1, (size_t)n));
     uint32_t *k0 = reinterpret_cast<uint32_t *>(items), *v0 = k0 + n;   // the pairs are dead after the first pass: reused as split arrays
-    CU_TRY(ctx, cudaMemsetAsync(items, 0xff, sizeof(uint2) * (size_t)n, ctx->stream));  // a slot nobody writes shows up as depth 2^28-1
+    // a slot nobody writes shows up as depth 2^28-1.  (Dropping this fill for a written-count check was measured: basin_find gets
+    // SLOWER, 25.5 -> 26.2 ms at C3 -- the scattered 8-byte writes of k_pf_emit are cheaper on lines the fill has just touched.)
+    CU_TRY(ctx, cudaMemsetAsync(items, 0xff, sizeof(uint2) * (size_t)n, ctx->stream));
     LAUNCH(ctx, k_pf_emit, ntiles, NTHR, 0, LR, nc, nr, ntx, cmap, (int)n_exit, nxA, dpA, n, items, stat);
     LAUNCH(ctx, k_pf_outlet_check, 1, 1, 0, d_dir, LR, nc, nr, ntx, lin0, cmap, nxA, stat);
     unsigned h_stat[4] = {0, 0, 0, 0};
