@@ -57,6 +57,7 @@ struct wmf_ctx {
     bool q_acum_valid = false;
     int64_t q_cap = 0;
     int32_t find_n = 0, find_nc = 0, find_nr = 0, find_depth = 0;
+    bool find_outside = false;   // the last basin_find's outlet lay outside the map (one-cell pseudo basin, cuencas.f90:547)
     // basin_subbasin_nod state (the reference's module global sub_basins_temp(2,n_nodos), returned by basin_subbasin_cut)
     int32_t *sub_basins = nullptr;
     int32_t sub_n = 0;

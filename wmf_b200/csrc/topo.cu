@@ -854,6 +854,7 @@ int wmf_basin_find(wmf_ctx *ctx, float x, float y, const int32_t *dir, int32_t n
         ctx->q_cap = celTot;
     }
     ctx->q_acum_valid = false;
+    ctx->find_outside = (coli <= 0 || fili <= 0);
     if (coli <= 0 || fili <= 0) {
         // outlet outside the map: the Fortran returns a one-cell "basin" holding (-999 | col, -999 | fil)
         ctx->find_n = 1;
@@ -936,10 +937,7 @@ int wmf_basin_cut(wmf_ctx *ctx, int32_t nceldas, int32_t *basin_f) {
     Scope sc(ctx);
     int32_t *d_out;
     WMF_TRY(sc.out(basin_f, (size_t)3 * nceldas, &d_out));
-    int32_t lin0 = 0;
-    CU_TRY(ctx, cudaMemcpyAsync(&lin0, ctx->q_lin, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (lin0 < 0) {  // degenerate outlet outside the map
+    if (ctx->find_outside) {  // degenerate outlet outside the map
         const int32_t v[3] = {0, (int32_t)ctx->scalars[3], (int32_t)ctx->scalars[4]};
         CU_TRY(ctx, cudaMemcpyAsync(d_out, v, sizeof v, cudaMemcpyHostToDevice, ctx->stream));
         CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
