@@ -103,11 +103,13 @@ class ClockSampler:
         self.index, self.rows, self.proc, self.th = index, [], None, None
 
     def start(self):
+        if os.environ.get("BENCH_CLOCKS_MS") == "0":          # (A/B of the sampler's own cost; the bench line then says so)
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,clocks_throttle_reasons.hw_slowdown,"
                  "clocks_throttle_reasons.hw_thermal_slowdown,clocks_throttle_reasons.sw_thermal_slowdown,"
-                 "clocks_throttle_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                 "clocks_throttle_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_CLOCKS_MS", "200")],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
