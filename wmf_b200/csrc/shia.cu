@@ -2793,6 +2793,13 @@ int wmf_shia_run(wmf_ctx *ctx, const wmf_shia_cfg *cfg, const wmf_shia_inputs *i
     WMF_TRY(rs.schedule(ctx, h_first, Lmax, h_pos, KT ? KT : 1));
     ctx->sed_seq = 0;
     ctx->sed_two_streams = false;
+    // whatever way this call ends, the compute stream waits for the sediment stream before the scope's buffers are released
+    struct SedJoin {
+        wmf_ctx *c;
+        ~SedJoin() {
+            if (c->sed_two_streams && c->sed_seq > 0) cudaStreamWaitEvent(c->stream, c->sed_ev_s[(c->sed_seq - 1) & 3], 0);
+        }
+    } sed_join{ctx};
     if (KT && sed) {
         const char *e = getenv("WMF_SED_STREAMS");
         ctx->sed_two_streams = e ? atoi(e) == 2 : true;   // C5: one scenario 122 -> 106 ms, eight 8.07 -> 8.46 G cell-steps/s
