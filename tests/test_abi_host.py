@@ -76,6 +76,43 @@ def test_unsupported_switches_fail_loudly():
         m.shia_v1("x.bin", "x.hdr", np.ones(10), 1, 1, 1)      # calib(11) required (modelosv2.f90:201)
 
 
+def test_switch_combinations_are_decomposed_into_passes(monkeypatch):
+    """Host logic of `_models._switch_passes` / `_shia_v1_passes` (no GPU): which switches get a launch sequence of their own,
+    that every pass runs with exactly the switches it owns, which return values come from which pass, and that the caller's
+    switches are restored."""
+    from wmf_b200 import ModelsModule
+    m = ModelsModule()
+    assert m._switch_passes() == []
+    m.sim_sediments, m.save_storage, m.show_storage = 1, 1, 1
+    assert m._switch_passes() == []                                  # the base group is one launch sequence
+    m.separate_fluxes = 1
+    assert m._switch_passes() == ["separate_fluxes"]
+    m.separate_rain, m.sim_floods = 1, 1
+    assert m._switch_passes() == ["separate_fluxes", "separate_rain", "sim_floods"]
+    m.sim_sediments = m.save_storage = m.show_storage = 0
+    assert m._switch_passes() == ["separate_rain", "sim_floods"]     # no base group: the first switch rides the first pass
+    m.separate_rain = m.sim_floods = 0
+    assert m._switch_passes() == []                                  # separate_fluxes alone
+    # the passes themselves, with the single-pass body replaced by a recorder
+    m.sim_slides, m.separate_rain, m.show_mean_speed = 1, 1, 1
+    seen = []
+    real = ModelsModule.shia_v1
+
+    def fake(self, *a, **k):
+        if self._switch_passes():
+            return real(self, *a, **k)
+        on = tuple(k for k in self._BASE_SWITCHES + self._SOLO_SWITCHES if int(getattr(self, k)) == 1)
+        seen.append(on)
+        return tuple(f"{i}:{'+'.join(on)}" for i in range(11))
+
+    monkeypatch.setattr(ModelsModule, "shia_v1", fake)
+    ret = m.shia_v1(None, None, np.ones(11), 1, 1, 4)
+    assert seen == [("sim_slides", "show_mean_speed"), ("separate_fluxes",), ("separate_rain",)]
+    assert ret[0] == "0:sim_slides+show_mean_speed" and ret[2] == "2:separate_fluxes" and ret[10] == "10:separate_rain"
+    assert ret[1].endswith("sim_slides+show_mean_speed") and ret[9].endswith("sim_slides+show_mean_speed")
+    assert (int(m.sim_slides), int(m.separate_fluxes), int(m.separate_rain), int(m.show_mean_speed), int(m.sim_floods)) == (1, 1, 1, 1, 0)
+
+
 def test_rain_file_formats(tmp_path):
     from wmf_b200 import ModelsModule
     from wmf_b200._models import read_int_basin, read_rain_hdr, write_rain_files
