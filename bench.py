@@ -51,6 +51,9 @@ BYTES_PER_CELL_STEP = 144.0            # one cell-step of a single run
 BYTES_PER_MEMBER_CELL_STEP = 80.0      # one member-cell-step of an ensemble (statics amortised over the members of a cell)
 BYTES_SED, BYTES_SLIDES = 120.0, 28.0  # what the sediment / landslide sub-models add per cell-step
 BYTES_PER_CELL_PATH_A = 28.0           # basin_find + basin_cut 16 B, basin_acum 12 B per basin cell
+# what the tile path really moves: sum of dram__bytes_read + dram__bytes_write over every kernel of one basin_find +
+# basin_cut + basin_acum at 8192 x 8192 (67.1 M cells), ncu, profiles/dram_path_a_8192_r2.txt
+TRAFFIC_PER_CELL_PATH_A = 160.6
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the ncu --set full captures under
 # profiles/ (cold-cache replay of one mid-run launch); None until a capture exists
 TRAFFIC = {
@@ -180,7 +183,7 @@ def build_workload(name: str, cu, rank: int = 0, verbose: bool = False):
 # ---------------------------------------------------------------------------------------------------------------------
 # Path A: "Mcell/s D8 flow-acc"
 # ---------------------------------------------------------------------------------------------------------------------
-def bench_path_a(cu, nc, nr, reps=3, cpu=True, gen="G2", seed=0):
+def bench_path_a(cu, nc, nr, reps=3, cpu=True, gen="G2", seed=0, hand=False):
     """basin_find + basin_cut + basin_acum on a ``nc x nr`` raster resident in HBM: Mcell/s, per-call ms, roofline at
     28 B/cell, and -- ``cpu`` -- the reference's CPU path on the same raster with a bit-exactness check of both tables."""
     import torch
@@ -212,8 +215,39 @@ def bench_path_a(cu, nc, nr, reps=3, cpu=True, gen="G2", seed=0):
            "mcell_per_s": n / tot / 1e6, "ms": tot * 1e3,
            "ms_find": best[0] * 1e3, "ms_cut": best[1] * 1e3, "ms_acum": best[2] * 1e3,
            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                        "bytes_per_cell": BYTES_PER_CELL_PATH_A, "peak_kind": peak_kind, "traffic": None},
+                        "bytes_per_cell": BYTES_PER_CELL_PATH_A, "peak_kind": peak_kind, "traffic": TRAFFIC_PER_CELL_PATH_A * n,
+                        "traffic_note": "160.6 B of DRAM traffic per basin cell (ncu, sum over the 13 passes of the tile path at "
+                                        "8192 x 8192, profiles/dram_path_a_8192_r2.txt) x the cells of this raster: the BFS order "
+                                        "without the level chain costs two radix passes, the preorder scatter and the tile tables"},
            "timing": "host clock around the three synchronous C-ABI calls, DIR resident in HBM, best of %d" % reps}
+    if hand:
+        # BASELINE configs[2] also names HAND: raster-wide height above the nearest drainage (geo_hand_global,
+        # cuencas.f90:2175-2219) with the network = accumulation > 1000 cells; DEM = 10 + 0.5 x Chebyshev distance to the
+        # outlet, which falls along every G2 flow path.  Informational (not part of the 28 B/cell metric); never fatal.
+        try:
+            oc, orow = synth.outlet_colrow(nc, nr)
+            rr = (torch.arange(nr, device=dev, dtype=torch.int32) - orow).abs()[:, None]
+            cc = (torch.arange(nc, device=dev, dtype=torch.int32) - oc).abs()[None, :]
+            d_dem = (10.0 + 0.5 * torch.maximum(rr, cc).float()).contiguous()
+            del rr, cc
+
+            def timed(fn):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                r = fn()
+                torch.cuda.synchronize()
+                return (time.perf_counter() - t0) * 1e3, r
+            t_v2m, acum_map = timed(lambda: cu.basin_float_var2map(b, acum.float(), nc, nr))
+            t_net, red = timed(lambda: cu.geo_acum_to_cauce(acum_map.int(), 1000))
+            del acum_map
+            t_hg, hand_g = timed(lambda: cu.geo_hand_global(d_dem, d_dir, red))
+            res["hand"] = {"ms_var2map": t_v2m, "ms_acum_to_cauce": t_net, "ms_geo_hand_global": t_hg,
+                           "network_cells": int(red.sum().item()), "hand_max_m": float(hand_g.max().item()),
+                           "gbs_16B_per_raster_cell": 16.0 * nc * nr / (t_hg / 1e3) / 1e9,
+                           "what": "acum back on the raster, network mask acum > 1000 cells, every other cell walks down DIR to the network"}
+            del d_dem, red, hand_g
+        except Exception as e:                         # keep the bench line
+            res["hand"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if cpu:
         from oracle import ref as _ref
         import oracle
@@ -732,7 +766,7 @@ def run_ours(args):
                 extra["c5"] = bench_c5(args, env, cu, peak)
             pa = {"c1": bench_path_a(cu, 512, 512, reps=5)}
             if not args.skip_c3:
-                pa["c3"] = bench_path_a(cu, 20000, 20000, reps=2, cpu=not args.skip_c3_cpu)
+                pa["c3"] = bench_path_a(cu, 20000, 20000, reps=2, cpu=not args.skip_c3_cpu, hand=True)
             extra["path_a"] = pa
         emit(line)
     if world > 1:
