@@ -231,12 +231,17 @@ def bench_path_a(cu, nc, nr, reps=3, cpu=True, gen="G2", seed=0, hand=False):
             d_dem = (10.0 + 0.5 * torch.maximum(rr, cc).float()).contiguous()
             del rr, cc
 
-            def timed(fn):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                r = fn()
-                torch.cuda.synchronize()
-                return (time.perf_counter() - t0) * 1e3, r
+            def timed(fn):                             # best of two: the first call sizes the context's memory pool
+                best_t, r = None, None
+                for _ in range(2):
+                    del r
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    r = fn()
+                    torch.cuda.synchronize()
+                    dt = (time.perf_counter() - t0) * 1e3
+                    best_t = dt if best_t is None else min(best_t, dt)
+                return best_t, r
             t_v2m, acum_map = timed(lambda: cu.basin_float_var2map(b, acum.float(), nc, nr))
             t_net, red = timed(lambda: cu.geo_acum_to_cauce(acum_map.int(), 1000))
             del acum_map

@@ -170,6 +170,34 @@ def test_hand_global(cu):
                                   o.geo_acum_to_cauce(np.maximum(acum_map, 0).astype(np.int32), 50))
 
 
+@pytest.mark.parametrize("shape", [(300, 260, 3), (150, 210, 5)])
+def test_hand_global_with_holes_vs_oracle_and_walk(cu, shape, monkeypatch):
+    """geo_hand_global (cuencas.f90:2175-2219) on a raster several tiles wide with nodata holes in DIR, invalid direction
+    codes, nodata cells in the network mask and a sparse random network: the tile pass + pointer jumping against the
+    oracle's walk, and against the one-walk-per-cell kernel it replaced (WMF_HAND_ALGO=walk), bit for bit."""
+    import oracle
+    from wmf_b200 import synth
+    nc, nr, seed = shape
+    DIR, DEM = synth.make_raster("G2", nc, nr, seed)
+    rng = np.random.default_rng(seed)
+    DIR = np.array(DIR, copy=True)
+    DIR[rng.random(DIR.shape) < 0.004] = int(synth.NODATA)
+    DIR[rng.random(DIR.shape) < 0.001] = 5
+    red = (rng.random(DIR.shape) < 0.01).astype(np.int32)
+    red[rng.random(DIR.shape) < 0.002] = int(synth.NODATA)
+    o = oracle.Cu()
+    for c in (cu, o):
+        c.ncols, c.nrows, c.xll, c.yll, c.dx, c.dy, c.dxp, c.nodata = nc, nr, 0.0, 0.0, 30.0, 30.0, 30.0, synth.NODATA
+    DIR, red = np.asfortranarray(DIR), np.asfortranarray(red)
+    want = o.geo_hand_global(DEM, DIR, red)
+    got = cu.geo_hand_global(DEM, DIR, red)
+    np.testing.assert_array_equal(got, want)
+    assert (want != synth.NODATA).sum() > 0.3 * nc * nr and (want == synth.NODATA).sum() > 100
+    for algo in ("walk", "jump_global"):
+        monkeypatch.setenv("WMF_HAND_ALGO", algo)
+        np.testing.assert_array_equal(cu.geo_hand_global(DEM, DIR, red), want)
+
+
 def test_resident_pipeline(cu):
     """Device-resident tensors: same answers, no host copies of the big arrays."""
     import torch

@@ -1,0 +1,37 @@
+#!/bin/bash
+# round 2, GPU job 44: geo_hand_global by pointer jumping: parity (bit-exact against the oracle), walk vs jump on the device,
+# timing at 4096^2 and C3
+mkdir -p gpurun_out
+( timeout 900 python -m pytest tests/test_gpu_topo.py tests/test_gpu_reference.py tests/test_golden.py tests/test_gpu_fuzz.py -x -q -p no:cacheprovider -k "not shia" ) > gpurun_out/j44_pytest.log 2>&1
+timeout 900 python - > gpurun_out/j44_hand.json 2> gpurun_out/j44_hand.err <<'PY'
+import json, os, sys
+sys.path.insert(0, ".")
+import torch
+import bench
+from wmf_b200 import Context, CuModule
+cu = CuModule(Context(0))
+for size in (4096, 20000):
+    out = {}
+    for algo in ("walk", "jump"):
+        os.environ["WMF_HAND_ALGO"] = algo
+        r = bench.bench_path_a(cu, size, size, reps=1, cpu=False, hand=True)
+        out[algo] = r["hand"]
+    print(json.dumps({"size": size, **out}), flush=True)
+# walk vs jump, element by element, on a raster with nodata holes and a sparse network
+from wmf_b200 import synth
+nc = nr = 3000
+d_dir = synth.make_dir_torch("G2", nc, nr, 3, device="cuda:0")
+g = torch.Generator(device="cuda:0"); g.manual_seed(1)
+holes = torch.rand((nr, nc), device="cuda:0", generator=g) < 0.002
+d_dir = torch.where(holes, torch.full_like(d_dir, int(synth.NODATA)), d_dir)
+dem = torch.rand((nr, nc), device="cuda:0", generator=g) * 100
+red = (torch.rand((nr, nc), device="cuda:0", generator=g) < 0.01).int()
+red = torch.where(torch.rand((nr, nc), device="cuda:0", generator=g) < 0.001, torch.full_like(red, int(synth.NODATA)), red)
+cu.ncols, cu.nrows, cu.xll, cu.yll, cu.dx, cu.dy, cu.dxp, cu.nodata = nc, nr, 0.0, 0.0, 30.0, 30.0, 30.0, synth.NODATA
+res = {}
+for algo in ("walk", "jump"):
+    os.environ["WMF_HAND_ALGO"] = algo
+    res[algo] = cu.geo_hand_global(dem, d_dir, red)
+print(json.dumps({"walk_equals_jump": bool(torch.equal(res["walk"], res["jump"])), "cells": nc * nr,
+                  "with_value": int((res["jump"] != synth.NODATA).sum().item())}), flush=True)
+PY
